@@ -1,0 +1,257 @@
+/*
+ * x264dsp_b200.h -- C ABI of the B200-native x264-dsp hot path.
+ *
+ * One shared library, libx264dsp_b200.so (CUDA, sm_100a), stands behind two headers:
+ *
+ *   x264dsp_tables.h  the reference's own function-pointer tables
+ *                     (x264_pixel_function_t, x264_dct_function_t, x264_zigzag_function_t,
+ *                     x264_mc_functions_t, x264_quant_function_t, x264_deblock_function_t) and
+ *                     their x264_*_init entry points, same layouts and signatures, so the
+ *                     reference can be linked against this library unchanged for that path;
+ *   x264dsp_b200.h    (this file) frame-batched entry points with identical per-block /
+ *                     per-macroblock semantics -- the calls that are worth a kernel launch.
+ *
+ * Conventions
+ *   - plain C, no CUDA or torch types.  `stream` arguments are a cudaStream_t passed as void*
+ *     (NULL = the context's own stream).
+ *   - *_dev functions take DEVICE pointers and only enqueue work on the stream; the *_host
+ *     functions take HOST pointers, stage through the context's pinned buffers, and return
+ *     when the results are in the caller's memory.
+ *   - return value: 0 = ok, <0 = bad argument (X264DSP_E_*), >0 = cudaError_t of the failing call.
+ *   - there is NO CPU fallback.  If no CUDA device can be opened, x264dsp_create fails and
+ *     every other entry point refuses to run.
+ *   - all arithmetic is integer; every output is bit-exact with the reference's portable C path.
+ *
+ * Each declaration cites the reference interface (file:line under the x264-dsp tree) it replaces.
+ */
+#ifndef X264DSP_B200_H
+#define X264DSP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X264DSP_E_ARG     (-1)   /* NULL / out-of-range argument */
+#define X264DSP_E_NOGPU   (-2)   /* no usable CUDA device (there is no CPU path) */
+#define X264DSP_E_NOMEM   (-3)
+
+/* block sizes: same numbering as the reference's enum (common/pixel.h:14-36) */
+enum
+{
+    X264DSP_PIXEL_16x16 = 0, X264DSP_PIXEL_16x8 = 1, X264DSP_PIXEL_8x16 = 2, X264DSP_PIXEL_8x8 = 3,
+    X264DSP_PIXEL_8x4 = 4, X264DSP_PIXEL_4x8 = 5, X264DSP_PIXEL_4x4 = 6, X264DSP_PIXEL_4x16 = 7
+};
+
+enum { X264DSP_CMP_SAD = 0, X264DSP_CMP_SSD = 1, X264DSP_CMP_SATD = 2 };
+enum { X264DSP_ME_DIA = 0, X264DSP_ME_HEX = 1 };          /* common/x264.h:117-118 */
+
+#define X264DSP_PADH 32                                   /* common/frame.h:9-10 */
+#define X264DSP_PADV 32
+#define X264DSP_LOOKAHEAD_QP 12                           /* common/common.h:46 */
+
+/* ------------------------------------------------------------------ geometry
+ * Frame layout of the reference (common/frame.c:22-57, 77-97, 126-133), reproduced exactly so
+ * that planes can be compared byte for byte including padding.
+ *
+ * One "frame slot" in HBM is a single allocation:
+ *     [ luma N | luma H | luma V | luma HV ]   4 x luma_plane_size      (frame.c:83-92)
+ *     [ chroma NV12 ]                          chroma_plane_size        (frame.c:78-80)
+ *     [ lowres N | H | V | HV ]                4 x lowres_plane_size    (frame.c:129-132)
+ * luma_origin / chroma_origin / lowres_origin are the byte offsets of sample (0,0) inside a plane.
+ */
+typedef struct x264dsp_geom
+{
+    int32_t width, height;            /* picture size */
+    int32_t mb_w, mb_h, mb_count;     /* 16x16 macroblock grid */
+    int32_t luma_w, luma_h;           /* mb_w*16, mb_h*16 */
+    int32_t luma_stride, luma_plane_size, luma_origin;
+    int32_t chroma_stride, chroma_h, chroma_plane_size, chroma_origin;
+    int32_t lowres_w, lowres_h, lowres_stride, lowres_plane_size, lowres_origin;
+    int32_t slot_chroma_off, slot_lowres_off;
+    int64_t slot_bytes;               /* bytes of one frame slot, multiple of 256 */
+} x264dsp_geom_t;
+
+int x264dsp_geometry( int width, int height, x264dsp_geom_t *g );
+
+/* ------------------------------------------------------------------ context */
+typedef struct x264dsp_ctx x264dsp_ctx_t;
+
+/* opens CUDA device `device`, creates a stream, uploads the constant tables (cost_mv for every
+ * distinct lambda: encoder/analyse.c:243-315; flat-CQM quant/dequant tables: common/set.c:265-353) */
+int  x264dsp_create( int device, x264dsp_ctx_t **out );
+void x264dsp_destroy( x264dsp_ctx_t *ctx );
+/* the context's stream as a cudaStream_t (so a caller can record events on it) */
+void *x264dsp_stream( x264dsp_ctx_t *ctx );
+int  x264dsp_sync( x264dsp_ctx_t *ctx );
+/* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */
+int64_t x264dsp_launch_count( const x264dsp_ctx_t *ctx );
+const char *x264dsp_version( void );
+
+/* host copies of the constant tables, for callers and tests
+ * (encoder/analyse.c:98-111, 171-206, 243-315; common/set.c:265-353; common/macroblock.h:251-266) */
+int x264dsp_lambda( int qp );
+int x264dsp_cost_mv_table( int qp, uint16_t out8193[8193] );           /* index i+4096 <-> mv delta i */
+int x264dsp_quant_tables( int b_inter, int qp, uint16_t mf[16], uint16_t bias[16] );
+int x264dsp_dequant_table( int out[6][16] );
+int x264dsp_chroma_qp( int qp );
+
+/* device memory helpers so that a plain-C caller needs no CUDA headers */
+int x264dsp_dev_alloc( x264dsp_ctx_t *ctx, size_t bytes, void **dev );
+int x264dsp_dev_free( x264dsp_ctx_t *ctx, void *dev );
+int x264dsp_dev_zero( x264dsp_ctx_t *ctx, void *dev, size_t bytes, void *stream );
+int x264dsp_h2d( x264dsp_ctx_t *ctx, void *dev, const void *host, size_t bytes, void *stream );
+int x264dsp_d2h( x264dsp_ctx_t *ctx, void *host, const void *dev, size_t bytes, void *stream );
+
+/* ------------------------------------------------------------------ synthetic input
+ * Seeded synthetic YUV 4:2:0: panning blurred-noise texture, two moving gradient
+ * squares, +-2 noise, scene cut at `cut_frame` (<0: none).  Host code; writes planar I420. */
+int x264dsp_synth_frame( int width, int height, int frame_no, int cut_frame,
+                         uint8_t *y, uint8_t *u, uint8_t *v );
+
+/* ------------------------------------------------------------------ frame staging (8(f) N4)
+ * x264_frame_copy_picture for I420 input + x264_frame_expand_border_mod16
+ * (common/frame.c:198-232, 423-450): planar Y,U,V -> padded luma plane N + NV12 chroma plane.
+ * i420 holds n_frames consecutive pictures (Y then U then V, tightly packed).
+ * slots: n_frames frame slots. */
+int x264dsp_frame_load_i420_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *i420,
+                                 uint8_t *slots, int n_frames, void *stream );
+
+/* x264_frame_expand_border for every MB row (common/frame.c:386-396): replicate luma N and chroma
+ * into their 32 / 16 sample padding. */
+int x264dsp_frame_expand_border_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
+                                     int n_frames, void *stream );
+
+/* x264_frame_filter + x264_frame_expand_border_filtered over the whole frame
+ * (common/mc.c:144-167, 506-535; common/frame.c:398-413): H, V, HV half-pel planes from plane N
+ * (whose border must already be expanded), padded from the last filtered sample. */
+int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
+                              int n_frames, void *stream );
+
+/* x264_frame_init_lowres (common/mc.c:404-456 + common/frame.c:415-421): duplicates the last
+ * column/row INTO the source luma plane, builds the four half-resolution planes and pads them. */
+int x264dsp_frame_init_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
+                                   int n_frames, void *stream );
+
+/* ------------------------------------------------------------------ block costs
+ * x264_pixel_function_t::sad / ssd / satd  (common/pixel.c:44-102, 267-337) on n independent
+ * block pairs.  Block i compares  pix1 + off1[i] (stride1)  with  pix2 + off2[i] (stride2);
+ * size[i] is an X264DSP_PIXEL_* value.  off1/off2/size/out are device arrays. */
+int x264dsp_cost_batch_dev( x264dsp_ctx_t *ctx, int cmp, int n,
+                            const uint8_t *pix1, const int64_t *off1, int stride1,
+                            const uint8_t *pix2, const int64_t *off2, int stride2,
+                            const uint8_t *size, int32_t *out, void *stream );
+
+/* ------------------------------------------------------------------ lowres lookahead
+ * x264_slicetype_frame_cost / x264_slicetype_mb_cost (encoder/slicetype.c:48-322) with the
+ * reference's defaults (do_edges = 0, no B frames, lookahead QP 12, DIA + subme 2).
+ *
+ * pair p analyses frame slot b[p] against reference slot p0[p] (P frame, p1 == b).
+ * p0[p] < 0 means intra only (the reference's frame_cost(b,b,b) call).
+ * want_intra[p] != 0 also produces the intra estimate (first analysis of that frame,
+ * slicetype.c:145-180).
+ *
+ * outputs per pair:
+ *   mvs   [p][mb_count][2] int16   lowres_mvs[0][0]        (border blocks stay 0)
+ *   costs [p][mb_count]    int32   lowres_mv_costs[0][0]   (border blocks stay 0)
+ *   sums  [p][X264DSP_LA_SUMS]     see enum below
+ *   row_satds [p][2][mb_h] int32   inter / intra row sums (i_row_satds; may be NULL)
+ */
+enum
+{
+    X264DSP_LA_COST_INTER = 0,   /* i_cost_est[b-p0][0] */
+    X264DSP_LA_COST_INTRA = 1,   /* i_cost_est[0][0] (valid when want_intra) */
+    X264DSP_LA_INTRA_MBS  = 2,   /* i_intra_mbs[b-p0] */
+    X264DSP_LA_SAD_EVALS  = 3,   /* work counters: 8x8 SAD evaluations the reference would issue */
+    X264DSP_LA_SATD_EVALS = 4,   /* 8x8 SATD evaluations the reference would issue */
+    X264DSP_LA_SUMS       = 8
+};
+int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots,
+                                      int n_pairs, const int32_t *b, const int32_t *p0,
+                                      const uint8_t *want_intra,
+                                      int16_t *mvs, int32_t *costs, int32_t *sums, int32_t *row_satds,
+                                      void *stream );
+
+/* Whole lookahead pass of a clip from HOST memory: n_frames planar luma pictures (width*height
+ * bytes each; chroma is not used by the lookahead) -> per-frame results in host arrays.
+ * Frame 0 is analysed intra-only, frame i>0 against frame i-1.  This is the call bench.py times
+ * end to end (H2D of the pictures and D2H of the results inside). */
+int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames,
+                                 const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums );
+
+/* ------------------------------------------------------------------ motion search
+ * x264_me_search_ref (+ optional x264_me_refine_qpel) (encoder/me.c:129-435) on n independent
+ * blocks of one source frame against one reference frame's N/H/V/HV planes. */
+typedef struct x264dsp_me_block
+{
+    int32_t i_pixel;                       /* x264_me_t::i_pixel */
+    int32_t bx, by;                        /* luma position of the block */
+    int16_t mvp[2];                        /* x264_me_t::mvp */
+    int32_t i_mvc;                         /* number of candidates, 0..16 */
+    int16_t mvc[16][2];
+    int32_t mv_min_fpel[2], mv_max_fpel[2];   /* h->mb.mv_{min,max}_fpel */
+    int32_t mv_min_spel[2], mv_max_spel[2];   /* h->mb.mv_{min,max}_spel */
+} x264dsp_me_block_t;
+
+typedef struct x264dsp_me_result
+{
+    int16_t mv[2];                         /* quarter-pel */
+    int32_t cost;
+    int32_t cost_mv;
+} x264dsp_me_result_t;
+
+typedef struct x264dsp_me_params
+{
+    int32_t me_method;                     /* h->mb.i_me_method: X264DSP_ME_DIA / _HEX */
+    int32_t subpel_refine;                 /* h->mb.i_subpel_refine, 1..5 */
+    int32_t me_range;                      /* h->param.analyse.i_me_range */
+    int32_t qp;                            /* selects cost_mv[qp] */
+    int32_t refine_qpel;                   /* also run x264_me_refine_qpel on each result */
+} x264dsp_me_params_t;
+
+int x264dsp_me_search_batch_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                 const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                                 const x264dsp_me_params_t *params, int n,
+                                 const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                 void *stream );
+
+/* ------------------------------------------------------------------ residual
+ * The inter-macroblock branch of x264_macroblock_encode + x264_mb_encode_chroma
+ * (encoder/macroblock.c:175-305, 379-471) for every macroblock of a frame, b_dct_decimate = 1,
+ * CABAC cbp packing, one slice QP.  pred_slot holds the motion-compensated prediction
+ * (luma plane N + NV12 chroma) and is updated IN PLACE to the reconstruction, as p_fdec is.
+ *   levels [mb][24+... ] see X264DSP_RES_*   zig-zagged quantised levels (h->dct.luma4x4 / chroma_dc)
+ *   nnz    [mb][48+3] uint8                  non_zero_count per 4x4 (coding order) + luma DC + 2 chroma DC
+ *   cbp    [mb] int16                        h->mb.cbp
+ */
+#define X264DSP_RES_LEVELS_PER_MB (16*16 + 2*4 + 2*4*16)   /* luma 4x4s, chroma DC u/v, chroma 4x4s */
+#define X264DSP_RES_NNZ_PER_MB    (16 + 8 + 3)             /* luma, chroma u/v, luma DC, chroma DC u/v */
+int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
+                                int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream );
+
+/* x264_mb_mc for P_L0 16x16 macroblocks (common/macroblock.c:8-28; mc_luma common/mc.c:216-239,
+ * mc_chroma common/mc.c:290-323): builds the prediction frame from one quarter-pel MV per MB. */
+int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,
+                          const int16_t *mv, uint8_t *pred_slot, void *stream );
+
+/* ------------------------------------------------------------------ deblock
+ * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's
+ * slice-QP rule.  mb_type / partition / cbp: per-MB; bs: [mb][2][8][4] boundary strengths.
+ * Filters luma plane N and the NV12 chroma plane of `slot` in place. */
+int x264dsp_deblock_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slot,
+                               const int8_t *mb_type, const uint8_t *partition, const int16_t *cbp,
+                               const uint8_t *bs, int qp, int alpha_c0_offset, int beta_offset,
+                               void *stream );
+
+/* deblock_strength_c (common/deblock.c:297-323) for n macroblocks:
+ * nnz [n][120], ref [n][2][40], mv [n][2][40][2] -> bs [n][2][8][4] (scan8 layout). */
+int x264dsp_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const uint8_t *nnz, const int8_t *ref,
+                                  const int16_t *mv, uint8_t *bs, void *stream );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X264DSP_B200_H */

@@ -1,0 +1,460 @@
+/* Test harness around the UNMODIFIED reference (colin121/x264-dsp) C path.
+ *
+ * Compiled together with the reference sources where they lie under
+ * /root/reference into oracle/_ref/libx264ref.so (see oracle/Makefile).  It opens a
+ * real encoder instance with x264_encoder_open, so every table (pixf, dctf,
+ * quantf, mc, loopf, cost_mv, quant4_mf ...) is the one the reference itself
+ * would use, and then exposes plain C entry points that drive the hot-path
+ * functions on caller supplied data.  None of the reference's arithmetic is
+ * restated here: this file only moves bytes in and out.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Loaded by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs; never by the product library.
+ */
+#include "common/common.h"
+#include "encoder/macroblock.h"
+#include "encoder/me.h"
+#include "encoder/analyse.h"
+#include <time.h>
+
+int xref_slicetype_frame_cost( x264_t *h, x264_frame_t **frames, int p0, int p1, int b );
+
+static void xref_quiet_log( void *priv, int level, const char *fmt, va_list ap )
+{
+    (void)priv; (void)level; (void)fmt; (void)ap;
+}
+
+/* ------------------------------------------------------------------ open/close */
+
+void *xref_open( int width, int height, int me_method, int subme, int me_range, int qp, int psub16x16 )
+{
+    x264_param_t param;
+    x264_param_default( &param );
+    param.i_width = width;
+    param.i_height = height;
+    param.i_csp = X264_CSP_I420;
+    param.pf_log = xref_quiet_log;
+    param.i_log_level = X264_LOG_NONE;
+    param.analyse.i_me_method = me_method;
+    param.analyse.i_subpel_refine = subme;
+    param.analyse.i_me_range = me_range;
+    if( psub16x16 )
+        param.analyse.inter |= X264_ANALYSE_PSUB16x16;
+    param.rc.i_rc_method = X264_RC_CQP;
+    param.rc.i_qp_constant = qp;
+    /* keep lowres planes even under CQP: scenecut stays at its default (>0) */
+    return x264_encoder_open( &param );
+}
+
+void xref_close( void *hv )
+{
+    /* x264_encoder_close prints stats and frees; leaking a test encoder is harmless
+     * but closing keeps valgrind/ASan runs clean. */
+    x264_encoder_close( (x264_t *)hv );
+}
+
+/* out[0..15]: geometry the oracle's own layout code must reproduce */
+void xref_geometry( void *hv, int *out )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = h->fdec;
+    out[0] = h->mb.i_mb_width;
+    out[1] = h->mb.i_mb_height;
+    out[2] = f->i_stride[0];
+    out[3] = f->i_width[0];
+    out[4] = f->i_lines[0];
+    out[5] = f->i_stride_lowres;
+    out[6] = f->i_width_lowres;
+    out[7] = f->i_lines_lowres;
+    out[8] = (int)(f->filtered[0][1] - f->filtered[0][0]);   /* luma_plane_size */
+    out[9] = (int)(f->plane[0] - f->buffer[0]);              /* origin offset in the buffer */
+    out[10] = (int)(f->plane[1] - f->buffer[1]);
+    out[11] = f->i_stride[1];
+    out[12] = f->i_lines[1];
+    out[13] = h->param.analyse.i_me_range;
+    out[14] = h->param.analyse.i_subpel_refine;
+    out[15] = h->param.analyse.i_me_method;
+}
+
+/* ------------------------------------------------------------------ tables */
+
+void *xref_pixf( void *hv )    { return &((x264_t *)hv)->pixf; }
+void *xref_dctf( void *hv )    { return &((x264_t *)hv)->dctf; }
+void *xref_zigzagf( void *hv ) { return &((x264_t *)hv)->zigzagf; }
+void *xref_mcf( void *hv )     { return &((x264_t *)hv)->mc; }
+void *xref_quantf( void *hv )  { return &((x264_t *)hv)->quantf; }
+void *xref_loopf( void *hv )   { return &((x264_t *)hv)->loopf; }
+int xref_table_sizes( int *out )
+{
+    out[0] = sizeof(x264_pixel_function_t);
+    out[1] = sizeof(x264_dct_function_t);
+    out[2] = sizeof(x264_zigzag_function_t);
+    out[3] = sizeof(x264_mc_functions_t);
+    out[4] = sizeof(x264_quant_function_t);
+    out[5] = sizeof(x264_deblock_function_t);
+    out[6] = sizeof(x264_me_t);
+    out[7] = sizeof(x264_weight_t);
+    return 8;
+}
+
+/* centre pointer of cost_mv[qp]; valid for indices -4096..4096 */
+const uint16_t *xref_cost_mv( void *hv, int qp ) { return ((x264_t *)hv)->cost_mv[qp]; }
+int xref_lambda( int qp ) { return x264_lambda_tab[qp]; }
+int xref_chroma_qp( void *hv, int qp ) { return ((x264_t *)hv)->chroma_qp_table[qp]; }
+
+void xref_quant_tables( void *hv, int cat, int qp, uint16_t *mf, uint16_t *bias )
+{
+    x264_t *h = hv;
+    memcpy( mf, h->quant4_mf[cat][qp], 16 * sizeof(uint16_t) );
+    memcpy( bias, h->quant4_bias[cat][qp], 16 * sizeof(uint16_t) );
+}
+void xref_dequant_table( void *hv, int cat, int *out )
+{
+    x264_t *h = hv;
+    memcpy( out, h->dequant4_mf[cat], 6 * 16 * sizeof(int) );
+}
+
+/* x264_predict_8x8c_{dc,h,v}_c (common/predict.c:224-288), mode 0=DC 1=H 2=V */
+void xref_predict_8x8c( void *hv, int mode, uint8_t *src_fdec )
+{
+    x264_t *h = hv;
+    static const int map[3] = { I_PRED_CHROMA_DC, I_PRED_CHROMA_H, I_PRED_CHROMA_V };
+    h->predict_8x8c[map[mode]]( src_fdec );
+}
+
+/* ------------------------------------------------------------------ frames */
+
+void *xref_frame_new( void *hv, int b_fdec )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = x264_frame_pop_unused( h, b_fdec );
+    int i;
+    if( !f )
+        return NULL;
+    /* the reference mallocs planes without clearing them; zero them so that every
+     * byte a comparison can see (alignment gaps included) is deterministic */
+    {
+        int luma_rows = f->i_lines[0] + 2*PADV;
+        int64_t plane_size = (int64_t)f->i_stride[0] * luma_rows;
+        if( !(plane_size & 1023) ) plane_size += 128;
+        memset( f->buffer[0], 0, (f->filtered[0][1] ? 4 : 1) * plane_size );
+        memset( f->buffer[1], 0, (size_t)f->i_stride[1] * (f->i_lines[1] + PADV) );
+        if( f->buffer_lowres[0] )
+        {
+            int64_t lsize = (int64_t)f->i_stride_lowres * (f->i_lines_lowres + 2*PADV);
+            if( !(lsize & 1023) ) lsize += 128;
+            memset( f->buffer_lowres[0], 0, 4 * lsize );
+        }
+    }
+    if( !b_fdec && f->lowres_mv_costs[0][0] )
+        for( i = 0; i < h->mb.i_mb_count; i++ )
+            f->lowres_mv_costs[0][0][i] = 0;
+    return f;
+}
+
+void xref_frame_release( void *hv, void *fv )
+{
+    x264_frame_push_unused( (x264_t *)hv, (x264_frame_t *)fv );
+}
+
+/* planar I420 in, exactly as x264_encoder_encode does it (encoder.c:1745-1770 region):
+ * x264_frame_copy_picture then x264_frame_expand_border_mod16 */
+void xref_frame_load_i420( void *hv, void *fv, uint8_t *y, uint8_t *u, uint8_t *v )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = fv;
+    x264_picture_t pic;
+    x264_picture_init( &pic );
+    pic.img.i_csp = X264_CSP_I420;
+    pic.img.i_plane = 3;
+    pic.img.plane[0] = y;
+    pic.img.plane[1] = u;
+    pic.img.plane[2] = v;
+    pic.img.i_stride[0] = h->param.i_width;
+    pic.img.i_stride[1] = h->param.i_width >> 1;
+    pic.img.i_stride[2] = h->param.i_width >> 1;
+    x264_frame_copy_picture( h, f, &pic );
+    if( h->param.i_width & 15 || h->param.i_height & 15 )
+        x264_frame_expand_border_mod16( h, f );
+}
+
+void xref_frame_init_lowres( void *hv, void *fv )
+{
+    x264_frame_init_lowres( (x264_t *)hv, (x264_frame_t *)fv );
+}
+
+/* which: 0 plane[0]  1 plane[1]  2..4 filtered[0][1..3]  5..8 lowres[0..3]
+ *        10 buffer[0]  11 buffer[1]  12 buffer_lowres[0] */
+uint8_t *xref_frame_ptr( void *fv, int which )
+{
+    x264_frame_t *f = fv;
+    switch( which )
+    {
+        case 0:  return f->plane[0];
+        case 1:  return f->plane[1];
+        case 2: case 3: case 4: return f->filtered[0][which-1];
+        case 5: case 6: case 7: case 8: return f->lowres[which-5];
+        case 10: return f->buffer[0];
+        case 11: return f->buffer[1];
+        case 12: return f->buffer_lowres[0];
+    }
+    return NULL;
+}
+
+/* The in-loop filter sequence of x264_fdec_filter_row (encoder/encoder.c:1359-1385)
+ * WITHOUT deblocking, row by row over the whole frame:
+ * expand_border -> frame_filter (hpel) -> expand_border_filtered */
+void xref_frame_filter_all( void *hv, void *fv )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = fv;
+    int mb_y;
+    for( mb_y = 1; mb_y <= h->mb.i_mb_height; mb_y++ )
+    {
+        int min_y = mb_y - 1;
+        int end = mb_y == h->mb.i_mb_height;
+        x264_frame_expand_border( h, f, min_y );
+        x264_frame_filter( h, f, min_y, end );
+        x264_frame_expand_border_filtered( h, f, min_y, end );
+    }
+}
+
+/* border expansion of the unfiltered planes only (luma + NV12 chroma) */
+void xref_frame_expand_border_all( void *hv, void *fv )
+{
+    x264_t *h = hv;
+    int mb_y;
+    for( mb_y = 0; mb_y < h->mb.i_mb_height; mb_y++ )
+        x264_frame_expand_border( h, (x264_frame_t *)fv, mb_y );
+}
+
+/* ------------------------------------------------------------------ lookahead */
+
+int xref_frame_cost( void *hv, void **frames, int p0, int p1, int b )
+{
+    return xref_slicetype_frame_cost( (x264_t *)hv, (x264_frame_t **)frames, p0, p1, b );
+}
+
+/* results of frame_cost for distance d = b-p0 (P frames: p1 == b):
+ * mvs[mb_count][2], costs[mb_count], sums = { i_cost_est[d][0], i_cost_est_aq[d][0],
+ * i_cost_est[0][0], i_intra_mbs[d], b_intra_calculated } */
+void xref_frame_lowres_results( void *hv, void *fv, int d, int16_t *mvs, int *costs, int *sums )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = fv;
+    if( d > 0 )
+    {
+        memcpy( mvs, f->lowres_mvs[0][d-1], 2 * h->mb.i_mb_count * sizeof(int16_t) );
+        memcpy( costs, f->lowres_mv_costs[0][d-1], h->mb.i_mb_count * sizeof(int) );
+    }
+    sums[0] = f->i_cost_est[d][0];
+    sums[1] = f->i_cost_est_aq[d][0];
+    sums[2] = f->i_cost_est[0][0];
+    sums[3] = f->i_intra_mbs[d];
+    sums[4] = f->b_intra_calculated;
+}
+
+/* ------------------------------------------------------------------ motion search */
+
+typedef struct
+{
+    int32_t i_pixel;          /* PIXEL_16x16 .. PIXEL_4x4 */
+    int32_t bx, by;           /* luma position of the block's top-left sample */
+    int16_t mvp[2];
+    int32_t i_mvc;
+    int16_t mvc[16][2];
+    int32_t mv_min_fpel[2], mv_max_fpel[2];
+    int32_t mv_min_spel[2], mv_max_spel[2];
+} xref_me_in_t;
+
+typedef struct
+{
+    int16_t mv[2];
+    int32_t cost;
+    int32_t cost_mv;
+} xref_me_out_t;
+
+/* x264_me_search_ref (encoder/me.c:129) on a list of blocks.
+ * fenc: any frame (source samples from plane[0]); fref: an fdec frame whose
+ * filtered[0][0..3] planes have been produced by xref_frame_filter_all.
+ * refine != 0 additionally runs x264_me_refine_qpel on each result (me.c:426). */
+void xref_me_search_batch( void *hv, void *fencv, void *frefv, int qp, int me_method, int subme,
+                           int me_range, int refine, const xref_me_in_t *in, int n, xref_me_out_t *out )
+{
+    x264_t *h = hv;
+    x264_frame_t *fenc = fencv, *fref = frefv;
+    int stride = fref->i_stride[0];
+    int i, k, y;
+    int keep_range = h->param.analyse.i_me_range;
+    h->param.analyse.i_me_range = me_range;
+    h->mb.i_me_method = me_method;
+    h->mb.i_subpel_refine = subme;
+    h->mb.b_chroma_me = 0;
+    for( i = 0; i < n; i++ )
+    {
+        x264_me_t m;
+        int16_t mvc[16][2];
+        int bw = x264_pixel_size[in[i].i_pixel].w;
+        int bh = x264_pixel_size[in[i].i_pixel].h;
+        pixel *src = fenc->plane[0] + in[i].by * fenc->i_stride[0] + in[i].bx;
+        pixel *dst = h->mb.pic.fenc_buf;
+        memset( &m, 0, sizeof(m) );
+        for( y = 0; y < bh; y++ )
+            memcpy( dst + y*FENC_STRIDE, src + y*fenc->i_stride[0], bw );
+        for( k = 0; k < 2; k++ )
+        {
+            h->mb.mv_min_fpel[k] = in[i].mv_min_fpel[k];
+            h->mb.mv_max_fpel[k] = in[i].mv_max_fpel[k];
+            h->mb.mv_min_spel[k] = in[i].mv_min_spel[k];
+            h->mb.mv_max_spel[k] = in[i].mv_max_spel[k];
+        }
+        m.i_pixel = in[i].i_pixel;
+        m.p_cost_mv = h->cost_mv[qp];
+        m.i_ref_cost = 0;
+        m.i_ref = 0;
+        m.weight = x264_weight_none;
+        for( k = 0; k < 4; k++ )
+            m.p_fref[k] = fref->filtered[0][k] + in[i].by * stride + in[i].bx;
+        m.p_fref_w = m.p_fref[0];
+        m.p_fenc[0] = dst;
+        m.i_stride[0] = stride;
+        m.mvp[0] = in[i].mvp[0];
+        m.mvp[1] = in[i].mvp[1];
+        memcpy( mvc, in[i].mvc, sizeof(mvc) );
+        x264_me_search_ref( h, &m, mvc, in[i].i_mvc, NULL );
+        if( refine )
+            x264_me_refine_qpel( h, &m );
+        out[i].mv[0] = m.mv[0];
+        out[i].mv[1] = m.mv[1];
+        out[i].cost = m.cost;
+        out[i].cost_mv = m.cost_mv;
+    }
+    h->param.analyse.i_me_range = keep_range;
+}
+
+/* ------------------------------------------------------------------ deblock */
+
+/* x264_frame_deblock_row (common/deblock.c:341) over every MB row of frame f.
+ * mb_type/partition/cbp: per-MB arrays (raster); bs: [mb][2][8][4] as produced by
+ * deblock_strength / x264_macroblock_deblock_strength. */
+void xref_deblock_frame( void *hv, void *fv, const int8_t *mb_type, const uint8_t *partition,
+                         const int16_t *cbp, const uint8_t *bs, int qp, int alpha_off, int beta_off )
+{
+    x264_t *h = hv;
+    x264_frame_t *keep = h->fdec;
+    int8_t *keep_type = h->mb.type;
+    uint8_t *keep_part = h->mb.partition;
+    int mb_y, n = h->mb.i_mb_count;
+    h->fdec = fv;
+    h->mb.i_mb_stride = h->mb.i_mb_width;
+    h->mb.type = h->fdec->mb_type;
+    h->mb.partition = h->fdec->mb_partition;
+    memcpy( h->mb.type, mb_type, n );
+    memcpy( h->mb.partition, partition, n );
+    memcpy( h->mb.cbp, cbp, n * sizeof(int16_t) );
+    h->sh.i_qp = qp;
+    h->sh.i_alpha_c0_offset = alpha_off;
+    h->sh.i_beta_offset = beta_off;
+    for( mb_y = 0; mb_y < h->mb.i_mb_height; mb_y++ )
+    {
+        memcpy( h->deblock_strength[mb_y&1], bs + (size_t)mb_y * h->mb.i_mb_width * 64,
+                (size_t)h->mb.i_mb_width * 64 );
+        x264_frame_deblock_row( h, mb_y );
+    }
+    h->fdec = keep;
+    h->mb.type = keep_type;
+    h->mb.partition = keep_part;
+}
+
+/* ------------------------------------------------------------------ residual
+
+ * x264_macroblock_encode (encoder/macroblock.c:310) for one P_L0 16x16 macroblock whose
+ * prediction is already in p_fdec (b_skip_mc = 1).  Buffers use the reference's fenc_buf /
+ * fdec_buf shapes: fenc_y 16 rows @16, fenc_c 8 rows @16 (U at +0, V at +8);
+ * fdec_y 16 rows @32, fdec_c 8 rows @32 (U at +0, V at +16); fdec is prediction in, recon out.
+ * levels: luma4x4[0..15][16], chroma_dc[0..1][4], luma4x4[16..19][16], luma4x4[32..35][16].
+ * nnz: 16 luma (coding order), 4 U, 4 V, luma DC, U DC, V DC.  Returns h->mb.cbp. */
+int xref_encode_inter_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y,
+                          uint8_t *fdec_c, int qp, int16_t *levels, uint8_t *nnz )
+{
+    x264_t *h = hv;
+    int i, y;
+    h->sh.i_type = SLICE_TYPE_P;
+    x264_macroblock_thread_init( h );
+    h->mb.i_type = P_L0;
+    h->mb.i_partition = D_16x16;
+    h->mb.b_skip_mc = 1;
+    h->mb.b_noise_reduction = 0;
+    h->mb.b_transform_8x8 = 0;
+    h->nr_count = h->nr_count_buf[0];
+    h->mb.i_qp = qp;
+    h->mb.i_chroma_qp = h->chroma_qp_table[qp];
+    h->mb.i_mb_xy = 0;
+    h->mb.cache.mv[0][x264_scan8[0]][0] = 1;       /* != pskip_mv: keep the type P_L0 */
+    h->mb.cache.mv[0][x264_scan8[0]][1] = 1;
+    M32( h->mb.cache.pskip_mv ) = 0;
+    memset( &h->dct, 0, sizeof(h->dct) );
+    memset( h->mb.cache.non_zero_count, 0, sizeof(h->mb.cache.non_zero_count) );
+    for( y = 0; y < 16; y++ )
+    {
+        memcpy( h->mb.pic.p_fenc[0] + y*FENC_STRIDE, fenc_y + y*16, 16 );
+        memcpy( h->mb.pic.p_fdec[0] + y*FDEC_STRIDE, fdec_y + y*32, 16 );
+    }
+    for( y = 0; y < 8; y++ )
+    {
+        memcpy( h->mb.pic.p_fenc[1] + y*FENC_STRIDE, fenc_c + y*16, 16 );
+        memcpy( h->mb.pic.p_fdec[1] + y*FDEC_STRIDE, fdec_c + y*32, 8 );
+        memcpy( h->mb.pic.p_fdec[2] + y*FDEC_STRIDE, fdec_c + y*32 + 16, 8 );
+    }
+    x264_macroblock_encode( h );
+    for( y = 0; y < 16; y++ )
+        memcpy( fdec_y + y*32, h->mb.pic.p_fdec[0] + y*FDEC_STRIDE, 16 );
+    for( y = 0; y < 8; y++ )
+    {
+        memcpy( fdec_c + y*32, h->mb.pic.p_fdec[1] + y*FDEC_STRIDE, 8 );
+        memcpy( fdec_c + y*32 + 16, h->mb.pic.p_fdec[2] + y*FDEC_STRIDE, 8 );
+    }
+    memcpy( levels, h->dct.luma4x4[0], 16*16*sizeof(int16_t) );
+    memcpy( levels + 256, h->dct.chroma_dc[0], 4*sizeof(int16_t) );
+    memcpy( levels + 260, h->dct.chroma_dc[1], 4*sizeof(int16_t) );
+    memcpy( levels + 264, h->dct.luma4x4[16], 4*16*sizeof(int16_t) );
+    memcpy( levels + 328, h->dct.luma4x4[32], 4*16*sizeof(int16_t) );
+    for( i = 0; i < 16; i++ )
+        nnz[i] = h->mb.cache.non_zero_count[x264_scan8[i]];
+    for( i = 0; i < 4; i++ )
+    {
+        nnz[16+i] = h->mb.cache.non_zero_count[x264_scan8[16+i]];
+        nnz[20+i] = h->mb.cache.non_zero_count[x264_scan8[32+i]];
+    }
+    nnz[24] = h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]];
+    nnz[25] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]];
+    nnz[26] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]];
+    return h->mb.cbp[0];
+}
+
+/* ------------------------------------------------------------------ timing helpers
+ * (cpu_baseline / --impl reference): loops over the reference functions with the
+ * input already in memory; CLOCK_MONOTONIC around the loop; returns seconds. */
+
+static double xref_now( void )
+{
+    struct timespec ts;
+    clock_gettime( CLOCK_MONOTONIC, &ts );
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* lookahead leg for n frames: init_lowres on every frame, then frame_cost(i-1,i,i) for
+ * i = 1..n-1 (frame 0 gets the intra-only call frame_cost(0,0,0)).
+ * frames must have been loaded with xref_frame_load_i420. */
+double xref_time_lookahead( void *hv, void **frames, int n, int *cost_out )
+{
+    x264_t *h = hv;
+    double t0 = xref_now();
+    int i;
+    for( i = 0; i < n; i++ )
+        x264_frame_init_lowres( h, (x264_frame_t *)frames[i] );
+    cost_out[0] = xref_slicetype_frame_cost( h, (x264_frame_t **)frames, 0, 0, 0 );
+    for( i = 1; i < n; i++ )
+        cost_out[i] = xref_slicetype_frame_cost( h, (x264_frame_t **)frames, i-1, i, i );
+    return xref_now() - t0;
+}
