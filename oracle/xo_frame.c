@@ -44,7 +44,8 @@ void xo_geometry( int width, int height, x264dsp_geom_t *g )
     g->lowres_plane_size = plane_size_rule( g->lowres_stride * (g->lowres_h + 2*X264DSP_PADV), 1 << 10 );
     g->lowres_origin = g->lowres_stride * X264DSP_PADV + X264DSP_PADH;
     {
-        int64_t off = 4 * (int64_t)g->luma_plane_size;
+        /* +64: the filtered-plane border writes 8 bytes past the last plane (frame.c:406-412) */
+        int64_t off = 4 * (int64_t)g->luma_plane_size + 64;
         off = (off + 255) & ~(int64_t)255;
         g->slot_chroma_off = (int32_t)off;
         off += g->chroma_plane_size;

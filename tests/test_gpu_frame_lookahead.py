@@ -1,0 +1,204 @@
+"""GPU parity: frame staging / borders / half-pel / lowres planes, block costs and the lowres
+lookahead, CUDA (through the C ABI) against the CPU oracle on the same seeded input.
+Bar: bit-exact, padding included."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cpu_checkers as cc
+
+pytestmark = pytest.mark.gpu
+
+# sizes: CIF; not a multiple of 16; plane size without the 128-byte gap; stride = w+80; 1080p
+SIZES = [(352, 288), (200, 120), (368, 304), (960, 540)]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def oracle_slots(g, frames, border=False, hpel=False, lowres=False):
+    o = cc.oracle()
+    out = []
+    for f in frames:
+        s = np.zeros(g.slot_bytes, np.uint8)
+        o.xo_frame_load_i420(C.byref(g), cc.ptr(f), cc.ptr(s))
+        if border:
+            o.xo_frame_expand_border(C.byref(g), cc.ptr(s))
+        if hpel:
+            o.xo_frame_filter(C.byref(g), cc.ptr(s))
+        if lowres:
+            o.xo_frame_init_lowres(C.byref(g), cc.ptr(s))
+        out.append(s)
+    return out
+
+
+def diff_report(a, b, g):
+    bad = np.nonzero(a != b)[0]
+    if len(bad) == 0:
+        return ""
+    regions = []
+    for off in bad[:8]:
+        if off < 4 * g.luma_plane_size:
+            k, r = divmod(int(off), g.luma_plane_size)
+            regions.append(f"luma{k} row {r // g.luma_stride - 32} col {r % g.luma_stride - 32}")
+        elif off < g.slot_lowres_off:
+            r = int(off) - g.slot_chroma_off
+            regions.append(f"chroma row {r // g.chroma_stride - 16} col {r % g.chroma_stride - 32}")
+        else:
+            k, r = divmod(int(off) - g.slot_lowres_off, g.lowres_plane_size)
+            regions.append(f"lowres{k} row {r // g.lowres_stride - 32} col {r % g.lowres_stride - 32}")
+    return f"{len(bad)} bytes differ, first: " + "; ".join(regions)
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_frame_planes_match_oracle(pkg, ctx, w, h):
+    torch = _torch()
+    n = 2
+    frames = [pkg.synth_frame(w, h, i) for i in range(n)]
+    g = pkg.geometry(w, h)
+    go = cc.oracle_geom(w, h)
+    assert bytes(g) == bytes(go), "geometry differs from the oracle"
+
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, n)
+    ctx.sync()
+    want = oracle_slots(go, frames)
+    got = slots.cpu().numpy().reshape(n, -1)
+    for i in range(n):
+        assert diff_report(got[i], want[i], g) == "", "load_i420"
+
+    ctx.frame_expand_border(g, slots, n)
+    ctx.frame_filter(g, slots, n)
+    ctx.sync()
+    want = oracle_slots(go, frames, border=True, hpel=True)
+    got = slots.cpu().numpy().reshape(n, -1)
+    for i in range(n):
+        assert diff_report(got[i], want[i], g) == "", "expand_border + hpel filter"
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(1920, 1080)])
+def test_lowres_planes_match_oracle(pkg, ctx, w, h):
+    torch = _torch()
+    n = 2
+    frames = [pkg.synth_frame(w, h, i) for i in range(n)]
+    g = pkg.geometry(w, h)
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, n)
+    ctx.frame_init_lowres(g, slots, n)
+    ctx.sync()
+    want = oracle_slots(cc.oracle_geom(w, h), frames, lowres=True)
+    got = slots.cpu().numpy().reshape(n, -1)
+    for i in range(n):
+        assert diff_report(got[i], want[i], g) == "", "init_lowres (incl. source-plane side effect)"
+
+
+@pytest.mark.parametrize("cmp", [0, 1, 2])
+def test_cost_batch_matches_oracle(pkg, ctx, cmp):
+    torch = _torch()
+    rng = np.random.RandomState(7 + cmp)
+    stride1, stride2, rows = 80, 112, 64
+    p1 = rng.randint(0, 256, stride1 * rows + 64).astype(np.uint8)
+    p2 = rng.randint(0, 256, stride2 * rows + 64).astype(np.uint8)
+    # adversarial rows: all 0 vs all 255, equal planes, checkerboard
+    p1[: stride1 * 16] = 0
+    p2[: stride2 * 16] = 255
+    p1[stride1 * 16: stride1 * 32] = (np.arange(stride1 * 16) & 1) * 255
+    n = 4000
+    size = rng.randint(0, 8, n).astype(np.uint8)
+    off1 = np.zeros(n, np.int64)
+    off2 = np.zeros(n, np.int64)
+    for i in range(n):
+        bw, bh = cc.BLOCK_W[size[i]], cc.BLOCK_H[size[i]]
+        off1[i] = rng.randint(0, rows - bh) * stride1 + rng.randint(0, stride1 - bw)
+        off2[i] = rng.randint(0, rows - bh) * stride2 + rng.randint(0, stride2 - bw)
+    want = np.zeros(n, np.int32)
+    cc.oracle().xo_cost_batch(cmp, n, cc.ptr(p1), cc.ptr(off1, cc.i64p), stride1, cc.ptr(p2),
+                              cc.ptr(off2, cc.i64p), stride2, cc.ptr(size), cc.ptr(want, cc.i32p))
+    d = [torch.from_numpy(a).cuda() for a in (p1, off1, p2, off2, size)]
+    out = torch.zeros(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.cost_batch(cmp, n, d[0], d[1], stride1, d[2], d[3], stride2, d[4], out)
+    ctx.sync()
+    got = out.cpu().numpy()
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, f"cmp {cmp}: {len(bad)} costs differ, e.g. block {bad[:5]} size {size[bad[:5]]}"
+
+
+def oracle_lookahead(g, slots, i, want_intra=1, rows=False):
+    o = cc.oracle()
+    mv = np.zeros((g.mb_count, 2), np.int16)
+    c = np.zeros(g.mb_count, np.int32)
+    s = np.zeros(8, np.int32)
+    r = np.zeros((2, g.mb_h), np.int32)
+    o.xo_lookahead_frame_cost(C.byref(g), cc.ptr(slots[i]), cc.ptr(slots[i - 1]) if i else None, want_intra,
+                              cc.ptr(mv, cc.i16p), cc.ptr(c, cc.i32p), cc.ptr(s, cc.i32p), cc.ptr(r, cc.i32p))
+    return mv, c, s, r
+
+
+@pytest.mark.parametrize("w,h,n,cut", [(352, 288, 5, 3), (200, 120, 3, -1), (64, 64, 3, -1), (1920, 1080, 3, -1)])
+def test_lookahead_matches_oracle(pkg, ctx, w, h, n, cut):
+    torch = _torch()
+    frames = [pkg.synth_frame(w, h, i, cut) for i in range(n)]
+    g = pkg.geometry(w, h)
+    go = cc.oracle_geom(w, h)
+    ref_slots = oracle_slots(go, frames, lowres=True)
+
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    mvs = torch.full((n, g.mb_count, 2), -7, dtype=torch.int16, device="cuda")
+    costs = torch.full((n, g.mb_count), -7, dtype=torch.int32, device="cuda")
+    sums = torch.full((n, pkg.LA_SUMS), -7, dtype=torch.int32, device="cuda")
+    rows = torch.full((n, 2, g.mb_h), -7, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, n)
+    ctx.frame_init_lowres(g, slots, n)
+    b = np.arange(n)
+    p0 = b - 1
+    for rep in range(2):            # second run exercises the epoch logic of the sync words
+        ctx.lookahead_frame_cost(g, slots, b, p0, np.ones(n, np.uint8), mvs, costs, sums, rows)
+        ctx.sync()
+        gm, gc, gs, gr = (t.cpu().numpy() for t in (mvs, costs, sums, rows))
+        for i in range(n):
+            mv_o, c_o, s_o, r_o = oracle_lookahead(go, ref_slots, i, rows=True)
+            assert np.array_equal(gm[i], mv_o), f"rep {rep} frame {i}: mvs"
+            assert np.array_equal(gc[i], c_o), f"rep {rep} frame {i}: block costs"
+            assert np.array_equal(gs[i][:5], s_o[:5]), f"rep {rep} frame {i}: sums {gs[i]} vs {s_o}"
+            assert np.array_equal(gr[i], r_o), f"rep {rep} frame {i}: row sums"
+
+
+def test_lookahead_without_intra_and_host_api(pkg, ctx):
+    """second analysis of a frame (intra already known) and the host-buffer entry point"""
+    torch = _torch()
+    w, h, n = 352, 288, 4
+    luma = np.stack([pkg.synth_frame(w, h, i, luma_only=True) for i in range(n)])
+    mvs, costs, sums = ctx.lookahead_clip_host(w, h, luma)
+    go = cc.oracle_geom(w, h)
+    frames = [np.concatenate([luma[i], np.zeros(w * h // 2, np.uint8)]) for i in range(n)]
+    ref_slots = oracle_slots(go, frames, lowres=True)
+    for i in range(n):
+        mv_o, c_o, s_o, _ = oracle_lookahead(go, ref_slots, i)
+        assert np.array_equal(mvs[i], mv_o) and np.array_equal(costs[i], c_o)
+        assert np.array_equal(sums[i][:5], s_o[:5])
+
+    g = pkg.geometry(w, h)
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    d_mvs = torch.zeros((1, g.mb_count, 2), dtype=torch.int16, device="cuda")
+    d_costs = torch.zeros((1, g.mb_count), dtype=torch.int32, device="cuda")
+    d_sums = torch.zeros((1, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, n)
+    ctx.frame_init_lowres(g, slots, n)
+    ctx.lookahead_frame_cost(g, slots, [2], [1], [0], d_mvs, d_costs, d_sums)
+    ctx.sync()
+    mv_o, c_o, s_o, _ = oracle_lookahead(go, ref_slots, 2, want_intra=0)
+    assert np.array_equal(d_mvs.cpu().numpy()[0], mv_o)
+    assert np.array_equal(d_costs.cpu().numpy()[0], c_o)
+    assert np.array_equal(d_sums.cpu().numpy()[0][:5], s_o[:5])

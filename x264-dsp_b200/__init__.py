@@ -1,0 +1,248 @@
+"""x264dsp_b200 -- ctypes binding of libx264dsp_b200.so (the B200-native x264-dsp hot path).
+
+The directory name carries a hyphen, so load it with `load_package()` from `__graft_entry__.py`
+(or importlib) under the module name `x264dsp_b200`.
+
+There is no CPU implementation behind these calls.  If the shared library has not been built the
+import fails; if no CUDA device can be opened, `Context()` raises.  PyTorch is used only to own
+device memory and streams in tests and benchmarks.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libx264dsp_b200.so")
+
+PIXEL_16x16, PIXEL_16x8, PIXEL_8x16, PIXEL_8x8, PIXEL_8x4, PIXEL_4x8, PIXEL_4x4, PIXEL_4x16 = range(8)
+BLOCK_W = [16, 16, 8, 8, 8, 4, 4, 4]
+BLOCK_H = [16, 8, 16, 8, 4, 8, 4, 16]
+CMP_SAD, CMP_SSD, CMP_SATD = 0, 1, 2
+ME_DIA, ME_HEX = 0, 1
+LA_COST_INTER, LA_COST_INTRA, LA_INTRA_MBS, LA_SAD_EVALS, LA_SATD_EVALS, LA_SUMS = 0, 1, 2, 3, 4, 8
+RES_LEVELS_PER_MB = 16 * 16 + 2 * 4 + 2 * 4 * 16
+RES_NNZ_PER_MB = 16 + 8 + 3
+
+u8p = C.POINTER(C.c_uint8)
+
+
+class Geom(C.Structure):
+    """x264dsp_geom_t"""
+    _fields_ = [(n, C.c_int32) for n in (
+        "width", "height", "mb_w", "mb_h", "mb_count", "luma_w", "luma_h",
+        "luma_stride", "luma_plane_size", "luma_origin",
+        "chroma_stride", "chroma_h", "chroma_plane_size", "chroma_origin",
+        "lowres_w", "lowres_h", "lowres_stride", "lowres_plane_size", "lowres_origin",
+        "slot_chroma_off", "slot_lowres_off")] + [("slot_bytes", C.c_int64)]
+
+
+class MeParams(C.Structure):
+    _fields_ = [("me_method", C.c_int32), ("subpel_refine", C.c_int32), ("me_range", C.c_int32),
+                ("qp", C.c_int32), ("refine_qpel", C.c_int32)]
+
+
+ME_BLOCK_DTYPE = np.dtype([("i_pixel", "<i4"), ("bx", "<i4"), ("by", "<i4"), ("mvp", "<i2", (2,)),
+                           ("i_mvc", "<i4"), ("mvc", "<i2", (16, 2)),
+                           ("mv_min_fpel", "<i4", (2,)), ("mv_max_fpel", "<i4", (2,)),
+                           ("mv_min_spel", "<i4", (2,)), ("mv_max_spel", "<i4", (2,))], align=True)
+ME_RESULT_DTYPE = np.dtype([("mv", "<i2", (2,)), ("cost", "<i4"), ("cost_mv", "<i4")], align=True)
+
+
+class X264DspError(RuntimeError):
+    pass
+
+
+def build(force=False):
+    """compile the CUDA library in-tree (nvcc, sm_100a)"""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-s", "-C", ROOT], check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """the loaded shared library; raises when it does not exist (no fallback)"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise X264DspError(
+                f"{LIB_PATH} is missing: run `make` (nvcc, sm_100a). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        l.x264dsp_version.restype = C.c_char_p
+        l.x264dsp_stream.restype = C.c_void_p
+        l.x264dsp_launch_count.restype = C.c_int64
+        l.x264dsp_stream.argtypes = [C.c_void_p]
+        l.x264dsp_launch_count.argtypes = [C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        kind = {-1: "bad argument", -2: "no CUDA device (there is no CPU path)", -3: "out of memory"}.get(
+            rc, f"cudaError {rc}")
+        raise X264DspError(f"{what} failed: {kind}")
+
+
+def geometry(width, height):
+    g = Geom()
+    check(lib().x264dsp_geometry(int(width), int(height), C.byref(g)), "x264dsp_geometry")
+    return g
+
+
+def synth_frame(width, height, n, cut_frame=-1, luma_only=False):
+    """planar I420 (or luma-only) numpy array of synthetic frame n"""
+    y = np.empty(width * height, np.uint8)
+    if luma_only:
+        check(lib().x264dsp_synth_frame(width, height, n, cut_frame, y.ctypes.data_as(u8p), None, None),
+              "x264dsp_synth_frame")
+        return y
+    cw, ch = width // 2, height // 2
+    buf = np.empty(width * height + 2 * cw * ch, np.uint8)
+    yv = buf[: width * height]
+    uv = buf[width * height: width * height + cw * ch]
+    vv = buf[width * height + cw * ch:]
+    check(lib().x264dsp_synth_frame(width, height, n, cut_frame, yv.ctypes.data_as(u8p),
+                                    uv.ctypes.data_as(u8p), vv.ctypes.data_as(u8p)), "x264dsp_synth_frame")
+    return buf
+
+
+def cost_mv_table(qp):
+    t = np.zeros(8193, np.uint16)
+    check(lib().x264dsp_cost_mv_table(qp, t.ctypes.data_as(C.POINTER(C.c_uint16))), "x264dsp_cost_mv_table")
+    return t
+
+
+def quant_tables(b_inter, qp):
+    mf = np.zeros(16, np.uint16)
+    bias = np.zeros(16, np.uint16)
+    check(lib().x264dsp_quant_tables(int(b_inter), qp, mf.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                     bias.ctypes.data_as(C.POINTER(C.c_uint16))), "x264dsp_quant_tables")
+    return mf, bias
+
+
+def dequant_table():
+    t = np.zeros((6, 16), np.int32)
+    check(lib().x264dsp_dequant_table(t.ctypes.data_as(C.POINTER(C.c_int))), "x264dsp_dequant_table")
+    return t
+
+
+def _dp(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _hp(a, ctype=C.c_uint8):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Context:
+    """x264dsp_ctx_t: one per process / GPU"""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib().x264dsp_create(int(device), C.byref(self._h)), "x264dsp_create")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().x264dsp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        """cudaStream_t of the context as an int"""
+        return lib().x264dsp_stream(self._h)
+
+    def torch_stream(self):
+        import torch
+        return torch.cuda.ExternalStream(self.stream, device=f"cuda:{self.device}")
+
+    def sync(self):
+        check(lib().x264dsp_sync(self._h), "x264dsp_sync")
+
+    @property
+    def launches(self):
+        return lib().x264dsp_launch_count(self._h)
+
+    # ---- frame staging -------------------------------------------------------------------
+    def frame_load_i420(self, g, i420_dev, slots_dev, n_frames):
+        check(lib().x264dsp_frame_load_i420_dev(self._h, C.byref(g), _dp(i420_dev), _dp(slots_dev),
+                                                int(n_frames), None), "x264dsp_frame_load_i420_dev")
+
+    def frame_expand_border(self, g, slots_dev, n_frames):
+        check(lib().x264dsp_frame_expand_border_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),
+              "x264dsp_frame_expand_border_dev")
+
+    def frame_filter(self, g, slots_dev, n_frames):
+        check(lib().x264dsp_frame_filter_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),
+              "x264dsp_frame_filter_dev")
+
+    def frame_init_lowres(self, g, slots_dev, n_frames):
+        check(lib().x264dsp_frame_init_lowres_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),
+              "x264dsp_frame_init_lowres_dev")
+
+    # ---- block costs ---------------------------------------------------------------------
+    def cost_batch(self, cmp, n, pix1, off1, stride1, pix2, off2, stride2, size, out):
+        check(lib().x264dsp_cost_batch_dev(self._h, int(cmp), int(n), _dp(pix1), _dp(off1), int(stride1),
+                                           _dp(pix2), _dp(off2), int(stride2), _dp(size), _dp(out), None),
+              "x264dsp_cost_batch_dev")
+
+    # ---- lookahead -----------------------------------------------------------------------
+    def lookahead_frame_cost(self, g, slots_dev, b, p0, want_intra, mvs, costs, sums, row_satds=None):
+        b = np.ascontiguousarray(b, np.int32)
+        p0 = np.ascontiguousarray(p0, np.int32)
+        wi = np.ascontiguousarray(want_intra, np.uint8)
+        check(lib().x264dsp_lookahead_frame_cost_dev(
+            self._h, C.byref(g), _dp(slots_dev), len(b), _hp(b, C.c_int32), _hp(p0, C.c_int32), _hp(wi),
+            _dp(mvs), _dp(costs), _dp(sums), _dp(row_satds), None), "x264dsp_lookahead_frame_cost_dev")
+
+    def lookahead_clip_host(self, width, height, luma_frames):
+        """luma_frames: uint8 numpy [n, height*width] in ordinary host memory.
+        Returns (mvs [n, mb_count, 2] int16, costs [n, mb_count] int32, sums [n, LA_SUMS] int32)."""
+        g = geometry(width, height)
+        luma = np.ascontiguousarray(luma_frames, np.uint8)
+        n = luma.shape[0]
+        mvs = np.empty((n, g.mb_count, 2), np.int16)
+        costs = np.empty((n, g.mb_count), np.int32)
+        sums = np.empty((n, LA_SUMS), np.int32)
+        check(lib().x264dsp_lookahead_clip_host(self._h, int(width), int(height), int(n), _hp(luma),
+                                                _hp(mvs, C.c_int16), _hp(costs, C.c_int32),
+                                                _hp(sums, C.c_int32)), "x264dsp_lookahead_clip_host")
+        return mvs, costs, sums
+
+    # ---- motion search -------------------------------------------------------------------
+    def me_search_batch(self, g, fenc_slot, fref_slot, params, n, blocks_dev, results_dev):
+        check(lib().x264dsp_me_search_batch_dev(self._h, C.byref(g), _dp(fenc_slot), _dp(fref_slot),
+                                                C.byref(params), int(n), _dp(blocks_dev), _dp(results_dev),
+                                                None), "x264dsp_me_search_batch_dev")
+
+    # ---- residual / MC / deblock ---------------------------------------------------------
+    def mc_frame(self, g, fref_slot, mv_dev, pred_slot):
+        check(lib().x264dsp_mc_frame_dev(self._h, C.byref(g), _dp(fref_slot), _dp(mv_dev), _dp(pred_slot), None),
+              "x264dsp_mc_frame_dev")
+
+    def residual_frame(self, g, fenc_slot, pred_slot, qp, levels, nnz, cbp):
+        check(lib().x264dsp_residual_frame_dev(self._h, C.byref(g), _dp(fenc_slot), _dp(pred_slot), int(qp),
+                                               _dp(levels), _dp(nnz), _dp(cbp), None),
+              "x264dsp_residual_frame_dev")
+
+    def deblock_frame(self, g, slot, mb_type, partition, cbp, bs, qp, alpha_off=0, beta_off=0):
+        check(lib().x264dsp_deblock_frame_dev(self._h, C.byref(g), _dp(slot), _dp(mb_type), _dp(partition),
+                                              _dp(cbp), _dp(bs), int(qp), int(alpha_off), int(beta_off), None),
+              "x264dsp_deblock_frame_dev")
+
+    def deblock_strength(self, n, nnz, ref, mv, bs):
+        check(lib().x264dsp_deblock_strength_dev(self._h, int(n), _dp(nnz), _dp(ref), _dp(mv), _dp(bs), None),
+              "x264dsp_deblock_strength_dev")

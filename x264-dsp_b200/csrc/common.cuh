@@ -1,0 +1,126 @@
+// common.cuh -- shared declarations of the CUDA side of libx264dsp_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/x264dsp_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// context: one per process/GPU.  Owns the stream, the constant tables in HBM and the scratch
+// buffers of the batched entry points.
+struct x264dsp_ctx
+{
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    int64_t launches;
+
+    // cost_mv tables, one per distinct lambda (encoder/analyse.c:243-315); cost_mv_dev[qp] points at
+    // entry 0 of a uint16[8193] whose centre (index 4096) is mv delta 0.
+    uint16_t *cost_mv_store;
+    const uint16_t *cost_mv_dev[52];
+
+    // lookahead scratch (grown on demand)
+    unsigned long long *la_sync;   // [pairs][mb_count] {mv, epoch} words
+    int32_t *la_icost;             // [pairs][mb_count] intra cost per block
+    int32_t *la_ticket;            // work-queue counter
+    size_t la_sync_cap, la_icost_cap;
+    uint32_t la_epoch;
+
+    // host-API staging (x264dsp_lookahead_clip_host)
+    uint8_t *stage_host;  size_t stage_host_cap;     // pinned
+    uint8_t *stage_dev;   size_t stage_dev_cap;
+    uint8_t *clip_slots;  size_t clip_slots_cap;
+    uint8_t *clip_out;    size_t clip_out_cap;       // device results
+    uint8_t *clip_out_host; size_t clip_out_host_cap; // pinned results
+    int32_t *clip_desc;   size_t clip_desc_cap;
+
+    // per-call table shims (tables.cu)
+    uint8_t *shim_host;   // pinned
+    uint8_t *shim_dev;
+    size_t shim_cap;
+};
+
+#define XD_CHECK( call )                                                        \
+    do {                                                                        \
+        cudaError_t e_ = ( call );                                              \
+        if( e_ != cudaSuccess )                                                 \
+            return (int)e_;                                                     \
+    } while( 0 )
+
+static inline cudaStream_t xd_stream( x264dsp_ctx *ctx, void *stream )
+{
+    return stream ? (cudaStream_t)stream : ctx->stream;
+}
+
+// grows a device buffer to at least `bytes`
+int xd_reserve_dev( void **p, size_t *cap, size_t bytes );
+int xd_reserve_pinned( void **p, size_t *cap, size_t bytes );
+
+// host tables (tables_host.cpp)
+extern "C" int x264dsp_lambda( int qp );
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+#ifdef __CUDACC__
+
+// per-byte rounded average (a+b+1)>>1 of four packed pixels, the pixel_avg of common/mc.c:74-87
+__device__ __forceinline__ uint32_t xd_avg4( uint32_t a, uint32_t b )
+{
+    return ( a | b ) - ( ( ( a ^ b ) & 0xFEFEFEFEu ) >> 1 );
+}
+
+// four-pixel SAD with accumulate: one VABSDIFF4.U8.ACC
+__device__ __forceinline__ uint32_t xd_sad4( uint32_t a, uint32_t b, uint32_t acc )
+{
+    return __vsadu4( a, b ) + acc;
+}
+
+__device__ __forceinline__ int xd_clip3( int v, int lo, int hi )
+{
+    return min( max( v, lo ), hi );
+}
+
+__device__ __forceinline__ int xd_clip_u8( int v )
+{
+    return min( max( v, 0 ), 255 );
+}
+
+// 8 consecutive pixels starting at an arbitrary byte address, through the read-only path:
+// three aligned words and two funnel shifts.
+__device__ __forceinline__ uint2 xd_load8_unaligned( const uint8_t *p )
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)( a & ~(uintptr_t)3 );
+    const uint32_t sh = ( (uint32_t)a & 3u ) * 8u;
+    uint32_t w0 = __ldg( w ), w1 = __ldg( w + 1 ), w2 = __ldg( w + 2 );
+    uint2 r;
+    r.x = __funnelshift_r( w0, w1, sh );
+    r.y = __funnelshift_r( w1, w2, sh );
+    return r;
+}
+
+// 4 consecutive pixels at an arbitrary byte address
+__device__ __forceinline__ uint32_t xd_load4_unaligned( const uint8_t *p )
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)( a & ~(uintptr_t)3 );
+    const uint32_t sh = ( (uint32_t)a & 3u ) * 8u;
+    return __funnelshift_r( __ldg( w ), __ldg( w + 1 ), sh );
+}
+
+// Quarter-pel plane selection of mc_luma / get_ref (common/mc.c:192-193, 222-234).
+// phase = (mvy&3)*4 + (mvx&3).  Packed as two bits per phase.
+__device__ __forceinline__ int xd_qpel_plane_a( int phase )
+{
+    // {0,1,1,1, 0,1,1,1, 2,3,3,3, 0,1,1,1}
+    return (int)( ( 0x54FE5454u >> ( phase * 2 ) ) & 3u );
+}
+__device__ __forceinline__ int xd_qpel_plane_b( int phase )
+{
+    // {0,0,0,0, 2,2,3,2, 2,2,3,2, 2,2,3,2}
+    return (int)( ( 0xBABABA00u >> ( phase * 2 ) ) & 3u );
+}
+
+#endif // __CUDACC__

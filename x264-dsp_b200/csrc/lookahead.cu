@@ -1,0 +1,750 @@
+// lookahead.cu -- lowres lookahead frame-cost pass, sm_100a.
+//
+// Reference: x264_slicetype_mb_cost / x264_slicetype_frame_cost (encoder/slicetype.c:48-322) with
+// the search it drives, x264_me_search_ref + refine_subpel at DIA / subme 2 (encoder/me.c:129-587),
+// on 8x8 blocks of the half-resolution planes, lambda = 1 (QP 12), do_edges = 0.
+//
+// Dependency structure: blocks are visited in reverse raster order and block (x,y)
+// takes its MV predictors from (x+1,y), (x,y+1), (x-1,y+1), (x+1,y+1).  Rows therefore pipeline
+// with a lag of two blocks.  Mapping:
+//   * one WARP owns one block row of one frame pair and walks it right to left;
+//   * rows are handed out through an atomic ticket in dependency order (pair-major, bottom row
+//     first), so the row a warp waits on is always held by a warp that is already running --
+//     no co-residency assumption, no deadlock;
+//   * a finished block publishes {mv, epoch} as ONE 64-bit word; the row above spins on that word
+//     (volatile load, issued a block ahead of its use).  The payload is the flag, so no fence sits
+//     on the critical path;
+//   * inside a block the warp evaluates up to four candidate positions at once: lane = 8*cand+row,
+//     8 pixels per lane (VABSDIFF4.U8.ACC x2), xor-shuffle reduction over the 8 rows, then a
+//     packed (cost,order) min over the candidates that reproduces the reference's strict-'<',
+//     first-wins tie breaking;
+//   * the intra estimate has no dependencies and runs first as a plain thread-per-block kernel.
+// Many frame pairs per launch fill the machine; a single pair is latency bound by construction.
+#include "common.cuh"
+
+#define LA_COST_MAX ( 1 << 28 )
+#define LA_WARPS 4
+
+struct xd_la_args
+{
+    x264dsp_geom_t g;
+    const uint8_t *slots;
+    const int32_t *b, *p0;
+    const uint8_t *want_intra;
+    int n_pairs;
+    int16_t *mvs;
+    int32_t *costs, *sums, *row_satds;
+    const uint16_t *cost_mv;            // centre of the lambda=1 table
+    unsigned long long *sync;
+    int32_t *icost;
+    int32_t *ticket;
+    uint32_t epoch;
+    int me_range;
+};
+
+// ---------------------------------------------------------------------------------------------
+// 4-point Hadamard butterfly; output 0 is the plain sum
+__device__ __forceinline__ void xd_had4( int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3 )
+{
+    const int s01 = a + b, d01 = a - b, s23 = c + d, d23 = c - d;
+    o0 = s01 + s23; o1 = s01 - s23; o2 = d01 + d23; o3 = d01 - d23;
+}
+
+// sum |H4 D H4^T| of a 4x4 block given as four packed rows of differences' operands
+__device__ __forceinline__ int xd_satd4x4_words( const uint32_t a[4], const uint32_t b[4] )
+{
+    int t[4][4];
+#pragma unroll
+    for( int r = 0; r < 4; r++ )
+    {
+        const int d0 = (int)( a[r] & 255 ) - (int)( b[r] & 255 );
+        const int d1 = (int)( ( a[r] >> 8 ) & 255 ) - (int)( ( b[r] >> 8 ) & 255 );
+        const int d2 = (int)( ( a[r] >> 16 ) & 255 ) - (int)( ( b[r] >> 16 ) & 255 );
+        const int d3 = (int)( a[r] >> 24 ) - (int)( b[r] >> 24 );
+        xd_had4( d0, d1, d2, d3, t[r][0], t[r][1], t[r][2], t[r][3] );
+    }
+    int acc = 0;
+#pragma unroll
+    for( int c = 0; c < 4; c++ )
+    {
+        int o0, o1, o2, o3;
+        xd_had4( t[0][c], t[1][c], t[2][c], t[3][c], o0, o1, o2, o3 );
+        acc += abs( o0 ) + abs( o1 ) + abs( o2 ) + abs( o3 );
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// intra estimate: x264_intra_satd_x3_8x8c on the SOURCE lowres plane (slicetype.c:145-180).
+// Hadamard is linear, so satd(pred - src) is evaluated from ONE transform of the source 4x4 and
+// the (sparse) transforms of the three predictions: DC touches coefficient (0,0), V the first row
+// of coefficients, H the first column.
+__global__ void __launch_bounds__( 128 )
+xd_la_intra_kernel( xd_la_args A )
+{
+    const int pair = blockIdx.y;
+    if( !A.want_intra[pair] )
+        return;
+    const x264dsp_geom_t &g = A.g;
+    const int W = g.mb_w, H = g.mb_h;
+    const int inner = ( W - 2 ) * ( H - 2 );
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int icost = 0, by = 0;
+    if( i < inner )
+    {
+        const int bx = 1 + i % ( W - 2 );
+        by = 1 + i / ( W - 2 );
+        const int ls = g.lowres_stride;
+        const uint8_t *src = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin
+                           + ( (size_t)by * ls + bx ) * 8;
+        uint2 row[8];
+        uint32_t left[8];
+#pragma unroll
+        for( int r = 0; r < 8; r++ )
+        {
+            row[r] = __ldg( (const uint2 *)( src + (size_t)r * ls ) );
+            left[r] = __ldg( src + (size_t)r * ls - 1 );
+        }
+        const uint2 top = __ldg( (const uint2 *)( src - ls ) );
+        int tp[8];
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            tp[k] = ( top.x >> ( 8 * k ) ) & 255;
+            tp[4 + k] = ( top.y >> ( 8 * k ) ) & 255;
+        }
+        // quadrant DC values (predict.c:224-262)
+        const int s0 = tp[0] + tp[1] + tp[2] + tp[3], s1 = tp[4] + tp[5] + tp[6] + tp[7];
+        const int s2 = left[0] + left[1] + left[2] + left[3], s3 = left[4] + left[5] + left[6] + left[7];
+        const int dcq[4] = { ( s0 + s2 + 4 ) >> 3, ( s1 + 2 ) >> 2, ( s3 + 2 ) >> 2, ( s1 + s3 + 4 ) >> 3 };
+
+        int sat_dc[4], sat_h[4], sat_v[4];
+#pragma unroll
+        for( int q = 0; q < 4; q++ )
+        {
+            const int qx = q & 1, qy = q >> 1;
+            int t[4][4];
+#pragma unroll
+            for( int r = 0; r < 4; r++ )
+            {
+                const uint32_t w = qx ? row[4 * qy + r].y : row[4 * qy + r].x;
+                xd_had4( w & 255, ( w >> 8 ) & 255, ( w >> 16 ) & 255, w >> 24, t[r][0], t[r][1], t[r][2], t[r][3] );
+            }
+            int f[4][4];                       // f[u][v]: u vertical, v horizontal frequency
+#pragma unroll
+            for( int c = 0; c < 4; c++ )
+                xd_had4( t[0][c], t[1][c], t[2][c], t[3][c], f[0][c], f[1][c], f[2][c], f[3][c] );
+            int all = 0, row0 = 0, col0 = 0;
+#pragma unroll
+            for( int u = 0; u < 4; u++ )
+#pragma unroll
+                for( int v = 0; v < 4; v++ )
+                    all += abs( f[u][v] );
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                row0 += abs( f[0][k] );
+                col0 += abs( f[k][0] );
+            }
+            int tv[4], th[4];
+            xd_had4( tp[4 * qx], tp[4 * qx + 1], tp[4 * qx + 2], tp[4 * qx + 3], tv[0], tv[1], tv[2], tv[3] );
+            xd_had4( left[4 * qy], left[4 * qy + 1], left[4 * qy + 2], left[4 * qy + 3], th[0], th[1], th[2], th[3] );
+            int v_part = 0, h_part = 0;
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                v_part += abs( f[0][k] - 4 * tv[k] );
+                h_part += abs( f[k][0] - 4 * th[k] );
+            }
+            sat_dc[q] = all - abs( f[0][0] ) + abs( f[0][0] - 16 * dcq[q] );
+            sat_v[q] = all - row0 + v_part;
+            sat_h[q] = all - col0 + h_part;
+        }
+        // pixel.c:294-335: an 8x8 is two 8x4 halves, each halved once
+        const int c_dc = ( ( sat_dc[0] + sat_dc[1] ) >> 1 ) + ( ( sat_dc[2] + sat_dc[3] ) >> 1 );
+        const int c_h = ( ( sat_h[0] + sat_h[1] ) >> 1 ) + ( ( sat_h[2] + sat_h[3] ) >> 1 );
+        const int c_v = ( ( sat_v[0] + sat_v[1] ) >> 1 ) + ( ( sat_v[2] + sat_v[3] ) >> 1 );
+        icost = min( c_dc, min( c_h, c_v ) ) + 5 + 4;         // intra_penalty + lowres_penalty
+        A.icost[(size_t)pair * g.mb_count + by * W + bx] = icost;
+        if( A.row_satds )
+            atomicAdd( &A.row_satds[( (size_t)pair * 2 + 1 ) * H + by], icost );
+    }
+    // block-level sum of the frame's intra cost (integer adds: order independent)
+    int sum = icost, cnt = i < inner ? 1 : 0;
+#pragma unroll
+    for( int o = 16; o > 0; o >>= 1 )
+    {
+        sum += __shfl_xor_sync( 0xffffffffu, sum, o );
+        cnt += __shfl_xor_sync( 0xffffffffu, cnt, o );
+    }
+    if( ( threadIdx.x & 31 ) == 0 && cnt )
+    {
+        int32_t *s = A.sums + (size_t)pair * X264DSP_LA_SUMS;
+        atomicAdd( &s[X264DSP_LA_COST_INTRA], sum );
+        atomicAdd( &s[X264DSP_LA_SATD_EVALS], 3 * cnt );
+        if( A.p0[pair] < 0 )
+            atomicAdd( &s[X264DSP_LA_INTRA_MBS], cnt );   // intra-only analysis: every block is intra
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inter search: warp-wide helpers.  All scalar state is replicated in every lane.
+
+struct xd_la_block
+{
+    const uint8_t *ref;       // reference lowres plane N at the block origin; planes H,V,HV follow
+    size_t plane_size;
+    int stride;
+    uint2 fenc;               // this lane's source row (row = lane & 7)
+    uint32_t fq[4];           // rows of the 4x4 quadrant (lane & 3) of the source block
+    int mvpx, mvpy;
+    const uint16_t *cost_mv;
+    int sad_evals, satd_evals;
+};
+
+__device__ __forceinline__ int xd_la_bits( const xd_la_block &B, int qx, int qy )
+{
+    return __ldg( B.cost_mv + ( qx - B.mvpx ) ) + __ldg( B.cost_mv + ( qy - B.mvpy ) );
+}
+
+// 8 pixels of row `row` of the prediction at quarter-pel position (qx,qy): get_ref / mc_luma
+__device__ __forceinline__ uint2 xd_la_fetch( const xd_la_block &B, int qx, int qy, int row )
+{
+    const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
+    const int64_t base = (int64_t)( ( qy >> 2 ) + row ) * B.stride + ( qx >> 2 );
+    const uint8_t *pa = B.ref + (size_t)xd_qpel_plane_a( phase ) * B.plane_size + base + ( fy == 3 ? B.stride : 0 );
+    uint2 a = xd_load8_unaligned( pa );
+    if( phase & 5 )
+    {
+        const uint8_t *pb = B.ref + (size_t)xd_qpel_plane_b( phase ) * B.plane_size + base + ( fx == 3 ? 1 : 0 );
+        const uint2 b = xd_load8_unaligned( pb );
+        a.x = xd_avg4( a.x, b.x );
+        a.y = xd_avg4( a.y, b.y );
+    }
+    return a;
+}
+
+// SAD of this lane's candidate (lane>>3) at (qx,qy); every lane of the candidate's group of 8 gets it
+__device__ __forceinline__ int xd_la_sad( const xd_la_block &B, int qx, int qy, int lane )
+{
+    const uint2 p = xd_la_fetch( B, qx, qy, lane & 7 );
+    int s = (int)( __vsadu4( p.x, B.fenc.x ) + __vsadu4( p.y, B.fenc.y ) );
+    s += __shfl_xor_sync( 0xffffffffu, s, 1 );
+    s += __shfl_xor_sync( 0xffffffffu, s, 2 );
+    s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+    return s;
+}
+
+// min over the four candidate groups of a packed key
+__device__ __forceinline__ int xd_la_min4( int key )
+{
+    key = min( key, __shfl_xor_sync( 0xffffffffu, key, 8 ) );
+    key = min( key, __shfl_xor_sync( 0xffffffffu, key, 16 ) );
+    return key;
+}
+
+// SATD 8x8 of the prediction at (qx,qy) against the source block (pixel.c:294-335)
+__device__ __forceinline__ int xd_la_satd( const xd_la_block &B, int qx, int qy, int lane )
+{
+    const uint2 p = xd_la_fetch( B, qx, qy, lane & 7 );
+    const int q = lane & 3, r0 = ( q >> 1 ) * 4;
+    uint32_t pr[4];
+#pragma unroll
+    for( int r = 0; r < 4; r++ )
+    {
+        const uint32_t lo = __shfl_sync( 0xffffffffu, p.x, r0 + r );
+        const uint32_t hi = __shfl_sync( 0xffffffffu, p.y, r0 + r );
+        pr[r] = ( q & 1 ) ? hi : lo;
+    }
+    int s = xd_satd4x4_words( B.fq, pr );
+    s += __shfl_xor_sync( 0xffffffffu, s, 1 );      // left + right 4x4 of an 8x4
+    s >>= 1;
+    s += __shfl_xor_sync( 0xffffffffu, s, 2 );      // upper + lower 8x4
+    return s;
+}
+
+// CHECK_MVRANGE (me.c:155-160)
+__device__ __forceinline__ bool xd_la_in_range( int mx, int my, int minx, int miny, int maxx, int maxy )
+{
+    const uint32_t lo = ( (uint32_t)( -minx ) << 16 ) | ( (uint32_t)( -miny ) & 0x7FFF );
+    const uint32_t hi = ( (uint32_t)maxx << 16 ) | ( (uint32_t)maxy & 0x7FFF ) | 0x8000;
+    const uint32_t v = ( (uint32_t)mx << 16 ) | ( (uint32_t)my & 0x7FFF );
+    return !( ( ( v + lo ) | ( hi - v ) ) & 0x80004000u );
+}
+
+__device__ __forceinline__ int xd_median3( int a, int b, int c )
+{
+    return max( min( a, b ), min( max( a, b ), c ) );
+}
+
+__device__ __forceinline__ unsigned long long xd_ld_sync( const unsigned long long *p )
+{
+    unsigned long long v;
+    asm volatile( "ld.volatile.global.u64 %0, [%1];" : "=l"( v ) : "l"( p ) : "memory" );
+    return v;
+}
+
+__device__ __forceinline__ void xd_st_sync( unsigned long long *p, unsigned long long v )
+{
+    asm volatile( "st.volatile.global.u64 [%0], %1;" :: "l"( p ), "l"( v ) : "memory" );
+}
+
+// wait until the word carries this launch's epoch; returns the packed mv
+__device__ __forceinline__ uint32_t xd_la_await( const unsigned long long *p, unsigned long long seen, uint32_t epoch )
+{
+    unsigned ns = 20;
+    while( (uint32_t)( seen >> 32 ) != epoch )
+    {
+        __nanosleep( ns );
+        if( ns < 200 )
+            ns += 20;
+        seen = xd_ld_sync( p );
+    }
+    return (uint32_t)seen;
+}
+
+#define MVX( m ) ( (int)(int16_t)( ( m ) & 0xFFFF ) )
+#define MVY( m ) ( (int)(int16_t)( ( m ) >> 16 ) )
+
+__global__ void __launch_bounds__( LA_WARPS * 32 )
+xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
+{
+    const x264dsp_geom_t &g = A.g;
+    const int lane = threadIdx.x & 31;
+    const int W = g.mb_w, H = g.mb_h, ls = g.lowres_stride;
+    const int rows = H - 2;
+    const int total = n_inter * rows;
+    const int cand = lane >> 3;
+
+    for( ;; )
+    {
+        int ticket = 0;
+        if( lane == 0 )
+            ticket = atomicAdd( A.ticket, 1 );
+        ticket = __shfl_sync( 0xffffffffu, ticket, 0 );
+        if( ticket >= total )
+            return;
+        const int pair = inter_pairs[ticket / rows];
+        const int by = H - 2 - ticket % rows;
+        const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
+        const uint8_t *ref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
+        unsigned long long *sync_row = A.sync + (size_t)pair * g.mb_count + (size_t)by * W;
+        const unsigned long long *sync_below = sync_row + W;
+        const bool has_below = by < H - 2;
+        const bool want_intra = A.want_intra[pair] != 0;
+
+        // MV limits (slicetype.c:79-89); the y limits are per row
+        const int miny = -( by << 3 ) - 4, maxy = ( ( H - by - 1 ) << 3 ) + 4;
+        const int sminy = ( miny - 8 ) << 2, smaxy = ( maxy + 8 ) << 2;
+
+        xd_la_block B;
+        B.plane_size = (size_t)g.lowres_plane_size;
+        B.stride = ls;
+        B.cost_mv = A.cost_mv;
+        B.sad_evals = 0;
+        B.satd_evals = 0;
+
+        uint32_t mv_right = 0;                           // (x+1, y): border block
+        uint32_t mv_b = 0, mv_br = 0, mv_bl = 0;         // (x, y+1), (x+1, y+1), (x-1, y+1)
+        unsigned long long pending = 0;
+        if( has_below )
+        {
+            mv_b = xd_la_await( sync_below + ( W - 2 ), xd_ld_sync( sync_below + ( W - 2 ) ), A.epoch );
+            pending = xd_ld_sync( sync_below + ( W - 3 ) );
+        }
+        int row_sum = 0, row_intra = 0;
+
+        for( int bx = W - 2; bx >= 1; bx-- )
+        {
+            // (x-1, y+1): needed now; for x == 1 that is a border block (zero)
+            if( has_below && bx >= 2 )
+                mv_bl = xd_la_await( sync_below + ( bx - 1 ), pending, A.epoch );
+            else
+                mv_bl = 0;
+            // start fetching the word the NEXT block will need
+            if( has_below && bx >= 3 )
+                pending = xd_ld_sync( sync_below + ( bx - 2 ) );
+
+            const size_t pel = ( (size_t)by * ls + bx ) * 8;
+            B.ref = ref + pel;
+            B.fenc = __ldg( (const uint2 *)( cur + pel + (size_t)( lane & 7 ) * ls ) );
+            {
+                const int q = lane & 3, r0 = ( q >> 1 ) * 4;
+#pragma unroll
+                for( int r = 0; r < 4; r++ )
+                {
+                    const uint32_t lo = __shfl_sync( 0xffffffffu, B.fenc.x, r0 + r );
+                    const uint32_t hi = __shfl_sync( 0xffffffffu, B.fenc.y, r0 + r );
+                    B.fq[r] = ( q & 1 ) ? hi : lo;
+                }
+            }
+            const int minx = -( bx << 3 ) - 4, maxx = ( ( W - bx - 1 ) << 3 ) + 4;
+            const int sminx = ( minx - 8 ) << 2, smaxx = ( maxx + 8 ) << 2;
+
+            // predictors (slicetype.c:105-113): right, below, below-left, below-right
+            const uint32_t mvc[4] = { mv_right, mv_b, mv_bl, mv_br };
+            B.mvpx = xd_median3( MVX( mvc[0] ), MVX( mvc[1] ), MVX( mvc[2] ) );
+            B.mvpy = xd_median3( MVY( mvc[0] ), MVY( mvc[1] ), MVY( mvc[2] ) );
+
+            int mvx = 0, mvy = 0, cost = -1;
+            if( !( B.mvpx | B.mvpy ) )                     // slicetype.c:117-125
+            {
+                const int c0 = xd_la_satd( B, 0, 0, lane );
+                B.satd_evals++;
+                if( c0 < 64 )
+                    cost = c0;
+            }
+            if( cost < 0 )
+            {
+                // ---- x264_me_search_ref, subme < 3 branch (me.c:194-233)
+                int bmx = xd_clip3( B.mvpx, minx * 4, maxx * 4 ), bmy = xd_clip3( B.mvpy, miny * 4, maxy * 4 );
+                const int pmx = ( bmx + 2 ) >> 2, pmy = ( bmy + 2 ) >> 2;
+                const uint32_t pmv = ( (uint32_t)pmx & 0xFFFF ) | ( (uint32_t)pmy << 16 );
+                int bcost;
+                {
+                    // candidates in evaluation order: 0 = rounded MVP (no mv cost), 1..4 = mvc, 5 = (0,0)
+                    int cx[2], cy[2];
+                    bool ok[2];
+                    const int idx[2] = { cand, cand + 4 };
+#pragma unroll
+                    for( int pass = 0; pass < 2; pass++ )
+                    {
+                        const int k = idx[pass];
+                        cx[pass] = 0; cy[pass] = 0; ok[pass] = false;
+                        if( k == 0 )
+                        {
+                            cx[pass] = pmx; cy[pass] = pmy; ok[pass] = true;
+                        }
+                        else if( k <= 4 )
+                        {
+                            const uint32_t m = mvc[k - 1];
+                            cx[pass] = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx );
+                            cy[pass] = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
+                            const uint32_t v = ( (uint32_t)cx[pass] & 0xFFFF ) | ( (uint32_t)cy[pass] << 16 );
+                            ok[pass] = v != 0 && v != pmv;
+                        }
+                        else if( k == 5 )
+                            ok[pass] = pmv != 0;
+                    }
+                    int key = 0x7FFFFFFF;
+#pragma unroll
+                    for( int pass = 0; pass < 2; pass++ )
+                    {
+                        // pass 1 only carries candidates 4 and 5 (groups 0 and 1)
+                        int s = xd_la_sad( B, cx[pass] << 2, cy[pass] << 2, lane );
+                        if( idx[pass] != 0 )
+                            s += xd_la_bits( B, cx[pass] << 2, cy[pass] << 2 );
+                        if( ok[pass] )
+                            key = min( key, ( s << 3 ) | idx[pass] );
+                    }
+                    key = xd_la_min4( key );
+                    bcost = key >> 3;
+                    const int win = key & 7;
+                    // every lane recomputes the winner's coordinates
+                    if( win == 0 ) { bmx = pmx; bmy = pmy; }
+                    else if( win == 5 ) { bmx = 0; bmy = 0; }
+                    else
+                    {
+                        const uint32_t m = mvc[win - 1];
+                        bmx = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx );
+                        bmy = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
+                    }
+                    // evaluations the reference issues: MVP + valid candidates + (0,0)
+                    int n = 1 + ( pmv != 0 );
+#pragma unroll
+                    for( int k = 0; k < 4; k++ )
+                    {
+                        const uint32_t m = mvc[k];
+                        const int x = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx ), y = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
+                        const uint32_t v = ( (uint32_t)x & 0xFFFF ) | ( (uint32_t)y << 16 );
+                        n += v != 0 && v != pmv;
+                    }
+                    B.sad_evals += n;
+                }
+
+                // ---- diamond search (me.c:237-274): up, down, left, right
+                {
+                    const int dx = cand == 2 ? -1 : cand == 3 ? 1 : 0;
+                    const int dy = cand == 0 ? -1 : cand == 1 ? 1 : 0;
+                    int left = A.me_range;
+                    do
+                    {
+                        const int cxq = ( bmx + dx ) << 2, cyq = ( bmy + dy ) << 2;
+                        const int s = xd_la_sad( B, cxq, cyq, lane ) + xd_la_bits( B, cxq, cyq );
+                        const int key = xd_la_min4( ( s << 2 ) | cand );
+                        B.sad_evals += 4;
+                        if( ( key >> 2 ) >= bcost )
+                            break;
+                        bcost = key >> 2;
+                        const int w = key & 3;
+                        bmx += w == 2 ? -1 : w == 3 ? 1 : 0;
+                        bmy += w == 0 ? -1 : w == 1 ? 1 : 0;
+                    } while( --left && xd_la_in_range( bmx, bmy, minx, miny, maxx, maxy ) );
+                }
+
+                // ---- me.c:397-414
+                int qx = bmx << 2, qy = bmy << 2;
+                if( bmx == pmx && bmy == pmy )
+                    bcost += xd_la_bits( B, qx, qy );
+
+                // ---- refine_subpel( hpel_iters = 1, qpel_iters = 0 ) (me.c:466-587)
+                {
+                    const int px = xd_clip3( B.mvpx, sminx + 2, smaxx - 2 ), py = xd_clip3( B.mvpy, sminy + 2, smaxy - 2 );
+                    if( px != qx || py != qy )                       // me.c:483-490
+                    {
+                        const int s = xd_la_sad( B, px, py, lane ) + xd_la_bits( B, px, py );
+                        B.sad_evals++;
+                        if( s < bcost ) { bcost = s; qx = px; qy = py; }
+                    }
+                    // half-pel diamond (me.c:492-517)
+                    const int hx = qx + ( cand == 2 ? -2 : cand == 3 ? 2 : 0 );
+                    const int hy = qy + ( cand == 0 ? -2 : cand == 1 ? 2 : 0 );
+                    const int s = xd_la_sad( B, hx, hy, lane ) + xd_la_bits( B, hx, hy );
+                    const int key = xd_la_min4( ( s << 2 ) | cand );
+                    B.sad_evals += 4;
+                    if( ( key >> 2 ) < bcost )
+                    {
+                        const int w = key & 3;
+                        qx += w == 2 ? -2 : w == 3 ? 2 : 0;
+                        qy += w == 0 ? -2 : w == 1 ? 2 : 0;
+                    }
+                    // me.c:519-524: the winner is re-costed with SATD
+                    bcost = xd_la_satd( B, qx, qy, lane ) + xd_la_bits( B, qx, qy );
+                    B.satd_evals++;
+                }
+                mvx = qx; mvy = qy;
+                cost = bcost - 1;                                    // slicetype.c:128-130
+                if( mvx | mvy )
+                    cost += 5;
+            }
+
+            // publish, then account (slicetype.c:132-196)
+            const uint32_t mv_packed = ( (uint32_t)mvx & 0xFFFF ) | ( (uint32_t)mvy << 16 );
+            const int xy = by * W + bx;
+            if( lane == 0 )
+            {
+                xd_st_sync( sync_row + bx, ( (unsigned long long)A.epoch << 32 ) | mv_packed );
+                *(uint32_t *)( A.mvs + ( (size_t)pair * g.mb_count + xy ) * 2 ) = mv_packed;
+                A.costs[(size_t)pair * g.mb_count + xy] = cost;
+            }
+            int bcost_blk = cost + 4;
+            if( want_intra )
+            {
+                const int ic = A.icost[(size_t)pair * g.mb_count + xy];
+                if( ic < bcost_blk )
+                {
+                    bcost_blk = ic;
+                    row_intra++;
+                }
+            }
+            row_sum += bcost_blk;
+
+            mv_right = mv_packed;
+            mv_br = mv_b;
+            mv_b = mv_bl;
+        }
+
+        if( lane == 0 )
+        {
+            int32_t *s = A.sums + (size_t)pair * X264DSP_LA_SUMS;
+            atomicAdd( &s[X264DSP_LA_COST_INTER], row_sum );
+            atomicAdd( &s[X264DSP_LA_INTRA_MBS], row_intra );
+            atomicAdd( &s[X264DSP_LA_SAD_EVALS], B.sad_evals );
+            atomicAdd( &s[X264DSP_LA_SATD_EVALS], B.satd_evals );
+            if( A.row_satds )
+                A.row_satds[(size_t)pair * 2 * H + by] = row_sum;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots, int n_pairs,
+                         const int32_t *b_dev, const int32_t *p0_dev, const uint8_t *wi_dev,
+                         const int32_t *inter_list_dev, int n_inter,
+                         int16_t *mvs, int32_t *costs, int32_t *sums, int32_t *row_satds, cudaStream_t s )
+{
+    const size_t blocks = (size_t)n_pairs * g->mb_count;
+    if( ctx->la_sync_cap < blocks * sizeof( unsigned long long ) )
+    {
+        int rc = xd_reserve_dev( (void **)&ctx->la_sync, &ctx->la_sync_cap, blocks * sizeof( unsigned long long ) );
+        if( rc )
+            return rc;
+        XD_CHECK( cudaMemsetAsync( ctx->la_sync, 0, ctx->la_sync_cap, s ) );
+        ctx->la_epoch = 0;
+    }
+    int rc = xd_reserve_dev( (void **)&ctx->la_icost, &ctx->la_icost_cap, blocks * sizeof( int32_t ) );
+    if( rc )
+        return rc;
+    if( ++ctx->la_epoch == 0 )
+    {
+        XD_CHECK( cudaMemsetAsync( ctx->la_sync, 0, ctx->la_sync_cap, s ) );
+        ctx->la_epoch = 1;
+    }
+
+    XD_CHECK( cudaMemsetAsync( mvs, 0, blocks * 2 * sizeof( int16_t ), s ) );
+    XD_CHECK( cudaMemsetAsync( costs, 0, blocks * sizeof( int32_t ), s ) );
+    XD_CHECK( cudaMemsetAsync( sums, 0, (size_t)n_pairs * X264DSP_LA_SUMS * sizeof( int32_t ), s ) );
+    if( row_satds )
+        XD_CHECK( cudaMemsetAsync( row_satds, 0, (size_t)n_pairs * 2 * g->mb_h * sizeof( int32_t ), s ) );
+    XD_CHECK( cudaMemsetAsync( ctx->la_ticket, 0, sizeof( int32_t ), s ) );
+
+    xd_la_args A;
+    A.g = *g;
+    A.slots = slots;
+    A.b = b_dev; A.p0 = p0_dev; A.want_intra = wi_dev;
+    A.n_pairs = n_pairs;
+    A.mvs = mvs; A.costs = costs; A.sums = sums; A.row_satds = row_satds;
+    A.cost_mv = ctx->cost_mv_dev[X264DSP_LOOKAHEAD_QP] + 4096;
+    A.sync = ctx->la_sync;
+    A.icost = ctx->la_icost;
+    A.ticket = ctx->la_ticket;
+    A.epoch = ctx->la_epoch;
+    A.me_range = 16;                                 // x264_param_default: analyse.i_me_range
+
+    const int inner = ( g->mb_w - 2 ) * ( g->mb_h - 2 );
+    if( inner <= 0 )
+        return X264DSP_E_ARG;
+    dim3 igrid( ( inner + 127 ) / 128, n_pairs );
+    xd_la_intra_kernel<<<igrid, 128, 0, s>>>( A );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    if( n_inter > 0 )
+    {
+        const int total_rows = n_inter * ( g->mb_h - 2 );
+        int ctas = ( total_rows + LA_WARPS - 1 ) / LA_WARPS;
+        const int cap = ctx->sm_count * ( 2048 / ( LA_WARPS * 32 ) );
+        if( ctas > cap )
+            ctas = cap;
+        xd_la_inter_kernel<<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list_dev );
+        ctx->launches++;
+        XD_CHECK( cudaGetLastError() );
+    }
+    return 0;
+}
+
+// pair descriptors live in a small device array owned by the context:
+// [b | p0 | inter list | want_intra bytes]
+static int xd_la_upload_desc( x264dsp_ctx_t *ctx, int n_pairs, const int32_t *b, const int32_t *p0,
+                              const uint8_t *want_intra, int *n_inter_out, cudaStream_t s,
+                              const int32_t **b_dev, const int32_t **p0_dev, const int32_t **list_dev,
+                              const uint8_t **wi_dev )
+{
+    const size_t words = (size_t)n_pairs * 3;
+    const size_t bytes = words * sizeof( int32_t ) + n_pairs;
+    int rc = xd_reserve_dev( (void **)&ctx->clip_desc, &ctx->clip_desc_cap, bytes );
+    if( rc )
+        return rc;
+    int32_t *host = (int32_t *)malloc( bytes );
+    if( !host )
+        return X264DSP_E_NOMEM;
+    int n_inter = 0;
+    for( int i = 0; i < n_pairs; i++ )
+    {
+        host[i] = b[i];
+        host[n_pairs + i] = p0[i];
+        if( p0[i] >= 0 )
+            host[2 * n_pairs + n_inter++] = i;
+    }
+    memcpy( host + words, want_intra, n_pairs );
+    cudaError_t e = cudaMemcpyAsync( ctx->clip_desc, host, bytes, cudaMemcpyHostToDevice, s );
+    if( e == cudaSuccess )
+        e = cudaStreamSynchronize( s );          // host staging buffer is pageable
+    free( host );
+    if( e != cudaSuccess )
+        return (int)e;
+    *n_inter_out = n_inter;
+    *b_dev = ctx->clip_desc;
+    *p0_dev = ctx->clip_desc + n_pairs;
+    *list_dev = ctx->clip_desc + 2 * n_pairs;
+    *wi_dev = (const uint8_t *)( ctx->clip_desc + words );
+    return 0;
+}
+
+// b / p0 / want_intra are HOST arrays here (they are a handful of integers describing the batch);
+// everything pixel- or result-sized is device memory.
+extern "C" int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots,
+                                                  int n_pairs, const int32_t *b, const int32_t *p0,
+                                                  const uint8_t *want_intra,
+                                                  int16_t *mvs, int32_t *costs, int32_t *sums, int32_t *row_satds,
+                                                  void *stream )
+{
+    if( !ctx || !g || !slots || n_pairs <= 0 || !b || !p0 || !want_intra || !mvs || !costs || !sums )
+        return X264DSP_E_ARG;
+    if( g->mb_w < 3 || g->mb_h < 3 )
+        return X264DSP_E_ARG;                        // do_edges would be forced on (slicetype.c:285)
+    cudaStream_t s = xd_stream( ctx, stream );
+    int n_inter = 0;
+    const int32_t *b_dev, *p0_dev, *list_dev;
+    const uint8_t *wi_dev;
+    int rc = xd_la_upload_desc( ctx, n_pairs, b, p0, want_intra, &n_inter, s, &b_dev, &p0_dev, &list_dev, &wi_dev );
+    if( rc )
+        return rc;
+    return xd_la_launch( ctx, g, slots, n_pairs, b_dev, p0_dev, wi_dev, list_dev, n_inter,
+                         mvs, costs, sums, row_satds, s );
+}
+
+int xd_frame_load_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma, uint8_t *slots,
+                        int n_frames, cudaStream_t s );
+
+extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames,
+                                             const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums )
+{
+    if( !ctx || !luma || !mvs || !costs || !sums || n_frames <= 0 )
+        return X264DSP_E_ARG;
+    x264dsp_geom_t g;
+    int rc = x264dsp_geometry( width, height, &g );
+    if( rc )
+        return rc;
+    if( g.mb_w < 3 || g.mb_h < 3 )
+        return X264DSP_E_ARG;
+    cudaStream_t s = ctx->stream;
+    const size_t pic = (size_t)width * height;
+    const size_t blocks = (size_t)n_frames * g.mb_count;
+    const size_t out_bytes = blocks * ( 2 * sizeof( int16_t ) + sizeof( int32_t ) )
+                           + (size_t)n_frames * X264DSP_LA_SUMS * sizeof( int32_t );
+
+    if( ( rc = xd_reserve_pinned( (void **)&ctx->stage_host, &ctx->stage_host_cap, pic * n_frames ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->stage_dev, &ctx->stage_dev_cap, pic * n_frames ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->clip_out, &ctx->clip_out_cap, out_bytes ) ) ) return rc;
+    if( ( rc = xd_reserve_pinned( (void **)&ctx->clip_out_host, &ctx->clip_out_host_cap, out_bytes ) ) ) return rc;
+    if( ctx->clip_slots_cap < (size_t)g.slot_bytes * n_frames )
+    {
+        if( ( rc = xd_reserve_dev( (void **)&ctx->clip_slots, &ctx->clip_slots_cap, (size_t)g.slot_bytes * n_frames ) ) )
+            return rc;
+        XD_CHECK( cudaMemsetAsync( ctx->clip_slots, 0, ctx->clip_slots_cap, s ) );
+    }
+
+    // host -> pinned -> device (the caller's buffer is ordinary memory)
+    memcpy( ctx->stage_host, luma, pic * n_frames );
+    XD_CHECK( cudaMemcpyAsync( ctx->stage_dev, ctx->stage_host, pic * n_frames, cudaMemcpyHostToDevice, s ) );
+    if( ( rc = xd_frame_load_luma( ctx, &g, ctx->stage_dev, ctx->clip_slots, n_frames, s ) ) ) return rc;
+    if( ( rc = x264dsp_frame_init_lowres_dev( ctx, &g, ctx->clip_slots, n_frames, s ) ) ) return rc;
+
+    int32_t *b = (int32_t *)malloc( (size_t)n_frames * ( 2 * sizeof( int32_t ) + 1 ) );
+    if( !b )
+        return X264DSP_E_NOMEM;
+    int32_t *p0 = b + n_frames;
+    uint8_t *wi = (uint8_t *)( p0 + n_frames );
+    for( int i = 0; i < n_frames; i++ )
+    {
+        b[i] = i;
+        p0[i] = i - 1;                               // frame 0: intra only
+        wi[i] = 1;
+    }
+    int16_t *d_mvs = (int16_t *)ctx->clip_out;
+    int32_t *d_costs = (int32_t *)( ctx->clip_out + blocks * 2 * sizeof( int16_t ) );
+    int32_t *d_sums = d_costs + blocks;
+    rc = x264dsp_lookahead_frame_cost_dev( ctx, &g, ctx->clip_slots, n_frames, b, p0, wi,
+                                           d_mvs, d_costs, d_sums, NULL, s );
+    free( b );
+    if( rc )
+        return rc;
+    XD_CHECK( cudaMemcpyAsync( ctx->clip_out_host, ctx->clip_out, out_bytes, cudaMemcpyDeviceToHost, s ) );
+    XD_CHECK( cudaStreamSynchronize( s ) );
+    memcpy( mvs, ctx->clip_out_host, blocks * 2 * sizeof( int16_t ) );
+    memcpy( costs, ctx->clip_out_host + blocks * 2 * sizeof( int16_t ), blocks * sizeof( int32_t ) );
+    memcpy( sums, ctx->clip_out_host + blocks * ( 2 * sizeof( int16_t ) + sizeof( int32_t ) ),
+            (size_t)n_frames * X264DSP_LA_SUMS * sizeof( int32_t ) );
+    return 0;
+}
