@@ -374,6 +374,10 @@ xd_filtered_border_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots )
         uint32_t v0 = v;
         if( tight && y <= -8 && x0 == -32 )
             v0 = base[(int64_t)( -7 ) * ls] * 0x01010101u;
+        // no alignment gap between the planes: the previous plane's last row tail (written last by
+        // the reference) lands on this plane's very first 8 bytes
+        if( tight && plane >= 2 && y == -32 && x0 == -32 && g.luma_plane_size == ls * ( h + 64 ) )
+            v0 = ( base - g.luma_plane_size )[(int64_t)( h + 7 ) * ls] * 0x01010101u;
         *(uint4 *)( drow + x0 ) = make_uint4( v0, v0, v, v );
     }
     else if( x0 >= w + 8 )
