@@ -105,6 +105,21 @@ int x264dsp_dev_zero( x264dsp_ctx_t *ctx, void *dev, size_t bytes, void *stream 
 int x264dsp_h2d( x264dsp_ctx_t *ctx, void *dev, const void *host, size_t bytes, void *stream );
 int x264dsp_d2h( x264dsp_ctx_t *ctx, void *host, const void *dev, size_t bytes, void *stream );
 
+/* pinned host memory: buffers obtained here are copied from / to directly by the *_host entry points */
+int x264dsp_host_alloc( x264dsp_ctx_t *ctx, size_t bytes, void **host );
+int x264dsp_host_free( x264dsp_ctx_t *ctx, void *host );
+
+/* per-kernel timing with CUDA events recorded around each launch on its own stream.
+ * kind: one of X264DSP_PROF_*; total_ms / count cover the launches since x264dsp_profile_enable. */
+enum
+{
+    X264DSP_PROF_LOAD = 0, X264DSP_PROF_LOWRES, X264DSP_PROF_LA_INTRA, X264DSP_PROF_LA_INTER, X264DSP_PROF_HPEL,
+    X264DSP_PROF_BORDER, X264DSP_PROF_COST, X264DSP_PROF_ME, X264DSP_PROF_MC, X264DSP_PROF_RESIDUAL,
+    X264DSP_PROF_DEBLOCK, X264DSP_PROF_KINDS
+};
+int x264dsp_profile_enable( x264dsp_ctx_t *ctx, int on );
+int x264dsp_profile_read( x264dsp_ctx_t *ctx, int kind, double *total_ms, int *count );
+
 /* ------------------------------------------------------------------ synthetic input
  * Seeded synthetic YUV 4:2:0: panning blurred-noise texture, two moving gradient
  * squares, +-2 noise, scene cut at `cut_frame` (<0: none).  Host code; writes planar I420. */
@@ -148,6 +163,7 @@ int x264dsp_cost_batch_dev( x264dsp_ctx_t *ctx, int cmp, int n,
  * x264_slicetype_frame_cost / x264_slicetype_mb_cost (encoder/slicetype.c:48-322) with the
  * reference's defaults (do_edges = 0, no B frames, lookahead QP 12, DIA + subme 2).
  *
+ * b / p0 / want_intra are small HOST arrays describing the batch; everything else is device memory.
  * pair p analyses frame slot b[p] against reference slot p0[p] (P frame, p1 == b).
  * p0[p] < 0 means intra only (the reference's frame_cost(b,b,b) call).
  * want_intra[p] != 0 also produces the intra estimate (first analysis of that frame,
@@ -174,10 +190,15 @@ int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *
                                       int16_t *mvs, int32_t *costs, int32_t *sums, int32_t *row_satds,
                                       void *stream );
 
-/* Whole lookahead pass of a clip from HOST memory: n_frames planar luma pictures (width*height
- * bytes each; chroma is not used by the lookahead) -> per-frame results in host arrays.
- * Frame 0 is analysed intra-only, frame i>0 against frame i-1.  This is the call bench.py times
- * end to end (H2D of the pictures and D2H of the results inside). */
+/* Whole lookahead pass from HOST memory: n_clips independent clips of clip_len planar luma pictures
+ * (width*height bytes each; chroma is not used by the lookahead) -> per-frame results in host
+ * arrays laid out like the _dev outputs ([frame][mb_count]...).  The first frame of every clip is
+ * analysed intra-only, every other frame against its predecessor.  This is the call bench.py
+ * times end to end (H2D of the pictures and D2H of the results inside).  Groups of clips run on
+ * separate streams so that copies and kernels overlap. */
+int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int height, int n_clips, int clip_len,
+                                  const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums );
+/* single clip: same as n_clips = 1 */
 int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames,
                                  const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums );
 

@@ -23,6 +23,8 @@ BLOCK_H = [16, 8, 16, 8, 4, 8, 4, 16]
 CMP_SAD, CMP_SSD, CMP_SATD = 0, 1, 2
 ME_DIA, ME_HEX = 0, 1
 LA_COST_INTER, LA_COST_INTRA, LA_INTRA_MBS, LA_SAD_EVALS, LA_SATD_EVALS, LA_SUMS = 0, 1, 2, 3, 4, 8
+(PROF_LOAD, PROF_LOWRES, PROF_LA_INTRA, PROF_LA_INTER, PROF_HPEL, PROF_BORDER, PROF_COST, PROF_ME, PROF_MC,
+ PROF_RESIDUAL, PROF_DEBLOCK) = range(11)
 RES_LEVELS_PER_MB = 16 * 16 + 2 * 4 + 2 * 4 * 16
 RES_NNZ_PER_MB = 16 + 8 + 3
 
@@ -151,6 +153,9 @@ class Context:
 
     def close(self):
         if self._h:
+            for p in getattr(self, "_pinned", []):
+                lib().x264dsp_host_free(self._h, p)
+            self._pinned = []
             lib().x264dsp_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -221,6 +226,40 @@ class Context:
                                                 _hp(mvs, C.c_int16), _hp(costs, C.c_int32),
                                                 _hp(sums, C.c_int32)), "x264dsp_lookahead_clip_host")
         return mvs, costs, sums
+
+    def lookahead_clips_host(self, width, height, n_clips, clip_len, luma, mvs=None, costs=None, sums=None):
+        """luma: uint8 numpy [n_clips*clip_len, height*width]; outputs are allocated unless given
+        (pass arrays created with `pinned_empty` to skip the staging copies)."""
+        g = geometry(width, height)
+        n = n_clips * clip_len
+        assert luma.dtype == np.uint8 and luma.size == n * width * height and luma.flags.c_contiguous
+        mvs = np.empty((n, g.mb_count, 2), np.int16) if mvs is None else mvs
+        costs = np.empty((n, g.mb_count), np.int32) if costs is None else costs
+        sums = np.empty((n, LA_SUMS), np.int32) if sums is None else sums
+        check(lib().x264dsp_lookahead_clips_host(self._h, int(width), int(height), int(n_clips), int(clip_len),
+                                                 _hp(luma), _hp(mvs, C.c_int16), _hp(costs, C.c_int32),
+                                                 _hp(sums, C.c_int32)), "x264dsp_lookahead_clips_host")
+        return mvs, costs, sums
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array backed by pinned host memory (x264dsp_host_alloc); freed with the context"""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        check(lib().x264dsp_host_alloc(self._h, C.c_size_t(max(nbytes, 1)), C.byref(p)), "x264dsp_host_alloc")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def profile_enable(self, on=True):
+        check(lib().x264dsp_profile_enable(self._h, int(on)), "x264dsp_profile_enable")
+
+    def profile_read(self, kind):
+        """(total_ms, launches) of kernel class `kind` (PROF_*) since profile_enable"""
+        ms, n = C.c_double(), C.c_int()
+        check(lib().x264dsp_profile_read(self._h, int(kind), C.byref(ms), C.byref(n)), "x264dsp_profile_read")
+        return ms.value, n.value
 
     # ---- motion search -------------------------------------------------------------------
     def me_search_batch(self, g, fenc_slot, fref_slot, params, n, blocks_dev, results_dev):

@@ -6,6 +6,11 @@
 #include <stdio.h>
 #include "../../include/x264dsp_b200.h"
 
+// kernel classes for x264dsp_profile_read
+enum { XD_PROF_LOAD = 0, XD_PROF_LOWRES, XD_PROF_LA_INTRA, XD_PROF_LA_INTER, XD_PROF_HPEL, XD_PROF_BORDER,
+       XD_PROF_COST, XD_PROF_ME, XD_PROF_MC, XD_PROF_RESIDUAL, XD_PROF_DEBLOCK, XD_PROF_KINDS };
+#define XD_PROF_MAX 512
+
 // ---------------------------------------------------------------------------------------------
 // context: one per process/GPU.  Owns the stream, the constant tables in HBM and the scratch
 // buffers of the batched entry points.
@@ -36,6 +41,14 @@ struct x264dsp_ctx
     uint8_t *clip_out_host; size_t clip_out_host_cap; // pinned results
     int32_t *clip_desc;   size_t clip_desc_cap;
 
+    // extra streams so that independent groups of a host-level batch overlap copies and kernels
+    cudaStream_t aux[4];
+
+    // optional per-kernel timing with CUDA events (x264dsp_profile_*)
+    int prof_on;
+    int prof_n[XD_PROF_KINDS];
+    cudaEvent_t prof_ev[XD_PROF_KINDS][XD_PROF_MAX][2];
+
     // per-call table shims (tables.cu)
     uint8_t *shim_host;   // pinned
     uint8_t *shim_dev;
@@ -52,6 +65,26 @@ struct x264dsp_ctx
 static inline cudaStream_t xd_stream( x264dsp_ctx *ctx, void *stream )
 {
     return stream ? (cudaStream_t)stream : ctx->stream;
+}
+
+// event pair around one launch when profiling is on; returns the slot or -1
+static inline int xd_prof_begin( x264dsp_ctx *ctx, int kind, cudaStream_t s )
+{
+    if( !ctx->prof_on || ctx->prof_n[kind] >= XD_PROF_MAX )
+        return -1;
+    const int i = ctx->prof_n[kind]++;
+    if( !ctx->prof_ev[kind][i][0] )
+    {
+        cudaEventCreate( &ctx->prof_ev[kind][i][0] );
+        cudaEventCreate( &ctx->prof_ev[kind][i][1] );
+    }
+    cudaEventRecord( ctx->prof_ev[kind][i][0], s );
+    return i;
+}
+static inline void xd_prof_end( x264dsp_ctx *ctx, int kind, int slot, cudaStream_t s )
+{
+    if( slot >= 0 )
+        cudaEventRecord( ctx->prof_ev[kind][slot][1], s );
 }
 
 // grows a device buffer to at least `bytes`

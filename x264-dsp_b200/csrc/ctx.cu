@@ -195,6 +195,8 @@ extern "C" int x264dsp_create( int device, x264dsp_ctx_t **out )
     XD_CHECK( cudaGetDeviceProperties( &prop, device ) );
     ctx->sm_count = prop.multiProcessorCount;
     XD_CHECK( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
+    for( int i = 0; i < 4; i++ )
+        XD_CHECK( cudaStreamCreateWithFlags( &ctx->aux[i], cudaStreamNonBlocking ) );
 
     // one cost table per distinct lambda, shared between the QPs that map to it
     {
@@ -250,6 +252,15 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     if( ctx->stage_host ) cudaFreeHost( ctx->stage_host );
     if( ctx->clip_out_host ) cudaFreeHost( ctx->clip_out_host );
     if( ctx->shim_host ) cudaFreeHost( ctx->shim_host );
+    for( int k = 0; k < XD_PROF_KINDS; k++ )
+        for( int i = 0; i < XD_PROF_MAX; i++ )
+            if( ctx->prof_ev[k][i][0] )
+            {
+                cudaEventDestroy( ctx->prof_ev[k][i][0] );
+                cudaEventDestroy( ctx->prof_ev[k][i][1] );
+            }
+    for( int i = 0; i < 4; i++ )
+        cudaStreamDestroy( ctx->aux[i] );
     cudaStreamDestroy( ctx->stream );
     free( ctx );
 }
@@ -307,5 +318,51 @@ extern "C" int x264dsp_d2h( x264dsp_ctx_t *ctx, void *host, const void *dev, siz
     cudaStream_t s = xd_stream( ctx, stream );
     XD_CHECK( cudaMemcpyAsync( host, dev, bytes, cudaMemcpyDeviceToHost, s ) );
     XD_CHECK( cudaStreamSynchronize( s ) );
+    return 0;
+}
+
+// pinned host memory for callers that want the host entry points to copy straight from / to it
+extern "C" int x264dsp_host_alloc( x264dsp_ctx_t *ctx, size_t bytes, void **host )
+{
+    if( !ctx || !host )
+        return X264DSP_E_ARG;
+    XD_CHECK( cudaHostAlloc( host, bytes, cudaHostAllocDefault ) );
+    return 0;
+}
+
+extern "C" int x264dsp_host_free( x264dsp_ctx_t *ctx, void *host )
+{
+    if( !ctx )
+        return X264DSP_E_ARG;
+    XD_CHECK( cudaFreeHost( host ) );
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ profiling
+
+extern "C" int x264dsp_profile_enable( x264dsp_ctx_t *ctx, int on )
+{
+    if( !ctx )
+        return X264DSP_E_ARG;
+    ctx->prof_on = on != 0;
+    for( int k = 0; k < XD_PROF_KINDS; k++ )
+        ctx->prof_n[k] = 0;
+    return 0;
+}
+
+extern "C" int x264dsp_profile_read( x264dsp_ctx_t *ctx, int kind, double *total_ms, int *count )
+{
+    if( !ctx || kind < 0 || kind >= XD_PROF_KINDS || !total_ms || !count )
+        return X264DSP_E_ARG;
+    XD_CHECK( cudaDeviceSynchronize() );
+    double acc = 0;
+    for( int i = 0; i < ctx->prof_n[kind]; i++ )
+    {
+        float ms = 0;
+        XD_CHECK( cudaEventElapsedTime( &ms, ctx->prof_ev[kind][i][0], ctx->prof_ev[kind][i][1] ) );
+        acc += ms;
+    }
+    *total_ms = acc;
+    *count = ctx->prof_n[kind];
     return 0;
 }

@@ -121,11 +121,11 @@ struct xd_border_job
     int32_t stride, w, h, padh, padv, unit;
 };
 
-__device__ __forceinline__ uint4 xd_border_chunk( const uint8_t *row, int x0, int w, int unit )
+__device__ __forceinline__ uint2 xd_border_chunk( const uint8_t *row, int x0, int w, int unit )
 {
-    // 16 bytes starting at column x0 (multiple of 16) of a row whose picture part is [0,w)
-    if( x0 >= 0 && x0 + 16 <= w )
-        return *(const uint4 *)( row + x0 );
+    // 8 bytes starting at column x0 (multiple of 8) of a row whose picture part is [0,w)
+    if( x0 >= 0 && x0 + 8 <= w )
+        return *(const uint2 *)( row + x0 );
     uint32_t a, b;
     if( x0 < 0 )
     {
@@ -138,17 +138,18 @@ __device__ __forceinline__ uint4 xd_border_chunk( const uint8_t *row, int x0, in
         b = row[w - 1];
     }
     const uint32_t v = ( a | ( b << 8 ) ) * 0x00010001u;
-    return make_uint4( v, v, v, v );
+    return make_uint2( v, v );
 }
 
+// 8-byte granularity: lowres widths are multiples of 8, not of 16
 __global__ void __launch_bounds__( 256 )
 xd_expand_border_kernel( xd_border_job job, uint8_t *__restrict__ slots, int64_t slot_bytes, int n_planes,
                          int64_t plane_pitch )
 {
     uint8_t *base = slots + ( blockIdx.z / n_planes ) * slot_bytes + ( blockIdx.z % n_planes ) * plane_pitch
                   + job.plane_off;
-    const int side_chunks = job.padh >> 4;                          // per side
-    const int row_chunks = ( job.w + 2 * job.padh ) >> 4;
+    const int side_chunks = job.padh >> 3;                          // per side
+    const int row_chunks = ( job.w + 2 * job.padh ) >> 3;
     const int n_side = job.h * 2 * side_chunks;
     const int n_total = n_side + 2 * job.padv * row_chunks;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,18 +160,18 @@ xd_expand_border_kernel( xd_border_job job, uint8_t *__restrict__ slots, int64_t
     {
         y = i / ( 2 * side_chunks );
         const int c = i % ( 2 * side_chunks );
-        x0 = c < side_chunks ? -job.padh + 16 * c : job.w + 16 * ( c - side_chunks );
+        x0 = c < side_chunks ? -job.padh + 8 * c : job.w + 8 * ( c - side_chunks );
     }
     else
     {
         const int j = i - n_side;
         const int r = j / row_chunks;
         y = r < job.padv ? r - job.padv : job.h + ( r - job.padv );
-        x0 = -job.padh + 16 * ( j % row_chunks );
+        x0 = -job.padh + 8 * ( j % row_chunks );
     }
     const int ys = min( max( y, 0 ), job.h - 1 );
-    const uint4 v = xd_border_chunk( base + (int64_t)ys * job.stride, x0, job.w, job.unit );
-    *(uint4 *)( base + (int64_t)y * job.stride + x0 ) = v;
+    const uint2 v = xd_border_chunk( base + (int64_t)ys * job.stride, x0, job.w, job.unit );
+    *(uint2 *)( base + (int64_t)y * job.stride + x0 ) = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,7 +409,10 @@ extern "C" int x264dsp_frame_load_i420_dev( x264dsp_ctx_t *ctx, const x264dsp_ge
     if( !ctx || !g || !i420 || !slots || n_frames <= 0 )
         return X264DSP_E_ARG;
     dim3 grid( ( ( g->luma_w >> 4 ) + 255 ) / 256, g->luma_h + g->chroma_h, n_frames );
-    xd_load_i420_kernel<<<grid, 256, 0, xd_stream( ctx, stream )>>>( *g, i420, slots );
+    cudaStream_t s = xd_stream( ctx, stream );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_LOAD, s );
+    xd_load_i420_kernel<<<grid, 256, 0, s>>>( *g, i420, slots );
+    xd_prof_end( ctx, XD_PROF_LOAD, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
@@ -418,7 +422,9 @@ int xd_frame_load_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8
                         int n_frames, cudaStream_t s )
 {
     dim3 grid( ( ( g->luma_w >> 4 ) + 255 ) / 256, g->luma_h, n_frames );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_LOAD, s );
     xd_load_luma_kernel<<<grid, 256, 0, s>>>( *g, luma, slots );
+    xd_prof_end( ctx, XD_PROF_LOAD, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
@@ -427,10 +433,12 @@ int xd_frame_load_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8
 static int xd_launch_border( x264dsp_ctx_t *ctx, const xd_border_job &job, uint8_t *slots, int64_t slot_bytes,
                              int n_frames, int n_planes, int64_t plane_pitch, cudaStream_t s )
 {
-    const int side_chunks = job.padh >> 4, row_chunks = ( job.w + 2 * job.padh ) >> 4;
+    const int side_chunks = job.padh >> 3, row_chunks = ( job.w + 2 * job.padh ) >> 3;
     const int n_total = job.h * 2 * side_chunks + 2 * job.padv * row_chunks;
     dim3 grid( ( n_total + 255 ) / 256, 1, n_frames * n_planes );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_BORDER, s );
     xd_expand_border_kernel<<<grid, 256, 0, s>>>( job, slots, slot_bytes, n_planes, plane_pitch );
+    xd_prof_end( ctx, XD_PROF_BORDER, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
@@ -458,7 +466,9 @@ extern "C" int x264dsp_frame_init_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_
         return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
     dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h, n_frames );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_LOWRES, s );
     xd_lowres_kernel<<<grid, 128, 0, s>>>( *g, slots );
+    xd_prof_end( ctx, XD_PROF_LOWRES, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     xd_border_job lowres = { (int64_t)g->slot_lowres_off + g->lowres_origin, g->lowres_stride, g->lowres_w,
@@ -473,7 +483,9 @@ extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_
         return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
     dim3 grid( ( g->luma_w + 8 + HP_TW - 1 ) / HP_TW, ( g->luma_h + 16 + HP_TH - 1 ) / HP_TH, n_frames );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_HPEL, s );
     xd_hpel_kernel<<<grid, 256, 0, s>>>( *g, slots );
+    xd_prof_end( ctx, XD_PROF_HPEL, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     const int n_total = ( g->luma_h + 16 ) * 5 + 48 * ( ( ( g->luma_w + 64 ) >> 4 ) + 1 );

@@ -31,7 +31,7 @@ struct xd_la_args
     const uint8_t *slots;
     const int32_t *b, *p0;
     const uint8_t *want_intra;
-    int n_pairs;
+    int n_pairs, pair0;
     int16_t *mvs;
     int32_t *costs, *sums, *row_satds;
     const uint16_t *cost_mv;            // centre of the lambda=1 table
@@ -82,7 +82,7 @@ __device__ __forceinline__ int xd_satd4x4_words( const uint32_t a[4], const uint
 __global__ void __launch_bounds__( 128 )
 xd_la_intra_kernel( xd_la_args A )
 {
-    const int pair = blockIdx.y;
+    const int pair = A.pair0 + blockIdx.y;
     if( !A.want_intra[pair] )
         return;
     const x264dsp_geom_t &g = A.g;
@@ -558,55 +558,72 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 }
 
 // ---------------------------------------------------------------------------------------------
+// host side
 
-static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots, int n_pairs,
-                         const int32_t *b_dev, const int32_t *p0_dev, const uint8_t *wi_dev,
-                         const int32_t *inter_list_dev, int n_inter,
-                         int16_t *mvs, int32_t *costs, int32_t *sums, int32_t *row_satds, cudaStream_t s )
+// scratch for `n_pairs` pairs; called once per batch before any group is launched
+static int xd_la_prepare( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, int n_pairs, cudaStream_t s )
 {
     const size_t blocks = (size_t)n_pairs * g->mb_count;
     if( ctx->la_sync_cap < blocks * sizeof( unsigned long long ) )
     {
+        XD_CHECK( cudaDeviceSynchronize() );
         int rc = xd_reserve_dev( (void **)&ctx->la_sync, &ctx->la_sync_cap, blocks * sizeof( unsigned long long ) );
         if( rc )
             return rc;
         XD_CHECK( cudaMemsetAsync( ctx->la_sync, 0, ctx->la_sync_cap, s ) );
+        XD_CHECK( cudaStreamSynchronize( s ) );
         ctx->la_epoch = 0;
     }
-    int rc = xd_reserve_dev( (void **)&ctx->la_icost, &ctx->la_icost_cap, blocks * sizeof( int32_t ) );
-    if( rc )
-        return rc;
+    if( ctx->la_icost_cap < blocks * sizeof( int32_t ) )
+    {
+        XD_CHECK( cudaDeviceSynchronize() );
+        int rc = xd_reserve_dev( (void **)&ctx->la_icost, &ctx->la_icost_cap, blocks * sizeof( int32_t ) );
+        if( rc )
+            return rc;
+    }
     if( ++ctx->la_epoch == 0 )
     {
         XD_CHECK( cudaMemsetAsync( ctx->la_sync, 0, ctx->la_sync_cap, s ) );
+        XD_CHECK( cudaStreamSynchronize( s ) );
         ctx->la_epoch = 1;
     }
+    return 0;
+}
 
-    XD_CHECK( cudaMemsetAsync( mvs, 0, blocks * 2 * sizeof( int16_t ), s ) );
-    XD_CHECK( cudaMemsetAsync( costs, 0, blocks * sizeof( int32_t ), s ) );
-    XD_CHECK( cudaMemsetAsync( sums, 0, (size_t)n_pairs * X264DSP_LA_SUMS * sizeof( int32_t ), s ) );
+// analyses pairs [pair0, pair0+count) on stream s; `inter_list` holds the global indices of the
+// pairs of that range that have a reference frame; `slot` selects one of the ticket counters
+static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots,
+                         int pair0, int count, const int32_t *b_dev, const int32_t *p0_dev, const uint8_t *wi_dev,
+                         const int32_t *inter_list, int n_inter, int ticket_slot,
+                         int16_t *mvs, int32_t *costs, int32_t *sums, int32_t *row_satds, cudaStream_t s )
+{
+    const size_t mbc = g->mb_count;
+    XD_CHECK( cudaMemsetAsync( mvs + (size_t)pair0 * mbc * 2, 0, (size_t)count * mbc * 2 * sizeof( int16_t ), s ) );
+    XD_CHECK( cudaMemsetAsync( costs + (size_t)pair0 * mbc, 0, (size_t)count * mbc * sizeof( int32_t ), s ) );
+    XD_CHECK( cudaMemsetAsync( sums + (size_t)pair0 * X264DSP_LA_SUMS, 0, (size_t)count * X264DSP_LA_SUMS * sizeof( int32_t ), s ) );
     if( row_satds )
-        XD_CHECK( cudaMemsetAsync( row_satds, 0, (size_t)n_pairs * 2 * g->mb_h * sizeof( int32_t ), s ) );
-    XD_CHECK( cudaMemsetAsync( ctx->la_ticket, 0, sizeof( int32_t ), s ) );
+        XD_CHECK( cudaMemsetAsync( row_satds + (size_t)pair0 * 2 * g->mb_h, 0, (size_t)count * 2 * g->mb_h * sizeof( int32_t ), s ) );
+    XD_CHECK( cudaMemsetAsync( ctx->la_ticket + ticket_slot, 0, sizeof( int32_t ), s ) );
 
     xd_la_args A;
     A.g = *g;
     A.slots = slots;
     A.b = b_dev; A.p0 = p0_dev; A.want_intra = wi_dev;
-    A.n_pairs = n_pairs;
+    A.n_pairs = count;
+    A.pair0 = pair0;
     A.mvs = mvs; A.costs = costs; A.sums = sums; A.row_satds = row_satds;
     A.cost_mv = ctx->cost_mv_dev[X264DSP_LOOKAHEAD_QP] + 4096;
     A.sync = ctx->la_sync;
     A.icost = ctx->la_icost;
-    A.ticket = ctx->la_ticket;
+    A.ticket = ctx->la_ticket + ticket_slot;
     A.epoch = ctx->la_epoch;
     A.me_range = 16;                                 // x264_param_default: analyse.i_me_range
 
     const int inner = ( g->mb_w - 2 ) * ( g->mb_h - 2 );
-    if( inner <= 0 )
-        return X264DSP_E_ARG;
-    dim3 igrid( ( inner + 127 ) / 128, n_pairs );
+    dim3 igrid( ( inner + 127 ) / 128, count );
+    int pslot = xd_prof_begin( ctx, XD_PROF_LA_INTRA, s );
     xd_la_intra_kernel<<<igrid, 128, 0, s>>>( A );
+    xd_prof_end( ctx, XD_PROF_LA_INTRA, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     if( n_inter > 0 )
@@ -616,7 +633,9 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         const int cap = ctx->sm_count * ( 2048 / ( LA_WARPS * 32 ) );
         if( ctas > cap )
             ctas = cap;
-        xd_la_inter_kernel<<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list_dev );
+        pslot = xd_prof_begin( ctx, XD_PROF_LA_INTER, s );
+        xd_la_inter_kernel<<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
+        xd_prof_end( ctx, XD_PROF_LA_INTER, pslot, s );
         ctx->launches++;
         XD_CHECK( cudaGetLastError() );
     }
@@ -624,7 +643,7 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
 }
 
 // pair descriptors live in a small device array owned by the context:
-// [b | p0 | inter list | want_intra bytes]
+// [b | p0 | inter list | want_intra bytes].  inter_pos[i] = number of inter pairs before pair i.
 static int xd_la_upload_desc( x264dsp_ctx_t *ctx, int n_pairs, const int32_t *b, const int32_t *p0,
                               const uint8_t *want_intra, int *n_inter_out, cudaStream_t s,
                               const int32_t **b_dev, const int32_t **p0_dev, const int32_t **list_dev,
@@ -632,6 +651,8 @@ static int xd_la_upload_desc( x264dsp_ctx_t *ctx, int n_pairs, const int32_t *b,
 {
     const size_t words = (size_t)n_pairs * 3;
     const size_t bytes = words * sizeof( int32_t ) + n_pairs;
+    if( ctx->clip_desc_cap < bytes )
+        XD_CHECK( cudaDeviceSynchronize() );
     int rc = xd_reserve_dev( (void **)&ctx->clip_desc, &ctx->clip_desc_cap, bytes );
     if( rc )
         return rc;
@@ -661,8 +682,8 @@ static int xd_la_upload_desc( x264dsp_ctx_t *ctx, int n_pairs, const int32_t *b,
     return 0;
 }
 
-// b / p0 / want_intra are HOST arrays here (they are a handful of integers describing the batch);
-// everything pixel- or result-sized is device memory.
+// b / p0 / want_intra are HOST arrays (a handful of integers describing the batch); everything
+// pixel- or result-sized is device memory.
 extern "C" int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots,
                                                   int n_pairs, const int32_t *b, const int32_t *p0,
                                                   const uint8_t *want_intra,
@@ -680,17 +701,35 @@ extern "C" int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264d
     int rc = xd_la_upload_desc( ctx, n_pairs, b, p0, want_intra, &n_inter, s, &b_dev, &p0_dev, &list_dev, &wi_dev );
     if( rc )
         return rc;
-    return xd_la_launch( ctx, g, slots, n_pairs, b_dev, p0_dev, wi_dev, list_dev, n_inter,
+    if( ( rc = xd_la_prepare( ctx, g, n_pairs, s ) ) )
+        return rc;
+    return xd_la_launch( ctx, g, slots, 0, n_pairs, b_dev, p0_dev, wi_dev, list_dev, n_inter, 0,
                          mvs, costs, sums, row_satds, s );
 }
 
 int xd_frame_load_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma, uint8_t *slots,
                         int n_frames, cudaStream_t s );
 
-extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames,
-                                             const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums )
+static bool xd_is_pinned( const void *p )
 {
-    if( !ctx || !luma || !mvs || !costs || !sums || n_frames <= 0 )
+    cudaPointerAttributes attr;
+    if( cudaPointerGetAttributes( &attr, p ) != cudaSuccess )
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// Lookahead pass of n_clips independent clips of clip_len frames each, from HOST memory.
+// The batch is cut into up to four groups of whole clips; each group runs on its own stream
+// (H2D copy -> staging kernel -> lowres planes -> intra + inter cost kernels -> D2H), so that one
+// group's copies overlap another group's kernels.  Pinned caller buffers (x264dsp_host_alloc) are
+// copied from / to directly; ordinary memory goes through the context's pinned staging area.
+extern "C" int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int height, int n_clips, int clip_len,
+                                              const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums )
+{
+    if( !ctx || !luma || !mvs || !costs || !sums || n_clips <= 0 || clip_len <= 0 )
         return X264DSP_E_ARG;
     x264dsp_geom_t g;
     int rc = x264dsp_geometry( width, height, &g );
@@ -698,29 +737,32 @@ extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int h
         return rc;
     if( g.mb_w < 3 || g.mb_h < 3 )
         return X264DSP_E_ARG;
-    cudaStream_t s = ctx->stream;
+    const int n_frames = n_clips * clip_len;
     const size_t pic = (size_t)width * height;
-    const size_t blocks = (size_t)n_frames * g.mb_count;
-    const size_t out_bytes = blocks * ( 2 * sizeof( int16_t ) + sizeof( int32_t ) )
-                           + (size_t)n_frames * X264DSP_LA_SUMS * sizeof( int32_t );
+    const size_t mbc = g.mb_count;
+    const size_t blocks = (size_t)n_frames * mbc;
+    const size_t mv_bytes = blocks * 2 * sizeof( int16_t ), cost_bytes = blocks * sizeof( int32_t );
+    const size_t sum_bytes = (size_t)n_frames * X264DSP_LA_SUMS * sizeof( int32_t );
+    const size_t out_bytes = mv_bytes + cost_bytes + sum_bytes;
+    const bool pinned_in = xd_is_pinned( luma );
+    const bool pinned_out = xd_is_pinned( mvs ) && xd_is_pinned( costs ) && xd_is_pinned( sums );
 
-    if( ( rc = xd_reserve_pinned( (void **)&ctx->stage_host, &ctx->stage_host_cap, pic * n_frames ) ) ) return rc;
+    if( ctx->stage_dev_cap < pic * n_frames || ctx->clip_out_cap < out_bytes
+        || ctx->clip_slots_cap < (size_t)g.slot_bytes * n_frames )
+        XD_CHECK( cudaDeviceSynchronize() );
+    if( !pinned_in && ( rc = xd_reserve_pinned( (void **)&ctx->stage_host, &ctx->stage_host_cap, pic * n_frames ) ) ) return rc;
     if( ( rc = xd_reserve_dev( (void **)&ctx->stage_dev, &ctx->stage_dev_cap, pic * n_frames ) ) ) return rc;
     if( ( rc = xd_reserve_dev( (void **)&ctx->clip_out, &ctx->clip_out_cap, out_bytes ) ) ) return rc;
-    if( ( rc = xd_reserve_pinned( (void **)&ctx->clip_out_host, &ctx->clip_out_host_cap, out_bytes ) ) ) return rc;
+    if( !pinned_out && ( rc = xd_reserve_pinned( (void **)&ctx->clip_out_host, &ctx->clip_out_host_cap, out_bytes ) ) ) return rc;
     if( ctx->clip_slots_cap < (size_t)g.slot_bytes * n_frames )
     {
         if( ( rc = xd_reserve_dev( (void **)&ctx->clip_slots, &ctx->clip_slots_cap, (size_t)g.slot_bytes * n_frames ) ) )
             return rc;
-        XD_CHECK( cudaMemsetAsync( ctx->clip_slots, 0, ctx->clip_slots_cap, s ) );
+        XD_CHECK( cudaMemsetAsync( ctx->clip_slots, 0, ctx->clip_slots_cap, ctx->stream ) );
+        XD_CHECK( cudaStreamSynchronize( ctx->stream ) );
     }
 
-    // host -> pinned -> device (the caller's buffer is ordinary memory)
-    memcpy( ctx->stage_host, luma, pic * n_frames );
-    XD_CHECK( cudaMemcpyAsync( ctx->stage_dev, ctx->stage_host, pic * n_frames, cudaMemcpyHostToDevice, s ) );
-    if( ( rc = xd_frame_load_luma( ctx, &g, ctx->stage_dev, ctx->clip_slots, n_frames, s ) ) ) return rc;
-    if( ( rc = x264dsp_frame_init_lowres_dev( ctx, &g, ctx->clip_slots, n_frames, s ) ) ) return rc;
-
+    // batch description: frame i is analysed against frame i-1 unless it opens a clip
     int32_t *b = (int32_t *)malloc( (size_t)n_frames * ( 2 * sizeof( int32_t ) + 1 ) );
     if( !b )
         return X264DSP_E_NOMEM;
@@ -729,22 +771,69 @@ extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int h
     for( int i = 0; i < n_frames; i++ )
     {
         b[i] = i;
-        p0[i] = i - 1;                               // frame 0: intra only
+        p0[i] = ( i % clip_len ) ? i - 1 : -1;
         wi[i] = 1;
     }
-    int16_t *d_mvs = (int16_t *)ctx->clip_out;
-    int32_t *d_costs = (int32_t *)( ctx->clip_out + blocks * 2 * sizeof( int16_t ) );
-    int32_t *d_sums = d_costs + blocks;
-    rc = x264dsp_lookahead_frame_cost_dev( ctx, &g, ctx->clip_slots, n_frames, b, p0, wi,
-                                           d_mvs, d_costs, d_sums, NULL, s );
+    int n_inter = 0;
+    const int32_t *b_dev, *p0_dev, *list_dev;
+    const uint8_t *wi_dev;
+    rc = xd_la_upload_desc( ctx, n_frames, b, p0, wi, &n_inter, ctx->stream, &b_dev, &p0_dev, &list_dev, &wi_dev );
     free( b );
     if( rc )
         return rc;
-    XD_CHECK( cudaMemcpyAsync( ctx->clip_out_host, ctx->clip_out, out_bytes, cudaMemcpyDeviceToHost, s ) );
-    XD_CHECK( cudaStreamSynchronize( s ) );
-    memcpy( mvs, ctx->clip_out_host, blocks * 2 * sizeof( int16_t ) );
-    memcpy( costs, ctx->clip_out_host + blocks * 2 * sizeof( int16_t ), blocks * sizeof( int32_t ) );
-    memcpy( sums, ctx->clip_out_host + blocks * ( 2 * sizeof( int16_t ) + sizeof( int32_t ) ),
-            (size_t)n_frames * X264DSP_LA_SUMS * sizeof( int32_t ) );
+    if( ( rc = xd_la_prepare( ctx, &g, n_frames, ctx->stream ) ) )
+        return rc;
+
+    int16_t *d_mvs = (int16_t *)ctx->clip_out;
+    int32_t *d_costs = (int32_t *)( ctx->clip_out + mv_bytes );
+    int32_t *d_sums = (int32_t *)( ctx->clip_out + mv_bytes + cost_bytes );
+    uint8_t *h_out = ctx->clip_out_host;
+
+    const int groups = n_clips < 4 ? n_clips : 4;
+    for( int gi = 0; gi < groups; gi++ )
+    {
+        cudaStream_t s = ctx->aux[gi];
+        const int c0 = (int)( (int64_t)n_clips * gi / groups ), c1 = (int)( (int64_t)n_clips * ( gi + 1 ) / groups );
+        const int f0 = c0 * clip_len, nf = ( c1 - c0 ) * clip_len;
+        if( nf <= 0 )
+            continue;
+        const uint8_t *src = luma + (size_t)f0 * pic;
+        if( !pinned_in )
+        {
+            memcpy( ctx->stage_host + (size_t)f0 * pic, src, pic * nf );
+            src = ctx->stage_host + (size_t)f0 * pic;
+        }
+        XD_CHECK( cudaMemcpyAsync( ctx->stage_dev + (size_t)f0 * pic, src, pic * nf, cudaMemcpyHostToDevice, s ) );
+        uint8_t *slots = ctx->clip_slots + (size_t)f0 * g.slot_bytes;
+        if( ( rc = xd_frame_load_luma( ctx, &g, ctx->stage_dev + (size_t)f0 * pic, slots, nf, s ) ) ) return rc;
+        if( ( rc = x264dsp_frame_init_lowres_dev( ctx, &g, slots, nf, s ) ) ) return rc;
+        // every clip of the group contributes clip_len-1 inter pairs, in frame order
+        const int inter0 = c0 * ( clip_len - 1 ), ninter = ( c1 - c0 ) * ( clip_len - 1 );
+        if( ( rc = xd_la_launch( ctx, &g, ctx->clip_slots, f0, nf, b_dev, p0_dev, wi_dev, list_dev + inter0, ninter, gi,
+                                 d_mvs, d_costs, d_sums, NULL, s ) ) )
+            return rc;
+        uint8_t *o_mv = pinned_out ? (uint8_t *)mvs : h_out;
+        uint8_t *o_cost = pinned_out ? (uint8_t *)costs : h_out + mv_bytes;
+        uint8_t *o_sum = pinned_out ? (uint8_t *)sums : h_out + mv_bytes + cost_bytes;
+        const size_t mo = (size_t)f0 * mbc * 2 * sizeof( int16_t ), co = (size_t)f0 * mbc * sizeof( int32_t );
+        const size_t so = (size_t)f0 * X264DSP_LA_SUMS * sizeof( int32_t );
+        XD_CHECK( cudaMemcpyAsync( o_mv + mo, (uint8_t *)d_mvs + mo, (size_t)nf * mbc * 2 * sizeof( int16_t ), cudaMemcpyDeviceToHost, s ) );
+        XD_CHECK( cudaMemcpyAsync( o_cost + co, (uint8_t *)d_costs + co, (size_t)nf * mbc * sizeof( int32_t ), cudaMemcpyDeviceToHost, s ) );
+        XD_CHECK( cudaMemcpyAsync( o_sum + so, (uint8_t *)d_sums + so, (size_t)nf * X264DSP_LA_SUMS * sizeof( int32_t ), cudaMemcpyDeviceToHost, s ) );
+    }
+    for( int gi = 0; gi < groups; gi++ )
+        XD_CHECK( cudaStreamSynchronize( ctx->aux[gi] ) );
+    if( !pinned_out )
+    {
+        memcpy( mvs, h_out, mv_bytes );
+        memcpy( costs, h_out + mv_bytes, cost_bytes );
+        memcpy( sums, h_out + mv_bytes + cost_bytes, sum_bytes );
+    }
     return 0;
+}
+
+extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames,
+                                             const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums )
+{
+    return x264dsp_lookahead_clips_host( ctx, width, height, 1, n_frames, luma, mvs, costs, sums );
 }
