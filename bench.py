@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- the x264-dsp hot path on B200: 1080p lowres-lookahead motion estimation.
+
+Workload (BASELINE.json configs[1]): 1080p synthetic clips of 8 frames; for every clip the lowres
+planes of all 8 frames are built (x264_frame_init_lowres) and x264_slicetype_frame_cost is run
+intra-only on frame 0 and as a P analysis (DIA + SAD full-pel, half-pel refine, SATD re-cost, 3-mode
+intra SATD) on frames 1..7.  One step = `--clips` independent clips per GPU (default 16, so that
+the step's input, 265 MB of luma, is larger than the 126 MB L2).  Frames/s counts all frames.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
+  python bench.py --impl reference ...                      the reference's own C path on host cores
+
+Under torchrun (N > 1) every rank drives its own GPU on its own clips (weak scaling, no collective
+on the data path); time = max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+LOOKAHEAD_BYTES_PER_PAIR = None   # filled from the geometry: 5 lowres planes in + 8 B per block out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--clips", type=int, default=16, help="independent 8-frame clips per GPU per step")
+    ap.add_argument("--clip-len", type=int, default=8)
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_package():
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+def make_clips(pkg, w, h, clips, clip_len, first_clip=0, out=None):
+    """luma of `clips` consecutive synthetic clips, [clips*clip_len, h*w] uint8"""
+    n = clips * clip_len
+    luma = np.empty((n, w * h), np.uint8) if out is None else out
+    for i in range(n):
+        y = luma[i]
+        rc = pkg.lib().x264dsp_synth_frame(w, h, first_clip * clip_len + i, -1, y.ctypes.data_as(pkg.u8p), None, None)
+        assert rc == 0
+    return luma
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's own C path (oracle/_ref) or, if that build is absent, the oracle port
+
+def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats):
+    """runs the lookahead pass of len(luma_clips) clips on `threads` host threads, one clip at a
+    time per thread; returns (seconds of the timed region, kind, frames processed)"""
+    import cpu_checkers as cc
+    lib = cc.ref() if os.path.exists(cc.REF_SO) or os.path.isdir(cc.REFERENCE_TREE) else None
+    kind = "reference" if lib is not None else "port"
+    n_clips = len(luma_clips)
+    chroma = np.full(w * h // 2, 128, np.uint8)
+    work = [[] for _ in range(threads)]
+    for c in range(n_clips):
+        work[c % threads].append(c)
+    state = []
+    if kind == "reference":
+        for t in range(threads):
+            if not work[t]:
+                state.append(None)
+                continue
+            enc = cc.RefEncoder(w, h)
+            frames = [enc.new_frame(False) for _ in range(clip_len)]
+            state.append((enc, frames))
+    else:
+        o = cc.oracle()
+        g = cc.oracle_geom(w, h)
+        for t in range(threads):
+            state.append([np.zeros(g.slot_bytes, np.uint8) for _ in range(clip_len)] if work[t] else None)
+
+    barrier = threading.Barrier(threads + 1)
+    done = threading.Barrier(threads + 1)
+
+    def run(t):
+        barrier.wait()
+        if state[t] is not None:
+            for _ in range(repeats):
+                for c in work[t]:
+                    luma = luma_clips[c]
+                    if kind == "reference":
+                        enc, frames = state[t]
+                        for i in range(clip_len):
+                            pic = np.concatenate([luma[i], chroma])
+                            enc.load(frames[i], pic)        # x264_frame_copy_picture: part of the pass
+                        arr = (C.c_void_p * clip_len)(*[f.value for f in frames])
+                        costs = (C.c_int * clip_len)()
+                        enc.lib.xref_time_lookahead(enc.h, arr, clip_len, costs)
+                    else:
+                        slots = state[t]
+                        for i in range(clip_len):
+                            pic = np.concatenate([luma[i], chroma])
+                            o.xo_frame_load_i420(C.byref(g), cc.ptr(pic), cc.ptr(slots[i]))
+                            o.xo_frame_init_lowres(C.byref(g), cc.ptr(slots[i]))
+                        mv = np.zeros((g.mb_count, 2), np.int16)
+                        cs = np.zeros(g.mb_count, np.int32)
+                        sm = np.zeros(8, np.int32)
+                        for i in range(clip_len):
+                            o.xo_lookahead_frame_cost(C.byref(g), cc.ptr(slots[i]), cc.ptr(slots[i - 1]) if i else None, 1,
+                                                      cc.ptr(mv, cc.i16p), cc.ptr(cs, cc.i32p), cc.ptr(sm, cc.i32p), None)
+        done.wait()
+
+    ths = [threading.Thread(target=run, args=(t,), daemon=True) for t in range(threads)]
+    for th in ths:
+        th.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    dt = time.perf_counter() - t0
+    for th in ths:
+        th.join()
+    return dt, kind, n_clips * clip_len * repeats
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, pkg):
+    w, h = args.width, args.height
+    threads = args.cpu_threads or host_cores()
+    # one clip per thread and step: a bounded sample of the GPU arm's step (args.clips clips per GPU)
+    n_clips = threads
+    base = make_clips(pkg, w, h, min(n_clips, 8), args.clip_len)
+    luma_clips = [base.reshape(-1, args.clip_len, w * h)[c % min(n_clips, 8)] for c in range(n_clips)]
+    for _ in range(max(args.warmup, 1)):
+        cpu_lookahead(w, h, args.clip_len, luma_clips[: threads], threads, 1)
+    times = []
+    kind = "reference"
+    for _ in range(args.steps):
+        dt, kind, frames = cpu_lookahead(w, h, args.clip_len, luma_clips, threads, 1)
+        times.append(dt)
+    total = sum(times)
+    frames_per_step = n_clips * args.clip_len
+    value = frames_per_step * args.steps / total
+    line = {
+        "impl": "reference",
+        "metric": "1080p ME frames/sec" if (w, h) == (1920, 1080) else f"{w}x{h} ME frames/sec",
+        "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, frames_per_step, sample=f"{n_clips} clips of {args.clip_len} frames per step, "
+                                  f"one clip per host thread"),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": f"{n_clips} clips x {args.clip_len} frames per step x {args.steps} steps"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, frames_per_step, sample=None):
+    cfg = {
+        "workload": (f"{args.width}x{args.height} lowres lookahead: x264_frame_init_lowres + "
+                     f"x264_slicetype_frame_cost (DIA/SAD full-pel, hpel refine, SATD) over {args.clip_len}-frame clips"),
+        "clips_per_gpu_per_step": args.clips, "clip_len": args.clip_len, "frames_per_step_per_gpu": args.clips * args.clip_len,
+        "l2_policy": "step input larger than L2 (luma %.0f MB per GPU per step)" % (args.clips * args.clip_len * args.width * args.height / 1e6),
+        "parallelism": f"frame-range sharding, {args.gpus} GPU(s), no data-path collective",
+    }
+    if sample:
+        cfg["reference_sample"] = sample
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    pkg = load_package()
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference_arm(args, pkg)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    ctx = pkg.Context(local_rank)
+    w, h, clips, clip_len = args.width, args.height, args.clips, args.clip_len
+    g = pkg.geometry(w, h)
+    n = clips * clip_len
+    mbc = g.mb_count
+
+    # ---- synthetic input in pinned host memory (each rank gets its own clips)
+    luma_host = ctx.pinned_empty((n, w * h), np.uint8)
+    make_clips(pkg, w, h, clips, clip_len, first_clip=rank * clips, out=luma_host)
+    mvs_host = ctx.pinned_empty((n, mbc, 2), np.int16)
+    costs_host = ctx.pinned_empty((n, mbc), np.int32)
+    sums_host = ctx.pinned_empty((n, pkg.LA_SUMS), np.int32)
+
+    # ---- device-resident arm: raw luma already in HBM when the timed region starts
+    stream = ctx.torch_stream()
+    luma_dev = torch.from_numpy(luma_host).cuda()
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    d_mvs = torch.zeros((n, mbc, 2), dtype=torch.int16, device="cuda")
+    d_costs = torch.zeros((n, mbc), dtype=torch.int32, device="cuda")
+    d_sums = torch.zeros((n, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
+    b = np.arange(n, dtype=np.int32)
+    p0 = np.where(b % clip_len == 0, -1, b - 1).astype(np.int32)
+    wi = np.ones(n, np.uint8)
+    torch.cuda.synchronize()
+
+    def step_dev():
+        ctx.frame_load_luma(g, luma_dev, slots, n)
+        ctx.frame_init_lowres(g, slots, n)
+        ctx.lookahead_frame_cost(g, slots, b, p0, wi, d_mvs, d_costs, d_sums)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile_enable(True)
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record(stream)
+    sync_all()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - launches0
+    inter_ms, inter_n = ctx.profile_read(pkg.PROF_LA_INTER)
+    prof = {name: ctx.profile_read(kind) for name, kind in (
+        ("load", pkg.PROF_LOAD), ("lowres", pkg.PROF_LOWRES), ("border", pkg.PROF_BORDER),
+        ("la_intra", pkg.PROF_LA_INTRA), ("la_inter", pkg.PROF_LA_INTER))}
+    ctx.profile_enable(False)
+    sums_np = d_sums.cpu().numpy()
+
+    # ---- end-to-end arm: host buffers in, host results out, through the C ABI
+    for _ in range(2):
+        ctx.lookahead_clips_host(w, h, clips, clip_len, luma_host, mvs_host, costs_host, sums_host)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.lookahead_clips_host(w, h, clips, clip_len, luma_host, mvs_host, costs_host, sums_host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(sums_host, sums_np), "host and device arms disagree"
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- single clip latency (exactly the 8-frame configuration), device resident
+    one = clip_len
+    def step_one():
+        ctx.frame_load_luma(g, luma_dev, slots, one)
+        ctx.frame_init_lowres(g, slots, one)
+        ctx.lookahead_frame_cost(g, slots, b[:one], p0[:one], wi[:one], d_mvs, d_costs, d_sums)
+    for _ in range(3):
+        step_one()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_one()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    one_ms = ev0.elapsed_time(ev1) / args.steps
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        frames_total = world * n * args.steps
+        value = frames_total / (dev_ms / 1e3)
+        e2e_value = frames_total / (e2e_ms / 1e3)
+        pairs_per_launch = clips * (clip_len - 1)
+        bytes_per_pair = 5 * g.lowres_w * g.lowres_h + 8 * mbc
+        inter_avg_s = inter_ms / max(inter_n, 1) / 1e3
+        achieved = bytes_per_pair * pairs_per_launch / inter_avg_s / 1e9
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("xd_la_inter_kernel_bytes_per_launch")
+        sad_px = int(sums_np[:, pkg.LA_SAD_EVALS].sum()) * 64
+        satd_px = int(sums_np[:, pkg.LA_SATD_EVALS].sum()) * 64
+        step_s = dev_ms / 1e3 / args.steps
+        line = {
+            "metric": "1080p ME frames/sec" if (w, h) == (1920, 1080) else f"{w}x{h} ME frames/sec",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, n),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(n * w * h),
+                    "d2h_bytes_per_step": int(mvs_host.nbytes + costs_host.nbytes + sums_host.nbytes),
+                    "ms_per_step": e2e_ms / args.steps, "api": "x264dsp_lookahead_clips_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "xd_la_inter_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(bytes_per_pair * pairs_per_launch),
+                         "avg_launch_ms": inter_avg_s * 1e3, "launches_timed": inter_n,
+                         "note": "dependency/latency bound wavefront (SURVEY 8(d) config 2); HBM % reported as required"},
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "pixel_cmp": {"sad_gpix_per_s": sad_px * world / step_s / 1e9, "satd_gpix_per_s": satd_px * world / step_s / 1e9,
+                          "sad_pix_per_step_per_gpu": sad_px, "satd_pix_per_step_per_gpu": satd_px,
+                          "counted_by": "evaluations the reference issues on the same input (kernel work counters == oracle counters)"},
+            "single_clip": {"frames": one, "ms": one_ms, "frames_per_s": one / (one_ms / 1e3),
+                            "note": "exactly one 8-frame clip in flight: latency bound"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = args.cpu_threads or host_cores()
+            sample_clips = threads
+            luma_clips = [luma_host.reshape(clips, clip_len, w * h)[c % clips] for c in range(sample_clips)]
+            cpu_lookahead(w, h, clip_len, luma_clips, threads, 1)          # warm-up (page-in, allocations)
+            dt, kind, frames = cpu_lookahead(w, h, clip_len, luma_clips, threads, 2)
+            line["cpu_baseline"] = {"value": frames / dt, "unit": "frames/s", "cores": threads, "kind": kind,
+                                    "sample": f"{sample_clips} clips x {clip_len} frames, 2 passes, one clip per thread "
+                                              f"({frames} frames in {dt:.2f} s)"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -134,6 +134,12 @@ int x264dsp_synth_frame( int width, int height, int frame_no, int cut_frame,
 int x264dsp_frame_load_i420_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *i420,
                                  uint8_t *slots, int n_frames, void *stream );
 
+/* luma-only staging for the lookahead path, which never touches chroma: n_frames pictures of
+ * width*height bytes -> padded luma plane N of each slot (plane_copy + mod16 padding,
+ * common/frame.c:227, 435-448). */
+int x264dsp_frame_load_luma_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
+                                 uint8_t *slots, int n_frames, void *stream );
+
 /* x264_frame_expand_border for every MB row (common/frame.c:386-396): replicate luma N and chroma
  * into their 32 / 16 sample padding. */
 int x264dsp_frame_expand_border_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,

@@ -452,7 +452,11 @@ double xref_time_lookahead( void *hv, void **frames, int n, int *cost_out )
     double t0 = xref_now();
     int i;
     for( i = 0; i < n; i++ )
+    {
+        /* a recycled frame starts with b_intra_calculated = 0 (x264_frame_pop_unused, frame.c:511) */
+        ((x264_frame_t *)frames[i])->b_intra_calculated = 0;
         x264_frame_init_lowres( h, (x264_frame_t *)frames[i] );
+    }
     cost_out[0] = xref_slicetype_frame_cost( h, (x264_frame_t **)frames, 0, 0, 0 );
     for( i = 1; i < n; i++ )
         cost_out[i] = xref_slicetype_frame_cost( h, (x264_frame_t **)frames, i-1, i, i );

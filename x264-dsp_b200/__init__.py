@@ -186,6 +186,10 @@ class Context:
         check(lib().x264dsp_frame_load_i420_dev(self._h, C.byref(g), _dp(i420_dev), _dp(slots_dev),
                                                 int(n_frames), None), "x264dsp_frame_load_i420_dev")
 
+    def frame_load_luma(self, g, luma_dev, slots_dev, n_frames):
+        check(lib().x264dsp_frame_load_luma_dev(self._h, C.byref(g), _dp(luma_dev), _dp(slots_dev),
+                                                int(n_frames), None), "x264dsp_frame_load_luma_dev")
+
     def frame_expand_border(self, g, slots_dev, n_frames):
         check(lib().x264dsp_frame_expand_border_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),
               "x264dsp_frame_expand_border_dev")

@@ -40,6 +40,7 @@ struct x264dsp_ctx
     uint8_t *clip_out;    size_t clip_out_cap;       // device results
     uint8_t *clip_out_host; size_t clip_out_host_cap; // pinned results
     int32_t *clip_desc;   size_t clip_desc_cap;
+    void *desc_cache;     size_t desc_cache_bytes;   // host copy of what clip_desc holds
 
     // extra streams so that independent groups of a host-level batch overlap copies and kernels
     cudaStream_t aux[4];

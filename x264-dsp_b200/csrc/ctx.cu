@@ -248,6 +248,7 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     cudaFree( ctx->clip_slots );
     cudaFree( ctx->clip_out );
     cudaFree( ctx->clip_desc );
+    free( ctx->desc_cache );
     cudaFree( ctx->shim_dev );
     if( ctx->stage_host ) cudaFreeHost( ctx->stage_host );
     if( ctx->clip_out_host ) cudaFreeHost( ctx->clip_out_host );

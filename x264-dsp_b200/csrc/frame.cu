@@ -430,6 +430,14 @@ int xd_frame_load_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8
     return 0;
 }
 
+extern "C" int x264dsp_frame_load_luma_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
+                                             uint8_t *slots, int n_frames, void *stream )
+{
+    if( !ctx || !g || !luma || !slots || n_frames <= 0 )
+        return X264DSP_E_ARG;
+    return xd_frame_load_luma( ctx, g, luma, slots, n_frames, xd_stream( ctx, stream ) );
+}
+
 static int xd_launch_border( x264dsp_ctx_t *ctx, const xd_border_job &job, uint8_t *slots, int64_t slot_bytes,
                              int n_frames, int n_planes, int64_t plane_pitch, cudaStream_t s )
 {

@@ -668,12 +668,26 @@ static int xd_la_upload_desc( x264dsp_ctx_t *ctx, int n_pairs, const int32_t *b,
             host[2 * n_pairs + n_inter++] = i;
     }
     memcpy( host + words, want_intra, n_pairs );
-    cudaError_t e = cudaMemcpyAsync( ctx->clip_desc, host, bytes, cudaMemcpyHostToDevice, s );
-    if( e == cudaSuccess )
-        e = cudaStreamSynchronize( s );          // host staging buffer is pageable
-    free( host );
-    if( e != cudaSuccess )
-        return (int)e;
+    // the same batch shape is usually analysed over and over: keep the last description and skip
+    // the upload (and its synchronisation) when nothing changed
+    if( ctx->desc_cache && ctx->desc_cache_bytes == bytes && !memcmp( ctx->desc_cache, host, bytes ) )
+        free( host );
+    else
+    {
+        cudaError_t e = cudaDeviceSynchronize();         // earlier launches may still read the old one
+        if( e == cudaSuccess )
+            e = cudaMemcpyAsync( ctx->clip_desc, host, bytes, cudaMemcpyHostToDevice, s );
+        if( e == cudaSuccess )
+            e = cudaStreamSynchronize( s );              // host staging buffer is pageable
+        free( ctx->desc_cache );
+        ctx->desc_cache = host;
+        ctx->desc_cache_bytes = bytes;
+        if( e != cudaSuccess )
+        {
+            ctx->desc_cache_bytes = 0;
+            return (int)e;
+        }
+    }
     *n_inter_out = n_inter;
     *b_dev = ctx->clip_desc;
     *p0_dev = ctx->clip_desc + n_pairs;
