@@ -1,0 +1,104 @@
+"""GPU parity: x264dsp_me_search_batch_dev against the CPU oracle (itself pinned to the reference's
+x264_me_search_ref / x264_me_refine_qpel in tests/test_oracle_vs_ref.py), all partition sizes,
+DIA and HEX, subme 1..5, with and without the final qpel refinement.  Bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cpu_checkers as cc
+from test_oracle_vs_ref import make_me_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+def prepare(pkg, ctx, w, h):
+    import torch
+    frames = [pkg.synth_frame(w, h, i) for i in range(2)]
+    g = pkg.geometry(w, h)
+    go = cc.oracle_geom(w, h)
+    o = cc.oracle()
+    host = []
+    for f in frames:
+        s = np.zeros(go.slot_bytes, np.uint8)
+        o.xo_frame_load_i420(C.byref(go), cc.ptr(f), cc.ptr(s))
+        o.xo_frame_expand_border(C.byref(go), cc.ptr(s))
+        o.xo_frame_filter(C.byref(go), cc.ptr(s))
+        host.append(s)
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros(2 * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, 2)
+    ctx.frame_expand_border(g, slots, 2)
+    ctx.frame_filter(g, slots, 2)
+    ctx.sync()
+    return g, go, host, slots
+
+
+@pytest.mark.parametrize("me,subme,refine", [(0, 1, 1), (0, 2, 0), (1, 2, 1), (1, 3, 0), (1, 4, 1), (1, 5, 1), (0, 5, 0), (1, 1, 0)])
+def test_me_search_batch(pkg, ctx, me, subme, refine):
+    import torch
+    w, h = 352, 288
+    g, go, host, slots = prepare(pkg, ctx, w, h)
+    o = cc.oracle()
+    rng = np.random.RandomState(500 + me * 10 + subme)
+    ref_slot, enc_slot = slots[: g.slot_bytes], slots[g.slot_bytes:]
+    for size in range(7):
+        for qp, mv_scale in ((26, 24), (38, 90)):
+            n = 400
+            blocks = make_me_blocks(go, rng, size, n, mv_scale)
+            want = np.zeros(n, cc.ME_RESULT_DTYPE)
+            prm = cc.MeParams(me, subme, 16, qp, refine)
+            o.xo_me_search_batch(C.byref(go), cc.ptr(host[1]), cc.ptr(host[0]), C.byref(prm), n,
+                                 blocks.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+            d_blocks = torch.from_numpy(blocks.view(np.uint8)).cuda()
+            d_res = torch.zeros(n * cc.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            p = pkg.MeParams(me, subme, 16, qp, refine)
+            ctx.me_search_batch(g, enc_slot, ref_slot, p, n, d_blocks, d_res)
+            ctx.sync()
+            got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)
+            bad = [i for i in range(n) if got[i] != want[i]]
+            assert not bad, (f"me {me} subme {subme} refine {refine} size {size} qp {qp}: {len(bad)}/{n} differ; "
+                             f"first {bad[0]}: gpu {got[bad[0]]} oracle {want[bad[0]]} block {blocks[bad[0]]}")
+
+
+def test_me_search_1080p_tiling(pkg, ctx):
+    """config 3 shape: every 16x16 and 8x8 block of a 1080p frame, HEX + subme 5 + qpel refine,
+    mvp/mvc as a harness would derive them"""
+    import torch
+    w, h = 1920, 1080
+    g, go, host, slots = prepare(pkg, ctx, w, h)
+    o = cc.oracle()
+    rng = np.random.RandomState(9)
+    for size, step in ((0, 16), (3, 8)):
+        xs, ys = np.meshgrid(np.arange(0, g.luma_w, step), np.arange(0, g.luma_h, step))
+        n = xs.size
+        blocks = np.zeros(n, cc.ME_BLOCK_DTYPE)
+        blocks["i_pixel"] = size
+        blocks["bx"] = xs.ravel()
+        blocks["by"] = ys.ravel()
+        mbx, mby = blocks["bx"] // 16, blocks["by"] // 16
+        fmv = 512 << 2
+        for k, (mb, nmb) in enumerate(((mbx, g.mb_w), (mby, g.mb_h))):
+            smin = np.clip((-(mb << 4) - 24) << 2, -fmv, fmv - 1)
+            smax = np.clip((((nmb - mb - 1) << 4) + 24) << 2, -fmv, fmv - 1)
+            blocks["mv_min_spel"][:, k], blocks["mv_max_spel"][:, k] = smin, smax
+            blocks["mv_min_fpel"][:, k], blocks["mv_max_fpel"][:, k] = (smin >> 2) + 6, (smax >> 2) - 6
+        blocks["mvp"] = rng.randint(-16, 17, (n, 2))
+        blocks["i_mvc"] = 2
+        blocks["mvc"][:, 0] = blocks["mvp"]
+        blocks["mvc"][:, 1] = 0
+        keep = rng.choice(n, 4000, replace=False)           # the oracle is a scalar CPU loop
+        sub = np.ascontiguousarray(blocks[keep])
+        want = np.zeros(len(sub), cc.ME_RESULT_DTYPE)
+        prm = cc.MeParams(1, 5, 16, 26, 1)
+        o.xo_me_search_batch(C.byref(go), cc.ptr(host[1]), cc.ptr(host[0]), C.byref(prm), len(sub),
+                             sub.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+        d_blocks = torch.from_numpy(blocks.view(np.uint8)).cuda()
+        d_res = torch.zeros(n * cc.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.me_search_batch(g, slots[g.slot_bytes:], slots[: g.slot_bytes], pkg.MeParams(1, 5, 16, 26, 1), n, d_blocks, d_res)
+        ctx.sync()
+        got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)[keep]
+        assert np.array_equal(got, want), f"size {size}: {np.count_nonzero(got != want)} of {len(sub)} differ"

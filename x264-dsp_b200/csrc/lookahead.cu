@@ -224,43 +224,64 @@ __device__ __forceinline__ uint2 xd_la_fetch( const xd_la_block &B, int qx, int 
     return a;
 }
 
-// SAD of this lane's candidate (lane>>3) at (qx,qy); every lane of the candidate's group of 8 gets it
-__device__ __forceinline__ int xd_la_sad( const xd_la_block &B, int qx, int qy, int lane )
+// Costs of the four candidate groups in one step.  Lane = 8*cand + row holds the SAD of its 8
+// pixels; the lane of row 0 also adds the candidate's mv bits (or 0xFFFF when the candidate does not
+// compete).  Each candidate owns a 16-bit field (an 8x8 SAD plus its mv bits stays below 2^15 at
+// lambda = 1), so two whole-warp REDUX.SUM instructions replace the 3 + 2 dependent shuffles of a
+// tree reduction; afterwards EVERY lane holds all four costs and picks the winner locally.
+struct xd_cost4
+{
+    int c[4];
+};
+__device__ __forceinline__ xd_cost4 xd_la_reduce4( int partial, int lane )
+{
+    const unsigned v = (unsigned)partial << ( ( lane & 8 ) ? 16 : 0 );
+    const unsigned lo = __reduce_add_sync( 0xffffffffu, ( lane & 16 ) ? 0u : v );   // candidates 0, 1
+    const unsigned hi = __reduce_add_sync( 0xffffffffu, ( lane & 16 ) ? v : 0u );   // candidates 2, 3
+    xd_cost4 r;
+    r.c[0] = (int)( lo & 0xFFFF ); r.c[1] = (int)( lo >> 16 );
+    r.c[2] = (int)( hi & 0xFFFF ); r.c[3] = (int)( hi >> 16 );
+    return r;
+}
+
+// this lane's share of the cost of candidate (lane>>3) at quarter-pel (qx,qy):
+// SAD of its row, plus (row 0 only) the mv bits, or the "does not compete" marker
+__device__ __forceinline__ int xd_la_partial( const xd_la_block &B, int qx, int qy, int lane, bool ok, bool with_bits )
 {
     const uint2 p = xd_la_fetch( B, qx, qy, lane & 7 );
     int s = (int)( __vsadu4( p.x, B.fenc.x ) + __vsadu4( p.y, B.fenc.y ) );
-    s += __shfl_xor_sync( 0xffffffffu, s, 1 );
-    s += __shfl_xor_sync( 0xffffffffu, s, 2 );
-    s += __shfl_xor_sync( 0xffffffffu, s, 4 );
+    if( !ok )
+        s = 0;
+    if( ( lane & 7 ) == 0 )
+        s += !ok ? 0xFFFF : with_bits ? xd_la_bits( B, qx, qy ) : 0;
     return s;
 }
 
-// min over the four candidate groups of a packed key
-__device__ __forceinline__ int xd_la_min4( int key )
+// 4 pixels of the prediction at (qx,qy), block-relative position (x,y)
+__device__ __forceinline__ uint32_t xd_la_fetch4( const xd_la_block &B, int qx, int qy, int x, int y )
 {
-    key = min( key, __shfl_xor_sync( 0xffffffffu, key, 8 ) );
-    key = min( key, __shfl_xor_sync( 0xffffffffu, key, 16 ) );
-    return key;
+    const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
+    const int64_t base = (int64_t)( ( qy >> 2 ) + y ) * B.stride + ( qx >> 2 ) + x;
+    uint32_t a = xd_load4_unaligned( B.ref + (size_t)xd_qpel_plane_a( phase ) * B.plane_size + base + ( fy == 3 ? B.stride : 0 ) );
+    if( phase & 5 )
+        a = xd_avg4( a, xd_load4_unaligned( B.ref + (size_t)xd_qpel_plane_b( phase ) * B.plane_size + base + ( fx == 3 ? 1 : 0 ) ) );
+    return a;
 }
 
-// SATD 8x8 of the prediction at (qx,qy) against the source block (pixel.c:294-335)
+// SATD 8x8 of the prediction at (qx,qy) against the source block (pixel.c:294-335).
+// Lane & 3 selects the 4x4 quadrant; every lane loads its quadrant directly (no redistribution).
 __device__ __forceinline__ int xd_la_satd( const xd_la_block &B, int qx, int qy, int lane )
 {
-    const uint2 p = xd_la_fetch( B, qx, qy, lane & 7 );
-    const int q = lane & 3, r0 = ( q >> 1 ) * 4;
+    const int q = lane & 3, x = ( q & 1 ) * 4, y = ( q >> 1 ) * 4;
     uint32_t pr[4];
 #pragma unroll
     for( int r = 0; r < 4; r++ )
-    {
-        const uint32_t lo = __shfl_sync( 0xffffffffu, p.x, r0 + r );
-        const uint32_t hi = __shfl_sync( 0xffffffffu, p.y, r0 + r );
-        pr[r] = ( q & 1 ) ? hi : lo;
-    }
-    int s = xd_satd4x4_words( B.fq, pr );
-    s += __shfl_xor_sync( 0xffffffffu, s, 1 );      // left + right 4x4 of an 8x4
-    s >>= 1;
-    s += __shfl_xor_sync( 0xffffffffu, s, 2 );      // upper + lower 8x4
-    return s;
+        pr[r] = xd_la_fetch4( B, qx, qy, x, y + r );
+    const unsigned s = (unsigned)xd_satd4x4_words( B.fq, pr );
+    // upper 8x4 = quadrants 0+1, lower 8x4 = quadrants 2+3, each halved once
+    const unsigned up = __reduce_add_sync( 0xffffffffu, lane < 2 ? s : 0u );
+    const unsigned dn = __reduce_add_sync( 0xffffffffu, ( lane & ~1 ) == 2 ? s : 0u );
+    return (int)( ( up >> 1 ) + ( dn >> 1 ) );
 }
 
 // CHECK_MVRANGE (me.c:155-160)
@@ -369,22 +390,18 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             B.ref = ref + pel;
             B.fenc = __ldg( (const uint2 *)( cur + pel + (size_t)( lane & 7 ) * ls ) );
             {
-                const int q = lane & 3, r0 = ( q >> 1 ) * 4;
+                // rows of this lane's 4x4 quadrant of the source block (for SATD)
+                const int q = lane & 3;
 #pragma unroll
                 for( int r = 0; r < 4; r++ )
-                {
-                    const uint32_t lo = __shfl_sync( 0xffffffffu, B.fenc.x, r0 + r );
-                    const uint32_t hi = __shfl_sync( 0xffffffffu, B.fenc.y, r0 + r );
-                    B.fq[r] = ( q & 1 ) ? hi : lo;
-                }
+                    B.fq[r] = __ldg( (const uint32_t *)( cur + pel + (size_t)( ( q >> 1 ) * 4 + r ) * ls + ( q & 1 ) * 4 ) );
             }
             const int minx = -( bx << 3 ) - 4, maxx = ( ( W - bx - 1 ) << 3 ) + 4;
             const int sminx = ( minx - 8 ) << 2, smaxx = ( maxx + 8 ) << 2;
 
             // predictors (slicetype.c:105-113): right, below, below-left, below-right
-            const uint32_t mvc[4] = { mv_right, mv_b, mv_bl, mv_br };
-            B.mvpx = xd_median3( MVX( mvc[0] ), MVX( mvc[1] ), MVX( mvc[2] ) );
-            B.mvpy = xd_median3( MVY( mvc[0] ), MVY( mvc[1] ), MVY( mvc[2] ) );
+            B.mvpx = xd_median3( MVX( mv_right ), MVX( mv_b ), MVX( mv_bl ) );
+            B.mvpy = xd_median3( MVY( mv_right ), MVY( mv_b ), MVY( mv_bl ) );
 
             int mvx = 0, mvy = 0, cost = -1;
             if( !( B.mvpx | B.mvpy ) )                     // slicetype.c:117-125
@@ -402,64 +419,50 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 const uint32_t pmv = ( (uint32_t)pmx & 0xFFFF ) | ( (uint32_t)pmy << 16 );
                 int bcost;
                 {
-                    // candidates in evaluation order: 0 = rounded MVP (no mv cost), 1..4 = mvc, 5 = (0,0)
-                    int cx[2], cy[2];
-                    bool ok[2];
-                    const int idx[2] = { cand, cand + 4 };
+                    // candidates in evaluation order: 0 = rounded MVP (no mv cost), 1..4 = mvc, 5 = (0,0);
+                    // pass 0 carries 0..3 in the four lane groups, pass 1 carries 4 and 5
+                    int best = 0x7FFFFFFF;
+                    int n_evals = 0;
 #pragma unroll
                     for( int pass = 0; pass < 2; pass++ )
                     {
-                        const int k = idx[pass];
-                        cx[pass] = 0; cy[pass] = 0; ok[pass] = false;
+                        const int k = pass * 4 + cand;
+                        int cx = 0, cy = 0;
+                        bool ok = false;
                         if( k == 0 )
                         {
-                            cx[pass] = pmx; cy[pass] = pmy; ok[pass] = true;
+                            cx = pmx; cy = pmy; ok = true;
                         }
                         else if( k <= 4 )
                         {
-                            const uint32_t m = mvc[k - 1];
-                            cx[pass] = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx );
-                            cy[pass] = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
-                            const uint32_t v = ( (uint32_t)cx[pass] & 0xFFFF ) | ( (uint32_t)cy[pass] << 16 );
-                            ok[pass] = v != 0 && v != pmv;
+                            const uint32_t m = k == 1 ? mv_right : k == 2 ? mv_b : k == 3 ? mv_bl : mv_br;
+                            cx = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx );
+                            cy = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
+                            const uint32_t v = ( (uint32_t)cx & 0xFFFF ) | ( (uint32_t)cy << 16 );
+                            ok = v != 0 && v != pmv;
                         }
                         else if( k == 5 )
-                            ok[pass] = pmv != 0;
-                    }
-                    int key = 0x7FFFFFFF;
+                            ok = pmv != 0;
+                        const xd_cost4 r = xd_la_reduce4( xd_la_partial( B, cx << 2, cy << 2, lane, ok, k != 0 ), lane );
 #pragma unroll
-                    for( int pass = 0; pass < 2; pass++ )
-                    {
-                        // pass 1 only carries candidates 4 and 5 (groups 0 and 1)
-                        int s = xd_la_sad( B, cx[pass] << 2, cy[pass] << 2, lane );
-                        if( idx[pass] != 0 )
-                            s += xd_la_bits( B, cx[pass] << 2, cy[pass] << 2 );
-                        if( ok[pass] )
-                            key = min( key, ( s << 3 ) | idx[pass] );
+                        for( int c = 0; c < 4; c++ )
+                            if( r.c[c] < 0xFFFF )
+                            {
+                                best = min( best, ( r.c[c] << 3 ) | ( pass * 4 + c ) );
+                                n_evals++;
+                            }
                     }
-                    key = xd_la_min4( key );
-                    bcost = key >> 3;
-                    const int win = key & 7;
-                    // every lane recomputes the winner's coordinates
+                    bcost = best >> 3;
+                    const int win = best & 7;
                     if( win == 0 ) { bmx = pmx; bmy = pmy; }
                     else if( win == 5 ) { bmx = 0; bmy = 0; }
                     else
                     {
-                        const uint32_t m = mvc[win - 1];
+                        const uint32_t m = win == 1 ? mv_right : win == 2 ? mv_b : win == 3 ? mv_bl : mv_br;
                         bmx = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx );
                         bmy = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
                     }
-                    // evaluations the reference issues: MVP + valid candidates + (0,0)
-                    int n = 1 + ( pmv != 0 );
-#pragma unroll
-                    for( int k = 0; k < 4; k++ )
-                    {
-                        const uint32_t m = mvc[k];
-                        const int x = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx ), y = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
-                        const uint32_t v = ( (uint32_t)x & 0xFFFF ) | ( (uint32_t)y << 16 );
-                        n += v != 0 && v != pmv;
-                    }
-                    B.sad_evals += n;
+                    B.sad_evals += n_evals;          // MVP + competing candidates + (0,0), as the reference issues
                 }
 
                 // ---- diamond search (me.c:237-274): up, down, left, right
@@ -469,10 +472,9 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     int left = A.me_range;
                     do
                     {
-                        const int cxq = ( bmx + dx ) << 2, cyq = ( bmy + dy ) << 2;
-                        const int s = xd_la_sad( B, cxq, cyq, lane ) + xd_la_bits( B, cxq, cyq );
-                        const int key = xd_la_min4( ( s << 2 ) | cand );
+                        const xd_cost4 r = xd_la_reduce4( xd_la_partial( B, ( bmx + dx ) << 2, ( bmy + dy ) << 2, lane, true, true ), lane );
                         B.sad_evals += 4;
+                        const int key = min( min( ( r.c[0] << 2 ) | 0, ( r.c[1] << 2 ) | 1 ), min( ( r.c[2] << 2 ) | 2, ( r.c[3] << 2 ) | 3 ) );
                         if( ( key >> 2 ) >= bcost )
                             break;
                         bcost = key >> 2;
@@ -492,16 +494,17 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     const int px = xd_clip3( B.mvpx, sminx + 2, smaxx - 2 ), py = xd_clip3( B.mvpy, sminy + 2, smaxy - 2 );
                     if( px != qx || py != qy )                       // me.c:483-490
                     {
-                        const int s = xd_la_sad( B, px, py, lane ) + xd_la_bits( B, px, py );
+                        // a single candidate: let group 0 carry it
+                        const xd_cost4 r = xd_la_reduce4( xd_la_partial( B, px, py, lane, cand == 0, true ), lane );
                         B.sad_evals++;
-                        if( s < bcost ) { bcost = s; qx = px; qy = py; }
+                        if( r.c[0] < bcost ) { bcost = r.c[0]; qx = px; qy = py; }
                     }
                     // half-pel diamond (me.c:492-517)
                     const int hx = qx + ( cand == 2 ? -2 : cand == 3 ? 2 : 0 );
                     const int hy = qy + ( cand == 0 ? -2 : cand == 1 ? 2 : 0 );
-                    const int s = xd_la_sad( B, hx, hy, lane ) + xd_la_bits( B, hx, hy );
-                    const int key = xd_la_min4( ( s << 2 ) | cand );
+                    const xd_cost4 r = xd_la_reduce4( xd_la_partial( B, hx, hy, lane, true, true ), lane );
                     B.sad_evals += 4;
+                    const int key = min( min( ( r.c[0] << 2 ) | 0, ( r.c[1] << 2 ) | 1 ), min( ( r.c[2] << 2 ) | 2, ( r.c[3] << 2 ) | 3 ) );
                     if( ( key >> 2 ) < bcost )
                     {
                         const int w = key & 3;
