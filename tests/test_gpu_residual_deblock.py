@@ -1,0 +1,121 @@
+"""GPU parity: motion compensation, residual coding (DCT / quant / dequant / IDCT / decimation /
+chroma DC) and in-loop deblocking of whole frames, CUDA through the C ABI against the CPU oracle
+(pinned to the reference's x264_macroblock_encode / x264_frame_deblock_row).  Bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cpu_checkers as cc
+from cpu_checkers import ptr, i16p, i8p
+
+pytestmark = pytest.mark.gpu
+
+
+def _slots(pkg, ctx, w, h, n, filtered):
+    import torch
+    frames = [pkg.synth_frame(w, h, i) for i in range(n)]
+    g = pkg.geometry(w, h)
+    go = cc.oracle_geom(w, h)
+    o = cc.oracle()
+    host = []
+    for f in frames:
+        s = np.zeros(go.slot_bytes, np.uint8)
+        o.xo_frame_load_i420(C.byref(go), ptr(f), ptr(s))
+        if filtered:
+            o.xo_frame_expand_border(C.byref(go), ptr(s))
+            o.xo_frame_filter(C.byref(go), ptr(s))
+        host.append(s)
+    dev = torch.from_numpy(np.concatenate(host)).cuda()
+    return g, go, host, dev
+
+
+@pytest.mark.parametrize("w,h,qp", [(352, 288, 26), (200, 120, 20), (352, 288, 38), (1920, 1080, 26), (352, 288, 12)])
+def test_mc_and_residual_frame(pkg, ctx, w, h, qp):
+    import torch
+    g, go, host, dev = _slots(pkg, ctx, w, h, 2, True)
+    o = cc.oracle()
+    rng = np.random.RandomState(qp + w)
+    n = g.mb_count
+    # MVs around the true pan (3,2 px/frame -> 12,8 qpel) with outliers, incl. out-of-range ones that get clipped
+    mv = (np.array([12, 8]) + rng.randint(-6, 7, (n, 2))).astype(np.int16)
+    mv[rng.rand(n) < 0.05] = rng.randint(-3000, 3000, 2)
+    mv[rng.rand(n) < 0.1] = 0
+
+    pred_o = np.zeros(go.slot_bytes, np.uint8)
+    o.xo_mc_frame(C.byref(go), ptr(host[0]), ptr(mv, i16p), ptr(pred_o))
+    ref_slot, enc_slot = dev[: g.slot_bytes], dev[g.slot_bytes:]
+    pred = torch.zeros(g.slot_bytes, dtype=torch.uint8, device="cuda")
+    d_mv = torch.from_numpy(mv).cuda()
+    torch.cuda.synchronize()
+    ctx.mc_frame(g, ref_slot, d_mv, pred)
+    ctx.sync()
+    assert np.array_equal(pred.cpu().numpy(), pred_o), "mc_frame"
+
+    lv_o = np.zeros((n, pkg.RES_LEVELS_PER_MB), np.int16)
+    nz_o = np.zeros((n, pkg.RES_NNZ_PER_MB), np.uint8)
+    cbp_o = np.zeros(n, np.int16)
+    o.xo_residual_frame(C.byref(go), ptr(host[1]), ptr(pred_o), qp, ptr(lv_o, i16p), ptr(nz_o), ptr(cbp_o, i16p))
+    lv = torch.full((n, pkg.RES_LEVELS_PER_MB), -1, dtype=torch.int16, device="cuda")
+    nz = torch.full((n, pkg.RES_NNZ_PER_MB), 77, dtype=torch.uint8, device="cuda")
+    cbp = torch.full((n,), -1, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    ctx.residual_frame(g, enc_slot, pred, qp, lv, nz, cbp)
+    ctx.sync()
+    bad = np.nonzero(cbp.cpu().numpy() != cbp_o)[0]
+    assert len(bad) == 0, f"cbp differs at MBs {bad[:5]}: {cbp.cpu().numpy()[bad[:5]]} vs {cbp_o[bad[:5]]}"
+    assert np.array_equal(nz.cpu().numpy(), nz_o), "nnz"
+    bad = np.nonzero((lv.cpu().numpy() != lv_o).any(1))[0]
+    assert len(bad) == 0, f"levels differ at MBs {bad[:5]}"
+    assert np.array_equal(pred.cpu().numpy(), pred_o), "reconstruction"
+    # the test must exercise coded, decimated and skipped macroblocks
+    assert (cbp_o == 0).any() or qp < 20
+    assert (cbp_o != 0).any()
+
+
+@pytest.mark.parametrize("w,h,qp,aoff,boff", [(352, 288, 26, 0, 0), (200, 120, 38, 0, 0), (352, 288, 20, 3, -2),
+                                              (1920, 1080, 30, 0, 0), (64, 64, 51, 0, 0), (352, 288, 14, 0, 0)])
+def test_deblock_frame(pkg, ctx, w, h, qp, aoff, boff):
+    import torch
+    g, go, host, dev = _slots(pkg, ctx, w, h, 1, False)
+    o = cc.oracle()
+    rng = np.random.RandomState(qp * 7 + w)
+    n = g.mb_count
+    mb_type = rng.choice([0, 2, 4, 5, 6], n, p=[0.05, 0.05, 0.5, 0.2, 0.2]).astype(np.int8)
+    partition = rng.choice([13, 14, 15, 16], n).astype(np.uint8)
+    cbp = (rng.randint(0, 48, n) * (rng.rand(n) < 0.6)).astype(np.int16)
+    bs = rng.randint(0, 4, (n, 2, 8, 4)).astype(np.uint8)
+    bs[rng.rand(n) < 0.2] = 0
+    want = host[0].copy()
+    o.xo_deblock_frame(C.byref(go), ptr(want), ptr(mb_type, i8p), ptr(partition), ptr(cbp, i16p), ptr(bs), qp, aoff, boff)
+    slot = dev.clone()
+    d = [torch.from_numpy(a).cuda() for a in (mb_type, partition, cbp, bs)]
+    torch.cuda.synchronize()
+    for rep in range(2):                       # twice: the row counters must reset between launches
+        slot.copy_(dev)
+        torch.cuda.synchronize()
+        ctx.deblock_frame(g, slot, d[0], d[1], d[2], d[3], qp, aoff, boff)
+        ctx.sync()
+        got = slot.cpu().numpy()
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, f"rep {rep}: {len(bad)} bytes differ, first at offset {bad[:4]}"
+    if qp >= 20:
+        assert np.count_nonzero(want != host[0]) > 0, "the test must exercise the filter"
+
+
+def test_deblock_strength(pkg, ctx):
+    import torch
+    rng = np.random.RandomState(3)
+    n = 5000
+    nnz = (rng.rand(n, 120) < 0.3).astype(np.uint8)
+    ref = rng.randint(-1, 2, (n, 2, 40)).astype(np.int8)
+    mv = rng.randint(-6, 7, (n, 2, 40, 2)).astype(np.int16)
+    want = np.zeros((n, 2, 8, 4), np.uint8)
+    cc.oracle().xo_deblock_strength(n, ptr(nnz), ptr(ref, i8p), ptr(mv, i16p), ptr(want))
+    d = [torch.from_numpy(a).cuda() for a in (nnz, ref, mv)]
+    bs = torch.zeros((n, 2, 8, 4), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.deblock_strength(n, d[0], d[1], d[2], bs)
+    ctx.sync()
+    got = bs.cpu().numpy()
+    assert np.array_equal(got[:, :, :4], want[:, :, :4])

@@ -42,6 +42,9 @@ struct x264dsp_ctx
     int32_t *clip_desc;   size_t clip_desc_cap;
     void *desc_cache;     size_t desc_cache_bytes;   // host copy of what clip_desc holds
 
+    // deblock wavefront: per-row progress counters + ticket
+    int32_t *db_progress; size_t db_progress_cap;
+
     // extra streams so that independent groups of a host-level batch overlap copies and kernels
     cudaStream_t aux[4];
 

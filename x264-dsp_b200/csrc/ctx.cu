@@ -247,6 +247,7 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     cudaFree( ctx->stage_dev );
     cudaFree( ctx->clip_slots );
     cudaFree( ctx->clip_out );
+    cudaFree( ctx->db_progress );
     cudaFree( ctx->clip_desc );
     free( ctx->desc_cache );
     cudaFree( ctx->shim_dev );

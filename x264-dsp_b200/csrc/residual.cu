@@ -1,0 +1,584 @@
+// residual.cu -- frame-wide motion compensation and residual coding of inter macroblocks, sm_100a.
+//
+// Reference:
+//   x264_mb_mc / x264_mb_mc_xywh (16x16 case)          common/macroblock.c:8-28
+//   mc_luma, mc_chroma                                  common/mc.c:216-239, 290-323
+//   x264_macroblock_encode, inter branch + cbp packing  encoder/macroblock.c:379-471
+//   x264_mb_encode_chroma (b_inter = 1)                 encoder/macroblock.c:175-305
+//   sub4x4_dct / add4x4_idct / add*_idct_dc             common/dct.c:115-150, 197-284
+//   quant_4x4 / quant_2x2_dc / dequant_4x4              common/quant.c:29-81
+//   optimize_chroma_2x2_dc, decimate_score15/16         common/quant.c:133-261
+// with h->mb.b_dct_decimate = 1 (P slice), no noise reduction, CABAC cbp layout.
+//
+// Mapping of the residual kernel: one WARP per macroblock.  Lanes 0..15 own the sixteen luma 4x4
+// blocks (coding order), lanes 16..19 the U blocks and 20..23 the V blocks; a 4x4 block lives
+// entirely in one lane's registers from the pixel loads to the reconstructed store (DCT, quant,
+// zig-zag, dequant, decimate score, IDCT).  The decisions that couple blocks (8x8 / MB
+// decimation, chroma DC 2x2 transform, variance early-out, cbp) are taken with shuffles and
+// ballots.  HBM traffic per MB: 2 x 384 B in, 384 B recon + 784 B levels + 29 B flags out.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// motion compensation: 64 threads per macroblock (4 luma pixels + 1 UV pair each), 4 MBs per CTA
+__global__ void __launch_bounds__( 256 )
+xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const int16_t *__restrict__ mv,
+                    uint8_t *__restrict__ pred )
+{
+    const int mb = blockIdx.x * 4 + ( threadIdx.x >> 6 );
+    if( mb >= g.mb_count )
+        return;
+    const int t = threadIdx.x & 63;
+    const int mb_x = mb % g.mb_w, mb_y = mb / g.mb_w;
+    const int ls = g.luma_stride, cs = g.chroma_stride;
+    // analyse.c:378-390: mv_min / mv_max of the macroblock (quarter-pel)
+    const int mvx = xd_clip3( mv[2 * mb], ( -( mb_x << 4 ) - 24 ) << 2, ( ( ( g.mb_w - mb_x - 1 ) << 4 ) + 24 ) << 2 );
+    const int mvy = xd_clip3( mv[2 * mb + 1], ( -( mb_y << 4 ) - 24 ) << 2, ( ( ( g.mb_h - mb_y - 1 ) << 4 ) + 24 ) << 2 );
+    {
+        // luma: row t/4, pixels 4*(t%4) .. +3
+        const int y = t >> 2, x = ( t & 3 ) * 4;
+        const int fx = mvx & 3, fy = mvy & 3, phase = fy * 4 + fx;
+        const int64_t pos = (int64_t)( ( mb_y << 4 ) + y + ( mvy >> 2 ) ) * ls + ( mb_x << 4 ) + x + ( mvx >> 2 );
+        const uint8_t *base = fref + g.luma_origin;
+        uint32_t a = xd_load4_unaligned( base + (size_t)xd_qpel_plane_a( phase ) * g.luma_plane_size + pos + ( fy == 3 ? ls : 0 ) );
+        if( phase & 5 )
+            a = xd_avg4( a, xd_load4_unaligned( base + (size_t)xd_qpel_plane_b( phase ) * g.luma_plane_size + pos + ( fx == 3 ? 1 : 0 ) ) );
+        *(uint32_t *)( pred + g.luma_origin + (int64_t)( ( mb_y << 4 ) + y ) * ls + ( mb_x << 4 ) + x ) = a;
+    }
+    {
+        // chroma: row t/8, pair t%8; eighth-pel bilinear on NV12 (mc.c:290-323)
+        const int y = t >> 3, x = t & 7;
+        const int dx = mvx & 7, dy = mvy & 7;
+        const int cA = ( 8 - dx ) * ( 8 - dy ), cB = dx * ( 8 - dy ), cC = ( 8 - dx ) * dy, cD = dx * dy;
+        const uint8_t *s0 = fref + g.slot_chroma_off + g.chroma_origin
+                          + (int64_t)( ( mb_y << 3 ) + y + ( mvy >> 3 ) ) * cs + ( mb_x << 4 ) + 2 * ( x + ( mvx >> 3 ) );
+        const uint8_t *s1 = s0 + cs;
+        const int u = ( cA * __ldg( s0 ) + cB * __ldg( s0 + 2 ) + cC * __ldg( s1 ) + cD * __ldg( s1 + 2 ) + 32 ) >> 6;
+        const int v = ( cA * __ldg( s0 + 1 ) + cB * __ldg( s0 + 3 ) + cC * __ldg( s1 + 1 ) + cD * __ldg( s1 + 3 ) + 32 ) >> 6;
+        *(uint16_t *)( pred + g.slot_chroma_off + g.chroma_origin + (int64_t)( ( mb_y << 3 ) + y ) * cs + ( mb_x << 4 ) + 2 * x )
+            = (uint16_t)( u | ( v << 8 ) );
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4x4 pipeline in registers
+
+__device__ __forceinline__ void xd_fwd4( int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3 )
+{
+    const int s_ad = a + d, s_bc = b + c, d_ad = a - d, d_bc = b - c;
+    o0 = s_ad + s_bc; o1 = 2 * d_ad + d_bc; o2 = s_ad - s_bc; o3 = d_ad - 2 * d_bc;
+}
+
+__device__ __forceinline__ void xd_inv4( int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3 )
+{
+    const int e = a + c, f = a - c, gg = b + ( d >> 1 ), hh = ( b >> 1 ) - d;
+    o0 = e + gg; o1 = f + hh; o2 = f - hh; o3 = e - gg;
+}
+
+// residual 4x4 DCT: f, p = four packed rows each (dct.c:115-150)
+__device__ __forceinline__ void xd_sub4x4_dct( int dct[16], const uint32_t f[4], const uint32_t p[4] )
+{
+    int t[16];
+#pragma unroll
+    for( int r = 0; r < 4; r++ )
+    {
+        const int d0 = (int)( f[r] & 255 ) - (int)( p[r] & 255 );
+        const int d1 = (int)( ( f[r] >> 8 ) & 255 ) - (int)( ( p[r] >> 8 ) & 255 );
+        const int d2 = (int)( ( f[r] >> 16 ) & 255 ) - (int)( ( p[r] >> 16 ) & 255 );
+        const int d3 = (int)( f[r] >> 24 ) - (int)( p[r] >> 24 );
+        xd_fwd4( d0, d1, d2, d3, t[r], t[4 + r], t[8 + r], t[12 + r] );
+    }
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+        xd_fwd4( t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3], dct[4 * i], dct[4 * i + 1], dct[4 * i + 2], dct[4 * i + 3] );
+}
+
+// inverse transform + add to the prediction rows, clipped (dct.c:197-235); coefficients are
+// truncated to 16 bits between the stages exactly as the reference's dctcoef stores do
+__device__ __forceinline__ void xd_add4x4_idct( uint32_t p[4], const int dct[16] )
+{
+    int t[16], r[16];
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        int o0, o1, o2, o3;
+        xd_inv4( dct[i], dct[4 + i], dct[8 + i], dct[12 + i], o0, o1, o2, o3 );
+        t[4 * i] = (int16_t)o0; t[4 * i + 1] = (int16_t)o1; t[4 * i + 2] = (int16_t)o2; t[4 * i + 3] = (int16_t)o3;
+    }
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        int o0, o1, o2, o3;
+        xd_inv4( t[i], t[4 + i], t[8 + i], t[12 + i], o0, o1, o2, o3 );
+        r[i] = (int16_t)( ( o0 + 32 ) >> 6 ); r[4 + i] = (int16_t)( ( o1 + 32 ) >> 6 );
+        r[8 + i] = (int16_t)( ( o2 + 32 ) >> 6 ); r[12 + i] = (int16_t)( ( o3 + 32 ) >> 6 );
+    }
+#pragma unroll
+    for( int y = 0; y < 4; y++ )
+    {
+        uint32_t w = 0;
+#pragma unroll
+        for( int x = 0; x < 4; x++ )
+            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + r[4 * y + x] ) << ( 8 * x );
+        p[y] = w;
+    }
+}
+
+__device__ __forceinline__ void xd_add4x4_dc( uint32_t p[4], int dc )
+{
+    dc = (int16_t)( ( dc + 32 ) >> 6 );
+#pragma unroll
+    for( int y = 0; y < 4; y++ )
+    {
+        uint32_t w = 0;
+#pragma unroll
+        for( int x = 0; x < 4; x++ )
+            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + dc ) << ( 8 * x );
+        p[y] = w;
+    }
+}
+
+// quant.c:29-36
+__device__ __forceinline__ int xd_quant1( int c, int mf, int bias )
+{
+    return (int16_t)( c > 0 ? ( ( bias + c ) * mf ) >> 16 : -( ( ( bias - c ) * mf ) >> 16 ) );
+}
+
+// position class of coefficient i for the flat quant matrices: 0 (even,even) 1 (mixed) 2 (odd,odd)
+#define XD_POS_CLASS( i ) ( ( ( i ) & 1 ) + ( ( ( i ) >> 2 ) & 1 ) )
+
+struct xd_qparams
+{
+    int mf[3], bias[3], dmf[3];      // per position class
+    int qbits;                       // qp/6 - 4
+};
+
+__device__ __forceinline__ int xd_quant_4x4( int dct[16], const xd_qparams &Q )
+{
+    int nz = 0;
+#pragma unroll
+    for( int i = 0; i < 16; i++ )
+    {
+        dct[i] = xd_quant1( dct[i], Q.mf[XD_POS_CLASS( i )], Q.bias[XD_POS_CLASS( i )] );
+        nz |= dct[i];
+    }
+    return nz != 0;
+}
+
+// quant.c:64-81
+__device__ __forceinline__ void xd_dequant_4x4( int dct[16], const xd_qparams &Q )
+{
+    if( Q.qbits >= 0 )
+    {
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+            dct[i] = (int16_t)( ( dct[i] * Q.dmf[XD_POS_CLASS( i )] ) << Q.qbits );
+    }
+    else
+    {
+        const int f = 1 << ( -Q.qbits - 1 );
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+            dct[i] = (int16_t)( ( dct[i] * Q.dmf[XD_POS_CLASS( i )] + f ) >> ( -Q.qbits ) );
+    }
+}
+
+// zig-zag order (dct.c:329-347)
+__device__ __forceinline__ void xd_zigzag( int lv[16], const int q[16] )
+{
+    lv[0] = q[0];   lv[1] = q[4];   lv[2] = q[1];   lv[3] = q[2];
+    lv[4] = q[5];   lv[5] = q[8];   lv[6] = q[12];  lv[7] = q[9];
+    lv[8] = q[6];   lv[9] = q[3];   lv[10] = q[7];  lv[11] = q[10];
+    lv[12] = q[13]; lv[13] = q[14]; lv[14] = q[11]; lv[15] = q[15];
+}
+
+// x264_decimate_score_internal (quant.c:226-252) over lv[first..15]
+__device__ __forceinline__ int xd_decimate( const int lv[16], int first )
+{
+    int score = 0, run = 0;
+    bool seen = false, big = false;
+#pragma unroll
+    for( int i = 15; i >= 0; i-- )
+    {
+        if( i < first )
+            continue;
+        const int v = lv[i];
+        if( v != 0 )
+        {
+            big |= v > 1 || v < -1;
+            if( seen )
+                score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;
+            seen = true;
+            run = 0;
+        }
+        else if( seen )
+            run++;
+    }
+    if( seen )
+        score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;
+    return big ? 9 : score;
+}
+
+__device__ __forceinline__ void xd_store_levels( int16_t *dst, const int lv[16] )
+{
+    uint4 a, b;
+    a.x = ( lv[0] & 0xFFFF ) | ( lv[1] << 16 );   a.y = ( lv[2] & 0xFFFF ) | ( lv[3] << 16 );
+    a.z = ( lv[4] & 0xFFFF ) | ( lv[5] << 16 );   a.w = ( lv[6] & 0xFFFF ) | ( lv[7] << 16 );
+    b.x = ( lv[8] & 0xFFFF ) | ( lv[9] << 16 );   b.y = ( lv[10] & 0xFFFF ) | ( lv[11] << 16 );
+    b.z = ( lv[12] & 0xFFFF ) | ( lv[13] << 16 ); b.w = ( lv[14] & 0xFFFF ) | ( lv[15] << 16 );
+    ( (uint4 *)dst )[0] = a;
+    ( (uint4 *)dst )[1] = b;
+}
+
+// quant.c:133-192 on one lane
+__device__ __forceinline__ void xd_chroma_dc_recon( int out[4], const int dc[4], int dmf )
+{
+    const int a = dc[0] + dc[1], b = dc[2] + dc[3], c = dc[0] - dc[1], d = dc[2] - dc[3];
+    out[0] = (int16_t)( ( ( a + b ) * dmf >> 5 ) + 32 );
+    out[1] = (int16_t)( ( ( a - b ) * dmf >> 5 ) + 32 );
+    out[2] = (int16_t)( ( ( c + d ) * dmf >> 5 ) + 32 );
+    out[3] = (int16_t)( ( ( c - d ) * dmf >> 5 ) + 32 );
+}
+
+__device__ int xd_optimize_chroma_dc( int dc[4], int dmf )
+{
+    int want[4], got[4];
+    xd_chroma_dc_recon( want, dc, dmf );
+    if( !( ( want[0] | want[1] | want[2] | want[3] ) >> 6 ) )
+        return 0;
+    int nz = 0;
+    for( int k = 3; k >= 0; k-- )
+    {
+        int level = dc[k];
+        const int step = level < 0 ? -1 : 1;
+        while( level )
+        {
+            dc[k] = (int16_t)( level - step );
+            xd_chroma_dc_recon( got, dc, dmf );
+            const int diff = ( want[0] ^ got[0] ) | ( want[1] ^ got[1] ) | ( want[2] ^ got[2] ) | ( want[3] ^ got[3] );
+            if( diff >> 6 )
+            {
+                nz = 1;
+                dc[k] = (int16_t)level;
+                break;
+            }
+            level -= step;
+        }
+    }
+    return nz;
+}
+
+struct xd_res_tables
+{
+    xd_qparams luma, chroma;
+    int chroma_dc_mf, chroma_dc_bias, chroma_dmf_full;   // mf[0]>>1, bias[0]<<1, dequant_mf[qpc%6][0] << qpc/6
+    int qpc, thresh;                                      // chroma qp, (lambda2[qpc]+32)>>6
+};
+
+__global__ void __launch_bounds__( 128 )
+xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t *__restrict__ pred,
+                    xd_res_tables T, int16_t *__restrict__ levels, uint8_t *__restrict__ nnz_out,
+                    int16_t *__restrict__ cbp_out )
+{
+    const int lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * 4 + ( threadIdx.x >> 5 );
+    if( mb >= g.mb_count )
+        return;
+    const int mb_x = mb % g.mb_w, mb_y = mb / g.mb_w;
+    const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
+    const int ch = ( lane - 16 ) >> 2, ci = ( lane - 16 ) & 3;
+
+    // ---- load the lane's 4x4 source and prediction rows
+    uint32_t f[4] = { 0, 0, 0, 0 }, p[4] = { 0, 0, 0, 0 };
+    int64_t luma_off = 0, chroma_off = 0;
+    if( is_luma )
+    {
+        const int bx = ( ( lane & 1 ) + ( ( lane >> 2 ) & 1 ) * 2 ) * 4, by = ( ( ( lane >> 1 ) & 1 ) + ( ( lane >> 3 ) & 1 ) * 2 ) * 4;
+        luma_off = g.luma_origin + (int64_t)( ( mb_y << 4 ) + by ) * g.luma_stride + ( mb_x << 4 ) + bx;
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            f[r] = __ldg( (const uint32_t *)( fenc + luma_off + (int64_t)r * g.luma_stride ) );
+            p[r] = *(const uint32_t *)( pred + luma_off + (int64_t)r * g.luma_stride );
+        }
+    }
+    else if( is_chroma )
+    {
+        const int bx = ( ci & 1 ) * 4, by = ( ci >> 1 ) * 4;
+        chroma_off = g.slot_chroma_off + g.chroma_origin + (int64_t)( ( mb_y << 3 ) + by ) * g.chroma_stride + ( mb_x << 4 ) + 2 * bx;
+        const uint32_t sel = ch ? 0x7531 : 0x6420;
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            const uint2 a = __ldg( (const uint2 *)( fenc + chroma_off + (int64_t)r * g.chroma_stride ) );
+            const uint2 b = *(const uint2 *)( pred + chroma_off + (int64_t)r * g.chroma_stride );
+            f[r] = __byte_perm( a.x, a.y, sel );
+            p[r] = __byte_perm( b.x, b.y, sel );
+        }
+    }
+
+    int dct[16], lv[16];
+    xd_sub4x4_dct( dct, f, p );
+
+    // ---- chroma: variance early-out statistics (macroblock.c:188-196, pixel.c:209-231)
+    int diff_sum = dct[0];                         // sum of the 16 differences == DC coefficient
+    int diff_sqr = 0;
+    if( is_chroma )
+    {
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            const uint32_t d = __vabsdiffu4( f[r], p[r] );
+            diff_sqr += __dp4a( d, d, 0u );
+        }
+    }
+    int psum = diff_sum, psqr = diff_sqr;          // totals over the 4 lanes of a plane
+    psum += __shfl_xor_sync( 0xffffffffu, psum, 1 ); psqr += __shfl_xor_sync( 0xffffffffu, psqr, 1 );
+    psum += __shfl_xor_sync( 0xffffffffu, psum, 2 ); psqr += __shfl_xor_sync( 0xffffffffu, psqr, 2 );
+    const int sum_u = __shfl_sync( 0xffffffffu, psum, 16 ), sqr_u = __shfl_sync( 0xffffffffu, psqr, 16 );
+    const int sum_v = __shfl_sync( 0xffffffffu, psum, 20 ), sqr_v = __shfl_sync( 0xffffffffu, psqr, 20 );
+    bool early = false;
+    if( T.qpc >= 18 )
+    {
+        const unsigned au = (unsigned)abs( sum_u ), av = (unsigned)abs( sum_v );
+        const int var_u = (int)( (unsigned)sqr_u - (unsigned)( ( (unsigned long long)au * au ) >> 6 ) );
+        const int var_v = (int)( (unsigned)sqr_v - (unsigned)( ( (unsigned long long)av * av ) >> 6 ) );
+        early = var_u < ( T.thresh << 2 ) && var_u + var_v < ( T.thresh << 2 );
+    }
+
+    // ---- chroma DC of the plane: 2x2 transform of the four DC terms, on every lane of the plane
+    const int base4 = lane & ~3;
+    const int c0 = __shfl_sync( 0xffffffffu, dct[0], base4 ), c1 = __shfl_sync( 0xffffffffu, dct[0], base4 + 1 );
+    const int c2 = __shfl_sync( 0xffffffffu, dct[0], base4 + 2 ), c3 = __shfl_sync( 0xffffffffu, dct[0], base4 + 3 );
+    int dc[4] = { (int16_t)( c0 + c1 + c2 + c3 ), (int16_t)( c0 + c1 - c2 - c3 ), (int16_t)( c0 - c1 + c2 - c3 ), (int16_t)( c0 - c1 - c2 + c3 ) };
+    // note the reference's ordering d[1] = (c0+c1)-(c2+c3), d[2] = (c0-c1)+(c2-c3)
+
+    const xd_qparams &Q = is_luma ? T.luma : T.chroma;
+    if( is_chroma )
+        dct[0] = 0;                                // dct2x2dc clears the DC terms (macroblock.c:55-58)
+    int nz = 0, score = 0;
+    if( is_luma || ( is_chroma && !early ) )
+    {
+        nz = xd_quant_4x4( dct, Q );
+        xd_zigzag( lv, dct );
+        if( nz )
+        {
+            xd_dequant_4x4( dct, Q );
+            score = xd_decimate( lv, is_luma ? 0 : 1 );
+        }
+    }
+    else
+    {
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+            lv[i] = 0;
+    }
+    int16_t *mb_levels = levels + (size_t)mb * X264DSP_RES_LEVELS_PER_MB;
+    if( is_luma )
+        xd_store_levels( mb_levels + lane * 16, lv );
+    else if( is_chroma )
+        xd_store_levels( mb_levels + 264 + ( lane - 16 ) * 16, lv );
+
+    // ---- luma decimation (macroblock.c:394-452): scores add up in coding order while < 6
+    const int s0 = __shfl_sync( 0xffffffffu, score, base4 ), s1 = __shfl_sync( 0xffffffffu, score, base4 + 1 );
+    const int s2 = __shfl_sync( 0xffffffffu, score, base4 + 2 ), s3 = __shfl_sync( 0xffffffffu, score, base4 + 3 );
+    int score8 = s0;
+    if( score8 < 6 ) score8 += s1;
+    if( score8 < 6 ) score8 += s2;
+    if( score8 < 6 ) score8 += s3;
+    // (a block that quantised to zero has score 0, which is what "skipped" adds)
+    const int mb_score = __shfl_sync( 0xffffffffu, score8, 0 ) + __shfl_sync( 0xffffffffu, score8, 4 )
+                       + __shfl_sync( 0xffffffffu, score8, 8 ) + __shfl_sync( 0xffffffffu, score8, 12 );
+    const bool keep8 = score8 >= 4 && mb_score >= 6;
+    int nnz_flag = 0;
+    if( is_luma )
+    {
+        nnz_flag = keep8 ? nz : 0;
+        if( keep8 )
+            xd_add4x4_idct( p, dct );
+    }
+    const unsigned keep_mask = __ballot_sync( 0xffffffffu, is_luma && keep8 );
+    const int cbp_luma = ( ( keep_mask >> 0 ) & 1 ) | ( ( ( keep_mask >> 4 ) & 1 ) << 1 )
+                       | ( ( ( keep_mask >> 8 ) & 1 ) << 2 ) | ( ( ( keep_mask >> 12 ) & 1 ) << 3 );
+
+    // ---- chroma (macroblock.c:175-305)
+    int nz_dc_final = 0, plane_cbp = 0;
+    int dc_levels[4] = { 0, 0, 0, 0 };
+    if( is_chroma )
+    {
+        const int dmf = T.chroma_dmf_full;
+        const int psc = s0 + s1 + s2 + s3;                          // decimate score of the plane
+        const unsigned nzmask = __ballot_sync( 0x00ff0000u, nz != 0 );
+        const bool nz_ac = ( ( nzmask >> base4 ) & 15 ) != 0;
+        const int ssd = ch ? sqr_v : sqr_u;
+        bool do_dc = false, ac_coded = false;
+        if( early )
+            do_dc = ssd > T.thresh;
+        else
+        {
+            ac_coded = !( psc < 7 || !nz_ac );
+            do_dc = true;
+        }
+        int nz_dc = 0;
+        if( do_dc )
+        {
+            nz_dc = 0;
+#pragma unroll
+            for( int i = 0; i < 4; i++ )
+            {
+                dc[i] = xd_quant1( dc[i], T.chroma_dc_mf, T.chroma_dc_bias );
+                nz_dc |= dc[i];
+            }
+            nz_dc = nz_dc != 0;
+        }
+        nz_dc_final = nz_dc;
+        if( nz_dc && !ac_coded && T.qpc <= 22 )
+        {
+            // every lane of the plane runs the same scalar optimiser on the same values
+            if( !xd_optimize_chroma_dc( dc, dmf ) )
+                nz_dc_final = 0;
+        }
+        if( ac_coded )
+        {
+            plane_cbp = 1;
+            if( nz_dc )
+            {
+                // idct_dequant_2x2_dc (macroblock.c:17-29): this lane's DC term
+                const int a = dc[0] + dc[1], b = dc[2] + dc[3], c = dc[0] - dc[1], d = dc[2] - dc[3];
+                const int rec = ci == 0 ? a + b : ci == 1 ? a - b : ci == 2 ? c + d : c - d;
+                dct[0] = (int16_t)( rec * ( dmf >> 5 ) );
+            }
+            xd_add4x4_idct( p, dct );
+            nnz_flag = nz;
+        }
+        else
+        {
+            nnz_flag = 0;
+            if( nz_dc_final )
+            {
+                const int a = dc[0] + dc[1], b = dc[2] + dc[3], c = dc[0] - dc[1], d = dc[2] - dc[3];
+                const int rec = ci == 0 ? a + b : ci == 1 ? a - b : ci == 2 ? c + d : c - d;
+                xd_add4x4_dc( p, (int16_t)( rec * ( dmf >> 5 ) ) );
+                if( early )
+                    plane_cbp = 1;
+            }
+        }
+        if( nz_dc_final )
+        {
+            dc_levels[0] = dc[0]; dc_levels[1] = dc[2]; dc_levels[2] = dc[1]; dc_levels[3] = dc[3];
+        }
+        if( ci == 0 )
+            *(uint2 *)( mb_levels + 256 + 4 * ch ) = make_uint2( ( dc_levels[0] & 0xFFFF ) | ( dc_levels[1] << 16 ),
+                                                                 ( dc_levels[2] & 0xFFFF ) | ( dc_levels[3] << 16 ) );
+    }
+
+    // ---- stores: reconstruction, flags
+    if( is_luma )
+    {
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+            *(uint32_t *)( pred + luma_off + (int64_t)r * g.luma_stride ) = p[r];
+    }
+    // interleave U (lanes 16..19) with V (lanes 20..23)
+    uint32_t other[4];
+#pragma unroll
+    for( int r = 0; r < 4; r++ )
+        other[r] = __shfl_sync( 0xffffffffu, p[r], is_chroma ? lane ^ 4 : lane );
+    if( is_chroma && ch == 0 )
+    {
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            const uint32_t lo = __byte_perm( p[r], other[r], 0x5140 ), hi = __byte_perm( p[r], other[r], 0x7362 );
+            *(uint2 *)( pred + chroma_off + (int64_t)r * g.chroma_stride ) = make_uint2( lo, hi );
+        }
+    }
+
+    const int dc_u = __shfl_sync( 0xffffffffu, nz_dc_final, 16 ), dc_v = __shfl_sync( 0xffffffffu, nz_dc_final, 20 );
+    const int pc_u = __shfl_sync( 0xffffffffu, plane_cbp, 16 ), pc_v = __shfl_sync( 0xffffffffu, plane_cbp, 20 );
+    int cbp_chroma = pc_u | pc_v;
+    if( !early )
+        cbp_chroma += dc_u | dc_v | cbp_chroma;                          // macroblock.c:303-304
+    uint8_t *mb_nnz = nnz_out + (size_t)mb * X264DSP_RES_NNZ_PER_MB;
+    if( lane < 24 )
+        mb_nnz[lane] = (uint8_t)nnz_flag;
+    if( lane == 24 )
+        mb_nnz[24] = 0;                                                  // luma DC: inter MB
+    if( lane == 25 )
+        mb_nnz[25] = (uint8_t)dc_u;
+    if( lane == 26 )
+        mb_nnz[26] = (uint8_t)dc_v;
+    if( lane == 0 )
+        cbp_out[mb] = (int16_t)( ( cbp_chroma << 4 ) | cbp_luma | ( dc_u << 9 ) | ( dc_v << 10 ) );
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static const int xd_lambda2_tab[52] =
+{
+        14,     18,     22,     28,     36,     45,     57,     72,     91,    115,    145,    182,    230,
+       290,    365,    460,    580,    731,    921,   1161,   1462,   1843,   2322,   2925,   3686,   4644,
+      5851,   7372,   9289,  11703,  14745,  18578,  23407,  29491,  37156,  46814,  58982,  74313,  93628,
+    117964, 148626, 187257, 235929, 297252, 374514, 471859, 594505, 749029, 943718,1189010,1498059,1887436
+};
+
+static void xd_fill_qparams( xd_qparams *q, int qp )
+{
+    uint16_t mf[16], bias[16];
+    int dq[6][16];
+    x264dsp_quant_tables( 1, qp, mf, bias );
+    x264dsp_dequant_table( dq );
+    static const int rep[3] = { 0, 1, 5 };          // a position of each class
+    for( int c = 0; c < 3; c++ )
+    {
+        q->mf[c] = mf[rep[c]];
+        q->bias[c] = bias[rep[c]];
+        q->dmf[c] = dq[qp % 6][rep[c]];
+    }
+    q->qbits = qp / 6 - 4;
+}
+
+extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                            const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
+                                            int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream )
+{
+    if( !ctx || !g || !fenc_slot || !pred_slot || !levels || !nnz || !cbp || qp < 0 || qp > 51 )
+        return X264DSP_E_ARG;
+    xd_res_tables T;
+    const int qpc = x264dsp_chroma_qp( qp );
+    xd_fill_qparams( &T.luma, qp );
+    xd_fill_qparams( &T.chroma, qpc );
+    {
+        uint16_t mf[16], bias[16];
+        int dq[6][16];
+        x264dsp_quant_tables( 1, qpc, mf, bias );
+        x264dsp_dequant_table( dq );
+        T.chroma_dc_mf = mf[0] >> 1;
+        T.chroma_dc_bias = bias[0] << 1;
+        T.chroma_dmf_full = dq[qpc % 6][0] << ( qpc / 6 );
+    }
+    T.qpc = qpc;
+    T.thresh = ( xd_lambda2_tab[qpc] + 32 ) >> 6;
+    cudaStream_t s = xd_stream( ctx, stream );
+    const int grid = ( g->mb_count + 3 ) / 4;
+    const int pslot = xd_prof_begin( ctx, XD_PROF_RESIDUAL, s );
+    xd_residual_kernel<<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, levels, nnz, cbp );
+    xd_prof_end( ctx, XD_PROF_RESIDUAL, pslot, s );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
+}
+
+extern "C" int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,
+                                      const int16_t *mv, uint8_t *pred_slot, void *stream )
+{
+    if( !ctx || !g || !fref_slot || !mv || !pred_slot || fref_slot == pred_slot )
+        return X264DSP_E_ARG;
+    cudaStream_t s = xd_stream( ctx, stream );
+    const int grid = ( g->mb_count + 3 ) / 4;
+    const int pslot = xd_prof_begin( ctx, XD_PROF_MC, s );
+    xd_mc_frame_kernel<<<grid, 256, 0, s>>>( *g, fref_slot, mv, pred_slot );
+    xd_prof_end( ctx, XD_PROF_MC, pslot, s );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
+}
