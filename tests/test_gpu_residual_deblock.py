@@ -69,7 +69,7 @@ def test_mc_and_residual_frame(pkg, ctx, w, h, qp):
     assert len(bad) == 0, f"levels differ at MBs {bad[:5]}"
     assert np.array_equal(pred.cpu().numpy(), pred_o), "reconstruction"
     # the test must exercise coded, decimated and skipped macroblocks
-    assert (cbp_o == 0).any() or qp < 20
+    assert (cbp_o == 0).any() or qp < 30
     assert (cbp_o != 0).any()
 
 
