@@ -10,40 +10,8 @@
 // and the units are dealt round-robin to the 8 lanes; three xor-shuffles finish the sum.
 // Blocks may start at any byte address (pix2 is a motion-compensated position).
 #include "common.cuh"
+#include "leaf.cuh"
 
-__constant__ uint8_t xd_blk_w[8] = { 16, 16, 8, 8, 8, 4, 4, 4 };
-__constant__ uint8_t xd_blk_h[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
-
-__device__ __forceinline__ int xd_had_abs4x4( const uint32_t a[4], const uint32_t b[4] )
-{
-    int t[4][4];
-#pragma unroll
-    for( int r = 0; r < 4; r++ )
-    {
-        const int d0 = (int)( a[r] & 255 ) - (int)( b[r] & 255 );
-        const int d1 = (int)( ( a[r] >> 8 ) & 255 ) - (int)( ( b[r] >> 8 ) & 255 );
-        const int d2 = (int)( ( a[r] >> 16 ) & 255 ) - (int)( ( b[r] >> 16 ) & 255 );
-        const int d3 = (int)( a[r] >> 24 ) - (int)( b[r] >> 24 );
-        const int s01 = d0 + d1, m01 = d0 - d1, s23 = d2 + d3, m23 = d2 - d3;
-        t[r][0] = s01 + s23; t[r][1] = s01 - s23; t[r][2] = m01 + m23; t[r][3] = m01 - m23;
-    }
-    int acc = 0;
-#pragma unroll
-    for( int c = 0; c < 4; c++ )
-    {
-        const int s01 = t[0][c] + t[1][c], m01 = t[0][c] - t[1][c];
-        const int s23 = t[2][c] + t[3][c], m23 = t[2][c] - t[3][c];
-        acc += abs( s01 + s23 ) + abs( s01 - s23 ) + abs( m01 + m23 ) + abs( m01 - m23 );
-    }
-    return acc;
-}
-
-__device__ __forceinline__ uint32_t xd_sq4( uint32_t a, uint32_t b )
-{
-    // sum of squared differences of four packed pixels
-    const uint32_t d = __vabsdiffu4( a, b );
-    return __dp4a( d, d, 0u );
-}
 
 __global__ void __launch_bounds__( 256 )
 xd_cost_batch_kernel( int cmp, int n, const uint8_t *__restrict__ pix1, const int64_t *__restrict__ off1, int stride1,

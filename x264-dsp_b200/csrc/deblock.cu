@@ -16,114 +16,7 @@
 //     accesses (ld.cg / st.cg), a __syncwarp between the two passes and a fence before the row
 //     counter is advanced.
 #include "common.cuh"
-
-__constant__ uint8_t xd_alpha_tab[52] =
-{
-    0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0, 4,4,5,6,7,8,9,10,12,13,15,17,20,22,
-    25,28,32,36,40,45,50,56,63,71,80,90,101,113,127,144,162,182,203,226,255,255
-};
-__constant__ uint8_t xd_beta_tab[52] =
-{
-    0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0, 2,2,2,3,3,3,3,4,4,4,6,6,7,7,
-    8,8,9,9,10,10,11,11,12,12,13,13,14,14,15,15,16,16,17,17,18,18
-};
-__constant__ int8_t xd_tc0_tab[52][3] =
-{
-    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},
-    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,1},{0,0,1},{0,0,1},
-    {0,0,1},{0,1,1},{0,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,2},{1,1,2},{1,1,2},
-    {1,1,2},{1,2,3},{1,2,3},{2,2,3},{2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},
-    {4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},{10,13,20},
-    {11,15,23},{13,17,25}
-};
-
-struct xd_db_params
-{
-    int alpha, beta, alphac, betac;     // luma / chroma thresholds from the slice QP
-    int ia, iac;                        // clamped indexA (luma, chroma); < 0 : tc0 = 0
-};
-
-__device__ __forceinline__ int xd_tc0( int index_a, int bs )
-{
-    if( bs == 0 )
-        return -1;
-    return index_a < 0 ? 0 : xd_tc0_tab[index_a][bs - 1];
-}
-
-// bS < 4 luma line: s[0..7] = p3 p2 p1 p0 q0 q1 q2 q3 (deblock.c:80-120)
-__device__ __forceinline__ void xd_luma_line( int s[8], int alpha, int beta, int tc0 )
-{
-    const int p2 = s[1], p1 = s[2], p0 = s[3], q0 = s[4], q1 = s[5], q2 = s[6];
-    if( abs( p0 - q0 ) >= alpha || abs( p1 - p0 ) >= beta || abs( q1 - q0 ) >= beta )
-        return;
-    int tc = tc0;
-    if( abs( p2 - p0 ) < beta )
-    {
-        if( tc0 )
-            s[2] = p1 + xd_clip3( ( ( p2 + ( ( p0 + q0 + 1 ) >> 1 ) ) >> 1 ) - p1, -tc0, tc0 );
-        tc++;
-    }
-    if( abs( q2 - q0 ) < beta )
-    {
-        if( tc0 )
-            s[5] = q1 + xd_clip3( ( ( q2 + ( ( p0 + q0 + 1 ) >> 1 ) ) >> 1 ) - q1, -tc0, tc0 );
-        tc++;
-    }
-    const int delta = xd_clip3( ( ( ( q0 - p0 ) << 2 ) + ( p1 - q1 ) + 4 ) >> 3, -tc, tc );
-    s[3] = xd_clip_u8( p0 + delta );
-    s[4] = xd_clip_u8( q0 - delta );
-}
-
-// bS = 4 luma line (deblock.c:196-243)
-__device__ __forceinline__ void xd_luma_intra_line( int s[8], int alpha, int beta )
-{
-    const int p3 = s[0], p2 = s[1], p1 = s[2], p0 = s[3], q0 = s[4], q1 = s[5], q2 = s[6], q3 = s[7];
-    if( abs( p0 - q0 ) >= alpha || abs( p1 - p0 ) >= beta || abs( q1 - q0 ) >= beta )
-        return;
-    if( abs( p0 - q0 ) < ( ( alpha >> 2 ) + 2 ) )
-    {
-        if( abs( p2 - p0 ) < beta )
-        {
-            s[3] = ( p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4 ) >> 3;
-            s[2] = ( p2 + p1 + p0 + q0 + 2 ) >> 2;
-            s[1] = ( 2 * p3 + 3 * p2 + p1 + p0 + q0 + 4 ) >> 3;
-        }
-        else
-            s[3] = ( 2 * p1 + p0 + q1 + 2 ) >> 2;
-        if( abs( q2 - q0 ) < beta )
-        {
-            s[4] = ( p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4 ) >> 3;
-            s[5] = ( p0 + q0 + q1 + q2 + 2 ) >> 2;
-            s[6] = ( 2 * q3 + 3 * q2 + q1 + q0 + p0 + 4 ) >> 3;
-        }
-        else
-            s[4] = ( 2 * q1 + q0 + p1 + 2 ) >> 2;
-    }
-    else
-    {
-        s[3] = ( 2 * p1 + p0 + q1 + 2 ) >> 2;
-        s[4] = ( 2 * q1 + q0 + p1 + 2 ) >> 2;
-    }
-}
-
-// chroma line: s = p1 p0 q0 q1 (deblock.c:147-167, 261-278)
-__device__ __forceinline__ void xd_chroma_line( int s[4], int alpha, int beta, int tc, bool intra )
-{
-    const int p1 = s[0], p0 = s[1], q0 = s[2], q1 = s[3];
-    if( abs( p0 - q0 ) >= alpha || abs( p1 - p0 ) >= beta || abs( q1 - q0 ) >= beta )
-        return;
-    if( intra )
-    {
-        s[1] = ( 2 * p1 + p0 + q1 + 2 ) >> 2;
-        s[2] = ( 2 * q1 + q0 + p1 + 2 ) >> 2;
-    }
-    else
-    {
-        const int delta = xd_clip3( ( ( ( q0 - p0 ) << 2 ) + ( p1 - q1 ) + 4 ) >> 3, -tc, tc );
-        s[1] = xd_clip_u8( p0 + delta );
-        s[2] = xd_clip_u8( q0 - delta );
-    }
-}
+#include "leaf.cuh"
 
 // what to do on one edge: mode 0 = nothing, 1 = bS<4 filter, 2 = bS=4 filter
 struct xd_edge

@@ -1,0 +1,350 @@
+// leaf.cuh -- register-level device routines shared by the batched kernels and the per-call
+// table shims: 4x4 transform / quant pipeline (common/dct.c, common/quant.c), Hadamard cost
+// (common/pixel.c:243-314), deblocking line filters (common/deblock.c:80-295).
+#pragma once
+#include "common.cuh"
+
+static __constant__ uint8_t xd_blk_w[8] = { 16, 16, 8, 8, 8, 4, 4, 4 };
+static __constant__ uint8_t xd_blk_h[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
+
+// ---------------------------------------------------------------------------------------------
+// Hadamard cost of one 4x4: sum |H4 (a-b) H4^T|, rows given as packed pixels (not yet halved)
+__device__ __forceinline__ int xd_had_abs4x4( const uint32_t a[4], const uint32_t b[4] )
+{
+    int t[4][4];
+#pragma unroll
+    for( int r = 0; r < 4; r++ )
+    {
+        const int d0 = (int)( a[r] & 255 ) - (int)( b[r] & 255 );
+        const int d1 = (int)( ( a[r] >> 8 ) & 255 ) - (int)( ( b[r] >> 8 ) & 255 );
+        const int d2 = (int)( ( a[r] >> 16 ) & 255 ) - (int)( ( b[r] >> 16 ) & 255 );
+        const int d3 = (int)( a[r] >> 24 ) - (int)( b[r] >> 24 );
+        const int s01 = d0 + d1, m01 = d0 - d1, s23 = d2 + d3, m23 = d2 - d3;
+        t[r][0] = s01 + s23; t[r][1] = s01 - s23; t[r][2] = m01 + m23; t[r][3] = m01 - m23;
+    }
+    int acc = 0;
+#pragma unroll
+    for( int c = 0; c < 4; c++ )
+    {
+        const int s01 = t[0][c] + t[1][c], m01 = t[0][c] - t[1][c];
+        const int s23 = t[2][c] + t[3][c], m23 = t[2][c] - t[3][c];
+        acc += abs( s01 + s23 ) + abs( s01 - s23 ) + abs( m01 + m23 ) + abs( m01 - m23 );
+    }
+    return acc;
+}
+
+__device__ __forceinline__ uint32_t xd_sq4( uint32_t a, uint32_t b )
+{
+    // sum of squared differences of four packed pixels
+    const uint32_t d = __vabsdiffu4( a, b );
+    return __dp4a( d, d, 0u );
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4x4 pipeline in registers
+
+__device__ __forceinline__ void xd_fwd4( int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3 )
+{
+    const int s_ad = a + d, s_bc = b + c, d_ad = a - d, d_bc = b - c;
+    o0 = s_ad + s_bc; o1 = 2 * d_ad + d_bc; o2 = s_ad - s_bc; o3 = d_ad - 2 * d_bc;
+}
+
+__device__ __forceinline__ void xd_inv4( int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3 )
+{
+    const int e = a + c, f = a - c, gg = b + ( d >> 1 ), hh = ( b >> 1 ) - d;
+    o0 = e + gg; o1 = f + hh; o2 = f - hh; o3 = e - gg;
+}
+
+// residual 4x4 DCT: f, p = four packed rows each (dct.c:115-150)
+__device__ __forceinline__ void xd_sub4x4_dct( int dct[16], const uint32_t f[4], const uint32_t p[4] )
+{
+    int t[16];
+#pragma unroll
+    for( int r = 0; r < 4; r++ )
+    {
+        const int d0 = (int)( f[r] & 255 ) - (int)( p[r] & 255 );
+        const int d1 = (int)( ( f[r] >> 8 ) & 255 ) - (int)( ( p[r] >> 8 ) & 255 );
+        const int d2 = (int)( ( f[r] >> 16 ) & 255 ) - (int)( ( p[r] >> 16 ) & 255 );
+        const int d3 = (int)( f[r] >> 24 ) - (int)( p[r] >> 24 );
+        xd_fwd4( d0, d1, d2, d3, t[r], t[4 + r], t[8 + r], t[12 + r] );
+    }
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+        xd_fwd4( t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3], dct[4 * i], dct[4 * i + 1], dct[4 * i + 2], dct[4 * i + 3] );
+}
+
+// inverse transform + add to the prediction rows, clipped (dct.c:197-235); coefficients are
+// truncated to 16 bits between the stages exactly as the reference's dctcoef stores do
+__device__ __forceinline__ void xd_add4x4_idct( uint32_t p[4], const int dct[16] )
+{
+    int t[16], r[16];
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        int o0, o1, o2, o3;
+        xd_inv4( dct[i], dct[4 + i], dct[8 + i], dct[12 + i], o0, o1, o2, o3 );
+        t[4 * i] = (int16_t)o0; t[4 * i + 1] = (int16_t)o1; t[4 * i + 2] = (int16_t)o2; t[4 * i + 3] = (int16_t)o3;
+    }
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        int o0, o1, o2, o3;
+        xd_inv4( t[i], t[4 + i], t[8 + i], t[12 + i], o0, o1, o2, o3 );
+        r[i] = (int16_t)( ( o0 + 32 ) >> 6 ); r[4 + i] = (int16_t)( ( o1 + 32 ) >> 6 );
+        r[8 + i] = (int16_t)( ( o2 + 32 ) >> 6 ); r[12 + i] = (int16_t)( ( o3 + 32 ) >> 6 );
+    }
+#pragma unroll
+    for( int y = 0; y < 4; y++ )
+    {
+        uint32_t w = 0;
+#pragma unroll
+        for( int x = 0; x < 4; x++ )
+            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + r[4 * y + x] ) << ( 8 * x );
+        p[y] = w;
+    }
+}
+
+__device__ __forceinline__ void xd_add4x4_dc( uint32_t p[4], int dc )
+{
+    dc = (int16_t)( ( dc + 32 ) >> 6 );
+#pragma unroll
+    for( int y = 0; y < 4; y++ )
+    {
+        uint32_t w = 0;
+#pragma unroll
+        for( int x = 0; x < 4; x++ )
+            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + dc ) << ( 8 * x );
+        p[y] = w;
+    }
+}
+
+// quant.c:29-36
+__device__ __forceinline__ int xd_quant1( int c, int mf, int bias )
+{
+    return (int16_t)( c > 0 ? ( ( bias + c ) * mf ) >> 16 : -( ( ( bias - c ) * mf ) >> 16 ) );
+}
+
+// position class of coefficient i for the flat quant matrices: 0 (even,even) 1 (mixed) 2 (odd,odd)
+#define XD_POS_CLASS( i ) ( ( ( i ) & 1 ) + ( ( ( i ) >> 2 ) & 1 ) )
+
+struct xd_qparams
+{
+    int mf[3], bias[3], dmf[3];      // per position class
+    int qbits;                       // qp/6 - 4
+};
+
+__device__ __forceinline__ int xd_quant_4x4( int dct[16], const xd_qparams &Q )
+{
+    int nz = 0;
+#pragma unroll
+    for( int i = 0; i < 16; i++ )
+    {
+        dct[i] = xd_quant1( dct[i], Q.mf[XD_POS_CLASS( i )], Q.bias[XD_POS_CLASS( i )] );
+        nz |= dct[i];
+    }
+    return nz != 0;
+}
+
+// quant.c:64-81
+__device__ __forceinline__ void xd_dequant_4x4( int dct[16], const xd_qparams &Q )
+{
+    if( Q.qbits >= 0 )
+    {
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+            dct[i] = (int16_t)( ( dct[i] * Q.dmf[XD_POS_CLASS( i )] ) << Q.qbits );
+    }
+    else
+    {
+        const int f = 1 << ( -Q.qbits - 1 );
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+            dct[i] = (int16_t)( ( dct[i] * Q.dmf[XD_POS_CLASS( i )] + f ) >> ( -Q.qbits ) );
+    }
+}
+
+// zig-zag order (dct.c:329-347)
+__device__ __forceinline__ void xd_zigzag( int lv[16], const int q[16] )
+{
+    lv[0] = q[0];   lv[1] = q[4];   lv[2] = q[1];   lv[3] = q[2];
+    lv[4] = q[5];   lv[5] = q[8];   lv[6] = q[12];  lv[7] = q[9];
+    lv[8] = q[6];   lv[9] = q[3];   lv[10] = q[7];  lv[11] = q[10];
+    lv[12] = q[13]; lv[13] = q[14]; lv[14] = q[11]; lv[15] = q[15];
+}
+
+// x264_decimate_score_internal (quant.c:226-252) over lv[first..15]
+__device__ __forceinline__ int xd_decimate( const int lv[16], int first )
+{
+    int score = 0, run = 0;
+    bool seen = false, big = false;
+#pragma unroll
+    for( int i = 15; i >= 0; i-- )
+    {
+        if( i < first )
+            continue;
+        const int v = lv[i];
+        if( v != 0 )
+        {
+            big |= v > 1 || v < -1;
+            if( seen )
+                score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;
+            seen = true;
+            run = 0;
+        }
+        else if( seen )
+            run++;
+    }
+    if( seen )
+        score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;
+    return big ? 9 : score;
+}
+
+__device__ __forceinline__ void xd_store_levels( int16_t *dst, const int lv[16] )
+{
+    uint4 a, b;
+    a.x = ( lv[0] & 0xFFFF ) | ( lv[1] << 16 );   a.y = ( lv[2] & 0xFFFF ) | ( lv[3] << 16 );
+    a.z = ( lv[4] & 0xFFFF ) | ( lv[5] << 16 );   a.w = ( lv[6] & 0xFFFF ) | ( lv[7] << 16 );
+    b.x = ( lv[8] & 0xFFFF ) | ( lv[9] << 16 );   b.y = ( lv[10] & 0xFFFF ) | ( lv[11] << 16 );
+    b.z = ( lv[12] & 0xFFFF ) | ( lv[13] << 16 ); b.w = ( lv[14] & 0xFFFF ) | ( lv[15] << 16 );
+    ( (uint4 *)dst )[0] = a;
+    ( (uint4 *)dst )[1] = b;
+}
+
+// quant.c:133-192 on one lane
+__device__ __forceinline__ void xd_chroma_dc_recon( int out[4], const int dc[4], int dmf )
+{
+    const int a = dc[0] + dc[1], b = dc[2] + dc[3], c = dc[0] - dc[1], d = dc[2] - dc[3];
+    out[0] = (int16_t)( ( ( a + b ) * dmf >> 5 ) + 32 );
+    out[1] = (int16_t)( ( ( a - b ) * dmf >> 5 ) + 32 );
+    out[2] = (int16_t)( ( ( c + d ) * dmf >> 5 ) + 32 );
+    out[3] = (int16_t)( ( ( c - d ) * dmf >> 5 ) + 32 );
+}
+
+__device__ __noinline__ static int xd_optimize_chroma_dc( int dc[4], int dmf )
+{
+    int want[4], got[4];
+    xd_chroma_dc_recon( want, dc, dmf );
+    if( !( ( want[0] | want[1] | want[2] | want[3] ) >> 6 ) )
+        return 0;
+    int nz = 0;
+    for( int k = 3; k >= 0; k-- )
+    {
+        int level = dc[k];
+        const int step = level < 0 ? -1 : 1;
+        while( level )
+        {
+            dc[k] = (int16_t)( level - step );
+            xd_chroma_dc_recon( got, dc, dmf );
+            const int diff = ( want[0] ^ got[0] ) | ( want[1] ^ got[1] ) | ( want[2] ^ got[2] ) | ( want[3] ^ got[3] );
+            if( diff >> 6 )
+            {
+                nz = 1;
+                dc[k] = (int16_t)level;
+                break;
+            }
+            level -= step;
+        }
+    }
+    return nz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// deblocking line filters
+static __constant__ int8_t xd_tc0_tab[52][3] =
+{
+    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},
+    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,1},{0,0,1},{0,0,1},
+    {0,0,1},{0,1,1},{0,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,2},{1,1,2},{1,1,2},
+    {1,1,2},{1,2,3},{1,2,3},{2,2,3},{2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},
+    {4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},{10,13,20},
+    {11,15,23},{13,17,25}
+};
+
+struct xd_db_params
+{
+    int alpha, beta, alphac, betac;     // luma / chroma thresholds from the slice QP
+    int ia, iac;                        // clamped indexA (luma, chroma); < 0 : tc0 = 0
+};
+
+__device__ __forceinline__ int xd_tc0( int index_a, int bs )
+{
+    if( bs == 0 )
+        return -1;
+    return index_a < 0 ? 0 : xd_tc0_tab[index_a][bs - 1];
+}
+
+// bS < 4 luma line: s[0..7] = p3 p2 p1 p0 q0 q1 q2 q3 (deblock.c:80-120)
+__device__ __forceinline__ void xd_luma_line( int s[8], int alpha, int beta, int tc0 )
+{
+    const int p2 = s[1], p1 = s[2], p0 = s[3], q0 = s[4], q1 = s[5], q2 = s[6];
+    if( abs( p0 - q0 ) >= alpha || abs( p1 - p0 ) >= beta || abs( q1 - q0 ) >= beta )
+        return;
+    int tc = tc0;
+    if( abs( p2 - p0 ) < beta )
+    {
+        if( tc0 )
+            s[2] = p1 + xd_clip3( ( ( p2 + ( ( p0 + q0 + 1 ) >> 1 ) ) >> 1 ) - p1, -tc0, tc0 );
+        tc++;
+    }
+    if( abs( q2 - q0 ) < beta )
+    {
+        if( tc0 )
+            s[5] = q1 + xd_clip3( ( ( q2 + ( ( p0 + q0 + 1 ) >> 1 ) ) >> 1 ) - q1, -tc0, tc0 );
+        tc++;
+    }
+    const int delta = xd_clip3( ( ( ( q0 - p0 ) << 2 ) + ( p1 - q1 ) + 4 ) >> 3, -tc, tc );
+    s[3] = xd_clip_u8( p0 + delta );
+    s[4] = xd_clip_u8( q0 - delta );
+}
+
+// bS = 4 luma line (deblock.c:196-243)
+__device__ __forceinline__ void xd_luma_intra_line( int s[8], int alpha, int beta )
+{
+    const int p3 = s[0], p2 = s[1], p1 = s[2], p0 = s[3], q0 = s[4], q1 = s[5], q2 = s[6], q3 = s[7];
+    if( abs( p0 - q0 ) >= alpha || abs( p1 - p0 ) >= beta || abs( q1 - q0 ) >= beta )
+        return;
+    if( abs( p0 - q0 ) < ( ( alpha >> 2 ) + 2 ) )
+    {
+        if( abs( p2 - p0 ) < beta )
+        {
+            s[3] = ( p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4 ) >> 3;
+            s[2] = ( p2 + p1 + p0 + q0 + 2 ) >> 2;
+            s[1] = ( 2 * p3 + 3 * p2 + p1 + p0 + q0 + 4 ) >> 3;
+        }
+        else
+            s[3] = ( 2 * p1 + p0 + q1 + 2 ) >> 2;
+        if( abs( q2 - q0 ) < beta )
+        {
+            s[4] = ( p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4 ) >> 3;
+            s[5] = ( p0 + q0 + q1 + q2 + 2 ) >> 2;
+            s[6] = ( 2 * q3 + 3 * q2 + q1 + q0 + p0 + 4 ) >> 3;
+        }
+        else
+            s[4] = ( 2 * q1 + q0 + p1 + 2 ) >> 2;
+    }
+    else
+    {
+        s[3] = ( 2 * p1 + p0 + q1 + 2 ) >> 2;
+        s[4] = ( 2 * q1 + q0 + p1 + 2 ) >> 2;
+    }
+}
+
+// chroma line: s = p1 p0 q0 q1 (deblock.c:147-167, 261-278)
+__device__ __forceinline__ void xd_chroma_line( int s[4], int alpha, int beta, int tc, bool intra )
+{
+    const int p1 = s[0], p0 = s[1], q0 = s[2], q1 = s[3];
+    if( abs( p0 - q0 ) >= alpha || abs( p1 - p0 ) >= beta || abs( q1 - q0 ) >= beta )
+        return;
+    if( intra )
+    {
+        s[1] = ( 2 * p1 + p0 + q1 + 2 ) >> 2;
+        s[2] = ( 2 * q1 + q0 + p1 + 2 ) >> 2;
+    }
+    else
+    {
+        const int delta = xd_clip3( ( ( ( q0 - p0 ) << 2 ) + ( p1 - q1 ) + 4 ) >> 3, -tc, tc );
+        s[1] = xd_clip_u8( p0 + delta );
+        s[2] = xd_clip_u8( q0 - delta );
+    }
+}
+

@@ -17,6 +17,7 @@
 // decimation, chroma DC 2x2 transform, variance early-out, cbp) are taken with shuffles and
 // ballots.  HBM traffic per MB: 2 x 384 B in, 384 B recon + 784 B levels + 29 B flags out.
 #include "common.cuh"
+#include "leaf.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // motion compensation: 64 threads per macroblock (4 luma pixels + 1 UV pair each), 4 MBs per CTA
@@ -57,214 +58,6 @@ xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const in
         *(uint16_t *)( pred + g.slot_chroma_off + g.chroma_origin + (int64_t)( ( mb_y << 3 ) + y ) * cs + ( mb_x << 4 ) + 2 * x )
             = (uint16_t)( u | ( v << 8 ) );
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// 4x4 pipeline in registers
-
-__device__ __forceinline__ void xd_fwd4( int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3 )
-{
-    const int s_ad = a + d, s_bc = b + c, d_ad = a - d, d_bc = b - c;
-    o0 = s_ad + s_bc; o1 = 2 * d_ad + d_bc; o2 = s_ad - s_bc; o3 = d_ad - 2 * d_bc;
-}
-
-__device__ __forceinline__ void xd_inv4( int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3 )
-{
-    const int e = a + c, f = a - c, gg = b + ( d >> 1 ), hh = ( b >> 1 ) - d;
-    o0 = e + gg; o1 = f + hh; o2 = f - hh; o3 = e - gg;
-}
-
-// residual 4x4 DCT: f, p = four packed rows each (dct.c:115-150)
-__device__ __forceinline__ void xd_sub4x4_dct( int dct[16], const uint32_t f[4], const uint32_t p[4] )
-{
-    int t[16];
-#pragma unroll
-    for( int r = 0; r < 4; r++ )
-    {
-        const int d0 = (int)( f[r] & 255 ) - (int)( p[r] & 255 );
-        const int d1 = (int)( ( f[r] >> 8 ) & 255 ) - (int)( ( p[r] >> 8 ) & 255 );
-        const int d2 = (int)( ( f[r] >> 16 ) & 255 ) - (int)( ( p[r] >> 16 ) & 255 );
-        const int d3 = (int)( f[r] >> 24 ) - (int)( p[r] >> 24 );
-        xd_fwd4( d0, d1, d2, d3, t[r], t[4 + r], t[8 + r], t[12 + r] );
-    }
-#pragma unroll
-    for( int i = 0; i < 4; i++ )
-        xd_fwd4( t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3], dct[4 * i], dct[4 * i + 1], dct[4 * i + 2], dct[4 * i + 3] );
-}
-
-// inverse transform + add to the prediction rows, clipped (dct.c:197-235); coefficients are
-// truncated to 16 bits between the stages exactly as the reference's dctcoef stores do
-__device__ __forceinline__ void xd_add4x4_idct( uint32_t p[4], const int dct[16] )
-{
-    int t[16], r[16];
-#pragma unroll
-    for( int i = 0; i < 4; i++ )
-    {
-        int o0, o1, o2, o3;
-        xd_inv4( dct[i], dct[4 + i], dct[8 + i], dct[12 + i], o0, o1, o2, o3 );
-        t[4 * i] = (int16_t)o0; t[4 * i + 1] = (int16_t)o1; t[4 * i + 2] = (int16_t)o2; t[4 * i + 3] = (int16_t)o3;
-    }
-#pragma unroll
-    for( int i = 0; i < 4; i++ )
-    {
-        int o0, o1, o2, o3;
-        xd_inv4( t[i], t[4 + i], t[8 + i], t[12 + i], o0, o1, o2, o3 );
-        r[i] = (int16_t)( ( o0 + 32 ) >> 6 ); r[4 + i] = (int16_t)( ( o1 + 32 ) >> 6 );
-        r[8 + i] = (int16_t)( ( o2 + 32 ) >> 6 ); r[12 + i] = (int16_t)( ( o3 + 32 ) >> 6 );
-    }
-#pragma unroll
-    for( int y = 0; y < 4; y++ )
-    {
-        uint32_t w = 0;
-#pragma unroll
-        for( int x = 0; x < 4; x++ )
-            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + r[4 * y + x] ) << ( 8 * x );
-        p[y] = w;
-    }
-}
-
-__device__ __forceinline__ void xd_add4x4_dc( uint32_t p[4], int dc )
-{
-    dc = (int16_t)( ( dc + 32 ) >> 6 );
-#pragma unroll
-    for( int y = 0; y < 4; y++ )
-    {
-        uint32_t w = 0;
-#pragma unroll
-        for( int x = 0; x < 4; x++ )
-            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + dc ) << ( 8 * x );
-        p[y] = w;
-    }
-}
-
-// quant.c:29-36
-__device__ __forceinline__ int xd_quant1( int c, int mf, int bias )
-{
-    return (int16_t)( c > 0 ? ( ( bias + c ) * mf ) >> 16 : -( ( ( bias - c ) * mf ) >> 16 ) );
-}
-
-// position class of coefficient i for the flat quant matrices: 0 (even,even) 1 (mixed) 2 (odd,odd)
-#define XD_POS_CLASS( i ) ( ( ( i ) & 1 ) + ( ( ( i ) >> 2 ) & 1 ) )
-
-struct xd_qparams
-{
-    int mf[3], bias[3], dmf[3];      // per position class
-    int qbits;                       // qp/6 - 4
-};
-
-__device__ __forceinline__ int xd_quant_4x4( int dct[16], const xd_qparams &Q )
-{
-    int nz = 0;
-#pragma unroll
-    for( int i = 0; i < 16; i++ )
-    {
-        dct[i] = xd_quant1( dct[i], Q.mf[XD_POS_CLASS( i )], Q.bias[XD_POS_CLASS( i )] );
-        nz |= dct[i];
-    }
-    return nz != 0;
-}
-
-// quant.c:64-81
-__device__ __forceinline__ void xd_dequant_4x4( int dct[16], const xd_qparams &Q )
-{
-    if( Q.qbits >= 0 )
-    {
-#pragma unroll
-        for( int i = 0; i < 16; i++ )
-            dct[i] = (int16_t)( ( dct[i] * Q.dmf[XD_POS_CLASS( i )] ) << Q.qbits );
-    }
-    else
-    {
-        const int f = 1 << ( -Q.qbits - 1 );
-#pragma unroll
-        for( int i = 0; i < 16; i++ )
-            dct[i] = (int16_t)( ( dct[i] * Q.dmf[XD_POS_CLASS( i )] + f ) >> ( -Q.qbits ) );
-    }
-}
-
-// zig-zag order (dct.c:329-347)
-__device__ __forceinline__ void xd_zigzag( int lv[16], const int q[16] )
-{
-    lv[0] = q[0];   lv[1] = q[4];   lv[2] = q[1];   lv[3] = q[2];
-    lv[4] = q[5];   lv[5] = q[8];   lv[6] = q[12];  lv[7] = q[9];
-    lv[8] = q[6];   lv[9] = q[3];   lv[10] = q[7];  lv[11] = q[10];
-    lv[12] = q[13]; lv[13] = q[14]; lv[14] = q[11]; lv[15] = q[15];
-}
-
-// x264_decimate_score_internal (quant.c:226-252) over lv[first..15]
-__device__ __forceinline__ int xd_decimate( const int lv[16], int first )
-{
-    int score = 0, run = 0;
-    bool seen = false, big = false;
-#pragma unroll
-    for( int i = 15; i >= 0; i-- )
-    {
-        if( i < first )
-            continue;
-        const int v = lv[i];
-        if( v != 0 )
-        {
-            big |= v > 1 || v < -1;
-            if( seen )
-                score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;
-            seen = true;
-            run = 0;
-        }
-        else if( seen )
-            run++;
-    }
-    if( seen )
-        score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;
-    return big ? 9 : score;
-}
-
-__device__ __forceinline__ void xd_store_levels( int16_t *dst, const int lv[16] )
-{
-    uint4 a, b;
-    a.x = ( lv[0] & 0xFFFF ) | ( lv[1] << 16 );   a.y = ( lv[2] & 0xFFFF ) | ( lv[3] << 16 );
-    a.z = ( lv[4] & 0xFFFF ) | ( lv[5] << 16 );   a.w = ( lv[6] & 0xFFFF ) | ( lv[7] << 16 );
-    b.x = ( lv[8] & 0xFFFF ) | ( lv[9] << 16 );   b.y = ( lv[10] & 0xFFFF ) | ( lv[11] << 16 );
-    b.z = ( lv[12] & 0xFFFF ) | ( lv[13] << 16 ); b.w = ( lv[14] & 0xFFFF ) | ( lv[15] << 16 );
-    ( (uint4 *)dst )[0] = a;
-    ( (uint4 *)dst )[1] = b;
-}
-
-// quant.c:133-192 on one lane
-__device__ __forceinline__ void xd_chroma_dc_recon( int out[4], const int dc[4], int dmf )
-{
-    const int a = dc[0] + dc[1], b = dc[2] + dc[3], c = dc[0] - dc[1], d = dc[2] - dc[3];
-    out[0] = (int16_t)( ( ( a + b ) * dmf >> 5 ) + 32 );
-    out[1] = (int16_t)( ( ( a - b ) * dmf >> 5 ) + 32 );
-    out[2] = (int16_t)( ( ( c + d ) * dmf >> 5 ) + 32 );
-    out[3] = (int16_t)( ( ( c - d ) * dmf >> 5 ) + 32 );
-}
-
-__device__ int xd_optimize_chroma_dc( int dc[4], int dmf )
-{
-    int want[4], got[4];
-    xd_chroma_dc_recon( want, dc, dmf );
-    if( !( ( want[0] | want[1] | want[2] | want[3] ) >> 6 ) )
-        return 0;
-    int nz = 0;
-    for( int k = 3; k >= 0; k-- )
-    {
-        int level = dc[k];
-        const int step = level < 0 ? -1 : 1;
-        while( level )
-        {
-            dc[k] = (int16_t)( level - step );
-            xd_chroma_dc_recon( got, dc, dmf );
-            const int diff = ( want[0] ^ got[0] ) | ( want[1] ^ got[1] ) | ( want[2] ^ got[2] ) | ( want[3] ^ got[3] );
-            if( diff >> 6 )
-            {
-                nz = 1;
-                dc[k] = (int16_t)level;
-                break;
-            }
-            level -= step;
-        }
-    }
-    return nz;
 }
 
 struct xd_res_tables
