@@ -87,6 +87,15 @@ QUANT4 = C.CFUNCTYPE(C.c_int, i16p, u16p, u16p)
 QUANT_DC = C.CFUNCTYPE(C.c_int, i16p, C.c_int, C.c_int)
 DEQUANT = C.CFUNCTYPE(None, i16p, C.POINTER(C.c_int), C.c_int)
 COEF_INT = C.CFUNCTYPE(C.c_int, i16p)
+DENOISE = C.CFUNCTYPE(None, i16p, C.POINTER(C.c_uint32), u16p, C.c_int)
+
+
+class RunLevel(C.Structure):
+    """x264_run_level_t (common/bitstream.h:33-38)"""
+    _fields_ = [("last", C.c_int), ("mask", C.c_int), ("level", C.c_int16 * 16)]
+
+
+LEVEL_RUN = C.CFUNCTYPE(C.c_int, i16p, C.POINTER(RunLevel))
 
 
 class QuantTable(C.Structure):
@@ -94,10 +103,10 @@ class QuantTable(C.Structure):
         ("quant_4x4", QUANT4), ("quant_4x4_dc", QUANT_DC), ("quant_2x2_dc", QUANT_DC),
         ("dequant_4x4", DEQUANT), ("dequant_4x4_dc", DEQUANT),
         ("optimize_chroma_2x2_dc", C.CFUNCTYPE(C.c_int, i16p, C.c_int)),
-        ("denoise_dct", VOIDP),
+        ("denoise_dct", DENOISE),
         ("decimate_score15", COEF_INT), ("decimate_score16", COEF_INT),
         ("coeff_last", COEF_INT * 14), ("coeff_last4", COEF_INT), ("coeff_last8", COEF_INT),
-        ("coeff_level_run", VOIDP * 13), ("coeff_level_run4", VOIDP), ("coeff_level_run8", VOIDP),
+        ("coeff_level_run", LEVEL_RUN * 13), ("coeff_level_run4", LEVEL_RUN), ("coeff_level_run8", LEVEL_RUN),
     ]
 
 
