@@ -462,3 +462,82 @@ double xref_time_lookahead( void *hv, void **frames, int n, int *cost_out )
         cost_out[i] = xref_slicetype_frame_cost( h, (x264_frame_t **)frames, i-1, i, i );
     return xref_now() - t0;
 }
+
+/* ------------------------------------------------------------------ drop-in table test
+ * Replace the six function-pointer tables of an open encoder by caller-supplied ones (the product's
+ * x264_*_init output) and redo the aliasing x264_encoder_open performs after the init calls
+ * (mbcmp_init / chroma_dsp_init, encoder/encoder.c:412-457, both static there). */
+void xref_install_tables( void *hv, const void *pixf, const void *dctf, const void *zigzagf,
+                          const void *mcf, const void *quantf, const void *loopf )
+{
+    x264_t *h = hv;
+    int satd = h->param.analyse.i_subpel_refine > 0;
+    memcpy( &h->pixf, pixf, sizeof(h->pixf) );
+    memcpy( &h->dctf, dctf, sizeof(h->dctf) );
+    memcpy( &h->zigzagf, zigzagf, sizeof(h->zigzagf) );
+    memcpy( &h->mc, mcf, sizeof(h->mc) );
+    memcpy( &h->quantf, quantf, sizeof(h->quantf) );
+    memcpy( &h->loopf, loopf, sizeof(h->loopf) );
+
+    memcpy( h->pixf.mbcmp, satd ? h->pixf.satd : h->pixf.sad_aligned, sizeof(h->pixf.mbcmp) );
+    memcpy( h->pixf.mbcmp_unaligned, satd ? h->pixf.satd : h->pixf.sad, sizeof(h->pixf.mbcmp_unaligned) );
+    h->pixf.intra_mbcmp_x3_16x16 = satd ? h->pixf.intra_satd_x3_16x16 : h->pixf.intra_sad_x3_16x16;
+    h->pixf.intra_mbcmp_x3_8x8c  = satd ? h->pixf.intra_satd_x3_8x8c  : h->pixf.intra_sad_x3_8x8c;
+    h->pixf.intra_mbcmp_x3_4x4   = satd ? h->pixf.intra_satd_x3_4x4   : h->pixf.intra_sad_x3_4x4;
+    h->pixf.intra_mbcmp_x4_4x4_h = satd ? h->pixf.intra_satd_x4_4x4_h : h->pixf.intra_sad_x4_4x4_h;
+    h->pixf.intra_mbcmp_x4_4x4_v = satd ? h->pixf.intra_satd_x4_4x4_v : h->pixf.intra_sad_x4_4x4_v;
+    h->pixf.intra_mbcmp_x9_4x4   = NULL;
+    satd &= h->param.analyse.i_me_method == X264_ME_TESA;
+    memcpy( h->pixf.fpelcmp, satd ? h->pixf.satd : h->pixf.sad, sizeof(h->pixf.fpelcmp) );
+    memcpy( h->pixf.fpelcmp_x3, satd ? h->pixf.satd_x3 : h->pixf.sad_x3, sizeof(h->pixf.fpelcmp_x3) );
+    memcpy( h->pixf.fpelcmp_x4, satd ? h->pixf.satd_x4 : h->pixf.sad_x4, sizeof(h->pixf.fpelcmp_x4) );
+
+    h->mc.prefetch_fenc = h->mc.prefetch_fenc_420;
+    h->pixf.intra_mbcmp_x3_chroma = h->pixf.intra_mbcmp_x3_8x8c;
+    h->quantf.coeff_last[DCT_CHROMA_DC] = h->quantf.coeff_last4;
+    h->quantf.coeff_level_run[DCT_CHROMA_DC] = h->quantf.coeff_level_run4;
+}
+
+/* encode n_frames tightly packed I420 pictures with x264_encoder_encode, flush, and concatenate every
+ * NAL payload into out; returns the byte count, or <0 on error / overflow */
+int xref_encode_clip( void *hv, uint8_t *i420, int n_frames, uint8_t *out, int out_cap )
+{
+    x264_t *h = hv;
+    const int w = h->param.i_width, ht = h->param.i_height;
+    const size_t pic_bytes = (size_t)w * ht * 3 / 2;
+    int total = 0, i, k;
+    for( i = 0; ; i++ )
+    {
+        x264_picture_t pic, pic_out;
+        x264_nal_t *nal;
+        int n_nal = 0, size;
+        if( i < n_frames )
+        {
+            uint8_t *y = i420 + (size_t)i * pic_bytes;
+            x264_picture_init( &pic );
+            pic.img.i_csp = X264_CSP_I420;
+            pic.img.i_plane = 3;
+            pic.img.plane[0] = y;
+            pic.img.plane[1] = y + (size_t)w * ht;
+            pic.img.plane[2] = y + (size_t)w * ht + (size_t)( w / 2 ) * ( ht / 2 );
+            pic.img.i_stride[0] = w;
+            pic.img.i_stride[1] = pic.img.i_stride[2] = w / 2;
+            pic.i_pts = i;
+            size = x264_encoder_encode( h, &nal, &n_nal, &pic, &pic_out );
+        }
+        else
+            size = x264_encoder_encode( h, &nal, &n_nal, NULL, &pic_out );
+        if( size < 0 )
+            return -1;
+        for( k = 0; k < n_nal; k++ )
+        {
+            if( total + nal[k].i_payload > out_cap )
+                return -2;
+            memcpy( out + total, nal[k].p_payload, nal[k].i_payload );
+            total += nal[k].i_payload;
+        }
+        if( i >= n_frames && ( size == 0 || i > 2 * n_frames + 8 ) )
+            break;
+    }
+    return total;
+}

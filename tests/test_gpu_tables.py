@@ -355,3 +355,35 @@ def test_deblock_tables(tabs):
         lr.deblock_strength(ptr(nnz), ptr(refi, i8p), ptr(mv, i16p), ptr(b1))
         lo.deblock_strength(ptr(nnz), ptr(refi, i8p), ptr(mv, i16p), ptr(b2))
         assert np.array_equal(b1, b2), "deblock_strength"
+
+
+@pytest.mark.parametrize("w,h,n,me,subme,qp", [(96, 64, 4, 1, 5, 26), (64, 48, 3, 0, 2, 20), (176, 144, 5, 1, 4, 32)])
+def test_reference_encoder_runs_on_our_tables(pkg, ctx, w, h, n, me, subme, qp):
+    """THE drop-in check: the unmodified reference encoder (x264_encoder_encode: lookahead, analysis,
+    ME, residual, deblock, CABAC) with its six tables replaced by ours must emit the same bitstream,
+    byte for byte, as with its own tables."""
+    lib = cc.ref()
+    assert lib is not None
+    clip = np.concatenate(cc.synth_clip(w, h, n, seed=77, cut_frame=2))
+    outs = []
+    for use_ours in (False, True):
+        enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=qp, psub16x16=1)
+        if use_ours:
+            t = [rt.PixelTable(), rt.DctTable(), rt.ZigzagTable(), rt.McTable(), rt.QuantTable(), rt.DeblockTable()]
+            plib = pkg.lib()
+            plib.x264_pixel_init(0, C.byref(t[0]))
+            plib.x264_dct_init(0, C.byref(t[1]))
+            plib.x264_zigzag_init(0, C.byref(t[2]))
+            plib.x264_mc_init(0, C.byref(t[3]))
+            plib.x264_quant_init(None, 0, C.byref(t[4]))
+            plib.x264_deblock_init(0, C.byref(t[5]))
+            lib.xref_install_tables(enc.h, *[C.byref(x) for x in t])
+        out = np.zeros(1 << 20, np.uint8)
+        launches0 = ctx.launches
+        size = lib.xref_encode_clip(enc.h, ptr(clip), n, ptr(out), out.size)
+        assert size > 0, size
+        outs.append(out[:size].copy())
+    assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), \
+        f"bitstreams differ: {outs[0].size} vs {outs[1].size} bytes"
+    shim_ctx_launches = pkg.lib().x264dsp_launch_count(C.c_void_p(pkg.lib().x264dsp_tables_context()))
+    assert shim_ctx_launches > 1000, "the encode must have gone through the CUDA shims"

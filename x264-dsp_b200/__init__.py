@@ -78,6 +78,7 @@ def lib():
         l.x264dsp_version.restype = C.c_char_p
         l.x264dsp_stream.restype = C.c_void_p
         l.x264dsp_launch_count.restype = C.c_int64
+        l.x264dsp_tables_context.restype = C.c_void_p
         l.x264dsp_stream.argtypes = [C.c_void_p]
         l.x264dsp_launch_count.argtypes = [C.c_void_p]
         _lib = l
