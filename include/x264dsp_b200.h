@@ -208,6 +208,14 @@ int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int height, int
 int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames,
                                  const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums );
 
+/* ------------------------------------------------------------------ multi-GPU sharding
+ * The path shards by frame range with no exchange step (each frame's lookahead / ME costs depend
+ * only on source frames).  Rank `rank` of `world` owns frames [first, first + count) of an
+ * n_frames sequence, contiguous and balanced to within one frame; to analyse its first frame as a
+ * P frame it must also LOAD frame first-1, which *need_prev reports (0 for the rank that owns
+ * frame 0, and for empty ranges).  Returns X264DSP_E_ARG for a bad rank / world. */
+int x264dsp_frame_range( int n_frames, int rank, int world, int *first, int *count, int *need_prev );
+
 /* ------------------------------------------------------------------ motion search
  * x264_me_search_ref (+ optional x264_me_refine_qpel) (encoder/me.c:129-435) on n independent
  * blocks of one source frame against one reference frame's N/H/V/HV planes. */

@@ -115,6 +115,43 @@ def synth_frame(width, height, n, cut_frame=-1, luma_only=False):
     return buf
 
 
+def frame_range(n_frames, rank, world):
+    """(first, count, need_prev): the frames rank `rank` of `world` owns (x264dsp_frame_range)"""
+    first, count, prev = C.c_int(), C.c_int(), C.c_int()
+    check(lib().x264dsp_frame_range(int(n_frames), int(rank), int(world), C.byref(first), C.byref(count),
+                                    C.byref(prev)), "x264dsp_frame_range")
+    return first.value, count.value, bool(prev.value)
+
+
+def lookahead_sharded(analyse, luma, rank, world, gather=None):
+    """Frame-range sharded lookahead pass of ONE sequence.
+
+    `luma` [n, h*w] is the whole sequence (every rank sees the same host input; only its own range
+    plus the one overlap frame is uploaded).  `analyse(frames)` is the single-GPU pass -- in the
+    product `lambda f: ctx.lookahead_clip_host(w, h, f)` -- returning (mvs, costs, sums) with the
+    first frame analysed intra-only and every other frame against its predecessor.
+    Returns this rank's (first, mvs, costs, sums) for exactly the frames it owns; frame 0 of the
+    sequence keeps its intra-only result.  If `gather` is given (a callable doing an all-gather of
+    a numpy array along axis 0, e.g. over torch.distributed) every rank gets the full-sequence
+    arrays instead -- the only collective of the path, and an optional one.
+    """
+    n = luma.shape[0]
+    first, count, need_prev = frame_range(n, rank, world)
+    lo = first - 1 if need_prev else first
+    if count == 0:
+        g = None
+        mvs = np.zeros((0,), np.int16)
+        costs = np.zeros((0,), np.int32)
+        sums = np.zeros((0, LA_SUMS), np.int32)
+    else:
+        mvs, costs, sums = analyse(luma[lo:first + count])
+        if need_prev:               # drop the overlap frame's own (intra-only) result
+            mvs, costs, sums = mvs[1:], costs[1:], sums[1:]
+    if gather is None:
+        return first, mvs, costs, sums
+    return 0, gather(mvs), gather(costs), gather(sums)
+
+
 def cost_mv_table(qp):
     t = np.zeros(8193, np.uint16)
     check(lib().x264dsp_cost_mv_table(qp, t.ctypes.data_as(C.POINTER(C.c_uint16))), "x264dsp_cost_mv_table")

@@ -65,6 +65,19 @@ extern "C" int x264dsp_geometry( int width, int height, x264dsp_geom_t *g )
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ sharding
+
+extern "C" int x264dsp_frame_range( int n_frames, int rank, int world, int *first, int *count, int *need_prev )
+{
+    if( n_frames < 0 || world < 1 || rank < 0 || rank >= world || !first || !count || !need_prev )
+        return X264DSP_E_ARG;
+    const int lo = (int)( (int64_t)n_frames * rank / world ), hi = (int)( (int64_t)n_frames * ( rank + 1 ) / world );
+    *first = lo;
+    *count = hi - lo;
+    *need_prev = hi > lo && lo > 0;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ tables
 
 static const uint16_t xd_lambda_tab[52] =
