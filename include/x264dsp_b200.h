@@ -204,6 +204,11 @@ int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *
  * separate streams so that copies and kernels overlap. */
 int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int height, int n_clips, int clip_len,
                                   const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums );
+/* debug aid: clock64() cycles the inter kernel's warps spent per phase, summed over all warps since the
+ * last reset: out[0..9] = waiting on the row below, block setup, zero-mv SATD probe, predictor
+ * candidates, diamond search, sub-pel refine + SATD, publish/accounting, blocks processed, first wait
+ * of each row, rows processed. */
+int x264dsp_debug_lookahead_timing( x264dsp_ctx_t *ctx, int enable, int reset, uint64_t out[10] );
 /* single clip: same as n_clips = 1 */
 int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames,
                                  const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums );

@@ -32,6 +32,7 @@ struct x264dsp_ctx
     int32_t *la_ticket;            // work-queue counter
     size_t la_sync_cap, la_icost_cap;
     uint32_t la_epoch;
+    unsigned long long *la_timing; // phase-cycle counters of the inter kernel (debug aid, normally NULL)
 
     // host-API staging (x264dsp_lookahead_clip_host)
     uint8_t *stage_host;  size_t stage_host_cap;     // pinned

@@ -8,9 +8,10 @@
 // takes its MV predictors from (x+1,y), (x,y+1), (x-1,y+1), (x+1,y+1).  Rows therefore pipeline
 // with a lag of two blocks.  Mapping:
 //   * one WARP owns one block row of one frame pair and walks it right to left;
-//   * rows are handed out through an atomic ticket in dependency order (pair-major, bottom row
-//     first), so the row a warp waits on is always held by a warp that is already running --
-//     no co-residency assumption, no deadlock;
+//   * rows are handed out through an atomic ticket in dependency order (bottom rows of all pairs
+//     first, then the next row of all pairs, ...), so the row a warp waits on is always held by a
+//     warp that is already running -- no co-residency assumption, no deadlock -- and the wavefronts
+//     of all pairs of a launch advance together;
 //   * a finished block publishes {mv, epoch} as ONE 64-bit word; the row above spins on that word
 //     (volatile load, issued a block ahead of its use).  The payload is the flag, so no fence sits
 //     on the critical path;
@@ -20,6 +21,7 @@
 //     first-wins tie breaking;
 //   * the intra estimate has no dependencies and runs first as a plain thread-per-block kernel.
 // Many frame pairs per launch fill the machine; a single pair is latency bound by construction.
+#include <stdlib.h>
 #include "common.cuh"
 
 #define LA_COST_MAX ( 1 << 28 )
@@ -40,7 +42,13 @@ struct xd_la_args
     int32_t *ticket;
     uint32_t epoch;
     int me_range;
+    unsigned long long *timing;         // optional phase-cycle counters (x264dsp_debug_lookahead_timing)
 };
+
+// phase-cycle accounting of the inter kernel, off unless A.timing is set: lane 0 of every warp adds the
+// clock64() deltas of its phases at the end of its row
+enum { LA_T_WAIT = 0, LA_T_SETUP, LA_T_ZERO, LA_T_CAND, LA_T_DIA, LA_T_SUBPEL, LA_T_TAIL, LA_T_BLOCKS, LA_T_FIRST_WAIT, LA_T_ROWS, LA_T_KINDS };
+#define LA_TICK( kind ) do { if( TIMED ) { const unsigned now_ = (unsigned)clock(); tacc[kind] += now_ - tlast; tlast = now_; } } while( 0 )
 
 // ---------------------------------------------------------------------------------------------
 // 4-point Hadamard butterfly; output 0 is the plain sum
@@ -311,14 +319,19 @@ __device__ __forceinline__ void xd_st_sync( unsigned long long *p, unsigned long
 }
 
 // wait until the word carries this launch's epoch; returns the packed mv
-__device__ __forceinline__ uint32_t xd_la_await( const unsigned long long *p, unsigned long long seen, uint32_t epoch )
+// `ns0` / `ns_max`: first and longest pause between polls.  Inside a row the expected wait is a
+// fraction of a block time, so polls are dense; the FIRST wait of a row (its lower neighbour has to
+// get two blocks ahead, which for the upper rows of a frame means waiting for most of the pipeline
+// fill) backs off much further so that parked warps leave the issue slots to the working ones.
+__device__ __forceinline__ uint32_t xd_la_await( const unsigned long long *p, unsigned long long seen, uint32_t epoch,
+                                                 unsigned ns0 = 20, unsigned ns_max = 200 )
 {
-    unsigned ns = 20;
+    unsigned ns = ns0;
     while( (uint32_t)( seen >> 32 ) != epoch )
     {
         __nanosleep( ns );
-        if( ns < 200 )
-            ns += 20;
+        if( ns < ns_max )
+            ns += ns0;
         seen = xd_ld_sync( p );
     }
     return (uint32_t)seen;
@@ -327,7 +340,8 @@ __device__ __forceinline__ uint32_t xd_la_await( const unsigned long long *p, un
 #define MVX( m ) ( (int)(int16_t)( ( m ) & 0xFFFF ) )
 #define MVY( m ) ( (int)(int16_t)( ( m ) >> 16 ) )
 
-__global__ void __launch_bounds__( LA_WARPS * 32 )
+template<bool TIMED>
+__global__ void __launch_bounds__( LA_WARPS * 32, 8 )
 xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 {
     const x264dsp_geom_t &g = A.g;
@@ -345,8 +359,14 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         ticket = __shfl_sync( 0xffffffffu, ticket, 0 );
         if( ticket >= total )
             return;
-        const int pair = inter_pairs[ticket / rows];
-        const int by = H - 2 - ticket % rows;
+        // row-major over the pairs of the launch: all bottom rows first, then all second rows, ...
+        // Row (pair, r) waits on (pair, r-1), whose ticket is n_inter smaller and therefore already
+        // held by a running warp; and when the launch has more rows than the machine has warp slots,
+        // the rows handed out next are exactly the ones whose lower neighbours are furthest along,
+        // so warps spend their residency searching instead of waiting for a pipeline to fill.
+        const int row_idx = ticket / n_inter;
+        const int pair = inter_pairs[ticket - row_idx * n_inter];
+        const int by = H - 2 - row_idx;
         const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
         const uint8_t *ref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
         unsigned long long *sync_row = A.sync + (size_t)pair * g.mb_count + (size_t)by * W;
@@ -365,15 +385,35 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         B.sad_evals = 0;
         B.satd_evals = 0;
 
+        unsigned tacc[LA_T_KINDS] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, tlast = TIMED ? (unsigned)clock() : 0u;
         uint32_t mv_right = 0;                           // (x+1, y): border block
         uint32_t mv_b = 0, mv_br = 0, mv_bl = 0;         // (x, y+1), (x+1, y+1), (x-1, y+1)
         unsigned long long pending = 0;
         if( has_below )
         {
-            mv_b = xd_la_await( sync_below + ( W - 2 ), xd_ld_sync( sync_below + ( W - 2 ) ), A.epoch );
+            mv_b = xd_la_await( sync_below + ( W - 2 ), xd_ld_sync( sync_below + ( W - 2 ) ), A.epoch, 250, 4000 );
             pending = xd_ld_sync( sync_below + ( W - 3 ) );
         }
         int row_sum = 0, row_intra = 0;
+        LA_TICK( LA_T_FIRST_WAIT );
+
+        // The source block, its SATD quadrant rows and the block's intra cost do not depend on any
+        // search result: they are fetched one block ahead so that their L2 / HBM latency overlaps
+        // the previous block's search instead of opening every block with a stall.
+        const int fq_off = ( ( ( lane & 3 ) >> 1 ) * 4 ) * ls + ( lane & 1 ) * 4;
+        const int32_t *icost_row = A.icost + (size_t)pair * g.mb_count + (size_t)by * W;
+        uint2 nx_fenc;
+        uint32_t nx_fq[4];
+        int nx_ic = 0;
+        {
+            const size_t pel0 = ( (size_t)by * ls + ( W - 2 ) ) * 8;
+            nx_fenc = __ldg( (const uint2 *)( cur + pel0 + (size_t)( lane & 7 ) * ls ) );
+#pragma unroll
+            for( int r = 0; r < 4; r++ )
+                nx_fq[r] = __ldg( (const uint32_t *)( cur + pel0 + fq_off + (size_t)r * ls ) );
+            if( want_intra )
+                nx_ic = icost_row[W - 2];
+        }
 
         for( int bx = W - 2; bx >= 1; bx-- )
         {
@@ -385,16 +425,23 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             // start fetching the word the NEXT block will need
             if( has_below && bx >= 3 )
                 pending = xd_ld_sync( sync_below + ( bx - 2 ) );
+            LA_TICK( LA_T_WAIT );
 
             const size_t pel = ( (size_t)by * ls + bx ) * 8;
             B.ref = ref + pel;
-            B.fenc = __ldg( (const uint2 *)( cur + pel + (size_t)( lane & 7 ) * ls ) );
+            B.fenc = nx_fenc;
+#pragma unroll
+            for( int r = 0; r < 4; r++ )
+                B.fq[r] = nx_fq[r];
+            const int ic = nx_ic;
+            if( bx > 1 )
             {
-                // rows of this lane's 4x4 quadrant of the source block (for SATD)
-                const int q = lane & 3;
+                nx_fenc = __ldg( (const uint2 *)( cur + pel - 8 + (size_t)( lane & 7 ) * ls ) );
 #pragma unroll
                 for( int r = 0; r < 4; r++ )
-                    B.fq[r] = __ldg( (const uint32_t *)( cur + pel + (size_t)( ( q >> 1 ) * 4 + r ) * ls + ( q & 1 ) * 4 ) );
+                    nx_fq[r] = __ldg( (const uint32_t *)( cur + pel - 8 + fq_off + (size_t)r * ls ) );
+                if( want_intra )
+                    nx_ic = icost_row[bx - 1];
             }
             const int minx = -( bx << 3 ) - 4, maxx = ( ( W - bx - 1 ) << 3 ) + 4;
             const int sminx = ( minx - 8 ) << 2, smaxx = ( maxx + 8 ) << 2;
@@ -404,6 +451,7 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             B.mvpy = xd_median3( MVY( mv_right ), MVY( mv_b ), MVY( mv_bl ) );
 
             int mvx = 0, mvy = 0, cost = -1;
+            LA_TICK( LA_T_SETUP );
             if( !( B.mvpx | B.mvpy ) )                     // slicetype.c:117-125
             {
                 const int c0 = xd_la_satd( B, 0, 0, lane );
@@ -411,6 +459,7 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 if( c0 < 64 )
                     cost = c0;
             }
+            LA_TICK( LA_T_ZERO );
             if( cost < 0 )
             {
                 // ---- x264_me_search_ref, subme < 3 branch (me.c:194-233)
@@ -465,6 +514,7 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     B.sad_evals += n_evals;          // MVP + competing candidates + (0,0), as the reference issues
                 }
 
+                LA_TICK( LA_T_CAND );
                 // ---- diamond search (me.c:237-274): up, down, left, right
                 {
                     const int dx = cand == 2 ? -1 : cand == 3 ? 1 : 0;
@@ -484,6 +534,7 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     } while( --left && xd_la_in_range( bmx, bmy, minx, miny, maxx, maxy ) );
                 }
 
+                LA_TICK( LA_T_DIA );
                 // ---- me.c:397-414
                 int qx = bmx << 2, qy = bmy << 2;
                 if( bmx == pmx && bmy == pmy )
@@ -515,6 +566,7 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     bcost = xd_la_satd( B, qx, qy, lane ) + xd_la_bits( B, qx, qy );
                     B.satd_evals++;
                 }
+                LA_TICK( LA_T_SUBPEL );
                 mvx = qx; mvy = qy;
                 cost = bcost - 1;                                    // slicetype.c:128-130
                 if( mvx | mvy )
@@ -533,7 +585,6 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             int bcost_blk = cost + 4;
             if( want_intra )
             {
-                const int ic = A.icost[(size_t)pair * g.mb_count + xy];
                 if( ic < bcost_blk )
                 {
                     bcost_blk = ic;
@@ -545,6 +596,7 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             mv_right = mv_packed;
             mv_br = mv_b;
             mv_b = mv_bl;
+            LA_TICK( LA_T_TAIL );
         }
 
         if( lane == 0 )
@@ -556,6 +608,13 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             atomicAdd( &s[X264DSP_LA_SATD_EVALS], B.satd_evals );
             if( A.row_satds )
                 A.row_satds[(size_t)pair * 2 * H + by] = row_sum;
+            if( TIMED )
+            {
+                tacc[LA_T_BLOCKS] = W - 2;
+                tacc[LA_T_ROWS] = 1;
+                for( int k = 0; k < LA_T_KINDS; k++ )
+                    atomicAdd( A.timing + k, (unsigned long long)tacc[k] );
+            }
         }
     }
 }
@@ -621,6 +680,7 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
     A.ticket = ctx->la_ticket + ticket_slot;
     A.epoch = ctx->la_epoch;
     A.me_range = 16;                                 // x264_param_default: analyse.i_me_range
+    A.timing = ctx->la_timing;
 
     const int inner = ( g->mb_w - 2 ) * ( g->mb_h - 2 );
     dim3 igrid( ( inner + 127 ) / 128, count );
@@ -633,11 +693,30 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
     {
         const int total_rows = n_inter * ( g->mb_h - 2 );
         int ctas = ( total_rows + LA_WARPS - 1 ) / LA_WARPS;
-        const int cap = ctx->sm_count * ( 2048 / ( LA_WARPS * 32 ) );
+        // persistent launch: never more CTAs than fit on the machine at once (rows beyond that are
+        // picked up through the ticket as warps finish; the ticket order keeps that deadlock-free)
+        static int per_sm[2] = { 0, 0 };
+        const int timed = ctx->la_timing != NULL;
+        if( !per_sm[timed] )
+        {
+            if( timed )
+                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[1], xd_la_inter_kernel<true>, LA_WARPS * 32, 0 ) );
+            else
+                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[0], xd_la_inter_kernel<false>, LA_WARPS * 32, 0 ) );
+            if( per_sm[timed] < 1 )
+                per_sm[timed] = 1;
+            const char *e = getenv( "X264DSP_LA_CTAS_PER_SM" );      // tuning knob (tools/la_phase_timing.py)
+            if( e && atoi( e ) > 0 && atoi( e ) < per_sm[timed] )
+                per_sm[timed] = atoi( e );
+        }
+        const int cap = ctx->sm_count * per_sm[timed];
         if( ctas > cap )
             ctas = cap;
         pslot = xd_prof_begin( ctx, XD_PROF_LA_INTER, s );
-        xd_la_inter_kernel<<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
+        if( timed )
+            xd_la_inter_kernel<true><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
+        else
+            xd_la_inter_kernel<false><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
         xd_prof_end( ctx, XD_PROF_LA_INTER, pslot, s );
         ctx->launches++;
         XD_CHECK( cudaGetLastError() );
@@ -853,4 +932,29 @@ extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int h
                                              const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums )
 {
     return x264dsp_lookahead_clips_host( ctx, width, height, 1, n_frames, luma, mvs, costs, sums );
+}
+
+// Debug aid: cycle counters of the inter kernel's phases, summed over all warps since the last call
+// with reset != 0.  out[0..9] = wait, setup, zero-mv SATD, candidates, diamond, sub-pel, tail, blocks,
+// first wait of a row, rows.
+extern "C" int x264dsp_debug_lookahead_timing( x264dsp_ctx_t *ctx, int enable, int reset, uint64_t out[10] )
+{
+    if( !ctx )
+        return X264DSP_E_ARG;
+    XD_CHECK( cudaDeviceSynchronize() );
+    if( enable && !ctx->la_timing )
+    {
+        XD_CHECK( cudaMalloc( (void **)&ctx->la_timing, LA_T_KINDS * sizeof( unsigned long long ) ) );
+        XD_CHECK( cudaMemset( ctx->la_timing, 0, LA_T_KINDS * sizeof( unsigned long long ) ) );
+    }
+    if( out && ctx->la_timing )
+        XD_CHECK( cudaMemcpy( out, ctx->la_timing, LA_T_KINDS * sizeof( unsigned long long ), cudaMemcpyDeviceToHost ) );
+    if( reset && ctx->la_timing )
+        XD_CHECK( cudaMemset( ctx->la_timing, 0, LA_T_KINDS * sizeof( unsigned long long ) ) );
+    if( !enable && ctx->la_timing )
+    {
+        XD_CHECK( cudaFree( ctx->la_timing ) );
+        ctx->la_timing = NULL;
+    }
+    return 0;
 }
