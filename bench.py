@@ -4,8 +4,9 @@
 Workload (BASELINE.json configs[1]): 1080p synthetic clips of 8 frames; for every clip the lowres
 planes of all 8 frames are built (x264_frame_init_lowres) and x264_slicetype_frame_cost is run
 intra-only on frame 0 and as a P analysis (DIA + SAD full-pel, half-pel refine, SATD re-cost, 3-mode
-intra SATD) on frames 1..7.  One step = `--clips` independent clips per GPU (default 16, so that
-the step's input, 265 MB of luma, is larger than the 126 MB L2).  Frames/s counts all frames.
+intra SATD) on frames 1..7.  One step = `--clips` independent clips per GPU (default 64: the step's
+input, 1.06 GB of luma, is far larger than the 126 MB L2, and the wavefronts of 448 frame pairs keep
+every warp slot of the 148 SMs busy).  Frames/s counts all frames.
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
   python bench.py --impl reference ...                      the reference's own C path on host cores
@@ -34,12 +35,12 @@ LOOKAHEAD_BYTES_PER_PAIR = None   # filled from the geometry: 5 lowres planes in
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--clips", type=int, default=16, help="independent 8-frame clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=64, help="independent 8-frame clips per GPU per step")
     ap.add_argument("--clip-len", type=int, default=8)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -87,9 +88,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """summary of the samples received between wall-clock times t0 and t1 (all if None)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -99,7 +101,9 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for line in self.lines:
+        for stamp, line in self.lines:
+            if t0 is not None and not (t0 <= stamp <= t1 + 0.15):
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -197,8 +201,8 @@ def host_cores():
 def run_reference_arm(args, pkg):
     w, h = args.width, args.height
     threads = args.cpu_threads or host_cores()
-    # one clip per thread and step: a bounded sample of the GPU arm's step (args.clips clips per GPU)
-    n_clips = threads
+    # four clips per thread and step: a bounded sample of the GPU arm's step (args.clips clips per GPU)
+    n_clips = threads * 4
     base = make_clips(pkg, w, h, min(n_clips, 8), args.clip_len)
     luma_clips = [base.reshape(-1, args.clip_len, w * h)[c % min(n_clips, 8)] for c in range(n_clips)]
     for _ in range(max(args.warmup, 1)):
@@ -218,7 +222,7 @@ def run_reference_arm(args, pkg):
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, frames_per_step, sample=f"{n_clips} clips of {args.clip_len} frames per step, "
-                                  f"one clip per host thread"),
+                                  f"four clips per host thread"),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
                          "sample": f"{n_clips} clips x {args.clip_len} frames per step x {args.steps} steps"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -248,6 +252,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     pkg = load_package()
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and args.impl != "reference":
+        sampler.start()                    # nvidia-smi takes a while to produce its first line: start it early
 
     if args.impl == "reference":
         if rank == 0:
@@ -298,13 +305,11 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_dev()
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ctx.profile_enable(True)
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_region0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         step_dev()
@@ -329,7 +334,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(sums_host, sums_np), "host and device arms disagree"
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
 
     # ---- single clip latency (exactly the 8-frame configuration), device resident
     one = clip_len
@@ -401,9 +406,9 @@ def main():
             sample_clips = threads
             luma_clips = [luma_host.reshape(clips, clip_len, w * h)[c % clips] for c in range(sample_clips)]
             cpu_lookahead(w, h, clip_len, luma_clips, threads, 1)          # warm-up (page-in, allocations)
-            dt, kind, frames = cpu_lookahead(w, h, clip_len, luma_clips, threads, 2)
+            dt, kind, frames = cpu_lookahead(w, h, clip_len, luma_clips, threads, 24)
             line["cpu_baseline"] = {"value": frames / dt, "unit": "frames/s", "cores": threads, "kind": kind,
-                                    "sample": f"{sample_clips} clips x {clip_len} frames, 2 passes, one clip per thread "
+                                    "sample": f"{sample_clips} clips x {clip_len} frames, 24 passes, one clip per thread "
                                               f"({frames} frames in {dt:.2f} s)"}
         else:
             line["cpu_baseline"] = None

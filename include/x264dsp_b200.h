@@ -286,6 +286,14 @@ int x264dsp_deblock_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint
                                const uint8_t *bs, int qp, int alpha_c0_offset, int beta_offset,
                                void *stream );
 
+/* the same for n_frames independent frames in one launch (consecutive slots; mb_type / partition /
+ * cbp / bs hold n_frames x mb_count entries).  One frame alone is bound by the wavefront's critical
+ * path (mb_w + 2*mb_h macroblock times); batching frames is what fills the machine. */
+int x264dsp_deblock_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots, int n_frames,
+                                const int8_t *mb_type, const uint8_t *partition, const int16_t *cbp,
+                                const uint8_t *bs, int qp, int alpha_c0_offset, int beta_offset,
+                                void *stream );
+
 /* deblock_strength_c (common/deblock.c:297-323) for n macroblocks:
  * nnz [n][120], ref [n][2][40], mv [n][2][40][2] -> bs [n][2][8][4] (scan8 layout). */
 int x264dsp_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const uint8_t *nnz, const int8_t *ref,

@@ -103,6 +103,35 @@ def test_deblock_frame(pkg, ctx, w, h, qp, aoff, boff):
         assert np.count_nonzero(want != host[0]) > 0, "the test must exercise the filter"
 
 
+@pytest.mark.parametrize("w,h,nf,qp", [(352, 288, 5, 28), (1920, 1080, 3, 32), (64, 64, 7, 40)])
+def test_deblock_frames_batch(pkg, ctx, w, h, nf, qp):
+    """several independent frames in one launch (rows of all frames share the ticket queue)"""
+    import torch
+    g, go, host, dev = _slots(pkg, ctx, w, h, nf, False)
+    o = cc.oracle()
+    rng = np.random.RandomState(qp + nf)
+    n = g.mb_count
+    mb_type = rng.choice([0, 2, 4, 5, 6], (nf, n), p=[0.05, 0.05, 0.5, 0.2, 0.2]).astype(np.int8)
+    partition = rng.choice([13, 14, 15, 16], (nf, n)).astype(np.uint8)
+    cbp = (rng.randint(0, 48, (nf, n)) * (rng.rand(nf, n) < 0.6)).astype(np.int16)
+    bs = rng.randint(0, 4, (nf, n, 2, 8, 4)).astype(np.uint8)
+    bs[rng.rand(nf, n) < 0.2] = 0
+    want = []
+    for f in range(nf):
+        s = host[f].copy()
+        o.xo_deblock_frame(C.byref(go), ptr(s), ptr(mb_type[f], i8p), ptr(partition[f]), ptr(cbp[f], i16p), ptr(bs[f]), qp, 0, 0)
+        want.append(s)
+    want = np.concatenate(want)
+    slots = dev.clone()
+    d = [torch.from_numpy(a).cuda() for a in (mb_type, partition, cbp, bs)]
+    torch.cuda.synchronize()
+    ctx.deblock_frames(g, slots, nf, d[0], d[1], d[2], d[3], qp)
+    ctx.sync()
+    got = slots.cpu().numpy()
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, f"{len(bad)} bytes differ, first at {bad[:4]} (slot {bad[0] // g.slot_bytes})"
+
+
 def test_deblock_strength(pkg, ctx):
     import torch
     rng = np.random.RandomState(3)

@@ -324,6 +324,12 @@ class Context:
                                               _dp(cbp), _dp(bs), int(qp), int(alpha_off), int(beta_off), None),
               "x264dsp_deblock_frame_dev")
 
+    def deblock_frames(self, g, slots, n_frames, mb_type, partition, cbp, bs, qp, alpha_off=0, beta_off=0):
+        """n_frames consecutive slots in one launch; the per-MB arrays hold n_frames x mb_count entries"""
+        check(lib().x264dsp_deblock_frames_dev(self._h, C.byref(g), _dp(slots), int(n_frames), _dp(mb_type),
+                                               _dp(partition), _dp(cbp), _dp(bs), int(qp), int(alpha_off),
+                                               int(beta_off), None), "x264dsp_deblock_frames_dev")
+
     def deblock_strength(self, n, nnz, ref, mv, bs):
         check(lib().x264dsp_deblock_strength_dev(self._h, int(n), _dp(nnz), _dp(ref), _dp(mv), _dp(bs), None),
               "x264dsp_deblock_strength_dev")

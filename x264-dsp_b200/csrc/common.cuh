@@ -10,6 +10,7 @@
 enum { XD_PROF_LOAD = 0, XD_PROF_LOWRES, XD_PROF_LA_INTRA, XD_PROF_LA_INTER, XD_PROF_HPEL, XD_PROF_BORDER,
        XD_PROF_COST, XD_PROF_ME, XD_PROF_MC, XD_PROF_RESIDUAL, XD_PROF_DEBLOCK, XD_PROF_KINDS };
 #define XD_PROF_MAX 512
+#define XD_AUX_STREAMS 16
 
 // ---------------------------------------------------------------------------------------------
 // context: one per process/GPU.  Owns the stream, the constant tables in HBM and the scratch
@@ -47,7 +48,7 @@ struct x264dsp_ctx
     int32_t *db_progress; size_t db_progress_cap;
 
     // extra streams so that independent groups of a host-level batch overlap copies and kernels
-    cudaStream_t aux[4];
+    cudaStream_t aux[XD_AUX_STREAMS];
 
     // optional per-kernel timing with CUDA events (x264dsp_profile_*)
     int prof_on;

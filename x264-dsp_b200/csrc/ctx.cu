@@ -208,7 +208,7 @@ extern "C" int x264dsp_create( int device, x264dsp_ctx_t **out )
     XD_CHECK( cudaGetDeviceProperties( &prop, device ) );
     ctx->sm_count = prop.multiProcessorCount;
     XD_CHECK( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
-    for( int i = 0; i < 4; i++ )
+    for( int i = 0; i < XD_AUX_STREAMS; i++ )
         XD_CHECK( cudaStreamCreateWithFlags( &ctx->aux[i], cudaStreamNonBlocking ) );
 
     // one cost table per distinct lambda, shared between the QPs that map to it
@@ -274,7 +274,7 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
                 cudaEventDestroy( ctx->prof_ev[k][i][0] );
                 cudaEventDestroy( ctx->prof_ev[k][i][1] );
             }
-    for( int i = 0; i < 4; i++ )
+    for( int i = 0; i < XD_AUX_STREAMS; i++ )
         cudaStreamDestroy( ctx->aux[i] );
     cudaStreamDestroy( ctx->stream );
     free( ctx );

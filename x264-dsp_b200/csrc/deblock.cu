@@ -5,16 +5,19 @@
 //
 // The reference filters macroblocks in raster order; MB (x,y) reads pixels its left, top and
 // top-right neighbours have already modified, a 2-step wavefront.  Mapping:
-//   * one WARP per macroblock row, walking left to right; rows are taken through an atomic ticket
-//     in top-down order, and row y proceeds to MB x once row y-1 has finished MB x+1 (a progress
-//     counter per row, release/acquire through L2);
-//   * inside a macroblock the 32 lanes are the 16 luma lines plus the 8 x {U,V} chroma lines of a
-//     vertical-edge pass (then the 16 luma columns plus the 16 chroma bytes of a horizontal-edge
-//     pass): a lane keeps its line in registers across the four edges, exactly the sequential
-//     dependence the reference has, while the lines run in parallel;
-//   * pixels cross between lanes and between warps only through memory, with L2-coherent
-//     accesses (ld.cg / st.cg), a __syncwarp between the two passes and a fence before the row
-//     counter is advanced.
+//   * one WARP per macroblock row, walking left to right; rows of ALL frames of a launch are taken
+//     through an atomic ticket (frame-interleaved, top rows first), and row y proceeds to MB x once
+//     row y-1 has finished MB x+1 (a progress counter per row, release/acquire through L2);
+//   * the warp keeps the macroblock with its 4-sample left and top aprons (20x20 luma, 10 rows x 20
+//     bytes NV12) in a shared-memory tile: the vertical-edge pass has the 32 lanes on the 16 luma
+//     lines plus the 8 x {U,V} chroma lines, the horizontal-edge pass on the 16 luma columns plus the
+//     16 chroma byte columns; a lane keeps its line in registers across the four edges, exactly the
+//     sequential dependence the reference has, while the lines run in parallel;
+//   * columns 12..15 stay in the tile and become the next macroblock's left apron, so within a row
+//     pixels never round-trip through memory; only the rows shared with the macroblock row above /
+//     below cross warps, through L2 (ld.cg / st.cg) with a fence before the row counter advances;
+//   * the macroblock's own samples and its side information (bS, types, cbp) are fetched one
+//     macroblock ahead.
 #include "common.cuh"
 #include "leaf.cuh"
 
@@ -33,28 +36,119 @@ __device__ __forceinline__ xd_edge xd_edge_inter( uint32_t bs, int alpha, int be
     return e;
 }
 
-__device__ __forceinline__ int xd_ld_u8( const uint8_t *p ) { return __ldcg( p ); }
-__device__ __forceinline__ void xd_st_u8( uint8_t *p, int v ) { __stcg( p, (uint8_t)v ); }
+#define DB_WARPS 4
+#define DB_PITCH 24                     // tile row pitch: columns -4 .. 19 of the macroblock
+#define DB_LROWS 20                     // luma rows -4 .. 15
+#define DB_CROWS 10                     // chroma rows -2 .. 7
 
-__global__ void __launch_bounds__( 128 )
-xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *__restrict__ mb_type,
-                   const uint8_t *__restrict__ partition, const int16_t *__restrict__ cbp,
-                   const uint8_t *__restrict__ bs_all, xd_db_params P, int32_t *progress, int32_t *ticket )
+struct xd_db_args
 {
+    x264dsp_geom_t g;
+    uint8_t *slots;
+    int n_frames;
+    const int8_t *mb_type;
+    const uint8_t *partition;
+    const int16_t *cbp;
+    const uint8_t *bs;
+    xd_db_params P;
+    int32_t *progress;                  // [n_frames][mb_h] macroblocks finished per row
+    int32_t *ticket;
+};
+
+// one 32-bit item of the next macroblock's side information per lane, fetched a macroblock ahead:
+// lanes 0..15 the sixteen bS words ([dir][edge] of 4 bS), 16 mb_type, 17 mb_type of the MB above,
+// 18 partition, 19 cbp, 20 mb_type of the MB to the left
+__device__ __forceinline__ uint32_t xd_db_meta( const xd_db_args &A, size_t mb0, int xy, int mb_x, int mb_y, int lane )
+{
+    const int W = A.g.mb_w;
+    if( lane < 16 )
+        return __ldg( (const uint32_t *)( A.bs + ( mb0 + xy ) * 64 ) + lane );
+    if( lane == 16 ) return (uint32_t)(int)__ldg( A.mb_type + mb0 + xy );
+    if( lane == 17 ) return mb_y > 0 ? (uint32_t)(int)__ldg( A.mb_type + mb0 + xy - W ) : 127u;
+    if( lane == 18 ) return __ldg( A.partition + mb0 + xy );
+    if( lane == 19 ) return (uint32_t)(int)__ldg( A.cbp + mb0 + xy );
+    if( lane == 20 ) return mb_x > 0 ? (uint32_t)(int)__ldg( A.mb_type + mb0 + xy - 1 ) : 127u;
+    return 0;
+}
+
+// The macroblock's own samples (nobody has modified them yet): lanes 0..15 one luma row each,
+// lanes 16..23 one NV12 chroma row each, as 16 bytes.
+__device__ __forceinline__ uint4 xd_db_own( const uint8_t *py, const uint8_t *pc, int ls, int cs, int lane )
+{
+    if( lane < 16 )
+        return __ldcg( (const uint4 *)( py + (int64_t)lane * ls ) );
+    if( lane < 24 )
+        return __ldcg( (const uint4 *)( pc + (int64_t)( lane - 16 ) * cs ) );
+    return make_uint4( 0, 0, 0, 0 );
+}
+
+__device__ __forceinline__ void xd_db_put16( uint8_t *row, uint4 v )        // row + 4 is 4-byte aligned
+{
+    uint32_t *w = (uint32_t *)( row + 4 );
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+
+__global__ void __launch_bounds__( DB_WARPS * 32 )
+xd_deblock_kernel( xd_db_args A )
+{
+    __shared__ __align__( 16 ) uint8_t s_luma[DB_WARPS][DB_LROWS * DB_PITCH];
+    __shared__ __align__( 16 ) uint8_t s_chroma[DB_WARPS][DB_CROWS * DB_PITCH];
     const int lane = threadIdx.x & 31;
+    uint8_t *L = s_luma[threadIdx.x >> 5], *Cc = s_chroma[threadIdx.x >> 5];
+    const x264dsp_geom_t &g = A.g;
+    const xd_db_params &P = A.P;
     const int W = g.mb_w, H = g.mb_h, ls = g.luma_stride, cs = g.chroma_stride;
+    const int total = A.n_frames * H;
     for( ;; )
     {
-        int mb_y = 0;
+        int t = 0;
         if( lane == 0 )
-            mb_y = atomicAdd( ticket, 1 );
-        mb_y = __shfl_sync( 0xffffffffu, mb_y, 0 );
-        if( mb_y >= H )
+            t = atomicAdd( A.ticket, 1 );
+        t = __shfl_sync( 0xffffffffu, t, 0 );
+        if( t >= total )
             return;
-        volatile int32_t *above = progress + mb_y - 1;
+        // rows are dealt frame-interleaved, top rows first: row (f, y) waits on (f, y-1), whose
+        // ticket is n_frames smaller and therefore held by a warp that is already running
+        const int mb_y = t / A.n_frames, f = t - mb_y * A.n_frames;
+        uint8_t *slot = A.slots + (size_t)f * g.slot_bytes;
+        const size_t mb0 = (size_t)f * g.mb_count;
+        volatile int32_t *mine = A.progress + (size_t)f * H + mb_y;
+        volatile int32_t *above = mine - 1;
+        uint8_t *row_y = slot + g.luma_origin + (int64_t)( mb_y << 4 ) * ls;
+        uint8_t *row_c = slot + g.slot_chroma_off + g.chroma_origin + (int64_t)( mb_y << 3 ) * cs;
+
+        uint4 own = xd_db_own( row_y, row_c, ls, cs, lane );
+        uint32_t meta = xd_db_meta( A, mb0, mb_y * W, 0, mb_y, lane );
         int seen = 0;
         for( int mb_x = 0; mb_x < W; mb_x++ )
         {
+            uint8_t *py = row_y + ( mb_x << 4 ), *pc = row_c + ( mb_x << 4 );
+            // ---- this macroblock's side information (fetched during the previous macroblock)
+            uint32_t bs[16];
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                bs[k] = __shfl_sync( 0xffffffffu, meta, k );
+                bs[8 + k] = __shfl_sync( 0xffffffffu, meta, 8 + k );
+            }
+            const int type_cur = (int)__shfl_sync( 0xffffffffu, meta, 16 ), type_top = (int)__shfl_sync( 0xffffffffu, meta, 17 );
+            const int part = (int)__shfl_sync( 0xffffffffu, meta, 18 ), cbp_cur = (int)(int16_t)__shfl_sync( 0xffffffffu, meta, 19 );
+            const int type_left = (int)__shfl_sync( 0xffffffffu, meta, 20 );
+            const bool intra_cur = type_cur < 4;
+            const bool first_only = part == 16 && cbp_cur == 0 && !intra_cur;
+
+            // ---- commit the macroblock's own samples to the tile, start fetching the next one's
+            if( lane < 16 )
+                xd_db_put16( L + ( lane + 4 ) * DB_PITCH, own );
+            else if( lane < 24 )
+                xd_db_put16( Cc + ( lane - 16 + 2 ) * DB_PITCH, own );
+            if( mb_x + 1 < W )
+            {
+                own = xd_db_own( py + 16, pc + 16, ls, cs, lane );
+                meta = xd_db_meta( A, mb0, mb_y * W + mb_x + 1, mb_x + 1, mb_y, lane );
+            }
+
+            // ---- the row above must have finished macroblock x+1; then its bottom rows are final
             if( mb_y > 0 )
             {
                 const int need = min( mb_x + 2, W );
@@ -70,18 +164,17 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                     }
                 }
                 __threadfence();
+                if( lane >= 24 && lane < 28 )
+                    xd_db_put16( L + ( lane - 24 ) * DB_PITCH, __ldcg( (const uint4 *)( py + (int64_t)( lane - 28 ) * ls ) ) );
+                else if( lane >= 28 && lane < 30 )
+                    xd_db_put16( Cc + ( lane - 28 ) * DB_PITCH, __ldcg( (const uint4 *)( pc + (int64_t)( lane - 30 ) * cs ) ) );
             }
-            const int xy = mb_y * W + mb_x;
-            const bool intra_cur = mb_type[xy] < 4;
-            const bool first_only = partition[xy] == 16 && cbp[xy] == 0 && !intra_cur;
-            const uint32_t *bs = (const uint32_t *)( bs_all + (size_t)xy * 64 );     // [2][8] words of 4 bS
-            uint8_t *py = slot + g.luma_origin + (int64_t)( mb_y << 4 ) * ls + ( mb_x << 4 );
-            uint8_t *pc = slot + g.slot_chroma_off + g.chroma_origin + (int64_t)( mb_y << 3 ) * cs + ( mb_x << 4 );
+            __syncwarp();
 
             // ======================= vertical edges (filter across x) =======================
             {
                 xd_edge le[4], ce[2];
-                const bool left_intra = mb_x > 0 && ( intra_cur || mb_type[xy - 1] < 4 );
+                const bool left_intra = mb_x > 0 && ( intra_cur || type_left < 4 );
                 le[0].mode = mb_x == 0 ? 0 : left_intra ? 2 : xd_edge_inter( bs[0], P.alpha, P.beta ).mode;
                 le[0].bs = bs[0];
                 ce[0].mode = mb_x == 0 ? 0 : left_intra ? 2 : xd_edge_inter( bs[0], P.alphac, P.betac ).mode;
@@ -100,11 +193,11 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                 if( lane < 16 )
                 {
                     // luma line `lane`: pixels x-4 .. x+15 in registers
-                    uint8_t *row = py + (int64_t)lane * ls;
+                    uint32_t *row = (uint32_t *)( L + ( lane + 4 ) * DB_PITCH );
                     uint32_t w[5];
 #pragma unroll
                     for( int k = 0; k < 5; k++ )
-                        w[k] = __ldcg( (const uint32_t *)( row - 4 + 4 * k ) );
+                        w[k] = row[k];
                     const int grp = lane >> 2;
 #pragma unroll
                     for( int e = 0; e < 4; e++ )
@@ -131,14 +224,13 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                     }
 #pragma unroll
                     for( int k = 0; k < 5; k++ )
-                        if( k > 0 || mb_x > 0 )
-                            __stcg( (uint32_t *)( row - 4 + 4 * k ), w[k] );
+                        row[k] = w[k];
                 }
                 else
                 {
                     // chroma row r, component c: edges at pair 0 (byte 0) and pair 4 (byte 8)
                     const int r = ( lane - 16 ) >> 1, c = ( lane - 16 ) & 1;
-                    uint8_t *row = pc + (int64_t)r * cs + c;
+                    uint8_t *row = Cc + ( r + 2 ) * DB_PITCH + 4 + c;
                     const int grp = r >> 1;
 #pragma unroll
                     for( int e = 0; e < 2; e++ )
@@ -146,8 +238,7 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                         if( ce[e].mode == 0 )
                             continue;
                         uint8_t *q = row + 8 * e;
-                        int s[4] = { xd_ld_u8( q - 4 ), xd_ld_u8( q - 2 ), xd_ld_u8( q ), xd_ld_u8( q + 2 ) };
-                        const int p0 = s[1], q0 = s[2];
+                        int s[4] = { q[-4], q[-2], q[0], q[2] };
                         if( ce[e].mode == 2 )
                             xd_chroma_line( s, P.alphac, P.betac, 0, true );
                         else
@@ -156,18 +247,17 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                             if( tc > 0 )
                                 xd_chroma_line( s, P.alphac, P.betac, tc, false );
                         }
-                        if( s[1] != p0 ) xd_st_u8( q - 2, s[1] );
-                        if( s[2] != q0 ) xd_st_u8( q, s[2] );
+                        q[-2] = (uint8_t)s[1];
+                        q[0] = (uint8_t)s[2];
                     }
                 }
             }
             __syncwarp();
-            __threadfence_block();
 
             // ======================= horizontal edges (filter across y) =======================
             {
                 xd_edge le[4], ce[2];
-                const bool top_intra = mb_y > 0 && ( intra_cur || mb_type[xy - W] < 4 );
+                const bool top_intra = mb_y > 0 && ( intra_cur || type_top < 4 );
                 le[0].mode = mb_y == 0 ? 0 : top_intra ? 2 : xd_edge_inter( bs[8], P.alpha, P.beta ).mode;
                 le[0].bs = bs[8];
                 ce[0].mode = mb_y == 0 ? 0 : top_intra ? 2 : xd_edge_inter( bs[8], P.alphac, P.betac ).mode;
@@ -186,18 +276,14 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                 if( lane < 16 )
                 {
                     // luma column `lane`: rows -4 .. 15
-                    uint8_t *col = py + lane;
-                    int v[20];
+                    uint8_t *col = L + 4 + lane;
                     const bool any = ( le[0].mode | le[1].mode | le[2].mode | le[3].mode ) != 0;
                     if( any )
                     {
+                        int v[20];
 #pragma unroll
                         for( int k = 0; k < 20; k++ )
-                            v[k] = ( k >= 4 || mb_y > 0 ) ? xd_ld_u8( col + (int64_t)( k - 4 ) * ls ) : 0;
-                        int orig[20];
-#pragma unroll
-                        for( int k = 0; k < 20; k++ )
-                            orig[k] = v[k];
+                            v[k] = col[k * DB_PITCH];
                         const int grp = lane >> 2;
 #pragma unroll
                         for( int e = 0; e < 4; e++ )
@@ -221,25 +307,23 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                                 v[4 * e + k] = s[k];
                         }
 #pragma unroll
-                        for( int k = 0; k < 20; k++ )
-                            if( v[k] != orig[k] )
-                                xd_st_u8( col + (int64_t)( k - 4 ) * ls, v[k] );
+                        for( int k = 1; k < 19; k++ )
+                            col[k * DB_PITCH] = (uint8_t)v[k];
                     }
                 }
                 else
                 {
                     // chroma byte b of the 16-byte row (pair b>>1, component b&1): edges at chroma rows 0 and 4
                     const int b = lane - 16;
-                    uint8_t *col = pc + b;
+                    uint8_t *col = Cc + 4 + b;
                     const int grp = b >> 2;
 #pragma unroll
                     for( int e = 0; e < 2; e++ )
                     {
                         if( ce[e].mode == 0 )
                             continue;
-                        uint8_t *q = col + (int64_t)( 4 * e ) * cs;
-                        int s[4] = { xd_ld_u8( q - 2 * (int64_t)cs ), xd_ld_u8( q - cs ), xd_ld_u8( q ), xd_ld_u8( q + cs ) };
-                        const int p0 = s[1], q0 = s[2];
+                        uint8_t *q = col + ( 2 + 4 * e ) * DB_PITCH;
+                        int s[4] = { q[-2 * DB_PITCH], q[-DB_PITCH], q[0], q[DB_PITCH] };
                         if( ce[e].mode == 2 )
                             xd_chroma_line( s, P.alphac, P.betac, 0, true );
                         else
@@ -248,15 +332,50 @@ xd_deblock_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slot, const int8_t *_
                             if( tc > 0 )
                                 xd_chroma_line( s, P.alphac, P.betac, tc, false );
                         }
-                        if( s[1] != p0 ) xd_st_u8( q - cs, s[1] );
-                        if( s[2] != q0 ) xd_st_u8( q, s[2] );
+                        q[-DB_PITCH] = (uint8_t)s[1];
+                        q[0] = (uint8_t)s[2];
                     }
                 }
+            }
+            __syncwarp();
+
+            // ---- write back what is final now: columns -4 .. 11 of the macroblock's rows (columns
+            // 12..15 still face the next macroblock's left edge and travel on in the tile), plus the
+            // rows of the macroblock above that the top edge touched
+            {
+                const bool last = mb_x == W - 1;
+                if( lane < 24 )
+                {
+                    const uint32_t *src = (const uint32_t *)( lane < 16 ? L + ( lane + 4 ) * DB_PITCH : Cc + ( lane - 16 + 2 ) * DB_PITCH );
+                    uint32_t *dst = (uint32_t *)( lane < 16 ? py + (int64_t)lane * ls - 4 : pc + (int64_t)( lane - 16 ) * cs - 4 );
+                    if( mb_x > 0 )
+                        __stcg( dst, src[0] );
+                    __stcg( dst + 1, src[1] );
+                    __stcg( dst + 2, src[2] );
+                    __stcg( dst + 3, src[3] );
+                    if( last )
+                        __stcg( dst + 4, src[4] );
+                }
+                if( mb_y > 0 && lane < 16 )
+                {
+                    if( lane < 12 )
+                    {
+                        const int r = lane >> 2, w = lane & 3;          // luma rows -3 .. -1
+                        __stcg( (uint32_t *)( py + (int64_t)( r - 3 ) * ls ) + w, ( (const uint32_t *)( L + ( r + 1 ) * DB_PITCH + 4 ) )[w] );
+                    }
+                    else
+                        __stcg( (uint32_t *)( pc - cs ) + ( lane - 12 ), ( (const uint32_t *)( Cc + DB_PITCH + 4 ) )[lane - 12] );
+                }
+                // carry columns 12..15 into the next macroblock's columns -4..-1
+                if( lane < 16 )
+                    *(uint32_t *)( L + ( lane + 4 ) * DB_PITCH ) = *(const uint32_t *)( L + ( lane + 4 ) * DB_PITCH + 16 );
+                else if( lane < 24 )
+                    *(uint32_t *)( Cc + ( lane - 16 + 2 ) * DB_PITCH ) = *(const uint32_t *)( Cc + ( lane - 16 + 2 ) * DB_PITCH + 16 );
             }
             __threadfence();            // every lane publishes its own stores device-wide ...
             __syncwarp();               // ... before lane 0 advances the row counter
             if( lane == 0 )
-                *( (volatile int32_t *)( progress + mb_y ) ) = mb_x + 1;
+                *mine = mb_x + 1;
         }
     }
 }
@@ -286,12 +405,12 @@ xd_deblock_strength_kernel( int n, const uint8_t *__restrict__ nnz, const int8_t
     bs[(size_t)m * 64 + dir * 32 + edge * 4 + i] = (uint8_t)s;
 }
 
-extern "C" int x264dsp_deblock_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slot,
-                                           const int8_t *mb_type, const uint8_t *partition, const int16_t *cbp,
-                                           const uint8_t *bs, int qp, int alpha_c0_offset, int beta_offset,
-                                           void *stream )
+extern "C" int x264dsp_deblock_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots, int n_frames,
+                                            const int8_t *mb_type, const uint8_t *partition, const int16_t *cbp,
+                                            const uint8_t *bs, int qp, int alpha_c0_offset, int beta_offset,
+                                            void *stream )
 {
-    if( !ctx || !g || !slot || !mb_type || !partition || !cbp || !bs || qp < 0 || qp > 51 )
+    if( !ctx || !g || !slots || n_frames <= 0 || !mb_type || !partition || !cbp || !bs || qp < 0 || qp > 51 )
         return X264DSP_E_ARG;
     static const uint8_t alpha_h[52] =
     {
@@ -307,31 +426,54 @@ extern "C" int x264dsp_deblock_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom
     auto clamp_idx = []( int i ) { return i > 51 ? 51 : i; };
     const int qpc = x264dsp_chroma_qp( qp );
     const int ia = qp + alpha_c0_offset, ib = qp + beta_offset, iac = qpc + alpha_c0_offset, ibc = qpc + beta_offset;
-    xd_db_params P;
-    P.alpha = ia < 0 ? 0 : alpha_h[clamp_idx( ia )];
-    P.beta = ib < 0 ? 0 : beta_h[clamp_idx( ib )];
-    P.alphac = iac < 0 ? 0 : alpha_h[clamp_idx( iac )];
-    P.betac = ibc < 0 ? 0 : beta_h[clamp_idx( ibc )];
-    P.ia = ia < 0 ? -1 : clamp_idx( ia );
-    P.iac = iac < 0 ? -1 : clamp_idx( iac );
+    xd_db_args A;
+    A.g = *g;
+    A.slots = slots;
+    A.n_frames = n_frames;
+    A.mb_type = mb_type; A.partition = partition; A.cbp = cbp; A.bs = bs;
+    A.P.alpha = ia < 0 ? 0 : alpha_h[clamp_idx( ia )];
+    A.P.beta = ib < 0 ? 0 : beta_h[clamp_idx( ib )];
+    A.P.alphac = iac < 0 ? 0 : alpha_h[clamp_idx( iac )];
+    A.P.betac = ibc < 0 ? 0 : beta_h[clamp_idx( ibc )];
+    A.P.ia = ia < 0 ? -1 : clamp_idx( ia );
+    A.P.iac = iac < 0 ? -1 : clamp_idx( iac );
 
     cudaStream_t s = xd_stream( ctx, stream );
-    // progress counters: one per MB row, plus the ticket, in the lookahead ticket array's tail
-    const size_t need = ( (size_t)g->mb_h + 1 ) * sizeof( int32_t );
+    // progress counters: one per MB row of every frame, plus the ticket
+    const size_t rows = (size_t)n_frames * g->mb_h;
+    const size_t need = ( rows + 1 ) * sizeof( int32_t );
     if( ctx->db_progress_cap < need )
         XD_CHECK( cudaDeviceSynchronize() );
     int rc = xd_reserve_dev( (void **)&ctx->db_progress, &ctx->db_progress_cap, need );
     if( rc )
         return rc;
     XD_CHECK( cudaMemsetAsync( ctx->db_progress, 0, need, s ) );
-    const int ctas = ( g->mb_h + 3 ) / 4;
+    A.progress = ctx->db_progress;
+    A.ticket = ctx->db_progress + rows;
+    static int per_sm = 0;
+    if( !per_sm )
+    {
+        XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, xd_deblock_kernel, DB_WARPS * 32, 0 ) );
+        if( per_sm < 1 )
+            per_sm = 1;
+    }
+    int64_t ctas = ( (int64_t)rows + DB_WARPS - 1 ) / DB_WARPS;
+    if( ctas > (int64_t)ctx->sm_count * per_sm )
+        ctas = (int64_t)ctx->sm_count * per_sm;          // persistent: the ticket hands out the remaining rows
     const int pslot = xd_prof_begin( ctx, XD_PROF_DEBLOCK, s );
-    xd_deblock_kernel<<<ctas, 128, 0, s>>>( *g, slot, mb_type, partition, cbp, bs, P, ctx->db_progress,
-                                            ctx->db_progress + g->mb_h );
+    xd_deblock_kernel<<<(int)ctas, DB_WARPS * 32, 0, s>>>( A );
     xd_prof_end( ctx, XD_PROF_DEBLOCK, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
+}
+
+extern "C" int x264dsp_deblock_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slot,
+                                           const int8_t *mb_type, const uint8_t *partition, const int16_t *cbp,
+                                           const uint8_t *bs, int qp, int alpha_c0_offset, int beta_offset,
+                                           void *stream )
+{
+    return x264dsp_deblock_frames_dev( ctx, g, slot, 1, mb_type, partition, cbp, bs, qp, alpha_c0_offset, beta_offset, stream );
 }
 
 extern "C" int x264dsp_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const uint8_t *nnz, const int8_t *ref,

@@ -818,7 +818,7 @@ static bool xd_is_pinned( const void *p )
 }
 
 // Lookahead pass of n_clips independent clips of clip_len frames each, from HOST memory.
-// The batch is cut into up to four groups of whole clips; each group runs on its own stream
+// The batch is cut into up to XD_AUX_STREAMS groups of whole clips; each group runs on its own stream
 // (H2D copy -> staging kernel -> lowres planes -> intra + inter cost kernels -> D2H), so that one
 // group's copies overlap another group's kernels.  Pinned caller buffers (x264dsp_host_alloc) are
 // copied from / to directly; ordinary memory goes through the context's pinned staging area.
@@ -885,7 +885,12 @@ extern "C" int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int 
     int32_t *d_sums = (int32_t *)( ctx->clip_out + mv_bytes + cost_bytes );
     uint8_t *h_out = ctx->clip_out_host;
 
-    const int groups = n_clips < 4 ? n_clips : 4;
+    // enough groups that the last group's kernels (the only work not hidden behind a copy) are a small
+    // share of the batch, but at least four clips per group so that every launch still fills its pipeline
+    int groups = n_clips / 4;
+    if( groups < 1 ) groups = 1;
+    if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
+    if( n_clips <= 4 ) groups = n_clips < 2 ? 1 : 2;
     for( int gi = 0; gi < groups; gi++ )
     {
         cudaStream_t s = ctx->aux[gi];
