@@ -257,6 +257,17 @@ int x264dsp_me_search_batch_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
                                  const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
                                  void *stream );
 
+/* Same search for a list whose blocks all have partition size i_pixel (blocks[k].i_pixel is ignored):
+ * the kernel is specialised on the size and packs 4 .. 32 blocks into a warp (one lane per 8x4 / 4x4
+ * Hadamard tile), which is several times faster than the generic entry point on small partitions.
+ * The reference's analysis visits one partition type at a time (encoder/analyse.c:787-1232), so its
+ * call sites map onto uniform lists. */
+int x264dsp_me_search_sized_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                 const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                                 const x264dsp_me_params_t *params, int i_pixel, int n,
+                                 const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                 void *stream );
+
 /* ------------------------------------------------------------------ residual
  * The inter-macroblock branch of x264_macroblock_encode + x264_mb_encode_chroma
  * (encoder/macroblock.c:175-305, 379-471) for every macroblock of a frame, b_dct_decimate = 1,

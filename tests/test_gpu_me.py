@@ -43,7 +43,7 @@ def test_me_search_batch(pkg, ctx, me, subme, refine):
     o = cc.oracle()
     rng = np.random.RandomState(500 + me * 10 + subme)
     ref_slot, enc_slot = slots[: g.slot_bytes], slots[g.slot_bytes:]
-    for size in range(7):
+    for size in range(8):
         for qp, mv_scale in ((26, 24), (38, 90)):
             n = 400
             blocks = make_me_blocks(go, rng, size, n, mv_scale)
@@ -60,6 +60,15 @@ def test_me_search_batch(pkg, ctx, me, subme, refine):
             got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)
             bad = [i for i in range(n) if got[i] != want[i]]
             assert not bad, (f"me {me} subme {subme} refine {refine} size {size} qp {qp}: {len(bad)}/{n} differ; "
+                             f"first {bad[0]}: gpu {got[bad[0]]} oracle {want[bad[0]]} block {blocks[bad[0]]}")
+            # the size-specialised kernel (G lanes per block) must agree as well
+            d_res.zero_()
+            torch.cuda.synchronize()
+            ctx.me_search_sized(g, enc_slot, ref_slot, p, size, n, d_blocks, d_res)
+            ctx.sync()
+            got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)
+            bad = [i for i in range(n) if got[i] != want[i]]
+            assert not bad, (f"SIZED me {me} subme {subme} refine {refine} size {size} qp {qp}: {len(bad)}/{n} differ; "
                              f"first {bad[0]}: gpu {got[bad[0]]} oracle {want[bad[0]]} block {blocks[bad[0]]}")
 
 
@@ -102,3 +111,9 @@ def test_me_search_1080p_tiling(pkg, ctx):
         ctx.sync()
         got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)[keep]
         assert np.array_equal(got, want), f"size {size}: {np.count_nonzero(got != want)} of {len(sub)} differ"
+        d_res.zero_()
+        torch.cuda.synchronize()
+        ctx.me_search_sized(g, slots[g.slot_bytes:], slots[: g.slot_bytes], pkg.MeParams(1, 5, 16, 26, 1), size, n, d_blocks, d_res)
+        ctx.sync()
+        got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)[keep]
+        assert np.array_equal(got, want), f"sized, size {size}: {np.count_nonzero(got != want)} of {len(sub)} differ"

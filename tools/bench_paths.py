@@ -148,8 +148,15 @@ def main():
             for p in range(P):
                 ctx.me_search_batch(g, slots[(p + 1) * g.slot_bytes:(p + 2) * g.slot_bytes],
                                     slots[p * g.slot_bytes:(p + 1) * g.slot_bytes], prm, nb, d_blocks[p], d_res[p])
-        t = timed(run_me)
-        rec = {"blocks_per_frame": nb, "ms_per_frame": t / P, "frames_per_s": 1e3 * P / t}
+        t_generic = timed(run_me)
+
+        def run_me_sized():
+            for p in range(P):
+                ctx.me_search_sized(g, slots[(p + 1) * g.slot_bytes:(p + 2) * g.slot_bytes],
+                                    slots[p * g.slot_bytes:(p + 1) * g.slot_bytes], prm, size, nb, d_blocks[p], d_res[p])
+        t = timed(run_me_sized)
+        rec = {"blocks_per_frame": nb, "ms_per_frame": t / P, "frames_per_s": 1e3 * P / t,
+               "generic_warp_per_block_ms_per_frame": t_generic / P}
         if size == 0:
             mv16 = [r.cpu().numpy().view(cc.ME_RESULT_DTYPE)["mv"].copy() for r in d_res]
         if o is not None:

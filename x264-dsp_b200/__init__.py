@@ -309,6 +309,12 @@ class Context:
                                                 C.byref(params), int(n), _dp(blocks_dev), _dp(results_dev),
                                                 None), "x264dsp_me_search_batch_dev")
 
+    def me_search_sized(self, g, fenc_slot, fref_slot, params, i_pixel, n, blocks_dev, results_dev):
+        """uniform-size list: the size-specialised kernel (x264dsp_me_search_sized_dev)"""
+        check(lib().x264dsp_me_search_sized_dev(self._h, C.byref(g), _dp(fenc_slot), _dp(fref_slot),
+                                                C.byref(params), int(i_pixel), int(n), _dp(blocks_dev),
+                                                _dp(results_dev), None), "x264dsp_me_search_sized_dev")
+
     # ---- residual / MC / deblock ---------------------------------------------------------
     def mc_frame(self, g, fref_slot, mv_dev, pred_slot):
         check(lib().x264dsp_mc_frame_dev(self._h, C.byref(g), _dp(fref_slot), _dp(mv_dev), _dp(pred_slot), None),
