@@ -21,7 +21,8 @@ all: $(LIB)
 
 $(OUT)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OUT)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OUT)/$*.ptxas.log || (cat $(OUT)/$*.ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OUT)/$*.ptxas.raw || (cat $(OUT)/$*.ptxas.raw; false)
+	@grep -v "Compile time" $(OUT)/$*.ptxas.raw > $(OUT)/$*.ptxas.log; rm -f $(OUT)/$*.ptxas.raw
 
 $(OUT)/%.o: $(CSRC)/%.cpp $(HDRS)
 	@mkdir -p $(OUT)
