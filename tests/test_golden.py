@@ -492,8 +492,9 @@ def test_gpu_cost_batch(G, pkg, ctx):
     n = len(cases)
     off1 = torch.from_numpy((cases[:, 1] * s1).astype(np.int64)).cuda()
     off2 = torch.from_numpy((cases[:, 2] * s2 + cases[:, 3]).astype(np.int64)).cuda()
-    size = torch.from_numpy(cases[:, 0].astype(np.int32)).cuda()
-    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    size = torch.from_numpy(cases[:, 0].astype(np.uint8)).cuda()
+    pad = np.zeros(64, np.uint8)            # unaligned 8-pixel loads read whole words
+    da, db = torch.from_numpy(np.concatenate([a, pad])).cuda(), torch.from_numpy(np.concatenate([b, pad])).cuda()
     for cmp in range(3):
         out = torch.zeros(n, dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()

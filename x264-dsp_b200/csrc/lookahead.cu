@@ -620,6 +620,475 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 }
 
 // ---------------------------------------------------------------------------------------------
+// Quad-row inter kernel: the throughput mapping.
+//
+// One warp owns FOUR consecutive block rows of one frame pair; lane = 8*sub + r, where group `sub`
+// (8 lanes) walks row by0-sub and lane r holds pixel row r of that group's current 8x8 block.  The
+// four groups run in lock step with the reference's own lag of two blocks per row (group sub is at
+// column W-2-t+2*sub in step t), so inside a warp the row-to-row dependency is a register shuffle;
+// only the bottom group polls the quad below (one {mv, epoch} word per step) and only the top group
+// publishes.  Every lane evaluates ALL candidates of a search step for its pixel row (VABSDIFF4 x2
+// per candidate); the per-candidate sums are packed two to a register and reduced over the 8 lanes
+// of a group with three xor-shuffles, which serves four blocks per instruction instead of one.
+// SATD: each lane transforms its row horizontally (x264's packed two-4x4s-per-word form,
+// pixel.c:243-266), the vertical 4-point transform runs across lanes.
+#define LQ_FULL 0xffffffffu
+
+struct xd_lq_block
+{
+    const uint8_t *ref;       // reference lowres plane N at the block origin; planes H,V,HV follow
+    size_t plane_size;
+    int stride;
+    uint2 fenc;               // this lane's source row
+    uint32_t fw[4];           // the same row as fw[k] = p[k] | p[k+4] << 16
+    int mvpx, mvpy;
+    const uint16_t *cost_mv;
+};
+
+__device__ __forceinline__ uint32_t xd_lq_reduce8( uint32_t v )
+{
+    v += __shfl_xor_sync( LQ_FULL, v, 1 );
+    v += __shfl_xor_sync( LQ_FULL, v, 2 );
+    v += __shfl_xor_sync( LQ_FULL, v, 4 );
+    return v;
+}
+
+__device__ __forceinline__ int xd_lq_bits( const xd_lq_block &B, int qx, int qy )
+{
+    return __ldg( B.cost_mv + ( qx - B.mvpx ) ) + __ldg( B.cost_mv + ( qy - B.mvpy ) );
+}
+
+// 8 pixels of row r of the prediction at quarter-pel (qx,qy): get_ref / mc_luma (mc.c:192-264)
+__device__ __forceinline__ uint2 xd_lq_fetch( const xd_lq_block &B, int qx, int qy, int r )
+{
+    const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
+    const int64_t base = (int64_t)( ( qy >> 2 ) + r ) * B.stride + ( qx >> 2 );
+    uint2 a = xd_load8_unaligned( B.ref + (size_t)xd_qpel_plane_a( phase ) * B.plane_size + base + ( fy == 3 ? B.stride : 0 ) );
+    if( phase & 5 )
+    {
+        const uint2 b = xd_load8_unaligned( B.ref + (size_t)xd_qpel_plane_b( phase ) * B.plane_size + base + ( fx == 3 ? 1 : 0 ) );
+        a.x = xd_avg4( a.x, b.x );
+        a.y = xd_avg4( a.y, b.y );
+    }
+    return a;
+}
+
+// full-pel position: plane N only
+__device__ __forceinline__ uint32_t xd_lq_sad_fpel( const xd_lq_block &B, int mx, int my, int r )
+{
+    const uint2 p = xd_load8_unaligned( B.ref + (int64_t)( my + r ) * B.stride + mx );
+    return __vsadu4( p.x, B.fenc.x ) + __vsadu4( p.y, B.fenc.y );
+}
+
+__device__ __forceinline__ uint32_t xd_lq_sad_qpel( const xd_lq_block &B, int qx, int qy, int r )
+{
+    const uint2 p = xd_lq_fetch( B, qx, qy, r );
+    return __vsadu4( p.x, B.fenc.x ) + __vsadu4( p.y, B.fenc.y );
+}
+
+// p[k] | p[k+4] << 16 for k = 0..3
+__device__ __forceinline__ void xd_lq_unpack( uint2 p, uint32_t w[4] )
+{
+    w[0] = __byte_perm( p.x, p.y, 0x7470 ) & 0x00FF00FFu;
+    w[1] = __byte_perm( p.x, p.y, 0x7571 ) & 0x00FF00FFu;
+    w[2] = __byte_perm( p.x, p.y, 0x7672 ) & 0x00FF00FFu;
+    w[3] = __byte_perm( p.x, p.y, 0x7773 ) & 0x00FF00FFu;
+}
+
+// abs of both 16-bit halves of a word that holds hi * 65536 + lo with a signed lo (pixel.c:236-241)
+__device__ __forceinline__ uint32_t xd_lq_abs2( uint32_t a )
+{
+    const uint32_t s = ( ( a >> 15 ) & 0x10001u ) * 0xffffu;
+    return ( a + s ) ^ s;
+}
+
+// SATD 8x8 (pixel.c:294-335) of the group's block against the prediction at (qx,qy).  Executed by
+// the whole warp (shuffles); `on` only gates the loads.  Every lane of a group returns the cost.
+__device__ __forceinline__ int xd_lq_satd( const xd_lq_block &B, int qx, int qy, int r, bool on )
+{
+    uint2 p = make_uint2( 0u, 0u );
+    if( on )
+        p = xd_lq_fetch( B, qx, qy, r );
+    uint32_t w[4];
+    xd_lq_unpack( p, w );
+    // horizontal 4-point transform of the row, left and right 4x4 side by side in the two halves
+    const uint32_t a0 = B.fw[0] - w[0], a1 = B.fw[1] - w[1], a2 = B.fw[2] - w[2], a3 = B.fw[3] - w[3];
+    const uint32_t t0 = a0 + a1, t1 = a0 - a1, t2 = a2 + a3, t3 = a2 - a3;
+    uint32_t h[4] = { t0 + t2, t1 + t3, t0 - t2, t1 - t3 };
+    // vertical transform over the four rows of an 8x4 (lanes r^1, r^2)
+    const uint32_t n1 = ( r & 1 ) ? ~0u : 0u, c1 = r & 1, n2 = ( r & 2 ) ? ~0u : 0u, c2 = ( r >> 1 ) & 1;
+    uint32_t sum = 0;
+#pragma unroll
+    for( int k = 0; k < 4; k++ )
+    {
+        uint32_t v = h[k];
+        v = __shfl_xor_sync( LQ_FULL, v, 1 ) + ( v ^ n1 ) + c1;
+        v = __shfl_xor_sync( LQ_FULL, v, 2 ) + ( v ^ n2 ) + c2;
+        sum += xd_lq_abs2( v );
+    }
+    sum += __shfl_xor_sync( LQ_FULL, sum, 1 );
+    sum += __shfl_xor_sync( LQ_FULL, sum, 2 );
+    const uint32_t half = ( ( sum & 0xFFFFu ) + ( sum >> 16 ) ) >> 1;        // one 8x4
+    return (int)( half + __shfl_xor_sync( LQ_FULL, half, 4 ) );
+}
+
+__global__ void __launch_bounds__( LA_WARPS * 32 )
+xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
+{
+    const x264dsp_geom_t &g = A.g;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, r = lane & 7;
+    const int W = g.mb_w, H = g.mb_h, ls = g.lowres_stride;
+    const int rows = H - 2, quads = ( rows + 3 ) >> 2;
+    const int total = n_inter * quads;
+
+    for( ;; )
+    {
+        int ticket = 0;
+        if( lane == 0 )
+            ticket = atomicAdd( A.ticket, 1 );
+        ticket = __shfl_sync( LQ_FULL, ticket, 0 );
+        if( ticket >= total )
+            return;
+        // quad-major over the pairs of the launch (see xd_la_inter_kernel): the quad a warp waits on
+        // always holds a smaller ticket, i.e. is running or finished
+        const int quad = ticket / n_inter;
+        const int pair = inter_pairs[ticket - quad * n_inter];
+        const int by0 = H - 2 - 4 * quad;                 // bottom row of the quad
+        const int nrows = min( 4, by0 );                  // rows by0, by0-1, ... down to row 1
+        const int by = by0 - sub;
+        const bool row_ok = sub < nrows;
+        const bool has_below = quad > 0;
+        const bool is_top = sub == nrows - 1;
+        const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
+        const uint8_t *ref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
+        unsigned long long *sync_row = A.sync + (size_t)pair * g.mb_count + (size_t)by * W;
+        const unsigned long long *sync_below = A.sync + (size_t)pair * g.mb_count + (size_t)( by0 + 1 ) * W;
+        const bool want_intra = A.want_intra[pair] != 0;
+        const int32_t *icost_row = A.icost + (size_t)pair * g.mb_count + (size_t)by * W;
+
+        // MV limits (slicetype.c:79-89); the y limits are per row
+        const int miny = -( by << 3 ) - 4, maxy = ( ( H - by - 1 ) << 3 ) + 4;
+        const int sminy = ( miny - 8 ) << 2, smaxy = ( maxy + 8 ) << 2;
+
+        xd_lq_block B;
+        B.plane_size = (size_t)g.lowres_plane_size;
+        B.stride = ls;
+        B.cost_mv = A.cost_mv;
+        B.ref = ref;
+        B.mvpx = B.mvpy = 0;
+        B.fenc = make_uint2( 0u, 0u );
+        B.fw[0] = B.fw[1] = B.fw[2] = B.fw[3] = 0u;
+        int sad_evals = 0, satd_evals = 0, row_sum = 0, row_intra = 0;
+
+        uint32_t mv_right = 0, mv_b = 0, mv_br = 0, mv_bl = 0;
+        uint32_t last_mv = 0;                              // this group's previous result (0 when it had none)
+        unsigned long long pending = 0;
+        // step t = -1 only shifts the neighbour pipeline: it brings (W-2, below) in
+        if( has_below )
+            pending = xd_ld_sync( sync_below + ( W - 2 ) );
+
+        // the first block's source row, fetched ahead like every later one
+        uint2 nx_fenc = make_uint2( 0u, 0u );
+        int nx_ic = 0;
+        if( row_ok )
+        {
+            nx_fenc = __ldg( (const uint2 *)( cur + ( (size_t)by * ls + ( W - 2 ) ) * 8 + (size_t)r * ls ) );
+            if( want_intra )
+                nx_ic = icost_row[W - 2];
+        }
+
+        const int n_steps = ( W - 2 ) + 2 * ( nrows - 1 );
+        for( int t = -1; t < n_steps; t++ )
+        {
+            const int bx = W - 2 - t + 2 * sub;
+            const bool act = row_ok && bx >= 1 && bx <= W - 2;
+
+            // ---- neighbour of the row below at column bx-1: the group underneath produced it in the
+            //      previous step; the bottom group reads it from the quad below
+            uint32_t incoming = __shfl_up_sync( LQ_FULL, last_mv, 8 );
+            {
+                const int bx0 = W - 2 - t;                 // the bottom group's column
+                uint32_t polled = 0;
+                if( has_below && bx0 - 1 >= 1 && bx0 - 1 <= W - 2 )
+                {
+                    polled = xd_la_await( sync_below + ( bx0 - 1 ), pending, A.epoch, t < 0 ? 250 : 20, t < 0 ? 4000 : 200 );
+                    if( bx0 - 2 >= 1 )
+                        pending = xd_ld_sync( sync_below + ( bx0 - 2 ) );
+                }
+                if( sub == 0 )
+                    incoming = polled;
+            }
+            mv_bl = incoming;
+
+            int mvx = 0, mvy = 0, cost = 0;
+            int ic = 0;
+            bool search = false;
+            int minx = 0, maxx = 0;
+            if( act )
+            {
+                const size_t pel = ( (size_t)by * ls + bx ) * 8;
+                B.ref = ref + pel;
+                B.fenc = nx_fenc;
+                ic = nx_ic;
+                if( bx > 1 )
+                {
+                    nx_fenc = __ldg( (const uint2 *)( cur + pel - 8 + (size_t)r * ls ) );
+                    if( want_intra )
+                        nx_ic = icost_row[bx - 1];
+                }
+                xd_lq_unpack( B.fenc, B.fw );
+                minx = -( bx << 3 ) - 4;
+                maxx = ( ( W - bx - 1 ) << 3 ) + 4;
+                // predictors (slicetype.c:105-113): right, below, below-left (below-right is a candidate only)
+                B.mvpx = xd_median3( MVX( mv_right ), MVX( mv_b ), MVX( mv_bl ) );
+                B.mvpy = xd_median3( MVY( mv_right ), MVY( mv_b ), MVY( mv_bl ) );
+                search = true;
+            }
+
+            // ---- slicetype.c:117-125: zero predictor -> try the zero vector with SATD first
+            const bool needz = act && !( B.mvpx | B.mvpy );
+            if( __any_sync( LQ_FULL, needz ) )
+            {
+                const int c0 = xd_lq_satd( B, 0, 0, r, needz );
+                if( needz )
+                {
+                    satd_evals++;
+                    if( c0 < 64 )
+                    {
+                        cost = c0;
+                        search = false;
+                    }
+                }
+            }
+
+            int bmx = 0, bmy = 0, pmx = 0, pmy = 0, bcost = 0;
+            // ---- x264_me_search_ref, subme < 3 branch (me.c:194-233): rounded MVP (no mv cost),
+            //      the four neighbour MVs, then (0,0)
+            if( __any_sync( LQ_FULL, search ) )
+            {
+                int ccx[6], ccy[6];
+                bool cok[6];
+                uint32_t pmv = 0;
+                if( search )
+                {
+                    bmx = xd_clip3( B.mvpx, minx * 4, maxx * 4 );
+                    bmy = xd_clip3( B.mvpy, miny * 4, maxy * 4 );
+                    pmx = ( bmx + 2 ) >> 2;
+                    pmy = ( bmy + 2 ) >> 2;
+                    pmv = ( (uint32_t)pmx & 0xFFFF ) | ( (uint32_t)pmy << 16 );
+                }
+                ccx[0] = pmx; ccy[0] = pmy; cok[0] = search;
+#pragma unroll
+                for( int k = 1; k <= 4; k++ )
+                {
+                    const uint32_t m = k == 1 ? mv_right : k == 2 ? mv_b : k == 3 ? mv_bl : mv_br;
+                    ccx[k] = xd_clip3( ( MVX( m ) + 2 ) >> 2, minx, maxx );
+                    ccy[k] = xd_clip3( ( MVY( m ) + 2 ) >> 2, miny, maxy );
+                    const uint32_t v = ( (uint32_t)ccx[k] & 0xFFFF ) | ( (uint32_t)ccy[k] << 16 );
+                    cok[k] = search && v != 0 && v != pmv;
+                }
+                ccx[5] = 0; ccy[5] = 0; cok[5] = search && pmv != 0;
+
+                uint32_t w[3] = { 0u, 0u, 0u };
+#pragma unroll
+                for( int k = 0; k < 6; k++ )
+                {
+                    uint32_t s = 0;
+                    if( cok[k] )
+                        s = xd_lq_sad_fpel( B, ccx[k], ccy[k], r );
+                    w[k >> 1] += s << ( 16 * ( k & 1 ) );
+                }
+                // lane r adds candidate r's mv bits, or the "does not compete" marker
+                if( search && r < 6 )
+                {
+                    int kx = ccx[0], ky = ccy[0];
+                    bool ok = cok[0];
+#pragma unroll
+                    for( int k = 1; k < 6; k++ )
+                        if( r == k ) { kx = ccx[k]; ky = ccy[k]; ok = cok[k]; }
+                    const uint32_t add = !ok ? 0xFFFFu : r ? (uint32_t)xd_lq_bits( B, kx << 2, ky << 2 ) : 0u;
+                    const uint32_t sh = add << ( 16 * ( r & 1 ) );
+                    if( ( r >> 1 ) == 0 ) w[0] += sh;
+                    else if( ( r >> 1 ) == 1 ) w[1] += sh;
+                    else w[2] += sh;
+                }
+                w[0] = xd_lq_reduce8( w[0] );
+                w[1] = xd_lq_reduce8( w[1] );
+                w[2] = xd_lq_reduce8( w[2] );
+                if( search )
+                {
+                    int best = 0x7FFFFFFF;
+#pragma unroll
+                    for( int k = 0; k < 6; k++ )
+                    {
+                        const int c = (int)( ( w[k >> 1] >> ( 16 * ( k & 1 ) ) ) & 0xFFFFu );
+                        if( c < 0xFFFF )
+                        {
+                            best = min( best, ( c << 3 ) | k );
+                            sad_evals++;
+                        }
+                    }
+                    bcost = best >> 3;
+                    const int win = best & 7;
+#pragma unroll
+                    for( int k = 0; k < 6; k++ )
+                        if( win == k ) { bmx = ccx[k]; bmy = ccy[k]; }
+                }
+            }
+
+            // ---- diamond search (me.c:237-274): up, down, left, right
+            {
+                bool dia = search;
+                int left = A.me_range;
+                while( __any_sync( LQ_FULL, dia ) )
+                {
+                    uint32_t w0 = 0, w1 = 0;
+                    if( dia )
+                    {
+                        w0 = xd_lq_sad_fpel( B, bmx, bmy - 1, r ) | ( xd_lq_sad_fpel( B, bmx, bmy + 1, r ) << 16 );
+                        w1 = xd_lq_sad_fpel( B, bmx - 1, bmy, r ) | ( xd_lq_sad_fpel( B, bmx + 1, bmy, r ) << 16 );
+                        if( r < 4 )
+                        {
+                            const int dx = r == 2 ? -1 : r == 3 ? 1 : 0, dy = r == 0 ? -1 : r == 1 ? 1 : 0;
+                            const uint32_t sh = (uint32_t)xd_lq_bits( B, ( bmx + dx ) << 2, ( bmy + dy ) << 2 ) << ( 16 * ( r & 1 ) );
+                            if( r < 2 ) w0 += sh; else w1 += sh;
+                        }
+                    }
+                    w0 = xd_lq_reduce8( w0 );
+                    w1 = xd_lq_reduce8( w1 );
+                    if( dia )
+                    {
+                        sad_evals += 4;
+                        const int k0 = (int)( ( w0 & 0xFFFFu ) << 2 ), k1 = (int)( ( w0 >> 16 ) << 2 ) | 1;
+                        const int k2 = (int)( ( w1 & 0xFFFFu ) << 2 ) | 2, k3 = (int)( ( w1 >> 16 ) << 2 ) | 3;
+                        const int key = min( min( k0, k1 ), min( k2, k3 ) );
+                        if( ( key >> 2 ) >= bcost )
+                            dia = false;
+                        else
+                        {
+                            bcost = key >> 2;
+                            const int wn = key & 3;
+                            bmx += wn == 2 ? -1 : wn == 3 ? 1 : 0;
+                            bmy += wn == 0 ? -1 : wn == 1 ? 1 : 0;
+                            if( !--left || !xd_la_in_range( bmx, bmy, minx, miny, maxx, maxy ) )
+                                dia = false;
+                        }
+                    }
+                }
+            }
+
+            // ---- me.c:397-414, then refine_subpel( hpel_iters = 1, qpel_iters = 0 ) (me.c:466-587)
+            if( __any_sync( LQ_FULL, search ) )
+            {
+                int qx = bmx << 2, qy = bmy << 2, px = 0, py = 0;
+                bool single = false;
+                if( search )
+                {
+                    if( bmx == pmx && bmy == pmy )
+                        bcost += xd_lq_bits( B, qx, qy );
+                    const int sminx = ( minx - 8 ) << 2, smaxx = ( maxx + 8 ) << 2;
+                    px = xd_clip3( B.mvpx, sminx + 2, smaxx - 2 );
+                    py = xd_clip3( B.mvpy, sminy + 2, smaxy - 2 );
+                    single = px != qx || py != qy;                   // me.c:483-490
+                }
+                if( __any_sync( LQ_FULL, single ) )
+                {
+                    uint32_t s = 0;
+                    if( single )
+                    {
+                        s = xd_lq_sad_qpel( B, px, py, r );
+                        if( r == 0 )
+                            s += (uint32_t)xd_lq_bits( B, px, py );
+                    }
+                    s = xd_lq_reduce8( s );
+                    if( single )
+                    {
+                        sad_evals++;
+                        if( (int)s < bcost ) { bcost = (int)s; qx = px; qy = py; }
+                    }
+                }
+                // half-pel diamond (me.c:492-517)
+                uint32_t w0 = 0, w1 = 0;
+                if( search )
+                {
+                    w0 = xd_lq_sad_qpel( B, qx, qy - 2, r ) | ( xd_lq_sad_qpel( B, qx, qy + 2, r ) << 16 );
+                    w1 = xd_lq_sad_qpel( B, qx - 2, qy, r ) | ( xd_lq_sad_qpel( B, qx + 2, qy, r ) << 16 );
+                    if( r < 4 )
+                    {
+                        const int dx = r == 2 ? -2 : r == 3 ? 2 : 0, dy = r == 0 ? -2 : r == 1 ? 2 : 0;
+                        const uint32_t sh = (uint32_t)xd_lq_bits( B, qx + dx, qy + dy ) << ( 16 * ( r & 1 ) );
+                        if( r < 2 ) w0 += sh; else w1 += sh;
+                    }
+                }
+                w0 = xd_lq_reduce8( w0 );
+                w1 = xd_lq_reduce8( w1 );
+                if( search )
+                {
+                    sad_evals += 4;
+                    const int k0 = (int)( ( w0 & 0xFFFFu ) << 2 ), k1 = (int)( ( w0 >> 16 ) << 2 ) | 1;
+                    const int k2 = (int)( ( w1 & 0xFFFFu ) << 2 ) | 2, k3 = (int)( ( w1 >> 16 ) << 2 ) | 3;
+                    const int key = min( min( k0, k1 ), min( k2, k3 ) );
+                    if( ( key >> 2 ) < bcost )
+                    {
+                        const int wn = key & 3;
+                        qx += wn == 2 ? -2 : wn == 3 ? 2 : 0;
+                        qy += wn == 0 ? -2 : wn == 1 ? 2 : 0;
+                    }
+                }
+                // me.c:519-524: the winner is re-costed with SATD
+                const int c = xd_lq_satd( B, qx, qy, r, search );
+                if( search )
+                {
+                    satd_evals++;
+                    mvx = qx; mvy = qy;
+                    cost = c + xd_lq_bits( B, qx, qy ) - 1;           // slicetype.c:128-130
+                    if( mvx | mvy )
+                        cost += 5;
+                }
+            }
+
+            // ---- publish, then account (slicetype.c:132-196)
+            const uint32_t mv_packed = ( (uint32_t)mvx & 0xFFFF ) | ( (uint32_t)mvy << 16 );
+            if( act )
+            {
+                if( r == 0 )
+                {
+                    const int xy = by * W + bx;
+                    if( is_top )
+                        xd_st_sync( sync_row + bx, ( (unsigned long long)A.epoch << 32 ) | mv_packed );
+                    *(uint32_t *)( A.mvs + ( (size_t)pair * g.mb_count + xy ) * 2 ) = mv_packed;
+                    A.costs[(size_t)pair * g.mb_count + xy] = cost;
+                }
+                int bcost_blk = cost + 4;
+                if( want_intra && ic < bcost_blk )
+                {
+                    bcost_blk = ic;
+                    row_intra++;
+                }
+                row_sum += bcost_blk;
+                mv_right = mv_packed;
+                last_mv = mv_packed;
+            }
+            else
+                last_mv = 0;
+            mv_br = mv_b;
+            mv_b = mv_bl;
+        }
+
+        if( row_ok && r == 0 )
+        {
+            int32_t *s = A.sums + (size_t)pair * X264DSP_LA_SUMS;
+            atomicAdd( &s[X264DSP_LA_COST_INTER], row_sum );
+            atomicAdd( &s[X264DSP_LA_INTRA_MBS], row_intra );
+            atomicAdd( &s[X264DSP_LA_SAD_EVALS], sad_evals );
+            atomicAdd( &s[X264DSP_LA_SATD_EVALS], satd_evals );
+            if( A.row_satds )
+                A.row_satds[(size_t)pair * 2 * H + by] = row_sum;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 
 // scratch for `n_pairs` pairs; called once per batch before any group is launched
@@ -691,32 +1160,45 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
     XD_CHECK( cudaGetLastError() );
     if( n_inter > 0 )
     {
-        const int total_rows = n_inter * ( g->mb_h - 2 );
-        int ctas = ( total_rows + LA_WARPS - 1 ) / LA_WARPS;
-        // persistent launch: never more CTAs than fit on the machine at once (rows beyond that are
-        // picked up through the ticket as warps finish; the ticket order keeps that deadlock-free)
-        static int per_sm[2] = { 0, 0 };
-        const int timed = ctx->la_timing != NULL;
-        if( !per_sm[timed] )
+        static int use_row = -1;                         // X264DSP_LA_ROW=1: the warp-per-row kernel (A/B timing)
+        if( use_row < 0 )
         {
-            if( timed )
-                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[1], xd_la_inter_kernel<true>, LA_WARPS * 32, 0 ) );
-            else
-                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[0], xd_la_inter_kernel<false>, LA_WARPS * 32, 0 ) );
-            if( per_sm[timed] < 1 )
-                per_sm[timed] = 1;
-            const char *e = getenv( "X264DSP_LA_CTAS_PER_SM" );      // tuning knob (tools/la_phase_timing.py)
-            if( e && atoi( e ) > 0 && atoi( e ) < per_sm[timed] )
-                per_sm[timed] = atoi( e );
+            const char *e = getenv( "X264DSP_LA_ROW" );
+            use_row = e && atoi( e ) > 0;
         }
-        const int cap = ctx->sm_count * per_sm[timed];
+        const int timed = ctx->la_timing != NULL;
+        const int row_kernel = use_row || timed;
+        const int rows = g->mb_h - 2;
+        const int total_warps = row_kernel ? n_inter * rows : n_inter * ( ( rows + 3 ) / 4 );
+        int ctas = ( total_warps + LA_WARPS - 1 ) / LA_WARPS;
+        // persistent launch: never more CTAs than fit on the machine at once (work beyond that is
+        // picked up through the ticket as warps finish; the ticket order keeps that deadlock-free)
+        static int per_sm[3] = { 0, 0, 0 };
+        const int which = timed ? 1 : row_kernel ? 0 : 2;
+        if( !per_sm[which] )
+        {
+            if( which == 1 )
+                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[1], xd_la_inter_kernel<true>, LA_WARPS * 32, 0 ) );
+            else if( which == 0 )
+                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[0], xd_la_inter_kernel<false>, LA_WARPS * 32, 0 ) );
+            else
+                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[2], xd_la_quad_kernel, LA_WARPS * 32, 0 ) );
+            if( per_sm[which] < 1 )
+                per_sm[which] = 1;
+            const char *e = getenv( "X264DSP_LA_CTAS_PER_SM" );      // tuning knob (tools/la_phase_timing.py)
+            if( e && atoi( e ) > 0 && atoi( e ) < per_sm[which] )
+                per_sm[which] = atoi( e );
+        }
+        const int cap = ctx->sm_count * per_sm[which];
         if( ctas > cap )
             ctas = cap;
         pslot = xd_prof_begin( ctx, XD_PROF_LA_INTER, s );
-        if( timed )
+        if( which == 1 )
             xd_la_inter_kernel<true><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
-        else
+        else if( which == 0 )
             xd_la_inter_kernel<false><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
+        else
+            xd_la_quad_kernel<<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
         xd_prof_end( ctx, XD_PROF_LA_INTER, pslot, s );
         ctx->launches++;
         XD_CHECK( cudaGetLastError() );
