@@ -42,6 +42,7 @@ struct xd_la_args
     int32_t *ticket;
     uint32_t epoch;
     int me_range;
+    int slack;                          // quad kernel: extra blocks a quad stays behind the one below
     unsigned long long *timing;         // optional phase-cycle counters (x264dsp_debug_lookahead_timing)
 };
 
@@ -636,8 +637,8 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 
 struct xd_lq_block
 {
-    const uint8_t *ref;       // reference lowres plane N at the block origin; planes H,V,HV follow
-    size_t plane_size;
+    const uint8_t *rowp;      // reference lowres plane N at this lane's row of the block origin; planes H,V,HV follow
+    int plane_size;           // all displacements from rowp are 32-bit byte offsets
     int stride;
     uint2 fenc;               // this lane's source row
     uint32_t fw[4];           // the same row as fw[k] = p[k] | p[k+4] << 16
@@ -658,32 +659,60 @@ __device__ __forceinline__ int xd_lq_bits( const xd_lq_block &B, int qx, int qy 
     return __ldg( B.cost_mv + ( qx - B.mvpx ) ) + __ldg( B.cost_mv + ( qy - B.mvpy ) );
 }
 
-// 8 pixels of row r of the prediction at quarter-pel (qx,qy): get_ref / mc_luma (mc.c:192-264)
-__device__ __forceinline__ uint2 xd_lq_fetch( const xd_lq_block &B, int qx, int qy, int r )
+// 8 consecutive pixels at an arbitrary byte address: three aligned words and two funnel shifts
+// (shf.r.wrap takes the shift modulo 32, so the byte offset needs no masking)
+__device__ __forceinline__ uint2 xd_lq_load8( const uint8_t *p )
+{
+    // two aligned 8-byte loads always contain the 8 wanted bytes; fewer, wider requests matter here
+    // because every lane of a warp reads a different cache line (the L1 wavefront count is the limit)
+    const uintptr_t a = (uintptr_t)p;
+    const uint2 *w = (const uint2 *)( a & ~(uintptr_t)7 );
+    const uint2 lo = __ldg( w ), hi = __ldg( w + 1 );
+    const uint32_t sh = (uint32_t)a << 3;
+    const bool up = ( (uint32_t)a & 4u ) != 0;
+    const uint32_t w0 = up ? lo.y : lo.x, w1 = up ? hi.x : lo.y, w2 = up ? hi.y : hi.x;
+    return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+}
+
+// SAD of this lane's 8 pixels against its source row, accumulated onto acc (two VABSDIFF4.U8.ACC)
+__device__ __forceinline__ uint32_t xd_lq_sad8( uint2 p, uint2 f, uint32_t acc )
+{
+    uint32_t t, d;
+    asm( "vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"( t ) : "r"( p.x ), "r"( f.x ), "r"( acc ) );
+    asm( "vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"( d ) : "r"( p.y ), "r"( f.y ), "r"( t ) );
+    return d;
+}
+
+// two 16-bit sums in one word
+__device__ __forceinline__ uint32_t xd_lq_pack( uint32_t lo, uint32_t hi )
+{
+    return __byte_perm( lo, hi, 0x5410 );
+}
+
+// 8 pixels of this lane's row of the prediction at quarter-pel (qx,qy): get_ref / mc_luma (mc.c:192-264)
+__device__ __forceinline__ uint2 xd_lq_fetch( const xd_lq_block &B, int qx, int qy )
 {
     const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
-    const int64_t base = (int64_t)( ( qy >> 2 ) + r ) * B.stride + ( qx >> 2 );
-    uint2 a = xd_load8_unaligned( B.ref + (size_t)xd_qpel_plane_a( phase ) * B.plane_size + base + ( fy == 3 ? B.stride : 0 ) );
+    const int off = ( qy >> 2 ) * B.stride + ( qx >> 2 );
+    uint2 a = xd_lq_load8( B.rowp + ( off + xd_qpel_plane_a( phase ) * B.plane_size + ( fy == 3 ? B.stride : 0 ) ) );
     if( phase & 5 )
     {
-        const uint2 b = xd_load8_unaligned( B.ref + (size_t)xd_qpel_plane_b( phase ) * B.plane_size + base + ( fx == 3 ? 1 : 0 ) );
+        const uint2 b = xd_lq_load8( B.rowp + ( off + xd_qpel_plane_b( phase ) * B.plane_size + ( fx == 3 ? 1 : 0 ) ) );
         a.x = xd_avg4( a.x, b.x );
         a.y = xd_avg4( a.y, b.y );
     }
     return a;
 }
 
-// full-pel position: plane N only
-__device__ __forceinline__ uint32_t xd_lq_sad_fpel( const xd_lq_block &B, int mx, int my, int r )
+// full-pel position given as a byte offset from the block origin: plane N only
+__device__ __forceinline__ uint32_t xd_lq_sad_off( const xd_lq_block &B, int off )
 {
-    const uint2 p = xd_load8_unaligned( B.ref + (int64_t)( my + r ) * B.stride + mx );
-    return __vsadu4( p.x, B.fenc.x ) + __vsadu4( p.y, B.fenc.y );
+    return xd_lq_sad8( xd_lq_load8( B.rowp + off ), B.fenc, 0u );
 }
 
-__device__ __forceinline__ uint32_t xd_lq_sad_qpel( const xd_lq_block &B, int qx, int qy, int r )
+__device__ __forceinline__ uint32_t xd_lq_sad_qpel( const xd_lq_block &B, int qx, int qy )
 {
-    const uint2 p = xd_lq_fetch( B, qx, qy, r );
-    return __vsadu4( p.x, B.fenc.x ) + __vsadu4( p.y, B.fenc.y );
+    return xd_lq_sad8( xd_lq_fetch( B, qx, qy ), B.fenc, 0u );
 }
 
 // p[k] | p[k+4] << 16 for k = 0..3
@@ -708,7 +737,7 @@ __device__ __forceinline__ int xd_lq_satd( const xd_lq_block &B, int qx, int qy,
 {
     uint2 p = make_uint2( 0u, 0u );
     if( on )
-        p = xd_lq_fetch( B, qx, qy, r );
+        p = xd_lq_fetch( B, qx, qy );
     uint32_t w[4];
     xd_lq_unpack( p, w );
     // horizontal 4-point transform of the row, left and right 4x4 side by side in the two halves
@@ -771,10 +800,10 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         const int sminy = ( miny - 8 ) << 2, smaxy = ( maxy + 8 ) << 2;
 
         xd_lq_block B;
-        B.plane_size = (size_t)g.lowres_plane_size;
+        B.plane_size = g.lowres_plane_size;
         B.stride = ls;
         B.cost_mv = A.cost_mv;
-        B.ref = ref;
+        B.rowp = ref;
         B.mvpx = B.mvpy = 0;
         B.fenc = make_uint2( 0u, 0u );
         B.fw[0] = B.fw[1] = B.fw[2] = B.fw[3] = 0u;
@@ -783,9 +812,17 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         uint32_t mv_right = 0, mv_b = 0, mv_br = 0, mv_bl = 0;
         uint32_t last_mv = 0;                              // this group's previous result (0 when it had none)
         unsigned long long pending = 0;
-        // step t = -1 only shifts the neighbour pipeline: it brings (W-2, below) in
+        // step t = -1 only shifts the neighbour pipeline: it brings (W-2, below) in.
+        // Rows could follow each other two blocks apart, but then every step of every quad of a pair
+        // would start with a publish -> poll round trip through L2 and the whole chain would advance at
+        // the pace of its slowest member.  Starting A.slack blocks later decouples them: in steady
+        // state the word a quad needs has been there for several block times.
         if( has_below )
+        {
+            const int far = max( W - 2 - A.slack, 1 );
+            xd_la_await( sync_below + far, xd_ld_sync( sync_below + far ), A.epoch, 500, 8000 );
             pending = xd_ld_sync( sync_below + ( W - 2 ) );
+        }
 
         // the first block's source row, fetched ahead like every later one
         uint2 nx_fenc = make_uint2( 0u, 0u );
@@ -811,7 +848,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 uint32_t polled = 0;
                 if( has_below && bx0 - 1 >= 1 && bx0 - 1 <= W - 2 )
                 {
-                    polled = xd_la_await( sync_below + ( bx0 - 1 ), pending, A.epoch, t < 0 ? 250 : 20, t < 0 ? 4000 : 200 );
+                    polled = xd_la_await( sync_below + ( bx0 - 1 ), pending, A.epoch, t < 0 ? 500 : 100, t < 0 ? 8000 : 1000 );
                     if( bx0 - 2 >= 1 )
                         pending = xd_ld_sync( sync_below + ( bx0 - 2 ) );
                 }
@@ -827,7 +864,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             if( act )
             {
                 const size_t pel = ( (size_t)by * ls + bx ) * 8;
-                B.ref = ref + pel;
+                B.rowp = ref + pel + r * ls;
                 B.fenc = nx_fenc;
                 ic = nx_ic;
                 if( bx > 1 )
@@ -895,7 +932,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 {
                     uint32_t s = 0;
                     if( cok[k] )
-                        s = xd_lq_sad_fpel( B, ccx[k], ccy[k], r );
+                        s = xd_lq_sad_off( B, ccy[k] * ls + ccx[k] );
                     w[k >> 1] += s << ( 16 * ( k & 1 ) );
                 }
                 // lane r adds candidate r's mv bits, or the "does not compete" marker
@@ -945,8 +982,9 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     uint32_t w0 = 0, w1 = 0;
                     if( dia )
                     {
-                        w0 = xd_lq_sad_fpel( B, bmx, bmy - 1, r ) | ( xd_lq_sad_fpel( B, bmx, bmy + 1, r ) << 16 );
-                        w1 = xd_lq_sad_fpel( B, bmx - 1, bmy, r ) | ( xd_lq_sad_fpel( B, bmx + 1, bmy, r ) << 16 );
+                        const int off = bmy * ls + bmx;
+                        w0 = xd_lq_pack( xd_lq_sad_off( B, off - ls ), xd_lq_sad_off( B, off + ls ) );
+                        w1 = xd_lq_pack( xd_lq_sad_off( B, off - 1 ), xd_lq_sad_off( B, off + 1 ) );
                         if( r < 4 )
                         {
                             const int dx = r == 2 ? -1 : r == 3 ? 1 : 0, dy = r == 0 ? -1 : r == 1 ? 1 : 0;
@@ -996,7 +1034,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     uint32_t s = 0;
                     if( single )
                     {
-                        s = xd_lq_sad_qpel( B, px, py, r );
+                        s = xd_lq_sad_qpel( B, px, py );
                         if( r == 0 )
                             s += (uint32_t)xd_lq_bits( B, px, py );
                     }
@@ -1011,8 +1049,8 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 uint32_t w0 = 0, w1 = 0;
                 if( search )
                 {
-                    w0 = xd_lq_sad_qpel( B, qx, qy - 2, r ) | ( xd_lq_sad_qpel( B, qx, qy + 2, r ) << 16 );
-                    w1 = xd_lq_sad_qpel( B, qx - 2, qy, r ) | ( xd_lq_sad_qpel( B, qx + 2, qy, r ) << 16 );
+                    w0 = xd_lq_pack( xd_lq_sad_qpel( B, qx, qy - 2 ), xd_lq_sad_qpel( B, qx, qy + 2 ) );
+                    w1 = xd_lq_pack( xd_lq_sad_qpel( B, qx - 2, qy ), xd_lq_sad_qpel( B, qx + 2, qy ) );
                     if( r < 4 )
                     {
                         const int dx = r == 2 ? -2 : r == 3 ? 2 : 0, dy = r == 0 ? -2 : r == 1 ? 2 : 0;
@@ -1149,6 +1187,16 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
     A.ticket = ctx->la_ticket + ticket_slot;
     A.epoch = ctx->la_epoch;
     A.me_range = 16;                                 // x264_param_default: analyse.i_me_range
+    {
+        static int slack = -1;
+        if( slack < 0 )
+        {
+            const char *e = getenv( "X264DSP_LA_SLACK" );            // tuning knob
+            slack = e ? atoi( e ) : 8;
+            if( slack < 0 ) slack = 0;
+        }
+        A.slack = slack;
+    }
     A.timing = ctx->la_timing;
 
     const int inner = ( g->mb_w - 2 ) * ( g->mb_h - 2 );
