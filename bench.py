@@ -374,7 +374,9 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("xd_la_inter_kernel_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("xd_la_quad_kernel_bytes_per_pair")
+            if traffic is not None:
+                traffic = traffic * pairs_per_launch
         sad_px = int(sums_np[:, pkg.LA_SAD_EVALS].sum()) * 64
         satd_px = int(sums_np[:, pkg.LA_SATD_EVALS].sum()) * 64
         step_s = dev_ms / 1e3 / args.steps
@@ -389,11 +391,13 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "api": "x264dsp_lookahead_clips_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "xd_la_inter_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "xd_la_quad_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(bytes_per_pair * pairs_per_launch),
                          "avg_launch_ms": inter_avg_s * 1e3, "launches_timed": inter_n,
-                         "note": "dependency/latency bound wavefront (SURVEY 8(d) config 2); HBM % reported as required"},
+                         "note": "dependent-search wavefront kernel (SURVEY 8(d) config 2): HBM % reported as required; ncu "
+                                 "(profiles/) shows the L1 data pipe (one cache line per lane) and issue slots as the "
+                                 "limiters, DRAM at a few % of peak"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "pixel_cmp": {"sad_gpix_per_s": sad_px * world / step_s / 1e9, "satd_gpix_per_s": satd_px * world / step_s / 1e9,
                           "sad_pix_per_step_per_gpu": sad_px, "satd_pix_per_step_per_gpu": satd_px,
