@@ -267,6 +267,14 @@ int x264dsp_me_search_sized_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
                                  const x264dsp_me_params_t *params, int i_pixel, int n,
                                  const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
                                  void *stream );
+/* the same for n_frames frame pairs in one launch: pair f searches fenc_slots + f*slot_bytes in
+ * fref_slots + f*slot_bytes with blocks[f*n .. f*n+n) -> results[f*n ..).  One 1080p frame of 16x16
+ * blocks is about half a wave on 148 SMs; a batch fills the machine. */
+int x264dsp_me_search_sized_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                        const uint8_t *fenc_slots, const uint8_t *fref_slots, int n_frames,
+                                        const x264dsp_me_params_t *params, int i_pixel, int n,
+                                        const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                        void *stream );
 
 /* ------------------------------------------------------------------ residual
  * The inter-macroblock branch of x264_macroblock_encode + x264_mb_encode_chroma
@@ -282,11 +290,19 @@ int x264dsp_me_search_sized_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
 int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
                                 const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
                                 int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream );
+/* the same for n_frames consecutive slots in one launch; levels / nnz / cbp hold n_frames x mb_count
+ * macroblocks back to back (one frame per launch is launch- and tail-bound, a batch streams) */
+int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                 const uint8_t *fenc_slots, uint8_t *pred_slots, int n_frames, int qp,
+                                 int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream );
 
 /* x264_mb_mc for P_L0 16x16 macroblocks (common/macroblock.c:8-28; mc_luma common/mc.c:216-239,
  * mc_chroma common/mc.c:290-323): builds the prediction frame from one quarter-pel MV per MB. */
 int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,
                           const int16_t *mv, uint8_t *pred_slot, void *stream );
+/* n_frames consecutive reference slots -> n_frames consecutive prediction slots, mv[n_frames][mb_count][2] */
+int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slots,
+                           int n_frames, const int16_t *mv, uint8_t *pred_slots, void *stream );
 
 /* ------------------------------------------------------------------ deblock
  * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's

@@ -73,6 +73,47 @@ def test_mc_and_residual_frame(pkg, ctx, w, h, qp):
     assert (cbp_o != 0).any()
 
 
+@pytest.mark.parametrize("w,h,nf,qp", [(352, 288, 4, 26), (1920, 1080, 3, 30), (200, 120, 5, 18)])
+def test_mc_and_residual_frames_batch(pkg, ctx, w, h, nf, qp):
+    """nf frame pairs in one launch each (x264dsp_mc_frames_dev / x264dsp_residual_frames_dev) against the
+    oracle frame by frame"""
+    import torch
+    g, go, host, dev = _slots(pkg, ctx, w, h, nf + 1, True)
+    o = cc.oracle()
+    rng = np.random.RandomState(qp + nf)
+    n = g.mb_count
+    mv = (np.array([12, 8]) + rng.randint(-6, 7, (nf, n, 2))).astype(np.int16)
+    mv[rng.rand(nf, n) < 0.05] = rng.randint(-3000, 3000, 2)
+    pred_o, lv_o, nz_o, cbp_o = [], [], [], []
+    for f in range(nf):
+        po = np.zeros(go.slot_bytes, np.uint8)
+        o.xo_mc_frame(C.byref(go), ptr(host[f]), ptr(mv[f], i16p), ptr(po))
+        lv, nz, cb = np.zeros((n, pkg.RES_LEVELS_PER_MB), np.int16), np.zeros((n, pkg.RES_NNZ_PER_MB), np.uint8), np.zeros(n, np.int16)
+        mc_only = po.copy()
+        o.xo_residual_frame(C.byref(go), ptr(host[f + 1]), ptr(po), qp, ptr(lv, i16p), ptr(nz), ptr(cb, i16p))
+        pred_o.append((mc_only, po)); lv_o.append(lv); nz_o.append(nz); cbp_o.append(cb)
+    pred = torch.zeros(nf * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    d_mv = torch.from_numpy(mv).cuda()
+    torch.cuda.synchronize()
+    ctx.mc_frames(g, dev[: nf * g.slot_bytes], nf, d_mv, pred)
+    ctx.sync()
+    got = pred.cpu().numpy().reshape(nf, -1)
+    for f in range(nf):
+        assert np.array_equal(got[f], pred_o[f][0]), f"mc frame {f}"
+    lv = torch.full((nf, n, pkg.RES_LEVELS_PER_MB), -1, dtype=torch.int16, device="cuda")
+    nz = torch.full((nf, n, pkg.RES_NNZ_PER_MB), 77, dtype=torch.uint8, device="cuda")
+    cbp = torch.full((nf, n), -1, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    ctx.residual_frames(g, dev[g.slot_bytes:], pred, nf, qp, lv, nz, cbp)
+    ctx.sync()
+    got = pred.cpu().numpy().reshape(nf, -1)
+    for f in range(nf):
+        assert np.array_equal(cbp.cpu().numpy()[f], cbp_o[f]), f"cbp frame {f}"
+        assert np.array_equal(nz.cpu().numpy()[f], nz_o[f]), f"nnz frame {f}"
+        assert np.array_equal(lv.cpu().numpy()[f], lv_o[f]), f"levels frame {f}"
+        assert np.array_equal(got[f], pred_o[f][1]), f"recon frame {f}"
+
+
 @pytest.mark.parametrize("w,h,qp,aoff,boff", [(352, 288, 26, 0, 0), (200, 120, 38, 0, 0), (352, 288, 20, 3, -2),
                                               (1920, 1080, 30, 0, 0), (64, 64, 51, 0, 0), (352, 288, 14, 0, 0)])
 def test_deblock_frame(pkg, ctx, w, h, qp, aoff, boff):

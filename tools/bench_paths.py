@@ -154,8 +154,13 @@ def main():
             for p in range(P):
                 ctx.me_search_sized(g, slots[(p + 1) * g.slot_bytes:(p + 2) * g.slot_bytes],
                                     slots[p * g.slot_bytes:(p + 1) * g.slot_bytes], prm, size, nb, d_blocks[p], d_res[p])
-        t = timed(run_me_sized)
+        t_single = timed(run_me_sized)
+        d_blocks_all = torch.cat(d_blocks)
+        d_res_all = torch.zeros(P * nb * cc.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        t = timed(lambda: ctx.me_search_sized_frames(g, slots[g.slot_bytes:], slots, P, prm, size, nb, d_blocks_all, d_res_all))
+        assert torch.equal(d_res_all, torch.cat(d_res)), "batched and per-frame launches disagree"
         rec = {"blocks_per_frame": nb, "ms_per_frame": t / P, "frames_per_s": 1e3 * P / t,
+               "one_frame_per_launch_ms_per_frame": t_single / P,
                "generic_warp_per_block_ms_per_frame": t_generic / P}
         if size == 0:
             mv16 = [r.cpu().numpy().view(cc.ME_RESULT_DTYPE)["mv"].copy() for r in d_res]
@@ -202,7 +207,10 @@ def main():
             for p in range(P):
                 ctx.mc_frame(g, sl(slots, p), d_mv[p], sl(pred, p))
         t = timed(run_mc)
-        report("mc_frame_16x16", t, P, nmb * 384 * 2, "384 B in (+halo) + 384 B out per MB")
+        report("mc_frame_16x16", t, P, nmb * 384 * 2, "one frame per launch: 384 B in (+halo) + 384 B out per MB")
+        d_mv_all = torch.stack(d_mv)
+        t = timed(lambda: ctx.mc_frames(g, slots, P, d_mv_all, pred))
+        report("mc_frames_batched", t, P, nmb * 384 * 2, f"{P} frames per launch")
 
         def run_res():
             for p in range(P):
@@ -210,7 +218,13 @@ def main():
         run_res()                                # warm-up (first launch of the kernel)
         run_mc()
         t = timed(run_res, warm=0, reps=1)       # in place: one pass over freshly predicted frames
-        report("residual_frame", t, P, nmb * (384 * 3 + 784 + 29), "SURVEY 8(d): ~2.0 kB/MB")
+        report("residual_frame", t, P, nmb * (384 * 3 + 784 + 29), "one frame per launch; SURVEY 8(d): ~2.0 kB/MB")
+        lv_all = torch.zeros((P, nmb, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda")
+        nz_all = torch.zeros((P, nmb, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda")
+        cbp_b = torch.zeros((P, nmb), dtype=torch.int16, device="cuda")
+        ctx.mc_frames(g, slots, P, d_mv_all, pred)
+        t = timed(lambda: ctx.residual_frames(g, slots[g.slot_bytes:], pred, P, args.qp, lv_all, nz_all, cbp_b), warm=0, reps=1)
+        report("residual_frames_batched", t, P, nmb * (384 * 3 + 784 + 29), f"{P} frames per launch")
 
         # deblock inputs: P_L0 16x16 everywhere, bS from a random-but-plausible field (timing only; parity is tests/)
         rng = np.random.RandomState(1)

@@ -315,6 +315,13 @@ class Context:
                                                 C.byref(params), int(i_pixel), int(n), _dp(blocks_dev),
                                                 _dp(results_dev), None), "x264dsp_me_search_sized_dev")
 
+    def me_search_sized_frames(self, g, fenc_slots, fref_slots, n_frames, params, i_pixel, n, blocks_dev, results_dev):
+        """n_frames frame pairs (consecutive slots), n blocks each, one launch"""
+        check(lib().x264dsp_me_search_sized_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(fref_slots),
+                                                       int(n_frames), C.byref(params), int(i_pixel), int(n),
+                                                       _dp(blocks_dev), _dp(results_dev), None),
+              "x264dsp_me_search_sized_frames_dev")
+
     # ---- residual / MC / deblock ---------------------------------------------------------
     def mc_frame(self, g, fref_slot, mv_dev, pred_slot):
         check(lib().x264dsp_mc_frame_dev(self._h, C.byref(g), _dp(fref_slot), _dp(mv_dev), _dp(pred_slot), None),
@@ -324,6 +331,15 @@ class Context:
         check(lib().x264dsp_residual_frame_dev(self._h, C.byref(g), _dp(fenc_slot), _dp(pred_slot), int(qp),
                                                _dp(levels), _dp(nnz), _dp(cbp), None),
               "x264dsp_residual_frame_dev")
+
+    def mc_frames(self, g, fref_slots, n_frames, mv_dev, pred_slots):
+        check(lib().x264dsp_mc_frames_dev(self._h, C.byref(g), _dp(fref_slots), int(n_frames), _dp(mv_dev),
+                                          _dp(pred_slots), None), "x264dsp_mc_frames_dev")
+
+    def residual_frames(self, g, fenc_slots, pred_slots, n_frames, qp, levels, nnz, cbp):
+        check(lib().x264dsp_residual_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
+                                                int(qp), _dp(levels), _dp(nnz), _dp(cbp), None),
+              "x264dsp_residual_frames_dev")
 
     def deblock_frame(self, g, slot, mb_type, partition, cbp, bs, qp, alpha_off=0, beta_off=0):
         check(lib().x264dsp_deblock_frame_dev(self._h, C.byref(g), _dp(slot), _dp(mb_type), _dp(partition),

@@ -1208,14 +1208,19 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
     XD_CHECK( cudaGetLastError() );
     if( n_inter > 0 )
     {
-        static int use_row = -1;                         // X264DSP_LA_ROW=1: the warp-per-row kernel (A/B timing)
-        if( use_row < 0 )
+        // Two mappings of the same search (both bit-exact): the quad-row kernel executes a third of the
+        // instructions per block and wins once the batch fills the machine; with few pairs in flight the
+        // launch is bound by the per-pair dependency chain and the warp-per-row kernel, which spreads a
+        // block over 32 lanes and a frame over four times as many warps, has the shorter chain.
+        // Measured crossover on B200: a few dozen pairs.  X264DSP_LA_ROW=0/1 forces one of them.
+        static int force_row = -2;
+        if( force_row == -2 )
         {
             const char *e = getenv( "X264DSP_LA_ROW" );
-            use_row = e && atoi( e ) > 0;
+            force_row = e ? ( atoi( e ) > 0 ) : -1;
         }
         const int timed = ctx->la_timing != NULL;
-        const int row_kernel = use_row || timed;
+        const int row_kernel = timed || ( force_row >= 0 ? force_row : n_inter < 48 );
         const int rows = g->mb_h - 2;
         const int total_warps = row_kernel ? n_inter * rows : n_inter * ( ( rows + 3 ) / 4 );
         int ctas = ( total_warps + LA_WARPS - 1 ) / LA_WARPS;

@@ -235,6 +235,11 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
     const int blk = tid / C::G, sub = tid % C::G;
     if( blk >= n )
         return;                     // whole groups leave together: n is counted in blocks, G divides the CTA
+    // blockIdx.y = frame pair of a batch: consecutive slots, n blocks / results per frame
+    fenc_slot += blockIdx.y * (size_t)g.slot_bytes;
+    fref_slot += blockIdx.y * (size_t)g.slot_bytes;
+    blocks += blockIdx.y * (size_t)n;
+    results += blockIdx.y * (size_t)n;
     const int lane = threadIdx.x & 31;
     const unsigned gmask = C::G == 32 ? 0xffffffffu : ( ( 1u << C::G ) - 1u ) << ( lane & ~( C::G - 1 ) );
     const x264dsp_me_block_t *in = blocks + blk;
@@ -439,11 +444,11 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
 
 template<int W, int H>
 static int xd_mes_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *fref_slot,
-                          const x264dsp_me_params_t *params, int n, const x264dsp_me_block_t *blocks,
+                          const x264dsp_me_params_t *params, int n_frames, int n, const x264dsp_me_block_t *blocks,
                           x264dsp_me_result_t *results, cudaStream_t s )
 {
     const int64_t threads = (int64_t)n * xd_mes_cfg<W, H>::G;
-    const int grid = (int)( ( threads + MES_THREADS - 1 ) / MES_THREADS );
+    const dim3 grid( (unsigned)( ( threads + MES_THREADS - 1 ) / MES_THREADS ), n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_ME, s );
     xd_me_sized_kernel<W, H><<<grid, MES_THREADS, 0, s>>>( *g, fenc_slot, fref_slot, *params,
                                                            ctx->cost_mv_dev[params->qp] + 4096, n, blocks, results );
@@ -453,13 +458,14 @@ static int xd_mes_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uin
     return 0;
 }
 
-extern "C" int x264dsp_me_search_sized_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
-                                             const uint8_t *fenc_slot, const uint8_t *fref_slot,
-                                             const x264dsp_me_params_t *params, int i_pixel, int n,
-                                             const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
-                                             void *stream )
+extern "C" int x264dsp_me_search_sized_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                                    const uint8_t *fenc_slot, const uint8_t *fref_slot, int n_frames,
+                                                    const x264dsp_me_params_t *params, int i_pixel, int n,
+                                                    const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                                    void *stream )
 {
-    if( !ctx || !g || !fenc_slot || !fref_slot || !params || n < 0 || i_pixel < 0 || i_pixel > 7 )
+    if( !ctx || !g || !fenc_slot || !fref_slot || !params || n < 0 || i_pixel < 0 || i_pixel > 7 || n_frames <= 0
+        || n_frames > 65535 )
         return X264DSP_E_ARG;
     if( params->subpel_refine < 1 || params->subpel_refine > 5 || params->qp < 0 || params->qp > 51
         || params->me_method < X264DSP_ME_DIA || params->me_method > X264DSP_ME_HEX || params->me_range < 1 )
@@ -471,13 +477,22 @@ extern "C" int x264dsp_me_search_sized_dev( x264dsp_ctx_t *ctx, const x264dsp_ge
     cudaStream_t s = xd_stream( ctx, stream );
     switch( i_pixel )
     {
-    case X264DSP_PIXEL_16x16: return xd_mes_launch<16, 16>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
-    case X264DSP_PIXEL_16x8:  return xd_mes_launch<16, 8>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
-    case X264DSP_PIXEL_8x16:  return xd_mes_launch<8, 16>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
-    case X264DSP_PIXEL_8x8:   return xd_mes_launch<8, 8>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
-    case X264DSP_PIXEL_8x4:   return xd_mes_launch<8, 4>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
-    case X264DSP_PIXEL_4x8:   return xd_mes_launch<4, 8>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
-    case X264DSP_PIXEL_4x4:   return xd_mes_launch<4, 4>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
-    default:                  return xd_mes_launch<4, 16>( ctx, g, fenc_slot, fref_slot, params, n, blocks, results, s );
+    case X264DSP_PIXEL_16x16: return xd_mes_launch<16, 16>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
+    case X264DSP_PIXEL_16x8:  return xd_mes_launch<16, 8>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
+    case X264DSP_PIXEL_8x16:  return xd_mes_launch<8, 16>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
+    case X264DSP_PIXEL_8x8:   return xd_mes_launch<8, 8>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
+    case X264DSP_PIXEL_8x4:   return xd_mes_launch<8, 4>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
+    case X264DSP_PIXEL_4x8:   return xd_mes_launch<4, 8>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
+    case X264DSP_PIXEL_4x4:   return xd_mes_launch<4, 4>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
+    default:                  return xd_mes_launch<4, 16>( ctx, g, fenc_slot, fref_slot, params, n_frames, n, blocks, results, s );
     }
+}
+
+extern "C" int x264dsp_me_search_sized_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                             const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                                             const x264dsp_me_params_t *params, int i_pixel, int n,
+                                             const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                             void *stream )
+{
+    return x264dsp_me_search_sized_frames_dev( ctx, g, fenc_slot, fref_slot, 1, params, i_pixel, n, blocks, results, stream );
 }

@@ -28,6 +28,10 @@ xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const in
     const int mb = blockIdx.x * 4 + ( threadIdx.x >> 6 );
     if( mb >= g.mb_count )
         return;
+    // blockIdx.y = frame of a batch: consecutive slots, mb_count MVs per frame
+    fref += blockIdx.y * (size_t)g.slot_bytes;
+    pred += blockIdx.y * (size_t)g.slot_bytes;
+    mv += blockIdx.y * (size_t)g.mb_count * 2;
     const int t = threadIdx.x & 63;
     const int mb_x = mb % g.mb_w, mb_y = mb / g.mb_w;
     const int ls = g.luma_stride, cs = g.chroma_stride;
@@ -76,6 +80,12 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     const int mb = blockIdx.x * 4 + ( threadIdx.x >> 5 );
     if( mb >= g.mb_count )
         return;
+    // blockIdx.y = frame of a batch: consecutive slots, per-frame output arrays back to back
+    fenc += blockIdx.y * (size_t)g.slot_bytes;
+    pred += blockIdx.y * (size_t)g.slot_bytes;
+    levels += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_LEVELS_PER_MB;
+    nnz_out += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_NNZ_PER_MB;
+    cbp_out += blockIdx.y * (size_t)g.mb_count;
     const int mb_x = mb % g.mb_w, mb_y = mb / g.mb_w;
     const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
     const int ch = ( lane - 16 ) >> 2, ci = ( lane - 16 ) & 3;
@@ -330,11 +340,12 @@ static void xd_fill_qparams( xd_qparams *q, int qp )
     q->qbits = qp / 6 - 4;
 }
 
-extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
-                                            const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
-                                            int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream )
+extern "C" int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                             const uint8_t *fenc_slot, uint8_t *pred_slot, int n_frames, int qp,
+                                             int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream )
 {
-    if( !ctx || !g || !fenc_slot || !pred_slot || !levels || !nnz || !cbp || qp < 0 || qp > 51 )
+    if( !ctx || !g || !fenc_slot || !pred_slot || !levels || !nnz || !cbp || qp < 0 || qp > 51 || n_frames <= 0
+        || n_frames > 65535 )
         return X264DSP_E_ARG;
     xd_res_tables T;
     const int qpc = x264dsp_chroma_qp( qp );
@@ -352,7 +363,7 @@ extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geo
     T.qpc = qpc;
     T.thresh = ( xd_lambda2_tab[qpc] + 32 ) >> 6;
     cudaStream_t s = xd_stream( ctx, stream );
-    const int grid = ( g->mb_count + 3 ) / 4;
+    const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_RESIDUAL, s );
     xd_residual_kernel<<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, levels, nnz, cbp );
     xd_prof_end( ctx, XD_PROF_RESIDUAL, pslot, s );
@@ -361,17 +372,30 @@ extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geo
     return 0;
 }
 
-extern "C" int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,
-                                      const int16_t *mv, uint8_t *pred_slot, void *stream )
+extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                            const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
+                                            int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream )
 {
-    if( !ctx || !g || !fref_slot || !mv || !pred_slot || fref_slot == pred_slot )
+    return x264dsp_residual_frames_dev( ctx, g, fenc_slot, pred_slot, 1, qp, levels, nnz, cbp, stream );
+}
+
+extern "C" int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,
+                                       int n_frames, const int16_t *mv, uint8_t *pred_slot, void *stream )
+{
+    if( !ctx || !g || !fref_slot || !mv || !pred_slot || fref_slot == pred_slot || n_frames <= 0 || n_frames > 65535 )
         return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
-    const int grid = ( g->mb_count + 3 ) / 4;
+    const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_MC, s );
     xd_mc_frame_kernel<<<grid, 256, 0, s>>>( *g, fref_slot, mv, pred_slot );
     xd_prof_end( ctx, XD_PROF_MC, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
+}
+
+extern "C" int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,
+                                      const int16_t *mv, uint8_t *pred_slot, void *stream )
+{
+    return x264dsp_mc_frames_dev( ctx, g, fref_slot, 1, mv, pred_slot, stream );
 }
