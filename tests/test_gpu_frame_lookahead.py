@@ -142,9 +142,12 @@ def oracle_lookahead(g, slots, i, want_intra=1, rows=False):
     return mv, c, s, r
 
 
-@pytest.mark.parametrize("w,h,n,cut", [(352, 288, 5, 3), (200, 120, 3, -1), (64, 64, 3, -1), (1920, 1080, 3, -1)])
-def test_lookahead_matches_oracle(pkg, ctx, w, h, n, cut):
+@pytest.mark.parametrize("kernel", [1, 2])      # 1 = warp per block row, 2 = warp per four block rows
+@pytest.mark.parametrize("w,h,n,cut", [(352, 288, 5, 3), (200, 120, 3, -1), (64, 64, 3, -1), (1920, 1080, 3, -1),
+                                       (96, 64, 2, -1), (80, 112, 4, 2), (64, 144, 3, -1)])
+def test_lookahead_matches_oracle(pkg, ctx, w, h, n, cut, kernel):
     torch = _torch()
+    ctx.lookahead_select_kernel(kernel)
     frames = [pkg.synth_frame(w, h, i, cut) for i in range(n)]
     g = pkg.geometry(w, h)
     go = cc.oracle_geom(w, h)
@@ -171,6 +174,48 @@ def test_lookahead_matches_oracle(pkg, ctx, w, h, n, cut):
             assert np.array_equal(gc[i], c_o), f"rep {rep} frame {i}: block costs"
             assert np.array_equal(gs[i][:5], s_o[:5]), f"rep {rep} frame {i}: sums {gs[i]} vs {s_o}"
             assert np.array_equal(gr[i], r_o), f"rep {rep} frame {i}: row sums"
+    ctx.lookahead_select_kernel(0)
+
+
+def test_lookahead_batch_of_clips_both_kernels(pkg, ctx):
+    """a launch large enough for the automatic choice to take the quad-row kernel (>= 48 pairs): many
+    short clips, both mappings and the automatic one must agree with the oracle and with each other"""
+    torch = _torch()
+    w, h, clips, clip_len = 208, 160, 20, 4
+    n = clips * clip_len
+    frames = [pkg.synth_frame(w, h, 3 * (i // clip_len) + i % clip_len, 2 if (i // clip_len) % 5 == 0 else -1) for i in range(n)]
+    g = pkg.geometry(w, h)
+    go = cc.oracle_geom(w, h)
+    ref_slots = oracle_slots(go, frames, lowres=True)
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, n)
+    ctx.frame_init_lowres(g, slots, n)
+    b = np.arange(n)
+    p0 = np.where(b % clip_len == 0, -1, b - 1)
+    want = []
+    for i in range(n):
+        o = cc.oracle()
+        mv, c, s = np.zeros((go.mb_count, 2), np.int16), np.zeros(go.mb_count, np.int32), np.zeros(8, np.int32)
+        o.xo_lookahead_frame_cost(C.byref(go), cc.ptr(ref_slots[i]), cc.ptr(ref_slots[i - 1]) if p0[i] >= 0 else None, 1,
+                                  cc.ptr(mv, cc.i16p), cc.ptr(c, cc.i32p), cc.ptr(s, cc.i32p), None)
+        want.append((mv, c, s))
+    for kernel in (2, 1, 0):
+        ctx.lookahead_select_kernel(kernel)
+        mvs = torch.full((n, g.mb_count, 2), -7, dtype=torch.int16, device="cuda")
+        costs = torch.full((n, g.mb_count), -7, dtype=torch.int32, device="cuda")
+        sums = torch.full((n, pkg.LA_SUMS), -7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.lookahead_frame_cost(g, slots, b, p0, np.ones(n, np.uint8), mvs, costs, sums)
+        ctx.sync()
+        gm, gc, gs = mvs.cpu().numpy(), costs.cpu().numpy(), sums.cpu().numpy()
+        for i in range(n):
+            if p0[i] >= 0:
+                assert np.array_equal(gm[i], want[i][0]), f"kernel {kernel} frame {i}: mvs"
+                assert np.array_equal(gc[i], want[i][1]), f"kernel {kernel} frame {i}: costs"
+            assert np.array_equal(gs[i][:5], want[i][2][:5]), f"kernel {kernel} frame {i}: sums"
+    ctx.lookahead_select_kernel(0)
 
 
 def test_lookahead_without_intra_and_host_api(pkg, ctx):

@@ -255,6 +255,10 @@ class Context:
             self._h, C.byref(g), _dp(slots_dev), len(b), _hp(b, C.c_int32), _hp(p0, C.c_int32), _hp(wi),
             _dp(mvs), _dp(costs), _dp(sums), _dp(row_satds), None), "x264dsp_lookahead_frame_cost_dev")
 
+    def lookahead_select_kernel(self, mode):
+        """0 = by batch size, 1 = warp-per-row kernel, 2 = quad-row kernel"""
+        check(lib().x264dsp_lookahead_select_kernel(self._h, int(mode)), "x264dsp_lookahead_select_kernel")
+
     def lookahead_clip_host(self, width, height, luma_frames):
         """luma_frames: uint8 numpy [n, height*width] in ordinary host memory.
         Returns (mvs [n, mb_count, 2] int16, costs [n, mb_count] int32, sums [n, LA_SUMS] int32)."""

@@ -1213,13 +1213,14 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         // launch is bound by the per-pair dependency chain and the warp-per-row kernel, which spreads a
         // block over 32 lanes and a frame over four times as many warps, has the shorter chain.
         // Measured crossover on B200: a few dozen pairs.  X264DSP_LA_ROW=0/1 forces one of them.
-        static int force_row = -2;
-        if( force_row == -2 )
+        static int env_row = -2;
+        if( env_row == -2 )
         {
             const char *e = getenv( "X264DSP_LA_ROW" );
-            force_row = e ? ( atoi( e ) > 0 ) : -1;
+            env_row = e ? ( atoi( e ) > 0 ) : -1;
         }
         const int timed = ctx->la_timing != NULL;
+        const int force_row = ctx->la_kernel ? ( ctx->la_kernel == 1 ) : env_row;
         const int row_kernel = timed || ( force_row >= 0 ? force_row : n_inter < 48 );
         const int rows = g->mb_h - 2;
         const int total_warps = row_kernel ? n_inter * rows : n_inter * ( ( rows + 3 ) / 4 );
@@ -1472,6 +1473,15 @@ extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int h
                                              const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums )
 {
     return x264dsp_lookahead_clips_host( ctx, width, height, 1, n_frames, luma, mvs, costs, sums );
+}
+
+// mode 0 = pick by batch size, 1 = warp-per-row kernel, 2 = quad-row kernel (results are identical)
+extern "C" int x264dsp_lookahead_select_kernel( x264dsp_ctx_t *ctx, int mode )
+{
+    if( !ctx || mode < 0 || mode > 2 )
+        return X264DSP_E_ARG;
+    ctx->la_kernel = mode;
+    return 0;
 }
 
 // Debug aid: cycle counters of the inter kernel's phases, summed over all warps since the last call
