@@ -4,8 +4,8 @@
 Workload (BASELINE.json configs[1]): 1080p synthetic clips of 8 frames; for every clip the lowres
 planes of all 8 frames are built (x264_frame_init_lowres) and x264_slicetype_frame_cost is run
 intra-only on frame 0 and as a P analysis (DIA + SAD full-pel, half-pel refine, SATD re-cost, 3-mode
-intra SATD) on frames 1..7.  One step = `--clips` independent clips per GPU (default 64: the step's
-input, 1.06 GB of luma, is far larger than the 126 MB L2, and the wavefronts of 448 frame pairs keep
+intra SATD) on frames 1..7.  One step = `--clips` independent clips per GPU (default 128: the step's
+input, 2.1 GB of luma, is far larger than the 126 MB L2, and the wavefronts of 896 frame pairs keep
 every warp slot of the 148 SMs busy).  Frames/s counts all frames.
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
@@ -40,10 +40,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--clips", type=int, default=64, help="independent 8-frame clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=128, help="independent 8-frame clips per GPU per step")
     ap.add_argument("--clip-len", type=int, default=8)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-me", action="store_true", help="skip the secondary full-resolution ME measurement")
     return ap.parse_args()
 
 
@@ -117,6 +118,67 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# secondary measurement (BASELINE.json configs[2]): full-resolution motion search of every partition
+# size, HEX + subme 5 + qpel refine, on the first `pairs` frame pairs of clip 0
+
+ME_SIZES = ("16x16", "16x8", "8x16", "8x8", "8x4", "4x8", "4x4")
+
+
+def me_search_measure(pkg, ctx, torch, g, luma_dev, la_mvs, pairs, reps=3, qp=26):
+    """returns (per-size ms per frame, blocks arrays of pair 0, the device slots) -- CUDA events on the
+    context's stream; one launch per size covers all `pairs` frame pairs"""
+    stream = ctx.torch_stream()
+    nf = pairs + 1
+    slots = torch.zeros(nf * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    ctx.frame_load_luma(g, luma_dev, slots, nf)
+    ctx.frame_expand_border(g, slots, nf)
+    ctx.frame_filter(g, slots, nf)
+    prm = pkg.MeParams(pkg.ME_HEX, 5, 16, qp, 1)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ms, blocks0 = {}, {}
+    for size, name in enumerate(ME_SIZES):
+        blocks = [pkg.tiling_blocks(g, size, la_mvs[p + 1]) for p in range(pairs)]
+        nb = len(blocks[0])
+        d_blocks = torch.from_numpy(np.concatenate(blocks).view(np.uint8)).cuda()
+        d_res = torch.zeros(pairs * nb * pkg.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        run = lambda: ctx.me_search_sized_frames(g, slots[g.slot_bytes:], slots, pairs, prm, size, nb, d_blocks, d_res)
+        run()
+        torch.cuda.synchronize()
+        ev[0].record(stream)
+        for _ in range(reps):
+            run()
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        ms[name] = ev[0].elapsed_time(ev[1]) / reps / pairs
+        blocks0[name] = (blocks[0], d_res[: nb * pkg.ME_RESULT_DTYPE.itemsize].cpu().numpy())
+    return ms, blocks0, slots
+
+
+def me_search_cpu_counts(pkg, g, slots, blocks0, qp=26):
+    """cpu_baseline leg: the oracle's x264_me_search_ref restatement on frame pair 0 (one core), which
+    also counts the pixel comparisons the reference issues and checks the GPU results"""
+    import cpu_checkers as cc
+    o = cc.oracle()
+    go = cc.oracle_geom(g.width, g.height)
+    host = slots[: 2 * g.slot_bytes].cpu().numpy()
+    out = {}
+    for name, (blocks, gpu_res) in blocks0.items():
+        nb = len(blocks)
+        want = np.zeros(nb, cc.ME_RESULT_DTYPE)
+        c0, c1 = (C.c_int64 * 4)(), (C.c_int64 * 4)()
+        prm = cc.MeParams(1, 5, 16, qp, 1)
+        o.xo_work_counters(c0, 1)
+        t0 = time.perf_counter()
+        o.xo_me_search_batch(C.byref(go), cc.ptr(host[g.slot_bytes:]), cc.ptr(host[: g.slot_bytes]), C.byref(prm), nb,
+                             blocks.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+        dt = time.perf_counter() - t0
+        o.xo_work_counters(c1, 0)
+        out[name] = {"sad_pix": int(c1[0]), "satd_pix": int(c1[1]), "cpu_s": dt,
+                     "bit_exact": bool(np.array_equal(gpu_res.view(cc.ME_RESULT_DTYPE), want))}
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -352,6 +414,12 @@ def main():
     torch.cuda.synchronize()
     one_ms = ev0.elapsed_time(ev1) / args.steps
 
+    # ---- secondary: full-resolution motion search (configs[2]), rank 0 only
+    me_ms = me_blocks0 = me_slots = None
+    if rank == 0 and not args.no_me:
+        me_pairs = min(8, clip_len - 1)
+        me_ms, me_blocks0, me_slots = me_search_measure(pkg, ctx, torch, g, luma_dev, d_mvs[: clip_len].cpu().numpy(), me_pairs)
+
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -416,6 +484,22 @@ def main():
                                               f"({frames} frames in {dt:.2f} s)"}
         else:
             line["cpu_baseline"] = None
+        if me_ms is not None:
+            tot_ms = sum(me_ms.values())
+            me = {"workload": f"{w}x{h} x264_me_search_ref + x264_me_refine_qpel, HEX, subme 5, range 16, QP 26, one block list "
+                              "per partition size tiling the frame (7 sizes), mvp from the lowres MVs",
+                  "frames_per_s_all_sizes": 1e3 / tot_ms, "ms_per_frame_by_size": me_ms,
+                  "launch": f"x264dsp_me_search_sized_frames_dev, {min(8, clip_len - 1)} frame pairs per launch"}
+            if not args.no_cpu_baseline and world == 1:
+                cnt = me_search_cpu_counts(pkg, g, me_slots, me_blocks0)
+                sad = sum(c["sad_pix"] for c in cnt.values())
+                satd = sum(c["satd_pix"] for c in cnt.values())
+                me.update({"sad_gpix_per_s": sad / (tot_ms / 1e3) / 1e9, "satd_gpix_per_s": satd / (tot_ms / 1e3) / 1e9,
+                           "sad_pix_per_frame": sad, "satd_pix_per_frame": satd,
+                           "counted_by": "the CPU oracle's instrumented run of the same block lists (frame pair 0)",
+                           "bit_exact_vs_oracle": all(c["bit_exact"] for c in cnt.values()),
+                           "cpu_port_1core_frames_per_s": 1.0 / sum(c["cpu_s"] for c in cnt.values())})
+            line["me_search"] = me
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -26,28 +26,6 @@ SIZES = [(0, 16, 16, "16x16"), (1, 16, 8, "16x8"), (2, 8, 16, "8x16"), (3, 8, 8,
          (5, 4, 8, "4x8"), (6, 4, 4, "4x4")]
 
 
-def me_blocks(cc, g, size, bw, bh, mb_mv):
-    """one block per bw x bh tile of the frame; mvp = 2 x lowres MV of the co-located macroblock"""
-    xs, ys = np.meshgrid(np.arange(0, g.luma_w, bw), np.arange(0, g.luma_h, bh))
-    n = xs.size
-    blocks = np.zeros(n, cc.ME_BLOCK_DTYPE)
-    blocks["i_pixel"] = size
-    blocks["bx"] = xs.ravel()
-    blocks["by"] = ys.ravel()
-    mbx, mby = blocks["bx"] // 16, blocks["by"] // 16
-    fmv = 512 << 2
-    for k, (mb, nmb) in enumerate(((mbx, g.mb_w), (mby, g.mb_h))):
-        smin = np.clip((-(mb << 4) - 24) << 2, -fmv, fmv - 1)
-        smax = np.clip((((nmb - mb - 1) << 4) + 24) << 2, -fmv, fmv - 1)
-        blocks["mv_min_spel"][:, k], blocks["mv_max_spel"][:, k] = smin, smax
-        blocks["mv_min_fpel"][:, k], blocks["mv_max_fpel"][:, k] = (smin >> 2) + 6, (smax >> 2) - 6
-    blocks["mvp"] = mb_mv[mby * g.mb_w + mbx] * 2
-    blocks["i_mvc"] = 2
-    blocks["mvc"][:, 0] = blocks["mvp"]
-    blocks["mvc"][:, 1] = 0
-    return blocks
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--width", type=int, default=1920)
@@ -139,7 +117,7 @@ def main():
     for size, bw, bh, name in SIZES:
         if not want("me" + name) and not (size == 0 and (want("residual") or want("deblock"))):
             continue
-        blocks = [me_blocks(cc, g, size, bw, bh, la_mv[p + 1]) for p in range(P)]
+        blocks = [pkg.tiling_blocks(g, size, la_mv[p + 1]) for p in range(P)]
         nb = len(blocks[0])
         d_blocks = [torch.from_numpy(bk.view(np.uint8)).cuda() for bk in blocks]
         d_res = [torch.zeros(nb * cc.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda") for _ in range(P)]

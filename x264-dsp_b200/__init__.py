@@ -115,6 +115,30 @@ def synth_frame(width, height, n, cut_frame=-1, luma_only=False):
     return buf
 
 
+def tiling_blocks(g, i_pixel, mb_mv):
+    """x264dsp_me_block_t list of one block per bw x bh tile of the frame:
+    mvp = 2 x the lowres MV of the co-located macroblock (common/mvpred.c:172-184), mvc = {mvp, 0},
+    MV limits as encoder/analyse.c:378-393 sets them (fpel border 6, mv_range 512)"""
+    bw, bh = BLOCK_W[i_pixel], BLOCK_H[i_pixel]
+    xs, ys = np.meshgrid(np.arange(0, g.luma_w, bw), np.arange(0, g.luma_h, bh))
+    blocks = np.zeros(xs.size, ME_BLOCK_DTYPE)
+    blocks["i_pixel"] = i_pixel
+    blocks["bx"] = xs.ravel()
+    blocks["by"] = ys.ravel()
+    mbx, mby = blocks["bx"] // 16, blocks["by"] // 16
+    fmv = 512 << 2
+    for k, (mb, nmb) in enumerate(((mbx, g.mb_w), (mby, g.mb_h))):
+        smin = np.clip((-(mb << 4) - 24) << 2, -fmv, fmv - 1)
+        smax = np.clip((((nmb - mb - 1) << 4) + 24) << 2, -fmv, fmv - 1)
+        blocks["mv_min_spel"][:, k], blocks["mv_max_spel"][:, k] = smin, smax
+        blocks["mv_min_fpel"][:, k], blocks["mv_max_fpel"][:, k] = (smin >> 2) + 6, (smax >> 2) - 6
+    blocks["mvp"] = mb_mv[mby * g.mb_w + mbx] * 2
+    blocks["i_mvc"] = 2
+    blocks["mvc"][:, 0] = blocks["mvp"]
+    blocks["mvc"][:, 1] = 0
+    return blocks
+
+
 def frame_range(n_frames, rank, world):
     """(first, count, need_prev): the frames rank `rank` of `world` owns (x264dsp_frame_range)"""
     first, count, prev = C.c_int(), C.c_int(), C.c_int()
