@@ -237,74 +237,115 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots )
 }
 
 // ---------------------------------------------------------------------------------------------
-// Half-pel planes.  Tile = 64 x 16 output samples per CTA of 256 threads:
-//   1. stage the (64+8) x (16+5) source window in shared memory,
-//   2. vertical six-tap -> 16-bit intermediate for 69 columns x 16 rows (shared memory),
-//   3. every thread emits 4 samples of H, V and HV on one row.
-// Computed region: rows [-8, luma_h+8), columns [0, luma_w+8) -- the rest of the padded plane is
-// filled by xd_filtered_border_kernel from these values (the reference overwrites columns < 0).
-#define HP_TW 64
-#define HP_TH 16
-#define HP_SW ( HP_TW + 8 )      // staged source columns: x0-4 .. x0+67
-#define HP_SH ( HP_TH + 5 )      // staged source rows:    y0-2 .. y0+18
+// Half-pel planes (hpel_filter, mc.c:144-167).  Computed region: rows [-8, luma_h+8), columns
+// [0, luma_w+8) -- the rest of the padded plane is filled by xd_filtered_border_kernel from these
+// values (the reference overwrites columns < 0).
+//
+// Mapping: a warp owns a strip of 30 output words (120 pixels) and walks HP_ROWS rows downwards; lane l
+// holds word column 30*strip + l - 1, lanes 0 and 31 are halo.  Each thread keeps the six source rows
+// of its four pixels in registers, unpacked to 16-bit pairs (p0,p2) / (p1,p3), so one new 4-byte load
+// per row feeds all three planes:
+//   V   six-tap down the window, two pixels per instruction (the sums fit 16 bits once biased by 2^15)
+//   H   six-tap along the row; the neighbours' pixels come from the adjacent lanes by shuffle
+//   HV  six-tap along the row over the UNCLIPPED 16-bit V values (the reference's int16 buf), 32-bit,
+//       neighbours again by shuffle
+// Biasing: every packed intermediate carries +32768 per half; (t+16)>>5 becomes ((u+16)>>5) - 1024 and
+// (t+512)>>10 of the 32-weight HV sum becomes ((u+512)>>10) - 1024, both exact.
+#define HP_ROWS 48
+#define HP_STRIP 30
 
-__device__ __forceinline__ int xd_tap6( int a, int b, int c, int d, int e, int f )
+// (a+f) - 5 (b+e) + 20 (c+d) + 32768 in both halves; inputs are 0..255 per half (or sums thereof)
+__device__ __forceinline__ uint32_t xd_hp_tap6_packed( uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f )
 {
-    return a + f - 5 * ( b + e ) + 20 * ( c + d );
+    const uint32_t pos = ( c + d ) * 20u + ( a + f );
+    return pos + 0x80008000u - ( b + e ) * 5u;
 }
 
-__global__ void __launch_bounds__( 256 )
+// clip( (t+16) >> 5 ) of both halves of a biased word -> values 0..255 in the low byte of each half
+__device__ __forceinline__ uint32_t xd_hp_round5_packed( uint32_t u )
+{
+    const uint32_t t = ( ( u + 0x00100010u ) >> 5 ) & 0x07FF07FFu;          // (t+16)>>5 + 1024
+    return __vminu2( __vmaxu2( t, 0x04000400u ), 0x04FF04FFu ) - 0x04000400u;
+}
+
+__global__ void __launch_bounds__( 128 )
 xd_hpel_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots )
 {
-    __shared__ __align__( 16 ) uint8_t s_src[HP_SH][HP_SW];
-    __shared__ __align__( 16 ) int16_t s_mid[HP_TH][HP_SW];
-
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
-    const uint8_t *pn = slot + g.luma_origin;
     const int ls = g.luma_stride;
-    const int x0 = blockIdx.x * HP_TW;
-    const int y0 = blockIdx.y * HP_TH - 8;
-    const int tid = threadIdx.x;
-
-    // 1. source window, 4 bytes per access (x0-4 is 4-byte aligned)
-    for( int i = tid; i < HP_SH * ( HP_SW / 4 ); i += 256 )
-    {
-        const int r = i / ( HP_SW / 4 ), c = i % ( HP_SW / 4 );
-        *(uint32_t *)&s_src[r][4 * c] = *(const uint32_t *)( pn + (int64_t)( y0 - 2 + r ) * ls + x0 - 4 + 4 * c );
-    }
-    __syncthreads();
-
-    // 2. vertical filter for staged columns 2..70 (x0-2 .. x0+66)
-    for( int i = tid; i < HP_TH * HP_SW; i += 256 )
-    {
-        const int r = i / HP_SW, c = i % HP_SW;
-        s_mid[r][c] = (int16_t)xd_tap6( s_src[r][c], s_src[r + 1][c], s_src[r + 2][c],
-                                       s_src[r + 3][c], s_src[r + 4][c], s_src[r + 5][c] );
-    }
-    __syncthreads();
-
-    // 3. outputs: thread -> row tid/16, columns 4*(tid%16) .. +3
-    const int r = tid >> 4, cx = ( tid & 15 ) * 4;
-    const int y = y0 + r, x = x0 + cx;
-    if( y >= g.luma_h + 8 || x >= g.luma_w + 8 )
+    const int wc = blockIdx.x * HP_STRIP + lane - 1;            // word column of this lane
+    const int n_words = ( g.luma_w + 8 ) >> 2;                   // output words per row
+    const int y0 = ( blockIdx.y * 4 + warp ) * HP_ROWS - 8;      // first output row of this warp
+    const int y_end = g.luma_h + 8;
+    if( y0 >= y_end )
         return;
-    uint32_t oh = 0, ov = 0, oc = 0;
+    // halo lanes beyond the padded row still read inside the allocation (pad is 32 >= 4 + 4)
+    const int wcl = min( wc, n_words );
+    const uint8_t *src = slot + g.luma_origin + 4 * wcl;
+    const bool writer = lane >= 1 && lane <= HP_STRIP && wc < n_words;
+    uint8_t *dh = slot + (size_t)g.luma_plane_size + g.luma_origin + 4 * wcl;
+    uint8_t *dv = dh + (size_t)g.luma_plane_size, *dc = dv + (size_t)g.luma_plane_size;
+
+    uint32_t E[6], O[6];                                         // rows y-2 .. y+3: (p0,p2), (p1,p3)
 #pragma unroll
-    for( int k = 0; k < 4; k++ )
+    for( int k = 0; k < 5; k++ )
     {
-        const int c = cx + k + 4;                    // staged column of output sample
-        const uint8_t *s = &s_src[r + 2][c];
-        const int16_t *m = &s_mid[r][c];
-        const int hv = xd_tap6( s[-2], s[-1], s[0], s[1], s[2], s[3] );
-        const int cv = xd_tap6( m[-2], m[-1], m[0], m[1], m[2], m[3] );
-        oh |= (uint32_t)xd_clip_u8( ( hv + 16 ) >> 5 ) << ( 8 * k );
-        ov |= (uint32_t)xd_clip_u8( ( m[0] + 16 ) >> 5 ) << ( 8 * k );
-        oc |= (uint32_t)xd_clip_u8( ( cv + 512 ) >> 10 ) << ( 8 * k );
+        const uint32_t w = *(const uint32_t *)( src + (int64_t)( y0 - 2 + k ) * ls );
+        E[k] = w & 0x00FF00FFu;
+        O[k] = __byte_perm( w, 0u, 0x4341 );
     }
-    const int64_t o = (int64_t)y * ls + x;
-    *(uint32_t *)( slot + (size_t)g.luma_plane_size + g.luma_origin + o ) = oh;
-    *(uint32_t *)( slot + 2 * (size_t)g.luma_plane_size + g.luma_origin + o ) = ov;
-    *(uint32_t *)( slot + 3 * (size_t)g.luma_plane_size + g.luma_origin + o ) = oc;
+    for( int yb = y0; yb < y0 + HP_ROWS; yb += 6 )
+    {
+#pragma unroll
+        for( int u = 0; u < 6; u++ )
+        {
+            const int y = yb + u;
+            if( y >= y_end )
+                break;                                           // warp-uniform
+            const int i0 = u % 6, i1 = ( u + 1 ) % 6, i2 = ( u + 2 ) % 6, i3 = ( u + 3 ) % 6, i4 = ( u + 4 ) % 6, i5 = ( u + 5 ) % 6;
+            {
+                const uint32_t w = *(const uint32_t *)( src + (int64_t)( y + 3 ) * ls );
+                E[i5] = w & 0x00FF00FFu;
+                O[i5] = __byte_perm( w, 0u, 0x4341 );
+            }
+            // ---- V: biased 16-bit intermediates of this lane's four columns
+            const uint32_t ue = xd_hp_tap6_packed( E[i0], E[i1], E[i2], E[i3], E[i4], E[i5] );   // (v0, v2)
+            const uint32_t uo = xd_hp_tap6_packed( O[i0], O[i1], O[i2], O[i3], O[i4], O[i5] );   // (v1, v3)
+            const uint32_t ov = xd_hp_round5_packed( ue ) | ( xd_hp_round5_packed( uo ) << 8 );
+
+            // ---- H: row y is window slot i2; neighbours' pairs by shuffle
+            const uint32_t eC = E[i2], oC = O[i2];
+            const uint32_t eP = __shfl_up_sync( 0xffffffffu, eC, 1 ), oP = __shfl_up_sync( 0xffffffffu, oC, 1 );
+            const uint32_t eN = __shfl_down_sync( 0xffffffffu, eC, 1 ), oN = __shfl_down_sync( 0xffffffffu, oC, 1 );
+            const uint32_t p2c0 = __byte_perm( eP, eC, 0x5432 ), p3c1 = __byte_perm( oP, oC, 0x5432 );
+            const uint32_t c2n0 = __byte_perm( eC, eN, 0x5432 ), c3n1 = __byte_perm( oC, oN, 0x5432 );
+            const uint32_t he = xd_hp_tap6_packed( p2c0, p3c1, eC, oC, c2n0, c3n1 );             // (h0, h2)
+            const uint32_t ho = xd_hp_tap6_packed( p3c1, eC, oC, c2n0, c3n1, eN );               // (h1, h3)
+            const uint32_t oh = xd_hp_round5_packed( he ) | ( xd_hp_round5_packed( ho ) << 8 );
+
+            // ---- HV: six-tap over the unclipped V values of columns -2 .. 6
+            const uint32_t ueP = __shfl_up_sync( 0xffffffffu, ue, 1 ), uoP = __shfl_up_sync( 0xffffffffu, uo, 1 );
+            const uint32_t ueN = __shfl_down_sync( 0xffffffffu, ue, 1 ), uoN = __shfl_down_sync( 0xffffffffu, uo, 1 );
+            const int vm2 = (int)( ueP >> 16 ), vm1 = (int)( uoP >> 16 );
+            const int v0 = (int)( ue & 0xFFFFu ), v1 = (int)( uo & 0xFFFFu ), v2 = (int)( ue >> 16 ), v3 = (int)( uo >> 16 );
+            const int v4 = (int)( ueN & 0xFFFFu ), v5 = (int)( uoN & 0xFFFFu ), v6 = (int)( ueN >> 16 );
+            const int kb = 512 - ( 1 << 20 );                   // rounding minus the bias of the 32 weights
+            const int c0 = xd_clip_u8( ( ( vm2 + v3 + kb ) + 20 * ( v0 + v1 ) - 5 * ( vm1 + v2 ) ) >> 10 );
+            const int c1 = xd_clip_u8( ( ( vm1 + v4 + kb ) + 20 * ( v1 + v2 ) - 5 * ( v0 + v3 ) ) >> 10 );
+            const int c2 = xd_clip_u8( ( ( v0 + v5 + kb ) + 20 * ( v2 + v3 ) - 5 * ( v1 + v4 ) ) >> 10 );
+            const int c3 = xd_clip_u8( ( ( v1 + v6 + kb ) + 20 * ( v3 + v4 ) - 5 * ( v2 + v5 ) ) >> 10 );
+            const uint32_t oc = (uint32_t)c0 | ( (uint32_t)c1 << 8 ) | ( (uint32_t)c2 << 16 ) | ( (uint32_t)c3 << 24 );
+
+            if( writer )
+            {
+                const int64_t o = (int64_t)y * ls;
+                *(uint32_t *)( dh + o ) = oh;
+                *(uint32_t *)( dv + o ) = ov;
+                *(uint32_t *)( dc + o ) = oc;
+            }
+        }
+    }
 }
 
 // Padding of the three filtered planes = the final state of x264_frame_expand_border_filtered
@@ -490,9 +531,10 @@ extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_
     if( !ctx || !g || !slots || n_frames <= 0 )
         return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
-    dim3 grid( ( g->luma_w + 8 + HP_TW - 1 ) / HP_TW, ( g->luma_h + 16 + HP_TH - 1 ) / HP_TH, n_frames );
+    const int n_words = ( g->luma_w + 8 ) >> 2, n_segs = ( g->luma_h + 16 + HP_ROWS - 1 ) / HP_ROWS;
+    dim3 grid( ( n_words + HP_STRIP - 1 ) / HP_STRIP, ( n_segs + 3 ) / 4, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_HPEL, s );
-    xd_hpel_kernel<<<grid, 256, 0, s>>>( *g, slots );
+    xd_hpel_kernel<<<grid, 128, 0, s>>>( *g, slots );
     xd_prof_end( ctx, XD_PROF_HPEL, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
