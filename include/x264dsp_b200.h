@@ -115,7 +115,7 @@ enum
 {
     X264DSP_PROF_LOAD = 0, X264DSP_PROF_LOWRES, X264DSP_PROF_LA_INTRA, X264DSP_PROF_LA_INTER, X264DSP_PROF_HPEL,
     X264DSP_PROF_BORDER, X264DSP_PROF_COST, X264DSP_PROF_ME, X264DSP_PROF_MC, X264DSP_PROF_RESIDUAL,
-    X264DSP_PROF_DEBLOCK, X264DSP_PROF_KINDS
+    X264DSP_PROF_DEBLOCK, X264DSP_PROF_LA_TILE, X264DSP_PROF_KINDS
 };
 int x264dsp_profile_enable( x264dsp_ctx_t *ctx, int on );
 int x264dsp_profile_read( x264dsp_ctx_t *ctx, int kind, double *total_ms, int *count );

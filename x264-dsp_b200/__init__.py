@@ -24,7 +24,7 @@ CMP_SAD, CMP_SSD, CMP_SATD = 0, 1, 2
 ME_DIA, ME_HEX = 0, 1
 LA_COST_INTER, LA_COST_INTRA, LA_INTRA_MBS, LA_SAD_EVALS, LA_SATD_EVALS, LA_SUMS = 0, 1, 2, 3, 4, 8
 (PROF_LOAD, PROF_LOWRES, PROF_LA_INTRA, PROF_LA_INTER, PROF_HPEL, PROF_BORDER, PROF_COST, PROF_ME, PROF_MC,
- PROF_RESIDUAL, PROF_DEBLOCK) = range(11)
+ PROF_RESIDUAL, PROF_DEBLOCK, PROF_LA_TILE) = range(12)
 RES_LEVELS_PER_MB = 16 * 16 + 2 * 4 + 2 * 4 * 16
 RES_NNZ_PER_MB = 16 + 8 + 3
 

@@ -8,7 +8,7 @@
 
 // kernel classes for x264dsp_profile_read
 enum { XD_PROF_LOAD = 0, XD_PROF_LOWRES, XD_PROF_LA_INTRA, XD_PROF_LA_INTER, XD_PROF_HPEL, XD_PROF_BORDER,
-       XD_PROF_COST, XD_PROF_ME, XD_PROF_MC, XD_PROF_RESIDUAL, XD_PROF_DEBLOCK, XD_PROF_KINDS };
+       XD_PROF_COST, XD_PROF_ME, XD_PROF_MC, XD_PROF_RESIDUAL, XD_PROF_DEBLOCK, XD_PROF_LA_TILE, XD_PROF_KINDS };
 #define XD_PROF_MAX 512
 #define XD_AUX_STREAMS 16
 
@@ -32,6 +32,8 @@ struct x264dsp_ctx
     int32_t *la_icost;             // [pairs][mb_count] intra cost per block
     int32_t *la_ticket;            // work-queue counter
     size_t la_sync_cap, la_icost_cap;
+    uint8_t *la_tiled;             // [pairs][4 planes] 8x8-tiled copies of the reference lowres planes (quad kernel)
+    size_t la_tiled_cap;
     uint32_t la_epoch;
     unsigned long long *la_timing; // phase-cycle counters of the inter kernel (debug aid, normally NULL)
     int la_kernel;                 // x264dsp_lookahead_select_kernel: 0 auto, 1 warp-per-row, 2 quad-row

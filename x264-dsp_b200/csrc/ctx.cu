@@ -256,6 +256,7 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     cudaFree( ctx->cost_mv_store );
     cudaFree( ctx->la_sync );
     cudaFree( ctx->la_icost );
+    cudaFree( ctx->la_tiled );
     cudaFree( ctx->la_ticket );
     cudaFree( ctx->stage_dev );
     cudaFree( ctx->clip_slots );

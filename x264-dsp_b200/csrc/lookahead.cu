@@ -43,6 +43,8 @@ struct xd_la_args
     uint32_t epoch;
     int me_range;
     int slack;                          // quad kernel: extra blocks a quad stays behind the one below
+    const uint8_t *tiled;               // quad kernel: [pair] tiled reference plane N
+    int tile_w, tile_h;                 // tiles per row / column of a padded lowres plane
     unsigned long long *timing;         // optional phase-cycle counters (x264dsp_debug_lookahead_timing)
 };
 
@@ -635,11 +637,19 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 // pixel.c:243-266), the vertical 4-point transform runs across lanes.
 #define LQ_FULL 0xffffffffu
 
+// The quad kernel reads the reference through an 8x8-TILED copy of the four padded lowres planes
+// (tile (tx,ty) = 64 contiguous bytes, tiles of a tile row back to back, built per launch by
+// xd_la_tile_kernel).  With lane = pixel row, the eight lanes of a block read eight different rows: in
+// the row-major plane that is eight cache lines per request and the L1 data pipe saturates (ncu: 91 %
+// of peak wavefronts, DRAM 4 %); tiled, the same rows sit in two or three lines.
 struct xd_lq_block
 {
-    const uint8_t *rowp;      // reference lowres plane N at this lane's row of the block origin; planes H,V,HV follow
-    int plane_size;           // all displacements from rowp are 32-bit byte offsets
-    int stride;
+    const uint8_t *tref;      // tiled planes N, H, V, HV of the reference frame
+    int tplane;               // bytes per tiled plane
+    int tw;                   // tiles per tile row
+    int X0, Y0;               // padded coordinates (x+32, y+32) of this lane's row of the block origin
+    const uint8_t *rowp;      // row-major plane N at this lane's row of the block origin; planes H,V,HV follow
+    int plane_size, stride;   // (sub-pel positions, a quarter of the fetches, read the row-major planes)
     uint2 fenc;               // this lane's source row
     uint32_t fw[4];           // the same row as fw[k] = p[k] | p[k+4] << 16
     int mvpx, mvpy;
@@ -659,17 +669,28 @@ __device__ __forceinline__ int xd_lq_bits( const xd_lq_block &B, int qx, int qy 
     return __ldg( B.cost_mv + ( qx - B.mvpx ) ) + __ldg( B.cost_mv + ( qy - B.mvpy ) );
 }
 
-// 8 consecutive pixels at an arbitrary byte address: three aligned words and two funnel shifts
-// (shf.r.wrap takes the shift modulo 32, so the byte offset needs no masking)
+// 8 consecutive pixels at an arbitrary byte address of a row-major plane: two aligned 8-byte loads
 __device__ __forceinline__ uint2 xd_lq_load8( const uint8_t *p )
 {
-    // two aligned 8-byte loads always contain the 8 wanted bytes; fewer, wider requests matter here
-    // because every lane of a warp reads a different cache line (the L1 wavefront count is the limit)
     const uintptr_t a = (uintptr_t)p;
     const uint2 *w = (const uint2 *)( a & ~(uintptr_t)7 );
     const uint2 lo = __ldg( w ), hi = __ldg( w + 1 );
     const uint32_t sh = (uint32_t)a << 3;
     const bool up = ( (uint32_t)a & 4u ) != 0;
+    const uint32_t w0 = up ? lo.y : lo.x, w1 = up ? hi.x : lo.y, w2 = up ? hi.y : hi.x;
+    return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+}
+
+// 8 pixels at padded coordinates (X,Y) of the tiled plane at byte offset poff: the row chunk of the
+// tile holding X and of its right-hand neighbour (two aligned 8-byte loads, 64 bytes apart), then a
+// funnel shift by the position inside the chunk (shf.r.wrap takes the shift modulo 32)
+__device__ __forceinline__ uint2 xd_lq_tile8( const xd_lq_block &B, int poff, int X, int Y )
+{
+    const int off = poff + ( ( ( Y >> 3 ) * B.tw + ( X >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 );
+    const uint2 *w = (const uint2 *)( B.tref + off );
+    const uint2 lo = __ldg( w ), hi = __ldg( w + 8 );
+    const uint32_t sh = (uint32_t)X << 3;
+    const bool up = ( X & 4 ) != 0;
     const uint32_t w0 = up ? lo.y : lo.x, w1 = up ? hi.x : lo.y, w2 = up ? hi.y : hi.x;
     return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
 }
@@ -693,6 +714,8 @@ __device__ __forceinline__ uint32_t xd_lq_pack( uint32_t lo, uint32_t hi )
 __device__ __forceinline__ uint2 xd_lq_fetch( const xd_lq_block &B, int qx, int qy )
 {
     const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
+    if( !phase )
+        return xd_lq_tile8( B, 0, B.X0 + ( qx >> 2 ), B.Y0 + ( qy >> 2 ) );
     const int off = ( qy >> 2 ) * B.stride + ( qx >> 2 );
     uint2 a = xd_lq_load8( B.rowp + ( off + xd_qpel_plane_a( phase ) * B.plane_size + ( fy == 3 ? B.stride : 0 ) ) );
     if( phase & 5 )
@@ -704,10 +727,10 @@ __device__ __forceinline__ uint2 xd_lq_fetch( const xd_lq_block &B, int qx, int 
     return a;
 }
 
-// full-pel position given as a byte offset from the block origin: plane N only
-__device__ __forceinline__ uint32_t xd_lq_sad_off( const xd_lq_block &B, int off )
+// full-pel displacement (mx,my): plane N only
+__device__ __forceinline__ uint32_t xd_lq_sad_fpel( const xd_lq_block &B, int mx, int my )
 {
-    return xd_lq_sad8( xd_lq_load8( B.rowp + off ), B.fenc, 0u );
+    return xd_lq_sad8( xd_lq_tile8( B, 0, B.X0 + mx, B.Y0 + my ), B.fenc, 0u );
 }
 
 __device__ __forceinline__ uint32_t xd_lq_sad_qpel( const xd_lq_block &B, int qx, int qy )
@@ -761,6 +784,30 @@ __device__ __forceinline__ int xd_lq_satd( const xd_lq_block &B, int qx, int qy,
     return (int)( half + __shfl_xor_sync( LQ_FULL, half, 4 ) );
 }
 
+// 8x8-tiled copy of the padded lowres plane N of every reference frame of the launch (the full-pel
+// search, three quarters of all fetches, reads only that plane).  Thread = one 16-byte row chunk, i.e.
+// one row of two neighbouring tiles; eight consecutive threads fill the tile pair (128 contiguous
+// bytes out), a warp covers four pairs (64 contiguous bytes per source row in).
+__global__ void __launch_bounds__( 256 )
+xd_la_tile_kernel( xd_la_args A, const int32_t *inter_pairs, uint8_t *tiled )
+{
+    const x264dsp_geom_t &g = A.g;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tp = t >> 3, row = t & 7;                     // tile pair, row inside the tiles
+    const int pairs_per_row = ( A.tile_w + 1 ) >> 1;        // tile_w = mb_w + 8 may be odd: the last pair is half
+    if( tp >= pairs_per_row * A.tile_h )
+        return;
+    const int pair = inter_pairs[blockIdx.y];
+    const int ty = tp / pairs_per_row, tx = ( tp - ty * pairs_per_row ) * 2;
+    const uint8_t *src = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin
+                       + (int64_t)( ty * 8 + row - 32 ) * g.lowres_stride + tx * 8 - 32;
+    uint8_t *dst = tiled + (size_t)pair * ( (size_t)A.tile_w * A.tile_h * 64 ) + ( (size_t)ty * A.tile_w + tx ) * 64 + row * 8;
+    const uint4 v = __ldg( (const uint4 *)src );
+    *(uint2 *)dst = make_uint2( v.x, v.y );
+    if( tx + 1 < A.tile_w )
+        *(uint2 *)( dst + 64 ) = make_uint2( v.z, v.w );
+}
+
 __global__ void __launch_bounds__( LA_WARPS * 32 )
 xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 {
@@ -800,10 +847,14 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         const int sminy = ( miny - 8 ) << 2, smaxy = ( maxy + 8 ) << 2;
 
         xd_lq_block B;
+        B.tw = A.tile_w;
+        B.tplane = A.tile_w * A.tile_h * 64;
+        B.tref = A.tiled + (size_t)pair * B.tplane;
+        B.rowp = ref;
         B.plane_size = g.lowres_plane_size;
         B.stride = ls;
+        B.X0 = B.Y0 = 32;
         B.cost_mv = A.cost_mv;
-        B.rowp = ref;
         B.mvpx = B.mvpy = 0;
         B.fenc = make_uint2( 0u, 0u );
         B.fw[0] = B.fw[1] = B.fw[2] = B.fw[3] = 0u;
@@ -865,6 +916,8 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             {
                 const size_t pel = ( (size_t)by * ls + bx ) * 8;
                 B.rowp = ref + pel + r * ls;
+                B.X0 = 8 * bx + 32;
+                B.Y0 = 8 * by + r + 32;
                 B.fenc = nx_fenc;
                 ic = nx_ic;
                 if( bx > 1 )
@@ -932,7 +985,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 {
                     uint32_t s = 0;
                     if( cok[k] )
-                        s = xd_lq_sad_off( B, ccy[k] * ls + ccx[k] );
+                        s = xd_lq_sad_fpel( B, ccx[k], ccy[k] );
                     w[k >> 1] += s << ( 16 * ( k & 1 ) );
                 }
                 // lane r adds candidate r's mv bits, or the "does not compete" marker
@@ -982,9 +1035,8 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     uint32_t w0 = 0, w1 = 0;
                     if( dia )
                     {
-                        const int off = bmy * ls + bmx;
-                        w0 = xd_lq_pack( xd_lq_sad_off( B, off - ls ), xd_lq_sad_off( B, off + ls ) );
-                        w1 = xd_lq_pack( xd_lq_sad_off( B, off - 1 ), xd_lq_sad_off( B, off + 1 ) );
+                        w0 = xd_lq_pack( xd_lq_sad_fpel( B, bmx, bmy - 1 ), xd_lq_sad_fpel( B, bmx, bmy + 1 ) );
+                        w1 = xd_lq_pack( xd_lq_sad_fpel( B, bmx - 1, bmy ), xd_lq_sad_fpel( B, bmx + 1, bmy ) );
                         if( r < 4 )
                         {
                             const int dx = r == 2 ? -1 : r == 3 ? 1 : 0, dy = r == 0 ? -1 : r == 1 ? 1 : 0;
@@ -1150,6 +1202,16 @@ static int xd_la_prepare( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, int n_pai
         if( rc )
             return rc;
     }
+    {
+        const size_t tiled = (size_t)n_pairs * ( ( g->lowres_w + 64 ) / 8 ) * ( ( g->lowres_h + 64 ) / 8 ) * 64;
+        if( ctx->la_tiled_cap < tiled )
+        {
+            XD_CHECK( cudaDeviceSynchronize() );
+            int rc = xd_reserve_dev( (void **)&ctx->la_tiled, &ctx->la_tiled_cap, tiled );
+            if( rc )
+                return rc;
+        }
+    }
     if( ++ctx->la_epoch == 0 )
     {
         XD_CHECK( cudaMemsetAsync( ctx->la_sync, 0, ctx->la_sync_cap, s ) );
@@ -1198,6 +1260,9 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         A.slack = slack;
     }
     A.timing = ctx->la_timing;
+    A.tiled = ctx->la_tiled;
+    A.tile_w = ( g->lowres_w + 64 ) / 8;
+    A.tile_h = ( g->lowres_h + 64 ) / 8;
 
     const int inner = ( g->mb_w - 2 ) * ( g->mb_h - 2 );
     dim3 igrid( ( inner + 127 ) / 128, count );
@@ -1246,6 +1311,14 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         const int cap = ctx->sm_count * per_sm[which];
         if( ctas > cap )
             ctas = cap;
+        if( which == 2 )
+        {
+            const int chunks = ( ( A.tile_w + 1 ) / 2 ) * A.tile_h * 8;
+            const int tslot = xd_prof_begin( ctx, XD_PROF_LA_TILE, s );
+            xd_la_tile_kernel<<<dim3( ( chunks + 255 ) / 256, n_inter ), 256, 0, s>>>( A, inter_list, ctx->la_tiled );
+            xd_prof_end( ctx, XD_PROF_LA_TILE, tslot, s );
+            ctx->launches++;
+        }
         pslot = xd_prof_begin( ctx, XD_PROF_LA_INTER, s );
         if( which == 1 )
             xd_la_inter_kernel<true><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
