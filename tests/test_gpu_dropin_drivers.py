@@ -1,0 +1,106 @@
+"""Driver-level drop-in proof: the UNMODIFIED reference encoder (oracle/_ref) encodes a clip with three
+of its hot-path drivers served by libx264dsp_b200.so --
+
+  x264_frame_init_lowres                        -> x264dsp_frame_init_lowres_dev
+  x264_frame_filter + _expand_border_filtered   -> x264dsp_frame_filter_dev
+  x264_slicetype_frame_cost (its per-frame cache, filled before x264_slicetype_decide runs)
+                                                -> x264dsp_lookahead_frame_cost_dev
+
+through the doors of oracle/ref_shim/hooks.c (the glue INTEGRATION.md describes), and must emit the
+byte-identical bitstream.  Every plane the main encode searches in (half-pel planes of every
+reconstructed frame), every lowres MV used as an MV candidate and every frame cost that drives scenecut
+and rate control then comes from the CUDA path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cpu_checkers as cc
+from cpu_checkers import ptr
+
+pytestmark = pytest.mark.gpu
+
+FRAME_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+COST_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
+@pytest.mark.parametrize("w,h,n,cut,me,subme", [(352, 288, 12, 7, 1, 5), (208, 160, 8, -1, 0, 2)])
+def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me, subme):
+    import torch
+    lib = cc.ref()
+    assert lib is not None, "oracle/_ref/libx264ref.so must travel to the GPU box (make -C oracle ref)"
+    lib.xref_frame_ptr.restype = C.c_void_p
+    lib.xref_frame_ptr.argtypes = [C.c_void_p, C.c_int]
+    g = pkg.geometry(w, h)
+    clip = np.concatenate([pkg.synth_frame(w, h, i, cut_frame=cut) for i in range(n)])
+    lps, wps = g.luma_plane_size, g.lowres_plane_size
+    slots = torch.zeros(2 * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    stage = np.zeros(2 * g.slot_bytes, np.uint8)
+
+    def host_view(addr, nbytes):
+        return np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def upload(slot_index, offset, addr, nbytes):
+        stage[:nbytes] = host_view(addr, nbytes)
+        slots[slot_index * g.slot_bytes + offset: slot_index * g.slot_bytes + offset + nbytes].copy_(
+            torch.from_numpy(stage[:nbytes]))
+
+    def download(slot_index, offset, addr, nbytes):
+        host_view(addr, nbytes)[:] = slots[slot_index * g.slot_bytes + offset:
+                                           slot_index * g.slot_bytes + offset + nbytes].cpu().numpy()
+
+    @FRAME_CB
+    def lowres_cb(hv, frame):
+        # the source frame's padded luma plane in, four padded lowres planes (and the source plane with its
+        # duplicated last column / row, mc.c:412-415) out
+        upload(0, 0, lib.xref_frame_ptr(frame, 10), lps)
+        ctx.frame_init_lowres(g, slots, 1)
+        ctx.sync()
+        download(0, 0, lib.xref_frame_ptr(frame, 10), lps)
+        download(0, g.slot_lowres_off, lib.xref_frame_ptr(frame, 12), 4 * wps)
+
+    @FRAME_CB
+    def filter_cb(hv, frame):
+        # the reconstructed, deblocked, border-expanded plane N in; planes H, V, HV with their borders out
+        upload(0, 0, lib.xref_frame_ptr(frame, 10), lps)
+        ctx.frame_filter(g, slots, 1)
+        ctx.sync()
+        download(0, lps, lib.xref_frame_ptr(frame, 10) + lps, 3 * lps)
+
+    @COST_CB
+    def cost_cb(hv, p0, b, want_intra, mvs, costs, sums):
+        upload(0, g.slot_lowres_off, lib.xref_frame_ptr(p0, 12), 4 * wps)
+        upload(1, g.slot_lowres_off, lib.xref_frame_ptr(b, 12), 4 * wps)
+        d_mvs = torch.zeros((1, g.mb_count, 2), dtype=torch.int16, device="cuda")
+        d_costs = torch.zeros((1, g.mb_count), dtype=torch.int32, device="cuda")
+        d_sums = torch.zeros((1, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.lookahead_frame_cost(g, slots, [1], [0], [want_intra], d_mvs, d_costs, d_sums)
+        ctx.sync()
+        host_view(mvs, g.mb_count * 4)[:] = d_mvs.cpu().numpy().view(np.uint8).ravel()
+        host_view(costs, g.mb_count * 4)[:] = d_costs.cpu().numpy().view(np.uint8).ravel()
+        host_view(sums, 32)[:] = d_sums.cpu().numpy().view(np.uint8).ravel()[:32]
+
+    outs, calls = [], (C.c_int * 3)()
+    for use_gpu in (False, True):
+        enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=26)
+        if use_gpu:
+            lib.xref_set_driver_hooks(lowres_cb, filter_cb, cost_cb)
+        else:
+            lib.xref_set_driver_hooks(None, None, None)
+        out = np.zeros(1 << 20, np.uint8)
+        launches0 = ctx.launches
+        try:
+            size = lib.xref_encode_clip(enc.h, ptr(clip), n, ptr(out), out.size)
+        finally:
+            lib.xref_driver_hook_calls(calls)
+            lib.xref_set_driver_hooks(None, None, None)
+        assert size > 0, size
+        outs.append(out[:size].copy())
+        if use_gpu:
+            assert calls[0] == n, f"x264_frame_init_lowres hooked {calls[0]} times for {n} frames"
+            assert calls[1] >= n - 1, f"x264_frame_filter hooked {calls[1]} times"
+            assert calls[2] >= n - 2, f"lookahead cost hooked {calls[2]} times"
+            assert ctx.launches - launches0 >= 2 * n, "the encode must have gone through the CUDA kernels"
+    assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), \
+        f"bitstreams differ: {outs[0].size} vs {outs[1].size} bytes"
