@@ -3,6 +3,8 @@ of its hot-path drivers served by libx264dsp_b200.so --
 
   x264_frame_init_lowres                        -> x264dsp_frame_init_lowres_dev
   x264_frame_filter + _expand_border_filtered   -> x264dsp_frame_filter_dev
+  x264_frame_deblock_row + x264_frame_expand_border (second test: the whole in-loop filter)
+                                                -> x264dsp_deblock_frame_dev + x264dsp_frame_expand_border_dev
   x264_slicetype_frame_cost (its per-frame cache, filled before x264_slicetype_decide runs)
                                                 -> x264dsp_lookahead_frame_cost_dev
 
@@ -22,10 +24,13 @@ pytestmark = pytest.mark.gpu
 
 FRAME_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 COST_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+FDEC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.c_int, C.c_int, C.c_int)
 
 
-@pytest.mark.parametrize("w,h,n,cut,me,subme", [(352, 288, 12, 7, 1, 5), (208, 160, 8, -1, 0, 2)])
-def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me, subme):
+@pytest.mark.parametrize("w,h,n,cut,me,subme,inloop", [(352, 288, 12, 7, 1, 5, False), (208, 160, 8, -1, 0, 2, False),
+                                                       (352, 288, 12, 7, 1, 5, True), (208, 160, 8, 4, 1, 3, True)])
+def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me, subme, inloop):
     import torch
     lib = cc.ref()
     assert lib is not None, "oracle/_ref/libx264ref.so must travel to the GPU box (make -C oracle ref)"
@@ -81,11 +86,34 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         host_view(costs, g.mb_count * 4)[:] = d_costs.cpu().numpy().view(np.uint8).ravel()
         host_view(sums, 32)[:] = d_sums.cpu().numpy().view(np.uint8).ravel()[:32]
 
+    deblocked = [0]
+
+    @FDEC_CB
+    def fdec_cb(hv, frame, do_deblock, mb_type, partition, cbp, bs, qp, aoff, boff):
+        # the reconstructed frame in; deblocked planes with borders and the three half-pel planes out
+        cps = g.chroma_plane_size
+        upload(0, 0, lib.xref_frame_ptr(frame, 10), lps)
+        upload(0, g.slot_chroma_off, lib.xref_frame_ptr(frame, 11), cps)
+        if do_deblock:
+            nmb = g.mb_count
+            d = [torch.from_numpy(host_view(p_, nb).copy()).cuda() for p_, nb in
+                 ((mb_type, nmb), (partition, nmb), (cbp, 2 * nmb), (bs, 64 * nmb))]
+            torch.cuda.synchronize()
+            ctx.deblock_frame(g, slots, d[0], d[1], d[2], d[3], qp, aoff, boff)
+            deblocked[0] += 1
+        ctx.frame_expand_border(g, slots, 1)
+        ctx.frame_filter(g, slots, 1)
+        ctx.sync()
+        download(0, 0, lib.xref_frame_ptr(frame, 10), 4 * lps)
+        download(0, g.slot_chroma_off, lib.xref_frame_ptr(frame, 11), cps)
+
     outs, calls = [], (C.c_int * 3)()
     for use_gpu in (False, True):
         enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=26)
         if use_gpu:
             lib.xref_set_driver_hooks(lowres_cb, filter_cb, cost_cb)
+            if inloop:
+                lib.xref_set_fdec_hook(fdec_cb)
         else:
             lib.xref_set_driver_hooks(None, None, None)
         out = np.zeros(1 << 20, np.uint8)
@@ -95,6 +123,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         finally:
             lib.xref_driver_hook_calls(calls)
             lib.xref_set_driver_hooks(None, None, None)
+            lib.xref_set_fdec_hook(None)
         assert size > 0, size
         outs.append(out[:size].copy())
         if use_gpu:
@@ -102,5 +131,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             assert calls[1] >= n - 1, f"x264_frame_filter hooked {calls[1]} times"
             assert calls[2] >= n - 2, f"lookahead cost hooked {calls[2]} times"
             assert ctx.launches - launches0 >= 2 * n, "the encode must have gone through the CUDA kernels"
+            if inloop:
+                assert deblocked[0] >= n - 1, f"deblocking ran on the device for {deblocked[0]} of {n} frames"
     assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), \
         f"bitstreams differ: {outs[0].size} vs {outs[1].size} bytes"
