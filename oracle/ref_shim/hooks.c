@@ -10,6 +10,8 @@
  *   x264_frame_deblock_row              common/deblock.c:341 called from encoder/encoder.c:1370
  *   x264_frame_expand_border            common/frame.c:386   called from encoder/encoder.c:1376
  *
+ *   x264_me_search_ref                  encoder/me.c:129     called from encoder/analyse.c:820 ... (every partition)
+ *
  * and encoder/slicetype.c's x264_slicetype_decide is wrapped in wrap_slicetype.c.  With no hooks
  * installed every definition forwards to the original, so the library and the CLI behave exactly like
  * the reference (tests/test_golden.py::test_reference_cli_bitstream pins that).  With hooks installed
@@ -17,6 +19,8 @@
  * this is the glue a maintainer of the reference would add.
  */
 #include "common/common.h"
+#include "encoder/macroblock.h"
+#include "encoder/me.h"
 
 typedef void (*xref_frame_cb)( void *h, void *frame );
 typedef void (*xref_cost_cb)( void *h, void *p0, void *b, int want_intra, int16_t *mvs, int *costs, int *sums );
@@ -136,4 +140,97 @@ void x264_frame_expand_border_filtered( x264_t *h, x264_frame_t *frame, int mb_y
         xref_hook_filter( h, frame );
         xref_hook_calls[1]++;
     }
+}
+
+
+/* ------------------------------------------------------------------ motion search
+ * x264_me_search_ref for one partition of the main encode, served by x264dsp_me_search_batch_dev with a
+ * one-block list.  The block description is exactly the x264_me_t inputs plus the MV limits the analysis
+ * has put into h->mb (the layout of x264dsp_me_block_t / xref_me_in_t in harness.c). */
+typedef struct
+{
+    int32_t i_pixel;
+    int32_t bx, by;
+    int16_t mvp[2];
+    int32_t i_mvc;
+    int16_t mvc[16][2];
+    int32_t mv_min_fpel[2], mv_max_fpel[2];
+    int32_t mv_min_spel[2], mv_max_spel[2];
+} xref_hook_me_in_t;
+
+typedef struct
+{
+    int16_t mv[2];
+    int32_t cost;
+    int32_t cost_mv;
+} xref_hook_me_out_t;
+
+typedef int (*xref_me_cb)( void *h, void *fenc, void *fref, const xref_hook_me_in_t *in, int me_method, int subme,
+                           int me_range, int qp, xref_hook_me_out_t *out );
+xref_me_cb xref_hook_me = NULL;
+int xref_hook_me_calls = 0;
+
+void xref_set_me_hook( xref_me_cb cb )
+{
+    xref_hook_me = cb;
+    xref_hook_me_calls = 0;
+}
+int xref_me_hook_calls( void ) { return xref_hook_me_calls; }
+
+void xref_orig_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
+
+void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh )
+{
+    x264_frame_t *fref = h->fref[0][0];
+    xref_hook_me_in_t in;
+    xref_hook_me_out_t out;
+    int k, qp;
+    /* only the main encode's searches in the newest reference frame; the lowres lookahead (other planes,
+     * other stride) and multi-reference early termination keep the reference's own code */
+    if( !xref_hook_me || p_halfpel_thresh || !fref || m->i_ref != 0 || m->i_stride[0] != fref->i_stride[0]
+        || i_mvc > 16 || m->p_fref[0] < fref->filtered[0][0]
+        || m->p_fref[0] >= fref->filtered[0][0] + (intptr_t)fref->i_stride[0] * fref->i_lines[0] )
+    {
+        xref_orig_me_search_ref( h, m, mvc, i_mvc, p_halfpel_thresh );
+        return;
+    }
+    for( qp = 0; qp < 52 && h->cost_mv[qp] != m->p_cost_mv; qp++ )
+        ;
+    if( qp == 52 )
+    {
+        xref_orig_me_search_ref( h, m, mvc, i_mvc, p_halfpel_thresh );
+        return;
+    }
+    {
+        const intptr_t off = m->p_fref[0] - fref->filtered[0][0];
+        in.by = (int32_t)( off / fref->i_stride[0] );
+        in.bx = (int32_t)( off - (intptr_t)in.by * fref->i_stride[0] );
+    }
+    in.i_pixel = m->i_pixel;
+    in.mvp[0] = m->mvp[0];
+    in.mvp[1] = m->mvp[1];
+    in.i_mvc = i_mvc;
+    memset( in.mvc, 0, sizeof(in.mvc) );
+    for( k = 0; k < i_mvc; k++ )
+    {
+        in.mvc[k][0] = mvc[k][0];
+        in.mvc[k][1] = mvc[k][1];
+    }
+    for( k = 0; k < 2; k++ )
+    {
+        in.mv_min_fpel[k] = h->mb.mv_min_fpel[k];
+        in.mv_max_fpel[k] = h->mb.mv_max_fpel[k];
+        in.mv_min_spel[k] = h->mb.mv_min_spel[k];
+        in.mv_max_spel[k] = h->mb.mv_max_spel[k];
+    }
+    if( xref_hook_me( h, h->fenc, fref, &in, h->mb.i_me_method, h->mb.i_subpel_refine, h->param.analyse.i_me_range, qp, &out ) )
+    {
+        xref_orig_me_search_ref( h, m, mvc, i_mvc, p_halfpel_thresh );     /* the hook declined (frame not resident) */
+        return;
+    }
+    xref_hook_me_calls++;
+    m->mv[0] = out.mv[0];
+    m->mv[1] = out.mv[1];
+    m->cost = out.cost;
+    m->cost_mv = out.cost_mv;
 }

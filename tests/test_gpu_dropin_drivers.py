@@ -7,6 +7,8 @@ of its hot-path drivers served by libx264dsp_b200.so --
                                                 -> x264dsp_deblock_frame_dev + x264dsp_frame_expand_border_dev
   x264_slicetype_frame_cost (its per-frame cache, filled before x264_slicetype_decide runs)
                                                 -> x264dsp_lookahead_frame_cost_dev
+  x264_me_search_ref (every partition search of the main encode, last two cases)
+                                                -> x264dsp_me_search_batch_dev on frames kept resident on the device
 
 through the doors of oracle/ref_shim/hooks.c (the glue INTEGRATION.md describes), and must emit the
 byte-identical bitstream.  Every plane the main encode searches in (half-pel planes of every
@@ -26,11 +28,14 @@ FRAME_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 COST_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 FDEC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                       C.c_int, C.c_int, C.c_int)
+ME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
 
 
-@pytest.mark.parametrize("w,h,n,cut,me,subme,inloop", [(352, 288, 12, 7, 1, 5, False), (208, 160, 8, -1, 0, 2, False),
-                                                       (352, 288, 12, 7, 1, 5, True), (208, 160, 8, 4, 1, 3, True)])
-def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me, subme, inloop):
+@pytest.mark.parametrize("w,h,n,cut,me,subme,psub,inloop,mehook", [
+    (352, 288, 12, 7, 1, 5, 0, False, False), (208, 160, 8, -1, 0, 2, 0, False, False),
+    (352, 288, 12, 7, 1, 5, 0, True, False), (208, 160, 8, 4, 1, 3, 0, True, False),
+    (352, 288, 10, 6, 1, 5, 0, True, True), (208, 160, 8, 4, 0, 2, 1, True, True), (208, 160, 6, -1, 1, 4, 1, True, True)])
+def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me, subme, psub, inloop, mehook):
     import torch
     lib = cc.ref()
     assert lib is not None, "oracle/_ref/libx264ref.so must travel to the GPU box (make -C oracle ref)"
@@ -54,11 +59,21 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         host_view(addr, nbytes)[:] = slots[slot_index * g.slot_bytes + offset:
                                            slot_index * g.slot_bytes + offset + nbytes].cpu().numpy()
 
+    resident = {}                         # x264_frame_t* -> device slot of the frame (for the ME hook)
+
+    def keep_resident(frame):
+        if not mehook:
+            return
+        if frame not in resident and len(resident) >= 8:
+            resident.pop(next(iter(resident)))
+        resident[frame] = slots[: g.slot_bytes].clone()
+
     @FRAME_CB
     def lowres_cb(hv, frame):
         # the source frame's padded luma plane in, four padded lowres planes (and the source plane with its
         # duplicated last column / row, mc.c:412-415) out
         upload(0, 0, lib.xref_frame_ptr(frame, 10), lps)
+        keep_resident(frame)              # the source samples as the main encode's searches will see them
         ctx.frame_init_lowres(g, slots, 1)
         ctx.sync()
         download(0, 0, lib.xref_frame_ptr(frame, 10), lps)
@@ -106,14 +121,32 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         ctx.sync()
         download(0, 0, lib.xref_frame_ptr(frame, 10), 4 * lps)
         download(0, g.slot_chroma_off, lib.xref_frame_ptr(frame, 11), cps)
+        keep_resident(frame)              # this reconstructed frame is the next frame's reference
+
+    me_calls = [0]
+
+    @ME_CB
+    def me_cb(hv, fenc, fref, blk, me_method, subme_, me_range, qp, out):
+        if fenc not in resident or fref not in resident:
+            return 1                      # declined: the reference's own code runs
+        d_blk = torch.from_numpy(host_view(blk, cc.ME_BLOCK_DTYPE.itemsize).copy()).cuda()
+        d_res = torch.zeros(cc.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.me_search_batch(g, resident[fenc], resident[fref], pkg.MeParams(me_method, subme_, me_range, qp, 0), 1, d_blk, d_res)
+        ctx.sync()
+        host_view(out, cc.ME_RESULT_DTYPE.itemsize)[:] = d_res.cpu().numpy()
+        me_calls[0] += 1
+        return 0
 
     outs, calls = [], (C.c_int * 3)()
     for use_gpu in (False, True):
-        enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=26)
+        enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=26, psub16x16=psub)
         if use_gpu:
             lib.xref_set_driver_hooks(lowres_cb, filter_cb, cost_cb)
             if inloop:
                 lib.xref_set_fdec_hook(fdec_cb)
+            if mehook:
+                lib.xref_set_me_hook(me_cb)
         else:
             lib.xref_set_driver_hooks(None, None, None)
         out = np.zeros(1 << 20, np.uint8)
@@ -124,6 +157,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             lib.xref_driver_hook_calls(calls)
             lib.xref_set_driver_hooks(None, None, None)
             lib.xref_set_fdec_hook(None)
+            lib.xref_set_me_hook(None)
         assert size > 0, size
         outs.append(out[:size].copy())
         if use_gpu:
@@ -131,6 +165,8 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             assert calls[1] >= n - 1, f"x264_frame_filter hooked {calls[1]} times"
             assert calls[2] >= n - 2, f"lookahead cost hooked {calls[2]} times"
             assert ctx.launches - launches0 >= 2 * n, "the encode must have gone through the CUDA kernels"
+            if mehook:
+                assert me_calls[0] >= (n - 3) * g.mb_count // 2, f"only {me_calls[0]} searches went to the device"
             if inloop:
                 assert deblocked[0] >= n - 1, f"deblocking ran on the device for {deblocked[0]} of {n} frames"
     assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), \
