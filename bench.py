@@ -354,8 +354,7 @@ def main():
     torch.cuda.synchronize()
 
     def step_dev():
-        ctx.frame_load_luma(g, luma_dev, slots, n)
-        ctx.frame_init_lowres(g, slots, n)
+        ctx.frame_load_luma_lowres(g, luma_dev, slots, n)          # picture staging + x264_frame_init_lowres
         ctx.lookahead_frame_cost(g, slots, b, p0, wi, d_mvs, d_costs, d_sums)
 
     def sync_all():
@@ -401,8 +400,7 @@ def main():
     # ---- single clip latency (exactly the 8-frame configuration), device resident
     one = clip_len
     def step_one():
-        ctx.frame_load_luma(g, luma_dev, slots, one)
-        ctx.frame_init_lowres(g, slots, one)
+        ctx.frame_load_luma_lowres(g, luma_dev, slots, one)
         ctx.lookahead_frame_cost(g, slots, b[:one], p0[:one], wi[:one], d_mvs, d_costs, d_sums)
     for _ in range(3):
         step_one()

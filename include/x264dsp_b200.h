@@ -155,6 +155,10 @@ int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8
  * column/row INTO the source luma plane, builds the four half-resolution planes and pads them. */
 int x264dsp_frame_init_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
                                    int n_frames, void *stream );
+/* x264dsp_frame_load_luma_dev + x264dsp_frame_init_lowres_dev in one pass over the picture (same final
+ * slot contents: luma plane N incl. the duplicated column / row, four padded lowres planes) */
+int x264dsp_frame_load_luma_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
+                                        uint8_t *slots, int n_frames, void *stream );
 
 /* ------------------------------------------------------------------ block costs
  * x264_pixel_function_t::sad / ssd / satd  (common/pixel.c:44-102, 267-337) on n independent

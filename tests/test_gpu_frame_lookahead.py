@@ -177,6 +177,26 @@ def test_lookahead_matches_oracle(pkg, ctx, w, h, n, cut, kernel):
     ctx.lookahead_select_kernel(0)
 
 
+@pytest.mark.parametrize("w,h", [(352, 288), (200, 120), (1920, 1080), (66, 70)])
+def test_fused_staging_and_lowres_equals_the_two_calls(pkg, ctx, w, h):
+    """x264dsp_frame_load_luma_lowres_dev leaves the slot exactly as load_luma + init_lowres do (incl.
+    non-mod-16 sizes, where the staging has to replicate the last column / row)"""
+    torch = _torch()
+    n = 3
+    luma = np.stack([pkg.synth_frame(w, h, i, luma_only=True) for i in range(n)])
+    g = pkg.geometry(w, h)
+    d_luma = torch.from_numpy(luma).cuda()
+    a = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    b = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_luma(g, d_luma, a, n)
+    ctx.frame_init_lowres(g, a, n)
+    ctx.frame_load_luma_lowres(g, d_luma, b, n)
+    ctx.sync()
+    diff = torch.nonzero(a != b)
+    assert diff.numel() == 0, f"{diff.numel()} bytes differ, first at slot offset {int(diff[0]) % g.slot_bytes}"
+
+
 def test_lookahead_batch_of_clips_both_kernels(pkg, ctx):
     """a launch large enough for the automatic choice to take the quad-row kernel (>= 48 pairs): many
     short clips, both mappings and the automatic one must agree with the oracle and with each other"""

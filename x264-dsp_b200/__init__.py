@@ -252,6 +252,11 @@ class Context:
         check(lib().x264dsp_frame_load_luma_dev(self._h, C.byref(g), _dp(luma_dev), _dp(slots_dev),
                                                 int(n_frames), None), "x264dsp_frame_load_luma_dev")
 
+    def frame_load_luma_lowres(self, g, luma_dev, slots_dev, n_frames):
+        """frame_load_luma + frame_init_lowres fused (one pass over the picture)"""
+        check(lib().x264dsp_frame_load_luma_lowres_dev(self._h, C.byref(g), _dp(luma_dev), _dp(slots_dev),
+                                                       int(n_frames), None), "x264dsp_frame_load_luma_lowres_dev")
+
     def frame_expand_border(self, g, slots_dev, n_frames):
         check(lib().x264dsp_frame_expand_border_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),
               "x264dsp_frame_expand_border_dev")

@@ -189,50 +189,122 @@ __device__ __forceinline__ void xd_lowres_line( const uint4 r, uint32_t e, uint2
     oh = make_uint2( xd_avg4( od_lo, nx_lo ), xd_avg4( od_hi, nx_hi ) );
 }
 
+// 16 source bytes of luma row `row` starting at column x0 (a multiple of 16), plus the byte after them.
+// PLANE: from the slot's padded luma plane (reads clamped to the picture, see above).
+// RAW:   straight from the caller's width x height picture; the mod-16 padding (frame.c:435-448) and the
+//        duplicated column / row are the same clamp.
+template<bool RAW>
+__device__ __forceinline__ void xd_lowres_src( const uint8_t *base, int pitch, int w, int h, int row, int x0,
+                                               uint4 &v, uint32_t &e )
+{
+    const uint8_t *p = base + (size_t)min( row, h - 1 ) * pitch;
+    if( !RAW || ( x0 + 16 <= w && ( ( (uintptr_t)( p + x0 ) ) & 15 ) == 0 ) )
+        v = *(const uint4 *)( p + x0 );
+    else
+    {
+        uint32_t q[4];
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            uint32_t acc = 0;
+#pragma unroll
+            for( int b = 0; b < 4; b++ )
+                acc |= (uint32_t)p[min( x0 + 4 * k + b, w - 1 )] << ( 8 * b );
+            q[k] = acc;
+        }
+        v = make_uint4( q[0], q[1], q[2], q[3] );
+    }
+    e = p[min( x0 + 16, w - 1 )];
+}
+
+// one 8-sample chunk of the four lowres planes at row y (may be a padding row), with the 32-sample
+// side bands when the chunk is the first / last of its row (x264_frame_expand_border_lowres,
+// frame.c:415-421: replicate padding of 32 on every side)
+__device__ __forceinline__ void xd_lowres_store( uint8_t *plane0, size_t plane_size, int stride, int y, int t,
+                                                 bool first, bool last, const uint2 o[4] )
+{
+#pragma unroll
+    for( int k = 0; k < 4; k++ )
+    {
+        uint8_t *row = plane0 + k * plane_size + (int64_t)y * stride;
+        *(uint2 *)( row + 8 * t ) = o[k];
+        if( first )
+        {
+            const uint32_t v = ( o[k].x & 255u ) * 0x01010101u;
+#pragma unroll
+            for( int c = 1; c <= X264DSP_PADH / 8; c++ )
+                *(uint2 *)( row - 8 * c ) = make_uint2( v, v );
+        }
+        if( last )
+        {
+            const uint32_t v = ( o[k].y >> 24 ) * 0x01010101u;
+#pragma unroll
+            for( int c = 1; c <= X264DSP_PADH / 8; c++ )
+                *(uint2 *)( row + 8 * ( t + c ) ) = make_uint2( v, v );
+        }
+    }
+}
+
+// RAW = false: x264_frame_init_lowres on a slot whose luma plane is loaded (planes + their padding).
+// RAW = true : picture staging fused in -- the thread also writes the two luma rows it has read into
+//              the slot's plane N, which saves re-reading 2 MB per 1080p frame.
+template<bool RAW>
 __global__ void __launch_bounds__( 128 )
-xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots )
+xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *__restrict__ raw )
 {
     uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
-    uint8_t *src = slot + g.luma_origin;
+    uint8_t *plane = slot + g.luma_origin;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if( t >= ( g.lowres_w >> 3 ) )
+    const int chunks = g.lowres_w >> 3;
+    if( t >= chunks )
         return;
     const int ls = g.luma_stride;
-    const int r0 = 2 * y, r1 = 2 * y + 1, r2 = min( 2 * y + 2, g.luma_h - 1 );
-    const int xe = min( 16 * t + 16, g.luma_w - 1 );
-    const uint4 a = *(const uint4 *)( src + (size_t)r0 * ls + 16 * t );
-    const uint4 b = *(const uint4 *)( src + (size_t)r1 * ls + 16 * t );
-    const uint4 c = *(const uint4 *)( src + (size_t)r2 * ls + 16 * t );
-    const uint32_t ea = src[(size_t)r0 * ls + xe], eb = src[(size_t)r1 * ls + xe], ec = src[(size_t)r2 * ls + xe];
+    const uint8_t *src = RAW ? raw + blockIdx.z * (size_t)g.width * g.height : plane;
+    const int pitch = RAW ? g.width : ls, sw = RAW ? g.width : g.luma_w, sh = RAW ? g.height : g.luma_h;
+    const int r0 = 2 * y, r1 = 2 * y + 1, r2 = 2 * y + 2;
+    uint4 a, b, c;
+    uint32_t ea, eb, ec;
+    xd_lowres_src<RAW>( src, pitch, sw, sh, r0, 16 * t, a, ea );
+    xd_lowres_src<RAW>( src, pitch, sw, sh, r1, 16 * t, b, eb );
+    xd_lowres_src<RAW>( src, pitch, sw, sh, r2, 16 * t, c, ec );
 
     const uint4 ab = make_uint4( xd_avg4( a.x, b.x ), xd_avg4( a.y, b.y ), xd_avg4( a.z, b.z ), xd_avg4( a.w, b.w ) );
     const uint4 bc = make_uint4( xd_avg4( b.x, c.x ), xd_avg4( b.y, c.y ), xd_avg4( b.z, c.z ), xd_avg4( b.w, c.w ) );
     const uint32_t eab = ( ea + eb + 1 ) >> 1, ebc = ( eb + ec + 1 ) >> 1;
 
-    uint2 o0, oh, ov, oc;
-    xd_lowres_line( ab, eab, o0, oh );
-    xd_lowres_line( bc, ebc, ov, oc );
+    uint2 o[4];
+    xd_lowres_line( ab, eab, o[0], o[1] );
+    xd_lowres_line( bc, ebc, o[2], o[3] );
 
-    uint8_t *dst = slot + g.slot_lowres_off + g.lowres_origin + (size_t)y * g.lowres_stride + 8 * t;
-    *(uint2 *)( dst ) = o0;
-    *(uint2 *)( dst + (size_t)g.lowres_plane_size ) = oh;
-    *(uint2 *)( dst + 2 * (size_t)g.lowres_plane_size ) = ov;
-    *(uint2 *)( dst + 3 * (size_t)g.lowres_plane_size ) = oc;
+    uint8_t *lw = slot + g.slot_lowres_off + g.lowres_origin;
+    const bool first = t == 0, last = t == chunks - 1;
+    xd_lowres_store( lw, (size_t)g.lowres_plane_size, g.lowres_stride, y, t, first, last, o );
+    if( y == 0 )
+        for( int r = 1; r <= X264DSP_PADV; r++ )
+            xd_lowres_store( lw, (size_t)g.lowres_plane_size, g.lowres_stride, -r, t, first, last, o );
+    if( y == g.lowres_h - 1 )
+        for( int r = 1; r <= X264DSP_PADV; r++ )
+            xd_lowres_store( lw, (size_t)g.lowres_plane_size, g.lowres_stride, y + r, t, first, last, o );
 
+    if( RAW )
+    {
+        *(uint4 *)( plane + (size_t)r0 * ls + 16 * t ) = a;
+        *(uint4 *)( plane + (size_t)r1 * ls + 16 * t ) = b;
+    }
     // side effect of x264_frame_init_lowres on the source plane: column luma_w of every row and
     // row luma_h (luma_w + 1 bytes) duplicate their neighbours
-    if( 16 * t + 16 == g.luma_w )
+    if( last )
     {
-        src[(size_t)r0 * ls + g.luma_w] = (uint8_t)ea;
-        src[(size_t)r1 * ls + g.luma_w] = (uint8_t)eb;
+        plane[(size_t)r0 * ls + g.luma_w] = (uint8_t)ea;
+        plane[(size_t)r1 * ls + g.luma_w] = (uint8_t)eb;
     }
     if( y == g.lowres_h - 1 )
     {
         // b is the last picture row here (r1 == luma_h - 1)
-        *(uint4 *)( src + (size_t)g.luma_h * ls + 16 * t ) = b;
-        if( 16 * t + 16 == g.luma_w )
-            src[(size_t)g.luma_h * ls + g.luma_w] = (uint8_t)eb;
+        *(uint4 *)( plane + (size_t)g.luma_h * ls + 16 * t ) = b;
+        if( last )
+            plane[(size_t)g.luma_h * ls + g.luma_w] = (uint8_t)eb;
     }
 }
 
@@ -508,21 +580,42 @@ extern "C" int x264dsp_frame_expand_border_dev( x264dsp_ctx_t *ctx, const x264ds
     return xd_launch_border( ctx, chroma, slots, g->slot_bytes, n_frames, 1, 0, s );
 }
 
+static int xd_launch_lowres( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots, const uint8_t *raw,
+                             int n_frames, cudaStream_t s )
+{
+    dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h, n_frames );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_LOWRES, s );
+    if( raw )
+        xd_lowres_kernel<true><<<grid, 128, 0, s>>>( *g, slots, raw );
+    else
+        xd_lowres_kernel<false><<<grid, 128, 0, s>>>( *g, slots, NULL );
+    xd_prof_end( ctx, XD_PROF_LOWRES, pslot, s );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
+}
+
 extern "C" int x264dsp_frame_init_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
                                                int n_frames, void *stream )
 {
     if( !ctx || !g || !slots || n_frames <= 0 )
         return X264DSP_E_ARG;
-    cudaStream_t s = xd_stream( ctx, stream );
-    dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h, n_frames );
-    const int pslot = xd_prof_begin( ctx, XD_PROF_LOWRES, s );
-    xd_lowres_kernel<<<grid, 128, 0, s>>>( *g, slots );
-    xd_prof_end( ctx, XD_PROF_LOWRES, pslot, s );
-    ctx->launches++;
-    XD_CHECK( cudaGetLastError() );
-    xd_border_job lowres = { (int64_t)g->slot_lowres_off + g->lowres_origin, g->lowres_stride, g->lowres_w,
-                             g->lowres_h, X264DSP_PADH, X264DSP_PADV, 1 };
-    return xd_launch_border( ctx, lowres, slots, g->slot_bytes, n_frames, 4, g->lowres_plane_size, s );
+    return xd_launch_lowres( ctx, g, slots, NULL, n_frames, xd_stream( ctx, stream ) );
+}
+
+// x264dsp_frame_load_luma_dev followed by x264dsp_frame_init_lowres_dev, in one pass over the picture
+int xd_frame_load_luma_lowres( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma, uint8_t *slots,
+                               int n_frames, cudaStream_t s )
+{
+    return xd_launch_lowres( ctx, g, slots, luma, n_frames, s );
+}
+
+extern "C" int x264dsp_frame_load_luma_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
+                                                    uint8_t *slots, int n_frames, void *stream )
+{
+    if( !ctx || !g || !luma || !slots || n_frames <= 0 )
+        return X264DSP_E_ARG;
+    return xd_launch_lowres( ctx, g, slots, luma, n_frames, xd_stream( ctx, stream ) );
 }
 
 extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
