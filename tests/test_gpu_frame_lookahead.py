@@ -144,7 +144,7 @@ def oracle_lookahead(g, slots, i, want_intra=1, rows=False):
 
 @pytest.mark.parametrize("kernel", [1, 2])      # 1 = warp per block row, 2 = warp per four block rows
 @pytest.mark.parametrize("w,h,n,cut", [(352, 288, 5, 3), (200, 120, 3, -1), (64, 64, 3, -1), (1920, 1080, 3, -1),
-                                       (96, 64, 2, -1), (80, 112, 4, 2), (64, 144, 3, -1)])
+                                       (96, 64, 2, -1), (80, 112, 4, 2), (64, 144, 3, -1), (3840, 2160, 2, -1)])
 def test_lookahead_matches_oracle(pkg, ctx, w, h, n, cut, kernel):
     torch = _torch()
     ctx.lookahead_select_kernel(kernel)
