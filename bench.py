@@ -440,7 +440,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("xd_la_quad_kernel_bytes_per_pair")
+            traffic = json.load(open(tpath)).get("xd_la_multi_kernel_bytes_per_pair")
             if traffic is not None:
                 traffic = traffic * pairs_per_launch
         sad_px = int(sums_np[:, pkg.LA_SAD_EVALS].sum()) * 64
@@ -457,7 +457,7 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "api": "x264dsp_lookahead_clips_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "xd_la_quad_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "xd_la_multi_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(bytes_per_pair * pairs_per_launch),
                          "avg_launch_ms": inter_avg_s * 1e3, "launches_timed": inter_n,

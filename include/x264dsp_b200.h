@@ -209,8 +209,9 @@ int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *
 int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int height, int n_clips, int clip_len,
                                   const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums );
 /* The inter search has two mappings with identical results: a warp per block row (shortest dependency
- * chain, best for a handful of frame pairs) and a warp per four block rows (a third of the instructions,
- * best once a launch holds a few dozen pairs).  mode 0 = choose by batch size (default), 1 = row, 2 = quad. */
+ * chain, best for a handful of frame pairs) and a warp per four or eight block rows (a quarter of the
+ * instructions, best once a launch holds a few dozen pairs).  mode 0 = choose by batch size (default),
+ * 1 = one row per warp, 2 = four rows per warp, 3 = eight rows per warp. */
 int x264dsp_lookahead_select_kernel( x264dsp_ctx_t *ctx, int mode );
 /* debug aid: clock64() cycles the inter kernel's warps spent per phase, summed over all warps since the
  * last reset: out[0..9] = waiting on the row below, block setup, zero-mv SATD probe, predictor

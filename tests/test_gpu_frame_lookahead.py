@@ -142,7 +142,7 @@ def oracle_lookahead(g, slots, i, want_intra=1, rows=False):
     return mv, c, s, r
 
 
-@pytest.mark.parametrize("kernel", [1, 2])      # 1 = warp per block row, 2 = warp per four block rows
+@pytest.mark.parametrize("kernel", [1, 2, 3])     # block rows per warp: 1, 4, 8
 @pytest.mark.parametrize("w,h,n,cut", [(352, 288, 5, 3), (200, 120, 3, -1), (64, 64, 3, -1), (1920, 1080, 3, -1),
                                        (96, 64, 2, -1), (80, 112, 4, 2), (64, 144, 3, -1), (3840, 2160, 2, -1)])
 def test_lookahead_matches_oracle(pkg, ctx, w, h, n, cut, kernel):
@@ -221,7 +221,7 @@ def test_lookahead_batch_of_clips_both_kernels(pkg, ctx):
         o.xo_lookahead_frame_cost(C.byref(go), cc.ptr(ref_slots[i]), cc.ptr(ref_slots[i - 1]) if p0[i] >= 0 else None, 1,
                                   cc.ptr(mv, cc.i16p), cc.ptr(c, cc.i32p), cc.ptr(s, cc.i32p), None)
         want.append((mv, c, s))
-    for kernel in (2, 1, 0):
+    for kernel in (3, 2, 1, 0):
         ctx.lookahead_select_kernel(kernel)
         mvs = torch.full((n, g.mb_count, 2), -7, dtype=torch.int16, device="cuda")
         costs = torch.full((n, g.mb_count), -7, dtype=torch.int32, device="cuda")

@@ -285,7 +285,7 @@ class Context:
             _dp(mvs), _dp(costs), _dp(sums), _dp(row_satds), None), "x264dsp_lookahead_frame_cost_dev")
 
     def lookahead_select_kernel(self, mode):
-        """0 = by batch size, 1 = warp-per-row kernel, 2 = quad-row kernel"""
+        """0 = by batch size, 1 = one block row per warp, 2 = four rows per warp, 3 = eight rows per warp"""
         check(lib().x264dsp_lookahead_select_kernel(self._h, int(mode)), "x264dsp_lookahead_select_kernel")
 
     def lookahead_clip_host(self, width, height, luma_frames):

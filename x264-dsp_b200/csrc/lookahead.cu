@@ -42,8 +42,8 @@ struct xd_la_args
     int32_t *ticket;
     uint32_t epoch;
     int me_range;
-    int slack;                          // quad kernel: extra blocks a quad stays behind the one below
-    const uint8_t *tiled;               // quad kernel: [pair] tiled reference plane N
+    int slack;                          // multi-row kernel: extra blocks a unit stays behind the one below
+    const uint8_t *tiled;               // multi-row kernel: [pair] tiled reference plane N
     int tile_w, tile_h;                 // tiles per row / column of a padded lowres plane
     unsigned long long *timing;         // optional phase-cycle counters (x264dsp_debug_lookahead_timing)
 };
@@ -623,51 +623,25 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 }
 
 // ---------------------------------------------------------------------------------------------
-// Quad-row inter kernel: the throughput mapping.
+// Multi-row inter kernel: the throughput mapping.
 //
-// One warp owns FOUR consecutive block rows of one frame pair; lane = 8*sub + r, where group `sub`
-// (8 lanes) walks row by0-sub and lane r holds pixel row r of that group's current 8x8 block.  The
-// four groups run in lock step with the reference's own lag of two blocks per row (group sub is at
-// column W-2-t+2*sub in step t), so inside a warp the row-to-row dependency is a register shuffle;
-// only the bottom group polls the quad below (one {mv, epoch} word per step) and only the top group
-// publishes.  Every lane evaluates ALL candidates of a search step for its pixel row (VABSDIFF4 x2
-// per candidate); the per-candidate sums are packed two to a register and reduced over the 8 lanes
-// of a group with three xor-shuffles, which serves four blocks per instruction instead of one.
-// SATD: each lane transforms its row horizontally (x264's packed two-4x4s-per-word form,
-// pixel.c:243-266), the vertical 4-point transform runs across lanes.
+// One warp owns 32/LPB consecutive block rows of one frame pair; a group of LPB lanes walks one block
+// row and each lane holds 8/LPB pixel rows of the group's current 8x8 block.  The groups run in lock
+// step with the reference's own lag of two blocks per row (group sub is at column W-2-t+2*sub in step
+// t), so inside a warp the row-to-row dependency is a register shuffle; only the bottom group polls the
+// unit below (one {mv, epoch} word per step) and only the top group publishes.  Every lane evaluates
+// ALL candidates of a search step for its pixel rows (VABSDIFF4 x2 per row and candidate); the
+// per-candidate sums are packed two to a register and reduced over the lanes of a group with
+// xor-shuffles, which serves 32/LPB blocks per instruction instead of one.
+// SATD: each lane transforms its rows horizontally (x264's packed two-4x4s-per-word form,
+// pixel.c:243-266), the vertical 4-point transform runs inside the lane and across lanes.
+//
+// The reference plane N is read through an 8x8-TILED copy (tile (tx,ty) = 64 contiguous bytes, tiles
+// of a tile row back to back, built per launch by xd_la_tile_kernel).  With lane = pixel row(s), the
+// lanes of a block read different rows: in the row-major plane that is one cache line per row and the
+// L1 data pipe saturates (ncu: 91 % of peak wavefronts, DRAM 4 %); tiled, the same rows sit in one or
+// two lines.  Sub-pel positions (a quarter of the fetches) read the row-major planes H, V, HV.
 #define LQ_FULL 0xffffffffu
-
-// The quad kernel reads the reference through an 8x8-TILED copy of the four padded lowres planes
-// (tile (tx,ty) = 64 contiguous bytes, tiles of a tile row back to back, built per launch by
-// xd_la_tile_kernel).  With lane = pixel row, the eight lanes of a block read eight different rows: in
-// the row-major plane that is eight cache lines per request and the L1 data pipe saturates (ncu: 91 %
-// of peak wavefronts, DRAM 4 %); tiled, the same rows sit in two or three lines.
-struct xd_lq_block
-{
-    const uint8_t *tref;      // tiled planes N, H, V, HV of the reference frame
-    int tplane;               // bytes per tiled plane
-    int tw;                   // tiles per tile row
-    int X0, Y0;               // padded coordinates (x+32, y+32) of this lane's row of the block origin
-    const uint8_t *rowp;      // row-major plane N at this lane's row of the block origin; planes H,V,HV follow
-    int plane_size, stride;   // (sub-pel positions, a quarter of the fetches, read the row-major planes)
-    uint2 fenc;               // this lane's source row
-    uint32_t fw[4];           // the same row as fw[k] = p[k] | p[k+4] << 16
-    int mvpx, mvpy;
-    const uint16_t *cost_mv;
-};
-
-__device__ __forceinline__ uint32_t xd_lq_reduce8( uint32_t v )
-{
-    v += __shfl_xor_sync( LQ_FULL, v, 1 );
-    v += __shfl_xor_sync( LQ_FULL, v, 2 );
-    v += __shfl_xor_sync( LQ_FULL, v, 4 );
-    return v;
-}
-
-__device__ __forceinline__ int xd_lq_bits( const xd_lq_block &B, int qx, int qy )
-{
-    return __ldg( B.cost_mv + ( qx - B.mvpx ) ) + __ldg( B.cost_mv + ( qy - B.mvpy ) );
-}
 
 // 8 consecutive pixels at an arbitrary byte address of a row-major plane: two aligned 8-byte loads
 __device__ __forceinline__ uint2 xd_lq_load8( const uint8_t *p )
@@ -677,20 +651,6 @@ __device__ __forceinline__ uint2 xd_lq_load8( const uint8_t *p )
     const uint2 lo = __ldg( w ), hi = __ldg( w + 1 );
     const uint32_t sh = (uint32_t)a << 3;
     const bool up = ( (uint32_t)a & 4u ) != 0;
-    const uint32_t w0 = up ? lo.y : lo.x, w1 = up ? hi.x : lo.y, w2 = up ? hi.y : hi.x;
-    return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
-}
-
-// 8 pixels at padded coordinates (X,Y) of the tiled plane at byte offset poff: the row chunk of the
-// tile holding X and of its right-hand neighbour (two aligned 8-byte loads, 64 bytes apart), then a
-// funnel shift by the position inside the chunk (shf.r.wrap takes the shift modulo 32)
-__device__ __forceinline__ uint2 xd_lq_tile8( const xd_lq_block &B, int poff, int X, int Y )
-{
-    const int off = poff + ( ( ( Y >> 3 ) * B.tw + ( X >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 );
-    const uint2 *w = (const uint2 *)( B.tref + off );
-    const uint2 lo = __ldg( w ), hi = __ldg( w + 8 );
-    const uint32_t sh = (uint32_t)X << 3;
-    const bool up = ( X & 4 ) != 0;
     const uint32_t w0 = up ? lo.y : lo.x, w1 = up ? hi.x : lo.y, w2 = up ? hi.y : hi.x;
     return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
 }
@@ -710,34 +670,6 @@ __device__ __forceinline__ uint32_t xd_lq_pack( uint32_t lo, uint32_t hi )
     return __byte_perm( lo, hi, 0x5410 );
 }
 
-// 8 pixels of this lane's row of the prediction at quarter-pel (qx,qy): get_ref / mc_luma (mc.c:192-264)
-__device__ __forceinline__ uint2 xd_lq_fetch( const xd_lq_block &B, int qx, int qy )
-{
-    const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
-    if( !phase )
-        return xd_lq_tile8( B, 0, B.X0 + ( qx >> 2 ), B.Y0 + ( qy >> 2 ) );
-    const int off = ( qy >> 2 ) * B.stride + ( qx >> 2 );
-    uint2 a = xd_lq_load8( B.rowp + ( off + xd_qpel_plane_a( phase ) * B.plane_size + ( fy == 3 ? B.stride : 0 ) ) );
-    if( phase & 5 )
-    {
-        const uint2 b = xd_lq_load8( B.rowp + ( off + xd_qpel_plane_b( phase ) * B.plane_size + ( fx == 3 ? 1 : 0 ) ) );
-        a.x = xd_avg4( a.x, b.x );
-        a.y = xd_avg4( a.y, b.y );
-    }
-    return a;
-}
-
-// full-pel displacement (mx,my): plane N only
-__device__ __forceinline__ uint32_t xd_lq_sad_fpel( const xd_lq_block &B, int mx, int my )
-{
-    return xd_lq_sad8( xd_lq_tile8( B, 0, B.X0 + mx, B.Y0 + my ), B.fenc, 0u );
-}
-
-__device__ __forceinline__ uint32_t xd_lq_sad_qpel( const xd_lq_block &B, int qx, int qy )
-{
-    return xd_lq_sad8( xd_lq_fetch( B, qx, qy ), B.fenc, 0u );
-}
-
 // p[k] | p[k+4] << 16 for k = 0..3
 __device__ __forceinline__ void xd_lq_unpack( uint2 p, uint32_t w[4] )
 {
@@ -752,36 +684,6 @@ __device__ __forceinline__ uint32_t xd_lq_abs2( uint32_t a )
 {
     const uint32_t s = ( ( a >> 15 ) & 0x10001u ) * 0xffffu;
     return ( a + s ) ^ s;
-}
-
-// SATD 8x8 (pixel.c:294-335) of the group's block against the prediction at (qx,qy).  Executed by
-// the whole warp (shuffles); `on` only gates the loads.  Every lane of a group returns the cost.
-__device__ __forceinline__ int xd_lq_satd( const xd_lq_block &B, int qx, int qy, int r, bool on )
-{
-    uint2 p = make_uint2( 0u, 0u );
-    if( on )
-        p = xd_lq_fetch( B, qx, qy );
-    uint32_t w[4];
-    xd_lq_unpack( p, w );
-    // horizontal 4-point transform of the row, left and right 4x4 side by side in the two halves
-    const uint32_t a0 = B.fw[0] - w[0], a1 = B.fw[1] - w[1], a2 = B.fw[2] - w[2], a3 = B.fw[3] - w[3];
-    const uint32_t t0 = a0 + a1, t1 = a0 - a1, t2 = a2 + a3, t3 = a2 - a3;
-    uint32_t h[4] = { t0 + t2, t1 + t3, t0 - t2, t1 - t3 };
-    // vertical transform over the four rows of an 8x4 (lanes r^1, r^2)
-    const uint32_t n1 = ( r & 1 ) ? ~0u : 0u, c1 = r & 1, n2 = ( r & 2 ) ? ~0u : 0u, c2 = ( r >> 1 ) & 1;
-    uint32_t sum = 0;
-#pragma unroll
-    for( int k = 0; k < 4; k++ )
-    {
-        uint32_t v = h[k];
-        v = __shfl_xor_sync( LQ_FULL, v, 1 ) + ( v ^ n1 ) + c1;
-        v = __shfl_xor_sync( LQ_FULL, v, 2 ) + ( v ^ n2 ) + c2;
-        sum += xd_lq_abs2( v );
-    }
-    sum += __shfl_xor_sync( LQ_FULL, sum, 1 );
-    sum += __shfl_xor_sync( LQ_FULL, sum, 2 );
-    const uint32_t half = ( ( sum & 0xFFFFu ) + ( sum >> 16 ) ) >> 1;        // one 8x4
-    return (int)( half + __shfl_xor_sync( LQ_FULL, half, 4 ) );
 }
 
 // 8x8-tiled copy of the padded lowres plane N of every reference frame of the launch (the full-pel
@@ -808,14 +710,187 @@ xd_la_tile_kernel( xd_la_args A, const int32_t *inter_pairs, uint8_t *tiled )
         *(uint2 *)( dst + 64 ) = make_uint2( v.z, v.w );
 }
 
-__global__ void __launch_bounds__( LA_WARPS * 32 )
-xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
+// ---------------------------------------------------------------------------------------------
+// LPB lanes per block (8: one pixel row per lane, four block rows per warp; 4: two pixel rows per
+// lane, EIGHT block rows per warp).  Everything that is uniform inside a group --
+// candidate coordinates, clips, medians, winner selection, the step bookkeeping -- is executed once per
+// warp instruction whatever the group size, so halving the lanes per block halves that share of the
+// instruction count per block; the per-pixel work (loads, VABSDIFF4, Hadamard) stays the same per block.
+template<int RPL>
+struct xd_lm_block
 {
+    const uint8_t *tref;      // tiled plane N of the reference frame
+    int tw;                   // tiles per tile row
+    int X0, Y0;               // padded coordinates (x+32, y+32) of this lane's FIRST row of the block origin
+    const uint8_t *rowp;      // row-major plane N at that row; planes H,V,HV follow
+    int plane_size, stride;
+    uint2 fenc[RPL];          // this lane's source rows
+    uint32_t fw[RPL][4];      // the same rows as fw[k] = p[k] | p[k+4] << 16
+    int mvpx, mvpy;
+    const uint16_t *cost_mv;
+};
+
+template<int LPB>
+__device__ __forceinline__ uint32_t xd_lm_reduce( uint32_t v )
+{
+#pragma unroll
+    for( int o = 1; o < LPB; o <<= 1 )
+        v += __shfl_xor_sync( LQ_FULL, v, o );
+    return v;
+}
+
+template<int RPL>
+__device__ __forceinline__ int xd_lm_bits( const xd_lm_block<RPL> &B, int qx, int qy )
+{
+    return __ldg( B.cost_mv + ( qx - B.mvpx ) ) + __ldg( B.cost_mv + ( qy - B.mvpy ) );
+}
+
+__device__ __forceinline__ uint2 xd_lm_assemble( uint2 lo, uint2 hi, uint32_t sh, bool up )
+{
+    const uint32_t w0 = up ? lo.y : lo.x, w1 = up ? hi.x : lo.y, w2 = up ? hi.y : hi.x;
+    return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+}
+
+// the lane's RPL rows, 8 pixels each, at padded coordinates (X,Y) of the tiled plane N
+template<int RPL>
+__device__ __forceinline__ void xd_lm_tile( const xd_lm_block<RPL> &B, int X, int Y, uint2 out[RPL] )
+{
+    const int off = ( ( ( Y >> 3 ) * B.tw + ( X >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 );
+    const uint32_t sh = (uint32_t)X << 3;
+    const bool up = ( X & 4 ) != 0;
+    const uint2 *w = (const uint2 *)( B.tref + off );
+    const uint2 lo = __ldg( w ), hi = __ldg( w + 8 );
+    if( RPL == 2 )
+    {
+        // the next row: 8 bytes further in the same tile, or the first row of the tile below
+        const uint2 *w1 = (const uint2 *)( B.tref + ( off + ( ( Y & 7 ) == 7 ? ( B.tw << 6 ) - 56 : 8 ) ) );
+        const uint2 lo1 = __ldg( w1 ), hi1 = __ldg( w1 + 8 );
+        out[RPL - 1] = xd_lm_assemble( lo1, hi1, sh, up );
+    }
+    out[0] = xd_lm_assemble( lo, hi, sh, up );
+}
+
+// the lane's rows of the prediction at quarter-pel (qx,qy): get_ref / mc_luma (mc.c:192-264)
+template<int RPL>
+__device__ __forceinline__ void xd_lm_fetch( const xd_lm_block<RPL> &B, int qx, int qy, uint2 out[RPL] )
+{
+    const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
+    if( !phase )
+    {
+        xd_lm_tile<RPL>( B, B.X0 + ( qx >> 2 ), B.Y0 + ( qy >> 2 ), out );
+        return;
+    }
+    const int off = ( qy >> 2 ) * B.stride + ( qx >> 2 );
+    const int offa = off + xd_qpel_plane_a( phase ) * B.plane_size + ( fy == 3 ? B.stride : 0 );
+    const int offb = off + xd_qpel_plane_b( phase ) * B.plane_size + ( fx == 3 ? 1 : 0 );
+#pragma unroll
+    for( int j = 0; j < RPL; j++ )
+        out[j] = xd_lq_load8( B.rowp + ( offa + j * B.stride ) );
+    if( phase & 5 )
+    {
+#pragma unroll
+        for( int j = 0; j < RPL; j++ )
+        {
+            const uint2 b = xd_lq_load8( B.rowp + ( offb + j * B.stride ) );
+            out[j].x = xd_avg4( out[j].x, b.x );
+            out[j].y = xd_avg4( out[j].y, b.y );
+        }
+    }
+}
+
+template<int RPL>
+__device__ __forceinline__ uint32_t xd_lm_sad( const xd_lm_block<RPL> &B, const uint2 p[RPL] )
+{
+    uint32_t acc = 0;
+#pragma unroll
+    for( int j = 0; j < RPL; j++ )
+        acc = xd_lq_sad8( p[j], B.fenc[j], acc );
+    return acc;
+}
+
+template<int RPL>
+__device__ __forceinline__ uint32_t xd_lm_sad_fpel( const xd_lm_block<RPL> &B, int mx, int my )
+{
+    uint2 p[RPL];
+    xd_lm_tile<RPL>( B, B.X0 + mx, B.Y0 + my, p );
+    return xd_lm_sad<RPL>( B, p );
+}
+
+template<int RPL>
+__device__ __forceinline__ uint32_t xd_lm_sad_qpel( const xd_lm_block<RPL> &B, int qx, int qy )
+{
+    uint2 p[RPL];
+    xd_lm_fetch<RPL>( B, qx, qy, p );
+    return xd_lm_sad<RPL>( B, p );
+}
+
+// SATD 8x8 (pixel.c:294-335); whole warp executes, `on` gates the loads, every lane of a group gets the cost.
+// q = lane inside the group; the lane holds pixel rows q*RPL .. q*RPL+RPL-1.
+template<int LPB>
+__device__ __forceinline__ int xd_lm_satd( const xd_lm_block<8 / LPB> &B, int qx, int qy, int q, bool on )
+{
+    constexpr int RPL = 8 / LPB;
+    uint2 p[RPL];
+#pragma unroll
+    for( int j = 0; j < RPL; j++ )
+        p[j] = make_uint2( 0u, 0u );
+    if( on )
+        xd_lm_fetch<RPL>( B, qx, qy, p );
+    uint32_t h[RPL][4];
+#pragma unroll
+    for( int j = 0; j < RPL; j++ )
+    {
+        uint32_t w[4];
+        xd_lq_unpack( p[j], w );
+        const uint32_t a0 = B.fw[j][0] - w[0], a1 = B.fw[j][1] - w[1], a2 = B.fw[j][2] - w[2], a3 = B.fw[j][3] - w[3];
+        const uint32_t t0 = a0 + a1, t1 = a0 - a1, t2 = a2 + a3, t3 = a2 - a3;
+        h[j][0] = t0 + t2; h[j][1] = t1 + t3; h[j][2] = t0 - t2; h[j][3] = t1 - t3;
+    }
+    const uint32_t n1 = ( q & 1 ) ? ~0u : 0u, c1 = q & 1;
+    uint32_t sum = 0;
+    if( RPL == 1 )
+    {
+        const uint32_t n2 = ( q & 2 ) ? ~0u : 0u, c2 = ( q >> 1 ) & 1;
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            uint32_t v = h[0][k];
+            v = __shfl_xor_sync( LQ_FULL, v, 1 ) + ( v ^ n1 ) + c1;
+            v = __shfl_xor_sync( LQ_FULL, v, 2 ) + ( v ^ n2 ) + c2;
+            sum += xd_lq_abs2( v );
+        }
+        sum += __shfl_xor_sync( LQ_FULL, sum, 1 );
+        sum += __shfl_xor_sync( LQ_FULL, sum, 2 );
+        const uint32_t half = ( ( sum & 0xFFFFu ) + ( sum >> 16 ) ) >> 1;
+        return (int)( half + __shfl_xor_sync( LQ_FULL, half, 4 ) );
+    }
+    else
+    {
+        // rows (2q, 2q+1) of an 8x4 live in this lane, the other two in lane q^1
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            uint32_t sk = h[0][k] + h[RPL - 1][k], dk = h[0][k] - h[RPL - 1][k];
+            sk = __shfl_xor_sync( LQ_FULL, sk, 1 ) + ( sk ^ n1 ) + c1;
+            dk = __shfl_xor_sync( LQ_FULL, dk, 1 ) + ( dk ^ n1 ) + c1;
+            sum += xd_lq_abs2( sk ) + xd_lq_abs2( dk );
+        }
+        sum += __shfl_xor_sync( LQ_FULL, sum, 1 );
+        const uint32_t half = ( ( sum & 0xFFFFu ) + ( sum >> 16 ) ) >> 1;
+        return (int)( half + __shfl_xor_sync( LQ_FULL, half, 2 ) );
+    }
+}
+
+template<int LPB>
+__global__ void __launch_bounds__( LA_WARPS * 32 )
+xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
+{
+    constexpr int RPL = 8 / LPB, GROUPS = 32 / LPB;
     const x264dsp_geom_t &g = A.g;
-    const int lane = threadIdx.x & 31, sub = lane >> 3, r = lane & 7;
+    const int lane = threadIdx.x & 31, sub = lane / LPB, q = lane % LPB;
     const int W = g.mb_w, H = g.mb_h, ls = g.lowres_stride;
-    const int rows = H - 2, quads = ( rows + 3 ) >> 2;
-    const int total = n_inter * quads;
+    const int rows = H - 2, units = ( rows + GROUPS - 1 ) / GROUPS;
+    const int total = n_inter * units;
 
     for( ;; )
     {
@@ -825,15 +900,15 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         ticket = __shfl_sync( LQ_FULL, ticket, 0 );
         if( ticket >= total )
             return;
-        // quad-major over the pairs of the launch (see xd_la_inter_kernel): the quad a warp waits on
-        // always holds a smaller ticket, i.e. is running or finished
-        const int quad = ticket / n_inter;
-        const int pair = inter_pairs[ticket - quad * n_inter];
-        const int by0 = H - 2 - 4 * quad;                 // bottom row of the quad
-        const int nrows = min( 4, by0 );                  // rows by0, by0-1, ... down to row 1
+        // unit-major over the pairs of the launch: the unit a warp waits on always holds a smaller
+        // ticket, i.e. is running or finished
+        const int unit = ticket / n_inter;
+        const int pair = inter_pairs[ticket - unit * n_inter];
+        const int by0 = H - 2 - GROUPS * unit;            // bottom row of the unit
+        const int nrows = min( GROUPS, by0 );             // rows by0, by0-1, ... down to row 1
         const int by = by0 - sub;
         const bool row_ok = sub < nrows;
-        const bool has_below = quad > 0;
+        const bool has_below = unit > 0;
         const bool is_top = sub == nrows - 1;
         const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
         const uint8_t *ref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
@@ -846,28 +921,27 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         const int miny = -( by << 3 ) - 4, maxy = ( ( H - by - 1 ) << 3 ) + 4;
         const int sminy = ( miny - 8 ) << 2, smaxy = ( maxy + 8 ) << 2;
 
-        xd_lq_block B;
+        xd_lm_block<RPL> B;
         B.tw = A.tile_w;
-        B.tplane = A.tile_w * A.tile_h * 64;
-        B.tref = A.tiled + (size_t)pair * B.tplane;
+        B.tref = A.tiled + (size_t)pair * ( (size_t)A.tile_w * A.tile_h * 64 );
         B.rowp = ref;
         B.plane_size = g.lowres_plane_size;
         B.stride = ls;
         B.X0 = B.Y0 = 32;
         B.cost_mv = A.cost_mv;
         B.mvpx = B.mvpy = 0;
-        B.fenc = make_uint2( 0u, 0u );
-        B.fw[0] = B.fw[1] = B.fw[2] = B.fw[3] = 0u;
+#pragma unroll
+        for( int j = 0; j < RPL; j++ )
+        {
+            B.fenc[j] = make_uint2( 0u, 0u );
+            B.fw[j][0] = B.fw[j][1] = B.fw[j][2] = B.fw[j][3] = 0u;
+        }
         int sad_evals = 0, satd_evals = 0, row_sum = 0, row_intra = 0;
 
         uint32_t mv_right = 0, mv_b = 0, mv_br = 0, mv_bl = 0;
         uint32_t last_mv = 0;                              // this group's previous result (0 when it had none)
         unsigned long long pending = 0;
-        // step t = -1 only shifts the neighbour pipeline: it brings (W-2, below) in.
-        // Rows could follow each other two blocks apart, but then every step of every quad of a pair
-        // would start with a publish -> poll round trip through L2 and the whole chain would advance at
-        // the pace of its slowest member.  Starting A.slack blocks later decouples them: in steady
-        // state the word a quad needs has been there for several block times.
+        // step t = -1 only shifts the neighbour pipeline: it brings (W-2, below) in
         if( has_below )
         {
             const int far = max( W - 2 - A.slack, 1 );
@@ -875,12 +949,17 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             pending = xd_ld_sync( sync_below + ( W - 2 ) );
         }
 
-        // the first block's source row, fetched ahead like every later one
-        uint2 nx_fenc = make_uint2( 0u, 0u );
+        // the first block's source rows, fetched ahead like every later one
+        uint2 nx_fenc[RPL];
         int nx_ic = 0;
+#pragma unroll
+        for( int j = 0; j < RPL; j++ )
+            nx_fenc[j] = make_uint2( 0u, 0u );
         if( row_ok )
         {
-            nx_fenc = __ldg( (const uint2 *)( cur + ( (size_t)by * ls + ( W - 2 ) ) * 8 + (size_t)r * ls ) );
+#pragma unroll
+            for( int j = 0; j < RPL; j++ )
+                nx_fenc[j] = __ldg( (const uint2 *)( cur + ( (size_t)by * ls + ( W - 2 ) ) * 8 + (size_t)( q * RPL + j ) * ls ) );
             if( want_intra )
                 nx_ic = icost_row[W - 2];
         }
@@ -892,8 +971,8 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             const bool act = row_ok && bx >= 1 && bx <= W - 2;
 
             // ---- neighbour of the row below at column bx-1: the group underneath produced it in the
-            //      previous step; the bottom group reads it from the quad below
-            uint32_t incoming = __shfl_up_sync( LQ_FULL, last_mv, 8 );
+            //      previous step; the bottom group reads it from the unit below
+            uint32_t incoming = __shfl_up_sync( LQ_FULL, last_mv, LPB );
             {
                 const int bx0 = W - 2 - t;                 // the bottom group's column
                 uint32_t polled = 0;
@@ -915,18 +994,24 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             if( act )
             {
                 const size_t pel = ( (size_t)by * ls + bx ) * 8;
-                B.rowp = ref + pel + r * ls;
+                B.rowp = ref + pel + ( q * RPL ) * ls;
                 B.X0 = 8 * bx + 32;
-                B.Y0 = 8 * by + r + 32;
-                B.fenc = nx_fenc;
+                B.Y0 = 8 * by + q * RPL + 32;
                 ic = nx_ic;
+#pragma unroll
+                for( int j = 0; j < RPL; j++ )
+                    B.fenc[j] = nx_fenc[j];
                 if( bx > 1 )
                 {
-                    nx_fenc = __ldg( (const uint2 *)( cur + pel - 8 + (size_t)r * ls ) );
+#pragma unroll
+                    for( int j = 0; j < RPL; j++ )
+                        nx_fenc[j] = __ldg( (const uint2 *)( cur + pel - 8 + (size_t)( q * RPL + j ) * ls ) );
                     if( want_intra )
                         nx_ic = icost_row[bx - 1];
                 }
-                xd_lq_unpack( B.fenc, B.fw );
+#pragma unroll
+                for( int j = 0; j < RPL; j++ )
+                    xd_lq_unpack( B.fenc[j], B.fw[j] );
                 minx = -( bx << 3 ) - 4;
                 maxx = ( ( W - bx - 1 ) << 3 ) + 4;
                 // predictors (slicetype.c:105-113): right, below, below-left (below-right is a candidate only)
@@ -939,7 +1024,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             const bool needz = act && !( B.mvpx | B.mvpy );
             if( __any_sync( LQ_FULL, needz ) )
             {
-                const int c0 = xd_lq_satd( B, 0, 0, r, needz );
+                const int c0 = xd_lm_satd<LPB>( B, 0, 0, q, needz );
                 if( needz )
                 {
                     satd_evals++;
@@ -985,26 +1070,31 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 {
                     uint32_t s = 0;
                     if( cok[k] )
-                        s = xd_lq_sad_fpel( B, ccx[k], ccy[k] );
+                        s = xd_lm_sad_fpel<RPL>( B, ccx[k], ccy[k] );
                     w[k >> 1] += s << ( 16 * ( k & 1 ) );
                 }
-                // lane r adds candidate r's mv bits, or the "does not compete" marker
-                if( search && r < 6 )
-                {
-                    int kx = ccx[0], ky = ccy[0];
-                    bool ok = cok[0];
+                // lane q adds the mv bits of candidates q, q+LPB, ... or the "does not compete" marker
 #pragma unroll
-                    for( int k = 1; k < 6; k++ )
-                        if( r == k ) { kx = ccx[k]; ky = ccy[k]; ok = cok[k]; }
-                    const uint32_t add = !ok ? 0xFFFFu : r ? (uint32_t)xd_lq_bits( B, kx << 2, ky << 2 ) : 0u;
-                    const uint32_t sh = add << ( 16 * ( r & 1 ) );
-                    if( ( r >> 1 ) == 0 ) w[0] += sh;
-                    else if( ( r >> 1 ) == 1 ) w[1] += sh;
-                    else w[2] += sh;
+                for( int rep = 0; rep < ( 6 + LPB - 1 ) / LPB; rep++ )
+                {
+                    const int kk = q + rep * LPB;
+                    if( search && kk < 6 )
+                    {
+                        int kx = ccx[0], ky = ccy[0];
+                        bool ok = cok[0];
+#pragma unroll
+                        for( int k = 1; k < 6; k++ )
+                            if( kk == k ) { kx = ccx[k]; ky = ccy[k]; ok = cok[k]; }
+                        const uint32_t add = !ok ? 0xFFFFu : kk ? (uint32_t)xd_lm_bits<RPL>( B, kx << 2, ky << 2 ) : 0u;
+                        const uint32_t sh = add << ( 16 * ( kk & 1 ) );
+                        if( ( kk >> 1 ) == 0 ) w[0] += sh;
+                        else if( ( kk >> 1 ) == 1 ) w[1] += sh;
+                        else w[2] += sh;
+                    }
                 }
-                w[0] = xd_lq_reduce8( w[0] );
-                w[1] = xd_lq_reduce8( w[1] );
-                w[2] = xd_lq_reduce8( w[2] );
+                w[0] = xd_lm_reduce<LPB>( w[0] );
+                w[1] = xd_lm_reduce<LPB>( w[1] );
+                w[2] = xd_lm_reduce<LPB>( w[2] );
                 if( search )
                 {
                     int best = 0x7FFFFFFF;
@@ -1035,17 +1125,17 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     uint32_t w0 = 0, w1 = 0;
                     if( dia )
                     {
-                        w0 = xd_lq_pack( xd_lq_sad_fpel( B, bmx, bmy - 1 ), xd_lq_sad_fpel( B, bmx, bmy + 1 ) );
-                        w1 = xd_lq_pack( xd_lq_sad_fpel( B, bmx - 1, bmy ), xd_lq_sad_fpel( B, bmx + 1, bmy ) );
-                        if( r < 4 )
+                        w0 = xd_lq_pack( xd_lm_sad_fpel<RPL>( B, bmx, bmy - 1 ), xd_lm_sad_fpel<RPL>( B, bmx, bmy + 1 ) );
+                        w1 = xd_lq_pack( xd_lm_sad_fpel<RPL>( B, bmx - 1, bmy ), xd_lm_sad_fpel<RPL>( B, bmx + 1, bmy ) );
+                        if( q < 4 )
                         {
-                            const int dx = r == 2 ? -1 : r == 3 ? 1 : 0, dy = r == 0 ? -1 : r == 1 ? 1 : 0;
-                            const uint32_t sh = (uint32_t)xd_lq_bits( B, ( bmx + dx ) << 2, ( bmy + dy ) << 2 ) << ( 16 * ( r & 1 ) );
-                            if( r < 2 ) w0 += sh; else w1 += sh;
+                            const int dx = q == 2 ? -1 : q == 3 ? 1 : 0, dy = q == 0 ? -1 : q == 1 ? 1 : 0;
+                            const uint32_t sh = (uint32_t)xd_lm_bits<RPL>( B, ( bmx + dx ) << 2, ( bmy + dy ) << 2 ) << ( 16 * ( q & 1 ) );
+                            if( q < 2 ) w0 += sh; else w1 += sh;
                         }
                     }
-                    w0 = xd_lq_reduce8( w0 );
-                    w1 = xd_lq_reduce8( w1 );
+                    w0 = xd_lm_reduce<LPB>( w0 );
+                    w1 = xd_lm_reduce<LPB>( w1 );
                     if( dia )
                     {
                         sad_evals += 4;
@@ -1075,7 +1165,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 if( search )
                 {
                     if( bmx == pmx && bmy == pmy )
-                        bcost += xd_lq_bits( B, qx, qy );
+                        bcost += xd_lm_bits<RPL>( B, qx, qy );
                     const int sminx = ( minx - 8 ) << 2, smaxx = ( maxx + 8 ) << 2;
                     px = xd_clip3( B.mvpx, sminx + 2, smaxx - 2 );
                     py = xd_clip3( B.mvpy, sminy + 2, smaxy - 2 );
@@ -1086,11 +1176,11 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     uint32_t s = 0;
                     if( single )
                     {
-                        s = xd_lq_sad_qpel( B, px, py );
-                        if( r == 0 )
-                            s += (uint32_t)xd_lq_bits( B, px, py );
+                        s = xd_lm_sad_qpel<RPL>( B, px, py );
+                        if( q == 0 )
+                            s += (uint32_t)xd_lm_bits<RPL>( B, px, py );
                     }
-                    s = xd_lq_reduce8( s );
+                    s = xd_lm_reduce<LPB>( s );
                     if( single )
                     {
                         sad_evals++;
@@ -1101,17 +1191,17 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 uint32_t w0 = 0, w1 = 0;
                 if( search )
                 {
-                    w0 = xd_lq_pack( xd_lq_sad_qpel( B, qx, qy - 2 ), xd_lq_sad_qpel( B, qx, qy + 2 ) );
-                    w1 = xd_lq_pack( xd_lq_sad_qpel( B, qx - 2, qy ), xd_lq_sad_qpel( B, qx + 2, qy ) );
-                    if( r < 4 )
+                    w0 = xd_lq_pack( xd_lm_sad_qpel<RPL>( B, qx, qy - 2 ), xd_lm_sad_qpel<RPL>( B, qx, qy + 2 ) );
+                    w1 = xd_lq_pack( xd_lm_sad_qpel<RPL>( B, qx - 2, qy ), xd_lm_sad_qpel<RPL>( B, qx + 2, qy ) );
+                    if( q < 4 )
                     {
-                        const int dx = r == 2 ? -2 : r == 3 ? 2 : 0, dy = r == 0 ? -2 : r == 1 ? 2 : 0;
-                        const uint32_t sh = (uint32_t)xd_lq_bits( B, qx + dx, qy + dy ) << ( 16 * ( r & 1 ) );
-                        if( r < 2 ) w0 += sh; else w1 += sh;
+                        const int dx = q == 2 ? -2 : q == 3 ? 2 : 0, dy = q == 0 ? -2 : q == 1 ? 2 : 0;
+                        const uint32_t sh = (uint32_t)xd_lm_bits<RPL>( B, qx + dx, qy + dy ) << ( 16 * ( q & 1 ) );
+                        if( q < 2 ) w0 += sh; else w1 += sh;
                     }
                 }
-                w0 = xd_lq_reduce8( w0 );
-                w1 = xd_lq_reduce8( w1 );
+                w0 = xd_lm_reduce<LPB>( w0 );
+                w1 = xd_lm_reduce<LPB>( w1 );
                 if( search )
                 {
                     sad_evals += 4;
@@ -1126,12 +1216,12 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     }
                 }
                 // me.c:519-524: the winner is re-costed with SATD
-                const int c = xd_lq_satd( B, qx, qy, r, search );
+                const int c = xd_lm_satd<LPB>( B, qx, qy, q, search );
                 if( search )
                 {
                     satd_evals++;
                     mvx = qx; mvy = qy;
-                    cost = c + xd_lq_bits( B, qx, qy ) - 1;           // slicetype.c:128-130
+                    cost = c + xd_lm_bits<RPL>( B, qx, qy ) - 1;      // slicetype.c:128-130
                     if( mvx | mvy )
                         cost += 5;
                 }
@@ -1141,7 +1231,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             const uint32_t mv_packed = ( (uint32_t)mvx & 0xFFFF ) | ( (uint32_t)mvy << 16 );
             if( act )
             {
-                if( r == 0 )
+                if( q == 0 )
                 {
                     const int xy = by * W + bx;
                     if( is_top )
@@ -1165,7 +1255,7 @@ xd_la_quad_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             mv_b = mv_bl;
         }
 
-        if( row_ok && r == 0 )
+        if( row_ok && q == 0 )
         {
             int32_t *s = A.sums + (size_t)pair * X264DSP_LA_SUMS;
             atomicAdd( &s[X264DSP_LA_COST_INTER], row_sum );
@@ -1273,7 +1363,7 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
     XD_CHECK( cudaGetLastError() );
     if( n_inter > 0 )
     {
-        // Two mappings of the same search (both bit-exact): the quad-row kernel executes a third of the
+        // Two mappings of the same search (both bit-exact): the multi-row kernel executes a quarter of the
         // instructions per block and wins once the batch fills the machine; with few pairs in flight the
         // launch is bound by the per-pair dependency chain and the warp-per-row kernel, which spreads a
         // block over 32 lanes and a frame over four times as many warps, has the shorter chain.
@@ -1287,21 +1377,26 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         const int timed = ctx->la_timing != NULL;
         const int force_row = ctx->la_kernel ? ( ctx->la_kernel == 1 ) : env_row;
         const int row_kernel = timed || ( force_row >= 0 ? force_row : n_inter < 48 );
+        // 2 = 8 lanes per block (four block rows per warp), 3 = 4 lanes per block (eight block rows per warp)
+        const int lanes_mode = ctx->la_kernel >= 2 ? ctx->la_kernel : 3;
         const int rows = g->mb_h - 2;
-        const int total_warps = row_kernel ? n_inter * rows : n_inter * ( ( rows + 3 ) / 4 );
+        const int rows_per_warp = lanes_mode == 3 ? 8 : 4;
+        const int total_warps = row_kernel ? n_inter * rows : n_inter * ( ( rows + rows_per_warp - 1 ) / rows_per_warp );
         int ctas = ( total_warps + LA_WARPS - 1 ) / LA_WARPS;
         // persistent launch: never more CTAs than fit on the machine at once (work beyond that is
         // picked up through the ticket as warps finish; the ticket order keeps that deadlock-free)
-        static int per_sm[3] = { 0, 0, 0 };
-        const int which = timed ? 1 : row_kernel ? 0 : 2;
+        static int per_sm[4] = { 0, 0, 0, 0 };
+        const int which = timed ? 1 : row_kernel ? 0 : lanes_mode;
         if( !per_sm[which] )
         {
             if( which == 1 )
                 XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[1], xd_la_inter_kernel<true>, LA_WARPS * 32, 0 ) );
             else if( which == 0 )
                 XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[0], xd_la_inter_kernel<false>, LA_WARPS * 32, 0 ) );
+            else if( which == 2 )
+                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[2], xd_la_multi_kernel<8>, LA_WARPS * 32, 0 ) );
             else
-                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[2], xd_la_quad_kernel, LA_WARPS * 32, 0 ) );
+                XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm[3], xd_la_multi_kernel<4>, LA_WARPS * 32, 0 ) );
             if( per_sm[which] < 1 )
                 per_sm[which] = 1;
             const char *e = getenv( "X264DSP_LA_CTAS_PER_SM" );      // tuning knob (tools/la_phase_timing.py)
@@ -1311,7 +1406,7 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         const int cap = ctx->sm_count * per_sm[which];
         if( ctas > cap )
             ctas = cap;
-        if( which == 2 )
+        if( which >= 2 )
         {
             const int chunks = ( ( A.tile_w + 1 ) / 2 ) * A.tile_h * 8;
             const int tslot = xd_prof_begin( ctx, XD_PROF_LA_TILE, s );
@@ -1324,8 +1419,10 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
             xd_la_inter_kernel<true><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
         else if( which == 0 )
             xd_la_inter_kernel<false><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
+        else if( which == 2 )
+            xd_la_multi_kernel<8><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
         else
-            xd_la_quad_kernel<<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
+            xd_la_multi_kernel<4><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
         xd_prof_end( ctx, XD_PROF_LA_INTER, pslot, s );
         ctx->launches++;
         XD_CHECK( cudaGetLastError() );
@@ -1547,10 +1644,10 @@ extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int h
     return x264dsp_lookahead_clips_host( ctx, width, height, 1, n_frames, luma, mvs, costs, sums );
 }
 
-// mode 0 = pick by batch size, 1 = warp-per-row kernel, 2 = quad-row kernel (results are identical)
+// mode 0 = pick by batch size, 1 = warp per block row, 2 = four block rows per warp, 3 = eight (identical results)
 extern "C" int x264dsp_lookahead_select_kernel( x264dsp_ctx_t *ctx, int mode )
 {
-    if( !ctx || mode < 0 || mode > 2 )
+    if( !ctx || mode < 0 || mode > 3 )
         return X264DSP_E_ARG;
     ctx->la_kernel = mode;
     return 0;
