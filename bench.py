@@ -308,11 +308,33 @@ def workload_config(args, frames_per_step, sample=None):
 
 # --------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: keep this process (and the pinned buffers it first-touches) on the CPU cores NVML
+    reports as local to its GPU, so that eight ranks' host->device copies do not cross sockets.  Best effort:
+    returns a short description, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cores = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cores &= allowed
+        if cores and cores != allowed:
+            os.sched_setaffinity(0, cores)
+            return f"{len(cores)} of {len(allowed)} cores (NVML affinity of GPU {gpu_index})"
+    except Exception:
+        pass
+    return None
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and args.impl != "reference" else None
     pkg = load_package()
     sampler = ClockSampler(local_rank)
     if rank == 0 and args.impl != "reference":
@@ -456,6 +478,7 @@ def main():
                     "d2h_bytes_per_step": int(mvs_host.nbytes + costs_host.nbytes + sums_host.nbytes),
                     "ms_per_step": e2e_ms / args.steps, "api": "x264dsp_lookahead_clips_host (pinned host buffers)"},
             "gpu_launches": int(launches),
+            "host_affinity": numa,
             "clocks": clocks,
             "roofline": {"kernel": "xd_la_multi_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
