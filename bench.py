@@ -403,7 +403,7 @@ def main():
     inter_ms, inter_n = ctx.profile_read(pkg.PROF_LA_INTER)
     prof = {name: ctx.profile_read(kind) for name, kind in (
         ("load", pkg.PROF_LOAD), ("lowres", pkg.PROF_LOWRES), ("border", pkg.PROF_BORDER),
-        ("la_intra", pkg.PROF_LA_INTRA), ("la_tile", pkg.PROF_LA_TILE), ("la_inter", pkg.PROF_LA_INTER))}
+        ("la_intra", pkg.PROF_LA_INTRA), ("la_inter", pkg.PROF_LA_INTER))}
     ctx.profile_enable(False)
     sums_np = d_sums.cpu().numpy()
 

@@ -72,6 +72,12 @@ typedef struct x264dsp_geom
     int32_t lowres_w, lowres_h, lowres_stride, lowres_plane_size, lowres_origin;
     int32_t slot_chroma_off, slot_lowres_off;
     int64_t slot_bytes;               /* bytes of one frame slot, multiple of 256 */
+    /* 8x8-tiled copies of the four padded lowres planes (the lookahead's search layout): tile (tx,ty) of
+     * the padded plane = 64 contiguous bytes (8 rows of 8 samples), tiles of a tile row back to back;
+     * sample (x,y) of plane k lives at slot_tiled_off + k*tiled_plane_size
+     *   + (((y+32)>>3) * tile_w + ((x+32)>>3)) * 64 + ((y+32)&7) * 8 + ((x+32)&7).
+     * Written by x264dsp_frame_init_lowres_dev together with the row-major planes. */
+    int32_t tile_w, tile_h, tiled_plane_size, slot_tiled_off;
 } x264dsp_geom_t;
 
 int x264dsp_geometry( int width, int height, x264dsp_geom_t *g );
@@ -152,13 +158,23 @@ int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8
                               int n_frames, void *stream );
 
 /* x264_frame_init_lowres (common/mc.c:404-456 + common/frame.c:415-421): duplicates the last
- * column/row INTO the source luma plane, builds the four half-resolution planes and pads them. */
+ * column/row INTO the source luma plane, builds the four half-resolution planes and pads them.
+ * The planes are kept in the slot's TILED form (see x264dsp_geom_t), which is what every lookahead
+ * entry point reads; x264dsp_frame_export_lowres_dev writes the reference's row-major lowres[0..3]
+ * (padding included) into the slot's lowres region when a caller wants them. */
 int x264dsp_frame_init_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
                                    int n_frames, void *stream );
 /* x264dsp_frame_load_luma_dev + x264dsp_frame_init_lowres_dev in one pass over the picture (same final
  * slot contents: luma plane N incl. the duplicated column / row, four padded lowres planes) */
 int x264dsp_frame_load_luma_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
                                         uint8_t *slots, int n_frames, void *stream );
+/* tiled -> row-major: fills the slot's lowres region (lowres[0..3] of x264_frame_t, padding included) */
+int x264dsp_frame_export_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
+                                     int n_frames, void *stream );
+/* row-major -> tiled: for a caller that has written row-major lowres planes into the slot's lowres
+ * region itself (e.g. planes computed by the reference) and wants the lookahead to use them */
+int x264dsp_frame_retile_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
+                                     int n_frames, void *stream );
 
 /* ------------------------------------------------------------------ block costs
  * x264_pixel_function_t::sad / ssd / satd  (common/pixel.c:44-102, 267-337) on n independent

@@ -44,6 +44,7 @@ void xo_frame_load_i420( const x264dsp_geom_t *g, const uint8_t *i420, uint8_t *
 void xo_frame_expand_border( const x264dsp_geom_t *g, uint8_t *slot );
 void xo_frame_filter( const x264dsp_geom_t *g, uint8_t *slot );
 void xo_frame_init_lowres( const x264dsp_geom_t *g, uint8_t *slot );
+void xo_frame_retile_lowres( const x264dsp_geom_t *g, uint8_t *slot );
 
 /* ---- pixel metrics (common/pixel.c) */
 int  xo_block_w( int size );

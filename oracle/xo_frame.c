@@ -52,6 +52,13 @@ void xo_geometry( int width, int height, x264dsp_geom_t *g )
         off = (off + 255) & ~(int64_t)255;
         g->slot_lowres_off = (int32_t)off;
         off += 4 * (int64_t)g->lowres_plane_size;
+        off = (off + 255) & ~(int64_t)255;
+        /* 8x8-tiled copies of the padded lowres planes (our own search layout, include/x264dsp_b200.h) */
+        g->tile_w = (g->lowres_w + 2*X264DSP_PADH) / 8;
+        g->tile_h = (g->lowres_h + 2*X264DSP_PADV) / 8;
+        g->tiled_plane_size = g->tile_w * g->tile_h * 64;
+        g->slot_tiled_off = (int32_t)off;
+        off += 4 * (int64_t)g->tiled_plane_size;
         g->slot_bytes = (off + 255) & ~(int64_t)255;
     }
 }
@@ -254,4 +261,21 @@ void xo_frame_init_lowres( const x264dsp_geom_t *g, uint8_t *slot )
     for( k = 0; k < 4; k++ )
         expand_border( lowres_plane( g, slot, k ), g->lowres_stride, g->lowres_w, g->lowres_h,
                        X264DSP_PADH, X264DSP_PADV, 1, 1, 1 );
+    xo_frame_retile_lowres( g, slot );
+}
+
+/* the slot's 8x8-tiled copies of the padded lowres planes (layout: include/x264dsp_b200.h; not a
+ * reference structure -- the product's search layout, mirrored so that whole slots compare) */
+void xo_frame_retile_lowres( const x264dsp_geom_t *g, uint8_t *slot )
+{
+    int k, X, Y;
+    for( k = 0; k < 4; k++ )
+    {
+        const pixel_t *src = lowres_plane( g, slot, k );
+        uint8_t *dst = slot + g->slot_tiled_off + (size_t)k * g->tiled_plane_size;
+        for( Y = 0; Y < g->tile_h * 8; Y++ )
+            for( X = 0; X < g->tile_w * 8; X++ )
+                dst[( (size_t)( Y >> 3 ) * g->tile_w + ( X >> 3 ) ) * 64 + ( Y & 7 ) * 8 + ( X & 7 )] =
+                    src[(ptrdiff_t)( Y - X264DSP_PADV ) * g->lowres_stride + X - X264DSP_PADH];
+    }
 }

@@ -33,7 +33,8 @@ class Geom(C.Structure):
         "luma_stride", "luma_plane_size", "luma_origin",
         "chroma_stride", "chroma_h", "chroma_plane_size", "chroma_origin",
         "lowres_w", "lowres_h", "lowres_stride", "lowres_plane_size", "lowres_origin",
-        "slot_chroma_off", "slot_lowres_off")] + [("slot_bytes", C.c_int64)]
+        "slot_chroma_off", "slot_lowres_off")] + [("slot_bytes", C.c_int64)] + [(n, C.c_int32) for n in (
+        "tile_w", "tile_h", "tiled_plane_size", "slot_tiled_off")]
 
 
 class MeBlock(C.Structure):

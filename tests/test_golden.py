@@ -375,6 +375,7 @@ def gpu_slots(G, pkg, ctx, tag, filtered, lowres):
         ctx.frame_filter(g, slots, n)
     if lowres:
         ctx.frame_init_lowres(g, slots, n)
+        ctx.frame_export_lowres(g, slots, n)      # row-major lowres[0..3] for the plane hashes
     ctx.sync()
     return w, h, g, n, slots
 

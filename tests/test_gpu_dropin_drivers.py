@@ -75,6 +75,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         upload(0, 0, lib.xref_frame_ptr(frame, 10), lps)
         keep_resident(frame)              # the source samples as the main encode's searches will see them
         ctx.frame_init_lowres(g, slots, 1)
+        ctx.frame_export_lowres(g, slots, 1)      # the reference wants its row-major lowres[0..3]
         ctx.sync()
         download(0, 0, lib.xref_frame_ptr(frame, 10), lps)
         download(0, g.slot_lowres_off, lib.xref_frame_ptr(frame, 12), 4 * wps)
@@ -91,6 +92,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
     def cost_cb(hv, p0, b, want_intra, mvs, costs, sums):
         upload(0, g.slot_lowres_off, lib.xref_frame_ptr(p0, 12), 4 * wps)
         upload(1, g.slot_lowres_off, lib.xref_frame_ptr(b, 12), 4 * wps)
+        ctx.frame_retile_lowres(g, slots, 2)      # the planes were written by the caller, not by init_lowres
         d_mvs = torch.zeros((1, g.mb_count, 2), dtype=torch.int16, device="cuda")
         d_costs = torch.zeros((1, g.mb_count), dtype=torch.int32, device="cuda")
         d_sums = torch.zeros((1, pkg.LA_SUMS), dtype=torch.int32, device="cuda")

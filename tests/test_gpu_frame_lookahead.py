@@ -47,9 +47,12 @@ def diff_report(a, b, g):
         elif off < g.slot_lowres_off:
             r = int(off) - g.slot_chroma_off
             regions.append(f"chroma row {r // g.chroma_stride - 16} col {r % g.chroma_stride - 32}")
-        else:
+        elif off < g.slot_tiled_off:
             k, r = divmod(int(off) - g.slot_lowres_off, g.lowres_plane_size)
             regions.append(f"lowres{k} row {r // g.lowres_stride - 32} col {r % g.lowres_stride - 32}")
+        else:
+            k, r = divmod(int(off) - g.slot_tiled_off, g.tiled_plane_size)
+            regions.append(f"tiled{k} tile {r // 64} byte {r % 64}")
     return f"{len(bad)} bytes differ, first: " + "; ".join(regions)
 
 
@@ -92,11 +95,12 @@ def test_lowres_planes_match_oracle(pkg, ctx, w, h):
     torch.cuda.synchronize()
     ctx.frame_load_i420(g, i420, slots, n)
     ctx.frame_init_lowres(g, slots, n)
+    ctx.frame_export_lowres(g, slots, n)      # the slot keeps the planes tiled; the row-major form is on request
     ctx.sync()
     want = oracle_slots(cc.oracle_geom(w, h), frames, lowres=True)
     got = slots.cpu().numpy().reshape(n, -1)
     for i in range(n):
-        assert diff_report(got[i], want[i], g) == "", "init_lowres (incl. source-plane side effect)"
+        assert diff_report(got[i], want[i], g) == "", "init_lowres (incl. source-plane side effect, tiled copies)"
 
 
 @pytest.mark.parametrize("cmp", [0, 1, 2])
@@ -195,6 +199,28 @@ def test_fused_staging_and_lowres_equals_the_two_calls(pkg, ctx, w, h):
     ctx.sync()
     diff = torch.nonzero(a != b)
     assert diff.numel() == 0, f"{diff.numel()} bytes differ, first at slot offset {int(diff[0]) % g.slot_bytes}"
+
+
+def test_lowres_export_and_import_are_inverse(pkg, ctx):
+    """row-major <-> tiled: export of the tiled planes equals the oracle's planes (above); importing those
+    planes back rebuilds the same tiles"""
+    torch = _torch()
+    w, h, n = 200, 120, 2
+    frames = [pkg.synth_frame(w, h, i) for i in range(n)]
+    g = pkg.geometry(w, h)
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, n)
+    ctx.frame_init_lowres(g, slots, n)
+    ctx.frame_export_lowres(g, slots, n)
+    ctx.sync()
+    before = slots.clone()
+    view = slots.view(n, -1)
+    view[:, g.slot_tiled_off: g.slot_tiled_off + 4 * g.tiled_plane_size] = 0
+    ctx.frame_retile_lowres(g, slots, n)
+    ctx.sync()
+    assert torch.equal(slots, before)
 
 
 def test_lookahead_batch_of_clips_both_kernels(pkg, ctx):

@@ -38,7 +38,8 @@ class Geom(C.Structure):
         "luma_stride", "luma_plane_size", "luma_origin",
         "chroma_stride", "chroma_h", "chroma_plane_size", "chroma_origin",
         "lowres_w", "lowres_h", "lowres_stride", "lowres_plane_size", "lowres_origin",
-        "slot_chroma_off", "slot_lowres_off")] + [("slot_bytes", C.c_int64)]
+        "slot_chroma_off", "slot_lowres_off")] + [("slot_bytes", C.c_int64)] + [(n, C.c_int32) for n in (
+        "tile_w", "tile_h", "tiled_plane_size", "slot_tiled_off")]
 
 
 class MeParams(C.Structure):
@@ -256,6 +257,16 @@ class Context:
         """frame_load_luma + frame_init_lowres fused (one pass over the picture)"""
         check(lib().x264dsp_frame_load_luma_lowres_dev(self._h, C.byref(g), _dp(luma_dev), _dp(slots_dev),
                                                        int(n_frames), None), "x264dsp_frame_load_luma_lowres_dev")
+
+    def frame_export_lowres(self, g, slots_dev, n_frames):
+        """tiled lowres planes -> the reference's row-major lowres[0..3] in the slot's lowres region"""
+        check(lib().x264dsp_frame_export_lowres_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),
+              "x264dsp_frame_export_lowres_dev")
+
+    def frame_retile_lowres(self, g, slots_dev, n_frames):
+        """rebuild the tiled lowres copies of slots whose row-major lowres planes were written by the caller"""
+        check(lib().x264dsp_frame_retile_lowres_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),
+              "x264dsp_frame_retile_lowres_dev")
 
     def frame_expand_border(self, g, slots_dev, n_frames):
         check(lib().x264dsp_frame_expand_border_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),

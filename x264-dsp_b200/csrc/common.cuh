@@ -32,8 +32,6 @@ struct x264dsp_ctx
     int32_t *la_icost;             // [pairs][mb_count] intra cost per block
     int32_t *la_ticket;            // work-queue counter
     size_t la_sync_cap, la_icost_cap;
-    uint8_t *la_tiled;             // [pairs][4 planes] 8x8-tiled copies of the reference lowres planes (quad kernel)
-    size_t la_tiled_cap;
     uint32_t la_epoch;
     unsigned long long *la_timing; // phase-cycle counters of the inter kernel (debug aid, normally NULL)
     int la_kernel;                 // x264dsp_lookahead_select_kernel: 0 auto, 1 warp-per-row, 2 quad-row

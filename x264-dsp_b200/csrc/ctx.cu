@@ -61,6 +61,12 @@ extern "C" int x264dsp_geometry( int width, int height, x264dsp_geom_t *g )
     off = ( off + 255 ) / 256 * 256;
     g->slot_lowres_off = (int32_t)off;
     off += 4 * wp;
+    off = ( off + 255 ) / 256 * 256;
+    g->tile_w = ( g->lowres_w + 2 * X264DSP_PADH ) / 8;
+    g->tile_h = ( g->lowres_h + 2 * X264DSP_PADV ) / 8;
+    g->tiled_plane_size = g->tile_w * g->tile_h * 64;
+    g->slot_tiled_off = (int32_t)off;
+    off += 4 * (int64_t)g->tiled_plane_size;
     g->slot_bytes = ( off + 255 ) / 256 * 256;
     return 0;
 }
@@ -256,7 +262,6 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     cudaFree( ctx->cost_mv_store );
     cudaFree( ctx->la_sync );
     cudaFree( ctx->la_icost );
-    cudaFree( ctx->la_tiled );
     cudaFree( ctx->la_ticket );
     cudaFree( ctx->stage_dev );
     cudaFree( ctx->clip_slots );

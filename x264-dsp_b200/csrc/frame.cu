@@ -217,37 +217,25 @@ __device__ __forceinline__ void xd_lowres_src( const uint8_t *base, int pitch, i
     e = p[min( x0 + 16, w - 1 )];
 }
 
-// one 8-sample chunk of the four lowres planes at row y (may be a padding row), with the 32-sample
-// side bands when the chunk is the first / last of its row (x264_frame_expand_border_lowres,
-// frame.c:415-421: replicate padding of 32 on every side)
-__device__ __forceinline__ void xd_lowres_store( uint8_t *plane0, size_t plane_size, int stride, int y, int t,
-                                                 bool first, bool last, const uint2 o[4] )
+// one whole tile (8 rows of 8 samples, 64 contiguous bytes) of the tiled copy
+__device__ __forceinline__ void xd_tile_store( uint8_t *tile, const uint2 rows[8] )
 {
+    uint4 *d = (uint4 *)tile;
 #pragma unroll
-    for( int k = 0; k < 4; k++ )
-    {
-        uint8_t *row = plane0 + k * plane_size + (int64_t)y * stride;
-        *(uint2 *)( row + 8 * t ) = o[k];
-        if( first )
-        {
-            const uint32_t v = ( o[k].x & 255u ) * 0x01010101u;
-#pragma unroll
-            for( int c = 1; c <= X264DSP_PADH / 8; c++ )
-                *(uint2 *)( row - 8 * c ) = make_uint2( v, v );
-        }
-        if( last )
-        {
-            const uint32_t v = ( o[k].y >> 24 ) * 0x01010101u;
-#pragma unroll
-            for( int c = 1; c <= X264DSP_PADH / 8; c++ )
-                *(uint2 *)( row + 8 * ( t + c ) ) = make_uint2( v, v );
-        }
-    }
+    for( int i = 0; i < 4; i++ )
+        d[i] = make_uint4( rows[2 * i].x, rows[2 * i].y, rows[2 * i + 1].x, rows[2 * i + 1].y );
 }
 
-// RAW = false: x264_frame_init_lowres on a slot whose luma plane is loaded (planes + their padding).
-// RAW = true : picture staging fused in -- the thread also writes the two luma rows it has read into
-//              the slot's plane N, which saves re-reading 2 MB per 1080p frame.
+// The four half-resolution planes are kept in the slot in TILED form only (the layout the lookahead
+// searches in; x264dsp_frame_export_lowres_dev produces the reference's row-major planes on request):
+// writing both forms costs 2.5 MB more per 1080p frame, and this kernel is bound by HBM writes.
+// Thread = one 8-sample column chunk of an 8-row band of the lowres planes, i.e. exactly one 8x8 tile of
+// each of the four planes: the thread walks the band's 17 source rows once (16-byte loads, every row
+// loaded once) and stores the four finished tiles as 64-byte units.  Edge threads also write the
+// padding tiles (x264_frame_expand_border_lowres, frame.c:415-421: replicate 32 samples on every side).
+// RAW = false: x264_frame_init_lowres on a slot whose luma plane is loaded.
+// RAW = true : picture staging fused in -- the thread also writes the luma rows it has read into the
+//              slot's plane N, which saves re-reading 2 MB per 1080p frame.
 template<bool RAW>
 __global__ void __launch_bounds__( 128 )
 xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *__restrict__ raw )
@@ -255,56 +243,109 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
     uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
     uint8_t *plane = slot + g.luma_origin;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    const int band = blockIdx.y;
     const int chunks = g.lowres_w >> 3;
     if( t >= chunks )
         return;
     const int ls = g.luma_stride;
     const uint8_t *src = RAW ? raw + blockIdx.z * (size_t)g.width * g.height : plane;
     const int pitch = RAW ? g.width : ls, sw = RAW ? g.width : g.luma_w, sh = RAW ? g.height : g.luma_h;
-    const int r0 = 2 * y, r1 = 2 * y + 1, r2 = 2 * y + 2;
+    uint8_t *tl = slot + g.slot_tiled_off;
+    const size_t tps = (size_t)g.tiled_plane_size;
+    const bool first = t == 0, last = t == chunks - 1;
+    const int n_bands = g.lowres_h >> 3;
+
+    uint2 T[4][8];                                   // the four tiles, row by row
     uint4 a, b, c;
     uint32_t ea, eb, ec;
-    xd_lowres_src<RAW>( src, pitch, sw, sh, r0, 16 * t, a, ea );
-    xd_lowres_src<RAW>( src, pitch, sw, sh, r1, 16 * t, b, eb );
-    xd_lowres_src<RAW>( src, pitch, sw, sh, r2, 16 * t, c, ec );
-
-    const uint4 ab = make_uint4( xd_avg4( a.x, b.x ), xd_avg4( a.y, b.y ), xd_avg4( a.z, b.z ), xd_avg4( a.w, b.w ) );
-    const uint4 bc = make_uint4( xd_avg4( b.x, c.x ), xd_avg4( b.y, c.y ), xd_avg4( b.z, c.z ), xd_avg4( b.w, c.w ) );
-    const uint32_t eab = ( ea + eb + 1 ) >> 1, ebc = ( eb + ec + 1 ) >> 1;
-
-    uint2 o[4];
-    xd_lowres_line( ab, eab, o[0], o[1] );
-    xd_lowres_line( bc, ebc, o[2], o[3] );
-
-    uint8_t *lw = slot + g.slot_lowres_off + g.lowres_origin;
-    const bool first = t == 0, last = t == chunks - 1;
-    xd_lowres_store( lw, (size_t)g.lowres_plane_size, g.lowres_stride, y, t, first, last, o );
-    if( y == 0 )
-        for( int r = 1; r <= X264DSP_PADV; r++ )
-            xd_lowres_store( lw, (size_t)g.lowres_plane_size, g.lowres_stride, -r, t, first, last, o );
-    if( y == g.lowres_h - 1 )
-        for( int r = 1; r <= X264DSP_PADV; r++ )
-            xd_lowres_store( lw, (size_t)g.lowres_plane_size, g.lowres_stride, y + r, t, first, last, o );
-
-    if( RAW )
+    xd_lowres_src<RAW>( src, pitch, sw, sh, 16 * band, 16 * t, a, ea );
+#pragma unroll
+    for( int r = 0; r < 8; r++ )
     {
-        *(uint4 *)( plane + (size_t)r0 * ls + 16 * t ) = a;
-        *(uint4 *)( plane + (size_t)r1 * ls + 16 * t ) = b;
-    }
-    // side effect of x264_frame_init_lowres on the source plane: column luma_w of every row and
-    // row luma_h (luma_w + 1 bytes) duplicate their neighbours
-    if( last )
-    {
-        plane[(size_t)r0 * ls + g.luma_w] = (uint8_t)ea;
-        plane[(size_t)r1 * ls + g.luma_w] = (uint8_t)eb;
-    }
-    if( y == g.lowres_h - 1 )
-    {
-        // b is the last picture row here (r1 == luma_h - 1)
-        *(uint4 *)( plane + (size_t)g.luma_h * ls + 16 * t ) = b;
+        const int y = 8 * band + r;
+        const int r0 = 2 * y, r1 = 2 * y + 1;
+        xd_lowres_src<RAW>( src, pitch, sw, sh, r1, 16 * t, b, eb );
+        xd_lowres_src<RAW>( src, pitch, sw, sh, r1 + 1, 16 * t, c, ec );
+        const uint4 ab = make_uint4( xd_avg4( a.x, b.x ), xd_avg4( a.y, b.y ), xd_avg4( a.z, b.z ), xd_avg4( a.w, b.w ) );
+        const uint4 bc = make_uint4( xd_avg4( b.x, c.x ), xd_avg4( b.y, c.y ), xd_avg4( b.z, c.z ), xd_avg4( b.w, c.w ) );
+        const uint32_t eab = ( ea + eb + 1 ) >> 1, ebc = ( eb + ec + 1 ) >> 1;
+        uint2 o[4];
+        xd_lowres_line( ab, eab, o[0], o[1] );
+        xd_lowres_line( bc, ebc, o[2], o[3] );
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+            T[k][r] = o[k];
+
+        if( RAW )
+        {
+            *(uint4 *)( plane + (size_t)r0 * ls + 16 * t ) = a;
+            *(uint4 *)( plane + (size_t)r1 * ls + 16 * t ) = b;
+        }
+        // side effect of x264_frame_init_lowres on the source plane: column luma_w of every row and
+        // row luma_h (luma_w + 1 bytes) duplicate their neighbours
         if( last )
-            plane[(size_t)g.luma_h * ls + g.luma_w] = (uint8_t)eb;
+        {
+            plane[(size_t)r0 * ls + g.luma_w] = (uint8_t)ea;
+            plane[(size_t)r1 * ls + g.luma_w] = (uint8_t)eb;
+        }
+        if( y == g.lowres_h - 1 )
+        {
+            // b is the last picture row here (r1 == luma_h - 1)
+            *(uint4 *)( plane + (size_t)g.luma_h * ls + 16 * t ) = b;
+            if( last )
+                plane[(size_t)g.luma_h * ls + g.luma_w] = (uint8_t)eb;
+        }
+        a = c;
+        ea = ec;
+    }
+
+    // ---- the tiled copies: this thread's tile is (tx, ty) = (t + 4, band + 4) of each padded plane
+    const int tx = t + X264DSP_PADH / 8, ty = band + X264DSP_PADV / 8;
+#pragma unroll
+    for( int k = 0; k < 4; k++ )
+    {
+        uint8_t *tp = tl + k * tps;
+        xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx ) * 64, T[k] );
+        uint2 L[8], R[8];                            // side padding: the first / last sample of every row
+#pragma unroll
+        for( int r = 0; r < 8; r++ )
+        {
+            const uint32_t vl = ( T[k][r].x & 255u ) * 0x01010101u, vr = ( T[k][r].y >> 24 ) * 0x01010101u;
+            L[r] = make_uint2( vl, vl );
+            R[r] = make_uint2( vr, vr );
+        }
+        if( first )
+            for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
+                xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx - cc ) * 64, L );
+        if( last )
+            for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
+                xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx + cc ) * 64, R );
+        // top / bottom padding: four tile rows that repeat the picture's first / last row
+#pragma unroll
+        for( int side = 0; side < 2; side++ )
+        {
+            if( side == 0 ? band != 0 : band != n_bands - 1 )
+                continue;
+            uint2 E[8], EL[8], ER[8];
+#pragma unroll
+            for( int r = 0; r < 8; r++ )
+            {
+                E[r] = side == 0 ? T[k][0] : T[k][7];
+                EL[r] = side == 0 ? L[0] : L[7];
+                ER[r] = side == 0 ? R[0] : R[7];
+            }
+            for( int rr = 1; rr <= X264DSP_PADV / 8; rr++ )
+            {
+                const int tyy = side == 0 ? ty - rr : ty + rr;
+                xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx ) * 64, E );
+                if( first )
+                    for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
+                        xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx - cc ) * 64, EL );
+                if( last )
+                    for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
+                        xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx + cc ) * 64, ER );
+            }
+        }
     }
 }
 
@@ -580,10 +621,80 @@ extern "C" int x264dsp_frame_expand_border_dev( x264dsp_ctx_t *ctx, const x264ds
     return xd_launch_border( ctx, chroma, slots, g->slot_bytes, n_frames, 1, 0, s );
 }
 
+// row-major padded lowres planes -> tiled copies (for slots whose lowres planes the caller wrote).
+// Thread = one 16-byte row chunk, i.e. one row of two neighbouring tiles; eight consecutive threads fill
+// the tile pair (128 contiguous bytes out), a warp covers four pairs (64 contiguous bytes per row in).
+__global__ void __launch_bounds__( 256 )
+xd_retile_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots )
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tp = t >> 3, row = t & 7;
+    const int pairs_per_row = ( g.tile_w + 1 ) >> 1;         // tile_w = mb_w + 8 may be odd: the last pair is half
+    if( tp >= pairs_per_row * g.tile_h )
+        return;
+    uint8_t *slot = slots + blockIdx.y * (size_t)g.slot_bytes;
+    const int pl = blockIdx.z;
+    const int ty = tp / pairs_per_row, tx = ( tp - ty * pairs_per_row ) * 2;
+    const uint8_t *src = slot + g.slot_lowres_off + (size_t)pl * g.lowres_plane_size + g.lowres_origin
+                       + (int64_t)( ty * 8 + row - X264DSP_PADV ) * g.lowres_stride + tx * 8 - X264DSP_PADH;
+    uint8_t *dst = slot + g.slot_tiled_off + (size_t)pl * g.tiled_plane_size + ( (size_t)ty * g.tile_w + tx ) * 64 + row * 8;
+    const uint2 lo = *(const uint2 *)src;
+    *(uint2 *)dst = lo;
+    if( tx + 1 < g.tile_w )
+        *(uint2 *)( dst + 64 ) = *(const uint2 *)( src + 8 );
+}
+
+// tiled copies -> the reference's row-major padded lowres planes (lowres[0..3] incl. their 32-sample
+// padding) in the slot's lowres region.  Thread = one 16-byte row-major chunk = one row of two tiles.
+__global__ void __launch_bounds__( 256 )
+xd_export_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots )
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tp = t >> 3, row = t & 7;
+    const int pairs_per_row = ( g.tile_w + 1 ) >> 1;
+    if( tp >= pairs_per_row * g.tile_h )
+        return;
+    uint8_t *slot = slots + blockIdx.y * (size_t)g.slot_bytes;
+    const int pl = blockIdx.z;
+    const int ty = tp / pairs_per_row, tx = ( tp - ty * pairs_per_row ) * 2;
+    uint8_t *dst = slot + g.slot_lowres_off + (size_t)pl * g.lowres_plane_size + g.lowres_origin
+                 + (int64_t)( ty * 8 + row - X264DSP_PADV ) * g.lowres_stride + tx * 8 - X264DSP_PADH;
+    const uint8_t *src = slot + g.slot_tiled_off + (size_t)pl * g.tiled_plane_size + ( (size_t)ty * g.tile_w + tx ) * 64 + row * 8;
+    *(uint2 *)dst = *(const uint2 *)src;
+    if( tx + 1 < g.tile_w )
+        *(uint2 *)( dst + 8 ) = *(const uint2 *)( src + 64 );
+}
+
+extern "C" int x264dsp_frame_export_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
+                                                 int n_frames, void *stream )
+{
+    if( !ctx || !g || !slots || n_frames <= 0 || n_frames > 65535 )
+        return X264DSP_E_ARG;
+    cudaStream_t s = xd_stream( ctx, stream );
+    const int chunks = ( ( g->tile_w + 1 ) / 2 ) * g->tile_h * 8;
+    xd_export_lowres_kernel<<<dim3( ( chunks + 255 ) / 256, n_frames, 4 ), 256, 0, s>>>( *g, slots );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
+}
+
+extern "C" int x264dsp_frame_retile_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
+                                                 int n_frames, void *stream )
+{
+    if( !ctx || !g || !slots || n_frames <= 0 || n_frames > 65535 )
+        return X264DSP_E_ARG;
+    cudaStream_t s = xd_stream( ctx, stream );
+    const int chunks = ( ( g->tile_w + 1 ) / 2 ) * g->tile_h * 8;
+    xd_retile_kernel<<<dim3( ( chunks + 255 ) / 256, n_frames, 4 ), 256, 0, s>>>( *g, slots );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
+}
+
 static int xd_launch_lowres( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots, const uint8_t *raw,
                              int n_frames, cudaStream_t s )
 {
-    dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h, n_frames );
+    dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h >> 3, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_LOWRES, s );
     if( raw )
         xd_lowres_kernel<true><<<grid, 128, 0, s>>>( *g, slots, raw );

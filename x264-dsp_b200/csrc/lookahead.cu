@@ -43,8 +43,6 @@ struct xd_la_args
     uint32_t epoch;
     int me_range;
     int slack;                          // multi-row kernel: extra blocks a unit stays behind the one below
-    const uint8_t *tiled;               // multi-row kernel: [pair] tiled reference plane N
-    int tile_w, tile_h;                 // tiles per row / column of a padded lowres plane
     unsigned long long *timing;         // optional phase-cycle counters (x264dsp_debug_lookahead_timing)
 };
 
@@ -86,6 +84,25 @@ __device__ __forceinline__ int xd_satd4x4_words( const uint32_t a[4], const uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// The lookahead reads the lowres planes through the slot's 8x8-TILED copies (x264dsp_geom_t: tile
+// (tx,ty) of the padded plane = 64 contiguous bytes, tiles of a tile row back to back).  A lane reads a
+// pixel row of a block; in a row-major plane the rows of a block are one cache line each and the L1 data
+// pipe saturates (ncu: 91 % of peak wavefronts at 4 % DRAM), tiled they share one or two lines.
+//
+// 8 pixels at padded coordinates (X,Y) = (x+32, y+32) of one tiled plane: the row chunk of the tile
+// holding X and of its right-hand neighbour (two aligned 8-byte loads, 64 bytes apart), then a funnel
+// shift by the position inside the chunk (shf.r.wrap takes the shift modulo 32)
+__device__ __forceinline__ uint2 xd_tl8( const uint8_t *tplane, int tw, int X, int Y )
+{
+    const uint2 *w = (const uint2 *)( tplane + ( ( ( Y >> 3 ) * tw + ( X >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 ) );
+    const uint2 lo = __ldg( w ), hi = __ldg( w + 8 );
+    const uint32_t sh = (uint32_t)X << 3;
+    const bool up = ( X & 4 ) != 0;
+    const uint32_t w0 = up ? lo.y : lo.x, w1 = up ? hi.x : lo.y, w2 = up ? hi.y : hi.x;
+    return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+}
+
+// ---------------------------------------------------------------------------------------------
 // intra estimate: x264_intra_satd_x3_8x8c on the SOURCE lowres plane (slicetype.c:145-180).
 // Hadamard is linear, so satd(pred - src) is evaluated from ONE transform of the source 4x4 and
 // the (sparse) transforms of the three predictions: DC touches coefficient (0,0), V the first row
@@ -105,18 +122,19 @@ xd_la_intra_kernel( xd_la_args A )
     {
         const int bx = 1 + i % ( W - 2 );
         by = 1 + i / ( W - 2 );
-        const int ls = g.lowres_stride;
-        const uint8_t *src = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin
-                           + ( (size_t)by * ls + bx ) * 8;
+        // block (bx,by) is tile (bx+4, by+4) of the tiled plane N; its left neighbours are the last
+        // column of the tile before it, its top neighbours the last row of the tile above
+        const uint8_t *src = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_tiled_off
+                           + ( (size_t)( by + 4 ) * g.tile_w + bx + 4 ) * 64;
         uint2 row[8];
         uint32_t left[8];
 #pragma unroll
         for( int r = 0; r < 8; r++ )
         {
-            row[r] = __ldg( (const uint2 *)( src + (size_t)r * ls ) );
-            left[r] = __ldg( src + (size_t)r * ls - 1 );
+            row[r] = __ldg( (const uint2 *)( src + r * 8 ) );
+            left[r] = __ldg( src - 64 + r * 8 + 7 );
         }
-        const uint2 top = __ldg( (const uint2 *)( src - ls ) );
+        const uint2 top = __ldg( (const uint2 *)( src - (size_t)g.tile_w * 64 + 56 ) );
         int tp[8];
 #pragma unroll
         for( int k = 0; k < 4; k++ )
@@ -203,9 +221,9 @@ xd_la_intra_kernel( xd_la_args A )
 
 struct xd_la_block
 {
-    const uint8_t *ref;       // reference lowres plane N at the block origin; planes H,V,HV follow
-    size_t plane_size;
-    int stride;
+    const uint8_t *tref;      // tiled planes N, H, V, HV of the reference frame
+    int tplane, tw;           // bytes per tiled plane, tiles per tile row
+    int X0, Y0;               // padded coordinates of the block origin
     uint2 fenc;               // this lane's source row (row = lane & 7)
     uint32_t fq[4];           // rows of the 4x4 quadrant (lane & 3) of the source block
     int mvpx, mvpy;
@@ -222,13 +240,11 @@ __device__ __forceinline__ int xd_la_bits( const xd_la_block &B, int qx, int qy 
 __device__ __forceinline__ uint2 xd_la_fetch( const xd_la_block &B, int qx, int qy, int row )
 {
     const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
-    const int64_t base = (int64_t)( ( qy >> 2 ) + row ) * B.stride + ( qx >> 2 );
-    const uint8_t *pa = B.ref + (size_t)xd_qpel_plane_a( phase ) * B.plane_size + base + ( fy == 3 ? B.stride : 0 );
-    uint2 a = xd_load8_unaligned( pa );
+    const int X = B.X0 + ( qx >> 2 ), Y = B.Y0 + ( qy >> 2 ) + row;
+    uint2 a = xd_tl8( B.tref + xd_qpel_plane_a( phase ) * B.tplane, B.tw, X, Y + ( fy == 3 ? 1 : 0 ) );
     if( phase & 5 )
     {
-        const uint8_t *pb = B.ref + (size_t)xd_qpel_plane_b( phase ) * B.plane_size + base + ( fx == 3 ? 1 : 0 );
-        const uint2 b = xd_load8_unaligned( pb );
+        const uint2 b = xd_tl8( B.tref + xd_qpel_plane_b( phase ) * B.tplane, B.tw, X + ( fx == 3 ? 1 : 0 ), Y );
         a.x = xd_avg4( a.x, b.x );
         a.y = xd_avg4( a.y, b.y );
     }
@@ -272,10 +288,10 @@ __device__ __forceinline__ int xd_la_partial( const xd_la_block &B, int qx, int 
 __device__ __forceinline__ uint32_t xd_la_fetch4( const xd_la_block &B, int qx, int qy, int x, int y )
 {
     const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
-    const int64_t base = (int64_t)( ( qy >> 2 ) + y ) * B.stride + ( qx >> 2 ) + x;
-    uint32_t a = xd_load4_unaligned( B.ref + (size_t)xd_qpel_plane_a( phase ) * B.plane_size + base + ( fy == 3 ? B.stride : 0 ) );
+    const int X = B.X0 + ( qx >> 2 ) + x, Y = B.Y0 + ( qy >> 2 ) + y;
+    uint32_t a = xd_tl8( B.tref + xd_qpel_plane_a( phase ) * B.tplane, B.tw, X, Y + ( fy == 3 ? 1 : 0 ) ).x;
     if( phase & 5 )
-        a = xd_avg4( a, xd_load4_unaligned( B.ref + (size_t)xd_qpel_plane_b( phase ) * B.plane_size + base + ( fx == 3 ? 1 : 0 ) ) );
+        a = xd_avg4( a, xd_tl8( B.tref + xd_qpel_plane_b( phase ) * B.tplane, B.tw, X + ( fx == 3 ? 1 : 0 ), Y ).x );
     return a;
 }
 
@@ -370,8 +386,9 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         const int row_idx = ticket / n_inter;
         const int pair = inter_pairs[ticket - row_idx * n_inter];
         const int by = H - 2 - row_idx;
-        const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
-        const uint8_t *ref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
+        // the source block (bx,by) is tile (bx+4, by+4) of the current frame's tiled plane N
+        const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_tiled_off
+                           + ( (size_t)( by + 4 ) * g.tile_w + 4 ) * 64;
         unsigned long long *sync_row = A.sync + (size_t)pair * g.mb_count + (size_t)by * W;
         const unsigned long long *sync_below = sync_row + W;
         const bool has_below = by < H - 2;
@@ -382,8 +399,10 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         const int sminy = ( miny - 8 ) << 2, smaxy = ( maxy + 8 ) << 2;
 
         xd_la_block B;
-        B.plane_size = (size_t)g.lowres_plane_size;
-        B.stride = ls;
+        B.tref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_tiled_off;
+        B.tplane = g.tiled_plane_size;
+        B.tw = g.tile_w;
+        B.X0 = B.Y0 = 32;
         B.cost_mv = A.cost_mv;
         B.sad_evals = 0;
         B.satd_evals = 0;
@@ -403,17 +422,17 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         // The source block, its SATD quadrant rows and the block's intra cost do not depend on any
         // search result: they are fetched one block ahead so that their L2 / HBM latency overlaps
         // the previous block's search instead of opening every block with a stall.
-        const int fq_off = ( ( ( lane & 3 ) >> 1 ) * 4 ) * ls + ( lane & 1 ) * 4;
+        const int fq_off = ( ( ( lane & 3 ) >> 1 ) * 4 ) * 8 + ( lane & 1 ) * 4;      // inside the 64-byte tile
         const int32_t *icost_row = A.icost + (size_t)pair * g.mb_count + (size_t)by * W;
         uint2 nx_fenc;
         uint32_t nx_fq[4];
         int nx_ic = 0;
         {
-            const size_t pel0 = ( (size_t)by * ls + ( W - 2 ) ) * 8;
-            nx_fenc = __ldg( (const uint2 *)( cur + pel0 + (size_t)( lane & 7 ) * ls ) );
+            const size_t pel0 = (size_t)( W - 2 ) * 64;
+            nx_fenc = __ldg( (const uint2 *)( cur + pel0 + ( lane & 7 ) * 8 ) );
 #pragma unroll
             for( int r = 0; r < 4; r++ )
-                nx_fq[r] = __ldg( (const uint32_t *)( cur + pel0 + fq_off + (size_t)r * ls ) );
+                nx_fq[r] = __ldg( (const uint32_t *)( cur + pel0 + fq_off + r * 8 ) );
             if( want_intra )
                 nx_ic = icost_row[W - 2];
         }
@@ -430,8 +449,9 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 pending = xd_ld_sync( sync_below + ( bx - 2 ) );
             LA_TICK( LA_T_WAIT );
 
-            const size_t pel = ( (size_t)by * ls + bx ) * 8;
-            B.ref = ref + pel;
+            const size_t pel = (size_t)bx * 64;
+            B.X0 = 8 * bx + 32;
+            B.Y0 = 8 * by + 32;
             B.fenc = nx_fenc;
 #pragma unroll
             for( int r = 0; r < 4; r++ )
@@ -439,10 +459,10 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             const int ic = nx_ic;
             if( bx > 1 )
             {
-                nx_fenc = __ldg( (const uint2 *)( cur + pel - 8 + (size_t)( lane & 7 ) * ls ) );
+                nx_fenc = __ldg( (const uint2 *)( cur + pel - 64 + ( lane & 7 ) * 8 ) );
 #pragma unroll
                 for( int r = 0; r < 4; r++ )
-                    nx_fq[r] = __ldg( (const uint32_t *)( cur + pel - 8 + fq_off + (size_t)r * ls ) );
+                    nx_fq[r] = __ldg( (const uint32_t *)( cur + pel - 64 + fq_off + r * 8 ) );
                 if( want_intra )
                     nx_ic = icost_row[bx - 1];
             }
@@ -640,7 +660,7 @@ xd_la_inter_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
 // of a tile row back to back, built per launch by xd_la_tile_kernel).  With lane = pixel row(s), the
 // lanes of a block read different rows: in the row-major plane that is one cache line per row and the
 // L1 data pipe saturates (ncu: 91 % of peak wavefronts, DRAM 4 %); tiled, the same rows sit in one or
-// two lines.  Sub-pel positions (a quarter of the fetches) read the row-major planes H, V, HV.
+// two lines.
 #define LQ_FULL 0xffffffffu
 
 // 8 consecutive pixels at an arbitrary byte address of a row-major plane: two aligned 8-byte loads
@@ -686,30 +706,6 @@ __device__ __forceinline__ uint32_t xd_lq_abs2( uint32_t a )
     return ( a + s ) ^ s;
 }
 
-// 8x8-tiled copy of the padded lowres plane N of every reference frame of the launch (the full-pel
-// search, three quarters of all fetches, reads only that plane).  Thread = one 16-byte row chunk, i.e.
-// one row of two neighbouring tiles; eight consecutive threads fill the tile pair (128 contiguous
-// bytes out), a warp covers four pairs (64 contiguous bytes per source row in).
-__global__ void __launch_bounds__( 256 )
-xd_la_tile_kernel( xd_la_args A, const int32_t *inter_pairs, uint8_t *tiled )
-{
-    const x264dsp_geom_t &g = A.g;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tp = t >> 3, row = t & 7;                     // tile pair, row inside the tiles
-    const int pairs_per_row = ( A.tile_w + 1 ) >> 1;        // tile_w = mb_w + 8 may be odd: the last pair is half
-    if( tp >= pairs_per_row * A.tile_h )
-        return;
-    const int pair = inter_pairs[blockIdx.y];
-    const int ty = tp / pairs_per_row, tx = ( tp - ty * pairs_per_row ) * 2;
-    const uint8_t *src = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin
-                       + (int64_t)( ty * 8 + row - 32 ) * g.lowres_stride + tx * 8 - 32;
-    uint8_t *dst = tiled + (size_t)pair * ( (size_t)A.tile_w * A.tile_h * 64 ) + ( (size_t)ty * A.tile_w + tx ) * 64 + row * 8;
-    const uint4 v = __ldg( (const uint4 *)src );
-    *(uint2 *)dst = make_uint2( v.x, v.y );
-    if( tx + 1 < A.tile_w )
-        *(uint2 *)( dst + 64 ) = make_uint2( v.z, v.w );
-}
-
 // ---------------------------------------------------------------------------------------------
 // LPB lanes per block (8: one pixel row per lane, four block rows per warp; 4: two pixel rows per
 // lane, EIGHT block rows per warp).  Everything that is uniform inside a group --
@@ -719,11 +715,10 @@ xd_la_tile_kernel( xd_la_args A, const int32_t *inter_pairs, uint8_t *tiled )
 template<int RPL>
 struct xd_lm_block
 {
-    const uint8_t *tref;      // tiled plane N of the reference frame
+    const uint8_t *tref;      // tiled planes N, H, V, HV of the reference frame (in its slot)
+    int tplane;               // bytes per tiled plane
     int tw;                   // tiles per tile row
     int X0, Y0;               // padded coordinates (x+32, y+32) of this lane's FIRST row of the block origin
-    const uint8_t *rowp;      // row-major plane N at that row; planes H,V,HV follow
-    int plane_size, stride;
     uint2 fenc[RPL];          // this lane's source rows
     uint32_t fw[RPL][4];      // the same rows as fw[k] = p[k] | p[k+4] << 16
     int mvpx, mvpy;
@@ -751,11 +746,11 @@ __device__ __forceinline__ uint2 xd_lm_assemble( uint2 lo, uint2 hi, uint32_t sh
     return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
 }
 
-// the lane's RPL rows, 8 pixels each, at padded coordinates (X,Y) of the tiled plane N
+// the lane's RPL rows, 8 pixels each, at padded coordinates (X,Y) of the tiled plane at byte offset poff
 template<int RPL>
-__device__ __forceinline__ void xd_lm_tile( const xd_lm_block<RPL> &B, int X, int Y, uint2 out[RPL] )
+__device__ __forceinline__ void xd_lm_tile( const xd_lm_block<RPL> &B, int poff, int X, int Y, uint2 out[RPL] )
 {
-    const int off = ( ( ( Y >> 3 ) * B.tw + ( X >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 );
+    const int off = poff + ( ( ( Y >> 3 ) * B.tw + ( X >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 );
     const uint32_t sh = (uint32_t)X << 3;
     const bool up = ( X & 4 ) != 0;
     const uint2 *w = (const uint2 *)( B.tref + off );
@@ -775,25 +770,17 @@ template<int RPL>
 __device__ __forceinline__ void xd_lm_fetch( const xd_lm_block<RPL> &B, int qx, int qy, uint2 out[RPL] )
 {
     const int fx = qx & 3, fy = qy & 3, phase = fy * 4 + fx;
-    if( !phase )
-    {
-        xd_lm_tile<RPL>( B, B.X0 + ( qx >> 2 ), B.Y0 + ( qy >> 2 ), out );
-        return;
-    }
-    const int off = ( qy >> 2 ) * B.stride + ( qx >> 2 );
-    const int offa = off + xd_qpel_plane_a( phase ) * B.plane_size + ( fy == 3 ? B.stride : 0 );
-    const int offb = off + xd_qpel_plane_b( phase ) * B.plane_size + ( fx == 3 ? 1 : 0 );
-#pragma unroll
-    for( int j = 0; j < RPL; j++ )
-        out[j] = xd_lq_load8( B.rowp + ( offa + j * B.stride ) );
+    const int X = B.X0 + ( qx >> 2 ), Y = B.Y0 + ( qy >> 2 );
+    xd_lm_tile<RPL>( B, xd_qpel_plane_a( phase ) * B.tplane, X, Y + ( fy == 3 ? 1 : 0 ), out );
     if( phase & 5 )
     {
+        uint2 b[RPL];
+        xd_lm_tile<RPL>( B, xd_qpel_plane_b( phase ) * B.tplane, X + ( fx == 3 ? 1 : 0 ), Y, b );
 #pragma unroll
         for( int j = 0; j < RPL; j++ )
         {
-            const uint2 b = xd_lq_load8( B.rowp + ( offb + j * B.stride ) );
-            out[j].x = xd_avg4( out[j].x, b.x );
-            out[j].y = xd_avg4( out[j].y, b.y );
+            out[j].x = xd_avg4( out[j].x, b[j].x );
+            out[j].y = xd_avg4( out[j].y, b[j].y );
         }
     }
 }
@@ -812,7 +799,7 @@ template<int RPL>
 __device__ __forceinline__ uint32_t xd_lm_sad_fpel( const xd_lm_block<RPL> &B, int mx, int my )
 {
     uint2 p[RPL];
-    xd_lm_tile<RPL>( B, B.X0 + mx, B.Y0 + my, p );
+    xd_lm_tile<RPL>( B, 0, B.X0 + mx, B.Y0 + my, p );
     return xd_lm_sad<RPL>( B, p );
 }
 
@@ -910,8 +897,10 @@ xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         const bool row_ok = sub < nrows;
         const bool has_below = unit > 0;
         const bool is_top = sub == nrows - 1;
-        const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
-        const uint8_t *ref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_lowres_off + g.lowres_origin;
+        // the source block (bx,by) is exactly tile (bx+4, by+4) of the current frame's tiled plane N:
+        // 64 contiguous bytes, this lane's rows at q*RPL*8
+        const uint8_t *cur = A.slots + (size_t)A.b[pair] * g.slot_bytes + g.slot_tiled_off
+                           + ( (size_t)( by + 4 ) * g.tile_w + 4 ) * 64 + q * RPL * 8;
         unsigned long long *sync_row = A.sync + (size_t)pair * g.mb_count + (size_t)by * W;
         const unsigned long long *sync_below = A.sync + (size_t)pair * g.mb_count + (size_t)( by0 + 1 ) * W;
         const bool want_intra = A.want_intra[pair] != 0;
@@ -922,11 +911,9 @@ xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         const int sminy = ( miny - 8 ) << 2, smaxy = ( maxy + 8 ) << 2;
 
         xd_lm_block<RPL> B;
-        B.tw = A.tile_w;
-        B.tref = A.tiled + (size_t)pair * ( (size_t)A.tile_w * A.tile_h * 64 );
-        B.rowp = ref;
-        B.plane_size = g.lowres_plane_size;
-        B.stride = ls;
+        B.tw = g.tile_w;
+        B.tplane = g.tiled_plane_size;
+        B.tref = A.slots + (size_t)A.p0[pair] * g.slot_bytes + g.slot_tiled_off;
         B.X0 = B.Y0 = 32;
         B.cost_mv = A.cost_mv;
         B.mvpx = B.mvpy = 0;
@@ -959,7 +946,7 @@ xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
         {
 #pragma unroll
             for( int j = 0; j < RPL; j++ )
-                nx_fenc[j] = __ldg( (const uint2 *)( cur + ( (size_t)by * ls + ( W - 2 ) ) * 8 + (size_t)( q * RPL + j ) * ls ) );
+                nx_fenc[j] = __ldg( (const uint2 *)( cur + (size_t)( W - 2 ) * 64 + j * 8 ) );
             if( want_intra )
                 nx_ic = icost_row[W - 2];
         }
@@ -993,8 +980,6 @@ xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
             int minx = 0, maxx = 0;
             if( act )
             {
-                const size_t pel = ( (size_t)by * ls + bx ) * 8;
-                B.rowp = ref + pel + ( q * RPL ) * ls;
                 B.X0 = 8 * bx + 32;
                 B.Y0 = 8 * by + q * RPL + 32;
                 ic = nx_ic;
@@ -1005,7 +990,7 @@ xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 {
 #pragma unroll
                     for( int j = 0; j < RPL; j++ )
-                        nx_fenc[j] = __ldg( (const uint2 *)( cur + pel - 8 + (size_t)( q * RPL + j ) * ls ) );
+                        nx_fenc[j] = __ldg( (const uint2 *)( cur + (size_t)( bx - 1 ) * 64 + j * 8 ) );
                     if( want_intra )
                         nx_ic = icost_row[bx - 1];
                 }
@@ -1292,16 +1277,6 @@ static int xd_la_prepare( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, int n_pai
         if( rc )
             return rc;
     }
-    {
-        const size_t tiled = (size_t)n_pairs * ( ( g->lowres_w + 64 ) / 8 ) * ( ( g->lowres_h + 64 ) / 8 ) * 64;
-        if( ctx->la_tiled_cap < tiled )
-        {
-            XD_CHECK( cudaDeviceSynchronize() );
-            int rc = xd_reserve_dev( (void **)&ctx->la_tiled, &ctx->la_tiled_cap, tiled );
-            if( rc )
-                return rc;
-        }
-    }
     if( ++ctx->la_epoch == 0 )
     {
         XD_CHECK( cudaMemsetAsync( ctx->la_sync, 0, ctx->la_sync_cap, s ) );
@@ -1350,9 +1325,6 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         A.slack = slack;
     }
     A.timing = ctx->la_timing;
-    A.tiled = ctx->la_tiled;
-    A.tile_w = ( g->lowres_w + 64 ) / 8;
-    A.tile_h = ( g->lowres_h + 64 ) / 8;
 
     const int inner = ( g->mb_w - 2 ) * ( g->mb_h - 2 );
     dim3 igrid( ( inner + 127 ) / 128, count );
@@ -1406,14 +1378,6 @@ static int xd_la_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint
         const int cap = ctx->sm_count * per_sm[which];
         if( ctas > cap )
             ctas = cap;
-        if( which >= 2 )
-        {
-            const int chunks = ( ( A.tile_w + 1 ) / 2 ) * A.tile_h * 8;
-            const int tslot = xd_prof_begin( ctx, XD_PROF_LA_TILE, s );
-            xd_la_tile_kernel<<<dim3( ( chunks + 255 ) / 256, n_inter ), 256, 0, s>>>( A, inter_list, ctx->la_tiled );
-            xd_prof_end( ctx, XD_PROF_LA_TILE, tslot, s );
-            ctx->launches++;
-        }
         pslot = xd_prof_begin( ctx, XD_PROF_LA_INTER, s );
         if( which == 1 )
             xd_la_inter_kernel<true><<<ctas, LA_WARPS * 32, 0, s>>>( A, n_inter, inter_list );
