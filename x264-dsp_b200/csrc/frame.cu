@@ -217,22 +217,23 @@ __device__ __forceinline__ void xd_lowres_src( const uint8_t *base, int pitch, i
     e = p[min( x0 + 16, w - 1 )];
 }
 
-// one whole tile (8 rows of 8 samples, 64 contiguous bytes) of the tiled copy
-__device__ __forceinline__ void xd_tile_store( uint8_t *tile, const uint2 rows[8] )
+// LR_ROWS consecutive rows of one tile (LR_ROWS * 8 contiguous bytes: one 32-byte sector for 4 rows)
+#define LR_ROWS 4
+__device__ __forceinline__ void xd_tile_store( uint8_t *tile_rows, const uint2 rows[LR_ROWS] )
 {
-    uint4 *d = (uint4 *)tile;
+    uint4 *d = (uint4 *)tile_rows;
 #pragma unroll
-    for( int i = 0; i < 4; i++ )
+    for( int i = 0; i < LR_ROWS / 2; i++ )
         d[i] = make_uint4( rows[2 * i].x, rows[2 * i].y, rows[2 * i + 1].x, rows[2 * i + 1].y );
 }
 
 // The four half-resolution planes are kept in the slot in TILED form only (the layout the lookahead
 // searches in; x264dsp_frame_export_lowres_dev produces the reference's row-major planes on request):
 // writing both forms costs 2.5 MB more per 1080p frame, and this kernel is bound by HBM writes.
-// Thread = one 8-sample column chunk of an 8-row band of the lowres planes, i.e. exactly one 8x8 tile of
-// each of the four planes: the thread walks the band's 17 source rows once (16-byte loads, every row
-// loaded once) and stores the four finished tiles as 64-byte units.  Edge threads also write the
-// padding tiles (x264_frame_expand_border_lowres, frame.c:415-421: replicate 32 samples on every side).
+// Thread = one 8-sample column chunk of LR_ROWS lowres rows, i.e. half an 8x8 tile (one 32-byte sector)
+// of each of the four planes: the thread walks its 2*LR_ROWS+1 source rows once (16-byte loads) and
+// stores the finished half tiles as whole sectors.  Edge threads also write the padding tiles
+// (x264_frame_expand_border_lowres, frame.c:415-421: replicate 32 samples on every side).
 // RAW = false: x264_frame_init_lowres on a slot whose luma plane is loaded.
 // RAW = true : picture staging fused in -- the thread also writes the luma rows it has read into the
 //              slot's plane N, which saves re-reading 2 MB per 1080p frame.
@@ -243,7 +244,7 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
     uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
     uint8_t *plane = slot + g.luma_origin;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int band = blockIdx.y;
+    const int hb = blockIdx.y;                       // group of LR_ROWS lowres rows
     const int chunks = g.lowres_w >> 3;
     if( t >= chunks )
         return;
@@ -253,28 +254,24 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
     uint8_t *tl = slot + g.slot_tiled_off;
     const size_t tps = (size_t)g.tiled_plane_size;
     const bool first = t == 0, last = t == chunks - 1;
-    const int n_bands = g.lowres_h >> 3;
+    const int y0 = LR_ROWS * hb;
 
-    uint2 T[4][8];                                   // the four tiles, row by row
+    uint2 T[4][LR_ROWS];                             // this thread's rows of the four tiles
     uint4 a, b, c;
     uint32_t ea, eb, ec;
-    xd_lowres_src<RAW>( src, pitch, sw, sh, 16 * band, 16 * t, a, ea );
+    xd_lowres_src<RAW>( src, pitch, sw, sh, 2 * y0, 16 * t, a, ea );
 #pragma unroll
-    for( int r = 0; r < 8; r++ )
+    for( int r = 0; r < LR_ROWS; r++ )
     {
-        const int y = 8 * band + r;
+        const int y = y0 + r;
         const int r0 = 2 * y, r1 = 2 * y + 1;
         xd_lowres_src<RAW>( src, pitch, sw, sh, r1, 16 * t, b, eb );
         xd_lowres_src<RAW>( src, pitch, sw, sh, r1 + 1, 16 * t, c, ec );
         const uint4 ab = make_uint4( xd_avg4( a.x, b.x ), xd_avg4( a.y, b.y ), xd_avg4( a.z, b.z ), xd_avg4( a.w, b.w ) );
         const uint4 bc = make_uint4( xd_avg4( b.x, c.x ), xd_avg4( b.y, c.y ), xd_avg4( b.z, c.z ), xd_avg4( b.w, c.w ) );
         const uint32_t eab = ( ea + eb + 1 ) >> 1, ebc = ( eb + ec + 1 ) >> 1;
-        uint2 o[4];
-        xd_lowres_line( ab, eab, o[0], o[1] );
-        xd_lowres_line( bc, ebc, o[2], o[3] );
-#pragma unroll
-        for( int k = 0; k < 4; k++ )
-            T[k][r] = o[k];
+        xd_lowres_line( ab, eab, T[0][r], T[1][r] );
+        xd_lowres_line( bc, ebc, T[2][r], T[3][r] );
 
         if( RAW )
         {
@@ -299,16 +296,18 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
         ea = ec;
     }
 
-    // ---- the tiled copies: this thread's tile is (tx, ty) = (t + 4, band + 4) of each padded plane
-    const int tx = t + X264DSP_PADH / 8, ty = band + X264DSP_PADV / 8;
+    // ---- the tiles: rows y0 .. y0+LR_ROWS-1 of tile (tx, ty) = (t + 4, y0/8 + 4) of each padded plane
+    const int tx = t + X264DSP_PADH / 8, ty = ( y0 >> 3 ) + X264DSP_PADV / 8;
+    const int roff = ( y0 & 7 ) * 8;                 // byte offset of the thread's rows inside a tile
+    const bool top = y0 == 0, bottom = y0 + LR_ROWS == g.lowres_h;
 #pragma unroll
     for( int k = 0; k < 4; k++ )
     {
         uint8_t *tp = tl + k * tps;
-        xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx ) * 64, T[k] );
-        uint2 L[8], R[8];                            // side padding: the first / last sample of every row
+        xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx ) * 64 + roff, T[k] );
+        uint2 L[LR_ROWS], R[LR_ROWS];                // side padding: the first / last sample of every row
 #pragma unroll
-        for( int r = 0; r < 8; r++ )
+        for( int r = 0; r < LR_ROWS; r++ )
         {
             const uint32_t vl = ( T[k][r].x & 255u ) * 0x01010101u, vr = ( T[k][r].y >> 24 ) * 0x01010101u;
             L[r] = make_uint2( vl, vl );
@@ -316,34 +315,38 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
         }
         if( first )
             for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
-                xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx - cc ) * 64, L );
+                xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx - cc ) * 64 + roff, L );
         if( last )
             for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
-                xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx + cc ) * 64, R );
+                xd_tile_store( tp + ( (size_t)ty * g.tile_w + tx + cc ) * 64 + roff, R );
         // top / bottom padding: four tile rows that repeat the picture's first / last row
 #pragma unroll
         for( int side = 0; side < 2; side++ )
         {
-            if( side == 0 ? band != 0 : band != n_bands - 1 )
+            if( side == 0 ? !top : !bottom )
                 continue;
-            uint2 E[8], EL[8], ER[8];
+            uint2 E[LR_ROWS], EL[LR_ROWS], ER[LR_ROWS];
 #pragma unroll
-            for( int r = 0; r < 8; r++ )
+            for( int r = 0; r < LR_ROWS; r++ )
             {
-                E[r] = side == 0 ? T[k][0] : T[k][7];
-                EL[r] = side == 0 ? L[0] : L[7];
-                ER[r] = side == 0 ? R[0] : R[7];
+                E[r] = side == 0 ? T[k][0] : T[k][LR_ROWS - 1];
+                EL[r] = side == 0 ? L[0] : L[LR_ROWS - 1];
+                ER[r] = side == 0 ? R[0] : R[LR_ROWS - 1];
             }
             for( int rr = 1; rr <= X264DSP_PADV / 8; rr++ )
             {
                 const int tyy = side == 0 ? ty - rr : ty + rr;
-                xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx ) * 64, E );
-                if( first )
-                    for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
-                        xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx - cc ) * 64, EL );
-                if( last )
-                    for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
-                        xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx + cc ) * 64, ER );
+                for( int half = 0; half < 8 / LR_ROWS; half++ )
+                {
+                    const int ho = half * LR_ROWS * 8;
+                    xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx ) * 64 + ho, E );
+                    if( first )
+                        for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
+                            xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx - cc ) * 64 + ho, EL );
+                    if( last )
+                        for( int cc = 1; cc <= X264DSP_PADH / 8; cc++ )
+                            xd_tile_store( tp + ( (size_t)tyy * g.tile_w + tx + cc ) * 64 + ho, ER );
+                }
             }
         }
     }
@@ -694,7 +697,7 @@ extern "C" int x264dsp_frame_retile_lowres_dev( x264dsp_ctx_t *ctx, const x264ds
 static int xd_launch_lowres( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots, const uint8_t *raw,
                              int n_frames, cudaStream_t s )
 {
-    dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h >> 3, n_frames );
+    dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h / LR_ROWS, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_LOWRES, s );
     if( raw )
         xd_lowres_kernel<true><<<grid, 128, 0, s>>>( *g, slots, raw );
