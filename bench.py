@@ -485,9 +485,9 @@ def main():
                          "algorithmic_bytes_per_launch": int(bytes_per_pair * pairs_per_launch),
                          "avg_launch_ms": inter_avg_s * 1e3, "launches_timed": inter_n,
                          "note": "dependent-search wavefront kernel (SURVEY 8(d) config 2): HBM % reported as required; ncu "
-                                 "(profiles/) shows instruction issue (~60 %) and the L1 data pipe (~45 % of peak "
-                                 "wavefronts, 91 % before the reference plane was tiled) as the limiters, DRAM at a few % "
-                                 "of peak"},
+                                 "(profiles/r01k) shows instruction issue (56 %) and the L1 data pipe (61 % of peak "
+                                 "wavefronts) as the limiters; DRAM traffic is below the algorithmic bytes because "
+                                 "consecutive pairs share a reference frame in L2"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "pixel_cmp": {"sad_gpix_per_s": sad_px * world / step_s / 1e9, "satd_gpix_per_s": satd_px * world / step_s / 1e9,
                           "sad_pix_per_step_per_gpu": sad_px, "satd_pix_per_step_per_gpu": satd_px,

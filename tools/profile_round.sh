@@ -4,7 +4,7 @@
 # $1 = tag for the output names, $2 = kernels (xd_<name>) to capture in full (default: all).
 # Each ncu command only runs after the same command line exited 0 without ncu (B200_PROFILING.md).
 TAG=${1:-r01}
-KERNELS=${2:-"hpel_kernel lowres_kernel residual_kernel mc_frame_kernel me_sized_kernel me_search_kernel deblock_kernel deblock_strength_kernel la_quad_kernel la_intra_kernel load_i420_kernel expand_border_kernel filtered_border_kernel"}
+KERNELS=${2:-"hpel_kernel lowres_kernel residual_kernel mc_frame_kernel me_sized_kernel me_search_kernel deblock_kernel deblock_strength_kernel la_multi_kernel la_intra_kernel load_i420_kernel expand_border_kernel filtered_border_kernel"}
 OUT=gpurun_out
 mkdir -p $OUT
 NCU_LIST="ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv"
@@ -20,7 +20,7 @@ $NCU_LIST --log-file $OUT/${TAG}_paths_launches.csv $P > $OUT/${TAG}_paths_ncu.l
 for k in $KERNELS; do
     CMD="$P"
     [ "$k" = "la_inter_kernel" ] && CMD="$B"
-    [ "$k" = "la_quad_kernel" ] && CMD="$B"
+    [ "$k" = "la_multi_kernel" ] && CMD="$B"
     [ "$k" = "la_intra_kernel" ] && CMD="$B"
     # skip the warm-up launch of each kernel so that the capture is a steady-state one
     $NCU_FULL -k regex:xd_$k -s 1 -c 1 -f -o $OUT/${TAG}_full_$k $CMD > $OUT/${TAG}_full_$k.log 2>&1
