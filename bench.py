@@ -299,6 +299,9 @@ def workload_config(args, frames_per_step, sample=None):
                      f"x264_slicetype_frame_cost (DIA/SAD full-pel, hpel refine, SATD) over {args.clip_len}-frame clips"),
         "clips_per_gpu_per_step": args.clips, "clip_len": args.clip_len, "frames_per_step_per_gpu": args.clips * args.clip_len,
         "l2_policy": "step input larger than L2 (luma %.0f MB per GPU per step)" % (args.clips * args.clip_len * args.width * args.height / 1e6),
+        "step": ("per frame: the four half-resolution planes from the w x h luma picture (the picture is read as "
+                 "frame->plane[0], mod-16 replication included), then intra cost of every frame and inter cost of "
+                 "frames 1.. against their predecessor; both arms return lowres MVs, MV costs and frame costs"),
         "parallelism": f"frame-range sharding, {args.gpus} GPU(s), no data-path collective",
     }
     if sample:
@@ -376,7 +379,7 @@ def main():
     torch.cuda.synchronize()
 
     def step_dev():
-        ctx.frame_load_luma_lowres(g, luma_dev, slots, n)          # picture staging + x264_frame_init_lowres
+        ctx.frame_lowres_from_luma(g, luma_dev, slots, n)          # x264_frame_init_lowres, the picture being plane[0]
         ctx.lookahead_frame_cost(g, slots, b, p0, wi, d_mvs, d_costs, d_sums)
 
     def sync_all():
@@ -422,7 +425,7 @@ def main():
     # ---- single clip latency (exactly the 8-frame configuration), device resident
     one = clip_len
     def step_one():
-        ctx.frame_load_luma_lowres(g, luma_dev, slots, one)
+        ctx.frame_lowres_from_luma(g, luma_dev, slots, one)
         ctx.lookahead_frame_cost(g, slots, b[:one], p0[:one], wi[:one], d_mvs, d_costs, d_sums)
     for _ in range(3):
         step_one()

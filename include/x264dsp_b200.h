@@ -168,6 +168,11 @@ int x264dsp_frame_init_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, 
  * slot contents: luma plane N incl. the duplicated column / row, four padded lowres planes) */
 int x264dsp_frame_load_luma_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
                                         uint8_t *slots, int n_frames, void *stream );
+/* x264_frame_init_lowres with the caller's width x height picture AS frame->plane[0]: only the (tiled)
+ * lowres planes of the slot are written, its luma plane is left alone.  For callers that want nothing
+ * but the lookahead of these pictures (x264dsp_lookahead_clips_host uses it internally). */
+int x264dsp_frame_lowres_from_luma_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
+                                        uint8_t *slots, int n_frames, void *stream );
 /* tiled -> row-major: fills the slot's lowres region (lowres[0..3] of x264_frame_t, padding included) */
 int x264dsp_frame_export_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
                                      int n_frames, void *stream );

@@ -199,6 +199,14 @@ def test_fused_staging_and_lowres_equals_the_two_calls(pkg, ctx, w, h):
     ctx.sync()
     diff = torch.nonzero(a != b)
     assert diff.numel() == 0, f"{diff.numel()} bytes differ, first at slot offset {int(diff[0]) % g.slot_bytes}"
+    # the lowres-only variant writes the same (tiled) lowres planes and nothing else
+    c = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_lowres_from_luma(g, d_luma, c, n)
+    ctx.sync()
+    av, cv = a.view(n, -1), c.view(n, -1)
+    assert torch.equal(av[:, g.slot_tiled_off:], cv[:, g.slot_tiled_off:]), "tiled lowres planes differ"
+    assert int(cv[:, : g.slot_tiled_off].max()) == 0, "the lowres-only entry point must not touch the other planes"
 
 
 def test_lowres_export_and_import_are_inverse(pkg, ctx):

@@ -258,6 +258,11 @@ class Context:
         check(lib().x264dsp_frame_load_luma_lowres_dev(self._h, C.byref(g), _dp(luma_dev), _dp(slots_dev),
                                                        int(n_frames), None), "x264dsp_frame_load_luma_lowres_dev")
 
+    def frame_lowres_from_luma(self, g, luma_dev, slots_dev, n_frames):
+        """x264_frame_init_lowres reading the pictures directly; the slots' luma planes are not written"""
+        check(lib().x264dsp_frame_lowres_from_luma_dev(self._h, C.byref(g), _dp(luma_dev), _dp(slots_dev),
+                                                       int(n_frames), None), "x264dsp_frame_lowres_from_luma_dev")
+
     def frame_export_lowres(self, g, slots_dev, n_frames):
         """tiled lowres planes -> the reference's row-major lowres[0..3] in the slot's lowres region"""
         check(lib().x264dsp_frame_export_lowres_dev(self._h, C.byref(g), _dp(slots_dev), int(n_frames), None),

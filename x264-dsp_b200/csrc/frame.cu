@@ -237,7 +237,9 @@ __device__ __forceinline__ void xd_tile_store( uint8_t *tile_rows, const uint2 r
 // RAW = false: x264_frame_init_lowres on a slot whose luma plane is loaded.
 // RAW = true : picture staging fused in -- the thread also writes the luma rows it has read into the
 //              slot's plane N, which saves re-reading 2 MB per 1080p frame.
-template<bool RAW>
+// KEEP = false (RAW only): the picture is read as the reference reads frame->plane[0] and NOTHING but the
+//              lowres planes is written -- for callers that only want the lookahead of these pictures.
+template<bool RAW, bool KEEP>
 __global__ void __launch_bounds__( 128 )
 xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *__restrict__ raw )
 {
@@ -273,19 +275,19 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
         xd_lowres_line( ab, eab, T[0][r], T[1][r] );
         xd_lowres_line( bc, ebc, T[2][r], T[3][r] );
 
-        if( RAW )
+        if( RAW && KEEP )
         {
             *(uint4 *)( plane + (size_t)r0 * ls + 16 * t ) = a;
             *(uint4 *)( plane + (size_t)r1 * ls + 16 * t ) = b;
         }
         // side effect of x264_frame_init_lowres on the source plane: column luma_w of every row and
         // row luma_h (luma_w + 1 bytes) duplicate their neighbours
-        if( last )
+        if( KEEP && last )
         {
             plane[(size_t)r0 * ls + g.luma_w] = (uint8_t)ea;
             plane[(size_t)r1 * ls + g.luma_w] = (uint8_t)eb;
         }
-        if( y == g.lowres_h - 1 )
+        if( KEEP && y == g.lowres_h - 1 )
         {
             // b is the last picture row here (r1 == luma_h - 1)
             *(uint4 *)( plane + (size_t)g.luma_h * ls + 16 * t ) = b;
@@ -695,14 +697,16 @@ extern "C" int x264dsp_frame_retile_lowres_dev( x264dsp_ctx_t *ctx, const x264ds
 }
 
 static int xd_launch_lowres( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots, const uint8_t *raw,
-                             int n_frames, cudaStream_t s )
+                             int n_frames, cudaStream_t s, bool keep_luma = true )
 {
     dim3 grid( ( ( g->lowres_w >> 3 ) + 127 ) / 128, g->lowres_h / LR_ROWS, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_LOWRES, s );
-    if( raw )
-        xd_lowres_kernel<true><<<grid, 128, 0, s>>>( *g, slots, raw );
+    if( raw && keep_luma )
+        xd_lowres_kernel<true, true><<<grid, 128, 0, s>>>( *g, slots, raw );
+    else if( raw )
+        xd_lowres_kernel<true, false><<<grid, 128, 0, s>>>( *g, slots, raw );
     else
-        xd_lowres_kernel<false><<<grid, 128, 0, s>>>( *g, slots, NULL );
+        xd_lowres_kernel<false, true><<<grid, 128, 0, s>>>( *g, slots, NULL );
     xd_prof_end( ctx, XD_PROF_LOWRES, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
@@ -722,6 +726,21 @@ int xd_frame_load_luma_lowres( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, cons
                                int n_frames, cudaStream_t s )
 {
     return xd_launch_lowres( ctx, g, slots, luma, n_frames, s );
+}
+
+// lowres planes of the slots straight from the pictures; the slots' luma planes are not touched
+int xd_frame_lowres_from_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma, uint8_t *slots,
+                               int n_frames, cudaStream_t s )
+{
+    return xd_launch_lowres( ctx, g, slots, luma, n_frames, s, false );
+}
+
+extern "C" int x264dsp_frame_lowres_from_luma_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,
+                                                    uint8_t *slots, int n_frames, void *stream )
+{
+    if( !ctx || !g || !luma || !slots || n_frames <= 0 )
+        return X264DSP_E_ARG;
+    return xd_launch_lowres( ctx, g, slots, luma, n_frames, xd_stream( ctx, stream ), false );
 }
 
 extern "C" int x264dsp_frame_load_luma_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma,

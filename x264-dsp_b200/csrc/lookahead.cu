@@ -1473,7 +1473,7 @@ extern "C" int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264d
                          mvs, costs, sums, row_satds, s );
 }
 
-int xd_frame_load_luma_lowres( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma, uint8_t *slots,
+int xd_frame_lowres_from_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma, uint8_t *slots,
                                int n_frames, cudaStream_t s );
 
 static bool xd_is_pinned( const void *p )
@@ -1576,7 +1576,7 @@ extern "C" int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int 
         }
         XD_CHECK( cudaMemcpyAsync( ctx->stage_dev + (size_t)f0 * pic, src, pic * nf, cudaMemcpyHostToDevice, s ) );
         uint8_t *slots = ctx->clip_slots + (size_t)f0 * g.slot_bytes;
-        if( ( rc = xd_frame_load_luma_lowres( ctx, &g, ctx->stage_dev + (size_t)f0 * pic, slots, nf, s ) ) ) return rc;
+        if( ( rc = xd_frame_lowres_from_luma( ctx, &g, ctx->stage_dev + (size_t)f0 * pic, slots, nf, s ) ) ) return rc;
         // every clip of the group contributes clip_len-1 inter pairs, in frame order
         const int inter0 = c0 * ( clip_len - 1 ), ninter = ( c1 - c0 ) * ( clip_len - 1 );
         if( ( rc = xd_la_launch( ctx, &g, ctx->clip_slots, f0, nf, b_dev, p0_dev, wi_dev, list_dev + inter0, ninter, gi,
