@@ -192,6 +192,12 @@ def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats):
     kind = "reference" if lib is not None else "port"
     n_clips = len(luma_clips)
     chroma = np.full(w * h // 2, 128, np.uint8)
+    # I420 pictures are assembled once, outside the timed region (distinct clips only: the lists may repeat)
+    pics = {}
+    for clip in luma_clips:
+        key = clip.__array_interface__["data"][0]
+        if key not in pics:
+            pics[key] = [np.concatenate([clip[i], chroma]) for i in range(clip_len)]
     work = [[] for _ in range(threads)]
     for c in range(n_clips):
         work[c % threads].append(c)
@@ -218,20 +224,18 @@ def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats):
         if state[t] is not None:
             for _ in range(repeats):
                 for c in work[t]:
-                    luma = luma_clips[c]
+                    clip_pics = pics[luma_clips[c].__array_interface__["data"][0]]
                     if kind == "reference":
                         enc, frames = state[t]
                         for i in range(clip_len):
-                            pic = np.concatenate([luma[i], chroma])
-                            enc.load(frames[i], pic)        # x264_frame_copy_picture: part of the pass
+                            enc.load(frames[i], clip_pics[i])   # x264_frame_copy_picture (the GPU arm's e2e has its H2D copy)
                         arr = (C.c_void_p * clip_len)(*[f.value for f in frames])
                         costs = (C.c_int * clip_len)()
                         enc.lib.xref_time_lookahead(enc.h, arr, clip_len, costs)
                     else:
                         slots = state[t]
                         for i in range(clip_len):
-                            pic = np.concatenate([luma[i], chroma])
-                            o.xo_frame_load_i420(C.byref(g), cc.ptr(pic), cc.ptr(slots[i]))
+                            o.xo_frame_load_i420(C.byref(g), cc.ptr(clip_pics[i]), cc.ptr(slots[i]))
                             o.xo_frame_init_lowres(C.byref(g), cc.ptr(slots[i]))
                         mv = np.zeros((g.mb_count, 2), np.int16)
                         cs = np.zeros(g.mb_count, np.int32)
