@@ -182,6 +182,81 @@ def me_search_cpu_counts(pkg, g, slots, blocks0, qp=26):
 
 
 # --------------------------------------------------------------------------------------------
+# secondary measurement (BASELINE.json configs[3]): motion compensation from 16x16 MVs, residual coding
+# (DCT / quant / dequant / IDCT / decimation) and in-loop deblocking of whole frames, QP 26
+
+def recon_measure(pkg, ctx, torch, g, w, h, n_frames, first_frame=0, reps=3, qp=26):
+    """n_frames frames coded against their predecessors, frame-batched launches; returns the per-kernel
+    ms per frame and what the cpu leg needs to check frame 0 bit for bit"""
+    stream = ctx.torch_stream()
+    nf = n_frames + 1
+    pics = np.stack([pkg.synth_frame(w, h, first_frame + i) for i in range(nf)])
+    i420 = torch.from_numpy(pics).cuda()
+    slots = torch.zeros(nf * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    ctx.frame_load_i420(g, i420, slots, nf)
+    ctx.frame_expand_border(g, slots, nf)
+    ctx.frame_filter(g, slots, nf)
+    nmb = g.mb_count
+    # 16x16 MVs: the true pan of the synthetic clip (3, 2 luma samples per frame) plus +-1 qpel of jitter
+    rng = np.random.RandomState(5)
+    mv = (np.array([12, 8]) + rng.randint(-1, 2, (n_frames, nmb, 2))).astype(np.int16)
+    d_mv = torch.from_numpy(mv).cuda()
+    pred = torch.zeros(n_frames * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    lv = torch.zeros((n_frames, nmb, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda")
+    nz = torch.zeros((n_frames, nmb, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda")
+    cbp = torch.zeros((n_frames, nmb), dtype=torch.int16, device="cuda")
+    mb_type = torch.from_numpy(np.full((n_frames, nmb), 4, np.int8)).cuda()          # P_L0
+    part = torch.from_numpy(np.full((n_frames, nmb), 16, np.uint8)).cuda()           # D_16x16
+    bs_h = (rng.rand(n_frames, nmb, 2, 8, 4) < 0.35).astype(np.uint8) * rng.randint(1, 3, (n_frames, nmb, 2, 8, 4)).astype(np.uint8)
+    bs = torch.from_numpy(bs_h).cuda()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ms = {"mc": 0.0, "residual": 0.0, "deblock": 0.0}
+    for rep in range(reps + 1):
+        ev[0].record(stream)
+        ctx.mc_frames(g, slots, n_frames, d_mv, pred)
+        ev[1].record(stream)
+        ctx.residual_frames(g, slots[g.slot_bytes:], pred, n_frames, qp, lv, nz, cbp)
+        ev[2].record(stream)
+        if rep == 0:
+            recon0 = pred[: g.slot_bytes].clone()          # frame 0 before deblocking, for the check
+        ctx.deblock_frames(g, pred, n_frames, mb_type, part, cbp, bs, qp, 0, 0)
+        ev[3].record(stream)
+        torch.cuda.synchronize()
+        if rep:                                            # rep 0 is the warm-up
+            ms["mc"] += ev[0].elapsed_time(ev[1]) / reps / n_frames
+            ms["residual"] += ev[1].elapsed_time(ev[2]) / reps / n_frames
+            ms["deblock"] += ev[2].elapsed_time(ev[3]) / reps / n_frames
+    check = {"slots": slots[: 2 * g.slot_bytes].cpu().numpy(), "mv": mv[0], "bs": bs_h[0], "qp": qp,
+             "recon": recon0.cpu().numpy(), "deblocked": pred[: g.slot_bytes].cpu().numpy(),
+             "levels": lv[0].cpu().numpy(), "nnz": nz[0].cpu().numpy(), "cbp": cbp[0].cpu().numpy()}
+    return ms, check
+
+
+def recon_cpu_check(pkg, g, check):
+    """cpu_baseline leg: frame 0 of the measurement through the oracle (one core), compared bit for bit"""
+    import cpu_checkers as cc
+    from cpu_checkers import ptr, i16p, i8p
+    o = cc.oracle()
+    go = cc.oracle_geom(g.width, g.height)
+    nmb = g.mb_count
+    host = check["slots"]
+    t0 = time.perf_counter()
+    pred = np.zeros(go.slot_bytes, np.uint8)
+    o.xo_mc_frame(C.byref(go), ptr(host[: g.slot_bytes]), ptr(check["mv"], i16p), ptr(pred))
+    lv = np.zeros((nmb, pkg.RES_LEVELS_PER_MB), np.int16)
+    nz = np.zeros((nmb, pkg.RES_NNZ_PER_MB), np.uint8)
+    cbp = np.zeros(nmb, np.int16)
+    o.xo_residual_frame(C.byref(go), ptr(host[g.slot_bytes:]), ptr(pred), check["qp"], ptr(lv, i16p), ptr(nz), ptr(cbp, i16p))
+    ok = (np.array_equal(pred, check["recon"]) and np.array_equal(lv, check["levels"])
+          and np.array_equal(nz, check["nnz"]) and np.array_equal(cbp, check["cbp"]))
+    mb_type, part = np.full(nmb, 4, np.int8), np.full(nmb, 16, np.uint8)
+    o.xo_deblock_frame(C.byref(go), ptr(pred), ptr(mb_type, i8p), ptr(part), ptr(cbp, i16p), ptr(check["bs"]), check["qp"], 0, 0)
+    dt = time.perf_counter() - t0
+    ok = ok and np.array_equal(pred, check["deblocked"])
+    return bool(ok), dt, int(np.count_nonzero(cbp))
+
+
+# --------------------------------------------------------------------------------------------
 # CPU arm: the reference's own C path (oracle/_ref) or, if that build is absent, the oracle port
 
 def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats):
@@ -446,6 +521,10 @@ def main():
     if rank == 0 and not args.no_me:
         me_pairs = min(8, clip_len - 1)
         me_ms, me_blocks0, me_slots = me_search_measure(pkg, ctx, torch, g, luma_dev, d_mvs[: clip_len].cpu().numpy(), me_pairs)
+    rc_ms = rc_check = None
+    if rank == 0 and not args.no_me:
+        rc_frames = 32 if w * h <= 1920 * 1088 else 8
+        rc_ms, rc_check = recon_measure(pkg, ctx, torch, g, w, h, rc_frames)
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -529,6 +608,17 @@ def main():
                            "bit_exact_vs_oracle": all(c["bit_exact"] for c in cnt.values()),
                            "cpu_port_1core_frames_per_s": 1.0 / sum(c["cpu_s"] for c in cnt.values())})
             line["me_search"] = me
+        if rc_ms is not None:
+            tot = sum(rc_ms.values())
+            rc = {"workload": f"{w}x{h} inter macroblocks: x264_mb_mc 16x16 + x264_macroblock_encode (4x4 DCT, quant, dequant, "
+                              "IDCT, decimation, chroma DC) + x264_frame_deblock_row, QP 26, frame-batched launches",
+                  "frames_per_s": 1e3 / tot, "ms_per_frame": rc_ms,
+                  "hbm_frac": {"residual": 16.5e6 / (rc_ms["residual"] / 1e3) / 1e9 / peak,
+                               "deblock": 6.8e6 / (rc_ms["deblock"] / 1e3) / 1e9 / peak} if (w, h) == (1920, 1080) else None}
+            if not args.no_cpu_baseline and world == 1:
+                ok, cpu_s, coded = recon_cpu_check(pkg, g, rc_check)
+                rc.update({"bit_exact_vs_oracle": ok, "coded_mbs_frame0": coded, "cpu_port_1core_frames_per_s": 1.0 / cpu_s})
+            line["recon"] = rc
         print(json.dumps(line))
     ctx.close()
     if world > 1:
