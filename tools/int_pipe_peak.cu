@@ -94,6 +94,59 @@ __global__ void __launch_bounds__( 1024, 2 ) pipe_kernel( uint32_t *out, unsigne
         clk[blockIdx.x] = (unsigned long long)( t1 - t0 );
 }
 
+// two different instructions alternating on independent chains: 128 thread-inst / clk / SM means the two issue on
+// different pipes (ALU + FMA), 64 means they share one
+template<int OPA, int OPB>
+__global__ void __launch_bounds__( 1024, 2 ) pair_kernel( uint32_t *out, unsigned long long *clk, uint32_t seed )
+{
+    uint32_t acc[ILP];
+    const uint32_t a = seed * ( threadIdx.x + 1 ), b = seed ^ ( blockIdx.x * 0x9E3779B9u + threadIdx.x );
+#pragma unroll
+    for( int i = 0; i < ILP; i++ )
+        acc[i] = a + i;
+    __syncthreads();
+    const long long t0 = clock64();
+    for( int it = 0; it < ITERS; it++ )
+#pragma unroll
+        for( int i = 0; i < ILP; i += 2 )
+        {
+            acc[i] = step<OPA>( acc[i], a, b );
+            acc[i + 1] = step<OPB>( acc[i + 1], a, b );
+        }
+    const long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for( int i = 0; i < ILP; i++ )
+        s ^= acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if( threadIdx.x == 0 )
+        clk[blockIdx.x] = (unsigned long long)( t1 - t0 );
+}
+
+template<int OPA, int OPB>
+static void run_pair( int sms, uint32_t *out, unsigned long long *clk, unsigned long long *clk_h, int last )
+{
+    const int grid = sms * 2;
+    pair_kernel<OPA, OPB><<<grid, 1024>>>( out, clk, 12345u );
+    cudaDeviceSynchronize();
+    double best_cyc = 1e30;
+    for( int rep = 0; rep < 5; rep++ )
+    {
+        pair_kernel<OPA, OPB><<<grid, 1024>>>( out, clk, 12345u + rep );
+        cudaDeviceSynchronize();
+        cudaMemcpy( clk_h, clk, grid * sizeof( *clk ), cudaMemcpyDeviceToHost );
+        double mx = 0;
+        for( int i = 0; i < grid; i++ )
+            if( (double)clk_h[i] > mx )
+                mx = (double)clk_h[i];
+        if( mx < best_cyc )
+            best_cyc = mx;
+    }
+    const double inst_sm = 2.0 * 1024 * ITERS * ILP;
+    printf( "  {\"pair\": [\"%s\", \"%s\"], \"thread_inst_per_clk_per_sm\": %.1f, \"warp_inst_per_clk_per_sm\": %.2f}%s\n",
+            op_name[OPA], op_name[OPB], inst_sm / best_cyc, inst_sm / best_cyc / 32.0, last ? "" : "," );
+}
+
 template<int OP>
 static void run( int sms, int khz, uint32_t *out, unsigned long long *clk, unsigned long long *clk_h, int last )
 {
@@ -162,6 +215,19 @@ int main()
     run<OP_SHFL>( sms, khz, out, clk, clk_h, 0 );
     run<OP_SHF>( sms, khz, out, clk, clk_h, 0 );
     run<OP_MIX_SAD>( sms, khz, out, clk, clk_h, 1 );
+    printf( "], \"pairs\": [\n" );
+    run_pair<OP_IMAD, OP_IADD3>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_IMAD, OP_VABSDIFF4_ACC>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_IMAD, OP_VIADD16X2>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_IMAD, OP_PRMT>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_IMAD, OP_VIMNMX>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_IMAD, OP_IDP4A>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_IDP4A, OP_LOP3>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_IDP4A, OP_SHF>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_VABSDIFF4_ACC, OP_IADD3>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_VABSDIFF4_ACC, OP_SHF>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_SHFL, OP_IADD3>( sms, out, clk, clk_h, 0 );
+    run_pair<OP_SHFL, OP_IMAD>( sms, out, clk, clk_h, 1 );
     printf( "]}\n" );
     return 0;
 }

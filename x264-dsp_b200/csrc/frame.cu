@@ -359,111 +359,199 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
 // [0, luma_w+8) -- the rest of the padded plane is filled by xd_filtered_border_kernel from these
 // values (the reference overwrites columns < 0).
 //
-// Mapping: a warp owns a strip of 30 output words (120 pixels) and walks HP_ROWS rows downwards; lane l
-// holds word column 30*strip + l - 1, lanes 0 and 31 are halo.  Each thread keeps the six source rows
-// of its four pixels in registers, unpacked to 16-bit pairs (p0,p2) / (p1,p3), so one new 4-byte load
-// per row feeds all three planes:
-//   V   six-tap down the window, two pixels per instruction (the sums fit 16 bits once biased by 2^15)
-//   H   six-tap along the row; the neighbours' pixels come from the adjacent lanes by shuffle
-//   HV  six-tap along the row over the UNCLIPPED 16-bit V values (the reference's int16 buf), 32-bit,
-//       neighbours again by shuffle
-// Biasing: every packed intermediate carries +32768 per half; (t+16)>>5 becomes ((u+16)>>5) - 1024 and
-// (t+512)>>10 of the 32-weight HV sum becomes ((u+512)>>10) - 1024, both exact.
+// Mapping: a lane owns 8 pixels of a row (one "unit", one 8-byte load and three 8-byte stores per row) and walks
+// HP_ROWS rows downwards; GW adjacent lanes form a strip whose first and last lane are halo (they hold the
+// neighbouring units so that every horizontal neighbour is one shuffle away).  Full strips use GW = 32 (30 units =
+// 240 pixels per warp); the units left over at the right edge (one for 1080p and 4K: 1928 = 8 x 240 + 8) are served
+// by narrower strips (GW = 4, 8, 16) with 32/GW strips per warp stacked over different row segments, so that the
+// remainder does not cost a whole warp column.
+//
+// Pipes (tools/int_pipe_peak.cu): PRMT / SHF / LOP3 / VIMNMX / I2IP issue on the ALU pipe, IMAD / VIADD.16x2 /
+// IDP.4A / IDP.2A on the FMA pipe, each at 2 warp instructions per clock per SM, so the taps are written as integer
+// dot products (FMA pipe) and only alignment, rounding and packing stay on the ALU pipe:
+//   V   six rows of the lane's pixels as 16-bit pairs in registers; (a+f) - 5 (b+e) + 20 (c+d) two pixels per
+//       instruction with each half biased by 2^15 + 16 (the sums fit 16 bits; the +16 is the rounding term)
+//   H   IDP.4A over byte windows at even offsets: pixel 2k   = W[2k-2].(1,-5,20,20) + W[2k+2].(-5,1,0,0)
+//                                                 pixel 2k+1 = W[2k-2].(0,1,-5,20) + W[2k+2].(20,-5,1,0)
+//   HV  IDP.2A (u16 x s8) over the UNCLIPPED biased V pairs (the reference's int16 buf): the bias contributes
+//       32 * 2^15 and the +16 contribute exactly the +512 rounding term, so the accumulator starts at -2^20
+//   clip + pack: cvt.pack.sat.u8.s32 (I2IP), two pixels per instruction
 #define HP_ROWS 48
-#define HP_STRIP 30
+#define HP_UNITS 30
 
-// (a+f) - 5 (b+e) + 20 (c+d) + 32768 in both halves; inputs are 0..255 per half (or sums thereof)
+// (a+f) - 5 (b+e) + 20 (c+d) + (32768 + 16) in both halves; inputs are 0..255 per half
 __device__ __forceinline__ uint32_t xd_hp_tap6_packed( uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f )
 {
-    const uint32_t pos = ( c + d ) * 20u + ( a + f );
-    return pos + 0x80008000u - ( b + e ) * 5u;
+    const uint32_t pos = ( c + d ) * 20u + ( a + f + 0x80108010u );
+    return pos - ( b + e ) * 5u;
 }
 
-// clip( (t+16) >> 5 ) of both halves of a biased word -> values 0..255 in the low byte of each half
-__device__ __forceinline__ uint32_t xd_hp_round5_packed( uint32_t u )
+__device__ __forceinline__ int xd_dp4a_us( uint32_t a, uint32_t b, int c )
 {
-    const uint32_t t = ( ( u + 0x00100010u ) >> 5 ) & 0x07FF07FFu;          // (t+16)>>5 + 1024
-    return __vminu2( __vmaxu2( t, 0x04000400u ), 0x04FF04FFu ) - 0x04000400u;
+    int d;
+    asm( "dp4a.u32.s32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a ), "r"( b ), "r"( c ) );
+    return d;
+}
+__device__ __forceinline__ int xd_dp2a_lo_us( uint32_t a, uint32_t b, int c )
+{
+    int d;
+    asm( "dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a ), "r"( b ), "r"( c ) );
+    return d;
+}
+__device__ __forceinline__ int xd_dp2a_hi_us( uint32_t a, uint32_t b, int c )
+{
+    int d;
+    asm( "dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a ), "r"( b ), "r"( c ) );
+    return d;
+}
+// clip to 0..255 and pack four values, a0 in the lowest byte
+__device__ __forceinline__ uint32_t xd_pack_sat4( int a0, int a1, int a2, int a3 )
+{
+    uint32_t t, d;
+    asm( "cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"( t ) : "r"( a3 ), "r"( a2 ), "r"( 0 ) );
+    asm( "cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a1 ), "r"( a0 ), "r"( t ) );
+    return d;
 }
 
-__global__ void __launch_bounds__( 128 )
-xd_hpel_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots )
+template<int GW>
+__device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *__restrict__ slot, int unit0, int strip_units, int wseg )
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & ( GW - 1 );
+    const int seg = wseg * ( 32 / GW ) + lane / GW;              // row segment of this lane's strip
     const int ls = g.luma_stride;
-    const int wc = blockIdx.x * HP_STRIP + lane - 1;            // word column of this lane
-    const int n_words = ( g.luma_w + 8 ) >> 2;                   // output words per row
-    const int y0 = ( blockIdx.y * 4 + warp ) * HP_ROWS - 8;      // first output row of this warp
     const int y_end = g.luma_h + 8;
-    if( y0 >= y_end )
+    const bool seg_ok = seg * HP_ROWS - 8 < y_end;
+    if( !__any_sync( 0xffffffffu, seg_ok ) )
         return;
-    // halo lanes beyond the padded row still read inside the allocation (pad is 32 >= 4 + 4)
-    const int wcl = min( wc, n_words );
-    const uint8_t *src = slot + g.luma_origin + 4 * wcl;
-    const bool writer = lane >= 1 && lane <= HP_STRIP && wc < n_words;
-    uint8_t *dh = slot + (size_t)g.luma_plane_size + g.luma_origin + 4 * wcl;
+    // strips of a partly filled warp that fall below the plane redo the first segment without storing; a segment
+    // reads at most 28 rows past the padded plane N, i.e. into plane H of the same slot
+    const int y0 = seg_ok ? seg * HP_ROWS - 8 : -8;              // first output row
+    const int n_units = ( g.luma_w + 8 ) >> 3;
+    // halo lanes (and idle lanes past the strip) still read inside the allocation: units -1 .. n_units, pad is 32
+    const int unit = min( unit0 + gl - 1, n_units );
+    const bool writer = seg_ok && gl >= 1 && gl <= GW - 2 && gl - 1 < strip_units;
+    const uint8_t *ps = slot + g.luma_origin + 8 * unit + (int64_t)( y0 - 2 ) * ls;      // next source row to load
+    uint8_t *dh = slot + (size_t)g.luma_plane_size + g.luma_origin + 8 * unit + (int64_t)y0 * ls;
     uint8_t *dv = dh + (size_t)g.luma_plane_size, *dc = dv + (size_t)g.luma_plane_size;
 
-    uint32_t E[6], O[6];                                         // rows y-2 .. y+3: (p0,p2), (p1,p3)
+    uint32_t A[6][4];                                            // rows y-2 .. y+3 as (p0,p1) (p2,p3) (p4,p5) (p6,p7)
+    uint2 R[3];                                                  // rows y .. y+2 as loaded
 #pragma unroll
     for( int k = 0; k < 5; k++ )
     {
-        const uint32_t w = *(const uint32_t *)( src + (int64_t)( y0 - 2 + k ) * ls );
-        E[k] = w & 0x00FF00FFu;
-        O[k] = __byte_perm( w, 0u, 0x4341 );
+        const uint2 w = *(const uint2 *)ps;
+        ps += ls;
+        A[k][0] = __byte_perm( w.x, 0u, 0x4140 );
+        A[k][1] = __byte_perm( w.x, 0u, 0x4342 );
+        A[k][2] = __byte_perm( w.y, 0u, 0x4140 );
+        A[k][3] = __byte_perm( w.y, 0u, 0x4342 );
+        if( k >= 2 )
+            R[k - 2] = w;
     }
+    // the rows two and three iterations ahead are already in flight: a row's DRAM latency is hidden behind two rows of
+    // arithmetic instead of stalling the warp at its first use (ncu r01n: 9.6 long-scoreboard stalls per issue)
+    uint2 Q[2];
+    Q[0] = *(const uint2 *)ps;
+    Q[1] = *(const uint2 *)( ps + ls );
+    ps += 2 * ls;
+    const uint32_t TA0 = 0x1414FB01u, TB0 = 0x000001FBu;         // (1,-5,20,20) (-5,1,0,0)
+    const uint32_t TA1 = 0x14FB0100u, TB1 = 0x0001FB14u;         // (0,1,-5,20) (20,-5,1,0)
+    const uint32_t T1 = 0x1414FB01u, T2 = 0x010001FBu;           // lo (1,-5) hi (20,20); lo (-5,1) hi (0,1)
+    const uint32_t T3 = 0xFB1414FBu, T4 = 0x00000001u;           // lo (-5,20) hi (20,-5); lo (1,0)
     for( int yb = y0; yb < y0 + HP_ROWS; yb += 6 )
     {
 #pragma unroll
         for( int u = 0; u < 6; u++ )
         {
             const int y = yb + u;
-            if( y >= y_end )
-                break;                                           // warp-uniform
             const int i0 = u % 6, i1 = ( u + 1 ) % 6, i2 = ( u + 2 ) % 6, i3 = ( u + 3 ) % 6, i4 = ( u + 4 ) % 6, i5 = ( u + 5 ) % 6;
+            const uint2 cur = R[u % 3];
             {
-                const uint32_t w = *(const uint32_t *)( src + (int64_t)( y + 3 ) * ls );
-                E[i5] = w & 0x00FF00FFu;
-                O[i5] = __byte_perm( w, 0u, 0x4341 );
+                const uint2 w = Q[u % 2];
+                Q[u % 2] = *(const uint2 *)ps;
+                ps += ls;
+                A[i5][0] = __byte_perm( w.x, 0u, 0x4140 );
+                A[i5][1] = __byte_perm( w.x, 0u, 0x4342 );
+                A[i5][2] = __byte_perm( w.y, 0u, 0x4140 );
+                A[i5][3] = __byte_perm( w.y, 0u, 0x4342 );
+                R[u % 3] = w;
             }
-            // ---- V: biased 16-bit intermediates of this lane's four columns
-            const uint32_t ue = xd_hp_tap6_packed( E[i0], E[i1], E[i2], E[i3], E[i4], E[i5] );   // (v0, v2)
-            const uint32_t uo = xd_hp_tap6_packed( O[i0], O[i1], O[i2], O[i3], O[i4], O[i5] );   // (v1, v3)
-            const uint32_t ov = xd_hp_round5_packed( ue ) | ( xd_hp_round5_packed( uo ) << 8 );
-
-            // ---- H: row y is window slot i2; neighbours' pairs by shuffle
-            const uint32_t eC = E[i2], oC = O[i2];
-            const uint32_t eP = __shfl_up_sync( 0xffffffffu, eC, 1 ), oP = __shfl_up_sync( 0xffffffffu, oC, 1 );
-            const uint32_t eN = __shfl_down_sync( 0xffffffffu, eC, 1 ), oN = __shfl_down_sync( 0xffffffffu, oC, 1 );
-            const uint32_t p2c0 = __byte_perm( eP, eC, 0x5432 ), p3c1 = __byte_perm( oP, oC, 0x5432 );
-            const uint32_t c2n0 = __byte_perm( eC, eN, 0x5432 ), c3n1 = __byte_perm( oC, oN, 0x5432 );
-            const uint32_t he = xd_hp_tap6_packed( p2c0, p3c1, eC, oC, c2n0, c3n1 );             // (h0, h2)
-            const uint32_t ho = xd_hp_tap6_packed( p3c1, eC, oC, c2n0, c3n1, eN );               // (h1, h3)
-            const uint32_t oh = xd_hp_round5_packed( he ) | ( xd_hp_round5_packed( ho ) << 8 );
-
-            // ---- HV: six-tap over the unclipped V values of columns -2 .. 6
-            const uint32_t ueP = __shfl_up_sync( 0xffffffffu, ue, 1 ), uoP = __shfl_up_sync( 0xffffffffu, uo, 1 );
-            const uint32_t ueN = __shfl_down_sync( 0xffffffffu, ue, 1 ), uoN = __shfl_down_sync( 0xffffffffu, uo, 1 );
-            const int vm2 = (int)( ueP >> 16 ), vm1 = (int)( uoP >> 16 );
-            const int v0 = (int)( ue & 0xFFFFu ), v1 = (int)( uo & 0xFFFFu ), v2 = (int)( ue >> 16 ), v3 = (int)( uo >> 16 );
-            const int v4 = (int)( ueN & 0xFFFFu ), v5 = (int)( uoN & 0xFFFFu ), v6 = (int)( ueN >> 16 );
-            const int kb = 512 - ( 1 << 20 );                   // rounding minus the bias of the 32 weights
-            const int c0 = xd_clip_u8( ( ( vm2 + v3 + kb ) + 20 * ( v0 + v1 ) - 5 * ( vm1 + v2 ) ) >> 10 );
-            const int c1 = xd_clip_u8( ( ( vm1 + v4 + kb ) + 20 * ( v1 + v2 ) - 5 * ( v0 + v3 ) ) >> 10 );
-            const int c2 = xd_clip_u8( ( ( v0 + v5 + kb ) + 20 * ( v2 + v3 ) - 5 * ( v1 + v4 ) ) >> 10 );
-            const int c3 = xd_clip_u8( ( ( v1 + v6 + kb ) + 20 * ( v3 + v4 ) - 5 * ( v2 + v5 ) ) >> 10 );
-            const uint32_t oc = (uint32_t)c0 | ( (uint32_t)c1 << 8 ) | ( (uint32_t)c2 << 16 ) | ( (uint32_t)c3 << 24 );
-
-            if( writer )
+            // ---- V: biased 16-bit intermediates of this lane's eight columns
+            uint32_t P[4];
+#pragma unroll
+            for( int j = 0; j < 4; j++ )
+                P[j] = xd_hp_tap6_packed( A[i0][j], A[i1][j], A[i2][j], A[i3][j], A[i4][j], A[i5][j] );
+            uint2 ov;
             {
-                const int64_t o = (int64_t)y * ls;
-                *(uint32_t *)( dh + o ) = oh;
-                *(uint32_t *)( dv + o ) = ov;
-                *(uint32_t *)( dc + o ) = oc;
+                uint32_t f[4];
+#pragma unroll
+                for( int j = 0; j < 4; j++ )
+                    f[j] = __vminu2( __vmaxu2( ( P[j] >> 5 ) & 0x07FF07FFu, 0x04000400u ), 0x04FF04FFu );   // clip((v+16)>>5) + 1024
+                ov.x = __byte_perm( f[0], f[1], 0x6420 );
+                ov.y = __byte_perm( f[2], f[3], 0x6420 );
             }
+
+            // ---- H: byte windows at offsets -2, 0, 2, 4, 6, 8 of [prev | cur.x | cur.y | next]
+            uint2 oh;
+            {
+                const uint32_t cP = __shfl_up_sync( 0xffffffffu, cur.y, 1, GW ), cN = __shfl_down_sync( 0xffffffffu, cur.x, 1, GW );
+                const uint32_t wm2 = __funnelshift_r( cP, cur.x, 16 ), w2 = __funnelshift_r( cur.x, cur.y, 16 ), w6 = __funnelshift_r( cur.y, cN, 16 );
+                const int h0 = xd_dp4a_us( wm2, TA0, xd_dp4a_us( w2, TB0, 16 ) ), h1 = xd_dp4a_us( wm2, TA1, xd_dp4a_us( w2, TB1, 16 ) );
+                const int h2 = xd_dp4a_us( cur.x, TA0, xd_dp4a_us( cur.y, TB0, 16 ) ), h3 = xd_dp4a_us( cur.x, TA1, xd_dp4a_us( cur.y, TB1, 16 ) );
+                const int h4 = xd_dp4a_us( w2, TA0, xd_dp4a_us( w6, TB0, 16 ) ), h5 = xd_dp4a_us( w2, TA1, xd_dp4a_us( w6, TB1, 16 ) );
+                const int h6 = xd_dp4a_us( cur.y, TA0, xd_dp4a_us( cN, TB0, 16 ) ), h7 = xd_dp4a_us( cur.y, TA1, xd_dp4a_us( cN, TB1, 16 ) );
+                oh.x = xd_pack_sat4( h0 >> 5, h1 >> 5, h2 >> 5, h3 >> 5 );
+                oh.y = xd_pack_sat4( h4 >> 5, h5 >> 5, h6 >> 5, h7 >> 5 );
+            }
+
+            // ---- HV: six-tap over the unclipped V pairs of columns -2 .. 11
+            uint2 oc;
+            {
+                const uint32_t Pm = __shfl_up_sync( 0xffffffffu, P[3], 1, GW );
+                const uint32_t P4 = __shfl_down_sync( 0xffffffffu, P[0], 1, GW ), P5 = __shfl_down_sync( 0xffffffffu, P[1], 1, GW );
+                const int kb = -( 1 << 20 );
+                const int c0 = xd_dp2a_lo_us( Pm, T1, xd_dp2a_hi_us( P[0], T1, xd_dp2a_lo_us( P[1], T2, kb ) ) );
+                const int c1 = xd_dp2a_hi_us( Pm, T2, xd_dp2a_lo_us( P[0], T3, xd_dp2a_hi_us( P[1], T3, xd_dp2a_lo_us( P[2], T4, kb ) ) ) );
+                const int c2 = xd_dp2a_lo_us( P[0], T1, xd_dp2a_hi_us( P[1], T1, xd_dp2a_lo_us( P[2], T2, kb ) ) );
+                const int c3 = xd_dp2a_hi_us( P[0], T2, xd_dp2a_lo_us( P[1], T3, xd_dp2a_hi_us( P[2], T3, xd_dp2a_lo_us( P[3], T4, kb ) ) ) );
+                const int c4 = xd_dp2a_lo_us( P[1], T1, xd_dp2a_hi_us( P[2], T1, xd_dp2a_lo_us( P[3], T2, kb ) ) );
+                const int c5 = xd_dp2a_hi_us( P[1], T2, xd_dp2a_lo_us( P[2], T3, xd_dp2a_hi_us( P[3], T3, xd_dp2a_lo_us( P4, T4, kb ) ) ) );
+                const int c6 = xd_dp2a_lo_us( P[2], T1, xd_dp2a_hi_us( P[3], T1, xd_dp2a_lo_us( P4, T2, kb ) ) );
+                const int c7 = xd_dp2a_hi_us( P[2], T2, xd_dp2a_lo_us( P[3], T3, xd_dp2a_hi_us( P4, T3, xd_dp2a_lo_us( P5, T4, kb ) ) ) );
+                oc.x = xd_pack_sat4( c0 >> 10, c1 >> 10, c2 >> 10, c3 >> 10 );
+                oc.y = xd_pack_sat4( c4 >> 10, c5 >> 10, c6 >> 10, c7 >> 10 );
+            }
+
+            if( writer && y < y_end )
+            {
+                *(uint2 *)dh = oh;
+                *(uint2 *)dv = ov;
+                *(uint2 *)dc = oc;
+            }
+            dh += ls;
+            dv += ls;
+            dc += ls;
         }
     }
+}
+
+// blockIdx.x < n_full: a full strip of HP_UNITS units per warp, the block's four warps on consecutive row segments;
+// blockIdx.x == n_full: the tail_units units left over, in strips of tail_gw lanes
+__global__ void __launch_bounds__( 128 )
+xd_hpel_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, int n_full, int tail_units, int tail_gw )
+{
+    uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
+    const int wseg = blockIdx.y * 4 + ( threadIdx.x >> 5 );
+    const int unit0 = blockIdx.x * HP_UNITS;
+    if( (int)blockIdx.x < n_full || tail_gw == 32 )
+        xd_hpel_body<32>( g, slot, unit0, (int)blockIdx.x < n_full ? HP_UNITS : tail_units, wseg );
+    else if( tail_gw == 4 )
+        xd_hpel_body<4>( g, slot, unit0, tail_units, wseg );
+    else if( tail_gw == 8 )
+        xd_hpel_body<8>( g, slot, unit0, tail_units, wseg );
+    else
+        xd_hpel_body<16>( g, slot, unit0, tail_units, wseg );
 }
 
 // Padding of the three filtered planes = the final state of x264_frame_expand_border_filtered
@@ -757,10 +845,12 @@ extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_
     if( !ctx || !g || !slots || n_frames <= 0 )
         return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
-    const int n_words = ( g->luma_w + 8 ) >> 2, n_segs = ( g->luma_h + 16 + HP_ROWS - 1 ) / HP_ROWS;
-    dim3 grid( ( n_words + HP_STRIP - 1 ) / HP_STRIP, ( n_segs + 3 ) / 4, n_frames );
+    const int n_units = ( g->luma_w + 8 ) >> 3, n_segs = ( g->luma_h + 16 + HP_ROWS - 1 ) / HP_ROWS;
+    const int n_full = n_units / HP_UNITS, tail_units = n_units % HP_UNITS;
+    const int tail_gw = tail_units <= 2 ? 4 : tail_units <= 6 ? 8 : tail_units <= 14 ? 16 : 32;
+    dim3 grid( n_full + ( tail_units ? 1 : 0 ), ( n_segs + 3 ) / 4, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_HPEL, s );
-    xd_hpel_kernel<<<grid, 128, 0, s>>>( *g, slots );
+    xd_hpel_kernel<<<grid, 128, 0, s>>>( *g, slots, n_full, tail_units, tail_gw );
     xd_prof_end( ctx, XD_PROF_HPEL, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
