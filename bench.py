@@ -218,7 +218,9 @@ def recon_measure(pkg, ctx, torch, g, w, h, n_frames, first_frame=0, reps=3, qp=
         ctx.residual_frames(g, slots[g.slot_bytes:], pred, n_frames, qp, lv, nz, cbp)
         ev[2].record(stream)
         if rep == 0:
+            torch.cuda.synchronize()                       # the clone runs on torch's stream, the kernels on the context's
             recon0 = pred[: g.slot_bytes].clone()          # frame 0 before deblocking, for the check
+            torch.cuda.synchronize()
         ctx.deblock_frames(g, pred, n_frames, mb_type, part, cbp, bs, qp, 0, 0)
         ev[3].record(stream)
         torch.cuda.synchronize()
@@ -254,6 +256,25 @@ def recon_cpu_check(pkg, g, check):
     dt = time.perf_counter() - t0
     ok = ok and np.array_equal(pred, check["deblocked"])
     return bool(ok), dt, int(np.count_nonzero(cbp))
+
+
+def int_pipe_roofline(sad_px, satd_px, seconds, kernels):
+    """algorithmic integer instructions (SAD 0.25 per pixel comparison = one VABSDIFF4.U8.ACC per 4 pixels,
+    SATD 3.5 packed instructions per pixel) / time / the measured ALU-pipe peak (tools/int_pipe_peak.cu on this pool's
+    B200: 64 thread-instructions per clock per SM for VABSDIFF4 / IADD3 / LOP3 / PRMT / VIADD.16x2 / IDP.4A)"""
+    path = os.path.join(ROOT, "profiles", "int_pipe_peak.json")
+    per_clk_sm, sms, khz = 64.0, 148, 1965000
+    src = "fallback: 64 thread-inst/clk/SM x 148 SMs x 1965 MHz"
+    if os.path.exists(path):
+        d = json.load(open(path))
+        per_clk_sm = next(o["thread_inst_per_clk_per_sm"] for o in d["ops"] if o["op"].startswith("VABSDIFF4.U8.ACC"))
+        sms, khz = d["sms"], d["max_clock_khz"]
+        src = "measured (profiles/int_pipe_peak.json)"
+    peak = per_clk_sm * sms * khz * 1e3
+    inst = 0.25 * sad_px + 3.5 * satd_px
+    return {"kernels": kernels, "algorithmic_thread_inst": inst, "achieved_tinst_per_s": inst / seconds / 1e12,
+            "peak_tinst_per_s": peak / 1e12, "frac": inst / seconds / peak, "peak_source": src,
+            "per_pixel": {"sad": 0.25, "satd": 3.5}}
 
 
 # --------------------------------------------------------------------------------------------
@@ -523,7 +544,7 @@ def main():
         me_ms, me_blocks0, me_slots = me_search_measure(pkg, ctx, torch, g, luma_dev, d_mvs[: clip_len].cpu().numpy(), me_pairs)
     rc_ms = rc_check = None
     if rank == 0 and not args.no_me:
-        rc_frames = 32 if w * h <= 1920 * 1088 else 8
+        rc_frames = 96 if w * h <= 1920 * 1088 else 16
         rc_ms, rc_check = recon_measure(pkg, ctx, torch, g, w, h, rc_frames)
 
     # ---- max over ranks
@@ -570,9 +591,12 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(bytes_per_pair * pairs_per_launch),
                          "avg_launch_ms": inter_avg_s * 1e3, "launches_timed": inter_n,
+                         "int_pipe": int_pipe_roofline(sad_px, satd_px, (prof["la_inter"][0] + prof["la_intra"][0]) / args.steps / 1e3,
+                                                       "xd_la_multi_kernel<4> + xd_la_intra_kernel"),
                          "note": "dependent-search wavefront kernel (SURVEY 8(d) config 2): HBM % reported as required; ncu "
-                                 "(profiles/r01k) shows instruction issue (56 %) and the L1 data pipe (61 % of peak "
-                                 "wavefronts) as the limiters; DRAM traffic is below the algorithmic bytes because "
+                                 "(profiles/r01k) shows instruction issue (56 % of 4 warp-inst/clk/SM), the ALU pipe (60 % of "
+                                 "its measured 2 warp-inst/clk/SM, profiles/int_pipe_peak.json) and the L1 data pipe (61 % of "
+                                 "peak wavefronts) as the limiters; DRAM traffic is below the algorithmic bytes because "
                                  "consecutive pairs share a reference frame in L2"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "pixel_cmp": {"sad_gpix_per_s": sad_px * world / step_s / 1e9, "satd_gpix_per_s": satd_px * world / step_s / 1e9,
@@ -606,7 +630,8 @@ def main():
                            "sad_pix_per_frame": sad, "satd_pix_per_frame": satd,
                            "counted_by": "the CPU oracle's instrumented run of the same block lists (frame pair 0)",
                            "bit_exact_vs_oracle": all(c["bit_exact"] for c in cnt.values()),
-                           "cpu_port_1core_frames_per_s": 1.0 / sum(c["cpu_s"] for c in cnt.values())})
+                           "cpu_port_1core_frames_per_s": 1.0 / sum(c["cpu_s"] for c in cnt.values()),
+                           "int_pipe": int_pipe_roofline(sad, satd, tot_ms / 1e3, "xd_me_sized_kernel<W,H>, 7 sizes")})
             line["me_search"] = me
         if rc_ms is not None:
             tot = sum(rc_ms.values())

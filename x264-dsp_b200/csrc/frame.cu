@@ -378,6 +378,7 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
 //   clip + pack: cvt.pack.sat.u8.s32 (I2IP), two pixels per instruction
 #define HP_ROWS 48
 #define HP_UNITS 30
+#define HP_AHEAD 2                      // source rows in flight per lane (must divide 6, the unroll of the row loop)
 
 // (a+f) - 5 (b+e) + 20 (c+d) + (32768 + 16) in both halves; inputs are 0..255 per half
 __device__ __forceinline__ uint32_t xd_hp_tap6_packed( uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f )
@@ -425,7 +426,7 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
     if( !__any_sync( 0xffffffffu, seg_ok ) )
         return;
     // strips of a partly filled warp that fall below the plane redo the first segment without storing; a segment
-    // reads at most 28 rows past the padded plane N, i.e. into plane H of the same slot
+    // reads at most 32 rows past the padded plane N, i.e. into plane H of the same slot
     const int y0 = seg_ok ? seg * HP_ROWS - 8 : -8;              // first output row
     const int n_units = ( g.luma_w + 8 ) >> 3;
     // halo lanes (and idle lanes past the strip) still read inside the allocation: units -1 .. n_units, pad is 32
@@ -449,12 +450,16 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
         if( k >= 2 )
             R[k - 2] = w;
     }
-    // the rows two and three iterations ahead are already in flight: a row's DRAM latency is hidden behind two rows of
-    // arithmetic instead of stalling the warp at its first use (ncu r01n: 9.6 long-scoreboard stalls per issue)
-    uint2 Q[2];
-    Q[0] = *(const uint2 *)ps;
-    Q[1] = *(const uint2 *)( ps + ls );
-    ps += 2 * ls;
+    // HP_AHEAD source rows are in flight per lane, so that a row's DRAM latency is hidden behind the arithmetic of the
+    // rows before it (without it: 9.6 long-scoreboard stall cycles per issue, 3.3 us per frame; 2 rows: 2.65 us;
+    // 3 and 6 rows measured the same, so the remaining stalls are not a matter of bytes in flight)
+    uint2 Q[HP_AHEAD];
+#pragma unroll
+    for( int k = 0; k < HP_AHEAD; k++ )
+    {
+        Q[k] = *(const uint2 *)ps;
+        ps += ls;
+    }
     const uint32_t TA0 = 0x1414FB01u, TB0 = 0x000001FBu;         // (1,-5,20,20) (-5,1,0,0)
     const uint32_t TA1 = 0x14FB0100u, TB1 = 0x0001FB14u;         // (0,1,-5,20) (20,-5,1,0)
     const uint32_t T1 = 0x1414FB01u, T2 = 0x010001FBu;           // lo (1,-5) hi (20,20); lo (-5,1) hi (0,1)
@@ -468,8 +473,8 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
             const int i0 = u % 6, i1 = ( u + 1 ) % 6, i2 = ( u + 2 ) % 6, i3 = ( u + 3 ) % 6, i4 = ( u + 4 ) % 6, i5 = ( u + 5 ) % 6;
             const uint2 cur = R[u % 3];
             {
-                const uint2 w = Q[u % 2];
-                Q[u % 2] = *(const uint2 *)ps;
+                const uint2 w = Q[u % HP_AHEAD];
+                Q[u % HP_AHEAD] = *(const uint2 *)ps;
                 ps += ls;
                 A[i5][0] = __byte_perm( w.x, 0u, 0x4140 );
                 A[i5][1] = __byte_perm( w.x, 0u, 0x4342 );
