@@ -378,7 +378,20 @@ xd_lowres_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, const uint8_t *
 //   clip + pack: cvt.pack.sat.u8.s32 (I2IP), two pixels per instruction
 #define HP_ROWS 48
 #define HP_UNITS 30
-#define HP_AHEAD 2                      // source rows in flight per lane (must divide 6, the unroll of the row loop)
+#define HP_RING 6                       // ring slots per lane (the unroll of the row loop)
+#define HP_AHEAD 5                      // source rows in flight per lane
+
+// one 8-byte cp.async as its own group
+__device__ __forceinline__ void xd_cp_async8( void *smem, const void *gmem )
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared( smem );
+    asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;" :: "r"( s ), "l"( gmem ) : "memory" );
+}
+template<int N>
+__device__ __forceinline__ void xd_cp_async_wait()
+{
+    asm volatile( "cp.async.wait_group %0;" :: "n"( N ) : "memory" );
+}
 
 // (a+f) - 5 (b+e) + 20 (c+d) + (32768 + 16) in both halves; inputs are 0..255 per half
 __device__ __forceinline__ uint32_t xd_hp_tap6_packed( uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f )
@@ -415,7 +428,8 @@ __device__ __forceinline__ uint32_t xd_pack_sat4( int a0, int a1, int a2, int a3
 }
 
 template<int GW>
-__device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *__restrict__ slot, int unit0, int strip_units, int wseg )
+__device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *__restrict__ slot, int unit0, int strip_units, int wseg,
+                                              uint2 *s_ring )
 {
     const int lane = threadIdx.x & 31;
     const int gl = lane & ( GW - 1 );
@@ -426,7 +440,7 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
     if( !__any_sync( 0xffffffffu, seg_ok ) )
         return;
     // strips of a partly filled warp that fall below the plane redo the first segment without storing; a segment
-    // reads at most 32 rows past the padded plane N, i.e. into plane H of the same slot
+    // reads at most 31 rows past the padded plane N, i.e. into plane H of the same slot
     const int y0 = seg_ok ? seg * HP_ROWS - 8 : -8;              // first output row
     const int n_units = ( g.luma_w + 8 ) >> 3;
     // halo lanes (and idle lanes past the strip) still read inside the allocation: units -1 .. n_units, pad is 32
@@ -450,14 +464,15 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
         if( k >= 2 )
             R[k - 2] = w;
     }
-    // HP_AHEAD source rows are in flight per lane, so that a row's DRAM latency is hidden behind the arithmetic of the
-    // rows before it (without it: 9.6 long-scoreboard stall cycles per issue, 3.3 us per frame; 2 rows: 2.65 us;
-    // 3 and 6 rows measured the same, so the remaining stalls are not a matter of bytes in flight)
-    uint2 Q[HP_AHEAD];
+    // HP_AHEAD source rows are in flight per lane through cp.async into a private ring in shared memory.  Plain
+    // prefetch loads into registers did not get past two rows: the loads of a warp share scoreboards, waiting for the
+    // oldest one waits for all of them (2, 3 and 6 rows ahead all measured 2.65 us per frame, 40 % of the stall samples
+    // on the first use of the row); cp.async groups complete in order and are waited for by count.
+    uint2 *ring = s_ring + threadIdx.x;                          // slot k of this thread: ring[k * 128]
 #pragma unroll
     for( int k = 0; k < HP_AHEAD; k++ )
     {
-        Q[k] = *(const uint2 *)ps;
+        xd_cp_async8( ring + k * 128, ps );
         ps += ls;
     }
     const uint32_t TA0 = 0x1414FB01u, TB0 = 0x000001FBu;         // (1,-5,20,20) (-5,1,0,0)
@@ -473,8 +488,9 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
             const int i0 = u % 6, i1 = ( u + 1 ) % 6, i2 = ( u + 2 ) % 6, i3 = ( u + 3 ) % 6, i4 = ( u + 4 ) % 6, i5 = ( u + 5 ) % 6;
             const uint2 cur = R[u % 3];
             {
-                const uint2 w = Q[u % HP_AHEAD];
-                Q[u % HP_AHEAD] = *(const uint2 *)ps;
+                xd_cp_async_wait<HP_AHEAD - 1>();                 // the oldest row in flight has landed
+                const uint2 w = ring[( u % HP_RING ) * 128];
+                xd_cp_async8( ring + ( ( u + HP_AHEAD ) % HP_RING ) * 128, ps );    // the slot read one row ago
                 ps += ls;
                 A[i5][0] = __byte_perm( w.x, 0u, 0x4140 );
                 A[i5][1] = __byte_perm( w.x, 0u, 0x4342 );
@@ -539,24 +555,31 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
             dc += ls;
         }
     }
+    xd_cp_async_wait<0>();                                       // nothing of this thread's may still be landing at exit
 }
 
-// blockIdx.x < n_full: a full strip of HP_UNITS units per warp, the block's four warps on consecutive row segments;
-// blockIdx.x == n_full: the tail_units units left over, in strips of tail_gw lanes
-__global__ void __launch_bounds__( 128 )
+// The four warps of a block take four ADJACENT strips of the same row segment (they start together and stay close, so
+// the block touches ~1 KB of consecutive bytes per row and plane at a time; with the warps on four row segments of one
+// strip instead, every access of the kernel was an isolated 240-byte piece).  Strip n_full is the tail: the tail_units
+// units left over, in strips of tail_gw lanes.
+__global__ void __launch_bounds__( 128, 6 )
 xd_hpel_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, int n_full, int tail_units, int tail_gw )
 {
+    __shared__ uint2 s_ring[HP_RING * 128];
     uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
-    const int wseg = blockIdx.y * 4 + ( threadIdx.x >> 5 );
-    const int unit0 = blockIdx.x * HP_UNITS;
-    if( (int)blockIdx.x < n_full || tail_gw == 32 )
-        xd_hpel_body<32>( g, slot, unit0, (int)blockIdx.x < n_full ? HP_UNITS : tail_units, wseg );
+    const int strip = blockIdx.x * 4 + ( threadIdx.x >> 5 );
+    const int wseg = blockIdx.y;
+    const int unit0 = strip * HP_UNITS;
+    if( strip > n_full || ( strip == n_full && !tail_units ) )
+        return;
+    if( strip < n_full || tail_gw == 32 )
+        xd_hpel_body<32>( g, slot, unit0, strip < n_full ? HP_UNITS : tail_units, wseg, s_ring );
     else if( tail_gw == 4 )
-        xd_hpel_body<4>( g, slot, unit0, tail_units, wseg );
+        xd_hpel_body<4>( g, slot, unit0, tail_units, wseg, s_ring );
     else if( tail_gw == 8 )
-        xd_hpel_body<8>( g, slot, unit0, tail_units, wseg );
+        xd_hpel_body<8>( g, slot, unit0, tail_units, wseg, s_ring );
     else
-        xd_hpel_body<16>( g, slot, unit0, tail_units, wseg );
+        xd_hpel_body<16>( g, slot, unit0, tail_units, wseg, s_ring );
 }
 
 // Padding of the three filtered planes = the final state of x264_frame_expand_border_filtered
@@ -853,7 +876,7 @@ extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_
     const int n_units = ( g->luma_w + 8 ) >> 3, n_segs = ( g->luma_h + 16 + HP_ROWS - 1 ) / HP_ROWS;
     const int n_full = n_units / HP_UNITS, tail_units = n_units % HP_UNITS;
     const int tail_gw = tail_units <= 2 ? 4 : tail_units <= 6 ? 8 : tail_units <= 14 ? 16 : 32;
-    dim3 grid( n_full + ( tail_units ? 1 : 0 ), ( n_segs + 3 ) / 4, n_frames );
+    dim3 grid( ( n_full + ( tail_units ? 1 : 0 ) + 3 ) / 4, n_segs, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_HPEL, s );
     xd_hpel_kernel<<<grid, 128, 0, s>>>( *g, slots, n_full, tail_units, tail_gw );
     xd_prof_end( ctx, XD_PROF_HPEL, pslot, s );
