@@ -451,7 +451,21 @@ def main():
     import torch
     import torch.distributed as dist
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # NCCL announces its version on stdout when the communicator is created (NCCL_DEBUG=VERSION on this image);
+        # stdout carries exactly one JSON line, so the banner goes to stderr
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
     torch.cuda.set_device(local_rank)
     ctx = pkg.Context(local_rank)
     w, h, clips, clip_len = args.width, args.height, args.clips, args.clip_len

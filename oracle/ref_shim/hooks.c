@@ -234,3 +234,77 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
     m->cost = out.cost;
     m->cost_mv = out.cost_mv;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * x264_macroblock_encode      encoder/macroblock.c:310     called from encoder/encoder.c (slice loop)
+ *
+ * Inter macroblocks of a P slice (P_L0, P_8x8; any partition -- the residual is one 16x16 transform
+ * whatever the motion partition): the reference's own x264_mb_mc builds the prediction in fdec, the
+ * hook turns source + prediction into levels / nnz / cbp / reconstruction (x264dsp_residual_frame_dev
+ * on the device), and what comes back is laid out where x264_macroblock_write_cabac / _cavlc and
+ * x264_macroblock_cache_save read it (the entropy coder's hand-off format):
+ *   levels  -> h->dct.luma4x4[0..15], h->dct.chroma_dc[0..1], h->dct.luma4x4[16..19] (U AC), [32..35] (V AC)
+ *   nnz     -> h->mb.cache.non_zero_count[x264_scan8[..]]
+ *   cbp     -> h->mb.i_cbp_luma, h->mb.i_cbp_chroma, h->mb.cbp[mb_xy] (CABAC: with the DC flags in bits 8..10)
+ * followed by the forced-P_SKIP rule of macroblock.c:465-485.  Buffer shapes are xref_encode_inter_mb's. */
+typedef int (*xref_mbenc_cb)( void *h, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y, uint8_t *fdec_c,
+                              int qp, int16_t *levels, uint8_t *nnz, int *cbp );
+xref_mbenc_cb xref_hook_mbenc = NULL;
+int xref_hook_mbenc_calls = 0;
+
+void xref_set_mbenc_hook( xref_mbenc_cb cb )
+{
+    xref_hook_mbenc = cb;
+    xref_hook_mbenc_calls = 0;
+}
+int xref_mbenc_hook_calls( void ) { return xref_hook_mbenc_calls; }
+
+void xref_orig_macroblock_encode( x264_t *h );
+
+void x264_macroblock_encode( x264_t *h )
+{
+    int16_t levels[392];
+    uint8_t nnz[27];
+    int cbp = 0, i;
+    if( !xref_hook_mbenc || IS_INTRA( h->mb.i_type ) || h->mb.i_type == P_SKIP || h->sh.i_type != SLICE_TYPE_P
+        || !h->mb.b_dct_decimate || h->mb.b_noise_reduction || h->mb.b_transform_8x8 || h->mb.b_lossless
+        || h->mb.i_chroma_qp != h->chroma_qp_table[h->mb.i_qp] )
+    {
+        xref_orig_macroblock_encode( h );
+        return;
+    }
+    h->mb.i_cbp_luma = 0;
+    h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = 0;
+    if( !h->mb.b_skip_mc )
+        x264_mb_mc( h );
+    memset( levels, 0, sizeof(levels) );
+    if( xref_hook_mbenc( h, h->mb.pic.p_fenc[0], h->mb.pic.p_fenc[1], h->mb.pic.p_fdec[0], h->mb.pic.p_fdec[1],
+                         h->mb.i_qp, levels, nnz, &cbp ) )
+    {
+        h->mb.b_skip_mc = 1;                          /* the prediction is already in fdec */
+        xref_orig_macroblock_encode( h );
+        return;
+    }
+    xref_hook_mbenc_calls++;
+    memcpy( h->dct.luma4x4[0], levels, 16*16*sizeof(int16_t) );
+    memcpy( h->dct.chroma_dc[0], levels + 256, 4*sizeof(int16_t) );
+    memcpy( h->dct.chroma_dc[1], levels + 260, 4*sizeof(int16_t) );
+    memcpy( h->dct.luma4x4[16], levels + 264, 4*16*sizeof(int16_t) );
+    memcpy( h->dct.luma4x4[32], levels + 328, 4*16*sizeof(int16_t) );
+    for( i = 0; i < 16; i++ )
+        h->mb.cache.non_zero_count[x264_scan8[i]] = nnz[i];
+    for( i = 0; i < 4; i++ )
+    {
+        h->mb.cache.non_zero_count[x264_scan8[16+i]] = nnz[16+i];
+        h->mb.cache.non_zero_count[x264_scan8[32+i]] = nnz[20+i];
+    }
+    h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]] = nnz[25];
+    h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]] = nnz[26];
+    h->mb.i_cbp_luma = cbp & 15;
+    h->mb.i_cbp_chroma = ( cbp >> 4 ) & 3;
+    h->mb.cbp[h->mb.i_mb_xy] = h->param.b_cabac ? cbp : ( cbp & 0x3f );
+    if( h->mb.i_type == P_L0 && h->mb.i_partition == D_16x16 && !( h->mb.i_cbp_luma | h->mb.i_cbp_chroma )
+        && M32( h->mb.cache.mv[0][x264_scan8[0]] ) == M32( h->mb.cache.pskip_mv )
+        && h->mb.cache.ref[0][x264_scan8[0]] == 0 )
+        h->mb.i_type = P_SKIP;
+}

@@ -7,8 +7,11 @@ of its hot-path drivers served by libx264dsp_b200.so --
                                                 -> x264dsp_deblock_frame_dev + x264dsp_frame_expand_border_dev
   x264_slicetype_frame_cost (its per-frame cache, filled before x264_slicetype_decide runs)
                                                 -> x264dsp_lookahead_frame_cost_dev
-  x264_me_search_ref (every partition search of the main encode, last two cases)
+  x264_me_search_ref (every partition search of the main encode, last cases)
                                                 -> x264dsp_me_search_batch_dev on frames kept resident on the device
+  x264_macroblock_encode (every inter macroblock of the P slices, last two cases: DCT, quant, zig-zag, dequant,
+  decimation, chroma DC, IDCT; levels / nnz / cbp handed to the reference's CABAC writer)
+                                                -> x264dsp_residual_frame_dev
 
 through the doors of oracle/ref_shim/hooks.c (the glue INTEGRATION.md describes), and must emit the
 byte-identical bitstream.  Every plane the main encode searches in (half-pel planes of every
@@ -29,13 +32,17 @@ COST_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_voi
 FDEC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                       C.c_int, C.c_int, C.c_int)
 ME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
+MBENC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                       C.POINTER(C.c_int))
 
 
-@pytest.mark.parametrize("w,h,n,cut,me,subme,psub,inloop,mehook", [
-    (352, 288, 12, 7, 1, 5, 0, False, False), (208, 160, 8, -1, 0, 2, 0, False, False),
-    (352, 288, 12, 7, 1, 5, 0, True, False), (208, 160, 8, 4, 1, 3, 0, True, False),
-    (352, 288, 10, 6, 1, 5, 0, True, True), (208, 160, 8, 4, 0, 2, 1, True, True), (208, 160, 6, -1, 1, 4, 1, True, True)])
-def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me, subme, psub, inloop, mehook):
+@pytest.mark.parametrize("w,h,n,cut,me,subme,psub,inloop,mehook,mbenc", [
+    (352, 288, 12, 7, 1, 5, 0, False, False, False), (208, 160, 8, -1, 0, 2, 0, False, False, False),
+    (352, 288, 12, 7, 1, 5, 0, True, False, False), (208, 160, 8, 4, 1, 3, 0, True, False, False),
+    (352, 288, 10, 6, 1, 5, 0, True, True, False), (208, 160, 8, 4, 0, 2, 1, True, True, False),
+    (208, 160, 6, -1, 1, 4, 1, True, True, False),
+    (208, 160, 6, 3, 1, 2, 0, True, False, True), (176, 144, 5, -1, 1, 5, 1, True, True, True)])
+def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me, subme, psub, inloop, mehook, mbenc):
     import torch
     lib = cc.ref()
     assert lib is not None, "oracle/_ref/libx264ref.so must travel to the GPU box (make -C oracle ref)"
@@ -140,6 +147,47 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         me_calls[0] += 1
         return 0
 
+    # one macroblock as a 16x16 "frame": source and prediction slots in the library's own plane layout
+    g1 = pkg.geometry(16, 16)
+    mb_slots = torch.zeros(2 * g1.slot_bytes, dtype=torch.uint8, device="cuda")
+    mb_stage = np.zeros((2, g1.slot_bytes), np.uint8)
+    d_lv = torch.zeros(pkg.RES_LEVELS_PER_MB, dtype=torch.int16, device="cuda")
+    d_nz = torch.zeros(pkg.RES_NNZ_PER_MB, dtype=torch.uint8, device="cuda")
+    d_cbp = torch.zeros(1, dtype=torch.int16, device="cuda")
+    mbenc_calls = [0]
+
+    def mb_planes(buf):
+        luma = buf[g1.luma_origin:][: 16 * g1.luma_stride].reshape(16, g1.luma_stride)[:, :16]
+        co = g1.slot_chroma_off + g1.chroma_origin
+        chroma = buf[co:][: 8 * g1.chroma_stride].reshape(8, g1.chroma_stride)[:, :16]
+        return luma, chroma
+
+    @MBENC_CB
+    def mbenc_cb(hv, fenc_y, fenc_c, fdec_y, fdec_c, qp, levels, nnz, cbp):
+        fy = host_view(fenc_y, 16 * 16).reshape(16, 16)
+        fc = host_view(fenc_c, 8 * 16).reshape(8, 16)              # U at +0, V at +8
+        dy = host_view(fdec_y, 16 * 32).reshape(16, 32)
+        dc = host_view(fdec_c, 8 * 32).reshape(8, 32)              # U at +0, V at +16
+        for k, (y_, u_, v_) in enumerate(((fy, fc[:, :8], fc[:, 8:16]), (dy[:, :16], dc[:, :8], dc[:, 16:24]))):
+            luma, chroma = mb_planes(mb_stage[k])
+            luma[:] = y_
+            chroma[:, 0::2] = u_
+            chroma[:, 1::2] = v_
+        mb_slots.copy_(torch.from_numpy(mb_stage.reshape(-1)))
+        torch.cuda.synchronize()
+        ctx.residual_frame(g1, mb_slots[: g1.slot_bytes], mb_slots[g1.slot_bytes:], qp, d_lv, d_nz, d_cbp)
+        ctx.sync()
+        rec = mb_slots[g1.slot_bytes:].cpu().numpy()
+        luma, chroma = mb_planes(rec)
+        dy[:, :16] = luma
+        dc[:, :8] = chroma[:, 0::2]
+        dc[:, 16:24] = chroma[:, 1::2]
+        host_view(levels, 2 * pkg.RES_LEVELS_PER_MB)[:] = d_lv.cpu().numpy().view(np.uint8)
+        host_view(nnz, pkg.RES_NNZ_PER_MB)[:] = d_nz.cpu().numpy()
+        cbp[0] = int(d_cbp.cpu().numpy()[0])
+        mbenc_calls[0] += 1
+        return 0
+
     outs, calls = [], (C.c_int * 3)()
     for use_gpu in (False, True):
         enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=26, psub16x16=psub)
@@ -149,6 +197,8 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
                 lib.xref_set_fdec_hook(fdec_cb)
             if mehook:
                 lib.xref_set_me_hook(me_cb)
+            if mbenc:
+                lib.xref_set_mbenc_hook(mbenc_cb)
         else:
             lib.xref_set_driver_hooks(None, None, None)
         out = np.zeros(1 << 20, np.uint8)
@@ -160,6 +210,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             lib.xref_set_driver_hooks(None, None, None)
             lib.xref_set_fdec_hook(None)
             lib.xref_set_me_hook(None)
+            lib.xref_set_mbenc_hook(None)
         assert size > 0, size
         outs.append(out[:size].copy())
         if use_gpu:
@@ -169,6 +220,8 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             assert ctx.launches - launches0 >= 2 * n, "the encode must have gone through the CUDA kernels"
             if mehook:
                 assert me_calls[0] >= (n - 3) * g.mb_count // 2, f"only {me_calls[0]} searches went to the device"
+            if mbenc:
+                assert mbenc_calls[0] >= g.mb_count, f"only {mbenc_calls[0]} macroblocks were coded on the device"
             if inloop:
                 assert deblocked[0] >= n - 1, f"deblocking ran on the device for {deblocked[0]} of {n} frames"
     assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), \
