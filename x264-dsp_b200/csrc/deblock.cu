@@ -88,7 +88,10 @@ __device__ __forceinline__ void xd_db_put16( uint8_t *row, uint4 v )        // r
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
 }
 
-__global__ void __launch_bounds__( DB_WARPS * 32 )
+// 8 CTAs per SM (58 registers): a row's warp spends most of its time in dependent-issue latency or waiting for the
+// row above, so throughput follows the number of resident rows -- 18.7 -> 14.9 us per 1080p frame in a 192-frame batch
+// against 6 CTAs (84 registers); 10 CTAs (48 registers, spills) measured no better
+__global__ void __launch_bounds__( DB_WARPS * 32, 8 )
 xd_deblock_kernel( xd_db_args A )
 {
     __shared__ __align__( 16 ) uint8_t s_luma[DB_WARPS][DB_LROWS * DB_PITCH];
