@@ -803,6 +803,58 @@ __device__ __forceinline__ uint32_t xd_lm_sad_fpel( const xd_lm_block<RPL> &B, i
     return xd_lm_sad<RPL>( B, p );
 }
 
+// The four neighbours of a diamond step (me.c:237-274) from ONE window of the reference plane: the lane's two rows
+// moved up / down / left / right by one pixel all lie inside rows Y-1 .. Y+2, columns X-1 .. X+8.  Four separate
+// fetches cost four address computations and sixteen 8-byte loads per lane; the window costs one address computation
+// and eight loads (a third tile column only when the window starts on a tile's last byte), and the candidates are
+// funnel shifts of the window's words by constant amounts.
+template<int RPL>
+__device__ __forceinline__ void xd_lm_sad_dia( const xd_lm_block<RPL> &B, int mx, int my,
+                                               uint32_t &up, uint32_t &dn, uint32_t &lf, uint32_t &rt )
+{
+    if constexpr( RPL != 2 )
+    {
+        up = xd_lm_sad_fpel<RPL>( B, mx, my - 1 );
+        dn = xd_lm_sad_fpel<RPL>( B, mx, my + 1 );
+        lf = xd_lm_sad_fpel<RPL>( B, mx - 1, my );
+        rt = xd_lm_sad_fpel<RPL>( B, mx + 1, my );
+    }
+    else
+    {
+        const int XW = B.X0 + mx - 1, R0 = B.Y0 + my - 1;        // window origin: column X-1, row Y-1
+        int off = ( ( ( R0 >> 3 ) * B.tw + ( XW >> 3 ) ) << 6 ) + ( ( R0 & 7 ) << 3 );
+        const int o = XW & 7;
+        const uint32_t sh = (uint32_t)o << 3;                      // the funnel shift takes it modulo 32
+        const bool hi4 = ( o & 4 ) != 0, third = o == 7;
+        const int jump = ( B.tw << 6 ) - 56;                       // from row 7 of a tile to row 0 of the tile below
+        uint32_t V[4][3];                                          // bytes X-1 .. X+10 of the four rows
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            const uint2 *w = (const uint2 *)( B.tref + off );
+            const uint2 lo = __ldg( w ), hi = __ldg( w + 8 );
+            uint32_t ex = 0;
+            if( third )
+                ex = __ldg( (const uint32_t *)( w + 16 ) );
+            const uint32_t w0 = hi4 ? lo.y : lo.x, w1 = hi4 ? hi.x : lo.y, w2 = hi4 ? hi.y : hi.x, w3 = hi4 ? ex : hi.y;
+            V[r][0] = __funnelshift_r( w0, w1, sh );
+            V[r][1] = __funnelshift_r( w1, w2, sh );
+            V[r][2] = __funnelshift_r( w2, w3, sh );
+            off += ( ( R0 + r ) & 7 ) == 7 ? jump : 8;
+        }
+        uint2 c[4];                                                // the rows at column X
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+            c[r] = make_uint2( __funnelshift_r( V[r][0], V[r][1], 8 ), __funnelshift_r( V[r][1], V[r][2], 8 ) );
+        up = xd_lq_sad8( c[1], B.fenc[1], xd_lq_sad8( c[0], B.fenc[0], 0u ) );
+        dn = xd_lq_sad8( c[3], B.fenc[1], xd_lq_sad8( c[2], B.fenc[0], 0u ) );
+        lf = xd_lq_sad8( make_uint2( V[2][0], V[2][1] ), B.fenc[1], xd_lq_sad8( make_uint2( V[1][0], V[1][1] ), B.fenc[0], 0u ) );
+        const uint2 r1 = make_uint2( __funnelshift_r( V[1][0], V[1][1], 16 ), __funnelshift_r( V[1][1], V[1][2], 16 ) );
+        const uint2 r2 = make_uint2( __funnelshift_r( V[2][0], V[2][1], 16 ), __funnelshift_r( V[2][1], V[2][2], 16 ) );
+        rt = xd_lq_sad8( r2, B.fenc[1], xd_lq_sad8( r1, B.fenc[0], 0u ) );
+    }
+}
+
 template<int RPL>
 __device__ __forceinline__ uint32_t xd_lm_sad_qpel( const xd_lm_block<RPL> &B, int qx, int qy )
 {
@@ -1110,8 +1162,10 @@ xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                     uint32_t w0 = 0, w1 = 0;
                     if( dia )
                     {
-                        w0 = xd_lq_pack( xd_lm_sad_fpel<RPL>( B, bmx, bmy - 1 ), xd_lm_sad_fpel<RPL>( B, bmx, bmy + 1 ) );
-                        w1 = xd_lq_pack( xd_lm_sad_fpel<RPL>( B, bmx - 1, bmy ), xd_lm_sad_fpel<RPL>( B, bmx + 1, bmy ) );
+                        uint32_t su, sd, sl, sr;
+                        xd_lm_sad_dia<RPL>( B, bmx, bmy, su, sd, sl, sr );
+                        w0 = xd_lq_pack( su, sd );
+                        w1 = xd_lq_pack( sl, sr );
                         if( q < 4 )
                         {
                             const int dx = q == 2 ? -1 : q == 3 ? 1 : 0, dy = q == 0 ? -1 : q == 1 ? 1 : 0;
