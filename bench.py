@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--clips", type=int, default=128, help="independent 8-frame clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=256, help="independent 8-frame clips per GPU per step")
     ap.add_argument("--clip-len", type=int, default=8)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
