@@ -326,6 +326,20 @@ int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
                                  const uint8_t *fenc_slots, uint8_t *pred_slots, int n_frames, int qp,
                                  int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream );
 
+/* Macroblocks of two kinds in one launch: mb_kind[frame][mb] = 0 codes the macroblock as above (inter, P slice),
+ * 1 codes it as an I16x16 macroblock of an I slice -- x264_mb_encode_i16x16 (encoder/macroblock.c:72-162: AC blocks
+ * with the CQM_4IY tables, the sixteen DC terms through dct4x4dc / quant_4x4_dc / idct4x4dc / dequant_4x4_dc,
+ * add16x16_idct or add16x16_idct_dc) and x264_mb_encode_chroma with b_inter = 0 (macroblock.c:175-305), both with
+ * h->mb.b_dct_decimate = 0 as in an I slice.  pred_slot holds the intra prediction the caller chose
+ * (h->predict_16x16[mode] / h->predict_chroma[mode] output), reconstruction in place.
+ *   luma_dc [frame][mb][16] int16   zig-zagged levels of the luma DC block (h->dct.luma16x16_dc), zero for kind 0;
+ *                                   may be NULL.  nnz[24] and bit 8 of cbp carry its non-zero flag.
+ * mb_kind == NULL codes every macroblock as kind 0. */
+int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                       const uint8_t *fenc_slots, uint8_t *pred_slots, int n_frames, int qp,
+                                       const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc,
+                                       uint8_t *nnz, int16_t *cbp, void *stream );
+
 /* x264_mb_mc for P_L0 16x16 macroblocks (common/macroblock.c:8-28; mc_luma common/mc.c:216-239,
  * mc_chroma common/mc.c:290-323): builds the prediction frame from one quarter-pel MV per MB. */
 int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,

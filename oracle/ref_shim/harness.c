@@ -432,6 +432,74 @@ int xref_encode_inter_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c
     return h->mb.cbp[0];
 }
 
+/* x264_macroblock_encode for one I16x16 macroblock of an I slice whose prediction (luma and chroma) is
+ * already in p_fdec: the predictors the function would call are swapped for no-ops during the call (the
+ * tables are plain data members of x264_t), everything else is the reference's own code.  Same buffer
+ * shapes as xref_encode_inter_mb; luma_dc receives h->dct.luma16x16_dc[0]. */
+static void xref_predict_noop( pixel *src ) { (void)src; }
+
+int xref_encode_intra16_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y,
+                            uint8_t *fdec_c, int qp, int16_t *levels, int16_t *luma_dc, uint8_t *nnz )
+{
+    x264_t *h = hv;
+    int i, y;
+    x264_predict_t keep16 = h->predict_16x16[0], keepc = h->predict_chroma[0];
+    h->sh.i_type = SLICE_TYPE_I;
+    x264_macroblock_thread_init( h );
+    h->mb.i_type = I_16x16;
+    h->mb.i_intra16x16_pred_mode = 0;
+    h->mb.i_chroma_pred_mode = 0;
+    h->mb.b_dct_decimate = 0;
+    h->mb.b_noise_reduction = 0;
+    h->mb.b_transform_8x8 = 0;
+    h->nr_count = h->nr_count_buf[0];
+    h->mb.i_qp = qp;
+    h->mb.i_chroma_qp = h->chroma_qp_table[qp];
+    h->mb.i_mb_xy = 0;
+    memset( &h->dct, 0, sizeof(h->dct) );
+    memset( h->mb.cache.non_zero_count, 0, sizeof(h->mb.cache.non_zero_count) );
+    for( y = 0; y < 16; y++ )
+    {
+        memcpy( h->mb.pic.p_fenc[0] + y*FENC_STRIDE, fenc_y + y*16, 16 );
+        memcpy( h->mb.pic.p_fdec[0] + y*FDEC_STRIDE, fdec_y + y*32, 16 );
+    }
+    for( y = 0; y < 8; y++ )
+    {
+        memcpy( h->mb.pic.p_fenc[1] + y*FENC_STRIDE, fenc_c + y*16, 16 );
+        memcpy( h->mb.pic.p_fdec[1] + y*FDEC_STRIDE, fdec_c + y*32, 8 );
+        memcpy( h->mb.pic.p_fdec[2] + y*FDEC_STRIDE, fdec_c + y*32 + 16, 8 );
+    }
+    h->predict_16x16[0] = xref_predict_noop;
+    h->predict_chroma[0] = xref_predict_noop;
+    x264_macroblock_encode( h );
+    h->predict_16x16[0] = keep16;
+    h->predict_chroma[0] = keepc;
+    for( y = 0; y < 16; y++ )
+        memcpy( fdec_y + y*32, h->mb.pic.p_fdec[0] + y*FDEC_STRIDE, 16 );
+    for( y = 0; y < 8; y++ )
+    {
+        memcpy( fdec_c + y*32, h->mb.pic.p_fdec[1] + y*FDEC_STRIDE, 8 );
+        memcpy( fdec_c + y*32 + 16, h->mb.pic.p_fdec[2] + y*FDEC_STRIDE, 8 );
+    }
+    memcpy( levels, h->dct.luma4x4[0], 16*16*sizeof(int16_t) );
+    memcpy( levels + 256, h->dct.chroma_dc[0], 4*sizeof(int16_t) );
+    memcpy( levels + 260, h->dct.chroma_dc[1], 4*sizeof(int16_t) );
+    memcpy( levels + 264, h->dct.luma4x4[16], 4*16*sizeof(int16_t) );
+    memcpy( levels + 328, h->dct.luma4x4[32], 4*16*sizeof(int16_t) );
+    memcpy( luma_dc, h->dct.luma16x16_dc[0], 16*sizeof(int16_t) );
+    for( i = 0; i < 16; i++ )
+        nnz[i] = h->mb.cache.non_zero_count[x264_scan8[i]];
+    for( i = 0; i < 4; i++ )
+    {
+        nnz[16+i] = h->mb.cache.non_zero_count[x264_scan8[16+i]];
+        nnz[20+i] = h->mb.cache.non_zero_count[x264_scan8[32+i]];
+    }
+    nnz[24] = h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]];
+    nnz[25] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]];
+    nnz[26] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]];
+    return h->mb.cbp[0];
+}
+
 /* ------------------------------------------------------------------ timing helpers
  * (cpu_baseline / --impl reference): loops over the reference functions with the
  * input already in memory; CLOCK_MONOTONIC around the loop; returns seconds. */

@@ -123,6 +123,10 @@ void xo_lookahead_frame_cost( const x264dsp_geom_t *g, const uint8_t *slot_b, co
 void xo_mc_frame( const x264dsp_geom_t *g, const uint8_t *fref_slot, const int16_t *mv, uint8_t *pred_slot );
 void xo_residual_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
                         int16_t *levels, uint8_t *nnz, int16_t *cbp );
+void xo_residual_frame_typed( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
+                              const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int16_t *cbp );
+int xo_encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
+                          int qp, int16_t *levels, int16_t *luma_dc, uint8_t *nnz );
 
 /* work counters of the last xo_me_search_batch / xo_lookahead_frame_cost call on this thread:
  * counts[0] = pixel comparisons done by SAD, counts[1] = by SATD, [2] = SAD calls, [3] = SATD calls */

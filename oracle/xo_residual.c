@@ -1,4 +1,4 @@
-/* xo_residual.c -- oracle: residual coding of inter macroblocks.
+/* xo_residual.c -- oracle: residual coding of inter macroblocks (P slices) and I16x16 macroblocks (I slices).
  * TEST INFRASTRUCTURE ONLY (see xo.h).
  *
  * encoder/macroblock.c:9-59 (2x2 chroma DC helpers), 175-305 (x264_mb_encode_chroma),
@@ -47,10 +47,13 @@ static void store_chroma_dc_levels( int16_t *dst, const coef_t dc[4] )
     dst[0] = dc[0]; dst[1] = dc[2]; dst[2] = dc[1]; dst[3] = dc[3];     /* macroblock.c:9-15 */
 }
 
-/* x264_mb_encode_chroma with b_inter = 1 (macroblock.c:175-305); returns i_cbp_chroma */
+/* x264_mb_encode_chroma (macroblock.c:175-305); returns i_cbp_chroma.  b_inter selects the quant tables
+ * (CQM_4IC + b_inter) and stands for h->mb.b_dct_decimate as well: inter macroblocks live in P slices
+ * (decimation and the variance early-out on), intra macroblocks in I slices (both off). */
 static int encode_chroma( const pixel_t *fenc_u, const pixel_t *fenc_v, pixel_t *fdec_u, pixel_t *fdec_v,
-                          int qpc, mb_out_t *o )
+                          int qpc, mb_out_t *o, int b_inter )
 {
+    const int b_decimate = b_inter;
     uint16_t mf[16], bias[16];
     int dequant[6][16];
     const pixel_t *src[2] = { fenc_u, fenc_v };
@@ -59,13 +62,13 @@ static int encode_chroma( const pixel_t *fenc_u, const pixel_t *fenc_v, pixel_t 
     const int dmf_full = 0;
     (void)dmf_full;
 
-    xo_quant_tables( 1, qpc, mf, bias );
+    xo_quant_tables( b_inter, qpc, mf, bias );
     xo_dequant_table( dequant );
     {
         const int dmf = dequant[qpc % 6][0] << (qpc / 6);
         const int dc_mf = mf[0] >> 1, dc_bias = bias[0] << 1;
 
-        if( qpc >= 18 )                                       /* macroblock.c:188-232 */
+        if( b_decimate && qpc >= 18 )                         /* macroblock.c:188-232 */
         {
             int thresh = (xo_lambda2( qpc ) + 32) >> 6;
             int ssd[2] = { 0, 0 };
@@ -117,13 +120,14 @@ static int encode_chroma( const pixel_t *fenc_u, const pixel_t *fenc_v, pixel_t 
                 {
                     nz_ac = 1;
                     xo_dequant_4x4( dct[i], dequant, qpc );
-                    score += xo_decimate_score15( lv );
+                    if( b_decimate )
+                        score += xo_decimate_score15( lv );
                 }
             }
             nz_dc = xo_quant_2x2_dc( dc, dc_mf, dc_bias );
             o->nnz[25 + ch] = (uint8_t)nz_dc;
 
-            if( score < 7 || !nz_ac )
+            if( ( b_decimate && score < 7 ) || !nz_ac )
             {
                 coef_t rec[4];
                 memset( o->nnz + 16 + ch*4, 0, 4 );
@@ -213,13 +217,89 @@ static int encode_inter_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_
     memset( o->chroma_ac, 0, 8*16*sizeof(int16_t) );
     memset( o->nnz, 0, X264DSP_RES_NNZ_PER_MB );
     cbp_luma = encode_luma_inter( fenc_y, fdec_y, qp, o );
-    cbp_chroma = encode_chroma( fenc_c, fenc_c + 8, fdec_c, fdec_c + 16, xo_chroma_qp( qp ), o );
+    cbp_chroma = encode_chroma( fenc_c, fenc_c + 8, fdec_c, fdec_c + 16, xo_chroma_qp( qp ), o, 1 );
     /* macroblock.c:465-471, CABAC */
     return (cbp_chroma << 4) | cbp_luma | (o->nnz[24] << 8) | (o->nnz[25] << 9) | (o->nnz[26] << 10);
 }
 
+/* block_idx_xy_1d (common/macroblock.h): coding index of a luma 4x4 -> raster index x + 4 y */
+static const uint8_t blk_raster[16] = { 0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15 };
+
+/* x264_mb_encode_i16x16 (macroblock.c:72-162) with the prediction already in fdec and
+ * h->mb.b_dct_decimate = 0 (I slice: decimate_score starts at 9, nothing is dropped); returns i_cbp_luma.
+ * luma_dc[16] receives the zig-zagged levels of the DC block (h->dct.luma16x16_dc). */
+static int encode_luma_i16x16( const pixel_t *fenc, pixel_t *fdec, int qp, mb_out_t *o, int16_t *luma_dc )
+{
+    uint16_t mf[16], bias[16];
+    int dequant[6][16];
+    coef_t dct[16][16], dc[16];
+    int i, nz, block_cbp = 0;
+    xo_quant_tables( 0, qp, mf, bias );
+    xo_dequant_table( dequant );
+    xo_sub16x16_dct( dct, fenc, fdec );
+    for( i = 0; i < 16; i++ )
+    {
+        dc[blk_raster[i]] = dct[i][0];
+        dct[i][0] = 0;
+        nz = xo_quant_4x4( dct[i], mf, bias );
+        o->nnz[i] = (uint8_t)nz;
+        xo_zigzag_4x4( o->luma + i*16, dct[i] );
+        if( nz )
+        {
+            xo_dequant_4x4( dct[i], dequant, qp );
+            block_cbp = 0xf;
+        }
+    }
+    xo_dct4x4dc( dc );
+    nz = xo_quant_4x4_dc( dc, mf[0] >> 1, bias[0] << 1 );
+    o->nnz[24] = (uint8_t)nz;
+    memset( luma_dc, 0, 16*sizeof(int16_t) );
+    if( nz )
+    {
+        xo_zigzag_4x4( luma_dc, dc );
+        xo_idct4x4dc( dc );
+        xo_dequant_4x4_dc( dc, dequant, qp );
+        if( block_cbp )
+            for( i = 0; i < 16; i++ )
+                dct[i][0] = dc[blk_raster[i]];
+    }
+    if( block_cbp )
+        xo_add16x16_idct( fdec, dct );
+    else if( nz )
+        xo_add16x16_idct_dc( fdec, dc );
+    return block_cbp;
+}
+
+static int encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
+                              int qp, mb_out_t *o, int16_t *luma_dc )
+{
+    int cbp_luma, cbp_chroma;
+    memset( o->luma, 0, 16*16*sizeof(int16_t) );
+    memset( o->chroma_dc, 0, 8*sizeof(int16_t) );
+    memset( o->chroma_ac, 0, 8*16*sizeof(int16_t) );
+    memset( o->nnz, 0, X264DSP_RES_NNZ_PER_MB );
+    cbp_luma = encode_luma_i16x16( fenc_y, fdec_y, qp, o, luma_dc );
+    cbp_chroma = encode_chroma( fenc_c, fenc_c + 8, fdec_c, fdec_c + 16, xo_chroma_qp( qp ), o, 0 );
+    return (cbp_chroma << 4) | cbp_luma | (o->nnz[24] << 8) | (o->nnz[25] << 9) | (o->nnz[26] << 10);
+}
+
+int xo_encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
+                          int qp, int16_t *levels, int16_t *luma_dc, uint8_t *nnz )
+{
+    mb_out_t o = { levels, levels + 256, levels + 264, nnz };
+    return encode_intra16_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp, &o, luma_dc );
+}
+
 void xo_residual_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
                         int16_t *levels, uint8_t *nnz, int16_t *cbp )
+{
+    xo_residual_frame_typed( g, fenc_slot, pred_slot, qp, NULL, levels, NULL, nnz, cbp );
+}
+
+/* mb_kind[xy]: 0 = inter macroblock of a P slice, 1 = I16x16 macroblock of an I slice (NULL: all inter);
+ * luma_dc[xy][16] is written for kind 1 (zeroed for kind 0) when not NULL */
+void xo_residual_frame_typed( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
+                              const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int16_t *cbp )
 {
     const int ls = g->luma_stride, cs = g->chroma_stride;
     int mb_x, mb_y, x, y;
@@ -250,7 +330,17 @@ void xo_residual_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8
                     fdec_c[y*FDEC + x]      = pc[(ptrdiff_t)y*cs + 2*x];
                     fdec_c[y*FDEC + 16 + x] = pc[(ptrdiff_t)y*cs + 2*x + 1];
                 }
-            cbp[xy] = (int16_t)encode_inter_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp, &o );
+            if( mb_kind && mb_kind[xy] )
+            {
+                int16_t dc_tmp[16];
+                cbp[xy] = (int16_t)encode_intra16_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp, &o, luma_dc ? luma_dc + (size_t)xy*16 : dc_tmp );
+            }
+            else
+            {
+                if( luma_dc )
+                    memset( luma_dc + (size_t)xy*16, 0, 16*sizeof(int16_t) );
+                cbp[xy] = (int16_t)encode_inter_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp, &o );
+            }
             for( y = 0; y < 16; y++ )
                 memcpy( py + (ptrdiff_t)y*ls, fdec_y + y*FDEC, 16 );
             for( y = 0; y < 8; y++ )

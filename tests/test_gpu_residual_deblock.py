@@ -189,3 +189,75 @@ def test_deblock_strength(pkg, ctx):
     ctx.sync()
     got = bs.cpu().numpy()
     assert np.array_equal(got[:, :, :4], want[:, :, :4])
+
+
+@pytest.mark.parametrize("w,h,nf,qp,intra_share", [(352, 288, 2, 26, 0.5), (200, 120, 3, 18, 1.0), (352, 288, 2, 38, 0.3),
+                                                    (1920, 1080, 2, 30, 0.5), (352, 288, 2, 12, 1.0), (208, 160, 2, 51, 0.5)])
+def test_residual_frames_typed_inter_and_i16x16(pkg, ctx, w, h, nf, qp, intra_share):
+    """x264dsp_residual_frames_typed_dev: inter macroblocks (P slice rules) and I16x16 macroblocks (I slice rules:
+    intra tables, luma DC block, no decimation) mixed in one launch, against the oracle (pinned to the reference's
+    x264_macroblock_encode for both kinds, tests/test_oracle_vs_ref.py)"""
+    import torch
+    g, go, host, dev = _slots(pkg, ctx, w, h, nf + 1, False)
+    o = cc.oracle()
+    rng = np.random.RandomState(qp + nf + w)
+    n = g.mb_count
+    kind = (rng.rand(nf, n) < intra_share).astype(np.uint8)
+    # prediction: the previous frame (zero-motion inter prediction); intra macroblocks get a flat (DC-like) luma block
+    # or a vertical / horizontal extension of the source's own first row / column, and flat chroma
+    preds = []
+    for f in range(nf):
+        p = host[f].copy()
+        src = host[f + 1]
+        luma = p[go.luma_origin:].reshape(-1)[: (16 * go.mb_h) * go.luma_stride].reshape(16 * go.mb_h, go.luma_stride)
+        sl = src[go.luma_origin:].reshape(-1)[: (16 * go.mb_h) * go.luma_stride].reshape(16 * go.mb_h, go.luma_stride)
+        co = go.slot_chroma_off + go.chroma_origin
+        chroma = p[co:].reshape(-1)[: (8 * go.mb_h) * go.chroma_stride].reshape(8 * go.mb_h, go.chroma_stride)
+        sc = src[co:].reshape(-1)[: (8 * go.mb_h) * go.chroma_stride].reshape(8 * go.mb_h, go.chroma_stride)
+        for xy in np.nonzero(kind[f])[0]:
+            mx, my = xy % go.mb_w, xy // go.mb_w
+            blk = sl[16 * my: 16 * my + 16, 16 * mx: 16 * mx + 16]
+            mode = rng.randint(4)
+            if mode == 0:
+                luma[16 * my: 16 * my + 16, 16 * mx: 16 * mx + 16] = int(blk.mean())
+            elif mode == 1:
+                luma[16 * my: 16 * my + 16, 16 * mx: 16 * mx + 16] = blk[0][None, :]
+            elif mode == 2:
+                luma[16 * my: 16 * my + 16, 16 * mx: 16 * mx + 16] = blk[:, 0][:, None]
+            else:                                            # nearly perfect prediction: DC-only / empty macroblocks
+                luma[16 * my: 16 * my + 16, 16 * mx: 16 * mx + 16] = np.clip(blk.astype(int) + rng.randint(-2, 3), 0, 255)
+            cb = sc[8 * my: 8 * my + 8, 16 * mx: 16 * mx + 16]
+            chroma[8 * my: 8 * my + 8, 16 * mx: 16 * mx + 16: 2] = int(cb[:, 0::2].mean())
+            chroma[8 * my: 8 * my + 8, 16 * mx + 1: 16 * mx + 16: 2] = int(cb[:, 1::2].mean())
+        preds.append(p)
+    lv_o = np.zeros((nf, n, pkg.RES_LEVELS_PER_MB), np.int16)
+    dc_o = np.zeros((nf, n, 16), np.int16)
+    nz_o = np.zeros((nf, n, pkg.RES_NNZ_PER_MB), np.uint8)
+    cbp_o = np.zeros((nf, n), np.int16)
+    rec_o = []
+    for f in range(nf):
+        po = preds[f].copy()
+        o.xo_residual_frame_typed(C.byref(go), ptr(host[f + 1]), ptr(po), qp, ptr(kind[f]), ptr(lv_o[f], i16p),
+                                  ptr(dc_o[f], i16p), ptr(nz_o[f]), ptr(cbp_o[f], i16p))
+        rec_o.append(po)
+    pred = torch.from_numpy(np.concatenate(preds)).cuda()
+    d_kind = torch.from_numpy(kind).cuda()
+    lv = torch.full((nf, n, pkg.RES_LEVELS_PER_MB), -1, dtype=torch.int16, device="cuda")
+    dc = torch.full((nf, n, 16), -1, dtype=torch.int16, device="cuda")
+    nz = torch.full((nf, n, pkg.RES_NNZ_PER_MB), 77, dtype=torch.uint8, device="cuda")
+    cbp = torch.full((nf, n), -1, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    ctx.residual_frames_typed(g, dev[g.slot_bytes:], pred, nf, qp, d_kind, lv, dc, nz, cbp)
+    ctx.sync()
+    got = pred.cpu().numpy().reshape(nf, -1)
+    for f in range(nf):
+        bad = np.nonzero(cbp[f].cpu().numpy() != cbp_o[f])[0]
+        assert len(bad) == 0, f"frame {f}: cbp differs at MBs {bad[:5]} kinds {kind[f][bad[:5]]}: {cbp[f].cpu().numpy()[bad[:5]]} vs {cbp_o[f][bad[:5]]}"
+        assert np.array_equal(nz[f].cpu().numpy(), nz_o[f]), f"frame {f}: nnz"
+        assert np.array_equal(lv[f].cpu().numpy(), lv_o[f]), f"frame {f}: levels"
+        assert np.array_equal(dc[f].cpu().numpy(), dc_o[f]), f"frame {f}: luma DC levels"
+        assert np.array_equal(got[f], rec_o[f]), f"frame {f}: reconstruction"
+    if intra_share > 0:
+        i16 = kind.astype(bool)
+        assert (nz_o[..., 24][i16] != 0).any(), "no I16x16 macroblock with a coded DC block"
+        assert ((cbp_o & 15)[i16] == 15).any() and ((cbp_o & 15)[i16] == 0).any(), "I16x16: both luma cbp cases wanted"

@@ -494,3 +494,63 @@ def test_residual_inter_mb(enc, qp):
             a, b = l1[264 + i * 16: 280 + i * 16], l2[264 + i * 16: 280 + i * 16]
             if a.any():
                 assert np.array_equal(a, b), f"chroma ac levels trial {trial} blk {i}"
+
+
+@pytest.mark.parametrize("qp", [12, 18, 22, 26, 32, 40, 51])
+def test_residual_intra16_mb(enc, qp):
+    """x264_mb_encode_i16x16 + intra chroma (I slice, no decimation) on caller-supplied predictions: the reference
+    (its predictors swapped for no-ops by the harness) against the oracle's restatement"""
+    o = cc.oracle()
+    rng = np.random.RandomState(100 + qp)
+    o.xo_encode_intra16_mb.restype = C.c_int
+    enc.lib.xref_encode_intra16_mb.restype = C.c_int
+    for trial in range(300):
+        amp = [1, 3, 8, 25, 80][trial % 5]
+        pred_y = np.zeros((16, 32), np.uint8)
+        pred_c = np.zeros((8, 32), np.uint8)
+        kind = trial % 4
+        if kind == 0:                                        # DC prediction
+            pred_y[:] = rng.randint(20, 236)
+            pred_c[:, :16] = rng.randint(20, 236)
+            pred_c[:, 16:] = rng.randint(20, 236)
+        elif kind == 1:                                      # vertical
+            pred_y[:, :16] = rng.randint(0, 256, 16)[None, :]
+            pred_c[:, :8] = rng.randint(0, 256, 8)[None, :]
+            pred_c[:, 16:24] = rng.randint(0, 256, 8)[None, :]
+        elif kind == 2:                                      # horizontal
+            pred_y[:, :16] = rng.randint(0, 256, 16)[:, None]
+            pred_c[:, :8] = rng.randint(0, 256, 8)[:, None]
+            pred_c[:, 16:24] = rng.randint(0, 256, 8)[:, None]
+        else:                                                # anything
+            pred_y[:] = rng.randint(0, 256, (16, 32))
+            pred_c[:] = rng.randint(0, 256, (8, 32))
+        fenc_y = np.clip(pred_y[:, :16].astype(int) + rng.randint(-amp, amp + 1, (16, 16)), 0, 255).astype(np.uint8)
+        if trial % 6 == 0:                                   # DC-only luma change: exercises add16x16_idct_dc
+            fenc_y = np.clip(pred_y[:, :16].astype(int) + rng.randint(-6, 7), 0, 255).astype(np.uint8)
+        fenc_c = np.zeros((8, 16), np.uint8)
+        fenc_c[:, :8] = np.clip(pred_c[:, :8].astype(int) + rng.randint(-amp, amp + 1, (8, 8)), 0, 255)
+        fenc_c[:, 8:] = np.clip(pred_c[:, 16:24].astype(int) + rng.randint(-amp, amp + 1, (8, 8)), 0, 255)
+        if trial % 7 == 0:
+            fenc_c[:, :8] = np.clip(pred_c[:, :8].astype(int) + rng.randint(-3, 4), 0, 255)
+        y1, c1, y2, c2 = pred_y.copy(), pred_c.copy(), pred_y.copy(), pred_c.copy()
+        l1, l2 = np.zeros(392, np.int16), np.zeros(392, np.int16)
+        d1, d2 = np.zeros(16, np.int16), np.zeros(16, np.int16)
+        n1, n2 = np.zeros(27, np.uint8), np.zeros(27, np.uint8)
+        cbp1 = enc.lib.xref_encode_intra16_mb(enc.h, ptr(fenc_y), ptr(fenc_c), ptr(y1), ptr(c1), qp, ptr(l1, i16p),
+                                              ptr(d1, i16p), ptr(n1))
+        cbp2 = o.xo_encode_intra16_mb(ptr(fenc_y), ptr(fenc_c), ptr(y2), ptr(c2), qp, ptr(l2, i16p), ptr(d2, i16p), ptr(n2))
+        assert cbp1 == cbp2, f"cbp trial {trial}: {cbp1:#x} vs {cbp2:#x}"
+        assert np.array_equal(n1, n2), f"nnz trial {trial}: {n1} {n2}"
+        assert np.array_equal(y1[:, :16], y2[:, :16]), f"luma recon trial {trial}"
+        assert np.array_equal(c1[:, :8], c2[:, :8]) and np.array_equal(c1[:, 16:24], c2[:, 16:24]), f"chroma recon {trial}"
+        for i in range(16):
+            if n1[i]:
+                assert np.array_equal(l1[i * 16:(i + 1) * 16], l2[i * 16:(i + 1) * 16]), f"luma levels trial {trial} blk {i}"
+        if n1[24]:
+            assert np.array_equal(d1, d2), f"luma dc levels trial {trial}: {d1} {d2}"
+        for ch in range(2):
+            if n1[25 + ch]:
+                assert np.array_equal(l1[256 + 4 * ch:260 + 4 * ch], l2[256 + 4 * ch:260 + 4 * ch]), f"chroma dc {trial}"
+        for i in range(8):
+            if n1[16 + i]:
+                assert np.array_equal(l1[264 + i * 16: 280 + i * 16], l2[264 + i * 16: 280 + i * 16]), f"chroma ac {trial} blk {i}"

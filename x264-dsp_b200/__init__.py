@@ -390,6 +390,13 @@ class Context:
                                                 int(qp), _dp(levels), _dp(nnz), _dp(cbp), None),
               "x264dsp_residual_frames_dev")
 
+    def residual_frames_typed(self, g, fenc_slots, pred_slots, n_frames, qp, mb_kind, levels, luma_dc, nnz, cbp):
+        """mb_kind: uint8 per macroblock, 0 = inter (P slice), 1 = I16x16 (I slice); luma_dc: int16[n][mb][16] or None"""
+        check(lib().x264dsp_residual_frames_typed_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
+                                                      int(qp), _dp(mb_kind) if mb_kind is not None else None, _dp(levels),
+                                                      _dp(luma_dc) if luma_dc is not None else None, _dp(nnz), _dp(cbp), None),
+              "x264dsp_residual_frames_typed_dev")
+
     def deblock_frame(self, g, slot, mb_type, partition, cbp, bs, qp, alpha_off=0, beta_off=0):
         check(lib().x264dsp_deblock_frame_dev(self._h, C.byref(g), _dp(slot), _dp(mb_type), _dp(partition),
                                               _dp(cbp), _dp(bs), int(qp), int(alpha_off), int(beta_off), None),

@@ -69,12 +69,49 @@ struct xd_res_tables
     xd_qparams luma, chroma;
     int chroma_dc_mf, chroma_dc_bias, chroma_dmf_full;   // mf[0]>>1, bias[0]<<1, dequant_mf[qpc%6][0] << qpc/6
     int qpc, thresh;                                      // chroma qp, (lambda2[qpc]+32)>>6
+    // I16x16 macroblocks of I slices (typed entry point): the intra quant tables (CQM_4IY / CQM_4IC differ from the
+    // inter ones in the rounding bias only) and the luma DC block's scalars (macroblock.c:123, quant.c:83-101)
+    xd_qparams luma_i, chroma_i;
+    int chroma_dc_bias_i;
+    int luma_dc_mf, luma_dc_bias, luma_dc_dmf, luma_dc_qbits;   // mf[0]>>1, bias[0]<<1, dequant_mf[qp%6][0], qp/6 - 6
 };
 
+// block_idx_xy_1d (common/macroblock.h): coding index of a luma 4x4 -> raster index x + 4 y
+__device__ __forceinline__ int xd_blk_raster( int i )
+{
+    return ( ( i & 1 ) + ( ( i >> 2 ) & 1 ) * 2 ) + 4 * ( ( ( i >> 1 ) & 1 ) + ( ( i >> 3 ) & 1 ) * 2 );
+}
+
+// dct4x4dc / idct4x4dc (dct.c:36-100): 4x4 Hadamard of the sixteen luma DC terms, every lane on the same values
+__device__ __forceinline__ void xd_hadamard_dc( int d[16], bool halve )
+{
+    int t[16];
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        const int s01 = d[4 * i] + d[4 * i + 1], d01 = d[4 * i] - d[4 * i + 1];
+        const int s23 = d[4 * i + 2] + d[4 * i + 3], d23 = d[4 * i + 2] - d[4 * i + 3];
+        t[i] = (int16_t)( s01 + s23 ); t[4 + i] = (int16_t)( s01 - s23 );
+        t[8 + i] = (int16_t)( d01 - d23 ); t[12 + i] = (int16_t)( d01 + d23 );
+    }
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        const int s01 = t[4 * i] + t[4 * i + 1], d01 = t[4 * i] - t[4 * i + 1];
+        const int s23 = t[4 * i + 2] + t[4 * i + 3], d23 = t[4 * i + 2] - t[4 * i + 3];
+        const int r = halve ? 1 : 0;
+        d[4 * i] = (int16_t)( ( s01 + s23 + r ) >> r ); d[4 * i + 1] = (int16_t)( ( s01 - s23 + r ) >> r );
+        d[4 * i + 2] = (int16_t)( ( d01 - d23 + r ) >> r ); d[4 * i + 3] = (int16_t)( ( d01 + d23 + r ) >> r );
+    }
+}
+
+// TYPED: mb_kind[mb] != 0 marks an I16x16 macroblock of an I slice (x264_mb_encode_i16x16, macroblock.c:72-162, and
+// x264_mb_encode_chroma with b_inter = 0, no decimation); the inter-only instantiation carries none of that code
+template<bool TYPED>
 __global__ void __launch_bounds__( 128 )
 xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t *__restrict__ pred,
                     xd_res_tables T, int16_t *__restrict__ levels, uint8_t *__restrict__ nnz_out,
-                    int16_t *__restrict__ cbp_out )
+                    int16_t *__restrict__ cbp_out, const uint8_t *__restrict__ mb_kind, int16_t *__restrict__ luma_dc )
 {
     const int lane = threadIdx.x & 31;
     const int mb = blockIdx.x * 4 + ( threadIdx.x >> 5 );
@@ -86,6 +123,18 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     levels += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_LEVELS_PER_MB;
     nnz_out += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_NNZ_PER_MB;
     cbp_out += blockIdx.y * (size_t)g.mb_count;
+    bool intra = false;
+    if( TYPED )
+    {
+        if( mb_kind )
+            intra = mb_kind[blockIdx.y * (size_t)g.mb_count + mb] != 0;
+        if( luma_dc )
+        {
+            luma_dc += ( blockIdx.y * (size_t)g.mb_count + mb ) * 16;
+            if( !intra && lane < 2 )
+                ( (uint4 *)luma_dc )[lane] = make_uint4( 0u, 0u, 0u, 0u );
+        }
+    }
     const int mb_x = mb % g.mb_w, mb_y = mb / g.mb_w;
     const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
     const int ch = ( lane - 16 ) >> 2, ci = ( lane - 16 ) & 3;
@@ -140,7 +189,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     const int sum_u = __shfl_sync( 0xffffffffu, psum, 16 ), sqr_u = __shfl_sync( 0xffffffffu, psqr, 16 );
     const int sum_v = __shfl_sync( 0xffffffffu, psum, 20 ), sqr_v = __shfl_sync( 0xffffffffu, psqr, 20 );
     bool early = false;
-    if( T.qpc >= 18 )
+    if( T.qpc >= 18 && !intra )
     {
         const unsigned au = (unsigned)abs( sum_u ), av = (unsigned)abs( sum_v );
         const int var_u = (int)( (unsigned)sqr_u - (unsigned)( ( (unsigned long long)au * au ) >> 6 ) );
@@ -155,8 +204,9 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     int dc[4] = { (int16_t)( c0 + c1 + c2 + c3 ), (int16_t)( c0 + c1 - c2 - c3 ), (int16_t)( c0 - c1 + c2 - c3 ), (int16_t)( c0 - c1 - c2 + c3 ) };
     // note the reference's ordering d[1] = (c0+c1)-(c2+c3), d[2] = (c0-c1)+(c2-c3)
 
-    const xd_qparams &Q = is_luma ? T.luma : T.chroma;
-    if( is_chroma )
+    const xd_qparams &Q = intra ? ( is_luma ? T.luma_i : T.chroma_i ) : ( is_luma ? T.luma : T.chroma );
+    const int luma_dcv = dct[0];                   // I16x16: the DC terms leave for their own 4x4 block (macroblock.c:92-93)
+    if( is_chroma || intra )
         dct[0] = 0;                                // dct2x2dc clears the DC terms (macroblock.c:55-58)
     int nz = 0, score = 0;
     if( is_luma || ( is_chroma && !early ) )
@@ -191,9 +241,72 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     // (a block that quantised to zero has score 0, which is what "skipped" adds)
     const int mb_score = __shfl_sync( 0xffffffffu, score8, 0 ) + __shfl_sync( 0xffffffffu, score8, 4 )
                        + __shfl_sync( 0xffffffffu, score8, 8 ) + __shfl_sync( 0xffffffffu, score8, 12 );
-    const bool keep8 = score8 >= 4 && mb_score >= 6;
+    bool keep8 = score8 >= 4 && mb_score >= 6;
     int nnz_flag = 0;
-    if( is_luma )
+    int nz_luma_dc = 0;
+    if( TYPED && intra )
+    {
+        // no decimation in an I slice: all sixteen blocks are coded as soon as one of them has a coefficient
+        const bool any_ac = ( __ballot_sync( 0xffffffffu, is_luma && nz ) ) != 0;
+        keep8 = any_ac;
+        int d[16];
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+            d[xd_blk_raster( i )] = __shfl_sync( 0xffffffffu, luma_dcv, i );
+        xd_hadamard_dc( d, true );
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+        {
+            d[i] = xd_quant1( d[i], T.luma_dc_mf, T.luma_dc_bias );
+            nz_luma_dc |= d[i];
+        }
+        nz_luma_dc = nz_luma_dc != 0;
+        int dlv[16];
+        xd_zigzag( dlv, d );
+        if( !nz_luma_dc )
+        {
+#pragma unroll
+            for( int i = 0; i < 16; i++ )
+                dlv[i] = 0;
+        }
+        if( lane == 0 && luma_dc )
+            xd_store_levels( luma_dc, dlv );
+        int my_dc = 0;
+        if( nz_luma_dc )
+        {
+            xd_hadamard_dc( d, false );
+            if( T.luma_dc_qbits >= 0 )
+            {
+#pragma unroll
+                for( int i = 0; i < 16; i++ )
+                    d[i] = (int16_t)( d[i] * ( T.luma_dc_dmf << T.luma_dc_qbits ) );
+            }
+            else
+            {
+                const int f = 1 << ( -T.luma_dc_qbits - 1 );
+#pragma unroll
+                for( int i = 0; i < 16; i++ )
+                    d[i] = (int16_t)( ( d[i] * T.luma_dc_dmf + f ) >> ( -T.luma_dc_qbits ) );
+            }
+            const int mine = xd_blk_raster( lane & 15 );
+#pragma unroll
+            for( int i = 0; i < 16; i++ )
+                if( mine == i )
+                    my_dc = d[i];
+        }
+        if( is_luma )
+        {
+            nnz_flag = nz;
+            if( any_ac )
+            {
+                dct[0] = my_dc;
+                xd_add4x4_idct( p, dct );
+            }
+            else if( nz_luma_dc )
+                xd_add4x4_dc( p, my_dc );
+        }
+    }
+    else if( is_luma )
     {
         nnz_flag = keep8 ? nz : 0;
         if( keep8 )
@@ -218,7 +331,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
             do_dc = ssd > T.thresh;
         else
         {
-            ac_coded = !( psc < 7 || !nz_ac );
+            ac_coded = intra ? nz_ac : !( psc < 7 || !nz_ac );
             do_dc = true;
         }
         int nz_dc = 0;
@@ -228,7 +341,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
 #pragma unroll
             for( int i = 0; i < 4; i++ )
             {
-                dc[i] = xd_quant1( dc[i], T.chroma_dc_mf, T.chroma_dc_bias );
+                dc[i] = xd_quant1( dc[i], T.chroma_dc_mf, intra ? T.chroma_dc_bias_i : T.chroma_dc_bias );
                 nz_dc |= dc[i];
             }
             nz_dc = nz_dc != 0;
@@ -305,13 +418,13 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     if( lane < 24 )
         mb_nnz[lane] = (uint8_t)nnz_flag;
     if( lane == 24 )
-        mb_nnz[24] = 0;                                                  // luma DC: inter MB
+        mb_nnz[24] = (uint8_t)nz_luma_dc;                                // luma DC: I16x16 only
     if( lane == 25 )
         mb_nnz[25] = (uint8_t)dc_u;
     if( lane == 26 )
         mb_nnz[26] = (uint8_t)dc_v;
     if( lane == 0 )
-        cbp_out[mb] = (int16_t)( ( cbp_chroma << 4 ) | cbp_luma | ( dc_u << 9 ) | ( dc_v << 10 ) );
+        cbp_out[mb] = (int16_t)( ( cbp_chroma << 4 ) | cbp_luma | ( nz_luma_dc << 8 ) | ( dc_u << 9 ) | ( dc_v << 10 ) );
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -324,11 +437,11 @@ static const int xd_lambda2_tab[52] =
     117964, 148626, 187257, 235929, 297252, 374514, 471859, 594505, 749029, 943718,1189010,1498059,1887436
 };
 
-static void xd_fill_qparams( xd_qparams *q, int qp )
+static void xd_fill_qparams( xd_qparams *q, int qp, int b_inter = 1 )
 {
     uint16_t mf[16], bias[16];
     int dq[6][16];
-    x264dsp_quant_tables( 1, qp, mf, bias );
+    x264dsp_quant_tables( b_inter, qp, mf, bias );
     x264dsp_dequant_table( dq );
     static const int rep[3] = { 0, 1, 5 };          // a position of each class
     for( int c = 0; c < 3; c++ )
@@ -340,9 +453,9 @@ static void xd_fill_qparams( xd_qparams *q, int qp )
     q->qbits = qp / 6 - 4;
 }
 
-extern "C" int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
-                                             const uint8_t *fenc_slot, uint8_t *pred_slot, int n_frames, int qp,
-                                             int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream )
+static int xd_residual_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot,
+                               int n_frames, int qp, const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc,
+                               uint8_t *nnz, int16_t *cbp, bool typed, void *stream )
 {
     if( !ctx || !g || !fenc_slot || !pred_slot || !levels || !nnz || !cbp || qp < 0 || qp > 51 || n_frames <= 0
         || n_frames > 65535 )
@@ -351,6 +464,8 @@ extern "C" int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_ge
     const int qpc = x264dsp_chroma_qp( qp );
     xd_fill_qparams( &T.luma, qp );
     xd_fill_qparams( &T.chroma, qpc );
+    xd_fill_qparams( &T.luma_i, qp, 0 );
+    xd_fill_qparams( &T.chroma_i, qpc, 0 );
     {
         uint16_t mf[16], bias[16];
         int dq[6][16];
@@ -359,17 +474,42 @@ extern "C" int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_ge
         T.chroma_dc_mf = mf[0] >> 1;
         T.chroma_dc_bias = bias[0] << 1;
         T.chroma_dmf_full = dq[qpc % 6][0] << ( qpc / 6 );
+        x264dsp_quant_tables( 0, qpc, mf, bias );
+        T.chroma_dc_bias_i = bias[0] << 1;
+        x264dsp_quant_tables( 0, qp, mf, bias );
+        T.luma_dc_mf = mf[0] >> 1;
+        T.luma_dc_bias = bias[0] << 1;
+        T.luma_dc_dmf = dq[qp % 6][0];
+        T.luma_dc_qbits = qp / 6 - 6;
     }
     T.qpc = qpc;
     T.thresh = ( xd_lambda2_tab[qpc] + 32 ) >> 6;
     cudaStream_t s = xd_stream( ctx, stream );
     const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_RESIDUAL, s );
-    xd_residual_kernel<<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, levels, nnz, cbp );
+    if( typed )
+        xd_residual_kernel<true><<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, levels, nnz, cbp, mb_kind, luma_dc );
+    else
+        xd_residual_kernel<false><<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, levels, nnz, cbp, NULL, NULL );
     xd_prof_end( ctx, XD_PROF_RESIDUAL, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
+}
+
+extern "C" int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                             const uint8_t *fenc_slot, uint8_t *pred_slot, int n_frames, int qp,
+                                             int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream )
+{
+    return xd_residual_launch( ctx, g, fenc_slot, pred_slot, n_frames, qp, NULL, levels, NULL, nnz, cbp, false, stream );
+}
+
+extern "C" int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                                   const uint8_t *fenc_slot, uint8_t *pred_slot, int n_frames, int qp,
+                                                   const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc,
+                                                   uint8_t *nnz, int16_t *cbp, void *stream )
+{
+    return xd_residual_launch( ctx, g, fenc_slot, pred_slot, n_frames, qp, mb_kind, levels, luma_dc, nnz, cbp, true, stream );
 }
 
 extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
