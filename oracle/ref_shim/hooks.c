@@ -239,7 +239,8 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
  * x264_macroblock_encode      encoder/macroblock.c:310     called from encoder/encoder.c (slice loop)
  *
  * Inter macroblocks of a P slice (P_L0, P_8x8; any partition -- the residual is one 16x16 transform
- * whatever the motion partition): the reference's own x264_mb_mc builds the prediction in fdec, the
+ * whatever the motion partition) and I16x16 macroblocks of an I slice: the reference's own x264_mb_mc /
+ * h->predict_16x16[] / h->predict_chroma[] build the prediction in fdec, the
  * hook turns source + prediction into levels / nnz / cbp / reconstruction (x264dsp_residual_frame_dev
  * on the device), and what comes back is laid out where x264_macroblock_write_cabac / _cavlc and
  * x264_macroblock_cache_save read it (the entropy coder's hand-off format):
@@ -248,7 +249,7 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
  *   cbp     -> h->mb.i_cbp_luma, h->mb.i_cbp_chroma, h->mb.cbp[mb_xy] (CABAC: with the DC flags in bits 8..10)
  * followed by the forced-P_SKIP rule of macroblock.c:465-485.  Buffer shapes are xref_encode_inter_mb's. */
 typedef int (*xref_mbenc_cb)( void *h, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y, uint8_t *fdec_c,
-                              int qp, int16_t *levels, uint8_t *nnz, int *cbp );
+                              int qp, int kind /* 0 inter, 1 I16x16 */, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int *cbp );
 xref_mbenc_cb xref_hook_mbenc = NULL;
 int xref_hook_mbenc_calls = 0;
 
@@ -263,11 +264,14 @@ void xref_orig_macroblock_encode( x264_t *h );
 
 void x264_macroblock_encode( x264_t *h )
 {
-    int16_t levels[392];
+    int16_t levels[392], luma_dc[16];
     uint8_t nnz[27];
     int cbp = 0, i;
-    if( !xref_hook_mbenc || IS_INTRA( h->mb.i_type ) || h->mb.i_type == P_SKIP || h->sh.i_type != SLICE_TYPE_P
-        || !h->mb.b_dct_decimate || h->mb.b_noise_reduction || h->mb.b_transform_8x8 || h->mb.b_lossless
+    /* I16x16 macroblocks of I slices (x264_mb_encode_i16x16 + intra chroma, no decimation): the reference's own
+     * predictors fill fdec, the device does the rest (x264dsp_residual_frames_typed_dev, kind 1) */
+    const int i16 = h->mb.i_type == I_16x16 && h->sh.i_type == SLICE_TYPE_I && !h->mb.b_dct_decimate;
+    const int inter = !IS_INTRA( h->mb.i_type ) && h->mb.i_type != P_SKIP && h->sh.i_type == SLICE_TYPE_P && h->mb.b_dct_decimate;
+    if( !xref_hook_mbenc || !( i16 || inter ) || h->mb.b_noise_reduction || h->mb.b_transform_8x8 || h->mb.b_lossless
         || h->mb.i_chroma_qp != h->chroma_qp_table[h->mb.i_qp] )
     {
         xref_orig_macroblock_encode( h );
@@ -275,13 +279,22 @@ void x264_macroblock_encode( x264_t *h )
     }
     h->mb.i_cbp_luma = 0;
     h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = 0;
-    if( !h->mb.b_skip_mc )
+    if( i16 )
+    {
+        h->predict_16x16[h->mb.i_intra16x16_pred_mode]( h->mb.pic.p_fdec[0] );
+        h->predict_chroma[h->mb.i_chroma_pred_mode]( h->mb.pic.p_fdec[1] );
+        h->predict_chroma[h->mb.i_chroma_pred_mode]( h->mb.pic.p_fdec[2] );
+    }
+    else if( !h->mb.b_skip_mc )
         x264_mb_mc( h );
     memset( levels, 0, sizeof(levels) );
+    memset( luma_dc, 0, sizeof(luma_dc) );
     if( xref_hook_mbenc( h, h->mb.pic.p_fenc[0], h->mb.pic.p_fenc[1], h->mb.pic.p_fdec[0], h->mb.pic.p_fdec[1],
-                         h->mb.i_qp, levels, nnz, &cbp ) )
+                         h->mb.i_qp, i16, levels, luma_dc, nnz, &cbp ) )
     {
-        h->mb.b_skip_mc = 1;                          /* the prediction is already in fdec */
+        /* declined: the prediction is already in fdec; an intra macroblock's predictors simply run again */
+        if( inter )
+            h->mb.b_skip_mc = 1;
         xref_orig_macroblock_encode( h );
         return;
     }
@@ -291,6 +304,8 @@ void x264_macroblock_encode( x264_t *h )
     memcpy( h->dct.chroma_dc[1], levels + 260, 4*sizeof(int16_t) );
     memcpy( h->dct.luma4x4[16], levels + 264, 4*16*sizeof(int16_t) );
     memcpy( h->dct.luma4x4[32], levels + 328, 4*16*sizeof(int16_t) );
+    if( i16 )
+        memcpy( h->dct.luma16x16_dc[0], luma_dc, 16*sizeof(int16_t) );
     for( i = 0; i < 16; i++ )
         h->mb.cache.non_zero_count[x264_scan8[i]] = nnz[i];
     for( i = 0; i < 4; i++ )
@@ -298,6 +313,7 @@ void x264_macroblock_encode( x264_t *h )
         h->mb.cache.non_zero_count[x264_scan8[16+i]] = nnz[16+i];
         h->mb.cache.non_zero_count[x264_scan8[32+i]] = nnz[20+i];
     }
+    h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = nnz[24];
     h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]] = nnz[25];
     h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]] = nnz[26];
     h->mb.i_cbp_luma = cbp & 15;

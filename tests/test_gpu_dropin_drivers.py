@@ -9,9 +9,9 @@ of its hot-path drivers served by libx264dsp_b200.so --
                                                 -> x264dsp_lookahead_frame_cost_dev
   x264_me_search_ref (every partition search of the main encode, last cases)
                                                 -> x264dsp_me_search_batch_dev on frames kept resident on the device
-  x264_macroblock_encode (every inter macroblock of the P slices, last two cases: DCT, quant, zig-zag, dequant,
-  decimation, chroma DC, IDCT; levels / nnz / cbp handed to the reference's CABAC writer)
-                                                -> x264dsp_residual_frame_dev
+  x264_macroblock_encode (every inter macroblock of the P slices and every I16x16 macroblock of the I slices, last
+  two cases: DCT, quant, zig-zag, dequant, decimation, luma / chroma DC, IDCT; levels / nnz / cbp handed to the
+  reference's CABAC writer)                     -> x264dsp_residual_frames_typed_dev
 
 through the doors of oracle/ref_shim/hooks.c (the glue INTEGRATION.md describes), and must emit the
 byte-identical bitstream.  Every plane the main encode searches in (half-pel planes of every
@@ -32,8 +32,8 @@ COST_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_voi
 FDEC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                       C.c_int, C.c_int, C.c_int)
 ME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
-MBENC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                       C.POINTER(C.c_int))
+MBENC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
 
 
 @pytest.mark.parametrize("w,h,n,cut,me,subme,psub,inloop,mehook,mbenc", [
@@ -154,7 +154,9 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
     d_lv = torch.zeros(pkg.RES_LEVELS_PER_MB, dtype=torch.int16, device="cuda")
     d_nz = torch.zeros(pkg.RES_NNZ_PER_MB, dtype=torch.uint8, device="cuda")
     d_cbp = torch.zeros(1, dtype=torch.int16, device="cuda")
-    mbenc_calls = [0]
+    d_dc = torch.zeros(16, dtype=torch.int16, device="cuda")
+    d_kind = torch.zeros(1, dtype=torch.uint8, device="cuda")
+    mbenc_calls = [0, 0]                  # inter, I16x16
 
     def mb_planes(buf):
         luma = buf[g1.luma_origin:][: 16 * g1.luma_stride].reshape(16, g1.luma_stride)[:, :16]
@@ -163,7 +165,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         return luma, chroma
 
     @MBENC_CB
-    def mbenc_cb(hv, fenc_y, fenc_c, fdec_y, fdec_c, qp, levels, nnz, cbp):
+    def mbenc_cb(hv, fenc_y, fenc_c, fdec_y, fdec_c, qp, kind, levels, luma_dc, nnz, cbp):
         fy = host_view(fenc_y, 16 * 16).reshape(16, 16)
         fc = host_view(fenc_c, 8 * 16).reshape(8, 16)              # U at +0, V at +8
         dy = host_view(fdec_y, 16 * 32).reshape(16, 32)
@@ -174,8 +176,10 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             chroma[:, 0::2] = u_
             chroma[:, 1::2] = v_
         mb_slots.copy_(torch.from_numpy(mb_stage.reshape(-1)))
+        d_kind.fill_(kind)
         torch.cuda.synchronize()
-        ctx.residual_frame(g1, mb_slots[: g1.slot_bytes], mb_slots[g1.slot_bytes:], qp, d_lv, d_nz, d_cbp)
+        ctx.residual_frames_typed(g1, mb_slots[: g1.slot_bytes], mb_slots[g1.slot_bytes:], 1, qp, d_kind, d_lv, d_dc,
+                                  d_nz, d_cbp)
         ctx.sync()
         rec = mb_slots[g1.slot_bytes:].cpu().numpy()
         luma, chroma = mb_planes(rec)
@@ -184,8 +188,9 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         dc[:, 16:24] = chroma[:, 1::2]
         host_view(levels, 2 * pkg.RES_LEVELS_PER_MB)[:] = d_lv.cpu().numpy().view(np.uint8)
         host_view(nnz, pkg.RES_NNZ_PER_MB)[:] = d_nz.cpu().numpy()
+        host_view(luma_dc, 32)[:] = d_dc.cpu().numpy().view(np.uint8)
         cbp[0] = int(d_cbp.cpu().numpy()[0])
-        mbenc_calls[0] += 1
+        mbenc_calls[kind] += 1
         return 0
 
     outs, calls = [], (C.c_int * 3)()
@@ -221,7 +226,8 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             if mehook:
                 assert me_calls[0] >= (n - 3) * g.mb_count // 2, f"only {me_calls[0]} searches went to the device"
             if mbenc:
-                assert mbenc_calls[0] >= g.mb_count, f"only {mbenc_calls[0]} macroblocks were coded on the device"
+                assert mbenc_calls[0] >= g.mb_count, f"only {mbenc_calls[0]} inter macroblocks were coded on the device"
+                assert mbenc_calls[1] > 0, "no I16x16 macroblock of the I frames was coded on the device"
             if inloop:
                 assert deblocked[0] >= n - 1, f"deblocking ran on the device for {deblocked[0]} of {n} frames"
     assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), \
