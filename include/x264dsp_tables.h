@@ -171,6 +171,16 @@ void x264_mc_init( int cpu, x264_mc_functions_t *pf );
 void x264_quant_init( x264_t *h, int cpu, x264_quant_function_t *pf );
 void x264_deblock_init( int cpu, x264_deblock_function_t *pf );
 
+/* The intra predictor tables: x264_predict_t (common/predict.h:8) arrays indexed by the reference's
+ * enums -- I_PRED_16x16_{V,H,DC,P,DC_LEFT,DC_TOP,DC_128} (predict.h:27-37), I_PRED_CHROMA_{DC,H,V,P,DC_LEFT,DC_TOP,
+ * DC_128} (predict.h:10-20), I_PRED_4x4_{V,H,DC,DDL,DDR,VR,HD,VL,HU,DC_LEFT,DC_TOP,DC_128} (predict.h:44-59).  Each
+ * entry predicts the block at src (FDEC_STRIDE 32) in place from its row above / column to the left, like
+ * x264_predict_16x16_init / _8x8c_init / _4x4_init (common/predict.c:474-546; called at encoder/encoder.c:551-553). */
+typedef void (*x264_predict_t)( pixel *src );
+void x264_predict_16x16_init( int cpu, x264_predict_t pf[7] );
+void x264_predict_8x8c_init( int cpu, x264_predict_t pf[7] );
+void x264_predict_4x4_init( int cpu, x264_predict_t pf[12] );
+
 /* the context the shims run on (created on first use); NULL if no CUDA device could be opened */
 struct x264dsp_ctx;
 struct x264dsp_ctx *x264dsp_tables_context( void );

@@ -566,6 +566,16 @@ void xref_install_tables( void *hv, const void *pixf, const void *dctf, const vo
     h->quantf.coeff_level_run[DCT_CHROMA_DC] = h->quantf.coeff_level_run4;
 }
 
+/* the three intra predictor tables (encoder/encoder.c:551-553; predict_chroma is the copy made at encoder.c:447) */
+void xref_install_predict_tables( void *hv, const x264_predict_t *p16, const x264_predict_t *p8c, const x264_predict_t *p4 )
+{
+    x264_t *h = hv;
+    memcpy( h->predict_16x16, p16, sizeof(h->predict_16x16) );
+    memcpy( h->predict_8x8c, p8c, sizeof(h->predict_8x8c) );
+    memcpy( h->predict_chroma, p8c, sizeof(h->predict_chroma) );
+    memcpy( h->predict_4x4, p4, sizeof(h->predict_4x4) );
+}
+
 /* encode n_frames tightly packed I420 pictures with x264_encoder_encode, flush, and concatenate every
  * NAL payload into out; returns the byte count, or <0 on error / overflow */
 int xref_encode_clip( void *hv, uint8_t *i420, int n_frames, uint8_t *out, int out_cap )

@@ -357,11 +357,46 @@ def test_deblock_tables(tabs):
         assert np.array_equal(b1, b2), "deblock_strength"
 
 
+PRED_T = C.CFUNCTYPE(None, C.c_void_p)
+
+
+def predict_tables(lib):
+    t = [(PRED_T * 7)(), (PRED_T * 7)(), (PRED_T * 12)()]
+    lib.x264_predict_16x16_init(0, t[0])
+    lib.x264_predict_8x8c_init(0, t[1])
+    lib.x264_predict_4x4_init(0, t[2])
+    return t
+
+
+def test_predict_tables(pkg, ref_enc):
+    """all 26 intra predictors (x264_predict_16x16_init / _8x8c_init / _4x4_init, common/predict.c:474-546) against the
+    reference's own functions on random neighbourhoods; the whole buffer is compared, so nothing outside the block
+    may change"""
+    ours, theirs = predict_tables(pkg.lib()), predict_tables(ref_enc.lib)
+    rng = np.random.RandomState(11)
+    for t, size in ((0, 16), (1, 8), (2, 4)):
+        for mode in range(len(ours[t])):
+            for trial in range(12):
+                buf = rng.randint(0, 256, (40, 32)).astype(np.uint8)
+                if trial == 0:
+                    buf[:] = 255
+                elif trial == 1:
+                    buf[:] = 0
+                elif trial == 2:                              # steep gradients: the plane predictors must clip
+                    buf[:] = np.clip(np.add.outer(np.arange(40) * 17, np.arange(32) * 23) - 300, 0, 255)
+                a, b = buf.copy(), buf.copy()
+                off = 8 * 32 + 8
+                theirs[t][mode](at(a, off))
+                ours[t][mode](at(b, off))
+                assert np.array_equal(a, b), f"predict size {size} mode {mode} trial {trial}"
+                assert not np.array_equal(a, buf) or trial < 2, f"predict size {size} mode {mode}: nothing written"
+
+
 @pytest.mark.parametrize("w,h,n,me,subme,qp", [(96, 64, 4, 1, 5, 26), (64, 48, 3, 0, 2, 20), (176, 144, 5, 1, 4, 32)])
 def test_reference_encoder_runs_on_our_tables(pkg, ctx, w, h, n, me, subme, qp):
     """THE drop-in check: the unmodified reference encoder (x264_encoder_encode: lookahead, analysis,
-    ME, residual, deblock, CABAC) with its six tables replaced by ours must emit the same bitstream,
-    byte for byte, as with its own tables."""
+    ME, residual, deblock, CABAC) with its six tables and its three intra predictor tables replaced by ours
+    must emit the same bitstream, byte for byte, as with its own tables."""
     lib = cc.ref()
     assert lib is not None
     clip = np.concatenate(cc.synth_clip(w, h, n, seed=77, cut_frame=2))
@@ -378,6 +413,8 @@ def test_reference_encoder_runs_on_our_tables(pkg, ctx, w, h, n, me, subme, qp):
             plib.x264_quant_init(None, 0, C.byref(t[4]))
             plib.x264_deblock_init(0, C.byref(t[5]))
             lib.xref_install_tables(enc.h, *[C.byref(x) for x in t])
+            pt = predict_tables(plib)
+            lib.xref_install_predict_tables(enc.h, pt[0], pt[1], pt[2])
         out = np.zeros(1 << 20, np.uint8)
         launches0 = ctx.launches
         size = lib.xref_encode_clip(enc.h, ptr(clip), n, ptr(out), out.size)

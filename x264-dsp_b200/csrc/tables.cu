@@ -26,7 +26,7 @@
 
 enum
 {
-    OP_CMP = 1, OP_VAR, OP_VAR2, OP_INTRA,
+    OP_CMP = 1, OP_VAR, OP_VAR2, OP_INTRA, OP_PREDICT,
     OP_SUB_DCT, OP_SUB_DCT_DC, OP_ADD_IDCT, OP_ADD_IDCT_DC, OP_DCT4X4DC, OP_IDCT4X4DC, OP_ZIGZAG,
     OP_QUANT, OP_QUANT_DC, OP_DEQUANT, OP_DEQUANT_DC, OP_OPT_CHROMA_DC, OP_DENOISE, OP_DECIMATE, OP_COEFF_LAST,
     OP_LEVEL_RUN,
@@ -35,7 +35,7 @@ enum
 };
 enum { CMP_SAD = 0, CMP_SSD = 1, CMP_SATD = 2 };
 // intra prediction modes of the shims (not the reference's enum values)
-enum { PR_V = 0, PR_H, PR_DC, PR_DDL, PR_DDR, PR_VR, PR_HD, PR_VL, PR_HU };
+enum { PR_V = 0, PR_H, PR_DC, PR_DDL, PR_DDR, PR_VR, PR_HD, PR_VL, PR_HU, PR_DC_LEFT, PR_DC_TOP, PR_DC_128, PR_PLANE };
 
 struct xd_shim_args
 {
@@ -108,6 +108,9 @@ __device__ int xs_pred4x4_px( int mode, int x, int y, const int e[13] )
     case PR_V: return t[x];
     case PR_H: return L( y );
     case PR_DC: return ( L( 0 ) + L( 1 ) + L( 2 ) + L( 3 ) + t[0] + t[1] + t[2] + t[3] + 4 ) >> 3;
+    case PR_DC_LEFT: return ( L( 0 ) + L( 1 ) + L( 2 ) + L( 3 ) + 2 ) >> 2;          // predict.c:334-343
+    case PR_DC_TOP: return ( t[0] + t[1] + t[2] + t[3] + 2 ) >> 2;
+    case PR_DC_128: return 128;
     case PR_DDL:
         return ( x == 3 && y == 3 ) ? XS_F2( t[6], t[7], t[7] ) : XS_F2( t[x + y], t[x + y + 1], t[x + y + 2] );
     case PR_DDR:
@@ -167,6 +170,54 @@ __device__ void xs_predict( uint8_t *fd, int size, int mode, int lane )
     }
     const int n = size * size;
     int dcq[4] = { 0, 0, 0, 0 };
+    if( mode == PR_PLANE )
+    {
+        // x264_predict_16x16_p_c (predict.c:125-158), x264_predict_8x8c_p_c (predict.c:290-318)
+        const int half = size >> 1;
+        int H = 0, V = 0;
+        for( int i = 0; i < half; i++ )
+        {
+            H += ( i + 1 ) * ( fd[half + i - FDEC_STRIDE] - fd[half - 2 - i - FDEC_STRIDE] );
+            V += ( i + 1 ) * ( fd[-1 + ( half + i ) * FDEC_STRIDE] - fd[-1 + ( half - 2 - i ) * FDEC_STRIDE] );
+        }
+        const int a = 16 * ( fd[-1 + ( size - 1 ) * FDEC_STRIDE] + fd[size - 1 - FDEC_STRIDE] );
+        const int b = size == 16 ? ( 5 * H + 32 ) >> 6 : ( 17 * H + 16 ) >> 5;
+        const int c = size == 16 ? ( 5 * V + 32 ) >> 6 : ( 17 * V + 16 ) >> 5;
+        const int i00 = a - ( half - 1 ) * ( b + c ) + 16;
+        __syncwarp();
+        for( int i = lane; i < n; i += 32 )
+        {
+            const int x = i % size, y = i / size;
+            fd[y * FDEC_STRIDE + x] = (uint8_t)min( max( ( i00 + b * x + c * y ) >> 5, 0 ), 255 );
+        }
+        return;
+    }
+    if( mode == PR_DC_LEFT || mode == PR_DC_TOP || mode == PR_DC_128 )
+    {
+        // predict.c:62-94 (16x16), 163-213 (8x8c): one value for the block, or one per half for 8x8c
+        if( mode == PR_DC_128 )
+            dcq[0] = dcq[1] = dcq[2] = dcq[3] = 128;
+        else if( size == 16 )
+        {
+            int dc = 0;
+            for( int i = 0; i < 16; i++ )
+                dc += mode == PR_DC_LEFT ? fd[i * FDEC_STRIDE - 1] : fd[i - FDEC_STRIDE];
+            dcq[0] = ( dc + 8 ) >> 4;
+        }
+        else
+        {
+            int d0 = 0, d1 = 0;
+            for( int i = 0; i < 4; i++ )
+            {
+                d0 += mode == PR_DC_LEFT ? fd[i * FDEC_STRIDE - 1] : fd[i - FDEC_STRIDE];
+                d1 += mode == PR_DC_LEFT ? fd[( i + 4 ) * FDEC_STRIDE - 1] : fd[i + 4 - FDEC_STRIDE];
+            }
+            d0 = ( d0 + 2 ) >> 2;
+            d1 = ( d1 + 2 ) >> 2;
+            if( mode == PR_DC_LEFT ) { dcq[0] = dcq[1] = d0; dcq[2] = dcq[3] = d1; }
+            else { dcq[0] = dcq[2] = d0; dcq[1] = dcq[3] = d1; }
+        }
+    }
     if( mode == PR_DC )
     {
         if( size == 16 )
@@ -286,6 +337,13 @@ xd_shim_kernel( xd_shim_args A, uint8_t *__restrict__ b )
             if( lane == 0 )
                 ( (int *)( b + a[5] ) )[a[10 + m]] = c;
         }
+        break;
+    }
+    case OP_PREDICT:    // a: size, mode, off_fdec (block origin)                  predict.c:42-546
+    {
+        if( tid >= 32 )
+            return;
+        xs_predict( b + a[2], a[0], a[1], lane );
         break;
     }
     case OP_SUB_DCT:    // a: n_blocks (1,4,16), off_fenc, off_fdec, off_dct      dct.c:115-166
@@ -825,6 +883,51 @@ static void xs_intra( int cmp, int size, pixel *fenc, pixel *fdec, int n_modes, 
     for( int m = 0; m < n_modes; m++ )
         res[res_index[m]] = r[res_index[m]];
     xs_get( fdec, FDEC_STRIDE, F, size, size, FDEC_STRIDE );
+}
+
+// the neighbourhood of the block at src -> the predicted block, in place (x264_predict_t, predict.h:8).
+// The same bytes are read that the reference's predictors may read: the row above with its corner (and the four
+// top-right samples for 4x4) and the column to the left -- fdec_buf always has them (common/macroblock.c:242-265).
+static void xs_predict_call( int size, int mode, pixel *src )
+{
+    const size_t F = 1024 + FDEC_STRIDE + 16;
+    memcpy( g_h + F - FDEC_STRIDE - 1, src - FDEC_STRIDE - 1, 1 + ( size == 4 ? 8 : size ) );
+    for( int y = 0; y < size; y++ )
+        g_h[F + y * FDEC_STRIDE - 1] = src[y * FDEC_STRIDE - 1];
+    xd_shim_args A = { OP_PREDICT, { size, mode, (int)F } };
+    xs_run( A, 32 );
+    xs_get( src, FDEC_STRIDE, F, size, size, FDEC_STRIDE );
+}
+#define XS_PRED( name, size, mode ) static void name( pixel *src ) { xs_predict_call( size, mode, src ); }
+XS_PRED( xs_p16_v, 16, PR_V ) XS_PRED( xs_p16_h, 16, PR_H ) XS_PRED( xs_p16_dc, 16, PR_DC ) XS_PRED( xs_p16_p, 16, PR_PLANE )
+XS_PRED( xs_p16_dcl, 16, PR_DC_LEFT ) XS_PRED( xs_p16_dct, 16, PR_DC_TOP ) XS_PRED( xs_p16_128, 16, PR_DC_128 )
+XS_PRED( xs_p8_v, 8, PR_V ) XS_PRED( xs_p8_h, 8, PR_H ) XS_PRED( xs_p8_dc, 8, PR_DC ) XS_PRED( xs_p8_p, 8, PR_PLANE )
+XS_PRED( xs_p8_dcl, 8, PR_DC_LEFT ) XS_PRED( xs_p8_dct, 8, PR_DC_TOP ) XS_PRED( xs_p8_128, 8, PR_DC_128 )
+XS_PRED( xs_p4_v, 4, PR_V ) XS_PRED( xs_p4_h, 4, PR_H ) XS_PRED( xs_p4_dc, 4, PR_DC ) XS_PRED( xs_p4_ddl, 4, PR_DDL )
+XS_PRED( xs_p4_ddr, 4, PR_DDR ) XS_PRED( xs_p4_vr, 4, PR_VR ) XS_PRED( xs_p4_hd, 4, PR_HD ) XS_PRED( xs_p4_vl, 4, PR_VL )
+XS_PRED( xs_p4_hu, 4, PR_HU ) XS_PRED( xs_p4_dcl, 4, PR_DC_LEFT ) XS_PRED( xs_p4_dct, 4, PR_DC_TOP ) XS_PRED( xs_p4_128, 4, PR_DC_128 )
+
+// common/predict.c:474-546; the table order is the reference's enums (predict.h:10-59)
+extern "C" void x264_predict_16x16_init( int cpu, x264_predict_t pf[7] )
+{
+    (void)cpu;
+    xs_open();
+    pf[0] = xs_p16_v; pf[1] = xs_p16_h; pf[2] = xs_p16_dc; pf[3] = xs_p16_p;
+    pf[4] = xs_p16_dcl; pf[5] = xs_p16_dct; pf[6] = xs_p16_128;
+}
+extern "C" void x264_predict_8x8c_init( int cpu, x264_predict_t pf[7] )
+{
+    (void)cpu;
+    xs_open();
+    pf[0] = xs_p8_dc; pf[1] = xs_p8_h; pf[2] = xs_p8_v; pf[3] = xs_p8_p;
+    pf[4] = xs_p8_dcl; pf[5] = xs_p8_dct; pf[6] = xs_p8_128;
+}
+extern "C" void x264_predict_4x4_init( int cpu, x264_predict_t pf[12] )
+{
+    (void)cpu;
+    xs_open();
+    pf[0] = xs_p4_v; pf[1] = xs_p4_h; pf[2] = xs_p4_dc; pf[3] = xs_p4_ddl; pf[4] = xs_p4_ddr; pf[5] = xs_p4_vr;
+    pf[6] = xs_p4_hd; pf[7] = xs_p4_vl; pf[8] = xs_p4_hu; pf[9] = xs_p4_dcl; pf[10] = xs_p4_dct; pf[11] = xs_p4_128;
 }
 
 static const int xs_idx3[3] = { 0, 1, 2 };
