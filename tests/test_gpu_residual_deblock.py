@@ -173,16 +173,21 @@ def test_deblock_frames_batch(pkg, ctx, w, h, nf, qp):
     assert len(bad) == 0, f"{len(bad)} bytes differ, first at {bad[:4]} (slot {bad[0] // g.slot_bytes})"
 
 
-def test_deblock_strength(pkg, ctx):
+@pytest.mark.parametrize("n,skew", [(5000, 0), (4999, 0), (1, 0), (7, 0), (8161, 0), (333, 4)])
+def test_deblock_strength(pkg, ctx, n, skew):
+    """odd counts exercise the staged kernel's tail, skew != 0 the direct kernel (inputs not 16-byte aligned)"""
     import torch
-    rng = np.random.RandomState(3)
-    n = 5000
+    rng = np.random.RandomState(3 + n)
     nnz = (rng.rand(n, 120) < 0.3).astype(np.uint8)
     ref = rng.randint(-1, 2, (n, 2, 40)).astype(np.int8)
     mv = rng.randint(-6, 7, (n, 2, 40, 2)).astype(np.int16)
     want = np.zeros((n, 2, 8, 4), np.uint8)
     cc.oracle().xo_deblock_strength(n, ptr(nnz), ptr(ref, i8p), ptr(mv, i16p), ptr(want))
-    d = [torch.from_numpy(a).cuda() for a in (nnz, ref, mv)]
+    d = []
+    for a in (nnz, ref, mv):
+        raw = torch.zeros(a.nbytes + 64, dtype=torch.uint8, device="cuda")
+        raw[skew: skew + a.nbytes] = torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
+        d.append(raw[skew: skew + a.nbytes])
     bs = torch.zeros((n, 2, 8, 4), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     ctx.deblock_strength(n, d[0], d[1], d[2], bs)
