@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Generates tests/golden/golden_r01_intra.npz from the UNMODIFIED reference (oracle/_ref/libx264ref.so): the
+round's additions to the path --
+
+  * x264_macroblock_encode for I16x16 macroblocks of an I slice (x264_mb_encode_i16x16 + intra chroma) on stored
+    source blocks and predictions (oracle/ref_shim/harness.c: xref_encode_intra16_mb),
+  * all 26 intra predictors of x264_predict_16x16_init / _8x8c_init / _4x4_init on stored neighbourhoods.
+
+Run in the dev container only:  python tests/golden/make_golden_intra.py
+Every OUTPUT array comes from the reference's own functions; tests/test_golden.py checks the CPU oracle and the
+CUDA path against the file (the GPU box has no /root/reference)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TESTS = os.path.dirname(HERE)
+sys.path.insert(0, TESTS)
+sys.path.insert(0, os.path.dirname(TESTS))
+
+import cpu_checkers as cc          # noqa: E402
+from cpu_checkers import ptr, i16p  # noqa: E402
+
+OUT = os.path.join(HERE, "golden_r01_intra.npz")
+PRED_T = C.CFUNCTYPE(None, C.c_void_p)
+
+
+def main():
+    lib = cc.ref()
+    assert lib is not None, "make -C oracle ref first"
+    enc = cc.RefEncoder(128, 96, me=1, subme=5, me_range=16, qp=26)
+    lib.xref_encode_intra16_mb.restype = C.c_int
+    G = {}
+    # ------------------------------------------------------------ I16x16 macroblocks, 48 per QP (= one 128x96 frame)
+    r = np.random.RandomState(1616)
+    RQ = [12, 20, 26, 34, 44]
+    NMB = 48
+    fy, fc = np.zeros((len(RQ), NMB, 16, 16), np.uint8), np.zeros((len(RQ), NMB, 8, 16), np.uint8)
+    py, pc = np.zeros((len(RQ), NMB, 16, 32), np.uint8), np.zeros((len(RQ), NMB, 8, 32), np.uint8)
+    ry, rc = np.zeros_like(py), np.zeros_like(pc)
+    lv, dc = np.zeros((len(RQ), NMB, 392), np.int16), np.zeros((len(RQ), NMB, 16), np.int16)
+    nz, cbp = np.zeros((len(RQ), NMB, 27), np.uint8), np.zeros((len(RQ), NMB), np.int32)
+    for qi, qp in enumerate(RQ):
+        for t in range(NMB):
+            amp = [1, 3, 8, 25, 80][t % 5]
+            kind = t % 4
+            if kind == 0:
+                py[qi, t, :, :16] = r.randint(20, 236)
+                pc[qi, t, :, :8], pc[qi, t, :, 16:24] = r.randint(20, 236), r.randint(20, 236)
+            elif kind == 1:
+                py[qi, t, :, :16] = r.randint(0, 256, 16)[None, :]
+                pc[qi, t, :, :8], pc[qi, t, :, 16:24] = r.randint(0, 256, 8)[None, :], r.randint(0, 256, 8)[None, :]
+            elif kind == 2:
+                py[qi, t, :, :16] = r.randint(0, 256, 16)[:, None]
+                pc[qi, t, :, :8], pc[qi, t, :, 16:24] = r.randint(0, 256, 8)[:, None], r.randint(0, 256, 8)[:, None]
+            else:
+                py[qi, t, :, :16] = r.randint(0, 256, (16, 16))
+                pc[qi, t, :, :8], pc[qi, t, :, 16:24] = r.randint(0, 256, (8, 8)), r.randint(0, 256, (8, 8))
+            f = np.clip(py[qi, t, :, :16].astype(int) + r.randint(-amp, amp + 1, (16, 16)), 0, 255)
+            if t % 6 == 0:
+                f = np.clip(py[qi, t, :, :16].astype(int) + r.randint(-6, 7), 0, 255)      # DC-only luma change
+            fy[qi, t] = f
+            fc[qi, t, :, :8] = np.clip(pc[qi, t, :, :8].astype(int) + r.randint(-amp, amp + 1, (8, 8)), 0, 255)
+            fc[qi, t, :, 8:] = np.clip(pc[qi, t, :, 16:24].astype(int) + r.randint(-amp, amp + 1, (8, 8)), 0, 255)
+            y1, c1 = py[qi, t].copy(), pc[qi, t].copy()
+            cbp[qi, t] = lib.xref_encode_intra16_mb(enc.h, ptr(np.ascontiguousarray(fy[qi, t])), ptr(np.ascontiguousarray(fc[qi, t])),
+                                                    ptr(y1), ptr(c1), qp, ptr(lv[qi, t], i16p), ptr(dc[qi, t], i16p), ptr(nz[qi, t]))
+            ry[qi, t], rc[qi, t] = y1, c1
+    G["i16_qps"] = np.array(RQ)
+    G["i16_fenc_y"], G["i16_fenc_c"], G["i16_pred_y"], G["i16_pred_c"] = fy, fc, py[..., :16], pc[..., :24]
+    G["i16_recon_y"], G["i16_recon_c"] = ry[..., :16], rc[..., :24]
+    G["i16_levels"], G["i16_luma_dc"], G["i16_nnz"], G["i16_cbp"] = lv, dc, nz, cbp
+
+    # ------------------------------------------------------------ the 26 predictors on 10 neighbourhoods each
+    tabs = [(PRED_T * 7)(), (PRED_T * 7)(), (PRED_T * 12)()]
+    lib.x264_predict_16x16_init(0, tabs[0])
+    lib.x264_predict_8x8c_init(0, tabs[1])
+    lib.x264_predict_4x4_init(0, tabs[2])
+    NT = 10
+    src = r.randint(0, 256, (NT, 40, 32)).astype(np.uint8)
+    src[0], src[1] = 255, 0
+    src[2] = np.clip(np.add.outer(np.arange(40) * 17, np.arange(32) * 23) - 300, 0, 255)
+    G["pred_src"] = src
+    for ti, (name, size) in enumerate((("p16", 16), ("p8c", 8), ("p4", 4))):
+        out = np.zeros((len(tabs[ti]), NT, size, size), np.uint8)
+        for mode in range(len(tabs[ti])):
+            for t in range(NT):
+                b = src[t].copy()
+                tabs[ti][mode](C.cast(b.ctypes.data + 8 * 32 + 8, C.c_void_p))
+                assert np.array_equal(np.delete(b.reshape(-1), [(8 + y) * 32 + 8 + x for y in range(size) for x in range(size)]),
+                                      np.delete(src[t].reshape(-1), [(8 + y) * 32 + 8 + x for y in range(size) for x in range(size)]))
+                out[mode, t] = b[8:8 + size, 8:8 + size]
+        G["pred_" + name] = out
+    np.savez_compressed(OUT, **G)
+    print(f"wrote {OUT}: {os.path.getsize(OUT) / 1024:.0f} KiB, {len(G)} arrays")
+
+
+if __name__ == "__main__":
+    main()

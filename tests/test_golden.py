@@ -595,3 +595,109 @@ def test_gpu_tables_vs_golden(G, pkg, ctx, tables):
                     getattr(lf, name)[d](at(q, dorg), dstride, alpha, beta, ptr(tc0, i8p))
                 assert np.array_equal(q, douts[k]), f"{name}[{d}]"
                 k += 1
+
+
+# ------------------------------------------------------------------ golden_r01_intra.npz: I16x16 macroblocks, predictors
+
+@pytest.fixture(scope="module")
+def GI():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_r01_intra.npz")
+    return np.load(path)
+
+
+def check_intra16(GI, qi, t, cbp, nz, lv, dc, ry, rc):
+    assert cbp == GI["i16_cbp"][qi, t], f"cbp qp#{qi} mb {t}: {cbp:#x} vs {int(GI['i16_cbp'][qi, t]):#x}"
+    want_nz = GI["i16_nnz"][qi, t]
+    assert np.array_equal(nz, want_nz), f"nnz qp#{qi} mb {t}"
+    assert np.array_equal(ry, GI["i16_recon_y"][qi, t]), f"luma recon qp#{qi} mb {t}"
+    assert np.array_equal(rc[:, :8], GI["i16_recon_c"][qi, t][:, :8]) and np.array_equal(rc[:, 16:24], GI["i16_recon_c"][qi, t][:, 16:24])
+    want = GI["i16_levels"][qi, t]
+    for i in range(16):
+        if want_nz[i]:
+            assert np.array_equal(lv[i * 16:(i + 1) * 16], want[i * 16:(i + 1) * 16]), f"luma levels qp#{qi} mb {t} blk {i}"
+    if want_nz[24]:
+        assert np.array_equal(dc, GI["i16_luma_dc"][qi, t]), f"luma dc levels qp#{qi} mb {t}"
+    for ch in range(2):
+        if want_nz[25 + ch]:
+            assert np.array_equal(lv[256 + 4 * ch: 260 + 4 * ch], want[256 + 4 * ch: 260 + 4 * ch]), f"chroma dc qp#{qi} mb {t}"
+    for i in range(8):
+        if want_nz[16 + i]:
+            assert np.array_equal(lv[264 + i * 16: 280 + i * 16], want[264 + i * 16: 280 + i * 16]), f"chroma ac {i}"
+
+
+def test_oracle_intra16_mb(GI):
+    o = cc.oracle()
+    o.xo_encode_intra16_mb.restype = C.c_int
+    coded_dc = 0
+    for qi, qp in enumerate(GI["i16_qps"]):
+        for t in range(GI["i16_fenc_y"].shape[1]):
+            y = np.zeros((16, 32), np.uint8)
+            c = np.zeros((8, 32), np.uint8)
+            y[:, :16], c[:, :24] = GI["i16_pred_y"][qi, t], GI["i16_pred_c"][qi, t]
+            lv, dc, nz = np.zeros(392, np.int16), np.zeros(16, np.int16), np.zeros(27, np.uint8)
+            cbp = o.xo_encode_intra16_mb(ptr(np.ascontiguousarray(GI["i16_fenc_y"][qi, t])),
+                                         ptr(np.ascontiguousarray(GI["i16_fenc_c"][qi, t])), ptr(y), ptr(c), int(qp),
+                                         ptr(lv, i16p), ptr(dc, i16p), ptr(nz))
+            check_intra16(GI, qi, t, cbp, nz, lv, dc, y[:, :16], c[:, :24])
+            coded_dc += int(nz[24])
+    assert coded_dc > 20
+
+
+@pytest.mark.gpu
+def test_gpu_intra16_frame(GI, pkg, ctx):
+    """the 48 stored I16x16 macroblocks of each QP laid out as one 128x96 frame, x264dsp_residual_frames_typed_dev"""
+    import torch
+    g = pkg.geometry(128, 96)
+    assert g.mb_count == GI["i16_fenc_y"].shape[1]
+    cs = g.chroma_stride
+    for qi, qp in enumerate(GI["i16_qps"]):
+        fenc, pred = np.zeros(g.slot_bytes, np.uint8), np.zeros(g.slot_bytes, np.uint8)
+        for t in range(g.mb_count):
+            mx, my = t % g.mb_w, t // g.mb_w
+            for slot, y, c, voff in ((fenc, GI["i16_fenc_y"][qi, t], GI["i16_fenc_c"][qi, t], 8),
+                                     (pred, GI["i16_pred_y"][qi, t], GI["i16_pred_c"][qi, t], 16)):
+                lo = g.luma_origin + my * 16 * g.luma_stride + mx * 16
+                for r in range(16):
+                    slot[lo + r * g.luma_stride: lo + r * g.luma_stride + 16] = y[r]
+                co = g.slot_chroma_off + g.chroma_origin + my * 8 * cs + mx * 16
+                for r in range(8):
+                    slot[co + r * cs: co + r * cs + 16: 2] = c[r, :8]
+                    slot[co + r * cs + 1: co + r * cs + 16: 2] = c[r, voff: voff + 8]
+        d_fenc, d_pred = torch.from_numpy(fenc).cuda(), torch.from_numpy(pred).cuda()
+        kind = torch.ones(g.mb_count, dtype=torch.uint8, device="cuda")
+        lv = torch.zeros((g.mb_count, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda")
+        dc = torch.zeros((g.mb_count, 16), dtype=torch.int16, device="cuda")
+        nz = torch.zeros((g.mb_count, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda")
+        cbp = torch.zeros(g.mb_count, dtype=torch.int16, device="cuda")
+        torch.cuda.synchronize()
+        ctx.residual_frames_typed(g, d_fenc, d_pred, 1, int(qp), kind, lv, dc, nz, cbp)
+        ctx.sync()
+        lv, dc, nz, cbp, rec = lv.cpu().numpy(), dc.cpu().numpy(), nz.cpu().numpy(), cbp.cpu().numpy(), d_pred.cpu().numpy()
+        for t in range(g.mb_count):
+            mx, my = t % g.mb_w, t // g.mb_w
+            lo = g.luma_origin + my * 16 * g.luma_stride + mx * 16
+            ry = np.stack([rec[lo + r * g.luma_stride: lo + r * g.luma_stride + 16] for r in range(16)])
+            co = g.slot_chroma_off + g.chroma_origin + my * 8 * cs + mx * 16
+            rc = np.zeros((8, 24), np.uint8)
+            for r in range(8):
+                rc[r, :8] = rec[co + r * cs: co + r * cs + 16: 2]
+                rc[r, 16:24] = rec[co + r * cs + 1: co + r * cs + 16: 2]
+            check_intra16(GI, qi, t, int(cbp[t]), nz[t], lv[t], dc[t], ry, rc)
+
+
+@pytest.mark.gpu
+def test_gpu_predict_tables_golden(GI, pkg):
+    """all 26 predictors of the library's x264_predict_*_init tables against the stored outputs of the reference's"""
+    lib = pkg.lib()
+    PRED_T = C.CFUNCTYPE(None, C.c_void_p)
+    tabs = [(PRED_T * 7)(), (PRED_T * 7)(), (PRED_T * 12)()]
+    lib.x264_predict_16x16_init(0, tabs[0])
+    lib.x264_predict_8x8c_init(0, tabs[1])
+    lib.x264_predict_4x4_init(0, tabs[2])
+    for ti, (name, size) in enumerate((("p16", 16), ("p8c", 8), ("p4", 4))):
+        want = GI["pred_" + name]
+        for mode in range(len(tabs[ti])):
+            for t in range(GI["pred_src"].shape[0]):
+                b = GI["pred_src"][t].copy()
+                tabs[ti][mode](C.cast(b.ctypes.data + 8 * 32 + 8, C.c_void_p))
+                assert np.array_equal(b[8:8 + size, 8:8 + size], want[mode, t]), f"{name} mode {mode} case {t}"
