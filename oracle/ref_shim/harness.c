@@ -500,6 +500,81 @@ int xref_encode_intra16_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc
     return h->mb.cbp[0];
 }
 
+/* x264_macroblock_encode for one I4x4 macroblock of an I slice.  fdec_y points at the macroblock origin inside a
+ * caller buffer of stride 32 that holds the reconstructed neighbours (row -1 from column -1 to 19, column -1 of rows
+ * 0..15), exactly what the reference's fdec_buf holds at that point; the 4x4 predictors and everything else are the
+ * reference's own, the chroma prediction is the caller's (predict_chroma swapped for a no-op as above).
+ * modes[16] = h->mb.cache.intra4x4_pred_mode in coding order; replicate5: block 5 lacks its top-right samples. */
+int xref_encode_intra4_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y, uint8_t *fdec_c,
+                           int qp, const uint8_t *modes, int replicate5, int16_t *levels, uint8_t *nnz )
+{
+    x264_t *h = hv;
+    int i, y;
+    const int all = MB_LEFT|MB_TOP|MB_TOPLEFT|MB_TOPRIGHT;
+    x264_predict_t keepc = h->predict_chroma[0];
+    h->sh.i_type = SLICE_TYPE_I;
+    x264_macroblock_thread_init( h );
+    h->mb.i_type = I_4x4;
+    h->mb.i_skip_intra = 0;
+    h->mb.i_chroma_pred_mode = 0;
+    h->mb.b_dct_decimate = 0;
+    h->mb.b_noise_reduction = 0;
+    h->mb.b_transform_8x8 = 0;
+    h->nr_count = h->nr_count_buf[0];
+    h->mb.i_qp = qp;
+    h->mb.i_chroma_qp = h->chroma_qp_table[qp];
+    h->mb.i_mb_xy = 0;
+    h->mb.i_neighbour4[0] = h->mb.i_neighbour4[1] = h->mb.i_neighbour4[2] = h->mb.i_neighbour4[4] =
+    h->mb.i_neighbour4[8] = h->mb.i_neighbour4[10] = all;
+    h->mb.i_neighbour4[5] = replicate5 ? MB_LEFT|MB_TOP|MB_TOPLEFT : all;
+    /* what x264_macroblock_slice_init sets once per slice (common/macroblock.c:217-225) */
+    h->mb.i_neighbour4[6] = h->mb.i_neighbour4[9] = h->mb.i_neighbour4[12] = h->mb.i_neighbour4[14] = all;
+    h->mb.i_neighbour4[3] = h->mb.i_neighbour4[7] = h->mb.i_neighbour4[11] = h->mb.i_neighbour4[13] =
+    h->mb.i_neighbour4[15] = MB_LEFT|MB_TOP|MB_TOPLEFT;
+    for( i = 0; i < 16; i++ )
+        h->mb.cache.intra4x4_pred_mode[x264_scan8[i]] = (int8_t)modes[i];
+    memset( &h->dct, 0, sizeof(h->dct) );
+    memset( h->mb.cache.non_zero_count, 0, sizeof(h->mb.cache.non_zero_count) );
+    memcpy( h->mb.pic.p_fdec[0] - FDEC_STRIDE - 1, fdec_y - 32 - 1, 21 );
+    for( y = 0; y < 16; y++ )
+    {
+        memcpy( h->mb.pic.p_fenc[0] + y*FENC_STRIDE, fenc_y + y*16, 16 );
+        memcpy( h->mb.pic.p_fdec[0] + y*FDEC_STRIDE - 1, fdec_y + y*32 - 1, 17 );
+    }
+    for( y = 0; y < 8; y++ )
+    {
+        memcpy( h->mb.pic.p_fenc[1] + y*FENC_STRIDE, fenc_c + y*16, 16 );
+        memcpy( h->mb.pic.p_fdec[1] + y*FDEC_STRIDE, fdec_c + y*32, 8 );
+        memcpy( h->mb.pic.p_fdec[2] + y*FDEC_STRIDE, fdec_c + y*32 + 16, 8 );
+    }
+    h->predict_chroma[0] = xref_predict_noop;
+    x264_macroblock_encode( h );
+    h->predict_chroma[0] = keepc;
+    for( y = 0; y < 16; y++ )
+        memcpy( fdec_y + y*32, h->mb.pic.p_fdec[0] + y*FDEC_STRIDE, 16 );
+    for( y = 0; y < 8; y++ )
+    {
+        memcpy( fdec_c + y*32, h->mb.pic.p_fdec[1] + y*FDEC_STRIDE, 8 );
+        memcpy( fdec_c + y*32 + 16, h->mb.pic.p_fdec[2] + y*FDEC_STRIDE, 8 );
+    }
+    memcpy( levels, h->dct.luma4x4[0], 16*16*sizeof(int16_t) );
+    memcpy( levels + 256, h->dct.chroma_dc[0], 4*sizeof(int16_t) );
+    memcpy( levels + 260, h->dct.chroma_dc[1], 4*sizeof(int16_t) );
+    memcpy( levels + 264, h->dct.luma4x4[16], 4*16*sizeof(int16_t) );
+    memcpy( levels + 328, h->dct.luma4x4[32], 4*16*sizeof(int16_t) );
+    for( i = 0; i < 16; i++ )
+        nnz[i] = h->mb.cache.non_zero_count[x264_scan8[i]];
+    for( i = 0; i < 4; i++ )
+    {
+        nnz[16+i] = h->mb.cache.non_zero_count[x264_scan8[16+i]];
+        nnz[20+i] = h->mb.cache.non_zero_count[x264_scan8[32+i]];
+    }
+    nnz[24] = h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]];
+    nnz[25] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]];
+    nnz[26] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]];
+    return h->mb.cbp[0];
+}
+
 /* ------------------------------------------------------------------ timing helpers
  * (cpu_baseline / --impl reference): loops over the reference functions with the
  * input already in memory; CLOCK_MONOTONIC around the loop; returns seconds. */

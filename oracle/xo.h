@@ -124,7 +124,13 @@ void xo_mc_frame( const x264dsp_geom_t *g, const uint8_t *fref_slot, const int16
 void xo_residual_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
                         int16_t *levels, uint8_t *nnz, int16_t *cbp );
 void xo_residual_frame_typed( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
-                              const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int16_t *cbp );
+                              const uint8_t *mb_kind, const uint8_t *i4_modes, int16_t *levels, int16_t *luma_dc,
+                              uint8_t *nnz, int16_t *cbp );
+void xo_predict_4x4( int mode, pixel_t *src );
+int xo_encode_luma_i4x4( const pixel_t *fenc, pixel_t *fdec, int qp, const uint8_t modes[16], int replicate5,
+                         int16_t *levels, uint8_t *nnz );
+int xo_encode_intra4_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
+                         int qp, const uint8_t modes[16], int replicate5, int16_t *levels, uint8_t *nnz );
 int xo_encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
                           int qp, int16_t *levels, int16_t *luma_dc, uint8_t *nnz );
 

@@ -283,6 +283,28 @@ static int encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixe
     return (cbp_chroma << 4) | cbp_luma | (o->nnz[24] << 8) | (o->nnz[25] << 9) | (o->nnz[26] << 10);
 }
 
+/* I4x4 macroblock of an I slice: luma through xo_encode_luma_i4x4 (fdec_y with its reconstructed neighbours, see
+ * xo_predict.c), chroma as for I16x16 on the caller's chroma prediction */
+static int encode_intra4_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
+                             int qp, const uint8_t modes[16], int replicate5, mb_out_t *o )
+{
+    int cbp_luma, cbp_chroma;
+    memset( o->luma, 0, 16*16*sizeof(int16_t) );
+    memset( o->chroma_dc, 0, 8*sizeof(int16_t) );
+    memset( o->chroma_ac, 0, 8*16*sizeof(int16_t) );
+    memset( o->nnz, 0, X264DSP_RES_NNZ_PER_MB );
+    cbp_luma = xo_encode_luma_i4x4( fenc_y, fdec_y, qp, modes, replicate5, o->luma, o->nnz );
+    cbp_chroma = encode_chroma( fenc_c, fenc_c + 8, fdec_c, fdec_c + 16, xo_chroma_qp( qp ), o, 0 );
+    return (cbp_chroma << 4) | cbp_luma | (o->nnz[25] << 9) | (o->nnz[26] << 10);
+}
+
+int xo_encode_intra4_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
+                         int qp, const uint8_t modes[16], int replicate5, int16_t *levels, uint8_t *nnz )
+{
+    mb_out_t o = { levels, levels + 256, levels + 264, nnz };
+    return encode_intra4_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp, modes, replicate5, &o );
+}
+
 int xo_encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t *fdec_y, pixel_t *fdec_c,
                           int qp, int16_t *levels, int16_t *luma_dc, uint8_t *nnz )
 {
@@ -293,13 +315,16 @@ int xo_encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t 
 void xo_residual_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
                         int16_t *levels, uint8_t *nnz, int16_t *cbp )
 {
-    xo_residual_frame_typed( g, fenc_slot, pred_slot, qp, NULL, levels, NULL, nnz, cbp );
+    xo_residual_frame_typed( g, fenc_slot, pred_slot, qp, NULL, NULL, levels, NULL, nnz, cbp );
 }
 
-/* mb_kind[xy]: 0 = inter macroblock of a P slice, 1 = I16x16 macroblock of an I slice (NULL: all inter);
- * luma_dc[xy][16] is written for kind 1 (zeroed for kind 0) when not NULL */
+/* mb_kind[xy]: 0 = inter macroblock of a P slice, 1 = I16x16 macroblock of an I slice, 2 = I4x4 macroblock of an
+ * I slice with modes i4_modes[xy][16] (+4: it has a row above but no top-right macroblock); NULL: all inter.
+ * Macroblocks are coded in raster order, so an I4x4 macroblock sees its neighbours' reconstruction in pred_slot.
+ * luma_dc[xy][16] is written for kind 1 (zeroed otherwise) when not NULL */
 void xo_residual_frame_typed( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
-                              const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int16_t *cbp )
+                              const uint8_t *mb_kind, const uint8_t *i4_modes, int16_t *levels, int16_t *luma_dc,
+                              uint8_t *nnz, int16_t *cbp )
 {
     const int ls = g->luma_stride, cs = g->chroma_stride;
     int mb_x, mb_y, x, y;
@@ -330,7 +355,23 @@ void xo_residual_frame_typed( const x264dsp_geom_t *g, const uint8_t *fenc_slot,
                     fdec_c[y*FDEC + x]      = pc[(ptrdiff_t)y*cs + 2*x];
                     fdec_c[y*FDEC + 16 + x] = pc[(ptrdiff_t)y*cs + 2*x + 1];
                 }
-            if( mb_kind && mb_kind[xy] )
+            if( mb_kind && ( mb_kind[xy] & 3 ) == 2 )
+            {
+                /* the macroblock with its neighbourhood: row -1 from column -1 to 19, column -1 */
+                pixel_t nb[17*FDEC];
+                pixel_t *org = nb + FDEC + 8;
+                memset( nb, 0, sizeof(nb) );
+                memcpy( org - FDEC - 1, py - ls - 1, 21 );
+                for( y = 0; y < 16; y++ )
+                    memcpy( org + y*FDEC - 1, py + (ptrdiff_t)y*ls - 1, 17 );
+                if( luma_dc )
+                    memset( luma_dc + (size_t)xy*16, 0, 16*sizeof(int16_t) );
+                cbp[xy] = (int16_t)encode_intra4_mb( fenc_y, fenc_c, org, fdec_c, qp, i4_modes + (size_t)xy*16,
+                                                     ( mb_kind[xy] & 4 ) != 0, &o );
+                for( y = 0; y < 16; y++ )
+                    memcpy( fdec_y + y*FDEC, org + y*FDEC, 16 );
+            }
+            else if( mb_kind && mb_kind[xy] )
             {
                 int16_t dc_tmp[16];
                 cbp[xy] = (int16_t)encode_intra16_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp, &o, luma_dc ? luma_dc + (size_t)xy*16 : dc_tmp );

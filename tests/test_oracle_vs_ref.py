@@ -554,3 +554,60 @@ def test_residual_intra16_mb(enc, qp):
         for i in range(8):
             if n1[16 + i]:
                 assert np.array_equal(l1[264 + i * 16: 280 + i * 16], l2[264 + i * 16: 280 + i * 16]), f"chroma ac {trial} blk {i}"
+
+
+def test_predict_4x4_oracle(enc):
+    """the oracle's per-pixel restatement of the twelve 4x4 predictors against x264_predict_4x4_init's functions"""
+    o = cc.oracle()
+    PRED_T = C.CFUNCTYPE(None, C.c_void_p)
+    tab = (PRED_T * 12)()
+    enc.lib.x264_predict_4x4_init(0, tab)
+    rng = np.random.RandomState(44)
+    for mode in range(12):
+        for trial in range(40):
+            buf = rng.randint(0, 256, (12, 32)).astype(np.uint8)
+            if trial < 2:
+                buf[:] = 255 * trial
+            a, b = buf.copy(), buf.copy()
+            tab[mode](C.cast(a.ctypes.data + 4 * 32 + 8, C.c_void_p))
+            o.xo_predict_4x4(mode, C.cast(b.ctypes.data + 4 * 32 + 8, C.c_void_p))
+            assert np.array_equal(a, b), f"mode {mode} trial {trial}"
+
+
+@pytest.mark.parametrize("qp", [12, 20, 26, 34, 44, 51])
+def test_residual_intra4_mb(enc, qp):
+    """x264_macroblock_encode on I4x4 macroblocks (sixteen predict / transform / reconstruct steps, each predicting
+    from the blocks before it) with random mode sets: reference against oracle"""
+    o = cc.oracle()
+    rng = np.random.RandomState(400 + qp)
+    o.xo_encode_intra4_mb.restype = C.c_int
+    enc.lib.xref_encode_intra4_mb.restype = C.c_int
+    for trial in range(200):
+        nb = rng.randint(0, 256, (17, 32)).astype(np.uint8)         # row 0 = the row above; origin at (1, 8)
+        if trial % 4 == 0:
+            nb[:] = rng.randint(40, 200)
+        base = rng.randint(0, 256) if trial % 3 else None
+        fenc_y = (rng.randint(0, 256, (16, 16)) if base is None else
+                  np.clip(base + rng.randint(-30, 31, (16, 16)) + np.arange(16)[None, :] * rng.randint(-3, 4), 0, 255)).astype(np.uint8)
+        pred_c = np.zeros((8, 32), np.uint8)
+        pred_c[:, :8], pred_c[:, 16:24] = rng.randint(20, 236), rng.randint(20, 236)
+        fenc_c = np.zeros((8, 16), np.uint8)
+        fenc_c[:, :8] = np.clip(pred_c[:, :8].astype(int) + rng.randint(-9, 10, (8, 8)), 0, 255)
+        fenc_c[:, 8:] = np.clip(pred_c[:, 16:24].astype(int) + rng.randint(-9, 10, (8, 8)), 0, 255)
+        modes = rng.randint(0, 12, 16).astype(np.uint8)
+        rep5 = int(trial % 2)
+        y1, y2, c1, c2 = nb.copy(), nb.copy(), pred_c.copy(), pred_c.copy()
+        l1, l2 = np.zeros(392, np.int16), np.zeros(392, np.int16)
+        n1, n2 = np.zeros(27, np.uint8), np.zeros(27, np.uint8)
+        org1 = C.cast(y1.ctypes.data + 32 + 8, C.c_void_p)
+        org2 = C.cast(y2.ctypes.data + 32 + 8, C.c_void_p)
+        cbp1 = enc.lib.xref_encode_intra4_mb(enc.h, ptr(fenc_y), ptr(fenc_c), org1, ptr(c1), qp, ptr(modes), rep5,
+                                             ptr(l1, i16p), ptr(n1))
+        cbp2 = o.xo_encode_intra4_mb(ptr(fenc_y), ptr(fenc_c), org2, ptr(c2), qp, ptr(modes), rep5, ptr(l2, i16p), ptr(n2))
+        assert cbp1 == cbp2, f"cbp trial {trial}: {cbp1:#x} vs {cbp2:#x}"
+        assert np.array_equal(n1, n2), f"nnz trial {trial}"
+        assert np.array_equal(y1[1:, 8:24], y2[1:, 8:24]), f"luma recon trial {trial} modes {modes}"
+        assert np.array_equal(c1[:, :8], c2[:, :8]) and np.array_equal(c1[:, 16:24], c2[:, 16:24]), f"chroma recon {trial}"
+        for i in range(16):
+            if n1[i]:
+                assert np.array_equal(l1[i * 16:(i + 1) * 16], l2[i * 16:(i + 1) * 16]), f"luma levels trial {trial} blk {i}"
