@@ -334,11 +334,19 @@ int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
  * (h->predict_16x16[mode] / h->predict_chroma[mode] output), reconstruction in place.
  *   luma_dc [frame][mb][16] int16   zig-zagged levels of the luma DC block (h->dct.luma16x16_dc), zero for kind 0;
  *                                   may be NULL.  nnz[24] and bit 8 of cbp carry its non-zero flag.
- * mb_kind == NULL codes every macroblock as kind 0. */
+ * mb_kind = 2 codes an I4x4 macroblock of an I slice (I_4x4 branch of x264_macroblock_encode, encoder/macroblock.c:
+ * 355-377, + x264_mb_encode_i4x4, encoder/macroblock.h:37-61): i4_modes[frame][mb][16] holds the sixteen I_PRED_4x4_*
+ * modes (h->mb.cache.intra4x4_pred_mode, coding order); each block is predicted from the RECONSTRUCTION around it, so
+ * pred_slot must hold the final reconstruction of the macroblock's left, top-left, top and top-right neighbours (their
+ * row / column next to the macroblock) -- no such neighbour may be an I4x4 macroblock of the same launch; a wavefront
+ * caller launches per anti-diagonal.  Add 4 to the kind (6) when the macroblock has a row above it but no top-right
+ * macroblock (block 5 then replicates its last top sample, macroblock.c:372-374).  The chroma prediction is the
+ * caller's, as for kind 1.
+ * mb_kind == NULL codes every macroblock as kind 0; i4_modes may be NULL when no macroblock has kind 2. */
 int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
                                        const uint8_t *fenc_slots, uint8_t *pred_slots, int n_frames, int qp,
-                                       const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc,
-                                       uint8_t *nnz, int16_t *cbp, void *stream );
+                                       const uint8_t *mb_kind, const uint8_t *i4_modes, int16_t *levels,
+                                       int16_t *luma_dc, uint8_t *nnz, int16_t *cbp, void *stream );
 
 /* x264_mb_mc for P_L0 16x16 macroblocks (common/macroblock.c:8-28; mc_luma common/mc.c:216-239,
  * mc_chroma common/mc.c:290-323): builds the prediction frame from one quarter-pel MV per MB. */

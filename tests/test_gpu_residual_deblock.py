@@ -198,16 +198,23 @@ def test_deblock_strength(pkg, ctx, n, skew):
 
 @pytest.mark.parametrize("w,h,nf,qp,intra_share", [(352, 288, 2, 26, 0.5), (200, 120, 3, 18, 1.0), (352, 288, 2, 38, 0.3),
                                                     (1920, 1080, 2, 30, 0.5), (352, 288, 2, 12, 1.0), (208, 160, 2, 51, 0.5)])
-def test_residual_frames_typed_inter_and_i16x16(pkg, ctx, w, h, nf, qp, intra_share):
-    """x264dsp_residual_frames_typed_dev: inter macroblocks (P slice rules) and I16x16 macroblocks (I slice rules:
-    intra tables, luma DC block, no decimation) mixed in one launch, against the oracle (pinned to the reference's
-    x264_macroblock_encode for both kinds, tests/test_oracle_vs_ref.py)"""
+def test_residual_frames_typed_inter_i16x16_i4x4(pkg, ctx, w, h, nf, qp, intra_share):
+    """x264dsp_residual_frames_typed_dev: inter macroblocks (P slice rules), I16x16 macroblocks (I slice rules: intra
+    tables, luma DC block, no decimation) and I4x4 macroblocks (sixteen serial predict / transform / reconstruct steps
+    on random mode sets; placed on the even-even lattice so that none neighbours another) mixed in one launch, against
+    the oracle (pinned to the reference's x264_macroblock_encode for all three kinds, tests/test_oracle_vs_ref.py)"""
     import torch
     g, go, host, dev = _slots(pkg, ctx, w, h, nf + 1, False)
     o = cc.oracle()
     rng = np.random.RandomState(qp + nf + w)
     n = g.mb_count
     kind = (rng.rand(nf, n) < intra_share).astype(np.uint8)
+    xs, ys = np.arange(n) % g.mb_w, np.arange(n) // g.mb_w
+    lattice = (xs % 2 == 0) & (ys % 2 == 0)
+    i4 = lattice[None, :] & (rng.rand(nf, n) < 0.7)
+    kind[i4] = 2
+    kind[i4 & (rng.rand(nf, n) < 0.3)] = 6                   # a row above but no top-right macroblock
+    modes = rng.randint(0, 12, (nf, n, 16)).astype(np.uint8)
     # prediction: the previous frame (zero-motion inter prediction); intra macroblocks get a flat (DC-like) luma block
     # or a vertical / horizontal extension of the source's own first row / column, and flat chroma
     preds = []
@@ -219,7 +226,7 @@ def test_residual_frames_typed_inter_and_i16x16(pkg, ctx, w, h, nf, qp, intra_sh
         co = go.slot_chroma_off + go.chroma_origin
         chroma = p[co:].reshape(-1)[: (8 * go.mb_h) * go.chroma_stride].reshape(8 * go.mb_h, go.chroma_stride)
         sc = src[co:].reshape(-1)[: (8 * go.mb_h) * go.chroma_stride].reshape(8 * go.mb_h, go.chroma_stride)
-        for xy in np.nonzero(kind[f])[0]:
+        for xy in np.nonzero(kind[f] == 1)[0]:
             mx, my = xy % go.mb_w, xy // go.mb_w
             blk = sl[16 * my: 16 * my + 16, 16 * mx: 16 * mx + 16]
             mode = rng.randint(4)
@@ -242,7 +249,7 @@ def test_residual_frames_typed_inter_and_i16x16(pkg, ctx, w, h, nf, qp, intra_sh
     rec_o = []
     for f in range(nf):
         po = preds[f].copy()
-        o.xo_residual_frame_typed(C.byref(go), ptr(host[f + 1]), ptr(po), qp, ptr(kind[f]), ptr(lv_o[f], i16p),
+        o.xo_residual_frame_typed(C.byref(go), ptr(host[f + 1]), ptr(po), qp, ptr(kind[f]), ptr(modes[f]), ptr(lv_o[f], i16p),
                                   ptr(dc_o[f], i16p), ptr(nz_o[f]), ptr(cbp_o[f], i16p))
         rec_o.append(po)
     pred = torch.from_numpy(np.concatenate(preds)).cuda()
@@ -252,7 +259,7 @@ def test_residual_frames_typed_inter_and_i16x16(pkg, ctx, w, h, nf, qp, intra_sh
     nz = torch.full((nf, n, pkg.RES_NNZ_PER_MB), 77, dtype=torch.uint8, device="cuda")
     cbp = torch.full((nf, n), -1, dtype=torch.int16, device="cuda")
     torch.cuda.synchronize()
-    ctx.residual_frames_typed(g, dev[g.slot_bytes:], pred, nf, qp, d_kind, lv, dc, nz, cbp)
+    ctx.residual_frames_typed(g, dev[g.slot_bytes:], pred, nf, qp, d_kind, lv, dc, nz, cbp, i4_modes=torch.from_numpy(modes).cuda())
     ctx.sync()
     got = pred.cpu().numpy().reshape(nf, -1)
     for f in range(nf):
@@ -262,7 +269,8 @@ def test_residual_frames_typed_inter_and_i16x16(pkg, ctx, w, h, nf, qp, intra_sh
         assert np.array_equal(lv[f].cpu().numpy(), lv_o[f]), f"frame {f}: levels"
         assert np.array_equal(dc[f].cpu().numpy(), dc_o[f]), f"frame {f}: luma DC levels"
         assert np.array_equal(got[f], rec_o[f]), f"frame {f}: reconstruction"
+    assert ((cbp_o & 15)[(kind & 3) == 2] != 0).any(), "no coded I4x4 macroblock"
     if intra_share > 0:
-        i16 = kind.astype(bool)
+        i16 = kind == 1
         assert (nz_o[..., 24][i16] != 0).any(), "no I16x16 macroblock with a coded DC block"
         assert ((cbp_o & 15)[i16] == 15).any() and ((cbp_o & 15)[i16] == 0).any(), "I16x16: both luma cbp cases wanted"

@@ -390,10 +390,13 @@ class Context:
                                                 int(qp), _dp(levels), _dp(nnz), _dp(cbp), None),
               "x264dsp_residual_frames_dev")
 
-    def residual_frames_typed(self, g, fenc_slots, pred_slots, n_frames, qp, mb_kind, levels, luma_dc, nnz, cbp):
-        """mb_kind: uint8 per macroblock, 0 = inter (P slice), 1 = I16x16 (I slice); luma_dc: int16[n][mb][16] or None"""
+    def residual_frames_typed(self, g, fenc_slots, pred_slots, n_frames, qp, mb_kind, levels, luma_dc, nnz, cbp,
+                              i4_modes=None):
+        """mb_kind: uint8 per macroblock, 0 = inter (P slice), 1 = I16x16, 2 (6) = I4x4 with i4_modes uint8[n][mb][16]
+        (I slice); luma_dc: int16[n][mb][16] or None"""
         check(lib().x264dsp_residual_frames_typed_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
-                                                      int(qp), _dp(mb_kind) if mb_kind is not None else None, _dp(levels),
+                                                      int(qp), _dp(mb_kind) if mb_kind is not None else None,
+                                                      _dp(i4_modes) if i4_modes is not None else None, _dp(levels),
                                                       _dp(luma_dc) if luma_dc is not None else None, _dp(nnz), _dp(cbp), None),
               "x264dsp_residual_frames_typed_dev")
 

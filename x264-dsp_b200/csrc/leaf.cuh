@@ -348,3 +348,65 @@ __device__ __forceinline__ void xd_chroma_line( int s[4], int alpha, int beta, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// intra prediction modes, numbered like the reference's I_PRED_4x4_* (common/predict.h:44-59)
+enum { PR_V = 0, PR_H, PR_DC, PR_DDL, PR_DDR, PR_VR, PR_HD, PR_VL, PR_HU, PR_DC_LEFT, PR_DC_TOP, PR_DC_128, PR_PLANE };
+
+#define XS_F1( a, b ) ( ( ( a ) + ( b ) + 1 ) >> 1 )
+#define XS_F2( a, b, c ) ( ( ( a ) + 2 * ( b ) + ( c ) + 2 ) >> 2 )
+
+// one predicted pixel of a 4x4 block (common/predict.c:330-470).  e[0..3] = l3..l0, e[4] = lt,
+// e[5..12] = t0..t7.
+__device__ __forceinline__ int xd_pred4x4_px( int mode, int x, int y, const int e[13] )
+{
+    const int *t = e + 5;
+#define L( k ) e[3 - ( k )]
+    switch( mode )
+    {
+    case PR_V: return t[x];
+    case PR_H: return L( y );
+    case PR_DC: return ( L( 0 ) + L( 1 ) + L( 2 ) + L( 3 ) + t[0] + t[1] + t[2] + t[3] + 4 ) >> 3;
+    case PR_DC_LEFT: return ( L( 0 ) + L( 1 ) + L( 2 ) + L( 3 ) + 2 ) >> 2;          // predict.c:334-343
+    case PR_DC_TOP: return ( t[0] + t[1] + t[2] + t[3] + 2 ) >> 2;
+    case PR_DC_128: return 128;
+    case PR_DDL:
+        return ( x == 3 && y == 3 ) ? XS_F2( t[6], t[7], t[7] ) : XS_F2( t[x + y], t[x + y + 1], t[x + y + 2] );
+    case PR_DDR:
+    {
+        const int i = 4 + x - y;
+        return XS_F2( e[i - 1], e[i], e[i + 1] );
+    }
+    case PR_VR:
+    {
+        const int z = 2 * x - y, i = 4 + x - ( y >> 1 );
+        if( z >= 0 )
+            return ( z & 1 ) ? XS_F2( e[i - 1], e[i], e[i + 1] ) : XS_F1( e[i], e[i + 1] );
+        if( z == -1 )
+            return XS_F2( e[3], e[4], e[5] );
+        return XS_F2( e[4 - y], e[5 - y], e[6 - y] );
+    }
+    case PR_HD:
+    {
+        const int z = 2 * y - x, k = y - ( x >> 1 );
+        if( z >= -1 )
+            return ( z & 1 ) ? XS_F2( e[5 - k], e[4 - k], e[3 - k] ) : XS_F1( e[4 - k], e[3 - k] );
+        return XS_F2( e[4 + x], e[3 + x], e[2 + x] );
+    }
+    case PR_VL:
+    {
+        const int i = x + ( y >> 1 );
+        return ( y & 1 ) ? XS_F2( t[i], t[i + 1], t[i + 2] ) : XS_F1( t[i], t[i + 1] );
+    }
+    default: // PR_HU
+    {
+        const int z = x + 2 * y, k = y + ( x >> 1 );
+        if( z > 5 )
+            return L( 3 );
+        if( z == 5 )
+            return XS_F2( L( 2 ), L( 3 ), L( 3 ) );
+        return ( z & 1 ) ? XS_F2( L( k ), L( k + 1 ), L( k + 2 ) ) : XS_F1( L( k ), L( k + 1 ) );
+    }
+    }
+#undef L
+}
+

@@ -123,15 +123,20 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     levels += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_LEVELS_PER_MB;
     nnz_out += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_NNZ_PER_MB;
     cbp_out += blockIdx.y * (size_t)g.mb_count;
-    bool intra = false;
+    bool intra = false, i16 = false, i4 = false;
     if( TYPED )
     {
         if( mb_kind )
-            intra = mb_kind[blockIdx.y * (size_t)g.mb_count + mb] != 0;
+        {
+            const int kind = mb_kind[blockIdx.y * (size_t)g.mb_count + mb] & 3;
+            intra = kind != 0;
+            i16 = kind == 1;
+            i4 = kind == 2;         // chroma here (intra rules); luma, its levels / nnz / cbp bits in xd_intra4_kernel
+        }
         if( luma_dc )
         {
             luma_dc += ( blockIdx.y * (size_t)g.mb_count + mb ) * 16;
-            if( !intra && lane < 2 )
+            if( !i16 && lane < 2 )
                 ( (uint4 *)luma_dc )[lane] = make_uint4( 0u, 0u, 0u, 0u );
         }
     }
@@ -226,7 +231,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
             lv[i] = 0;
     }
     int16_t *mb_levels = levels + (size_t)mb * X264DSP_RES_LEVELS_PER_MB;
-    if( is_luma )
+    if( is_luma && !i4 )
         xd_store_levels( mb_levels + lane * 16, lv );
     else if( is_chroma )
         xd_store_levels( mb_levels + 264 + ( lane - 16 ) * 16, lv );
@@ -244,7 +249,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     bool keep8 = score8 >= 4 && mb_score >= 6;
     int nnz_flag = 0;
     int nz_luma_dc = 0;
-    if( TYPED && intra )
+    if( TYPED && i16 )
     {
         // no decimation in an I slice: all sixteen blocks are coded as soon as one of them has a coefficient
         const bool any_ac = ( __ballot_sync( 0xffffffffu, is_luma && nz ) ) != 0;
@@ -306,13 +311,13 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
                 xd_add4x4_dc( p, my_dc );
         }
     }
-    else if( is_luma )
+    else if( is_luma && !i4 )
     {
         nnz_flag = keep8 ? nz : 0;
         if( keep8 )
             xd_add4x4_idct( p, dct );
     }
-    const unsigned keep_mask = __ballot_sync( 0xffffffffu, is_luma && keep8 );
+    const unsigned keep_mask = __ballot_sync( 0xffffffffu, is_luma && keep8 && !i4 );
     const int cbp_luma = ( ( keep_mask >> 0 ) & 1 ) | ( ( ( keep_mask >> 4 ) & 1 ) << 1 )
                        | ( ( ( keep_mask >> 8 ) & 1 ) << 2 ) | ( ( ( keep_mask >> 12 ) & 1 ) << 3 );
 
@@ -388,7 +393,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     }
 
     // ---- stores: reconstruction, flags
-    if( is_luma )
+    if( is_luma && !i4 )
     {
 #pragma unroll
         for( int r = 0; r < 4; r++ )
@@ -415,7 +420,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     if( !early )
         cbp_chroma += dc_u | dc_v | cbp_chroma;                          // macroblock.c:303-304
     uint8_t *mb_nnz = nnz_out + (size_t)mb * X264DSP_RES_NNZ_PER_MB;
-    if( lane < 24 )
+    if( lane < 24 && !( i4 && lane < 16 ) )
         mb_nnz[lane] = (uint8_t)nnz_flag;
     if( lane == 24 )
         mb_nnz[24] = (uint8_t)nz_luma_dc;                                // luma DC: I16x16 only
@@ -425,6 +430,110 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
         mb_nnz[26] = (uint8_t)dc_v;
     if( lane == 0 )
         cbp_out[mb] = (int16_t)( ( cbp_chroma << 4 ) | cbp_luma | ( nz_luma_dc << 8 ) | ( dc_u << 9 ) | ( dc_v << 10 ) );
+}
+
+// ---------------------------------------------------------------------------------------------
+// Luma of I4x4 macroblocks (encoder/macroblock.c:355-377, encoder/macroblock.h:37-61): sixteen blocks in coding order,
+// each predicted from the reconstruction of the blocks before it (and of the neighbouring macroblocks, which must be
+// final in pred: the caller's launch order guarantees it), transformed, quantised with the CQM_4IY tables and
+// reconstructed before the next one starts.  One warp per macroblock, the macroblock and its neighbourhood (row -1 from
+// column -1 to 19, column -1) in a shared-memory tile; lane = pixel for the prediction, the 4x4 transform pipeline runs
+// on every lane alike (the chain is serial by nature; an I slice comes once per keyint).  Runs after
+// xd_residual_kernel<true>, which has done the chroma and written the chroma bits of cbp.
+#define I4_PITCH 32
+__global__ void __launch_bounds__( 128 )
+xd_intra4_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t *__restrict__ pred, xd_res_tables T,
+                  const uint8_t *__restrict__ mb_kind, const uint8_t *__restrict__ i4_modes,
+                  int16_t *__restrict__ levels, uint8_t *__restrict__ nnz_out, int16_t *__restrict__ cbp_out )
+{
+    __shared__ __align__( 16 ) uint8_t s_tile[4][17 * I4_PITCH];
+    const int lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * 4 + ( threadIdx.x >> 5 );
+    if( mb >= g.mb_count )
+        return;
+    const size_t fmb = blockIdx.y * (size_t)g.mb_count + mb;
+    const int kind = mb_kind[fmb];
+    if( ( kind & 3 ) != 2 )
+        return;
+    const bool replicate5 = ( kind & 4 ) != 0;
+    fenc += blockIdx.y * (size_t)g.slot_bytes;
+    pred += blockIdx.y * (size_t)g.slot_bytes;
+    const int mb_x = mb % g.mb_w, mb_y = mb / g.mb_w;
+    const int ls = g.luma_stride;
+    const int64_t org = g.luma_origin + (int64_t)( mb_y << 4 ) * ls + ( mb_x << 4 );
+    uint8_t *tile = s_tile[threadIdx.x >> 5] + I4_PITCH + 8;          // macroblock origin: tile row 1, byte 8
+    if( lane < 21 )
+        tile[-I4_PITCH - 1 + lane] = pred[org - ls - 1 + lane];
+    if( lane < 16 )
+        tile[lane * I4_PITCH - 1] = pred[org + (int64_t)lane * ls - 1];
+    __syncwarp();
+    const uint8_t *modes = i4_modes + fmb * 16;
+    int16_t *mb_levels = levels + fmb * X264DSP_RES_LEVELS_PER_MB;
+    int cbp_luma = 0;
+    uint32_t nz_bits = 0;
+    for( int idx = 0; idx < 16; idx++ )
+    {
+        const int x = ( ( idx & 1 ) + ( ( idx >> 2 ) & 1 ) * 2 ) * 4, y = ( ( ( idx >> 1 ) & 1 ) + ( ( idx >> 3 ) & 1 ) * 2 ) * 4;
+        uint8_t *dst = tile + y * I4_PITCH + x;
+        // missing top-right samples: the block's top-right block is coded later (or lies in a macroblock that is not there)
+        if( idx == 3 || idx == 7 || idx == 11 || idx == 13 || idx == 15 || ( idx == 5 && replicate5 ) )
+        {
+            const uint8_t v = dst[3 - I4_PITCH];
+            __syncwarp();
+            if( lane < 4 )
+                dst[4 - I4_PITCH + lane] = v;
+            __syncwarp();
+        }
+        int e[13];
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+            e[3 - k] = dst[k * I4_PITCH - 1];
+        e[4] = dst[-I4_PITCH - 1];
+#pragma unroll
+        for( int k = 0; k < 8; k++ )
+            e[5 + k] = dst[-I4_PITCH + k];
+        const int mode = modes[idx];
+        __syncwarp();
+        if( lane < 16 )
+            dst[( lane >> 2 ) * I4_PITCH + ( lane & 3 )] = (uint8_t)xd_pred4x4_px( mode, lane & 3, lane >> 2, e );
+        __syncwarp();
+        uint32_t f[4], p[4];
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            f[r] = __ldg( (const uint32_t *)( fenc + org + (int64_t)( y + r ) * ls + x ) );
+            p[r] = *(const uint32_t *)( dst + r * I4_PITCH );
+        }
+        int dct[16], lv[16];
+        xd_sub4x4_dct( dct, f, p );
+        const int nz = xd_quant_4x4( dct, T.luma_i );
+        xd_zigzag( lv, dct );
+        if( nz )
+        {
+            xd_dequant_4x4( dct, T.luma_i );
+            xd_add4x4_idct( p, dct );
+            cbp_luma |= 1 << ( idx >> 2 );
+            nz_bits |= 1u << idx;
+        }
+        __syncwarp();
+        if( lane == 0 )
+        {
+            xd_store_levels( mb_levels + idx * 16, lv );
+#pragma unroll
+            for( int r = 0; r < 4; r++ )
+                *(uint32_t *)( dst + r * I4_PITCH ) = p[r];
+        }
+        __syncwarp();
+    }
+    // the reconstructed macroblock, its flags, the luma bits of cbp
+    if( lane < 16 )
+    {
+        const uint2 r0 = *(const uint2 *)( tile + lane * I4_PITCH ), r1 = *(const uint2 *)( tile + lane * I4_PITCH + 8 );
+        *(uint4 *)( pred + org + (int64_t)lane * ls ) = make_uint4( r0.x, r0.y, r1.x, r1.y );
+        nnz_out[fmb * X264DSP_RES_NNZ_PER_MB + lane] = (uint8_t)( ( nz_bits >> lane ) & 1u );
+    }
+    if( lane == 0 )
+        cbp_out[fmb] = (int16_t)( ( cbp_out[fmb] & ~0x10F ) | cbp_luma );
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -454,8 +563,8 @@ static void xd_fill_qparams( xd_qparams *q, int qp, int b_inter = 1 )
 }
 
 static int xd_residual_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot,
-                               int n_frames, int qp, const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc,
-                               uint8_t *nnz, int16_t *cbp, bool typed, void *stream )
+                               int n_frames, int qp, const uint8_t *mb_kind, const uint8_t *i4_modes, int16_t *levels,
+                               int16_t *luma_dc, uint8_t *nnz, int16_t *cbp, bool typed, void *stream )
 {
     if( !ctx || !g || !fenc_slot || !pred_slot || !levels || !nnz || !cbp || qp < 0 || qp > 51 || n_frames <= 0
         || n_frames > 65535 )
@@ -488,7 +597,14 @@ static int xd_residual_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, cons
     const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_RESIDUAL, s );
     if( typed )
+    {
         xd_residual_kernel<true><<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, levels, nnz, cbp, mb_kind, luma_dc );
+        if( mb_kind && i4_modes )
+        {
+            xd_intra4_kernel<<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, mb_kind, i4_modes, levels, nnz, cbp );
+            ctx->launches++;
+        }
+    }
     else
         xd_residual_kernel<false><<<grid, 128, 0, s>>>( *g, fenc_slot, pred_slot, T, levels, nnz, cbp, NULL, NULL );
     xd_prof_end( ctx, XD_PROF_RESIDUAL, pslot, s );
@@ -501,15 +617,15 @@ extern "C" int x264dsp_residual_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_ge
                                              const uint8_t *fenc_slot, uint8_t *pred_slot, int n_frames, int qp,
                                              int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream )
 {
-    return xd_residual_launch( ctx, g, fenc_slot, pred_slot, n_frames, qp, NULL, levels, NULL, nnz, cbp, false, stream );
+    return xd_residual_launch( ctx, g, fenc_slot, pred_slot, n_frames, qp, NULL, NULL, levels, NULL, nnz, cbp, false, stream );
 }
 
 extern "C" int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
                                                    const uint8_t *fenc_slot, uint8_t *pred_slot, int n_frames, int qp,
-                                                   const uint8_t *mb_kind, int16_t *levels, int16_t *luma_dc,
-                                                   uint8_t *nnz, int16_t *cbp, void *stream )
+                                                   const uint8_t *mb_kind, const uint8_t *i4_modes, int16_t *levels,
+                                                   int16_t *luma_dc, uint8_t *nnz, int16_t *cbp, void *stream )
 {
-    return xd_residual_launch( ctx, g, fenc_slot, pred_slot, n_frames, qp, mb_kind, levels, luma_dc, nnz, cbp, true, stream );
+    return xd_residual_launch( ctx, g, fenc_slot, pred_slot, n_frames, qp, mb_kind, i4_modes, levels, luma_dc, nnz, cbp, true, stream );
 }
 
 extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
