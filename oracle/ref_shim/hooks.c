@@ -249,7 +249,8 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
  *   cbp     -> h->mb.i_cbp_luma, h->mb.i_cbp_chroma, h->mb.cbp[mb_xy] (CABAC: with the DC flags in bits 8..10)
  * followed by the forced-P_SKIP rule of macroblock.c:465-485.  Buffer shapes are xref_encode_inter_mb's. */
 typedef int (*xref_mbenc_cb)( void *h, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y, uint8_t *fdec_c,
-                              int qp, int kind /* 0 inter, 1 I16x16 */, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int *cbp );
+                              int qp, int kind /* 0 inter, 1 I16x16, 2 / 6 I4x4 (mb_kind of the library) */,
+                              const uint8_t *i4_modes, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int *cbp );
 xref_mbenc_cb xref_hook_mbenc = NULL;
 int xref_hook_mbenc_calls = 0;
 
@@ -270,8 +271,14 @@ void x264_macroblock_encode( x264_t *h )
     /* I16x16 macroblocks of I slices (x264_mb_encode_i16x16 + intra chroma, no decimation): the reference's own
      * predictors fill fdec, the device does the rest (x264dsp_residual_frames_typed_dev, kind 1) */
     const int i16 = h->mb.i_type == I_16x16 && h->sh.i_type == SLICE_TYPE_I && !h->mb.b_dct_decimate;
+    /* I4x4 macroblocks: fdec_buf holds the reconstructed neighbours the sixteen predictions start from; the modes go
+     * over in coding order.  (h->mb.i_skip_intra only says that analysis has coded the blocks already -- the same
+     * deterministic steps, so coding all sixteen again gives what the reference's shortcut copies back.) */
+    const int i4 = h->mb.i_type == I_4x4 && h->sh.i_type == SLICE_TYPE_I && !h->mb.b_dct_decimate;
+    uint8_t i4_modes[16];
+    int kind = i16;
     const int inter = !IS_INTRA( h->mb.i_type ) && h->mb.i_type != P_SKIP && h->sh.i_type == SLICE_TYPE_P && h->mb.b_dct_decimate;
-    if( !xref_hook_mbenc || !( i16 || inter ) || h->mb.b_noise_reduction || h->mb.b_transform_8x8 || h->mb.b_lossless
+    if( !xref_hook_mbenc || !( i16 || i4 || inter ) || h->mb.b_noise_reduction || h->mb.b_transform_8x8 || h->mb.b_lossless
         || h->mb.i_chroma_qp != h->chroma_qp_table[h->mb.i_qp] )
     {
         xref_orig_macroblock_encode( h );
@@ -279,18 +286,25 @@ void x264_macroblock_encode( x264_t *h )
     }
     h->mb.i_cbp_luma = 0;
     h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = 0;
-    if( i16 )
+    if( i16 || i4 )
     {
-        h->predict_16x16[h->mb.i_intra16x16_pred_mode]( h->mb.pic.p_fdec[0] );
+        if( i16 )
+            h->predict_16x16[h->mb.i_intra16x16_pred_mode]( h->mb.pic.p_fdec[0] );
         h->predict_chroma[h->mb.i_chroma_pred_mode]( h->mb.pic.p_fdec[1] );
         h->predict_chroma[h->mb.i_chroma_pred_mode]( h->mb.pic.p_fdec[2] );
+    }
+    if( i4 )
+    {
+        for( i = 0; i < 16; i++ )
+            i4_modes[i] = (uint8_t)h->mb.cache.intra4x4_pred_mode[x264_scan8[i]];
+        kind = 2 + ( ( h->mb.i_neighbour4[5] & (MB_TOPRIGHT|MB_TOP) ) == MB_TOP ? 4 : 0 );
     }
     else if( !h->mb.b_skip_mc )
         x264_mb_mc( h );
     memset( levels, 0, sizeof(levels) );
     memset( luma_dc, 0, sizeof(luma_dc) );
     if( xref_hook_mbenc( h, h->mb.pic.p_fenc[0], h->mb.pic.p_fenc[1], h->mb.pic.p_fdec[0], h->mb.pic.p_fdec[1],
-                         h->mb.i_qp, i16, levels, luma_dc, nnz, &cbp ) )
+                         h->mb.i_qp, kind, i4_modes, levels, luma_dc, nnz, &cbp ) )
     {
         /* declined: the prediction is already in fdec; an intra macroblock's predictors simply run again */
         if( inter )

@@ -9,7 +9,7 @@ of its hot-path drivers served by libx264dsp_b200.so --
                                                 -> x264dsp_lookahead_frame_cost_dev
   x264_me_search_ref (every partition search of the main encode, last cases)
                                                 -> x264dsp_me_search_batch_dev on frames kept resident on the device
-  x264_macroblock_encode (every inter macroblock of the P slices and every I16x16 macroblock of the I slices, last
+  x264_macroblock_encode (every inter macroblock of the P slices and every I16x16 / I4x4 macroblock of the I slices, last
   two cases: DCT, quant, zig-zag, dequant, decimation, luma / chroma DC, IDCT; levels / nnz / cbp handed to the
   reference's CABAC writer)                     -> x264dsp_residual_frames_typed_dev
 
@@ -33,7 +33,7 @@ FDEC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_voi
                       C.c_int, C.c_int, C.c_int)
 ME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
 MBENC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
+                       C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
 
 
 @pytest.mark.parametrize("w,h,n,cut,me,subme,psub,inloop,mehook,mbenc", [
@@ -156,7 +156,8 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
     d_cbp = torch.zeros(1, dtype=torch.int16, device="cuda")
     d_dc = torch.zeros(16, dtype=torch.int16, device="cuda")
     d_kind = torch.zeros(1, dtype=torch.uint8, device="cuda")
-    mbenc_calls = [0, 0]                  # inter, I16x16
+    d_modes = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    mbenc_calls = [0, 0, 0]               # inter, I16x16, I4x4
 
     def mb_planes(buf):
         luma = buf[g1.luma_origin:][: 16 * g1.luma_stride].reshape(16, g1.luma_stride)[:, :16]
@@ -165,7 +166,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         return luma, chroma
 
     @MBENC_CB
-    def mbenc_cb(hv, fenc_y, fenc_c, fdec_y, fdec_c, qp, kind, levels, luma_dc, nnz, cbp):
+    def mbenc_cb(hv, fenc_y, fenc_c, fdec_y, fdec_c, qp, kind, i4_modes, levels, luma_dc, nnz, cbp):
         fy = host_view(fenc_y, 16 * 16).reshape(16, 16)
         fc = host_view(fenc_c, 8 * 16).reshape(8, 16)              # U at +0, V at +8
         dy = host_view(fdec_y, 16 * 32).reshape(16, 32)
@@ -175,11 +176,20 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             luma[:] = y_
             chroma[:, 0::2] = u_
             chroma[:, 1::2] = v_
+        if kind & 2:
+            # the reconstructed neighbourhood fdec_buf holds around the macroblock goes into the slot's padding:
+            # the row above from column -1 to 19 and the column to the left
+            nbh = host_view(fdec_y - 33, 17 * 32 + 1)
+            lo = g1.luma_origin
+            mb_stage[1][lo - g1.luma_stride - 1: lo - g1.luma_stride + 20] = nbh[:21]
+            for r in range(16):
+                mb_stage[1][lo + r * g1.luma_stride - 1] = nbh[33 + r * 32 - 1]
+            d_modes.copy_(torch.from_numpy(host_view(i4_modes, 16).copy()))
         mb_slots.copy_(torch.from_numpy(mb_stage.reshape(-1)))
         d_kind.fill_(kind)
         torch.cuda.synchronize()
         ctx.residual_frames_typed(g1, mb_slots[: g1.slot_bytes], mb_slots[g1.slot_bytes:], 1, qp, d_kind, d_lv, d_dc,
-                                  d_nz, d_cbp)
+                                  d_nz, d_cbp, i4_modes=d_modes)
         ctx.sync()
         rec = mb_slots[g1.slot_bytes:].cpu().numpy()
         luma, chroma = mb_planes(rec)
@@ -190,7 +200,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         host_view(nnz, pkg.RES_NNZ_PER_MB)[:] = d_nz.cpu().numpy()
         host_view(luma_dc, 32)[:] = d_dc.cpu().numpy().view(np.uint8)
         cbp[0] = int(d_cbp.cpu().numpy()[0])
-        mbenc_calls[kind] += 1
+        mbenc_calls[kind & 3] += 1
         return 0
 
     outs, calls = [], (C.c_int * 3)()
@@ -228,6 +238,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             if mbenc:
                 assert mbenc_calls[0] >= g.mb_count, f"only {mbenc_calls[0]} inter macroblocks were coded on the device"
                 assert mbenc_calls[1] > 0, "no I16x16 macroblock of the I frames was coded on the device"
+                assert mbenc_calls[2] > 0, "no I4x4 macroblock of the I frames was coded on the device"
             if inloop:
                 assert deblocked[0] >= n - 1, f"deblocking ran on the device for {deblocked[0]} of {n} frames"
     assert outs[0].size == outs[1].size and np.array_equal(outs[0], outs[1]), \
