@@ -73,6 +73,38 @@ def main():
     G["i16_recon_y"], G["i16_recon_c"] = ry[..., :16], rc[..., :24]
     G["i16_levels"], G["i16_luma_dc"], G["i16_nnz"], G["i16_cbp"] = lv, dc, nz, cbp
 
+    # ------------------------------------------------------------ I4x4 macroblocks, 48 per QP, each with its own neighbourhood
+    lib.xref_encode_intra4_mb.restype = C.c_int
+    r4 = np.random.RandomState(4444)
+    nbh = np.zeros((len(RQ), NMB, 17, 32), np.uint8)          # row 0 = the row above, origin (1, 8)
+    f4y, f4c = np.zeros((len(RQ), NMB, 16, 16), np.uint8), np.zeros((len(RQ), NMB, 8, 16), np.uint8)
+    p4c, r4c = np.zeros((len(RQ), NMB, 8, 32), np.uint8), np.zeros((len(RQ), NMB, 8, 32), np.uint8)
+    r4y = np.zeros((len(RQ), NMB, 16, 16), np.uint8)
+    m4, rep = np.zeros((len(RQ), NMB, 16), np.uint8), np.zeros((len(RQ), NMB), np.uint8)
+    l4, n4, c4 = np.zeros((len(RQ), NMB, 392), np.int16), np.zeros((len(RQ), NMB, 27), np.uint8), np.zeros((len(RQ), NMB), np.int32)
+    for qi, qp in enumerate(RQ):
+        for t in range(NMB):
+            nb = r4.randint(0, 256, (17, 32)).astype(np.uint8)
+            if t % 4 == 0:
+                nb[:] = r4.randint(40, 200)
+            base = r4.randint(0, 256)
+            f4y[qi, t] = (r4.randint(0, 256, (16, 16)) if t % 3 == 0 else
+                          np.clip(base + r4.randint(-30, 31, (16, 16)) + np.arange(16)[None, :] * r4.randint(-3, 4), 0, 255))
+            p4c[qi, t, :, :8], p4c[qi, t, :, 16:24] = r4.randint(20, 236), r4.randint(20, 236)
+            f4c[qi, t, :, :8] = np.clip(p4c[qi, t, :, :8].astype(int) + r4.randint(-9, 10, (8, 8)), 0, 255)
+            f4c[qi, t, :, 8:] = np.clip(p4c[qi, t, :, 16:24].astype(int) + r4.randint(-9, 10, (8, 8)), 0, 255)
+            m4[qi, t] = r4.randint(0, 12, 16)
+            rep[qi, t] = t % 2
+            nbh[qi, t] = nb
+            y1, c1 = nb.copy(), p4c[qi, t].copy()
+            c4[qi, t] = lib.xref_encode_intra4_mb(enc.h, ptr(np.ascontiguousarray(f4y[qi, t])), ptr(np.ascontiguousarray(f4c[qi, t])),
+                                                  C.cast(y1.ctypes.data + 32 + 8, C.c_void_p), ptr(c1), qp,
+                                                  ptr(np.ascontiguousarray(m4[qi, t])), int(rep[qi, t]), ptr(l4[qi, t], i16p), ptr(n4[qi, t]))
+            r4y[qi, t], r4c[qi, t] = y1[1:, 8:24], c1
+    G["i4_nbh"], G["i4_fenc_y"], G["i4_fenc_c"], G["i4_pred_c"] = nbh, f4y, f4c, p4c[..., :24]
+    G["i4_modes"], G["i4_replicate5"] = m4, rep
+    G["i4_recon_y"], G["i4_recon_c"], G["i4_levels"], G["i4_nnz"], G["i4_cbp"] = r4y, r4c[..., :24], l4, n4, c4
+
     # ------------------------------------------------------------ the 26 predictors on 10 neighbourhoods each
     tabs = [(PRED_T * 7)(), (PRED_T * 7)(), (PRED_T * 12)()]
     lib.x264_predict_16x16_init(0, tabs[0])

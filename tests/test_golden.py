@@ -701,3 +701,96 @@ def test_gpu_predict_tables_golden(GI, pkg):
                 b = GI["pred_src"][t].copy()
                 tabs[ti][mode](C.cast(b.ctypes.data + 8 * 32 + 8, C.c_void_p))
                 assert np.array_equal(b[8:8 + size, 8:8 + size], want[mode, t]), f"{name} mode {mode} case {t}"
+
+
+def check_intra4(GI, qi, t, cbp, nz, lv, ry, rc):
+    assert cbp == GI["i4_cbp"][qi, t], f"cbp qp#{qi} mb {t}: {cbp:#x} vs {int(GI['i4_cbp'][qi, t]):#x}"
+    want_nz = GI["i4_nnz"][qi, t]
+    assert np.array_equal(nz, want_nz), f"nnz qp#{qi} mb {t}"
+    assert np.array_equal(ry, GI["i4_recon_y"][qi, t]), f"luma recon qp#{qi} mb {t} modes {GI['i4_modes'][qi, t]}"
+    assert np.array_equal(rc[:, :8], GI["i4_recon_c"][qi, t][:, :8]) and np.array_equal(rc[:, 16:24], GI["i4_recon_c"][qi, t][:, 16:24])
+    want = GI["i4_levels"][qi, t]
+    for i in range(16):
+        if want_nz[i]:
+            assert np.array_equal(lv[i * 16:(i + 1) * 16], want[i * 16:(i + 1) * 16]), f"luma levels qp#{qi} mb {t} blk {i}"
+    for i in range(8):
+        if want_nz[16 + i]:
+            assert np.array_equal(lv[264 + i * 16: 280 + i * 16], want[264 + i * 16: 280 + i * 16]), f"chroma ac {i}"
+
+
+def test_oracle_intra4_mb(GI):
+    o = cc.oracle()
+    o.xo_encode_intra4_mb.restype = C.c_int
+    for qi, qp in enumerate(GI["i16_qps"]):
+        for t in range(GI["i4_fenc_y"].shape[1]):
+            nb = GI["i4_nbh"][qi, t].copy()
+            c = np.zeros((8, 32), np.uint8)
+            c[:, :24] = GI["i4_pred_c"][qi, t]
+            lv, nz = np.zeros(392, np.int16), np.zeros(27, np.uint8)
+            cbp = o.xo_encode_intra4_mb(ptr(np.ascontiguousarray(GI["i4_fenc_y"][qi, t])), ptr(np.ascontiguousarray(GI["i4_fenc_c"][qi, t])),
+                                        C.cast(nb.ctypes.data + 32 + 8, C.c_void_p), ptr(c), int(qp),
+                                        ptr(np.ascontiguousarray(GI["i4_modes"][qi, t])), int(GI["i4_replicate5"][qi, t]),
+                                        ptr(lv, i16p), ptr(nz))
+            check_intra4(GI, qi, t, cbp, nz, lv, nb[1:, 8:24], c[:, :24])
+
+
+@pytest.mark.gpu
+def test_gpu_intra4_frame(GI, pkg, ctx):
+    """the 48 stored I4x4 macroblocks of each QP on the even-even lattice of a 256x192 frame, each with its stored
+    neighbourhood around it; the macroblocks in between are inter macroblocks with source == prediction (nothing
+    coded, reconstruction == prediction), so the neighbourhoods are what the I4x4 kernel finds"""
+    import torch
+    g = pkg.geometry(256, 192)
+    ls, cs = g.luma_stride, g.chroma_stride
+    n = GI["i4_fenc_y"].shape[1]
+    assert (g.mb_w // 2) * (g.mb_h // 2) == n
+    for qi, qp in enumerate(GI["i16_qps"]):
+        pred = np.zeros(g.slot_bytes, np.uint8)
+        kind = np.zeros(g.mb_count, np.uint8)
+        modes = np.zeros((g.mb_count, 16), np.uint8)
+        where = []
+        for t in range(n):
+            mx, my = 2 * (t % (g.mb_w // 2)), 2 * (t // (g.mb_w // 2))
+            where.append(my * g.mb_w + mx)
+            lo = g.luma_origin + my * 16 * ls + mx * 16
+            nb = GI["i4_nbh"][qi, t]
+            pred[lo - ls - 1: lo - ls + 20] = nb[0, 7:28]
+            for r in range(16):
+                pred[lo + r * ls - 1] = nb[1 + r, 7]
+            co = g.slot_chroma_off + g.chroma_origin + my * 8 * cs + mx * 16
+            for r in range(8):
+                pred[co + r * cs: co + r * cs + 16: 2] = GI["i4_pred_c"][qi, t][r, :8]
+                pred[co + r * cs + 1: co + r * cs + 16: 2] = GI["i4_pred_c"][qi, t][r, 16:24]
+            kind[where[-1]] = 2 + 4 * int(GI["i4_replicate5"][qi, t])
+            modes[where[-1]] = GI["i4_modes"][qi, t]
+        fenc = pred.copy()                                    # inter macroblocks: source == prediction
+        for t in range(n):
+            mx, my = 2 * (t % (g.mb_w // 2)), 2 * (t // (g.mb_w // 2))
+            lo = g.luma_origin + my * 16 * ls + mx * 16
+            for r in range(16):
+                fenc[lo + r * ls: lo + r * ls + 16] = GI["i4_fenc_y"][qi, t][r]
+            co = g.slot_chroma_off + g.chroma_origin + my * 8 * cs + mx * 16
+            for r in range(8):
+                fenc[co + r * cs: co + r * cs + 16: 2] = GI["i4_fenc_c"][qi, t][r, :8]
+                fenc[co + r * cs + 1: co + r * cs + 16: 2] = GI["i4_fenc_c"][qi, t][r, 8:]
+        d_fenc, d_pred = torch.from_numpy(fenc).cuda(), torch.from_numpy(pred).cuda()
+        lv = torch.zeros((g.mb_count, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda")
+        nz = torch.zeros((g.mb_count, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda")
+        cbp = torch.zeros(g.mb_count, dtype=torch.int16, device="cuda")
+        torch.cuda.synchronize()
+        ctx.residual_frames_typed(g, d_fenc, d_pred, 1, int(qp), torch.from_numpy(kind).cuda(), lv, None, nz, cbp,
+                                  i4_modes=torch.from_numpy(modes).cuda())
+        ctx.sync()
+        lv, nz, cbp, rec = lv.cpu().numpy(), nz.cpu().numpy(), cbp.cpu().numpy(), d_pred.cpu().numpy()
+        others = np.setdiff1d(np.arange(g.mb_count), where)
+        assert not cbp[others].any(), "the filler macroblocks must not code anything"
+        for t in range(n):
+            mx, my = 2 * (t % (g.mb_w // 2)), 2 * (t // (g.mb_w // 2))
+            lo = g.luma_origin + my * 16 * ls + mx * 16
+            ry = np.stack([rec[lo + r * ls: lo + r * ls + 16] for r in range(16)])
+            co = g.slot_chroma_off + g.chroma_origin + my * 8 * cs + mx * 16
+            rc = np.zeros((8, 24), np.uint8)
+            for r in range(8):
+                rc[r, :8] = rec[co + r * cs: co + r * cs + 16: 2]
+                rc[r, 16:24] = rec[co + r * cs + 1: co + r * cs + 16: 2]
+            check_intra4(GI, qi, t, int(cbp[where[t]]), nz[where[t]], lv[where[t]], ry, rc)
