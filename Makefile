@@ -3,6 +3,7 @@
 #   make oracle     -> oracle/_build/libx264dsp_oracle.so (CPU checker, test infrastructure)
 #   make ref        -> oracle/_ref/libx264ref.so          (unmodified reference, needs /root/reference)
 #   make sass       -> x264-dsp_b200/_build/*.sass        (cuobjdump -sass of every kernel)
+#   make examples   -> examples/_build/lookahead_host      (plain C host program on the C ABI, gcc only)
 
 NVCC     ?= /usr/local/cuda/bin/nvcc
 PKG      := x264-dsp_b200
@@ -37,11 +38,17 @@ oracle:
 ref:
 	$(MAKE) -C oracle ref
 
+examples: examples/_build/lookahead_host
+
+examples/_build/lookahead_host: examples/lookahead_host.c include/x264dsp_b200.h $(LIB)
+	@mkdir -p examples/_build
+	gcc -std=c99 -O2 -Wall -Werror -Iinclude $< -o $@ -L$(PKG) -l:libx264dsp_b200.so -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
+
 sass: $(LIB)
 	/usr/local/cuda/bin/cuobjdump -sass $(LIB) > $(OUT)/libx264dsp_b200.sass
 
 clean:
-	rm -rf $(OUT) $(LIB)
+	rm -rf $(OUT) $(LIB) examples/_build
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle ref sass clean
+.PHONY: all oracle ref sass clean examples
