@@ -575,6 +575,62 @@ int xref_encode_intra4_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_
     return h->mb.cbp[0];
 }
 
+/* x264_macroblock_probe_pskip (encoder/macroblock.c:492) on a caller-supplied P_SKIP prediction: the function's
+ * own motion compensation calls (h->mc.mc_luma / mc_chroma, plain data members of x264_t) are pointed at two stand-ins
+ * that deliver the stashed prediction, everything after that -- transforms, quantisation, decimation, the chroma
+ * SSD / DC / AC ladder -- is the reference's code.  Buffer shapes as in xref_encode_inter_mb.  Returns its result. */
+static const uint8_t *xref_stash_y, *xref_stash_c;
+static void xref_stash_mc_luma( pixel *dst, intptr_t i_dst, pixel **src, intptr_t i_src, int mvx, int mvy, int w, int ht,
+                                const x264_weight_t *weight )
+{
+    int y;
+    (void)src; (void)i_src; (void)mvx; (void)mvy; (void)weight;
+    for( y = 0; y < ht; y++ )
+        memcpy( dst + y*i_dst, xref_stash_y + y*32, w );
+}
+static void xref_stash_mc_chroma( pixel *dstu, pixel *dstv, intptr_t i_dst, pixel *src, intptr_t i_src, int mvx, int mvy,
+                                  int w, int ht )
+{
+    int y;
+    (void)src; (void)i_src; (void)mvx; (void)mvy;
+    for( y = 0; y < ht; y++ )
+    {
+        memcpy( dstu + y*i_dst, xref_stash_c + y*32, w );
+        memcpy( dstv + y*i_dst, xref_stash_c + y*32 + 16, w );
+    }
+}
+
+int xref_probe_pskip_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, const uint8_t *pred_y,
+                         const uint8_t *pred_c, int qp )
+{
+    x264_t *h = hv;
+    x264_mc_functions_t keep = h->mc;
+    static pixel dummy[64];
+    int y, r;
+    h->sh.i_type = SLICE_TYPE_P;
+    x264_macroblock_thread_init( h );
+    h->mb.b_noise_reduction = 0;
+    h->mb.i_qp = qp;
+    h->mb.i_chroma_qp = h->chroma_qp_table[qp];
+    h->mb.cache.pskip_mv[0] = 4;                   /* non-zero: the chroma prediction comes through mc_chroma */
+    h->mb.cache.pskip_mv[1] = 4;
+    h->mb.mv_min[0] = h->mb.mv_min[1] = -64;
+    h->mb.mv_max[0] = h->mb.mv_max[1] = 64;
+    for( y = 0; y < 6; y++ )
+        h->mb.pic.p_fref[0][0][y] = dummy;
+    for( y = 0; y < 16; y++ )
+        memcpy( h->mb.pic.p_fenc[0] + y*FENC_STRIDE, fenc_y + y*16, 16 );
+    for( y = 0; y < 8; y++ )
+        memcpy( h->mb.pic.p_fenc[1] + y*FENC_STRIDE, fenc_c + y*16, 16 );
+    xref_stash_y = pred_y;
+    xref_stash_c = pred_c;
+    h->mc.mc_luma = xref_stash_mc_luma;
+    h->mc.mc_chroma = xref_stash_mc_chroma;
+    r = x264_macroblock_probe_pskip( h );
+    h->mc = keep;
+    return r;
+}
+
 /* ------------------------------------------------------------------ timing helpers
  * (cpu_baseline / --impl reference): loops over the reference functions with the
  * input already in memory; CLOCK_MONOTONIC around the loop; returns seconds. */

@@ -222,6 +222,98 @@ static int encode_inter_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_
     return (cbp_chroma << 4) | cbp_luma | (o->nnz[24] << 8) | (o->nnz[25] << 9) | (o->nnz[26] << 10);
 }
 
+/* x264_macroblock_probe_pskip (encoder/macroblock.c:492-604) after its motion compensation: fdec holds the P_SKIP
+ * prediction (mc_luma / mc_chroma at the clipped pskip mv).  Returns 1 when the macroblock may be skipped: the luma
+ * decimate scores of all coded 4x4s stay below 6 and each chroma plane passes its SSD / DC / AC-decimate ladder. */
+static int probe_pskip_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, const pixel_t *fdec_y, const pixel_t *fdec_c, int qp )
+{
+    uint16_t mf[16], bias[16];
+    int i8, i4, ch, score = 0;
+    const int qpc = xo_chroma_qp( qp );
+    xo_quant_tables( 1, qp, mf, bias );
+    for( i8 = 0; i8 < 4; i8++ )                                               /* macroblock.c:510-534 */
+    {
+        coef_t dct[4][16], scan[16];
+        xo_sub8x8_dct( dct, fenc_y + ((i8 & 1) + (i8 >> 1) * FENC) * 8, fdec_y + ((i8 & 1) + (i8 >> 1) * FDEC) * 8 );
+        for( i4 = 0; i4 < 4; i4++ )
+        {
+            if( !xo_quant_4x4( dct[i4], mf, bias ) )
+                continue;
+            xo_zigzag_4x4( scan, dct[i4] );
+            score += xo_decimate_score16( scan );
+            if( score >= 6 )
+                return 0;
+        }
+    }
+    {
+        const int thresh = ( xo_lambda2( qpc ) + 32 ) >> 6;                   /* macroblock.c:536-600 */
+        xo_quant_tables( 1, qpc, mf, bias );
+        for( ch = 0; ch < 2; ch++ )
+        {
+            const pixel_t *src = fenc_c + 8*ch, *dst = fdec_c + 16*ch;
+            coef_t dc[4], dct[4][16], scan[16];
+            int ssd = xo_ssd( 3 /* PIXEL_8x8 */, dst, FDEC, src, FENC );
+            if( ssd < thresh )
+                continue;
+            xo_sub8x8_dct_dc( dc, src, dst );
+            if( xo_quant_2x2_dc( dc, mf[0] >> 1, bias[0] << 1 ) )
+                return 0;
+            if( ssd < (thresh << 2) )
+                continue;
+            xo_sub8x8_dct( dct, src, dst );
+            for( i4 = 0, score = 0; i4 < 4; i4++ )
+            {
+                dct[i4][0] = 0;
+                if( !xo_quant_4x4( dct[i4], mf, bias ) )
+                    continue;
+                xo_zigzag_4x4( scan, dct[i4] );
+                score += xo_decimate_score15( scan );
+                if( score >= 7 )
+                    return 0;
+            }
+        }
+    }
+    return 1;
+}
+
+int xo_probe_pskip_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, const pixel_t *fdec_y, const pixel_t *fdec_c, int qp )
+{
+    return probe_pskip_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp );
+}
+
+/* every macroblock of a frame: pred_slot holds the P_SKIP prediction of each macroblock (x264dsp_mc_frame_dev /
+ * xo_mc_frame at the pskip MVs); skip[xy] = 1 when x264_macroblock_probe_pskip would return 1 */
+void xo_probe_pskip_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *pred_slot, int qp, uint8_t *skip )
+{
+    const int ls = g->luma_stride, cs = g->chroma_stride;
+    int mb_x, mb_y, x, y;
+    for( mb_y = 0; mb_y < g->mb_h; mb_y++ )
+        for( mb_x = 0; mb_x < g->mb_w; mb_x++ )
+        {
+            pixel_t fenc_y[16*FENC], fenc_c[8*FENC], fdec_y[16*FDEC], fdec_c[8*FDEC];
+            const pixel_t *sy = fenc_slot + g->luma_origin + (ptrdiff_t)(mb_y << 4) * ls + (mb_x << 4);
+            const pixel_t *sc = fenc_slot + g->slot_chroma_off + g->chroma_origin + (ptrdiff_t)(mb_y << 3) * cs + (mb_x << 4);
+            const pixel_t *py = pred_slot + g->luma_origin + (ptrdiff_t)(mb_y << 4) * ls + (mb_x << 4);
+            const pixel_t *pc = pred_slot + g->slot_chroma_off + g->chroma_origin + (ptrdiff_t)(mb_y << 3) * cs + (mb_x << 4);
+            memset( fdec_y, 0, sizeof(fdec_y) );
+            memset( fdec_c, 0, sizeof(fdec_c) );
+            for( y = 0; y < 16; y++ )
+            {
+                memcpy( fenc_y + y*FENC, sy + (ptrdiff_t)y*ls, 16 );
+                memcpy( fdec_y + y*FDEC, py + (ptrdiff_t)y*ls, 16 );
+            }
+            for( y = 0; y < 8; y++ )
+                for( x = 0; x < 8; x++ )
+                {
+                    fenc_c[y*FENC + x]      = sc[(ptrdiff_t)y*cs + 2*x];
+                    fenc_c[y*FENC + 8 + x]  = sc[(ptrdiff_t)y*cs + 2*x + 1];
+                    fdec_c[y*FDEC + x]      = pc[(ptrdiff_t)y*cs + 2*x];
+                    fdec_c[y*FDEC + 16 + x] = pc[(ptrdiff_t)y*cs + 2*x + 1];
+                }
+            skip[mb_y * g->mb_w + mb_x] = (uint8_t)probe_pskip_mb( fenc_y, fenc_c, fdec_y, fdec_c, qp );
+        }
+}
+
 /* block_idx_xy_1d (common/macroblock.h): coding index of a luma 4x4 -> raster index x + 4 y */
 static const uint8_t blk_raster[16] = { 0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15 };
 

@@ -611,3 +611,37 @@ def test_residual_intra4_mb(enc, qp):
         for i in range(16):
             if n1[i]:
                 assert np.array_equal(l1[i * 16:(i + 1) * 16], l2[i * 16:(i + 1) * 16]), f"luma levels trial {trial} blk {i}"
+
+
+@pytest.mark.parametrize("qp", [12, 18, 22, 26, 32, 40, 51])
+def test_probe_pskip_mb(enc, qp):
+    """x264_macroblock_probe_pskip on supplied P_SKIP predictions (its motion compensation stubbed by the harness):
+    reference against oracle, around the decision thresholds"""
+    o = cc.oracle()
+    rng = np.random.RandomState(700 + qp)
+    o.xo_probe_pskip_mb.restype = C.c_int
+    enc.lib.xref_probe_pskip_mb.restype = C.c_int
+    seen = [0, 0]
+    for trial in range(600):
+        pred_y = rng.randint(0, 256, (16, 32)).astype(np.uint8)
+        pred_c = rng.randint(0, 256, (8, 32)).astype(np.uint8)
+        if trial % 3 == 0:
+            pred_y[:], pred_c[:] = rng.randint(30, 220), rng.randint(30, 220)
+        scale = max(1, (qp - 14) // 5)                       # the thresholds grow with the quantiser
+        amp = [0, 1, 2, 3, 5, 8, 14][trial % 7] * scale
+        camp = [0, 1, 2, 4, 9][trial % 5] * scale
+        fenc_y = np.clip(pred_y[:, :16].astype(int) + rng.randint(-amp, amp + 1, (16, 16)), 0, 255).astype(np.uint8)
+        if trial % 11 == 0:                                  # one hot 4x4 in an otherwise perfect prediction
+            fenc_y = pred_y[:, :16].copy()
+            bx, by = rng.randint(4) * 4, rng.randint(4) * 4
+            fenc_y[by:by + 4, bx:bx + 4] = np.clip(fenc_y[by:by + 4, bx:bx + 4].astype(int) + rng.randint(-40, 41, (4, 4)), 0, 255)
+        fenc_c = np.zeros((8, 16), np.uint8)
+        fenc_c[:, :8] = np.clip(pred_c[:, :8].astype(int) + rng.randint(-camp, camp + 1, (8, 8)), 0, 255)
+        fenc_c[:, 8:] = np.clip(pred_c[:, 16:24].astype(int) + rng.randint(-camp, camp + 1, (8, 8)), 0, 255)
+        if trial % 13 == 0:
+            fenc_c[:, :8] = np.clip(pred_c[:, :8].astype(int) + rng.randint(-4, 5), 0, 255)       # DC shift only
+        r1 = enc.lib.xref_probe_pskip_mb(enc.h, ptr(fenc_y), ptr(fenc_c), ptr(pred_y), ptr(pred_c), qp)
+        r2 = o.xo_probe_pskip_mb(ptr(fenc_y), ptr(fenc_c), ptr(pred_y), ptr(pred_c), qp)
+        assert r1 == r2, f"trial {trial}: reference {r1} oracle {r2}"
+        seen[r1] += 1
+    assert seen[0] > 20 and seen[1] > 20, seen
