@@ -348,6 +348,14 @@ int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t 
                                        const uint8_t *mb_kind, const uint8_t *i4_modes, int16_t *levels,
                                        int16_t *luma_dc, uint8_t *nnz, int16_t *cbp, void *stream );
 
+/* x264_macroblock_probe_pskip (encoder/macroblock.c:492-604) for every macroblock of n_frames frames: pred_slots hold
+ * the P_SKIP prediction of each macroblock (x264dsp_mc_frames_dev at the clipped pskip MVs -- the function's own
+ * mc_luma / mc_chroma calls), fenc_slots the source; skip[frame][mb] = 1 when the reference would return 1 (luma
+ * decimate scores below 6 in total, each chroma plane passing its SSD / DC / AC-decimate ladder), else 0.  Nothing is
+ * modified: as in the reference, the prediction doubles as the reconstruction of a macroblock that ends up skipped. */
+int x264dsp_probe_pskip_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
+                                    const uint8_t *pred_slots, int n_frames, int qp, uint8_t *skip, void *stream );
+
 /* x264_mb_mc for P_L0 16x16 macroblocks (common/macroblock.c:8-28; mc_luma common/mc.c:216-239,
  * mc_chroma common/mc.c:290-323): builds the prediction frame from one quarter-pel MV per MB. */
 int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,

@@ -274,3 +274,34 @@ def test_residual_frames_typed_inter_i16x16_i4x4(pkg, ctx, w, h, nf, qp, intra_s
         i16 = kind == 1
         assert (nz_o[..., 24][i16] != 0).any(), "no I16x16 macroblock with a coded DC block"
         assert ((cbp_o & 15)[i16] == 15).any() and ((cbp_o & 15)[i16] == 0).any(), "I16x16: both luma cbp cases wanted"
+
+
+@pytest.mark.parametrize("w,h,nf,qp", [(352, 288, 3, 26), (1920, 1080, 2, 30), (200, 120, 3, 20), (352, 288, 2, 40), (352, 288, 2, 14)])
+def test_probe_pskip_frames(pkg, ctx, w, h, nf, qp):
+    """x264_macroblock_probe_pskip for whole frames: P_SKIP predictions from x264dsp_mc_frames_dev at MVs around the
+    clip's true pan (most macroblocks are skippable, the outliers are not), decision per macroblock against the oracle
+    (pinned to the reference's function, tests/test_oracle_vs_ref.py::test_probe_pskip_mb)"""
+    import torch
+    g, go, host, dev = _slots(pkg, ctx, w, h, nf + 1, True)
+    o = cc.oracle()
+    rng = np.random.RandomState(qp + nf + h)
+    n = g.mb_count
+    mv = (np.array([12, 8]) + rng.randint(-1, 2, (nf, n, 2))).astype(np.int16)
+    mv[rng.rand(nf, n) < 0.25] = rng.randint(-24, 25, 2)
+    want = np.zeros((nf, n), np.uint8)
+    for f in range(nf):
+        po = np.zeros(go.slot_bytes, np.uint8)
+        o.xo_mc_frame(C.byref(go), ptr(host[f]), ptr(mv[f], i16p), ptr(po))
+        o.xo_probe_pskip_frame(C.byref(go), ptr(host[f + 1]), ptr(po), qp, ptr(want[f]))
+    pred = torch.zeros(nf * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    skip = torch.full((nf, n), 7, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.mc_frames(g, dev[: nf * g.slot_bytes], nf, torch.from_numpy(mv).cuda(), pred)
+    before = pred.clone()
+    ctx.probe_pskip_frames(g, dev[g.slot_bytes:], pred, nf, qp, skip)
+    ctx.sync()
+    got = skip.cpu().numpy()
+    bad = np.argwhere(got != want)
+    assert len(bad) == 0, f"{len(bad)} decisions differ, first (frame, mb) {bad[:5].tolist()}: {got[tuple(bad[0])]} vs {want[tuple(bad[0])]}"
+    assert torch.equal(before, pred), "the probe must not modify the prediction"
+    assert not want.all() and (want.any() or qp < 26), f"one-sided test: {int(want.sum())} of {want.size} skippable"

@@ -400,6 +400,10 @@ class Context:
                                                       _dp(luma_dc) if luma_dc is not None else None, _dp(nnz), _dp(cbp), None),
               "x264dsp_residual_frames_typed_dev")
 
+    def probe_pskip_frames(self, g, fenc_slots, pred_slots, n_frames, qp, skip):
+        check(lib().x264dsp_probe_pskip_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
+                                                   int(qp), _dp(skip), None), "x264dsp_probe_pskip_frames_dev")
+
     def deblock_frame(self, g, slot, mb_type, partition, cbp, bs, qp, alpha_off=0, beta_off=0):
         check(lib().x264dsp_deblock_frame_dev(self._h, C.byref(g), _dp(slot), _dp(mb_type), _dp(partition),
                                               _dp(cbp), _dp(bs), int(qp), int(alpha_off), int(beta_off), None),

@@ -18,6 +18,7 @@
 // ballots.  HBM traffic per MB: 2 x 384 B in, 384 B recon + 784 B levels + 29 B flags out.
 #include "common.cuh"
 #include "leaf.cuh"
+#include <string.h>
 
 // ---------------------------------------------------------------------------------------------
 // motion compensation: 64 threads per macroblock (4 luma pixels + 1 UV pair each), 4 MBs per CTA
@@ -107,7 +108,10 @@ __device__ __forceinline__ void xd_hadamard_dc( int d[16], bool halve )
 
 // TYPED: mb_kind[mb] != 0 marks an I16x16 macroblock of an I slice (x264_mb_encode_i16x16, macroblock.c:72-162, and
 // x264_mb_encode_chroma with b_inter = 0, no decimation); the inter-only instantiation carries none of that code
-template<bool TYPED>
+// PROBE (third instantiation): x264_macroblock_probe_pskip (macroblock.c:492-604) on the P_SKIP prediction in `pred` --
+// same transforms and quantisers, but nothing is stored except one flag per macroblock (nnz_out[mb] = 1: skippable);
+// the early exits of the reference are sums here (scores only grow, so "ever >= 6" is "total >= 6")
+template<bool TYPED, bool PROBE = false>
 __global__ void __launch_bounds__( 128 )
 xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t *__restrict__ pred,
                     xd_res_tables T, int16_t *__restrict__ levels, uint8_t *__restrict__ nnz_out,
@@ -120,9 +124,14 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     // blockIdx.y = frame of a batch: consecutive slots, per-frame output arrays back to back
     fenc += blockIdx.y * (size_t)g.slot_bytes;
     pred += blockIdx.y * (size_t)g.slot_bytes;
-    levels += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_LEVELS_PER_MB;
-    nnz_out += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_NNZ_PER_MB;
-    cbp_out += blockIdx.y * (size_t)g.mb_count;
+    if( !PROBE )
+    {
+        levels += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_LEVELS_PER_MB;
+        nnz_out += blockIdx.y * (size_t)g.mb_count * X264DSP_RES_NNZ_PER_MB;
+        cbp_out += blockIdx.y * (size_t)g.mb_count;
+    }
+    else
+        nnz_out += blockIdx.y * (size_t)g.mb_count;
     bool intra = false, i16 = false, i4 = false;
     if( TYPED )
     {
@@ -194,7 +203,7 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
     const int sum_u = __shfl_sync( 0xffffffffu, psum, 16 ), sqr_u = __shfl_sync( 0xffffffffu, psqr, 16 );
     const int sum_v = __shfl_sync( 0xffffffffu, psum, 20 ), sqr_v = __shfl_sync( 0xffffffffu, psqr, 20 );
     bool early = false;
-    if( T.qpc >= 18 && !intra )
+    if( T.qpc >= 18 && !intra && !PROBE )
     {
         const unsigned au = (unsigned)abs( sum_u ), av = (unsigned)abs( sum_v );
         const int var_u = (int)( (unsigned)sqr_u - (unsigned)( ( (unsigned long long)au * au ) >> 6 ) );
@@ -229,6 +238,28 @@ xd_residual_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc, uint8_t 
 #pragma unroll
         for( int i = 0; i < 16; i++ )
             lv[i] = 0;
+    }
+    if( PROBE )
+    {
+        // luma: the decimate scores of all coded 4x4s; chroma per plane: SSD below thresh passes, a coded DC fails,
+        // SSD below 4 thresh passes, else the AC decimate scores decide (macroblock.c:510-600)
+        int luma_sum = is_luma ? score : 0, plane_sum = is_chroma ? score : 0;
+#pragma unroll
+        for( int o = 1; o < 16; o <<= 1 )
+            luma_sum += __shfl_xor_sync( 0xffffffffu, luma_sum, o );
+        luma_sum = __shfl_sync( 0xffffffffu, luma_sum, 0 );
+        plane_sum += __shfl_xor_sync( 0xffffffffu, plane_sum, 1 );
+        plane_sum += __shfl_xor_sync( 0xffffffffu, plane_sum, 2 );
+        int nz_dc = 0;
+#pragma unroll
+        for( int i = 0; i < 4; i++ )
+            nz_dc |= xd_quant1( dc[i], T.chroma_dc_mf, T.chroma_dc_bias );
+        const int ssd = ch ? sqr_v : sqr_u;
+        const bool plane_fail = is_chroma && ssd >= T.thresh && ( nz_dc != 0 || ( ssd >= ( T.thresh << 2 ) && plane_sum >= 7 ) );
+        const bool fail = luma_sum >= 6 || __any_sync( 0xffffffffu, plane_fail );
+        if( lane == 0 )
+            nnz_out[mb] = fail ? 0 : 1;
+        return;
     }
     int16_t *mb_levels = levels + (size_t)mb * X264DSP_RES_LEVELS_PER_MB;
     if( is_luma && !i4 )
@@ -626,6 +657,35 @@ extern "C" int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264
                                                    int16_t *luma_dc, uint8_t *nnz, int16_t *cbp, void *stream )
 {
     return xd_residual_launch( ctx, g, fenc_slot, pred_slot, n_frames, qp, mb_kind, i4_modes, levels, luma_dc, nnz, cbp, true, stream );
+}
+
+extern "C" int x264dsp_probe_pskip_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slot,
+                                               const uint8_t *pred_slot, int n_frames, int qp, uint8_t *skip, void *stream )
+{
+    if( !ctx || !g || !fenc_slot || !pred_slot || !skip || qp < 0 || qp > 51 || n_frames <= 0 || n_frames > 65535 )
+        return X264DSP_E_ARG;
+    xd_res_tables T;
+    memset( &T, 0, sizeof( T ) );
+    const int qpc = x264dsp_chroma_qp( qp );
+    xd_fill_qparams( &T.luma, qp );
+    xd_fill_qparams( &T.chroma, qpc );
+    {
+        uint16_t mf[16], bias[16];
+        x264dsp_quant_tables( 1, qpc, mf, bias );
+        T.chroma_dc_mf = mf[0] >> 1;
+        T.chroma_dc_bias = bias[0] << 1;
+    }
+    T.qpc = qpc;
+    T.thresh = ( xd_lambda2_tab[qpc] + 32 ) >> 6;
+    cudaStream_t s = xd_stream( ctx, stream );
+    const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_RESIDUAL, s );
+    // the kernel only reads pred in this mode
+    xd_residual_kernel<false, true><<<grid, 128, 0, s>>>( *g, fenc_slot, const_cast<uint8_t *>( pred_slot ), T, NULL, skip, NULL, NULL, NULL );
+    xd_prof_end( ctx, XD_PROF_RESIDUAL, pslot, s );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
 }
 
 extern "C" int x264dsp_residual_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
