@@ -338,3 +338,41 @@ void x264_macroblock_encode( x264_t *h )
         && h->mb.cache.ref[0][x264_scan8[0]] == 0 )
         h->mb.i_type = P_SKIP;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * x264_macroblock_probe_pskip   encoder/macroblock.c:492     called from encoder/analyse.c (P-slice analysis)
+ *
+ * The P_SKIP probe of a macroblock: motion compensation at the clipped pskip mv, then the "would anything be
+ * coded" test.  The hook gets the frames (kept resident on the device by the test), the macroblock position, the
+ * clipped mv and the QP; it leaves the prediction in fdec, as the reference does, and returns the decision
+ * (x264dsp_mc_frame_dev + x264dsp_probe_pskip_frames_dev). */
+typedef int (*xref_pskip_cb)( void *h, void *fenc, void *fref, int mb_x, int mb_y, int mvx, int mvy, int qp,
+                              uint8_t *fdec_y, uint8_t *fdec_c, int *skip );
+xref_pskip_cb xref_hook_pskip = NULL;
+int xref_hook_pskip_calls = 0;
+
+void xref_set_pskip_hook( xref_pskip_cb cb )
+{
+    xref_hook_pskip = cb;
+    xref_hook_pskip_calls = 0;
+}
+int xref_pskip_hook_calls( void ) { return xref_hook_pskip_calls; }
+
+int xref_orig_macroblock_probe_pskip( x264_t *h );
+
+int x264_macroblock_probe_pskip( x264_t *h )
+{
+    int skip = 0, mvx, mvy;
+    if( !xref_hook_pskip || h->mb.b_noise_reduction || !h->fref[0][0]
+        || h->mb.i_chroma_qp != h->chroma_qp_table[h->mb.i_qp] )
+        return xref_orig_macroblock_probe_pskip( h );
+    mvx = x264_clip3( h->mb.cache.pskip_mv[0], h->mb.mv_min[0], h->mb.mv_max[0] );
+    mvy = x264_clip3( h->mb.cache.pskip_mv[1], h->mb.mv_min[1], h->mb.mv_max[1] );
+    if( xref_hook_pskip( h, h->fenc, h->fref[0][0], h->mb.i_mb_x, h->mb.i_mb_y, mvx, mvy, h->mb.i_qp,
+                         h->mb.pic.p_fdec[0], h->mb.pic.p_fdec[1], &skip ) )
+        return xref_orig_macroblock_probe_pskip( h );          /* declined: a frame is not resident */
+    xref_hook_pskip_calls++;
+    if( skip )
+        h->mb.b_skip_mc = 1;                                   /* the prediction in fdec is the reconstruction */
+    return skip;
+}

@@ -9,6 +9,8 @@ of its hot-path drivers served by libx264dsp_b200.so --
                                                 -> x264dsp_lookahead_frame_cost_dev
   x264_me_search_ref (every partition search of the main encode, last cases)
                                                 -> x264dsp_me_search_batch_dev on frames kept resident on the device
+  x264_macroblock_probe_pskip (the P_SKIP test of the P-slice analysis, last case)
+                                                -> x264dsp_mc_frame_dev + x264dsp_probe_pskip_frames_dev
   x264_macroblock_encode (every inter macroblock of the P slices and every I16x16 / I4x4 macroblock of the I slices, last
   two cases: DCT, quant, zig-zag, dequant, decimation, luma / chroma DC, IDCT; levels / nnz / cbp handed to the
   reference's CABAC writer)                     -> x264dsp_residual_frames_typed_dev
@@ -32,6 +34,8 @@ COST_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_voi
 FDEC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                       C.c_int, C.c_int, C.c_int)
 ME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
+PSKIP_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                       C.c_void_p, C.POINTER(C.c_int))
 MBENC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
 
@@ -80,6 +84,8 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         # the source frame's padded luma plane in, four padded lowres planes (and the source plane with its
         # duplicated last column / row, mc.c:412-415) out
         upload(0, 0, lib.xref_frame_ptr(frame, 10), lps)
+        if mehook:
+            upload(0, g.slot_chroma_off, lib.xref_frame_ptr(frame, 11), g.chroma_plane_size)   # the P_SKIP probe reads it
         keep_resident(frame)              # the source samples as the main encode's searches will see them
         ctx.frame_init_lowres(g, slots, 1)
         ctx.frame_export_lowres(g, slots, 1)      # the reference wants its row-major lowres[0..3]
@@ -203,6 +209,37 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         mbenc_calls[kind & 3] += 1
         return 0
 
+    pskip_calls = [0, 0]                  # probes served, of which skippable
+    d_pmv = torch.zeros((g.mb_count, 2), dtype=torch.int16, device="cuda")
+    d_ppred = torch.zeros(g.slot_bytes, dtype=torch.uint8, device="cuda")
+    d_pskip = torch.zeros(g.mb_count, dtype=torch.uint8, device="cuda")
+
+    @PSKIP_CB
+    def pskip_cb(hv, fenc, fref, mb_x, mb_y, mvx, mvy, qp, fdec_y, fdec_c, skip):
+        if fenc not in resident or fref not in resident:
+            return 1
+        xy = mb_y * g.mb_w + mb_x
+        d_pmv.zero_()
+        d_pmv[xy, 0], d_pmv[xy, 1] = mvx, mvy
+        torch.cuda.synchronize()
+        ctx.mc_frame(g, resident[fref], d_pmv, d_ppred)                       # mc_luma + mc_chroma at the pskip mv
+        ctx.probe_pskip_frames(g, resident[fenc], d_ppred, 1, qp, d_pskip)
+        ctx.sync()
+        pred = d_ppred.cpu().numpy()
+        lo = g.luma_origin + mb_y * 16 * g.luma_stride + mb_x * 16
+        co = g.slot_chroma_off + g.chroma_origin + mb_y * 8 * g.chroma_stride + mb_x * 16
+        dy = host_view(fdec_y, 16 * 32).reshape(16, 32)
+        dc = host_view(fdec_c, 8 * 32).reshape(8, 32)
+        for r in range(16):
+            dy[r, :16] = pred[lo + r * g.luma_stride: lo + r * g.luma_stride + 16]
+        for r in range(8):
+            row = pred[co + r * g.chroma_stride: co + r * g.chroma_stride + 16]
+            dc[r, :8], dc[r, 16:24] = row[0::2], row[1::2]
+        skip[0] = int(d_pskip[xy].item())
+        pskip_calls[0] += 1
+        pskip_calls[1] += skip[0]
+        return 0
+
     outs, calls = [], (C.c_int * 3)()
     for use_gpu in (False, True):
         enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=26, psub16x16=psub)
@@ -214,6 +251,8 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
                 lib.xref_set_me_hook(me_cb)
             if mbenc:
                 lib.xref_set_mbenc_hook(mbenc_cb)
+            if mbenc and mehook:
+                lib.xref_set_pskip_hook(pskip_cb)
         else:
             lib.xref_set_driver_hooks(None, None, None)
         out = np.zeros(1 << 20, np.uint8)
@@ -226,6 +265,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             lib.xref_set_fdec_hook(None)
             lib.xref_set_me_hook(None)
             lib.xref_set_mbenc_hook(None)
+            lib.xref_set_pskip_hook(None)
         assert size > 0, size
         outs.append(out[:size].copy())
         if use_gpu:
@@ -235,6 +275,9 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             assert ctx.launches - launches0 >= 2 * n, "the encode must have gone through the CUDA kernels"
             if mehook:
                 assert me_calls[0] >= (n - 3) * g.mb_count // 2, f"only {me_calls[0]} searches went to the device"
+            if mbenc and mehook:
+                assert pskip_calls[0] >= g.mb_count // 4, f"only {pskip_calls[0]} P_SKIP probes went to the device"
+                assert 0 < pskip_calls[1] < pskip_calls[0], f"one-sided probes: {pskip_calls}"
             if mbenc:
                 assert mbenc_calls[0] >= g.mb_count, f"only {mbenc_calls[0]} inter macroblocks were coded on the device"
                 assert mbenc_calls[1] > 0, "no I16x16 macroblock of the I frames was coded on the device"
