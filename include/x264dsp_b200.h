@@ -363,6 +363,11 @@ int x264dsp_mc_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uin
 /* n_frames consecutive reference slots -> n_frames consecutive prediction slots, mv[n_frames][mb_count][2] */
 int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slots,
                            int n_frames, const int16_t *mv, uint8_t *pred_slots, void *stream );
+/* The same with one MV per 8x8 block (mv8x8[frame][mb][4][2], raster order inside the macroblock): every partition
+ * x264_mb_mc handles -- D_16x16, D_16x8, D_8x16, D_8x8 (common/macroblock.c:28-48) -- once the macroblock's MVs are
+ * written out per 8x8, as h->mb.cache.mv holds them at x264_scan8[0], [4], [8], [12]. */
+int x264dsp_mc_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slots,
+                                int n_frames, const int16_t *mv8x8, uint8_t *pred_slots, void *stream );
 
 /* ------------------------------------------------------------------ deblock
  * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's

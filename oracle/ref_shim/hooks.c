@@ -376,3 +376,49 @@ int x264_macroblock_probe_pskip( x264_t *h )
         h->mb.b_skip_mc = 1;                                   /* the prediction in fdec is the reconstruction */
     return skip;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * x264_mb_mc                    common/macroblock.c:28       called from x264_macroblock_encode (and analysis)
+ *
+ * Motion compensation of a P macroblock with any partition the reference analyses: the four 8x8 MVs of the cache go
+ * to x264dsp_mc_frames_part_dev on the resident reference frame, the prediction comes back into fdec. */
+typedef int (*xref_mbmc_cb)( void *h, void *fref, int mb_x, int mb_y, const int16_t *mv8x8, uint8_t *fdec_y, uint8_t *fdec_c );
+xref_mbmc_cb xref_hook_mbmc = NULL;
+int xref_hook_mbmc_calls = 0;
+
+void xref_set_mbmc_hook( xref_mbmc_cb cb )
+{
+    xref_hook_mbmc = cb;
+    xref_hook_mbmc_calls = 0;
+}
+int xref_mbmc_hook_calls( void ) { return xref_hook_mbmc_calls; }
+
+void xref_orig_mb_mc( x264_t *h );
+
+void x264_mb_mc( x264_t *h )
+{
+    static const int8_t cell[4] = { 0, 2, 16, 18 };            /* x264_scan8[0] + x + (y<<3) for the four 8x8 corners */
+    int16_t mv[4][2];
+    int k;
+    if( !xref_hook_mbmc || h->sh.i_type != SLICE_TYPE_P || !h->fref[0][0] )
+    {
+        xref_orig_mb_mc( h );
+        return;
+    }
+    for( k = 0; k < 4; k++ )
+    {
+        if( h->mb.cache.ref[0][x264_scan8[0] + cell[k]] != 0 )
+        {
+            xref_orig_mb_mc( h );
+            return;
+        }
+        mv[k][0] = h->mb.cache.mv[0][x264_scan8[0] + cell[k]][0];
+        mv[k][1] = h->mb.cache.mv[0][x264_scan8[0] + cell[k]][1];
+    }
+    if( xref_hook_mbmc( h, h->fref[0][0], h->mb.i_mb_x, h->mb.i_mb_y, &mv[0][0], h->mb.pic.p_fdec[0], h->mb.pic.p_fdec[1] ) )
+    {
+        xref_orig_mb_mc( h );
+        return;
+    }
+    xref_hook_mbmc_calls++;
+}

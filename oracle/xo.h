@@ -121,6 +121,7 @@ void xo_lookahead_frame_cost( const x264dsp_geom_t *g, const uint8_t *slot_b, co
 
 /* ---- residual + MC (encoder/macroblock.c, common/macroblock.c) */
 void xo_mc_frame( const x264dsp_geom_t *g, const uint8_t *fref_slot, const int16_t *mv, uint8_t *pred_slot );
+void xo_mc_frame_part( const x264dsp_geom_t *g, const uint8_t *fref_slot, const int16_t *mv, uint8_t *pred_slot );
 void xo_residual_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,
                         int16_t *levels, uint8_t *nnz, int16_t *cbp );
 void xo_residual_frame_typed( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *pred_slot, int qp,

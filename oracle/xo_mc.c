@@ -114,3 +114,42 @@ void xo_mc_frame( const x264dsp_geom_t *g, const uint8_t *fref_slot, const int16
                 }
         }
 }
+
+/* x264_mb_mc for every partition the reference analyses (common/macroblock.c:8-48), the macroblock's MVs written out
+ * per 8x8 block (mv: [mb][4][2], raster order): x264_mb_mc_xywh( x, y, 2, 2 ) four times -- the 16x16 / 16x8 / 8x16
+ * cases produce the same samples 8x8-wise, mc_luma and mc_chroma being per-pixel rules. */
+void xo_mc_frame_part( const x264dsp_geom_t *g, const uint8_t *fref_slot, const int16_t *mv, uint8_t *pred_slot )
+{
+    const int ls = g->luma_stride, cs = g->chroma_stride;
+    int mb_x, mb_y, k, x, y, p;
+    for( mb_y = 0; mb_y < g->mb_h; mb_y++ )
+        for( mb_x = 0; mb_x < g->mb_w; mb_x++ )
+        {
+            int i = mb_y * g->mb_w + mb_x;
+            int min_x = (-(mb_x << 4) - 24) << 2, max_x = (((g->mb_w - mb_x - 1) << 4) + 24) << 2;
+            int min_y = (-(mb_y << 4) - 24) << 2, max_y = (((g->mb_h - mb_y - 1) << 4) + 24) << 2;
+            for( p = 0; p < 4; p++ )
+            {
+                const int px = (p & 1) * 8, py = (p >> 1) * 8;
+                int mvx = mv[2*(4*i + p)], mvy = mv[2*(4*i + p) + 1];
+                const pixel_t *src[4];
+                pixel_t *dy = pred_slot + g->luma_origin + (ptrdiff_t)((mb_y << 4) + py) * ls + (mb_x << 4) + px;
+                pixel_t *dc = pred_slot + g->slot_chroma_off + g->chroma_origin + (ptrdiff_t)((mb_y << 3) + py/2) * cs + (mb_x << 4) + px;
+                pixel_t u[4*4], v[4*4];
+                mvx = mvx < min_x ? min_x : mvx > max_x ? max_x : mvx;
+                mvy = mvy < min_y ? min_y : mvy > max_y ? max_y : mvy;
+                for( k = 0; k < 4; k++ )
+                    src[k] = fref_slot + (size_t)k * g->luma_plane_size + g->luma_origin
+                           + (ptrdiff_t)((mb_y << 4) + py) * ls + (mb_x << 4) + px;
+                xo_mc_luma( dy, ls, src, ls, mvx, mvy, 8, 8 );
+                xo_mc_chroma( u, v, 4, fref_slot + g->slot_chroma_off + g->chroma_origin
+                              + (ptrdiff_t)((mb_y << 3) + py/2) * cs + (mb_x << 4) + px, cs, mvx, mvy, 4, 4 );
+                for( y = 0; y < 4; y++ )
+                    for( x = 0; x < 4; x++ )
+                    {
+                        dc[y*cs + 2*x]     = u[y*4 + x];
+                        dc[y*cs + 2*x + 1] = v[y*4 + x];
+                    }
+            }
+        }
+}

@@ -9,6 +9,7 @@ of its hot-path drivers served by libx264dsp_b200.so --
                                                 -> x264dsp_lookahead_frame_cost_dev
   x264_me_search_ref (every partition search of the main encode, last cases)
                                                 -> x264dsp_me_search_batch_dev on frames kept resident on the device
+  x264_mb_mc (motion compensation of every P macroblock, all partitions, last case) -> x264dsp_mc_frames_part_dev
   x264_macroblock_probe_pskip (the P_SKIP test of the P-slice analysis, last case)
                                                 -> x264dsp_mc_frame_dev + x264dsp_probe_pskip_frames_dev
   x264_macroblock_encode (every inter macroblock of the P slices and every I16x16 / I4x4 macroblock of the I slices, last
@@ -34,6 +35,7 @@ COST_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_voi
 FDEC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                       C.c_int, C.c_int, C.c_int)
 ME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
+MBMC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 PSKIP_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                        C.c_void_p, C.POINTER(C.c_int))
 MBENC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
@@ -240,6 +242,32 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         pskip_calls[1] += skip[0]
         return 0
 
+    mbmc_calls = [0]
+    d_mv4 = torch.zeros((g.mb_count, 4, 2), dtype=torch.int16, device="cuda")
+
+    @MBMC_CB
+    def mbmc_cb(hv, fref, mb_x, mb_y, mv8x8, fdec_y, fdec_c):
+        if fref not in resident:
+            return 1
+        xy = mb_y * g.mb_w + mb_x
+        d_mv4.zero_()
+        d_mv4[xy] = torch.from_numpy(np.frombuffer(host_view(mv8x8, 16).tobytes(), np.int16).reshape(4, 2).copy()).cuda()
+        torch.cuda.synchronize()
+        ctx.mc_frames_part(g, resident[fref], 1, d_mv4, d_ppred)
+        ctx.sync()
+        pred = d_ppred.cpu().numpy()
+        lo = g.luma_origin + mb_y * 16 * g.luma_stride + mb_x * 16
+        co = g.slot_chroma_off + g.chroma_origin + mb_y * 8 * g.chroma_stride + mb_x * 16
+        dy = host_view(fdec_y, 16 * 32).reshape(16, 32)
+        dc = host_view(fdec_c, 8 * 32).reshape(8, 32)
+        for r in range(16):
+            dy[r, :16] = pred[lo + r * g.luma_stride: lo + r * g.luma_stride + 16]
+        for r in range(8):
+            row = pred[co + r * g.chroma_stride: co + r * g.chroma_stride + 16]
+            dc[r, :8], dc[r, 16:24] = row[0::2], row[1::2]
+        mbmc_calls[0] += 1
+        return 0
+
     outs, calls = [], (C.c_int * 3)()
     for use_gpu in (False, True):
         enc = cc.RefEncoder(w, h, me=me, subme=subme, me_range=16, qp=26, psub16x16=psub)
@@ -253,6 +281,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
                 lib.xref_set_mbenc_hook(mbenc_cb)
             if mbenc and mehook:
                 lib.xref_set_pskip_hook(pskip_cb)
+                lib.xref_set_mbmc_hook(mbmc_cb)
         else:
             lib.xref_set_driver_hooks(None, None, None)
         out = np.zeros(1 << 20, np.uint8)
@@ -266,6 +295,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             lib.xref_set_me_hook(None)
             lib.xref_set_mbenc_hook(None)
             lib.xref_set_pskip_hook(None)
+            lib.xref_set_mbmc_hook(None)
         assert size > 0, size
         outs.append(out[:size].copy())
         if use_gpu:
@@ -276,6 +306,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             if mehook:
                 assert me_calls[0] >= (n - 3) * g.mb_count // 2, f"only {me_calls[0]} searches went to the device"
             if mbenc and mehook:
+                assert mbmc_calls[0] >= g.mb_count, f"only {mbmc_calls[0]} macroblocks were motion-compensated on the device"
                 assert pskip_calls[0] >= g.mb_count // 4, f"only {pskip_calls[0]} P_SKIP probes went to the device"
                 assert 0 < pskip_calls[1] < pskip_calls[0], f"one-sided probes: {pskip_calls}"
             if mbenc:

@@ -305,3 +305,35 @@ def test_probe_pskip_frames(pkg, ctx, w, h, nf, qp):
     assert len(bad) == 0, f"{len(bad)} decisions differ, first (frame, mb) {bad[:5].tolist()}: {got[tuple(bad[0])]} vs {want[tuple(bad[0])]}"
     assert torch.equal(before, pred), "the probe must not modify the prediction"
     assert not want.all() and (want.any() or qp < 26), f"one-sided test: {int(want.sum())} of {want.size} skippable"
+
+
+@pytest.mark.parametrize("w,h,nf", [(352, 288, 2), (200, 120, 3), (1920, 1080, 1)])
+def test_mc_frames_part(pkg, ctx, w, h, nf):
+    """one MV per 8x8 block (every partition of x264_mb_mc) against the oracle; with four equal MVs per macroblock the
+    oracle's partition-wise composition must reproduce its 16x16 one (which is what the reference's mc tables pin)"""
+    import torch
+    g, go, host, dev = _slots(pkg, ctx, w, h, nf, True)
+    o = cc.oracle()
+    rng = np.random.RandomState(w + nf)
+    n = g.mb_count
+    mv = (np.array([12, 8]) + rng.randint(-9, 10, (nf, n, 4, 2))).astype(np.int16)
+    mv[rng.rand(nf, n) < 0.05] = rng.randint(-3000, 3000, 2)             # clipped to the macroblock's limits
+    same = rng.rand(nf, n) < 0.3
+    mv[same] = mv[same][:, :1]                                            # 16x16 macroblocks
+    want = []
+    for f in range(nf):
+        po = np.zeros(go.slot_bytes, np.uint8)
+        o.xo_mc_frame_part(C.byref(go), ptr(host[f]), ptr(mv[f], i16p), ptr(po))
+        want.append(po)
+    mv16 = np.ascontiguousarray(mv[0][:, 0])
+    a, b = np.zeros(go.slot_bytes, np.uint8), np.zeros(go.slot_bytes, np.uint8)
+    o.xo_mc_frame(C.byref(go), ptr(host[0]), ptr(mv16, i16p), ptr(a))
+    o.xo_mc_frame_part(C.byref(go), ptr(host[0]), ptr(np.ascontiguousarray(np.repeat(mv16[:, None], 4, 1)), i16p), ptr(b))
+    assert np.array_equal(a, b), "oracle: partition-wise MC of a 16x16 macroblock differs from the 16x16 call"
+    pred = torch.zeros(nf * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.mc_frames_part(g, dev, nf, torch.from_numpy(mv).cuda(), pred)
+    ctx.sync()
+    got = pred.cpu().numpy().reshape(nf, -1)
+    for f in range(nf):
+        assert np.array_equal(got[f], want[f]), f"frame {f}"

@@ -385,6 +385,11 @@ class Context:
         check(lib().x264dsp_mc_frames_dev(self._h, C.byref(g), _dp(fref_slots), int(n_frames), _dp(mv_dev),
                                           _dp(pred_slots), None), "x264dsp_mc_frames_dev")
 
+    def mc_frames_part(self, g, fref_slots, n_frames, mv8x8_dev, pred_slots):
+        """one MV per 8x8 block: int16[n][mb][4][2]"""
+        check(lib().x264dsp_mc_frames_part_dev(self._h, C.byref(g), _dp(fref_slots), int(n_frames), _dp(mv8x8_dev),
+                                               _dp(pred_slots), None), "x264dsp_mc_frames_part_dev")
+
     def residual_frames(self, g, fenc_slots, pred_slots, n_frames, qp, levels, nnz, cbp):
         check(lib().x264dsp_residual_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
                                                 int(qp), _dp(levels), _dp(nnz), _dp(cbp), None),

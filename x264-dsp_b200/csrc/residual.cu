@@ -21,7 +21,11 @@
 #include <string.h>
 
 // ---------------------------------------------------------------------------------------------
-// motion compensation: 64 threads per macroblock (4 luma pixels + 1 UV pair each), 4 MBs per CTA
+// motion compensation: 64 threads per macroblock (4 luma pixels + 1 UV pair each), 4 MBs per CTA.
+// NMV = 1: one MV per macroblock (x264_mb_mc, D_16x16); NMV = 4: one MV per 8x8 in raster order, which covers every
+// partition the reference analyses -- x264_mb_mc's 16x8 / 8x16 / 8x8 cases are 8x8-wise the same samples, mc_luma and
+// mc_chroma being per-pixel rules (common/macroblock.c:8-48)
+template<int NMV>
 __global__ void __launch_bounds__( 256 )
 xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const int16_t *__restrict__ mv,
                     uint8_t *__restrict__ pred )
@@ -32,16 +36,18 @@ xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const in
     // blockIdx.y = frame of a batch: consecutive slots, mb_count MVs per frame
     fref += blockIdx.y * (size_t)g.slot_bytes;
     pred += blockIdx.y * (size_t)g.slot_bytes;
-    mv += blockIdx.y * (size_t)g.mb_count * 2;
+    mv += blockIdx.y * (size_t)g.mb_count * 2 * NMV;
     const int t = threadIdx.x & 63;
     const int mb_x = mb % g.mb_w, mb_y = mb / g.mb_w;
     const int ls = g.luma_stride, cs = g.chroma_stride;
     // analyse.c:378-390: mv_min / mv_max of the macroblock (quarter-pel)
-    const int mvx = xd_clip3( mv[2 * mb], ( -( mb_x << 4 ) - 24 ) << 2, ( ( ( g.mb_w - mb_x - 1 ) << 4 ) + 24 ) << 2 );
-    const int mvy = xd_clip3( mv[2 * mb + 1], ( -( mb_y << 4 ) - 24 ) << 2, ( ( ( g.mb_h - mb_y - 1 ) << 4 ) + 24 ) << 2 );
+    const int lo_x = ( -( mb_x << 4 ) - 24 ) << 2, hi_x = ( ( ( g.mb_w - mb_x - 1 ) << 4 ) + 24 ) << 2;
+    const int lo_y = ( -( mb_y << 4 ) - 24 ) << 2, hi_y = ( ( ( g.mb_h - mb_y - 1 ) << 4 ) + 24 ) << 2;
     {
         // luma: row t/4, pixels 4*(t%4) .. +3
         const int y = t >> 2, x = ( t & 3 ) * 4;
+        const int part = NMV == 4 ? ( y >> 3 ) * 2 + ( x >> 3 ) : 0;
+        const int mvx = xd_clip3( mv[2 * ( mb * NMV + part )], lo_x, hi_x ), mvy = xd_clip3( mv[2 * ( mb * NMV + part ) + 1], lo_y, hi_y );
         const int fx = mvx & 3, fy = mvy & 3, phase = fy * 4 + fx;
         const int64_t pos = (int64_t)( ( mb_y << 4 ) + y + ( mvy >> 2 ) ) * ls + ( mb_x << 4 ) + x + ( mvx >> 2 );
         const uint8_t *base = fref + g.luma_origin;
@@ -53,6 +59,8 @@ xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const in
     {
         // chroma: row t/8, pair t%8; eighth-pel bilinear on NV12 (mc.c:290-323)
         const int y = t >> 3, x = t & 7;
+        const int part = NMV == 4 ? ( y >> 2 ) * 2 + ( x >> 2 ) : 0;
+        const int mvx = xd_clip3( mv[2 * ( mb * NMV + part )], lo_x, hi_x ), mvy = xd_clip3( mv[2 * ( mb * NMV + part ) + 1], lo_y, hi_y );
         const int dx = mvx & 7, dy = mvy & 7;
         const int cA = ( 8 - dx ) * ( 8 - dy ), cB = dx * ( 8 - dy ), cC = ( 8 - dx ) * dy, cD = dx * dy;
         const uint8_t *s0 = fref + g.slot_chroma_off + g.chroma_origin
@@ -703,7 +711,22 @@ extern "C" int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *
     cudaStream_t s = xd_stream( ctx, stream );
     const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_MC, s );
-    xd_mc_frame_kernel<<<grid, 256, 0, s>>>( *g, fref_slot, mv, pred_slot );
+    xd_mc_frame_kernel<1><<<grid, 256, 0, s>>>( *g, fref_slot, mv, pred_slot );
+    xd_prof_end( ctx, XD_PROF_MC, pslot, s );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
+}
+
+extern "C" int x264dsp_mc_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slot,
+                                            int n_frames, const int16_t *mv8x8, uint8_t *pred_slot, void *stream )
+{
+    if( !ctx || !g || !fref_slot || !mv8x8 || !pred_slot || fref_slot == pred_slot || n_frames <= 0 || n_frames > 65535 )
+        return X264DSP_E_ARG;
+    cudaStream_t s = xd_stream( ctx, stream );
+    const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
+    const int pslot = xd_prof_begin( ctx, XD_PROF_MC, s );
+    xd_mc_frame_kernel<4><<<grid, 256, 0, s>>>( *g, fref_slot, mv8x8, pred_slot );
     xd_prof_end( ctx, XD_PROF_MC, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
