@@ -105,6 +105,34 @@ def main():
     G["i4_modes"], G["i4_replicate5"] = m4, rep
     G["i4_recon_y"], G["i4_recon_c"], G["i4_levels"], G["i4_nnz"], G["i4_cbp"] = r4y, r4c[..., :24], l4, n4, c4
 
+    # ------------------------------------------------------------ x264_macroblock_probe_pskip, 96 macroblocks per QP
+    lib.xref_probe_pskip_mb.restype = C.c_int
+    rp = np.random.RandomState(9292)
+    PQ = [14, 22, 26, 32, 40]
+    NP = 96
+    sk_fy, sk_fc = np.zeros((len(PQ), NP, 16, 16), np.uint8), np.zeros((len(PQ), NP, 8, 16), np.uint8)
+    sk_py, sk_pc = np.zeros((len(PQ), NP, 16, 32), np.uint8), np.zeros((len(PQ), NP, 8, 32), np.uint8)
+    sk = np.zeros((len(PQ), NP), np.uint8)
+    for qi, qp in enumerate(PQ):
+        scale = max(1, (qp - 14) // 5)
+        for t in range(NP):
+            p_y = rp.randint(0, 256, (16, 32)).astype(np.uint8)
+            p_c = rp.randint(0, 256, (8, 32)).astype(np.uint8)
+            if t % 3 == 0:
+                p_y[:], p_c[:] = rp.randint(30, 220), rp.randint(30, 220)
+            p_y[:, 16:], p_c[:, 8:16], p_c[:, 24:] = 0, 0, 0
+            amp, camp = [0, 1, 2, 3, 5, 8, 14][t % 7] * scale, [0, 1, 2, 4, 9][t % 5] * scale
+            f_y = np.clip(p_y[:, :16].astype(int) + rp.randint(-amp, amp + 1, (16, 16)), 0, 255).astype(np.uint8)
+            f_c = np.zeros((8, 16), np.uint8)
+            f_c[:, :8] = np.clip(p_c[:, :8].astype(int) + rp.randint(-camp, camp + 1, (8, 8)), 0, 255)
+            f_c[:, 8:] = np.clip(p_c[:, 16:24].astype(int) + rp.randint(-camp, camp + 1, (8, 8)), 0, 255)
+            if t % 13 == 0:
+                f_c[:, :8] = np.clip(p_c[:, :8].astype(int) + rp.randint(-4, 5), 0, 255)
+            sk[qi, t] = lib.xref_probe_pskip_mb(enc.h, ptr(f_y), ptr(f_c), ptr(p_y), ptr(p_c), qp)
+            sk_fy[qi, t], sk_fc[qi, t], sk_py[qi, t], sk_pc[qi, t] = f_y, f_c, p_y, p_c
+    G["pskip_qps"] = np.array(PQ)
+    G["pskip_fenc_y"], G["pskip_fenc_c"], G["pskip_pred_y"], G["pskip_pred_c"], G["pskip_skip"] = sk_fy, sk_fc, sk_py[..., :16], sk_pc[..., :24], sk
+
     # ------------------------------------------------------------ the 26 predictors on 10 neighbourhoods each
     tabs = [(PRED_T * 7)(), (PRED_T * 7)(), (PRED_T * 12)()]
     lib.x264_predict_16x16_init(0, tabs[0])

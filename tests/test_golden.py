@@ -794,3 +794,47 @@ def test_gpu_intra4_frame(GI, pkg, ctx):
                 rc[r, :8] = rec[co + r * cs: co + r * cs + 16: 2]
                 rc[r, 16:24] = rec[co + r * cs + 1: co + r * cs + 16: 2]
             check_intra4(GI, qi, t, int(cbp[where[t]]), nz[where[t]], lv[where[t]], ry, rc)
+
+
+def test_oracle_probe_pskip(GI):
+    o = cc.oracle()
+    o.xo_probe_pskip_mb.restype = C.c_int
+    for qi, qp in enumerate(GI["pskip_qps"]):
+        for t in range(GI["pskip_fenc_y"].shape[1]):
+            y = np.zeros((16, 32), np.uint8)
+            c = np.zeros((8, 32), np.uint8)
+            y[:, :16], c[:, :24] = GI["pskip_pred_y"][qi, t], GI["pskip_pred_c"][qi, t]
+            r = o.xo_probe_pskip_mb(ptr(np.ascontiguousarray(GI["pskip_fenc_y"][qi, t])), ptr(np.ascontiguousarray(GI["pskip_fenc_c"][qi, t])),
+                                    ptr(y), ptr(c), int(qp))
+            assert r == GI["pskip_skip"][qi, t], f"qp {qp} mb {t}: oracle {r} reference {GI['pskip_skip'][qi, t]}"
+
+
+@pytest.mark.gpu
+def test_gpu_probe_pskip_golden(GI, pkg, ctx):
+    """the 96 stored macroblocks of each QP as two 128x96 frames, x264dsp_probe_pskip_frames_dev against the
+    reference's stored decisions"""
+    import torch
+    g = pkg.geometry(128, 96)
+    cs = g.chroma_stride
+    nper = g.mb_count
+    for qi, qp in enumerate(GI["pskip_qps"]):
+        nfr = GI["pskip_fenc_y"].shape[1] // nper
+        fenc, pred = np.zeros((nfr, g.slot_bytes), np.uint8), np.zeros((nfr, g.slot_bytes), np.uint8)
+        for t in range(nfr * nper):
+            f, m = divmod(t, nper)
+            mx, my = m % g.mb_w, m // g.mb_w
+            for slot, y, c, voff in ((fenc[f], GI["pskip_fenc_y"][qi, t], GI["pskip_fenc_c"][qi, t], 8),
+                                     (pred[f], GI["pskip_pred_y"][qi, t], GI["pskip_pred_c"][qi, t], 16)):
+                lo = g.luma_origin + my * 16 * g.luma_stride + mx * 16
+                for r in range(16):
+                    slot[lo + r * g.luma_stride: lo + r * g.luma_stride + 16] = y[r]
+                co = g.slot_chroma_off + g.chroma_origin + my * 8 * cs + mx * 16
+                for r in range(8):
+                    slot[co + r * cs: co + r * cs + 16: 2] = c[r, :8]
+                    slot[co + r * cs + 1: co + r * cs + 16: 2] = c[r, voff: voff + 8]
+        skip = torch.full((nfr, nper), 9, dtype=torch.uint8, device="cuda")
+        d_fenc, d_pred = torch.from_numpy(fenc.reshape(-1)).cuda(), torch.from_numpy(pred.reshape(-1)).cuda()
+        torch.cuda.synchronize()
+        ctx.probe_pskip_frames(g, d_fenc, d_pred, nfr, int(qp), skip)
+        ctx.sync()
+        assert np.array_equal(skip.cpu().numpy().reshape(-1), GI["pskip_skip"][qi][: nfr * nper]), f"qp {qp}"
