@@ -855,12 +855,80 @@ __device__ __forceinline__ void xd_lm_sad_dia( const xd_lm_block<RPL> &B, int mx
     }
 }
 
+// The four neighbours of the half-pel diamond (me.c:492-517) around (qx,qy).  In the lookahead every position is on the
+// half-pel grid -- the search is full-pel, the refinement half-pel only (subme 2), the predictors are medians of such
+// vectors -- so each candidate is one plane, no averaging: up / down are three consecutive rows of the plane that has
+// the other vertical phase, left / right two rows and nine columns of the plane with the other horizontal phase.
+// Anything else (never seen here, but the reference allows it) takes the general path.
+template<int RPL>
+__device__ __forceinline__ void xd_lm_sad_hpel_dia( const xd_lm_block<RPL> &B, int qx, int qy,
+                                                    uint32_t &up, uint32_t &dn, uint32_t &lf, uint32_t &rt );
+
 template<int RPL>
 __device__ __forceinline__ uint32_t xd_lm_sad_qpel( const xd_lm_block<RPL> &B, int qx, int qy )
 {
     uint2 p[RPL];
     xd_lm_fetch<RPL>( B, qx, qy, p );
     return xd_lm_sad<RPL>( B, p );
+}
+
+template<int RPL>
+__device__ __forceinline__ void xd_lm_sad_hpel_dia( const xd_lm_block<RPL> &B, int qx, int qy,
+                                                    uint32_t &up, uint32_t &dn, uint32_t &lf, uint32_t &rt )
+{
+    if( RPL != 2 || ( ( qx | qy ) & 1 ) )
+    {
+        up = xd_lm_sad_qpel<RPL>( B, qx, qy - 2 );
+        dn = xd_lm_sad_qpel<RPL>( B, qx, qy + 2 );
+        lf = xd_lm_sad_qpel<RPL>( B, qx - 2, qy );
+        rt = xd_lm_sad_qpel<RPL>( B, qx + 2, qy );
+        return;
+    }
+    if constexpr( RPL == 2 )
+    {
+        const int hx = ( qx >> 1 ) & 1, hy = ( qy >> 1 ) & 1;        // half-pel phase bits: plane = hx | hy << 1
+        const int jump = ( B.tw << 6 ) - 56;
+        {
+            // up / down: plane with the other vertical phase, rows R0 .. R0+2 at column X
+            const int X = B.X0 + ( qx >> 2 ), R0 = B.Y0 + ( ( qy - 2 ) >> 2 );
+            int off = ( hx | ( ( hy ^ 1 ) << 1 ) ) * B.tplane + ( ( ( R0 >> 3 ) * B.tw + ( X >> 3 ) ) << 6 ) + ( ( R0 & 7 ) << 3 );
+            const uint32_t sh = (uint32_t)X << 3;
+            const bool hi4 = ( X & 4 ) != 0;
+            uint2 c[3];
+#pragma unroll
+            for( int r = 0; r < 3; r++ )
+            {
+                const uint2 *w = (const uint2 *)( B.tref + off );
+                c[r] = xd_lm_assemble( __ldg( w ), __ldg( w + 8 ), sh, hi4 );
+                off += ( ( R0 + r ) & 7 ) == 7 ? jump : 8;
+            }
+            up = xd_lq_sad8( c[1], B.fenc[1], xd_lq_sad8( c[0], B.fenc[0], 0u ) );
+            dn = xd_lq_sad8( c[2], B.fenc[1], xd_lq_sad8( c[1], B.fenc[0], 0u ) );
+        }
+        {
+            // left / right: plane with the other horizontal phase, rows Y, Y+1, columns XL .. XL+8
+            const int XL = B.X0 + ( ( qx - 2 ) >> 2 ), Y = B.Y0 + ( qy >> 2 );
+            int off = ( ( hx ^ 1 ) | ( hy << 1 ) ) * B.tplane + ( ( ( Y >> 3 ) * B.tw + ( XL >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 );
+            const uint32_t sh = (uint32_t)XL << 3;
+            const bool hi4 = ( XL & 4 ) != 0;
+            uint32_t V[2][3];
+#pragma unroll
+            for( int r = 0; r < 2; r++ )
+            {
+                const uint2 *w = (const uint2 *)( B.tref + off );
+                const uint2 lo = __ldg( w ), hi = __ldg( w + 8 );
+                const uint32_t w0 = hi4 ? lo.y : lo.x, w1 = hi4 ? hi.x : lo.y, w2 = hi4 ? hi.y : hi.x, w3 = hi4 ? 0u : hi.y;
+                V[r][0] = __funnelshift_r( w0, w1, sh );
+                V[r][1] = __funnelshift_r( w1, w2, sh );
+                V[r][2] = __funnelshift_r( w2, w3, sh );
+                off += ( Y & 7 ) == 7 ? jump : 8;
+            }
+            lf = xd_lq_sad8( make_uint2( V[1][0], V[1][1] ), B.fenc[1], xd_lq_sad8( make_uint2( V[0][0], V[0][1] ), B.fenc[0], 0u ) );
+            const uint2 r0 = make_uint2( __funnelshift_r( V[0][0], V[0][1], 8 ), __funnelshift_r( V[0][1], V[0][2], 8 ) );
+            const uint2 r1 = make_uint2( __funnelshift_r( V[1][0], V[1][1], 8 ), __funnelshift_r( V[1][1], V[1][2], 8 ) );
+            rt = xd_lq_sad8( r1, B.fenc[1], xd_lq_sad8( r0, B.fenc[0], 0u ) );
+        }
+    }
 }
 
 // SATD 8x8 (pixel.c:294-335); whole warp executes, `on` gates the loads, every lane of a group gets the cost.
@@ -1230,8 +1298,10 @@ xd_la_multi_kernel( xd_la_args A, int n_inter, const int32_t *inter_pairs )
                 uint32_t w0 = 0, w1 = 0;
                 if( search )
                 {
-                    w0 = xd_lq_pack( xd_lm_sad_qpel<RPL>( B, qx, qy - 2 ), xd_lm_sad_qpel<RPL>( B, qx, qy + 2 ) );
-                    w1 = xd_lq_pack( xd_lm_sad_qpel<RPL>( B, qx - 2, qy ), xd_lm_sad_qpel<RPL>( B, qx + 2, qy ) );
+                    uint32_t su, sd, sl, sr;
+                    xd_lm_sad_hpel_dia<RPL>( B, qx, qy, su, sd, sl, sr );
+                    w0 = xd_lq_pack( su, sd );
+                    w1 = xd_lq_pack( sl, sr );
                     if( q < 4 )
                     {
                         const int dx = q == 2 ? -2 : q == 3 ? 2 : 0, dy = q == 0 ? -2 : q == 1 ? 2 : 0;
