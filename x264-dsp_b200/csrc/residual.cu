@@ -65,9 +65,10 @@ xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const in
         const int cA = ( 8 - dx ) * ( 8 - dy ), cB = dx * ( 8 - dy ), cC = ( 8 - dx ) * dy, cD = dx * dy;
         const uint8_t *s0 = fref + g.slot_chroma_off + g.chroma_origin
                           + (int64_t)( ( mb_y << 3 ) + y + ( mvy >> 3 ) ) * cs + ( mb_x << 4 ) + 2 * ( x + ( mvx >> 3 ) );
-        const uint8_t *s1 = s0 + cs;
-        const int u = ( cA * __ldg( s0 ) + cB * __ldg( s0 + 2 ) + cC * __ldg( s1 ) + cD * __ldg( s1 + 2 ) + 32 ) >> 6;
-        const int v = ( cA * __ldg( s0 + 1 ) + cB * __ldg( s0 + 3 ) + cC * __ldg( s1 + 1 ) + cD * __ldg( s1 + 3 ) + 32 ) >> 6;
+        // the four bytes U0 V0 U1 V1 of each of the two rows as one (unaligned) word instead of eight byte loads
+        const uint32_t r0 = xd_load4_unaligned( s0 ), r1 = xd_load4_unaligned( s0 + cs );
+        const int u = ( cA * (int)( r0 & 255 ) + cB * (int)( ( r0 >> 16 ) & 255 ) + cC * (int)( r1 & 255 ) + cD * (int)( ( r1 >> 16 ) & 255 ) + 32 ) >> 6;
+        const int v = ( cA * (int)( ( r0 >> 8 ) & 255 ) + cB * (int)( r0 >> 24 ) + cC * (int)( ( r1 >> 8 ) & 255 ) + cD * (int)( r1 >> 24 ) + 32 ) >> 6;
         *(uint16_t *)( pred + g.slot_chroma_off + g.chroma_origin + (int64_t)( ( mb_y << 3 ) + y ) * cs + ( mb_x << 4 ) + 2 * x )
             = (uint16_t)( u | ( v << 8 ) );
     }
