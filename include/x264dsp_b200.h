@@ -348,6 +348,20 @@ int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t 
                                        const uint8_t *mb_kind, const uint8_t *i4_modes, int16_t *levels,
                                        int16_t *luma_dc, uint8_t *nnz, int16_t *cbp, void *stream );
 
+/* ------------------------------------------------------------------ MV prediction (8(f) N2)
+ * x264_mb_predict_mv_16x16 (common/mvpred.c:101-137) and x264_mb_predict_mv_pskip (mvpred.c:139-155) for n
+ * macroblocks: the median / single-match / left-only rules over the neighbours h->mb.cache holds around X264_SCAN8_0,
+ * and the P_SKIP vector (zero when a neighbour is missing or is a zero-vector reference-0 block).
+ *   ref[k], mv[k]: A = left, B = top, C = top-right, D = top-left; ref -2 = not available, -1 = intra, >= 0 = index.
+ * mvp[i] is the prediction for reference i_ref[i] (i_ref == NULL: reference 0 everywhere); either output may be NULL. */
+typedef struct x264dsp_mv_neighbours
+{
+    int8_t  ref[4];
+    int16_t mv[4][2];
+} x264dsp_mv_neighbours_t;
+int x264dsp_predict_mv_batch_dev( x264dsp_ctx_t *ctx, int n, const x264dsp_mv_neighbours_t *nb, const int8_t *i_ref,
+                                  int16_t *mvp, int16_t *pskip_mv, void *stream );
+
 /* x264_macroblock_probe_pskip (encoder/macroblock.c:492-604) for every macroblock of n_frames frames: pred_slots hold
  * the P_SKIP prediction of each macroblock (x264dsp_mc_frames_dev at the clipped pskip MVs -- the function's own
  * mc_luma / mc_chroma calls), fenc_slots the source; skip[frame][mb] = 1 when the reference would return 1 (luma

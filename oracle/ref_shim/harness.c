@@ -631,6 +631,23 @@ int xref_probe_pskip_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c,
     return r;
 }
 
+/* x264_mb_predict_mv_16x16 / x264_mb_predict_mv_pskip (common/mvpred.c:101-155) on a caller-supplied neighbourhood:
+ * ref[4] / mv[4][2] = left, top, top-right, top-left as they sit in h->mb.cache around X264_SCAN8_0 */
+void xref_predict_mv( void *hv, const int8_t *ref, const int16_t *mv, int i_ref, int16_t *mvp, int16_t *pskip )
+{
+    x264_t *h = hv;
+    static const int cell[4] = { X264_SCAN8_0 - 1, X264_SCAN8_0 - 8, X264_SCAN8_0 - 8 + 4, X264_SCAN8_0 - 8 - 1 };
+    int k;
+    for( k = 0; k < 4; k++ )
+    {
+        h->mb.cache.ref[0][cell[k]] = ref[k];
+        h->mb.cache.mv[0][cell[k]][0] = mv[2*k];
+        h->mb.cache.mv[0][cell[k]][1] = mv[2*k+1];
+    }
+    x264_mb_predict_mv_16x16( h, 0, i_ref, mvp );
+    x264_mb_predict_mv_pskip( h, pskip );
+}
+
 /* ------------------------------------------------------------------ timing helpers
  * (cpu_baseline / --impl reference): loops over the reference functions with the
  * input already in memory; CLOCK_MONOTONIC around the loop; returns seconds. */

@@ -1,0 +1,52 @@
+/* xo_mvpred.c -- oracle: motion-vector prediction of a 16x16 partition and the P_SKIP vector.
+ * TEST INFRASTRUCTURE ONLY (see xo.h).
+ *
+ * common/mvpred.c:101-137 (x264_mb_predict_mv_16x16), 139-155 (x264_mb_predict_mv_pskip),
+ * common/common.h:247-261 (x264_median_mv).  The neighbours are what h->mb.cache holds around X264_SCAN8_0:
+ * A = left (-1), B = top (-8), C = top-right (-8+4), D = top-left (-8-1); ref -2 = not available, -1 = intra. */
+#include "xo.h"
+
+/* the middle one of three (x264_median, common.h:247-255, is the branch-free form of the same) */
+static int median3( int a, int b, int c )
+{
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    return c < lo ? lo : c > hi ? hi : c;
+}
+
+void xo_predict_mv_16x16( const x264dsp_mv_neighbours_t *nb, int i_ref, int16_t mvp[2] )
+{
+    int refa = nb->ref[0], refb = nb->ref[1], refc = nb->ref[2];
+    const int16_t *mva = nb->mv[0], *mvb = nb->mv[1], *mvc = nb->mv[2];
+    int count;
+    if( refc == -2 )                                   /* no top-right macroblock: the top-left one stands in */
+    {
+        refc = nb->ref[3];
+        mvc = nb->mv[3];
+    }
+    count = ( refa == i_ref ) + ( refb == i_ref ) + ( refc == i_ref );
+    if( count == 1 )
+    {
+        const int16_t *m = refa == i_ref ? mva : refb == i_ref ? mvb : mvc;
+        mvp[0] = m[0]; mvp[1] = m[1];
+    }
+    else if( count == 0 && refb == -2 && refc == -2 && refa != -2 )
+    {
+        mvp[0] = mva[0]; mvp[1] = mva[1];
+    }
+    else
+    {
+        mvp[0] = (int16_t)median3( mva[0], mvb[0], mvc[0] );
+        mvp[1] = (int16_t)median3( mva[1], mvb[1], mvc[1] );
+    }
+}
+
+void xo_predict_mv_pskip( const x264dsp_mv_neighbours_t *nb, int16_t mv[2] )
+{
+    const int refa = nb->ref[0], refb = nb->ref[1];
+    if( refa == -2 || refb == -2
+        || ( refa == 0 && nb->mv[0][0] == 0 && nb->mv[0][1] == 0 )
+        || ( refb == 0 && nb->mv[1][0] == 0 && nb->mv[1][1] == 0 ) )
+        mv[0] = mv[1] = 0;
+    else
+        xo_predict_mv_16x16( nb, 0, mv );
+}

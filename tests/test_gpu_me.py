@@ -117,3 +117,33 @@ def test_me_search_1080p_tiling(pkg, ctx):
         ctx.sync()
         got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)[keep]
         assert np.array_equal(got, want), f"sized, size {size}: {np.count_nonzero(got != want)} of {len(sub)} differ"
+
+
+def test_predict_mv_batch(pkg, ctx):
+    """x264_mb_predict_mv_16x16 / x264_mb_predict_mv_pskip for a batch of neighbourhoods against the oracle (pinned to the
+    reference's functions, tests/test_oracle_vs_ref.py::test_predict_mv_16x16_and_pskip)"""
+    import torch
+    o = cc.oracle()
+    rng = np.random.RandomState(162)
+    n = 20000
+    ref = rng.choice([-2, -1, 0, 0, 0, 1], (n, 4)).astype(np.int8)
+    mv = rng.randint(-40, 41, (n, 4, 2)).astype(np.int16)
+    mv[rng.rand(n, 4) < 0.25] = 0
+    same = rng.rand(n) < 0.2
+    mv[same] = mv[same][:, :1]
+    i_ref = rng.choice([0, 0, 1], n).astype(np.int8)
+    nb = np.zeros((n, 20), np.uint8)
+    nb[:, :4] = ref.view(np.uint8)
+    nb[:, 4:] = mv.view(np.uint8).reshape(n, 16)
+    want_p, want_s = np.zeros((n, 2), np.int16), np.zeros((n, 2), np.int16)
+    for i in range(n):
+        o.xo_predict_mv_16x16(cc.ptr(nb[i]), int(i_ref[i]), cc.ptr(want_p[i], cc.i16p))
+        o.xo_predict_mv_pskip(cc.ptr(nb[i]), cc.ptr(want_s[i], cc.i16p))
+    d_p = torch.full((n, 2), 77, dtype=torch.int16, device="cuda")
+    d_s = torch.full((n, 2), 77, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    ctx.predict_mv_batch(n, torch.from_numpy(nb).cuda(), torch.from_numpy(i_ref).cuda(), d_p, d_s)
+    ctx.sync()
+    assert np.array_equal(d_p.cpu().numpy(), want_p), "mvp"
+    assert np.array_equal(d_s.cpu().numpy(), want_s), "pskip mv"
+    assert (want_s == 0).all(1).any() and (want_s != 0).any()

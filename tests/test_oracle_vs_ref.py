@@ -645,3 +645,27 @@ def test_probe_pskip_mb(enc, qp):
         assert r1 == r2, f"trial {trial}: reference {r1} oracle {r2}"
         seen[r1] += 1
     assert seen[0] > 20 and seen[1] > 20, seen
+
+
+def test_predict_mv_16x16_and_pskip(enc):
+    """x264_mb_predict_mv_16x16 / x264_mb_predict_mv_pskip on random neighbourhoods (every availability pattern, equal and
+    different references, zero vectors) against the oracle"""
+    o = cc.oracle()
+    rng = np.random.RandomState(161)
+    for trial in range(4000):
+        ref = rng.choice([-2, -1, 0, 0, 0, 1], 4).astype(np.int8)
+        mv = rng.randint(-40, 41, (4, 2)).astype(np.int16)
+        mv[rng.rand(4) < 0.25] = 0
+        if trial % 5 == 0:
+            mv[:] = mv[0]
+        i_ref = int(rng.choice([0, 0, 1]))
+        a, b = np.zeros(2, np.int16), np.zeros(2, np.int16)
+        enc.lib.xref_predict_mv(enc.h, ptr(ref, i8p), ptr(mv, i16p), i_ref, ptr(a, i16p), ptr(b, i16p))
+        nb = np.zeros(20, np.uint8)
+        nb[:4] = ref.view(np.uint8)
+        nb[4:] = mv.view(np.uint8).reshape(-1)
+        c, d = np.zeros(2, np.int16), np.zeros(2, np.int16)
+        o.xo_predict_mv_16x16(ptr(nb), i_ref, ptr(c, i16p))
+        o.xo_predict_mv_pskip(ptr(nb), ptr(d, i16p))
+        assert np.array_equal(a, c), f"mvp trial {trial}: ref {ref} mv {mv.tolist()} i_ref {i_ref}: {a} vs {c}"
+        assert np.array_equal(b, d), f"pskip trial {trial}: ref {ref} mv {mv.tolist()}: {b} vs {d}"

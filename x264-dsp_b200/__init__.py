@@ -405,6 +405,13 @@ class Context:
                                                       _dp(luma_dc) if luma_dc is not None else None, _dp(nnz), _dp(cbp), None),
               "x264dsp_residual_frames_typed_dev")
 
+    def predict_mv_batch(self, n, nb, i_ref, mvp, pskip_mv):
+        """nb: uint8[n][20] = {int8 ref[4], int16 mv[4][2]} (left, top, top-right, top-left); outputs int16[n][2]"""
+        check(lib().x264dsp_predict_mv_batch_dev(self._h, int(n), _dp(nb), _dp(i_ref) if i_ref is not None else None,
+                                                 _dp(mvp) if mvp is not None else None,
+                                                 _dp(pskip_mv) if pskip_mv is not None else None, None),
+              "x264dsp_predict_mv_batch_dev")
+
     def probe_pskip_frames(self, g, fenc_slots, pred_slots, n_frames, qp, skip):
         check(lib().x264dsp_probe_pskip_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
                                                    int(qp), _dp(skip), None), "x264dsp_probe_pskip_frames_dev")
