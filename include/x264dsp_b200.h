@@ -353,14 +353,18 @@ int x264dsp_residual_frames_typed_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t 
  * macroblocks: the median / single-match / left-only rules over the neighbours h->mb.cache holds around X264_SCAN8_0,
  * and the P_SKIP vector (zero when a neighbour is missing or is a zero-vector reference-0 block).
  *   ref[k], mv[k]: A = left, B = top, C = top-right, D = top-left; ref -2 = not available, -1 = intra, >= 0 = index.
- * mvp[i] is the prediction for reference i_ref[i] (i_ref == NULL: reference 0 everywhere); either output may be NULL. */
+ * mvp[i] is the prediction for reference i_ref[i] (i_ref == NULL: reference 0 everywhere); either output may be NULL.
+ * shape[i] (NULL: all 0) selects the partition rule of x264_mb_predict_mv (mvpred.c:22-99): 0 = 16x16 or 8x8 (the
+ * rules above), 1 / 2 = upper / lower 16x8 (B resp. A wins outright when it uses i_ref), 3 / 4 = left / right 8x16 (A
+ * resp. C); + 8 when the partition's top-right block comes later in scan order, so that D stands in for C.  The
+ * neighbours are then those of the partition (the cells around x264_scan8[idx]). */
 typedef struct x264dsp_mv_neighbours
 {
     int8_t  ref[4];
     int16_t mv[4][2];
 } x264dsp_mv_neighbours_t;
 int x264dsp_predict_mv_batch_dev( x264dsp_ctx_t *ctx, int n, const x264dsp_mv_neighbours_t *nb, const int8_t *i_ref,
-                                  int16_t *mvp, int16_t *pskip_mv, void *stream );
+                                  const uint8_t *shape, int16_t *mvp, int16_t *pskip_mv, void *stream );
 
 /* x264_macroblock_probe_pskip (encoder/macroblock.c:492-604) for every macroblock of n_frames frames: pred_slots hold
  * the P_SKIP prediction of each macroblock (x264dsp_mc_frames_dev at the clipped pskip MVs -- the function's own

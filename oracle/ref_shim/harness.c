@@ -648,6 +648,27 @@ void xref_predict_mv( void *hv, const int8_t *ref, const int16_t *mv, int i_ref,
     x264_mb_predict_mv_pskip( h, pskip );
 }
 
+/* x264_mb_predict_mv (common/mvpred.c:22) for partition `idx` of width `i_width` (in 4-pixel units) of a macroblock
+ * whose partition type is `partition` (D_16x8 / D_8x16 / D_8x8 / D_16x16): the neighbours go into the cache cells the
+ * function reads -- left, top, top-right, top-left of x264_scan8[idx] -- and the partition's own reference into its cell */
+void xref_predict_mv_part( void *hv, const int8_t *ref, const int16_t *mv, int i_ref, int partition, int idx, int i_width,
+                           int16_t *mvp )
+{
+    x264_t *h = hv;
+    const int i8 = x264_scan8[idx];
+    const int cell[4] = { i8 - 1, i8 - 8, i8 - 8 + i_width, i8 - 8 - 1 };
+    int k;
+    for( k = 0; k < 4; k++ )
+    {
+        h->mb.cache.ref[0][cell[k]] = ref[k];
+        h->mb.cache.mv[0][cell[k]][0] = mv[2*k];
+        h->mb.cache.mv[0][cell[k]][1] = mv[2*k+1];
+    }
+    h->mb.cache.ref[0][i8] = (int8_t)i_ref;
+    h->mb.i_partition = partition;
+    x264_mb_predict_mv( h, 0, idx, i_width, mvp );
+}
+
 /* ------------------------------------------------------------------ timing helpers
  * (cpu_baseline / --impl reference): loops over the reference functions with the
  * input already in memory; CLOCK_MONOTONIC around the loop; returns seconds. */

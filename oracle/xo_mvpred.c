@@ -13,6 +13,32 @@ static int median3( int a, int b, int c )
     return c < lo ? lo : c > hi ? hi : c;
 }
 
+/* x264_mb_predict_mv (mvpred.c:22-99) for the partitions the reference analyses.  shape: 0 = 16x16 or 8x8 (median
+ * rules only), 1 / 2 = upper / lower 16x8 (B resp. A wins outright when it uses the same reference), 3 / 4 = left /
+ * right 8x16 (A resp. C).  c_unreachable: the partition's top-right block comes later in scan order
+ * ((idx&3) >= 2 + (i_width&1) in the reference), so D stands in for C like for a missing macroblock. */
+void xo_predict_mv_part( const x264dsp_mv_neighbours_t *nb, int i_ref, int shape, int c_unreachable, int16_t mvp[2] )
+{
+    x264dsp_mv_neighbours_t v = *nb;
+    if( c_unreachable )
+        v.ref[2] = -2;
+    {
+        const int refc = v.ref[2] == -2 ? v.ref[3] : v.ref[2];
+        const int16_t *mvc = v.ref[2] == -2 ? v.mv[3] : v.mv[2];
+        const int16_t *win = NULL;
+        if( shape == 1 && v.ref[1] == i_ref ) win = v.mv[1];
+        if( shape == 2 && v.ref[0] == i_ref ) win = v.mv[0];
+        if( shape == 3 && v.ref[0] == i_ref ) win = v.mv[0];
+        if( shape == 4 && refc == i_ref )     win = mvc;
+        if( win )
+        {
+            mvp[0] = win[0]; mvp[1] = win[1];
+            return;
+        }
+    }
+    xo_predict_mv_16x16( &v, i_ref, mvp );
+}
+
 void xo_predict_mv_16x16( const x264dsp_mv_neighbours_t *nb, int i_ref, int16_t mvp[2] )
 {
     int refa = nb->ref[0], refb = nb->ref[1], refc = nb->ref[2];

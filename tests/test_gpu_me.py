@@ -135,15 +135,24 @@ def test_predict_mv_batch(pkg, ctx):
     nb = np.zeros((n, 20), np.uint8)
     nb[:, :4] = ref.view(np.uint8)
     nb[:, 4:] = mv.view(np.uint8).reshape(n, 16)
+    shape = (rng.randint(0, 5, n) + 8 * (rng.rand(n) < 0.3)).astype(np.uint8)
     want_p, want_s = np.zeros((n, 2), np.int16), np.zeros((n, 2), np.int16)
     for i in range(n):
-        o.xo_predict_mv_16x16(cc.ptr(nb[i]), int(i_ref[i]), cc.ptr(want_p[i], cc.i16p))
+        o.xo_predict_mv_part(cc.ptr(nb[i]), int(i_ref[i]), int(shape[i] & 7), int(shape[i] >> 3), cc.ptr(want_p[i], cc.i16p))
         o.xo_predict_mv_pskip(cc.ptr(nb[i]), cc.ptr(want_s[i], cc.i16p))
     d_p = torch.full((n, 2), 77, dtype=torch.int16, device="cuda")
     d_s = torch.full((n, 2), 77, dtype=torch.int16, device="cuda")
     torch.cuda.synchronize()
-    ctx.predict_mv_batch(n, torch.from_numpy(nb).cuda(), torch.from_numpy(i_ref).cuda(), d_p, d_s)
+    ctx.predict_mv_batch(n, torch.from_numpy(nb).cuda(), torch.from_numpy(i_ref).cuda(), d_p, d_s, shape=torch.from_numpy(shape).cuda())
     ctx.sync()
-    assert np.array_equal(d_p.cpu().numpy(), want_p), "mvp"
+    bad = np.nonzero((d_p.cpu().numpy() != want_p).any(1))[0]
+    assert len(bad) == 0, f"mvp differs at {bad[:5]}: shape {shape[bad[:5]]} ref {ref[bad[:5]].tolist()}"
+    d_p.fill_(77)
+    ctx.predict_mv_batch(n, torch.from_numpy(nb).cuda(), None, d_p, None)          # defaults: reference 0, shape 0
+    ctx.sync()
+    w0 = np.zeros((n, 2), np.int16)
+    for i in range(0, n, 7):
+        o.xo_predict_mv_16x16(cc.ptr(nb[i]), 0, cc.ptr(w0[i], cc.i16p))
+        assert np.array_equal(d_p[i].cpu().numpy(), w0[i]), f"default path, macroblock {i}"
     assert np.array_equal(d_s.cpu().numpy(), want_s), "pskip mv"
     assert (want_s == 0).all(1).any() and (want_s != 0).any()

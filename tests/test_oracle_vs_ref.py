@@ -669,3 +669,28 @@ def test_predict_mv_16x16_and_pskip(enc):
         o.xo_predict_mv_pskip(ptr(nb), ptr(d, i16p))
         assert np.array_equal(a, c), f"mvp trial {trial}: ref {ref} mv {mv.tolist()} i_ref {i_ref}: {a} vs {c}"
         assert np.array_equal(b, d), f"pskip trial {trial}: ref {ref} mv {mv.tolist()}: {b} vs {d}"
+
+
+def test_predict_mv_partitions(enc):
+    """x264_mb_predict_mv for every partition shape the reference analyses (16x16, 16x8 upper / lower, 8x16 left / right,
+    the four 8x8s) against the oracle's shape / c_unreachable formulation"""
+    o = cc.oracle()
+    rng = np.random.RandomState(163)
+    # (partition type, idx, width in 4-pixel units, oracle shape)
+    cases = [(16, 0, 4, 0), (14, 0, 4, 1), (14, 8, 4, 2), (15, 0, 2, 3), (15, 4, 2, 4),
+             (13, 0, 2, 0), (13, 4, 2, 0), (13, 8, 2, 0), (13, 12, 2, 0)]
+    for trial in range(6000):
+        part, idx, width, shape = cases[trial % len(cases)]
+        ref = rng.choice([-2, -1, 0, 0, 0, 1], 4).astype(np.int8)
+        mv = rng.randint(-40, 41, (4, 2)).astype(np.int16)
+        mv[rng.rand(4) < 0.2] = 0
+        i_ref = int(rng.choice([0, 0, 1]))
+        a = np.zeros(2, np.int16)
+        enc.lib.xref_predict_mv_part(enc.h, ptr(ref, i8p), ptr(mv, i16p), i_ref, part, idx, width, ptr(a, i16p))
+        nb = np.zeros(20, np.uint8)
+        nb[:4] = ref.view(np.uint8)
+        nb[4:] = mv.view(np.uint8).reshape(-1)
+        c_unreachable = int((idx & 3) >= 2 + (width & 1))
+        c = np.zeros(2, np.int16)
+        o.xo_predict_mv_part(ptr(nb), i_ref, shape, c_unreachable, ptr(c, i16p))
+        assert np.array_equal(a, c), f"trial {trial} case {cases[trial % len(cases)]}: ref {ref} mv {mv.tolist()} i_ref {i_ref}: {a} vs {c}"

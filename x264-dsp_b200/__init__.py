@@ -405,9 +405,11 @@ class Context:
                                                       _dp(luma_dc) if luma_dc is not None else None, _dp(nnz), _dp(cbp), None),
               "x264dsp_residual_frames_typed_dev")
 
-    def predict_mv_batch(self, n, nb, i_ref, mvp, pskip_mv):
-        """nb: uint8[n][20] = {int8 ref[4], int16 mv[4][2]} (left, top, top-right, top-left); outputs int16[n][2]"""
+    def predict_mv_batch(self, n, nb, i_ref, mvp, pskip_mv, shape=None):
+        """nb: uint8[n][20] = {int8 ref[4], int16 mv[4][2]} (left, top, top-right, top-left); outputs int16[n][2];
+        shape: uint8[n] partition rule (0 16x16 / 8x8, 1 / 2 16x8, 3 / 4 8x16, + 8: top-right not reachable)"""
         check(lib().x264dsp_predict_mv_batch_dev(self._h, int(n), _dp(nb), _dp(i_ref) if i_ref is not None else None,
+                                                 _dp(shape) if shape is not None else None,
                                                  _dp(mvp) if mvp is not None else None,
                                                  _dp(pskip_mv) if pskip_mv is not None else None, None),
               "x264dsp_predict_mv_batch_dev")

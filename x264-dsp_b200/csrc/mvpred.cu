@@ -43,6 +43,24 @@ __device__ __forceinline__ uint32_t xd_predict_mv_16x16( const x264dsp_mv_neighb
     return ( (uint32_t)x & 0xFFFFu ) | ( (uint32_t)y << 16 );
 }
 
+// x264_mb_predict_mv (mvpred.c:22-99): shape 0 = 16x16 / 8x8, 1 / 2 = upper / lower 16x8, 3 / 4 = left / right 8x16;
+// c_unreachable: the partition's top-right block comes later in scan order, D stands in for C
+__device__ __forceinline__ uint32_t xd_predict_mv_part( x264dsp_mv_neighbours_t nb, int i_ref, int shape, bool c_unreachable )
+{
+    if( c_unreachable )
+        nb.ref[2] = -2;
+    const bool use_d = nb.ref[2] == -2;
+    const int refc = use_d ? nb.ref[3] : nb.ref[2];
+    const int k = shape == 1 ? 1 : ( shape == 2 || shape == 3 ) ? 0 : 2;            // the neighbour that may win outright
+    const int refk = k == 2 ? refc : nb.ref[k];
+    if( shape != 0 && refk == i_ref )
+    {
+        const int kk = k == 2 && use_d ? 3 : k;
+        return ( (uint32_t)nb.mv[kk][0] & 0xFFFFu ) | ( (uint32_t)nb.mv[kk][1] << 16 );
+    }
+    return xd_predict_mv_16x16( nb, i_ref );
+}
+
 __device__ __forceinline__ uint32_t xd_predict_mv_pskip( const x264dsp_mv_neighbours_t &nb )
 {
     const int refa = nb.ref[0], refb = nb.ref[1];
@@ -53,7 +71,7 @@ __device__ __forceinline__ uint32_t xd_predict_mv_pskip( const x264dsp_mv_neighb
 
 __global__ void __launch_bounds__( 256 )
 xd_predict_mv_kernel( int n, const x264dsp_mv_neighbours_t *__restrict__ nb, const int8_t *__restrict__ i_ref,
-                      uint32_t *__restrict__ mvp, uint32_t *__restrict__ pskip )
+                      const uint8_t *__restrict__ shape, uint32_t *__restrict__ mvp, uint32_t *__restrict__ pskip )
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if( i >= n )
@@ -67,13 +85,16 @@ xd_predict_mv_kernel( int n, const x264dsp_mv_neighbours_t *__restrict__ nb, con
     x264dsp_mv_neighbours_t v;
     memcpy( &v, raw, sizeof( v ) );
     if( mvp )
-        mvp[i] = xd_predict_mv_16x16( v, i_ref ? i_ref[i] : 0 );
+    {
+        const int sh = shape ? shape[i] : 0;
+        mvp[i] = xd_predict_mv_part( v, i_ref ? i_ref[i] : 0, sh & 7, ( sh & 8 ) != 0 );
+    }
     if( pskip )
         pskip[i] = xd_predict_mv_pskip( v );
 }
 
 extern "C" int x264dsp_predict_mv_batch_dev( x264dsp_ctx_t *ctx, int n, const x264dsp_mv_neighbours_t *nb, const int8_t *i_ref,
-                                             int16_t *mvp, int16_t *pskip_mv, void *stream )
+                                             const uint8_t *shape, int16_t *mvp, int16_t *pskip_mv, void *stream )
 {
     if( !ctx || n < 0 || ( !mvp && !pskip_mv ) )
         return X264DSP_E_ARG;
@@ -81,7 +102,7 @@ extern "C" int x264dsp_predict_mv_batch_dev( x264dsp_ctx_t *ctx, int n, const x2
         return 0;
     if( !nb || ( (uintptr_t)nb & 3 ) || ( (uintptr_t)mvp & 3 ) || ( (uintptr_t)pskip_mv & 3 ) )
         return X264DSP_E_ARG;
-    xd_predict_mv_kernel<<<( n + 255 ) / 256, 256, 0, xd_stream( ctx, stream )>>>( n, nb, i_ref, (uint32_t *)mvp, (uint32_t *)pskip_mv );
+    xd_predict_mv_kernel<<<( n + 255 ) / 256, 256, 0, xd_stream( ctx, stream )>>>( n, nb, i_ref, shape, (uint32_t *)mvp, (uint32_t *)pskip_mv );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
