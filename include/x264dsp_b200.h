@@ -366,6 +366,18 @@ typedef struct x264dsp_mv_neighbours
 int x264dsp_predict_mv_batch_dev( x264dsp_ctx_t *ctx, int n, const x264dsp_mv_neighbours_t *nb, const int8_t *i_ref,
                                   const uint8_t *shape, int16_t *mvp, int16_t *pskip_mv, void *stream );
 
+/* x264_mb_predict_mv_ref16x16 (common/mvpred.c:167-219; list 0, reference 0) for every macroblock of n_frames frames:
+ * the candidate list of the 16x16 search -- the lookahead's MV doubled (lowres_mv[frame][mb][2], the MVs
+ * x264dsp_lookahead_frame_cost_dev writes; NULL or a first entry of 0x7fff: none), the 16x16 MVs of the left, top,
+ * top-left and top-right macroblocks (mvr[frame][mb][2] = h->mb.mvr[0][0]; outside the frame: (0,0)), and the reference
+ * frame's 16x16 MVs at the same, right and lower macroblock scaled by scale = (curpoc - refpoc) * inv_ref_poc
+ * ((mv * scale + 128) >> 8; l0_mv16 == NULL: the reference frame was intra, no temporal candidates).
+ *   mvc [frame][mb][9][2] int16 (entries beyond the count untouched), n_mvc [frame][mb] int32 (4 .. 8).
+ * The spatial candidates are the neighbours' FINAL vectors: a wavefront caller fills mvr as it goes. */
+int x264dsp_predict_mvc_16x16_frames_dev( x264dsp_ctx_t *ctx, int mb_w, int mb_h, int n_frames,
+                                          const int16_t *lowres_mv, const int16_t *mvr, const int16_t *l0_mv16,
+                                          int scale, int16_t *mvc, int32_t *n_mvc, void *stream );
+
 /* x264_macroblock_probe_pskip (encoder/macroblock.c:492-604) for every macroblock of n_frames frames: pred_slots hold
  * the P_SKIP prediction of each macroblock (x264dsp_mc_frames_dev at the clipped pskip MVs -- the function's own
  * mc_luma / mc_chroma calls), fenc_slots the source; skip[frame][mb] = 1 when the reference would return 1 (luma

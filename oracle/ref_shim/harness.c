@@ -669,6 +669,53 @@ void xref_predict_mv_part( void *hv, const int8_t *ref, const int16_t *mv, int i
     x264_mb_predict_mv( h, 0, idx, i_width, mvp );
 }
 
+/* x264_mb_predict_mv_ref16x16 (common/mvpred.c:167) for every macroblock of the encoder's frame size, on caller data:
+ * lowres_mv (or NULL), mvr = the current frame's 16x16 MVs, l0_mv16 (or NULL: intra reference frame), curpoc / refpoc /
+ * inv_ref_poc for the temporal scale.  Three scratch frames of the encoder carry the per-frame fields the function
+ * reads; the neighbour indices are set per macroblock the way x264_macroblock_cache_load_neighbours does for a
+ * single-slice frame (common/macroblock.c:304-367). */
+void xref_predict_mvc_frame( void *hv, void *fenc_v, void *fref_v, void *fdec_v, const int16_t *lowres_mv, const int16_t *mvr,
+                             const int16_t *l0_mv16, int curpoc, int refpoc, int inv_ref_poc, int16_t *mvc, int32_t *n_mvc )
+{
+    x264_t *h = hv;
+    x264_frame_t *fenc = fenc_v, *fref = fref_v, *fdec = fdec_v;
+    const int W = h->mb.i_mb_width, H = h->mb.i_mb_height, n = W * H;
+    x264_frame_t *keep_fenc = h->fenc, *keep_fref = h->fref[0][0], *keep_fdec = h->fdec;
+    int16_t (*keep_mvr)[2] = h->mb.mvr[0][0];
+    int16_t (*mvr_buf)[2] = malloc( ( n + 1 ) * 4 );
+    int x, y;
+    memset( mvr_buf, 0, 4 );
+    memcpy( mvr_buf + 1, mvr, n * 4 );
+    h->fenc = fenc; h->fref[0][0] = fref; h->fdec = fdec;
+    h->mb.mvr[0][0] = mvr_buf + 1;
+    h->frames.b_have_lowres = 1;
+    fenc->i_frame = 5; fref->i_frame = 4;                        /* idx = 0 <= i_bframe */
+    if( lowres_mv )
+        memcpy( fenc->lowres_mvs[0][0], lowres_mv, n * 4 );
+    else
+        fenc->lowres_mvs[0][0][0][0] = 0x7fff;
+    fref->i_ref[0] = l0_mv16 ? 1 : 0;
+    if( l0_mv16 )
+        memcpy( fref->mv16x16, l0_mv16, n * 4 );
+    fdec->i_poc = curpoc; fdec->i_delta_poc[0] = fdec->i_delta_poc[1] = 0;
+    fref->i_poc = refpoc; fref->i_delta_poc[0] = fref->i_delta_poc[1] = 0;
+    fref->inv_ref_poc[0] = fref->inv_ref_poc[1] = (int16_t)inv_ref_poc;
+    for( y = 0; y < H; y++ )
+        for( x = 0; x < W; x++ )
+        {
+            const int xy = y * W + x;
+            h->mb.i_mb_x = x; h->mb.i_mb_y = y; h->mb.i_mb_xy = xy;
+            h->mb.i_mb_left_xy[0] = x > 0 ? xy - 1 : -1;
+            h->mb.i_mb_top_xy = y > 0 ? xy - W : -1;
+            h->mb.i_mb_topleft_xy = ( x > 0 && y > 0 ) ? xy - W - 1 : -1;
+            h->mb.i_mb_topright_xy = ( y > 0 && x < W - 1 ) ? xy - W + 1 : -1;
+            x264_mb_predict_mv_ref16x16( h, 0, 0, (int16_t (*)[2])( mvc + (size_t)xy * 18 ), &n_mvc[xy] );
+        }
+    h->fenc = keep_fenc; h->fref[0][0] = keep_fref; h->fdec = keep_fdec;
+    h->mb.mvr[0][0] = keep_mvr;
+    free( mvr_buf );
+}
+
 /* ------------------------------------------------------------------ timing helpers
  * (cpu_baseline / --impl reference): loops over the reference functions with the
  * input already in memory; CLOCK_MONOTONIC around the loop; returns seconds. */

@@ -131,6 +131,8 @@ int xo_probe_pskip_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, const pixel
 void xo_probe_pskip_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *pred_slot, int qp, uint8_t *skip );
 void xo_predict_mv_16x16( const x264dsp_mv_neighbours_t *nb, int i_ref, int16_t mvp[2] );
 void xo_predict_mv_pskip( const x264dsp_mv_neighbours_t *nb, int16_t mv[2] );
+void xo_predict_mvc_16x16_frame( int mb_w, int mb_h, const int16_t *lowres_mv, const int16_t *mvr, const int16_t *l0_mv16,
+                                 int scale, int16_t *mvc, int32_t *n_mvc );
 void xo_predict_mv_part( const x264dsp_mv_neighbours_t *nb, int i_ref, int shape, int c_unreachable, int16_t mvp[2] );
 void xo_predict_4x4( int mode, pixel_t *src );
 int xo_encode_luma_i4x4( const pixel_t *fenc, pixel_t *fdec, int qp, const uint8_t modes[16], int replicate5,

@@ -76,3 +76,50 @@ void xo_predict_mv_pskip( const x264dsp_mv_neighbours_t *nb, int16_t mv[2] )
     else
         xo_predict_mv_16x16( nb, 0, mv );
 }
+
+/* x264_mb_predict_mv_ref16x16 (mvpred.c:167-219), list 0, reference 0, for every macroblock of a frame: the candidate
+ * list of the 16x16 search.
+ *   lowres_mv  [mb][2] the lookahead's MVs of this frame pair, or NULL / first entry 0x7fff when there are none
+ *              (doubled, mvpred.c:178-183)
+ *   mvr        [mb][2] the 16x16 MVs of the current frame's macroblocks (h->mb.mvr[0][0]); a neighbour outside the
+ *              frame contributes (0,0) -- the reference's index -1 (common/macroblock.c:87-89, 304-308)
+ *   l0_mv16    [mb][2] the 16x16 MVs of the reference frame for the temporal candidates, scaled by
+ *              scale = (curpoc - refpoc) * inv_ref_poc (mvpred.c:193-214); NULL: the reference frame was intra
+ * Out: mvc [mb][9][2] (unused entries untouched), n_mvc [mb]. */
+void xo_predict_mvc_16x16_frame( int mb_w, int mb_h, const int16_t *lowres_mv, const int16_t *mvr, const int16_t *l0_mv16,
+                                 int scale, int16_t *mvc, int32_t *n_mvc )
+{
+    int x, y, k;
+    for( y = 0; y < mb_h; y++ )
+        for( x = 0; x < mb_w; x++ )
+        {
+            const int xy = y * mb_w + x;
+            int16_t (*out)[2] = (int16_t (*)[2])( mvc + (size_t)xy * 18 );
+            int i = 0;
+            const int nb[4] = { x > 0 ? xy - 1 : -1, y > 0 ? xy - mb_w : -1, ( x > 0 && y > 0 ) ? xy - mb_w - 1 : -1,
+                                ( y > 0 && x < mb_w - 1 ) ? xy - mb_w + 1 : -1 };
+            if( lowres_mv && lowres_mv[0] != 0x7fff )
+            {
+                out[i][0] = (int16_t)( lowres_mv[2*xy] * 2 );
+                out[i][1] = (int16_t)( lowres_mv[2*xy+1] * 2 );
+                i++;
+            }
+            for( k = 0; k < 4; k++, i++ )
+            {
+                out[i][0] = nb[k] >= 0 ? mvr[2*nb[k]] : 0;
+                out[i][1] = nb[k] >= 0 ? mvr[2*nb[k]+1] : 0;
+            }
+            if( l0_mv16 )
+            {
+                const int t[3] = { xy, x < mb_w - 1 ? xy + 1 : -1, y < mb_h - 1 ? xy + mb_w : -1 };
+                for( k = 0; k < 3; k++ )
+                    if( t[k] >= 0 )
+                    {
+                        out[i][0] = (int16_t)( ( l0_mv16[2*t[k]] * scale + 128 ) >> 8 );
+                        out[i][1] = (int16_t)( ( l0_mv16[2*t[k]+1] * scale + 128 ) >> 8 );
+                        i++;
+                    }
+            }
+            n_mvc[xy] = i;
+        }
+}

@@ -156,3 +156,36 @@ def test_predict_mv_batch(pkg, ctx):
         assert np.array_equal(d_p[i].cpu().numpy(), w0[i]), f"default path, macroblock {i}"
     assert np.array_equal(d_s.cpu().numpy(), want_s), "pskip mv"
     assert (want_s == 0).all(1).any() and (want_s != 0).any()
+
+
+@pytest.mark.parametrize("mb_w,mb_h,nf", [(22, 18, 3), (120, 68, 2), (1, 1, 1), (13, 2, 2)])
+def test_predict_mvc_16x16_frames(pkg, ctx, mb_w, mb_h, nf):
+    """x264_mb_predict_mv_ref16x16 for whole frames against the oracle (pinned to the reference's function,
+    tests/test_oracle_vs_ref.py::test_predict_mvc_16x16_frame): with and without lookahead MVs / temporal candidates"""
+    import torch
+    o = cc.oracle()
+    rng = np.random.RandomState(mb_w * 7 + nf)
+    n = mb_w * mb_h
+    for variant in range(4):
+        lowres = rng.randint(-300, 301, (nf, n, 2)).astype(np.int16) if variant & 1 else None
+        if lowres is not None:
+            lowres[rng.rand(nf, n) < 0.2] = [-17000, 16500]
+            if nf > 1:
+                lowres[1, 0, 0] = 0x7FFF                         # this frame pair has not been analysed
+        mvr = rng.randint(-200, 201, (nf, n, 2)).astype(np.int16)
+        l0 = rng.randint(-200, 201, (nf, n, 2)).astype(np.int16) if variant & 2 else None
+        scale = [128, 256, 77, 385][variant]
+        want_c, want_n = np.full((nf, n, 9, 2), 999, np.int16), np.zeros((nf, n), np.int32)
+        for f in range(nf):
+            o.xo_predict_mvc_16x16_frame(mb_w, mb_h, cc.ptr(lowres[f], cc.i16p) if lowres is not None else None,
+                                         cc.ptr(mvr[f], cc.i16p), cc.ptr(l0[f], cc.i16p) if l0 is not None else None, scale,
+                                         cc.ptr(want_c[f], cc.i16p), cc.ptr(want_n[f], cc.i32p))
+        d_c = torch.full((nf, n, 9, 2), 999, dtype=torch.int16, device="cuda")
+        d_n = torch.zeros((nf, n), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.predict_mvc_16x16_frames(mb_w, mb_h, nf, torch.from_numpy(lowres).cuda() if lowres is not None else None,
+                                     torch.from_numpy(mvr).cuda(), torch.from_numpy(l0).cuda() if l0 is not None else None,
+                                     scale, d_c, d_n)
+        ctx.sync()
+        assert np.array_equal(d_n.cpu().numpy(), want_n), f"variant {variant}: counts"
+        assert np.array_equal(d_c.cpu().numpy(), want_c), f"variant {variant}: candidates"

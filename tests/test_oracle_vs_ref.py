@@ -694,3 +694,35 @@ def test_predict_mv_partitions(enc):
         c = np.zeros(2, np.int16)
         o.xo_predict_mv_part(ptr(nb), i_ref, shape, c_unreachable, ptr(c, i16p))
         assert np.array_equal(a, c), f"trial {trial} case {cases[trial % len(cases)]}: ref {ref} mv {mv.tolist()} i_ref {i_ref}: {a} vs {c}"
+
+
+def test_predict_mvc_16x16_frame(enc):
+    """x264_mb_predict_mv_ref16x16 for every macroblock of a frame (lowres candidate, the four spatial neighbours with
+    the frame-edge rule, the three scaled temporal candidates) against the oracle"""
+    o = cc.oracle()
+    lib = enc.lib
+    lib.xref_frame_new.restype = C.c_void_p
+    lib.xref_frame_new.argtypes = [C.c_void_p, C.c_int]
+    g = cc.oracle_geom(352, 288)
+    W, H, n = g.mb_w, g.mb_h, g.mb_count
+    fenc, fref, fdec = lib.xref_frame_new(enc.h, 0), lib.xref_frame_new(enc.h, 1), lib.xref_frame_new(enc.h, 1)
+    assert fenc and fref and fdec
+    rng = np.random.RandomState(164)
+    for trial in range(24):
+        lowres = rng.randint(-300, 301, (n, 2)).astype(np.int16) if trial % 3 else None
+        if lowres is not None and trial % 6 == 1:
+            lowres[rng.rand(n) < 0.3] = [-17000, 16500]          # doubling wraps in 16 bits
+        mvr = rng.randint(-200, 201, (n, 2)).astype(np.int16)
+        l0 = rng.randint(-200, 201, (n, 2)).astype(np.int16) if trial % 2 else None
+        curpoc, refpoc = 2 * (trial + 3), 2 * (trial + 2 - trial % 3)
+        inv = (256 + 1) // 2 if trial % 4 else 77
+        m1, m2 = np.full((n, 9, 2), 999, np.int16), np.full((n, 9, 2), 999, np.int16)
+        n1, n2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lib.xref_predict_mvc_frame(enc.h, C.c_void_p(fenc), C.c_void_p(fref), C.c_void_p(fdec),
+                                   ptr(lowres, i16p) if lowres is not None else None, ptr(mvr, i16p),
+                                   ptr(l0, i16p) if l0 is not None else None, curpoc, refpoc, inv, ptr(m1, i16p), ptr(n1, i32p))
+        o.xo_predict_mvc_16x16_frame(W, H, ptr(lowres, i16p) if lowres is not None else None, ptr(mvr, i16p),
+                                     ptr(l0, i16p) if l0 is not None else None, (curpoc - refpoc) * inv, ptr(m2, i16p), ptr(n2, i32p))
+        assert np.array_equal(n1, n2), f"trial {trial}: counts differ at {np.nonzero(n1 != n2)[0][:5]}: {n1[n1 != n2][:5]} vs {n2[n1 != n2][:5]}"
+        assert np.array_equal(m1, m2), f"trial {trial}: candidates differ at mb {np.nonzero((m1 != m2).any((1, 2)))[0][:5]}"
+        assert n1.min() >= 4 and n1.max() == 4 + (lowres is not None) + 3 * (l0 is not None)

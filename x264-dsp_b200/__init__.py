@@ -414,6 +414,12 @@ class Context:
                                                  _dp(pskip_mv) if pskip_mv is not None else None, None),
               "x264dsp_predict_mv_batch_dev")
 
+    def predict_mvc_16x16_frames(self, mb_w, mb_h, n_frames, lowres_mv, mvr, l0_mv16, scale, mvc, n_mvc):
+        check(lib().x264dsp_predict_mvc_16x16_frames_dev(self._h, int(mb_w), int(mb_h), int(n_frames),
+                                                         _dp(lowres_mv) if lowres_mv is not None else None, _dp(mvr),
+                                                         _dp(l0_mv16) if l0_mv16 is not None else None, int(scale),
+                                                         _dp(mvc), _dp(n_mvc), None), "x264dsp_predict_mvc_16x16_frames_dev")
+
     def probe_pskip_frames(self, g, fenc_slots, pred_slots, n_frames, qp, skip):
         check(lib().x264dsp_probe_pskip_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
                                                    int(qp), _dp(skip), None), "x264dsp_probe_pskip_frames_dev")
