@@ -46,7 +46,11 @@ enum
 };
 
 enum { X264DSP_CMP_SAD = 0, X264DSP_CMP_SSD = 1, X264DSP_CMP_SATD = 2 };
-enum { X264DSP_ME_DIA = 0, X264DSP_ME_HEX = 1 };          /* common/x264.h:117-118 */
+/* common/x264.h:117-121.  DIA and HEX are the two pattern searches of this reference; UMH, ESA and TESA pass its
+ * parameter check (encoder/encoder.c:251-259) but have no case in x264_me_search_ref's switch (encoder/me.c:389-394),
+ * so they evaluate the predictors and go straight to the sub-pel refinement -- which is what this library does too;
+ * TESA with subme >= 2 also makes the full-pel metric SATD (mbcmp_init, encoder/encoder.c:429-432). */
+enum { X264DSP_ME_DIA = 0, X264DSP_ME_HEX = 1, X264DSP_ME_UMH = 2, X264DSP_ME_ESA = 3, X264DSP_ME_TESA = 4 };
 
 #define X264DSP_PADH 32                                   /* common/frame.h:9-10 */
 #define X264DSP_PADV 32
@@ -100,6 +104,8 @@ const char *x264dsp_version( void );
  * (encoder/analyse.c:98-111, 171-206, 243-315; common/set.c:265-353; common/macroblock.h:251-266) */
 int x264dsp_lambda( int qp );
 int x264dsp_cost_mv_table( int qp, uint16_t out8193[8193] );           /* index i+4096 <-> mv delta i */
+/* the context's DEVICE copy of cost_mv[qp] (the table the search kernels index), read back to the host */
+int x264dsp_cost_mv_table_dev( x264dsp_ctx_t *ctx, int qp, uint16_t out8193[8193] );
 int x264dsp_quant_tables( int b_inter, int qp, uint16_t mf[16], uint16_t bias[16] );
 int x264dsp_dequant_table( int out[6][16] );
 int x264dsp_chroma_qp( int qp );
@@ -274,7 +280,7 @@ typedef struct x264dsp_me_result
 
 typedef struct x264dsp_me_params
 {
-    int32_t me_method;                     /* h->mb.i_me_method: X264DSP_ME_DIA / _HEX */
+    int32_t me_method;                     /* h->mb.i_me_method: X264DSP_ME_DIA .. _TESA */
     int32_t subpel_refine;                 /* h->mb.i_subpel_refine, 1..5 */
     int32_t me_range;                      /* h->param.analyse.i_me_range */
     int32_t qp;                            /* selects cost_mv[qp] */
@@ -286,6 +292,23 @@ int x264dsp_me_search_batch_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
                                  const x264dsp_me_params_t *params, int n,
                                  const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
                                  void *stream );
+
+/* The other two callers of refine_subpel, and x264_me_search_ref with a non-NULL p_halfpel_thresh
+ * (encoder/me.h:40-44, me.c:129, 426-440, 526-539; used by x264_mb_analyse_inter_p16x16 when several references are
+ * searched, encoder/analyse.c:792-820):
+ *   mode X264DSP_ME_MODE_SEARCH       x264_me_search_ref( h, m, mvc, i_mvc, p_halfpel_thresh )
+ *   mode X264DSP_ME_MODE_REFDUPE      x264_me_refine_qpel_refdupe( h, m, p_halfpel_thresh ): results[i] holds m->mv,
+ *                                     m->cost and m->cost_mv on entry and the refined values on return
+ *   mode X264DSP_ME_MODE_REFINE_QPEL  x264_me_refine_qpel( h, m ) alone, results[i] in/out; the caller has already
+ *                                     subtracted m->i_ref_cost for sizes <= 8x8 (me.c:431-432)
+ * halfpel_thresh: device array [n], *p_halfpel_thresh of each block, read and updated (NULL = the reference's NULL).
+ * When the early exit of me.c:529-536 fires, mv and cost are stored and cost_mv keeps its previous value. */
+enum { X264DSP_ME_MODE_SEARCH = 0, X264DSP_ME_MODE_REFDUPE = 1, X264DSP_ME_MODE_REFINE_QPEL = 2 };
+int x264dsp_me_search_batch_ex_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                    const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                                    const x264dsp_me_params_t *params, int n,
+                                    const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                    int mode, int32_t *halfpel_thresh, void *stream );
 
 /* Same search for a list whose blocks all have partition size i_pixel (blocks[k].i_pixel is ignored):
  * the kernel is specialised on the size and packs 4 .. 32 blocks into a warp (one lane per 8x4 / 4x4
@@ -420,6 +443,13 @@ int x264dsp_deblock_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uin
  * nnz [n][120], ref [n][2][40], mv [n][2][40][2] -> bs [n][2][8][4] (scan8 layout). */
 int x264dsp_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const uint8_t *nnz, const int8_t *ref,
                                   const int16_t *mv, uint8_t *bs, void *stream );
+
+/* x264_macroblock_deblock_strength (common/macroblock.c:677-691) for n macroblocks: an intra macroblock (mb_type[i]
+ * = I_4x4 .. I_PCM = 0 .. 3, common/macroblock.h:41-52) gets bS 3 on its three inner edges in both directions and its
+ * bs[dir][0] is left as it was (x264_frame_deblock_row filters the outer edges of an intra macroblock with bS 4 whatever
+ * is stored); every other macroblock goes through deblock_strength_c as above.  mb_type == NULL: all inter. */
+int x264dsp_macroblock_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const int8_t *mb_type, const uint8_t *nnz,
+                                             const int8_t *ref, const int16_t *mv, uint8_t *bs, void *stream );
 
 #ifdef __cplusplus
 }

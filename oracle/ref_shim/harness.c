@@ -278,8 +278,21 @@ typedef struct
  * fenc: any frame (source samples from plane[0]); fref: an fdec frame whose
  * filtered[0][0..3] planes have been produced by xref_frame_filter_all.
  * refine != 0 additionally runs x264_me_refine_qpel on each result (me.c:426). */
+void xref_me_search_batch_ex( void *hv, void *fencv, void *frefv, int qp, int me_method, int subme,
+                              int me_range, int refine, const xref_me_in_t *in, int n, xref_me_out_t *out,
+                              int mode, int *thresh );
 void xref_me_search_batch( void *hv, void *fencv, void *frefv, int qp, int me_method, int subme,
                            int me_range, int refine, const xref_me_in_t *in, int n, xref_me_out_t *out )
+{
+    xref_me_search_batch_ex( hv, fencv, frefv, qp, me_method, subme, me_range, refine, in, n, out, 0, NULL );
+}
+
+/* mode 0: x264_me_search_ref with p_halfpel_thresh = &thresh[i] (thresh == NULL: NULL);
+ * mode 1: x264_me_refine_qpel_refdupe (me.c:437) and mode 2: x264_me_refine_qpel (me.c:426), both starting
+ * from the mv / cost / cost_mv found in out[i]. */
+void xref_me_search_batch_ex( void *hv, void *fencv, void *frefv, int qp, int me_method, int subme,
+                              int me_range, int refine, const xref_me_in_t *in, int n, xref_me_out_t *out,
+                              int mode, int *thresh )
 {
     x264_t *h = hv;
     x264_frame_t *fenc = fencv, *fref = frefv;
@@ -321,9 +334,23 @@ void xref_me_search_batch( void *hv, void *fencv, void *frefv, int qp, int me_me
         m.mvp[0] = in[i].mvp[0];
         m.mvp[1] = in[i].mvp[1];
         memcpy( mvc, in[i].mvc, sizeof(mvc) );
-        x264_me_search_ref( h, &m, mvc, in[i].i_mvc, NULL );
-        if( refine )
-            x264_me_refine_qpel( h, &m );
+        if( mode )
+        {
+            m.mv[0] = out[i].mv[0];
+            m.mv[1] = out[i].mv[1];
+            m.cost = out[i].cost;
+            m.cost_mv = out[i].cost_mv;
+            if( mode == 1 )
+                x264_me_refine_qpel_refdupe( h, &m, thresh ? &thresh[i] : NULL );
+            else
+                x264_me_refine_qpel( h, &m );
+        }
+        else
+        {
+            x264_me_search_ref( h, &m, mvc, in[i].i_mvc, thresh ? &thresh[i] : NULL );
+            if( refine )
+                x264_me_refine_qpel( h, &m );
+        }
         out[i].mv[0] = m.mv[0];
         out[i].mv[1] = m.mv[1];
         out[i].cost = m.cost;
@@ -333,6 +360,21 @@ void xref_me_search_batch( void *hv, void *fencv, void *frefv, int qp, int me_me
 }
 
 /* ------------------------------------------------------------------ deblock */
+
+/* x264_macroblock_deblock_strength (common/macroblock.c:677) on a caller-filled cache; bs is read and written */
+void xref_macroblock_deblock_strength( void *hv, int mb_type, const uint8_t *nnz, const int8_t *ref, const int16_t *mv,
+                                       uint8_t *bs )
+{
+    x264_t *h = hv;
+    uint8_t (*keep)[8][4] = h->mb.cache.deblock_strength;
+    h->mb.i_type = mb_type;
+    memcpy( h->mb.cache.non_zero_count, nnz, sizeof(h->mb.cache.non_zero_count) );
+    memcpy( h->mb.cache.ref, ref, sizeof(h->mb.cache.ref) );
+    memcpy( h->mb.cache.mv, mv, sizeof(h->mb.cache.mv) );
+    h->mb.cache.deblock_strength = (uint8_t (*)[8][4])bs;
+    x264_macroblock_deblock_strength( h );
+    h->mb.cache.deblock_strength = keep;
+}
 
 /* x264_frame_deblock_row (common/deblock.c:341) over every MB row of frame f.
  * mb_type/partition/cbp: per-MB arrays (raster); bs: [mb][2][8][4] as produced by

@@ -33,6 +33,12 @@ xref_frame_cb xref_hook_lowres = NULL, xref_hook_filter = NULL;
 xref_cost_cb xref_hook_cost = NULL;
 xref_fdec_cb xref_hook_fdec = NULL;
 int xref_hook_calls[3] = { 0, 0, 0 };
+/* per door { calls that entered with the hook installed, of those eligible for the device (main-encode calls the
+ * door is meant for), of those served by the device }: the test requires served == eligible -- no silent fallback */
+enum { XREF_DOOR_ME = 0, XREF_DOOR_MBENC, XREF_DOOR_PSKIP, XREF_DOOR_MBMC, XREF_DOORS };
+int xref_door_stats[XREF_DOORS][3];
+void xref_door_stats_read( int out[XREF_DOORS * 3] ) { memcpy( out, xref_door_stats, sizeof(xref_door_stats) ); }
+void xref_door_stats_reset( void ) { memset( xref_door_stats, 0, sizeof(xref_door_stats) ); }
 static uint8_t *xref_bs_stash = NULL;       /* [mb_h][mb_w][2][8][4], filled row by row */
 static int xref_bs_rows = 0;
 
@@ -185,6 +191,8 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
     xref_hook_me_in_t in;
     xref_hook_me_out_t out;
     int k, qp;
+    if( xref_hook_me )
+        xref_door_stats[XREF_DOOR_ME][0]++;
     /* only the main encode's searches in the newest reference frame; the lowres lookahead (other planes,
      * other stride) and multi-reference early termination keep the reference's own code */
     if( !xref_hook_me || p_halfpel_thresh || !fref || m->i_ref != 0 || m->i_stride[0] != fref->i_stride[0]
@@ -201,6 +209,7 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
         xref_orig_me_search_ref( h, m, mvc, i_mvc, p_halfpel_thresh );
         return;
     }
+    xref_door_stats[XREF_DOOR_ME][1]++;
     {
         const intptr_t off = m->p_fref[0] - fref->filtered[0][0];
         in.by = (int32_t)( off / fref->i_stride[0] );
@@ -229,6 +238,7 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
         return;
     }
     xref_hook_me_calls++;
+    xref_door_stats[XREF_DOOR_ME][2]++;
     m->mv[0] = out.mv[0];
     m->mv[1] = out.mv[1];
     m->cost = out.cost;
@@ -278,12 +288,15 @@ void x264_macroblock_encode( x264_t *h )
     uint8_t i4_modes[16];
     int kind = i16;
     const int inter = !IS_INTRA( h->mb.i_type ) && h->mb.i_type != P_SKIP && h->sh.i_type == SLICE_TYPE_P && h->mb.b_dct_decimate;
+    if( xref_hook_mbenc )
+        xref_door_stats[XREF_DOOR_MBENC][0]++;
     if( !xref_hook_mbenc || !( i16 || i4 || inter ) || h->mb.b_noise_reduction || h->mb.b_transform_8x8 || h->mb.b_lossless
         || h->mb.i_chroma_qp != h->chroma_qp_table[h->mb.i_qp] )
     {
         xref_orig_macroblock_encode( h );
         return;
     }
+    xref_door_stats[XREF_DOOR_MBENC][1]++;
     h->mb.i_cbp_luma = 0;
     h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = 0;
     if( i16 || i4 )
@@ -313,6 +326,7 @@ void x264_macroblock_encode( x264_t *h )
         return;
     }
     xref_hook_mbenc_calls++;
+    xref_door_stats[XREF_DOOR_MBENC][2]++;
     memcpy( h->dct.luma4x4[0], levels, 16*16*sizeof(int16_t) );
     memcpy( h->dct.chroma_dc[0], levels + 256, 4*sizeof(int16_t) );
     memcpy( h->dct.chroma_dc[1], levels + 260, 4*sizeof(int16_t) );
@@ -363,15 +377,19 @@ int xref_orig_macroblock_probe_pskip( x264_t *h );
 int x264_macroblock_probe_pskip( x264_t *h )
 {
     int skip = 0, mvx, mvy;
+    if( xref_hook_pskip )
+        xref_door_stats[XREF_DOOR_PSKIP][0]++;
     if( !xref_hook_pskip || h->mb.b_noise_reduction || !h->fref[0][0]
         || h->mb.i_chroma_qp != h->chroma_qp_table[h->mb.i_qp] )
         return xref_orig_macroblock_probe_pskip( h );
+    xref_door_stats[XREF_DOOR_PSKIP][1]++;
     mvx = x264_clip3( h->mb.cache.pskip_mv[0], h->mb.mv_min[0], h->mb.mv_max[0] );
     mvy = x264_clip3( h->mb.cache.pskip_mv[1], h->mb.mv_min[1], h->mb.mv_max[1] );
     if( xref_hook_pskip( h, h->fenc, h->fref[0][0], h->mb.i_mb_x, h->mb.i_mb_y, mvx, mvy, h->mb.i_qp,
                          h->mb.pic.p_fdec[0], h->mb.pic.p_fdec[1], &skip ) )
         return xref_orig_macroblock_probe_pskip( h );          /* declined: a frame is not resident */
     xref_hook_pskip_calls++;
+    xref_door_stats[XREF_DOOR_PSKIP][2]++;
     if( skip )
         h->mb.b_skip_mc = 1;                                   /* the prediction in fdec is the reconstruction */
     return skip;
@@ -400,6 +418,8 @@ void x264_mb_mc( x264_t *h )
     static const int8_t cell[4] = { 0, 2, 16, 18 };            /* x264_scan8[0] + x + (y<<3) for the four 8x8 corners */
     int16_t mv[4][2];
     int k;
+    if( xref_hook_mbmc )
+        xref_door_stats[XREF_DOOR_MBMC][0]++;
     if( !xref_hook_mbmc || h->sh.i_type != SLICE_TYPE_P || !h->fref[0][0] )
     {
         xref_orig_mb_mc( h );
@@ -415,10 +435,12 @@ void x264_mb_mc( x264_t *h )
         mv[k][0] = h->mb.cache.mv[0][x264_scan8[0] + cell[k]][0];
         mv[k][1] = h->mb.cache.mv[0][x264_scan8[0] + cell[k]][1];
     }
+    xref_door_stats[XREF_DOOR_MBMC][1]++;
     if( xref_hook_mbmc( h, h->fref[0][0], h->mb.i_mb_x, h->mb.i_mb_y, &mv[0][0], h->mb.pic.p_fdec[0], h->mb.pic.p_fdec[1] ) )
     {
         xref_orig_mb_mc( h );
         return;
     }
     xref_hook_mbmc_calls++;
+    xref_door_stats[XREF_DOOR_MBMC][2]++;
 }

@@ -104,12 +104,17 @@ void xo_deblock_luma( pixel_t *pix, intptr_t stride, int dir_v, int alpha, int b
 void xo_deblock_chroma( pixel_t *pix, intptr_t stride, int dir_v, int alpha, int beta, const int8_t tc0[4] );
 void xo_deblock_luma_intra( pixel_t *pix, intptr_t stride, int dir_v, int alpha, int beta );
 void xo_deblock_chroma_intra( pixel_t *pix, intptr_t stride, int dir_v, int alpha, int beta );
+void xo_macroblock_deblock_strength( int n, const int8_t *mb_type, const uint8_t *nnz, const int8_t *ref,
+                                     const int16_t *mv, uint8_t *bs );
 void xo_deblock_strength( int n, const uint8_t *nnz, const int8_t *ref, const int16_t *mv, uint8_t *bs );
 void xo_deblock_frame( const x264dsp_geom_t *g, uint8_t *slot, const int8_t *mb_type,
                        const uint8_t *partition, const int16_t *cbp, const uint8_t *bs,
                        int qp, int alpha_c0_offset, int beta_offset );
 
 /* ---- motion search (encoder/me.c) */
+void xo_me_search_batch_ex( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                            const x264dsp_me_params_t *prm, int n, const x264dsp_me_block_t *blocks,
+                            x264dsp_me_result_t *results, int mode, int32_t *thresh );
 void xo_me_search_batch( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *fref_slot,
                          const x264dsp_me_params_t *params, int n, const x264dsp_me_block_t *blocks,
                          x264dsp_me_result_t *results );

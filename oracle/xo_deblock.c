@@ -185,6 +185,24 @@ void xo_deblock_strength( int n, const uint8_t *nnz, const int8_t *ref, const in
         }
 }
 
+/* x264_macroblock_deblock_strength (common/macroblock.c:677-691): intra macroblocks (type 0..3) get bS 3 on the
+ * inner edges and keep bs[dir][0]; the others go through deblock_strength_c */
+void xo_macroblock_deblock_strength( int n, const int8_t *mb_type, const uint8_t *nnz, const int8_t *ref,
+                                     const int16_t *mv, uint8_t *bs )
+{
+    int m;
+    for( m = 0; m < n; m++, nnz += 120, ref += 80, mv += 160, bs += 64 )
+    {
+        if( mb_type && mb_type[m] >= 0 && mb_type[m] < 4 )
+        {
+            memset( bs + 4, 3, 12 );
+            memset( bs + 32 + 4, 3, 12 );
+        }
+        else
+            xo_deblock_strength( 1, nnz, ref, mv, bs );
+    }
+}
+
 /* deblock_edge (deblock.c:325-339) */
 static void edge_inter( pixel_t *pix, intptr_t stride, const uint8_t bs[4], int index_a, int alpha, int beta,
                         int chroma, int dir_v )

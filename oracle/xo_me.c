@@ -26,6 +26,8 @@ typedef struct
     int mvp[2];
     int min_fpel[2], max_fpel[2], min_spel[2], max_spel[2];
     int method, subme, range;
+    int fpel_satd;                                /* fpelcmp == satd: TESA with subme >= 2 (encoder.c:429-432) */
+    int *thresh;                                  /* p_halfpel_thresh */
     /* result */
     int mv[2], cost, cost_mv_out;
 } me_t;
@@ -47,6 +49,8 @@ static int mv_bits( const me_t *m, int qx, int qy )
 /* full-pel SAD + mv cost (COST_MV, me.c:48-52) */
 static int fpel_sad( const me_t *m, int mx, int my )
 {
+    if( m->fpel_satd )
+        return xo_satd( m->size, m->fenc, XO_FENC_STRIDE, m->ref[0] + my * m->stride + mx, m->stride );
     return xo_sad( m->size, m->fenc, XO_FENC_STRIDE, m->ref[0] + my * m->stride + mx, m->stride );
 }
 static int fpel_cost( const me_t *m, int mx, int my )
@@ -60,7 +64,7 @@ static int qpel_cost( const me_t *m, int qx, int qy, int use_satd )
     pixel_t tmp[16 * 16];
     intptr_t ts = 16;
     const pixel_t *p = xo_get_ref( tmp, &ts, m->ref, m->stride, qx, qy, m->bw, m->bh );
-    int c = use_satd ? xo_satd( m->size, m->fenc, XO_FENC_STRIDE, p, ts )
+    int c = use_satd || m->fpel_satd ? xo_satd( m->size, m->fenc, XO_FENC_STRIDE, p, ts )
                      : xo_sad( m->size, m->fenc, XO_FENC_STRIDE, p, ts );
     return c + mv_bits( m, qx, qy );
 }
@@ -255,8 +259,21 @@ static void refine_subpel( me_t *m, int hpel_iters, int qpel_iters, int final_re
             break;
     }
 
-    if( !final_refine )                           /* me.c:519-524: re-cost the winner with SATD */
+    if( !final_refine && !m->fpel_satd )          /* me.c:519-524: re-cost the winner with SATD */
         bcost = qpel_cost( m, bmx, bmy, 1 );
+
+    if( m->thresh )                               /* me.c:526-539 */
+    {
+        if( (bcost * 7) >> 3 > *m->thresh )
+        {
+            m->cost = bcost;
+            m->mv[0] = bmx;
+            m->mv[1] = bmy;
+            return;                               /* cost_mv keeps its value */
+        }
+        else if( bcost < *m->thresh )
+            *m->thresh = bcost;
+    }
 
     if( m->subme != 1 )
     {
@@ -296,6 +313,16 @@ void xo_me_search_batch( const x264dsp_geom_t *g, const uint8_t *fenc_slot, cons
                          const x264dsp_me_params_t *prm, int n, const x264dsp_me_block_t *blocks,
                          x264dsp_me_result_t *results )
 {
+    xo_me_search_batch_ex( g, fenc_slot, fref_slot, prm, n, blocks, results, 0, NULL );
+}
+
+/* mode 0: x264_me_search_ref with p_halfpel_thresh = &thresh[i] (NULL: none); mode 1: x264_me_refine_qpel_refdupe
+ * (me.c:437-440) and mode 2: x264_me_refine_qpel alone (me.c:426-435, i_ref_cost already subtracted), both on the
+ * mv / cost / cost_mv found in results[i] */
+void xo_me_search_batch_ex( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                            const x264dsp_me_params_t *prm, int n, const x264dsp_me_block_t *blocks,
+                            x264dsp_me_result_t *results, int mode, int32_t *thresh )
+{
     uint16_t *table = malloc( 8193 * sizeof(uint16_t) );
     int i, k, y;
     xo_cost_mv_table( prm->qp, table );
@@ -325,9 +352,30 @@ void xo_me_search_batch( const x264dsp_geom_t *g, const uint8_t *fenc_slot, cons
         m.method = prm->me_method;
         m.subme = prm->subpel_refine;
         m.range = prm->me_range;
-        me_search( &m, b->mvc, b->i_mvc );
-        if( prm->refine_qpel )                    /* x264_me_refine_qpel, me.c:426-435 (i_ref_cost = 0) */
-            refine_subpel( &m, subpel_iters[m.subme][0], subpel_iters[m.subme][1], 1 );
+        m.fpel_satd = prm->me_method == X264DSP_ME_TESA && prm->subpel_refine >= 2;
+        m.thresh = thresh ? &thresh[i] : NULL;
+        if( mode )
+        {
+            int q = subpel_iters[m.subme][3];
+            m.mv[0] = results[i].mv[0];
+            m.mv[1] = results[i].mv[1];
+            m.cost = results[i].cost;
+            m.cost_mv_out = results[i].cost_mv;
+            if( mode == 1 )
+                refine_subpel( &m, 0, q < 2 ? q : 2, 0 );
+            else
+            {
+                m.thresh = NULL;
+                refine_subpel( &m, subpel_iters[m.subme][0], subpel_iters[m.subme][1], 1 );
+            }
+        }
+        else
+        {
+            me_search( &m, b->mvc, b->i_mvc );
+            m.thresh = NULL;
+            if( prm->refine_qpel )                /* x264_me_refine_qpel, me.c:426-435 (i_ref_cost = 0) */
+                refine_subpel( &m, subpel_iters[m.subme][0], subpel_iters[m.subme][1], 1 );
+        }
         results[i].mv[0] = (int16_t)m.mv[0];
         results[i].mv[1] = (int16_t)m.mv[1];
         results[i].cost = m.cost;

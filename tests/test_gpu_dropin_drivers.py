@@ -286,10 +286,13 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             lib.xref_set_driver_hooks(None, None, None)
         out = np.zeros(1 << 20, np.uint8)
         launches0 = ctx.launches
+        doors = (C.c_int * 12)()
+        lib.xref_door_stats_reset()
         try:
             size = lib.xref_encode_clip(enc.h, ptr(clip), n, ptr(out), out.size)
         finally:
             lib.xref_driver_hook_calls(calls)
+            lib.xref_door_stats_read(doors)
             lib.xref_set_driver_hooks(None, None, None)
             lib.xref_set_fdec_hook(None)
             lib.xref_set_me_hook(None)
@@ -299,17 +302,28 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
         assert size > 0, size
         outs.append(out[:size].copy())
         if use_gpu:
+            # exact counts: every frame's lowres init, every reconstructed frame's filter pass (all n frames are
+            # reference frames: no B frames), one lookahead cost per frame after the first (the reference's slicetype
+            # decision analyses each new frame once against its predecessor)
             assert calls[0] == n, f"x264_frame_init_lowres hooked {calls[0]} times for {n} frames"
-            assert calls[1] >= n - 1, f"x264_frame_filter hooked {calls[1]} times"
-            assert calls[2] >= n - 2, f"lookahead cost hooked {calls[2]} times"
+            assert calls[1] == n, f"x264_frame_filter / in-loop filter hooked {calls[1]} times for {n} frames"
+            print(f"DOORCOUNTS {w}x{h} n={n} cut={cut} me={me} subme={subme} psub={psub}: calls={list(calls)} doors={list(doors)}")
+            assert n - 2 <= calls[2] <= 2 * n, f"lookahead cost hooked {calls[2]} times for {n} frames"
             assert ctx.launches - launches0 >= 2 * n, "the encode must have gone through the CUDA kernels"
+            # per door {entered, eligible, served}: every eligible call must have been served by the device (a decline
+            # falls back to the reference's code silently inside hooks.c -- that must not happen), and the callbacks'
+            # own counters must agree with the doors'
+            st = {name: tuple(doors[3 * i: 3 * i + 3]) for i, name in enumerate(("me", "mbenc", "pskip", "mbmc"))}
             if mehook:
-                assert me_calls[0] >= (n - 3) * g.mb_count // 2, f"only {me_calls[0]} searches went to the device"
+                assert st["me"][1] > 0 and st["me"][2] == st["me"][1] == me_calls[0], f"ME door {st['me']} vs {me_calls[0]}"
+                # what is not eligible are the lookahead's own searches (lowres planes): the rest of the entries
+                assert st["me"][0] - st["me"][1] > 0
             if mbenc and mehook:
-                assert mbmc_calls[0] >= g.mb_count, f"only {mbmc_calls[0]} macroblocks were motion-compensated on the device"
-                assert pskip_calls[0] >= g.mb_count // 4, f"only {pskip_calls[0]} P_SKIP probes went to the device"
+                assert st["mbmc"][2] == st["mbmc"][1] == mbmc_calls[0] and mbmc_calls[0] > 0, f"mb_mc door {st['mbmc']}"
+                assert st["pskip"][2] == st["pskip"][1] == pskip_calls[0] and pskip_calls[0] > 0, f"pskip door {st['pskip']}"
                 assert 0 < pskip_calls[1] < pskip_calls[0], f"one-sided probes: {pskip_calls}"
             if mbenc:
+                assert st["mbenc"][2] == st["mbenc"][1] == sum(mbenc_calls), f"macroblock_encode door {st['mbenc']} vs {mbenc_calls}"
                 assert mbenc_calls[0] >= g.mb_count, f"only {mbenc_calls[0]} inter macroblocks were coded on the device"
                 assert mbenc_calls[1] > 0, "no I16x16 macroblock of the I frames was coded on the device"
                 assert mbenc_calls[2] > 0, "no I4x4 macroblock of the I frames was coded on the device"

@@ -56,7 +56,13 @@ def diff_report(a, b, g):
     return f"{len(bad)} bytes differ, first: " + "; ".join(regions)
 
 
-@pytest.mark.parametrize("w,h", SIZES)
+# the benchmark geometries, plus widths whose right-edge remainder (n_units % 30, n_units = W16/8 + 1) lands in each of the
+# hpel kernel's narrow tail strips: 1080p / 4K -> 1 unit (4 lanes), 256 -> 3 units (8 lanes), 320 -> 11 units (16 lanes),
+# 352 / 368 -> 15 / 17 units (32 lanes), 200 -> a single partial strip, 720 -> 1 unit after three full strips
+HPEL_SIZES = SIZES + [(1920, 1080), (3840, 2160), (256, 64), (320, 48), (720, 96), (1280, 720)]
+
+
+@pytest.mark.parametrize("w,h", HPEL_SIZES)
 def test_frame_planes_match_oracle(pkg, ctx, w, h):
     torch = _torch()
     n = 2
@@ -301,3 +307,45 @@ def test_lookahead_without_intra_and_host_api(pkg, ctx):
     assert np.array_equal(d_mvs.cpu().numpy()[0], mv_o)
     assert np.array_equal(d_costs.cpu().numpy()[0], c_o)
     assert np.array_equal(d_sums.cpu().numpy()[0][:5], s_o[:5])
+
+
+def test_wavefront_calls_on_two_streams_share_the_context(pkg, ctx):
+    """two x264dsp_lookahead_frame_cost_dev calls in flight on DIFFERENT streams of one context: the second queues
+    behind the first (they share the context's sync words and ticket) and both results equal the single-call ones"""
+    torch = _torch()
+    w, h, clips, clip_len = 208, 160, 14, 4
+    n = clips * clip_len
+    frames = [pkg.synth_frame(w, h, 5 * (i // clip_len) + i % clip_len) for i in range(n)]
+    g = pkg.geometry(w, h)
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, n)
+    ctx.frame_init_lowres(g, slots, n)
+    ctx.sync()
+    b = np.arange(n)
+    p0 = np.where(b % clip_len == 0, -1, b - 1)
+    half = n // 2
+
+    def outputs(k):
+        return (torch.full((k, g.mb_count, 2), -7, dtype=torch.int16, device="cuda"),
+                torch.full((k, g.mb_count), -7, dtype=torch.int32, device="cuda"),
+                torch.full((k, pkg.LA_SUMS), -7, dtype=torch.int32, device="cuda"))
+
+    want = []
+    for lo, hi in ((0, half), (half, n)):
+        o = outputs(hi - lo)
+        ctx.lookahead_frame_cost(g, slots, b[lo:hi], p0[lo:hi], np.ones(hi - lo, np.uint8), *o)
+        ctx.sync()
+        want.append([t.cpu().numpy() for t in o])
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for rep in range(3):
+        o1, o2 = outputs(half), outputs(n - half)
+        torch.cuda.synchronize()
+        ctx.lookahead_frame_cost(g, slots, b[:half], p0[:half], np.ones(half, np.uint8), *o1, stream=s1.cuda_stream)
+        ctx.lookahead_frame_cost(g, slots, b[half:], p0[half:], np.ones(n - half, np.uint8), *o2, stream=s2.cuda_stream)
+        torch.cuda.synchronize()
+        for got, exp in ((o1, want[0]), (o2, want[1])):
+            for t, e in zip(got, exp):
+                assert np.array_equal(t.cpu().numpy()[..., :5] if t.shape[-1] == pkg.LA_SUMS else t.cpu().numpy(),
+                                      e[..., :5] if e.shape[-1] == pkg.LA_SUMS else e), f"rep {rep}"

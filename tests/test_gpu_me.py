@@ -119,6 +119,127 @@ def test_me_search_1080p_tiling(pkg, ctx):
         assert np.array_equal(got, want), f"sized, size {size}: {np.count_nonzero(got != want)} of {len(sub)} differ"
 
 
+@pytest.mark.parametrize("me,subme,refine", [(2, 2, 0), (2, 5, 1), (3, 1, 1), (3, 4, 0), (4, 2, 1), (4, 5, 0), (4, 1, 1)])
+def test_me_search_umh_esa_tesa(pkg, ctx, me, subme, refine):
+    """me = UMH / ESA / TESA do what the reference does with them (encoder/me.c:389-394: no pattern search; TESA with
+    subme >= 2: SATD as the full-pel metric) -- oracle pinned in tests/test_oracle_vs_ref.py::test_me_search_umh_esa_tesa"""
+    import torch
+    w, h = 352, 288
+    g, go, host, slots = prepare(pkg, ctx, w, h)
+    o = cc.oracle()
+    rng = np.random.RandomState(40 + me * 10 + subme)
+    ref_slot, enc_slot = slots[: g.slot_bytes], slots[g.slot_bytes:]
+    for size in range(8):
+        n = 300
+        blocks = make_me_blocks(go, rng, size, n, 40)
+        want = np.zeros(n, cc.ME_RESULT_DTYPE)
+        prm = cc.MeParams(me, subme, 16, 30, refine)
+        o.xo_me_search_batch(C.byref(go), cc.ptr(host[1]), cc.ptr(host[0]), C.byref(prm), n,
+                             blocks.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+        d_blocks = torch.from_numpy(blocks.view(np.uint8)).cuda()
+        p = pkg.MeParams(me, subme, 16, 30, refine)
+        for which in ("batch", "sized"):
+            d_res = torch.zeros(n * cc.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            if which == "batch":
+                ctx.me_search_batch(g, enc_slot, ref_slot, p, n, d_blocks, d_res)
+            else:
+                ctx.me_search_sized(g, enc_slot, ref_slot, p, size, n, d_blocks, d_res)
+            ctx.sync()
+            got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)
+            assert np.array_equal(got, want), f"{which} me {me} subme {subme} size {size}: {np.count_nonzero(got != want)}/{n} differ"
+
+
+@pytest.mark.parametrize("me,subme", [(1, 2), (1, 4), (1, 5), (0, 3), (2, 5)])
+def test_me_halfpel_thresh_and_refdupe(pkg, ctx, me, subme):
+    """x264_me_search_ref with p_halfpel_thresh, x264_me_refine_qpel_refdupe and x264_me_refine_qpel alone
+    (encoder/me.c:421, 426-440, 526-539): x264dsp_me_search_batch_ex_dev against the oracle (pinned to the reference in
+    tests/test_oracle_vs_ref.py::test_me_halfpel_thresh_and_refdupe)"""
+    import torch
+    w, h = 352, 288
+    g, go, host, slots = prepare(pkg, ctx, w, h)
+    o = cc.oracle()
+    rng = np.random.RandomState(77 + me * 10 + subme)
+    ref_slot, enc_slot = slots[: g.slot_bytes], slots[g.slot_bytes:]
+    for size in range(8):
+        n = 300
+        blocks = make_me_blocks(go, rng, size, n, 40)
+        prm = cc.MeParams(me, subme, 16, 28, 0)
+        p = pkg.MeParams(me, subme, 16, 28, 0)
+        base = np.zeros(n, cc.ME_RESULT_DTYPE)
+        o.xo_me_search_batch(C.byref(go), cc.ptr(host[1]), cc.ptr(host[0]), C.byref(prm), n,
+                             blocks.ctypes.data_as(C.c_void_p), base.ctypes.data_as(C.c_void_p))
+        thresh0 = (base["cost"] * rng.choice([0.5, 0.8, 0.95, 1.0, 1.3, 4.0], n)).astype(np.int32)
+        thresh0[rng.rand(n) < 0.1] = 2**31 - 1
+        d_blocks = torch.from_numpy(blocks.view(np.uint8)).cuda()
+        for mode in (0, 1, 2):
+            start = base.copy()
+            if mode:
+                start["mv"] = (start["mv"] & ~3) if mode == 1 else start["mv"]
+                start["mv"] += rng.randint(-1, 2, (n, 2)) * 4
+                start["cost"] += rng.randint(0, 50, n)
+            want, t_want = start.copy(), thresh0.copy()
+            use_t = mode != 2
+            o.xo_me_search_batch_ex(C.byref(go), cc.ptr(host[1]), cc.ptr(host[0]), C.byref(prm), n,
+                                    blocks.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), mode,
+                                    cc.ptr(t_want, cc.i32p) if use_t else None)
+            d_res = torch.from_numpy(start.copy().view(np.uint8)).cuda()
+            d_t = torch.from_numpy(thresh0.copy()).cuda() if use_t else None
+            torch.cuda.synchronize()
+            ctx.me_search_batch_ex(g, enc_slot, ref_slot, p, n, d_blocks, d_res, mode, d_t)
+            ctx.sync()
+            got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE)
+            assert np.array_equal(got, want), f"mode {mode} size {size}: {np.count_nonzero(got != want)}/{n} results differ"
+            if use_t:
+                assert np.array_equal(d_t.cpu().numpy(), t_want), f"mode {mode} size {size}: thresholds differ"
+
+
+def test_me_search_sized_frames_1080p(pkg, ctx):
+    """x264dsp_me_search_sized_frames_dev -- the frame-batched call bench.py times for configs[2] -- at 1080p: all seven
+    partition sizes tiling the frame, three frame pairs per launch, HEX + subme 5 + qpel refine, EVERY block of every
+    pair compared with the oracle (0.2 s per frame and size on one core)."""
+    import torch
+    w, h, nf = 1920, 1080, 3
+    g = pkg.geometry(w, h)
+    go = cc.oracle_geom(w, h)
+    o = cc.oracle()
+    frames = [pkg.synth_frame(w, h, i) for i in range(nf + 1)]
+    host = []
+    for f in frames:
+        s = np.zeros(go.slot_bytes, np.uint8)
+        o.xo_frame_load_i420(C.byref(go), cc.ptr(f), cc.ptr(s))
+        o.xo_frame_expand_border(C.byref(go), cc.ptr(s))
+        o.xo_frame_filter(C.byref(go), cc.ptr(s))
+        host.append(s)
+    i420 = torch.from_numpy(np.concatenate(frames)).cuda()
+    slots = torch.zeros((nf + 1) * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.frame_load_i420(g, i420, slots, nf + 1)
+    ctx.frame_expand_border(g, slots, nf + 1)
+    ctx.frame_filter(g, slots, nf + 1)
+    ctx.sync()
+    rng = np.random.RandomState(31)
+    prm_t = (1, 5, 16, 26, 1)
+    for size in range(7):
+        # pair f: frame f+1 searched in frame f; the MB-level MVs differ per pair so that the block lists differ
+        per_pair = [pkg.tiling_blocks(g, size, rng.randint(-12, 13, (g.mb_count, 2)).astype(np.int16)) for _ in range(nf)]
+        n = len(per_pair[0])
+        blocks = np.concatenate(per_pair)
+        d_blocks = torch.from_numpy(blocks.view(np.uint8)).cuda()
+        d_res = torch.zeros(nf * n * cc.ME_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.me_search_sized_frames(g, slots[g.slot_bytes:], slots, nf, pkg.MeParams(*prm_t), size, n, d_blocks, d_res)
+        ctx.sync()
+        got = d_res.cpu().numpy().view(cc.ME_RESULT_DTYPE).reshape(nf, n)
+        for f in range(nf):
+            want = np.zeros(n, cc.ME_RESULT_DTYPE)
+            o.xo_me_search_batch(C.byref(go), cc.ptr(host[f + 1]), cc.ptr(host[f]), C.byref(cc.MeParams(*prm_t)), n,
+                                 per_pair[f].ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+            bad = np.nonzero(got[f] != want)[0]
+            assert len(bad) == 0, (f"size {size} pair {f}: {len(bad)} of {n} blocks differ; first {bad[0]}: "
+                                   f"gpu {got[f][bad[0]]} oracle {want[bad[0]]}")
+
+
 def test_predict_mv_batch(pkg, ctx):
     """x264_mb_predict_mv_16x16 / x264_mb_predict_mv_pskip for a batch of neighbourhoods against the oracle (pinned to the
     reference's functions, tests/test_oracle_vs_ref.py::test_predict_mv_16x16_and_pskip)"""

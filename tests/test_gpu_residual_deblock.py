@@ -196,6 +196,32 @@ def test_deblock_strength(pkg, ctx, n, skew):
     assert np.array_equal(got[:, :, :4], want[:, :, :4])
 
 
+@pytest.mark.parametrize("n,skew", [(5000, 0), (4999, 0), (1, 0), (8161, 0), (333, 4)])
+def test_macroblock_deblock_strength_with_intra(pkg, ctx, n, skew):
+    """x264_macroblock_deblock_strength (common/macroblock.c:677-691): intra macroblocks mixed in -- inner edges 3, edge 0
+    untouched; bs starts from a random pattern so that untouched bytes are compared as well"""
+    import torch
+    rng = np.random.RandomState(13 + n)
+    mb_type = rng.choice([0, 1, 2, 3, 4, 5, 6], n).astype(np.int8)
+    nnz = (rng.rand(n, 120) < 0.3).astype(np.uint8)
+    ref = rng.randint(-1, 2, (n, 2, 40)).astype(np.int8)
+    mv = rng.randint(-6, 7, (n, 2, 40, 2)).astype(np.int16)
+    start = rng.randint(0, 256, (n, 2, 8, 4)).astype(np.uint8)
+    want = start.copy()
+    cc.oracle().xo_macroblock_deblock_strength(n, ptr(mb_type, i8p), ptr(nnz), ptr(ref, i8p), ptr(mv, i16p), ptr(want))
+    assert (want[mb_type < 4][:, :, 1:4] == 3).all() and np.array_equal(want[:, :, 4:], start[:, :, 4:])
+    d = []
+    for a in (nnz, ref, mv):
+        raw = torch.zeros(a.nbytes + 64, dtype=torch.uint8, device="cuda")
+        raw[skew: skew + a.nbytes] = torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
+        d.append(raw[skew: skew + a.nbytes])
+    bs = torch.from_numpy(start.copy()).cuda()
+    torch.cuda.synchronize()
+    ctx.macroblock_deblock_strength(n, torch.from_numpy(mb_type).cuda(), d[0], d[1], d[2], bs)
+    ctx.sync()
+    assert np.array_equal(bs.cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("w,h,nf,qp,intra_share", [(352, 288, 2, 26, 0.5), (200, 120, 3, 18, 1.0), (352, 288, 2, 38, 0.3),
                                                     (1920, 1080, 2, 30, 0.5), (352, 288, 2, 12, 1.0), (208, 160, 2, 51, 0.5)])
 def test_residual_frames_typed_inter_i16x16_i4x4(pkg, ctx, w, h, nf, qp, intra_share):

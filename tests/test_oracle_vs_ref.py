@@ -294,6 +294,24 @@ def test_deblock_strength(enc):
         assert np.array_equal(b1, b2)
 
 
+def test_macroblock_deblock_strength(enc):
+    """x264_macroblock_deblock_strength (common/macroblock.c:677-691): every mb_type, bs pre-filled with a pattern so
+    that the bytes the reference leaves alone (edge 0 of an intra macroblock, rows 4..7) are checked too"""
+    o = cc.oracle()
+    rng = np.random.RandomState(81)
+    for trial in range(300):
+        mb_type = int(rng.choice([0, 1, 2, 3, 4, 5, 6]))
+        nnz = (rng.rand(120) < 0.3).astype(np.uint8)
+        ref = rng.randint(-1, 2, (2, 40)).astype(np.int8)
+        mv = rng.randint(-6, 7, (2, 40, 2)).astype(np.int16)
+        b1 = rng.randint(0, 256, (2, 8, 4)).astype(np.uint8)
+        b2 = b1.copy()
+        enc.lib.xref_macroblock_deblock_strength(enc.h, mb_type, ptr(nnz), ptr(ref, i8p), ptr(mv, i16p), ptr(b1))
+        t = np.array([mb_type], np.int8)
+        o.xo_macroblock_deblock_strength(1, ptr(t, i8p), ptr(nnz), ptr(ref, i8p), ptr(mv, i16p), ptr(b2))
+        assert np.array_equal(b1, b2), f"mb_type {mb_type}"
+
+
 @pytest.mark.parametrize("qp,aoff,boff", [(26, 0, 0), (38, 0, 0), (20, 3, -2), (51, 0, 0), (12, 0, 0)])
 def test_deblock_frame(enc, qp, aoff, boff):
     o = cc.oracle()
@@ -454,6 +472,86 @@ def test_me_search(me, subme, refine):
             bad = [i for i in range(n) if r_ref[i] != r_ora[i]]
             assert not bad, (f"me {me} subme {subme} size {size} qp {qp}: {len(bad)} differ, "
                              f"e.g. {bad[0]}: ref {r_ref[bad[0]]} oracle {r_ora[bad[0]]} block {blocks[bad[0]]}")
+
+
+def _me_pair(w, h, me, subme):
+    """a reference encoder + the oracle's slots of the same two frames"""
+    o = cc.oracle()
+    enc = cc.RefEncoder(w, h, me=me, subme=max(subme, 1), me_range=16, qp=26)
+    g = cc.oracle_geom(w, h)
+    clip = cc.synth_clip(w, h, 2)
+    fref = enc.new_frame(True)
+    fenc = enc.new_frame(False)
+    enc.load(fref, clip[0])
+    enc.load(fenc, clip[1])
+    enc.lib.xref_frame_filter_all(enc.h, fref)
+    slot_ref, slot_enc = np.zeros(g.slot_bytes, np.uint8), np.zeros(g.slot_bytes, np.uint8)
+    o.xo_frame_load_i420(C.byref(g), ptr(clip[0]), ptr(slot_ref))
+    o.xo_frame_expand_border(C.byref(g), ptr(slot_ref))
+    o.xo_frame_filter(C.byref(g), ptr(slot_ref))
+    o.xo_frame_load_i420(C.byref(g), ptr(clip[1]), ptr(slot_enc))
+    return enc, g, fenc, fref, slot_enc, slot_ref
+
+
+@pytest.mark.parametrize("me,subme,refine", [(2, 2, 0), (2, 5, 1), (3, 1, 1), (3, 4, 0), (4, 2, 1), (4, 5, 0), (4, 1, 1)])
+def test_me_search_umh_esa_tesa(me, subme, refine):
+    """me = UMH / ESA / TESA: the reference accepts the parameter (encoder.c:251-259) and its search has no case for
+    them (me.c:389-394) -- predictors + sub-pel refinement; TESA with subme >= 2 makes fpelcmp SATD (encoder.c:429-432;
+    with subme <= 1 the parameter check turns it into ESA).  The oracle must do the same, whatever that is."""
+    o = cc.oracle()
+    enc, g, fenc, fref, slot_enc, slot_ref = _me_pair(352, 288, me, subme)
+    assert enc.geom[15] == (3 if me == 4 and subme <= 1 else me)
+    rng = np.random.RandomState(900 + me * 10 + subme)
+    for size in range(7):
+        n = 120
+        blocks = make_me_blocks(g, rng, size, n, 40)
+        r_ref = np.zeros(n, cc.ME_RESULT_DTYPE)
+        r_ora = np.zeros(n, cc.ME_RESULT_DTYPE)
+        enc.lib.xref_me_search_batch(enc.h, fenc, fref, 30, enc.geom[15], subme, 16, refine,
+                                     blocks.ctypes.data_as(C.c_void_p), n, r_ref.ctypes.data_as(C.c_void_p))
+        prm = cc.MeParams(me, subme, 16, 30, refine)
+        o.xo_me_search_batch(C.byref(g), ptr(slot_enc), ptr(slot_ref), C.byref(prm), n,
+                             blocks.ctypes.data_as(C.c_void_p), r_ora.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(r_ref, r_ora), f"me {me} subme {subme} size {size}: {np.count_nonzero(r_ref != r_ora)} differ"
+
+
+@pytest.mark.parametrize("me,subme", [(1, 2), (1, 4), (1, 5), (0, 3), (2, 5)])
+def test_me_halfpel_thresh_and_refdupe(me, subme):
+    """x264_me_search_ref with p_halfpel_thresh, x264_me_refine_qpel_refdupe and x264_me_refine_qpel alone
+    (me.c:421, 426-440, 526-539) against the oracle's xo_me_search_batch_ex"""
+    o = cc.oracle()
+    enc, g, fenc, fref, slot_enc, slot_ref = _me_pair(352, 288, me, subme)
+    rng = np.random.RandomState(77 + me * 10 + subme)
+    for size in (0, 1, 3, 4, 6):
+        n = 150
+        blocks = make_me_blocks(g, rng, size, n, 40)
+        prm = cc.MeParams(me, subme, 16, 28, 0)
+        # plain search first: gives realistic costs to derive thresholds and starting points from
+        base = np.zeros(n, cc.ME_RESULT_DTYPE)
+        o.xo_me_search_batch(C.byref(g), ptr(slot_enc), ptr(slot_ref), C.byref(prm), n,
+                             blocks.ctypes.data_as(C.c_void_p), base.ctypes.data_as(C.c_void_p))
+        thresh0 = (base["cost"] * rng.choice([0.5, 0.8, 0.95, 1.0, 1.3, 4.0], n)).astype(np.int32)
+        thresh0[rng.rand(n) < 0.1] = 2**31 - 1
+        for mode in (0, 1, 2):
+            start = base.copy()
+            if mode:
+                start["mv"] = (start["mv"] & ~3) if mode == 1 else start["mv"]
+                start["mv"] += rng.randint(-1, 2, (n, 2)) * 4
+                start["cost"] += rng.randint(0, 50, n)
+            r_ref, r_ora = start.copy(), start.copy()
+            t_ref, t_ora = thresh0.copy(), thresh0.copy()
+            use_t = mode != 2
+            enc.lib.xref_me_search_batch_ex(enc.h, fenc, fref, 28, me, subme, 16, 0, blocks.ctypes.data_as(C.c_void_p), n,
+                                            r_ref.ctypes.data_as(C.c_void_p), mode, ptr(t_ref, cc.i32p) if use_t else None)
+            o.xo_me_search_batch_ex(C.byref(g), ptr(slot_enc), ptr(slot_ref), C.byref(prm), n,
+                                    blocks.ctypes.data_as(C.c_void_p), r_ora.ctypes.data_as(C.c_void_p), mode,
+                                    ptr(t_ora, cc.i32p) if use_t else None)
+            assert np.array_equal(r_ref, r_ora), f"mode {mode} size {size}: {np.count_nonzero(r_ref != r_ora)} results differ"
+            assert np.array_equal(t_ref, t_ora), f"mode {mode} size {size}: thresholds differ"
+            if mode == 0:
+                cut = np.count_nonzero((r_ref["mv"] != base["mv"]).any(1) | (r_ref["cost"] != base["cost"]))
+                assert cut > 0 or subme < 4, "the early exit never fired"
+                assert np.count_nonzero(t_ref != thresh0) > 0
 
 
 # ------------------------------------------------------------------ residual

@@ -21,7 +21,8 @@ PIXEL_16x16, PIXEL_16x8, PIXEL_8x16, PIXEL_8x8, PIXEL_8x4, PIXEL_4x8, PIXEL_4x4,
 BLOCK_W = [16, 16, 8, 8, 8, 4, 4, 4]
 BLOCK_H = [16, 8, 16, 8, 4, 8, 4, 16]
 CMP_SAD, CMP_SSD, CMP_SATD = 0, 1, 2
-ME_DIA, ME_HEX = 0, 1
+ME_DIA, ME_HEX, ME_UMH, ME_ESA, ME_TESA = range(5)
+ME_MODE_SEARCH, ME_MODE_REFDUPE, ME_MODE_REFINE_QPEL = range(3)
 LA_COST_INTER, LA_COST_INTRA, LA_INTRA_MBS, LA_SAD_EVALS, LA_SATD_EVALS, LA_SUMS = 0, 1, 2, 3, 4, 8
 (PROF_LOAD, PROF_LOWRES, PROF_LA_INTRA, PROF_LA_INTER, PROF_HPEL, PROF_BORDER, PROF_COST, PROF_ME, PROF_MC,
  PROF_RESIDUAL, PROF_DEBLOCK, PROF_LA_TILE) = range(12)
@@ -292,13 +293,15 @@ class Context:
               "x264dsp_cost_batch_dev")
 
     # ---- lookahead -----------------------------------------------------------------------
-    def lookahead_frame_cost(self, g, slots_dev, b, p0, want_intra, mvs, costs, sums, row_satds=None):
+    def lookahead_frame_cost(self, g, slots_dev, b, p0, want_intra, mvs, costs, sums, row_satds=None, stream=None):
+        """stream: a cudaStream_t as an int (e.g. torch.cuda.Stream().cuda_stream); None = the context's stream"""
         b = np.ascontiguousarray(b, np.int32)
         p0 = np.ascontiguousarray(p0, np.int32)
         wi = np.ascontiguousarray(want_intra, np.uint8)
         check(lib().x264dsp_lookahead_frame_cost_dev(
             self._h, C.byref(g), _dp(slots_dev), len(b), _hp(b, C.c_int32), _hp(p0, C.c_int32), _hp(wi),
-            _dp(mvs), _dp(costs), _dp(sums), _dp(row_satds), None), "x264dsp_lookahead_frame_cost_dev")
+            _dp(mvs), _dp(costs), _dp(sums), _dp(row_satds), C.c_void_p(stream) if stream else None),
+            "x264dsp_lookahead_frame_cost_dev")
 
     def lookahead_select_kernel(self, mode):
         """0 = by batch size, 1 = one block row per warp, 2 = four rows per warp, 3 = eight rows per warp"""
@@ -357,6 +360,13 @@ class Context:
         check(lib().x264dsp_me_search_batch_dev(self._h, C.byref(g), _dp(fenc_slot), _dp(fref_slot),
                                                 C.byref(params), int(n), _dp(blocks_dev), _dp(results_dev),
                                                 None), "x264dsp_me_search_batch_dev")
+
+    def me_search_batch_ex(self, g, fenc_slot, fref_slot, params, n, blocks_dev, results_dev, mode, thresh_dev=None):
+        """x264_me_search_ref with p_halfpel_thresh (mode 0), x264_me_refine_qpel_refdupe (1), x264_me_refine_qpel (2);
+        thresh_dev: int32[n] device tensor, read and updated (None = NULL)"""
+        check(lib().x264dsp_me_search_batch_ex_dev(self._h, C.byref(g), _dp(fenc_slot), _dp(fref_slot),
+                                                   C.byref(params), int(n), _dp(blocks_dev), _dp(results_dev),
+                                                   int(mode), _dp(thresh_dev), None), "x264dsp_me_search_batch_ex_dev")
 
     def me_search_sized(self, g, fenc_slot, fref_slot, params, i_pixel, n, blocks_dev, results_dev):
         """uniform-size list: the size-specialised kernel (x264dsp_me_search_sized_dev)"""
@@ -429,12 +439,18 @@ class Context:
                                               _dp(cbp), _dp(bs), int(qp), int(alpha_off), int(beta_off), None),
               "x264dsp_deblock_frame_dev")
 
-    def deblock_frames(self, g, slots, n_frames, mb_type, partition, cbp, bs, qp, alpha_off=0, beta_off=0):
+    def deblock_frames(self, g, slots, n_frames, mb_type, partition, cbp, bs, qp, alpha_off=0, beta_off=0, stream=None):
         """n_frames consecutive slots in one launch; the per-MB arrays hold n_frames x mb_count entries"""
         check(lib().x264dsp_deblock_frames_dev(self._h, C.byref(g), _dp(slots), int(n_frames), _dp(mb_type),
                                                _dp(partition), _dp(cbp), _dp(bs), int(qp), int(alpha_off),
-                                               int(beta_off), None), "x264dsp_deblock_frames_dev")
+                                               int(beta_off), C.c_void_p(stream) if stream else None),
+              "x264dsp_deblock_frames_dev")
 
     def deblock_strength(self, n, nnz, ref, mv, bs):
         check(lib().x264dsp_deblock_strength_dev(self._h, int(n), _dp(nnz), _dp(ref), _dp(mv), _dp(bs), None),
               "x264dsp_deblock_strength_dev")
+
+    def macroblock_deblock_strength(self, n, mb_type, nnz, ref, mv, bs):
+        """x264_macroblock_deblock_strength: mb_type int8[n] (0..3 = intra -> inner edges 3); None = all inter"""
+        check(lib().x264dsp_macroblock_deblock_strength_dev(self._h, int(n), _dp(mb_type), _dp(nnz), _dp(ref), _dp(mv),
+                                                            _dp(bs), None), "x264dsp_macroblock_deblock_strength_dev")

@@ -56,6 +56,13 @@ struct x264dsp_ctx
     int prof_n[XD_PROF_KINDS];
     cudaEvent_t prof_ev[XD_PROF_KINDS][XD_PROF_MAX][2];
 
+    // the wavefront kernels' scratch above (lookahead: sync words / tickets / epoch; deblock: progress counters) is
+    // per context, not per call: launches that reuse it are ordered after its previous user even when they arrive
+    // on different streams (xd_scratch_acquire / _release)
+    cudaEvent_t scratch_ev[2];
+    cudaStream_t scratch_last[2];
+    int scratch_busy[2];
+
     // per-call table shims (tables.cu)
     uint8_t *shim_host;   // pinned
     uint8_t *shim_dev;
@@ -92,6 +99,25 @@ static inline void xd_prof_end( x264dsp_ctx *ctx, int kind, int slot, cudaStream
 {
     if( slot >= 0 )
         cudaEventRecord( ctx->prof_ev[kind][slot][1], s );
+}
+
+enum { XD_SCRATCH_LOOKAHEAD = 0, XD_SCRATCH_DEBLOCK = 1 };
+// Before a launch that uses the context's wavefront scratch `which` on stream s: if the previous user ran on another
+// stream, make s wait for it (stream-side wait, the host does not block).  After the launch: mark s as the user.
+static inline int xd_scratch_acquire( x264dsp_ctx *ctx, int which, cudaStream_t s )
+{
+    if( ctx->scratch_busy[which] && ctx->scratch_last[which] != s )
+        XD_CHECK( cudaStreamWaitEvent( s, ctx->scratch_ev[which], 0 ) );
+    return 0;
+}
+static inline int xd_scratch_release( x264dsp_ctx *ctx, int which, cudaStream_t s )
+{
+    if( !ctx->scratch_ev[which] )
+        XD_CHECK( cudaEventCreateWithFlags( &ctx->scratch_ev[which], cudaEventDisableTiming ) );
+    XD_CHECK( cudaEventRecord( ctx->scratch_ev[which], s ) );
+    ctx->scratch_last[which] = s;
+    ctx->scratch_busy[which] = 1;
+    return 0;
 }
 
 // grows a device buffer to at least `bytes`

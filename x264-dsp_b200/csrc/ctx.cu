@@ -194,6 +194,10 @@ int xd_reserve_pinned( void **p, size_t *cap, size_t bytes )
     return 0;
 }
 
+// every failure after the calloc goes through x264dsp_destroy, which copes with a half-built context
+#define XD_CREATE_CHECK( call ) \
+    do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { free( host ); x264dsp_destroy( ctx ); cudaGetLastError(); return (int)e_; } } while( 0 )
+
 extern "C" int x264dsp_create( int device, x264dsp_ctx_t **out )
 {
     if( !out )
@@ -209,19 +213,23 @@ extern "C" int x264dsp_create( int device, x264dsp_ctx_t **out )
     x264dsp_ctx *ctx = (x264dsp_ctx *)calloc( 1, sizeof( x264dsp_ctx ) );
     if( !ctx )
         return X264DSP_E_NOMEM;
+    uint16_t *host = NULL;
     ctx->device = device;
     cudaDeviceProp prop;
-    XD_CHECK( cudaGetDeviceProperties( &prop, device ) );
+    XD_CREATE_CHECK( cudaGetDeviceProperties( &prop, device ) );
     ctx->sm_count = prop.multiProcessorCount;
-    XD_CHECK( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
+    XD_CREATE_CHECK( cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) );
     for( int i = 0; i < XD_AUX_STREAMS; i++ )
-        XD_CHECK( cudaStreamCreateWithFlags( &ctx->aux[i], cudaStreamNonBlocking ) );
+        XD_CREATE_CHECK( cudaStreamCreateWithFlags( &ctx->aux[i], cudaStreamNonBlocking ) );
 
     // one cost table per distinct lambda, shared between the QPs that map to it
     {
-        uint16_t *host = (uint16_t *)malloc( 52 * 8193 * sizeof( uint16_t ) );
+        host = (uint16_t *)malloc( 52 * 8193 * sizeof( uint16_t ) );
         if( !host )
+        {
+            x264dsp_destroy( ctx );
             return X264DSP_E_NOMEM;
+        }
         int n_tables = 0;
         int first_qp_of_table[52];
         int table_of_qp[52];
@@ -238,18 +246,29 @@ extern "C" int x264dsp_create( int device, x264dsp_ctx_t **out )
         for( int t = 0; t < n_tables; t++ )
             x264dsp_cost_mv_table( first_qp_of_table[t], host + (size_t)t * 8193 );
         // pad each table to 8200 entries so that every table starts 16-byte aligned
-        XD_CHECK( cudaMalloc( (void **)&ctx->cost_mv_store, (size_t)n_tables * 8200 * sizeof( uint16_t ) ) );
+        XD_CREATE_CHECK( cudaMalloc( (void **)&ctx->cost_mv_store, (size_t)n_tables * 8200 * sizeof( uint16_t ) ) );
         for( int t = 0; t < n_tables; t++ )
-            XD_CHECK( cudaMemcpy( ctx->cost_mv_store + (size_t)t * 8200, host + (size_t)t * 8193,
-                                  8193 * sizeof( uint16_t ), cudaMemcpyHostToDevice ) );
+            XD_CREATE_CHECK( cudaMemcpy( ctx->cost_mv_store + (size_t)t * 8200, host + (size_t)t * 8193,
+                                         8193 * sizeof( uint16_t ), cudaMemcpyHostToDevice ) );
         for( int qp = 0; qp < 52; qp++ )
             ctx->cost_mv_dev[qp] = ctx->cost_mv_store + (size_t)table_of_qp[qp] * 8200;
         free( host );
+        host = NULL;
     }
-    XD_CHECK( cudaMalloc( (void **)&ctx->la_ticket, 64 * sizeof( int32_t ) ) );
-    XD_CHECK( cudaMemset( ctx->la_ticket, 0, 64 * sizeof( int32_t ) ) );
+    XD_CREATE_CHECK( cudaMalloc( (void **)&ctx->la_ticket, 64 * sizeof( int32_t ) ) );
+    XD_CREATE_CHECK( cudaMemset( ctx->la_ticket, 0, 64 * sizeof( int32_t ) ) );
     ctx->la_epoch = 0;
     *out = ctx;
+    return 0;
+}
+
+// the DEVICE copy of cost_mv[qp] read back into host memory (what the search kernels index), for tests
+extern "C" int x264dsp_cost_mv_table_dev( x264dsp_ctx_t *ctx, int qp, uint16_t *out8193 )
+{
+    if( !ctx || !out8193 || qp < 0 || qp > 51 )
+        return X264DSP_E_ARG;
+    XD_CHECK( cudaSetDevice( ctx->device ) );
+    XD_CHECK( cudaMemcpy( out8193, ctx->cost_mv_dev[qp], 8193 * sizeof( uint16_t ), cudaMemcpyDeviceToHost ) );
     return 0;
 }
 
@@ -258,7 +277,8 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     if( !ctx )
         return;
     cudaSetDevice( ctx->device );
-    cudaStreamSynchronize( ctx->stream );
+    if( ctx->stream )
+        cudaStreamSynchronize( ctx->stream );
     cudaFree( ctx->cost_mv_store );
     cudaFree( ctx->la_sync );
     cudaFree( ctx->la_icost );
@@ -280,9 +300,14 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
                 cudaEventDestroy( ctx->prof_ev[k][i][0] );
                 cudaEventDestroy( ctx->prof_ev[k][i][1] );
             }
+    for( int i = 0; i < 2; i++ )
+        if( ctx->scratch_ev[i] )
+            cudaEventDestroy( ctx->scratch_ev[i] );
     for( int i = 0; i < XD_AUX_STREAMS; i++ )
-        cudaStreamDestroy( ctx->aux[i] );
-    cudaStreamDestroy( ctx->stream );
+        if( ctx->aux[i] )
+            cudaStreamDestroy( ctx->aux[i] );
+    if( ctx->stream )
+        cudaStreamDestroy( ctx->stream );
     free( ctx );
 }
 

@@ -389,8 +389,8 @@ xd_deblock_kernel( xd_db_args A )
 // aligned arrays, which the host checks.
 template<bool STAGED>
 __global__ void __launch_bounds__( 256 )
-xd_deblock_strength_kernel( int n, const uint8_t *__restrict__ nnz, const int8_t *__restrict__ ref,
-                            const int16_t *__restrict__ mv, uint8_t *__restrict__ bs )
+xd_deblock_strength_kernel( int n, const int8_t *__restrict__ mb_type, const uint8_t *__restrict__ nnz,
+                            const int8_t *__restrict__ ref, const int16_t *__restrict__ mv, uint8_t *__restrict__ bs )
 {
     __shared__ __align__( 16 ) uint8_t s_nnz[8 * 120];
     __shared__ __align__( 16 ) int8_t s_ref[8 * 80];
@@ -438,6 +438,19 @@ xd_deblock_strength_kernel( int n, const uint8_t *__restrict__ nnz, const int8_t
         v = mv + (size_t)m * 160;
     }
     const int dir = k >> 4, edge = ( k >> 2 ) & 3, i = k & 3;
+    if( mb_type )
+    {
+        // x264_macroblock_deblock_strength (common/macroblock.c:677-691): an intra macroblock sets its three inner
+        // edges to 3 and leaves bs[dir][0] alone (the outer edges of an intra macroblock are filtered with bS 4 by
+        // x264_frame_deblock_row whatever is stored there)
+        const int type = __ldg( mb_type + m );
+        if( type >= 0 && type < 4 )                          // IS_INTRA: I_4x4, I_8x8, I_16x16, I_PCM
+        {
+            if( edge )
+                bs[(size_t)m * 64 + dir * 32 + edge * 4 + i] = 3;
+            return;
+        }
+    }
     const int along = dir ? 1 : 8, across = dir ? 8 : 1;
     const int cur = 12 + edge * across + i * along, nb = cur - across;
     int s;
@@ -492,6 +505,9 @@ extern "C" int x264dsp_deblock_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geo
     int rc = xd_reserve_dev( (void **)&ctx->db_progress, &ctx->db_progress_cap, need );
     if( rc )
         return rc;
+    // the progress counters are the context's: a call on another stream queues behind the previous one
+    if( ( rc = xd_scratch_acquire( ctx, XD_SCRATCH_DEBLOCK, s ) ) )
+        return rc;
     XD_CHECK( cudaMemsetAsync( ctx->db_progress, 0, need, s ) );
     A.progress = ctx->db_progress;
     A.ticket = ctx->db_progress + rows;
@@ -510,7 +526,7 @@ extern "C" int x264dsp_deblock_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geo
     xd_prof_end( ctx, XD_PROF_DEBLOCK, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
-    return 0;
+    return xd_scratch_release( ctx, XD_SCRATCH_DEBLOCK, s );
 }
 
 extern "C" int x264dsp_deblock_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slot,
@@ -521,8 +537,8 @@ extern "C" int x264dsp_deblock_frame_dev( x264dsp_ctx_t *ctx, const x264dsp_geom
     return x264dsp_deblock_frames_dev( ctx, g, slot, 1, mb_type, partition, cbp, bs, qp, alpha_c0_offset, beta_offset, stream );
 }
 
-extern "C" int x264dsp_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const uint8_t *nnz, const int8_t *ref,
-                                              const int16_t *mv, uint8_t *bs, void *stream )
+extern "C" int x264dsp_macroblock_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const int8_t *mb_type, const uint8_t *nnz,
+                                                         const int8_t *ref, const int16_t *mv, uint8_t *bs, void *stream )
 {
     if( !ctx || n < 0 )
         return X264DSP_E_ARG;
@@ -533,10 +549,16 @@ extern "C" int x264dsp_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const ui
     const int64_t threads = (int64_t)n * 32;
     const bool aligned = ( ( (uintptr_t)nnz | (uintptr_t)ref | (uintptr_t)mv ) & 15 ) == 0;
     if( aligned )
-        xd_deblock_strength_kernel<true><<<(int)( ( threads + 255 ) / 256 ), 256, 0, xd_stream( ctx, stream )>>>( n, nnz, ref, mv, bs );
+        xd_deblock_strength_kernel<true><<<(int)( ( threads + 255 ) / 256 ), 256, 0, xd_stream( ctx, stream )>>>( n, mb_type, nnz, ref, mv, bs );
     else
-        xd_deblock_strength_kernel<false><<<(int)( ( threads + 255 ) / 256 ), 256, 0, xd_stream( ctx, stream )>>>( n, nnz, ref, mv, bs );
+        xd_deblock_strength_kernel<false><<<(int)( ( threads + 255 ) / 256 ), 256, 0, xd_stream( ctx, stream )>>>( n, mb_type, nnz, ref, mv, bs );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
+}
+
+extern "C" int x264dsp_deblock_strength_dev( x264dsp_ctx_t *ctx, int n, const uint8_t *nnz, const int8_t *ref,
+                                              const int16_t *mv, uint8_t *bs, void *stream )
+{
+    return x264dsp_macroblock_deblock_strength_dev( ctx, n, nullptr, nnz, ref, mv, bs, stream );
 }

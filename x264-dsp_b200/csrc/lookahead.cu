@@ -1588,13 +1588,21 @@ extern "C" int x264dsp_lookahead_frame_cost_dev( x264dsp_ctx_t *ctx, const x264d
     int n_inter = 0;
     const int32_t *b_dev, *p0_dev, *list_dev;
     const uint8_t *wi_dev;
-    int rc = xd_la_upload_desc( ctx, n_pairs, b, p0, want_intra, &n_inter, s, &b_dev, &p0_dev, &list_dev, &wi_dev );
+    // the sync words, the ticket and the batch description are the context's: a call on another stream queues behind
+    // the previous one instead of resetting its counters
+    int rc = xd_scratch_acquire( ctx, XD_SCRATCH_LOOKAHEAD, s );
+    if( rc )
+        return rc;
+    rc = xd_la_upload_desc( ctx, n_pairs, b, p0, want_intra, &n_inter, s, &b_dev, &p0_dev, &list_dev, &wi_dev );
     if( rc )
         return rc;
     if( ( rc = xd_la_prepare( ctx, g, n_pairs, s ) ) )
         return rc;
-    return xd_la_launch( ctx, g, slots, 0, n_pairs, b_dev, p0_dev, wi_dev, list_dev, n_inter, 0,
-                         mvs, costs, sums, row_satds, s );
+    rc = xd_la_launch( ctx, g, slots, 0, n_pairs, b_dev, p0_dev, wi_dev, list_dev, n_inter, 0,
+                       mvs, costs, sums, row_satds, s );
+    if( rc )
+        return rc;
+    return xd_scratch_release( ctx, XD_SCRATCH_LOOKAHEAD, s );
 }
 
 int xd_frame_lowres_from_luma( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *luma, uint8_t *slots,
@@ -1685,38 +1693,55 @@ extern "C" int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int 
     if( groups < 1 ) groups = 1;
     if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
     if( n_clips <= 4 ) groups = n_clips < 2 ? 1 : 2;
-    for( int gi = 0; gi < groups; gi++ )
+    // a failure in a later group must not return while earlier groups' copies are still writing into the caller's
+    // buffers: leave the loop, drain every stream that was used, then report
+#define XD_GROUP_CHECK( call ) { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { rc = (int)e_; break; } }
+    int used = 0;
+    for( int gi = 0; gi < groups && !rc; gi++ )
     {
         cudaStream_t s = ctx->aux[gi];
         const int c0 = (int)( (int64_t)n_clips * gi / groups ), c1 = (int)( (int64_t)n_clips * ( gi + 1 ) / groups );
         const int f0 = c0 * clip_len, nf = ( c1 - c0 ) * clip_len;
         if( nf <= 0 )
             continue;
+        used = gi + 1;
+        // a lookahead call enqueued earlier on some other stream still owns the context's sync words
+        if( ( rc = xd_scratch_acquire( ctx, XD_SCRATCH_LOOKAHEAD, s ) ) )
+            break;
         const uint8_t *src = luma + (size_t)f0 * pic;
         if( !pinned_in )
         {
             memcpy( ctx->stage_host + (size_t)f0 * pic, src, pic * nf );
             src = ctx->stage_host + (size_t)f0 * pic;
         }
-        XD_CHECK( cudaMemcpyAsync( ctx->stage_dev + (size_t)f0 * pic, src, pic * nf, cudaMemcpyHostToDevice, s ) );
+        XD_GROUP_CHECK( cudaMemcpyAsync( ctx->stage_dev + (size_t)f0 * pic, src, pic * nf, cudaMemcpyHostToDevice, s ) );
         uint8_t *slots = ctx->clip_slots + (size_t)f0 * g.slot_bytes;
-        if( ( rc = xd_frame_lowres_from_luma( ctx, &g, ctx->stage_dev + (size_t)f0 * pic, slots, nf, s ) ) ) return rc;
+        if( ( rc = xd_frame_lowres_from_luma( ctx, &g, ctx->stage_dev + (size_t)f0 * pic, slots, nf, s ) ) )
+            break;
         // every clip of the group contributes clip_len-1 inter pairs, in frame order
         const int inter0 = c0 * ( clip_len - 1 ), ninter = ( c1 - c0 ) * ( clip_len - 1 );
         if( ( rc = xd_la_launch( ctx, &g, ctx->clip_slots, f0, nf, b_dev, p0_dev, wi_dev, list_dev + inter0, ninter, gi,
                                  d_mvs, d_costs, d_sums, NULL, s ) ) )
-            return rc;
+            break;
         uint8_t *o_mv = pinned_out ? (uint8_t *)mvs : h_out;
         uint8_t *o_cost = pinned_out ? (uint8_t *)costs : h_out + mv_bytes;
         uint8_t *o_sum = pinned_out ? (uint8_t *)sums : h_out + mv_bytes + cost_bytes;
         const size_t mo = (size_t)f0 * mbc * 2 * sizeof( int16_t ), co = (size_t)f0 * mbc * sizeof( int32_t );
         const size_t so = (size_t)f0 * X264DSP_LA_SUMS * sizeof( int32_t );
-        XD_CHECK( cudaMemcpyAsync( o_mv + mo, (uint8_t *)d_mvs + mo, (size_t)nf * mbc * 2 * sizeof( int16_t ), cudaMemcpyDeviceToHost, s ) );
-        XD_CHECK( cudaMemcpyAsync( o_cost + co, (uint8_t *)d_costs + co, (size_t)nf * mbc * sizeof( int32_t ), cudaMemcpyDeviceToHost, s ) );
-        XD_CHECK( cudaMemcpyAsync( o_sum + so, (uint8_t *)d_sums + so, (size_t)nf * X264DSP_LA_SUMS * sizeof( int32_t ), cudaMemcpyDeviceToHost, s ) );
+        XD_GROUP_CHECK( cudaMemcpyAsync( o_mv + mo, (uint8_t *)d_mvs + mo, (size_t)nf * mbc * 2 * sizeof( int16_t ), cudaMemcpyDeviceToHost, s ) );
+        XD_GROUP_CHECK( cudaMemcpyAsync( o_cost + co, (uint8_t *)d_costs + co, (size_t)nf * mbc * sizeof( int32_t ), cudaMemcpyDeviceToHost, s ) );
+        XD_GROUP_CHECK( cudaMemcpyAsync( o_sum + so, (uint8_t *)d_sums + so, (size_t)nf * X264DSP_LA_SUMS * sizeof( int32_t ), cudaMemcpyDeviceToHost, s ) );
     }
-    for( int gi = 0; gi < groups; gi++ )
-        XD_CHECK( cudaStreamSynchronize( ctx->aux[gi] ) );
+#undef XD_GROUP_CHECK
+    for( int gi = 0; gi < used; gi++ )
+    {
+        const cudaError_t e = cudaStreamSynchronize( ctx->aux[gi] );
+        if( e != cudaSuccess && !rc )
+            rc = (int)e;
+    }
+    ctx->scratch_busy[XD_SCRATCH_LOOKAHEAD] = 0;         // everything that used the scratch has finished
+    if( rc )
+        return rc;
     if( !pinned_out )
     {
         memcpy( mvs, h_out, mv_bytes );

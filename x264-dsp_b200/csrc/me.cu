@@ -27,6 +27,7 @@ struct xd_me_blk
     int mvpx, mvpy;
     int minx, miny, maxx, maxy;     // full-pel limits
     int sminx, sminy, smaxx, smaxy; // sub-pel limits
+    bool fpel_satd;                 // h->pixf.fpelcmp == satd: me=TESA with subme >= 2 (encoder/encoder.c:412-432)
 };
 
 __device__ __forceinline__ int xd_me_bits( const xd_me_blk &B, int qx, int qy )
@@ -69,7 +70,7 @@ __device__ __forceinline__ uint32_t xd_me_pred4( const xd_qpel_src &s, int strid
 }
 
 // SAD of the block at quarter-pel (qx,qy); lanes of one candidate group cooperate (sub = lane & 7)
-__device__ __forceinline__ int xd_me_sad( const xd_me_blk &B, int qx, int qy, int sub )
+__device__ __forceinline__ int xd_me_sad_raw( const xd_me_blk &B, int qx, int qy, int sub )
 {
     const xd_qpel_src s = xd_me_src( B, qx, qy );
     int acc = 0;
@@ -158,6 +159,12 @@ __device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, i
     return acc;
 }
 
+// h->pixf.fpelcmp[i_pixel]: SAD, except under TESA where mbcmp_init (encoder.c:429-432) makes it SATD
+__device__ __forceinline__ int xd_me_sad( const xd_me_blk &B, int qx, int qy, int sub )
+{
+    return B.fpel_satd ? xd_me_satd( B, qx, qy, sub ) : xd_me_sad_raw( B, qx, qy, sub );
+}
+
 __device__ __forceinline__ int xd_min_groups( int key )
 {
     key = min( key, __shfl_xor_sync( 0xffffffffu, key, 8 ) );
@@ -187,9 +194,10 @@ struct xd_me_state
     int mvx, mvy, cost, cost_mv;
 };
 
-// refine_subpel (me.c:466-587) with p_halfpel_thresh == NULL
+// refine_subpel (me.c:466-587).  thresh = *p_halfpel_thresh (nullptr: the caller passed NULL); when the early
+// termination of me.c:527-536 fires, mv and cost are stored and cost_mv keeps its previous value, as there.
 __device__ void xd_me_refine( const xd_me_blk &B, xd_me_state &S, int subme, int hpel_iters, int qpel_iters,
-                              bool final_refine, int lane )
+                              bool final_refine, int lane, int *thresh = nullptr )
 {
     const int cand = lane >> 3, sub = lane & 7;
     const int dx = cand == 2 ? -1 : cand == 3 ? 1 : 0;
@@ -217,8 +225,21 @@ __device__ void xd_me_refine( const xd_me_blk &B, xd_me_state &S, int subme, int
         bmx += w == 2 ? -2 : w == 3 ? 2 : 0;
         bmy += w == 0 ? -2 : w == 1 ? 2 : 0;
     }
-    if( !final_refine )                                                  // me.c:519-524
+    if( !final_refine && !B.fpel_satd )                                  // me.c:519-524 (mbcmp_unaligned != fpelcmp)
         bcost = xd_me_satd( B, bmx, bmy, sub ) + xd_me_bits( B, bmx, bmy );
+
+    if( thresh )                                                         // me.c:526-539
+    {
+        if( ( bcost * 7 ) >> 3 > *thresh )
+        {
+            S.cost = bcost;
+            S.mvx = bmx;
+            S.mvy = bmy;
+            return;
+        }
+        else if( bcost < *thresh )
+            *thresh = bcost;
+    }
 
     if( subme != 1 )
     {
@@ -266,7 +287,8 @@ __device__ void xd_me_refine( const xd_me_blk &B, xd_me_state &S, int subme, int
 __global__ void __launch_bounds__( ME_WARPS * 32 )
 xd_me_search_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, const uint8_t *__restrict__ fref_slot,
                      x264dsp_me_params_t P, const uint16_t *__restrict__ cost_mv, int n,
-                     const x264dsp_me_block_t *__restrict__ blocks, x264dsp_me_result_t *__restrict__ results )
+                     const x264dsp_me_block_t *__restrict__ blocks, x264dsp_me_result_t *__restrict__ results,
+                     int mode, int32_t *__restrict__ halfpel_thresh )
 {
     const int lane = threadIdx.x & 31;
     const int blk = blockIdx.x * ME_WARPS + ( threadIdx.x >> 5 );
@@ -294,6 +316,37 @@ xd_me_search_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, co
     B.smaxx = in->mv_max_spel[0]; B.smaxy = in->mv_max_spel[1];
     const int n_mvc = min( max( in->i_mvc, 0 ), 16 );
     const int subme = P.subpel_refine;
+    B.fpel_satd = P.me_method == X264DSP_ME_TESA && subme >= 2;
+    int thresh_val = halfpel_thresh ? halfpel_thresh[blk] : 0;
+    int *thresh = halfpel_thresh ? &thresh_val : nullptr;
+
+    if( mode != X264DSP_ME_MODE_SEARCH )
+    {
+        // x264_me_refine_qpel_refdupe (me.c:437-440) / x264_me_refine_qpel alone (me.c:426-435; the caller has
+        // already taken i_ref_cost off the cost): m->mv, m->cost, m->cost_mv come in through results[blk]
+        xd_me_state S;
+        S.mvx = results[blk].mv[0];
+        S.mvy = results[blk].mv[1];
+        S.cost = results[blk].cost;
+        S.cost_mv = results[blk].cost_mv;
+        __syncwarp();
+        if( mode == X264DSP_ME_MODE_REFDUPE )
+            xd_me_refine( B, S, subme, 0, min( 2, (int)xd_subpel_iters[subme][3] ), false, lane, thresh );
+        else
+            xd_me_refine( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
+        if( lane == 0 )
+        {
+            x264dsp_me_result_t r;
+            r.mv[0] = (int16_t)S.mvx;
+            r.mv[1] = (int16_t)S.mvy;
+            r.cost = S.cost;
+            r.cost_mv = S.cost_mv;
+            results[blk] = r;
+            if( halfpel_thresh )
+                halfpel_thresh[blk] = thresh_val;
+        }
+        return;
+    }
 
     int bmx = xd_clip3( B.mvpx, B.minx * 4, B.maxx * 4 ), bmy = xd_clip3( B.mvpy, B.miny * 4, B.maxy * 4 );
     const int pmx = ( bmx + 2 ) >> 2, pmy = ( bmy + 2 ) >> 2;
@@ -481,7 +534,7 @@ xd_me_search_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, co
         S.cost += S.cost_mv;
 
     if( subme >= 2 )
-        xd_me_refine( B, S, subme, xd_subpel_iters[subme][2], xd_subpel_iters[subme][3], false, lane );
+        xd_me_refine( B, S, subme, xd_subpel_iters[subme][2], xd_subpel_iters[subme][3], false, lane, thresh );
     if( P.refine_qpel )                                                  // me.c:426-435, i_ref_cost = 0
         xd_me_refine( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
 
@@ -493,20 +546,30 @@ xd_me_search_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, co
         r.cost = S.cost;
         r.cost_mv = S.cost_mv;
         results[blk] = r;
+        if( halfpel_thresh )
+            halfpel_thresh[blk] = thresh_val;
     }
 }
 
-extern "C" int x264dsp_me_search_batch_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
-                                             const uint8_t *fenc_slot, const uint8_t *fref_slot,
-                                             const x264dsp_me_params_t *params, int n,
-                                             const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
-                                             void *stream )
+// me_method: DIA and HEX are the reference's two pattern searches; UMH / ESA / TESA pass its parameter check
+// (encoder/encoder.c:251-259) but have no case in the switch of x264_me_search_ref (me.c:235-394), so the
+// search is "predictors, then sub-pel refinement" -- and TESA with subme >= 2 additionally turns fpelcmp into SATD.
+int xd_me_params_ok( const x264dsp_me_params_t *p )
+{
+    return p->subpel_refine >= 1 && p->subpel_refine <= 5 && p->qp >= 0 && p->qp <= 51
+        && p->me_method >= X264DSP_ME_DIA && p->me_method <= X264DSP_ME_TESA && p->me_range >= 1;
+}
+
+extern "C" int x264dsp_me_search_batch_ex_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                                const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                                                const x264dsp_me_params_t *params, int n,
+                                                const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                                int mode, int32_t *halfpel_thresh, void *stream )
 {
     if( !ctx || !g || !fenc_slot || !fref_slot || !params || n < 0 )
         return X264DSP_E_ARG;
-    if( params->subpel_refine < 1 || params->subpel_refine > 5 || params->qp < 0 || params->qp > 51
-        || params->me_method < X264DSP_ME_DIA || params->me_method > X264DSP_ME_HEX || params->me_range < 1 )
-        return X264DSP_E_ARG;                        // subme 0 and UMH/ESA/TESA do not exist in the reference
+    if( !xd_me_params_ok( params ) || mode < X264DSP_ME_MODE_SEARCH || mode > X264DSP_ME_MODE_REFINE_QPEL )
+        return X264DSP_E_ARG;                        // subme 0 does not exist in the reference
     if( n == 0 )
         return 0;
     if( !blocks || !results )
@@ -515,9 +578,20 @@ extern "C" int x264dsp_me_search_batch_dev( x264dsp_ctx_t *ctx, const x264dsp_ge
     const int grid = ( n + ME_WARPS - 1 ) / ME_WARPS;
     const int pslot = xd_prof_begin( ctx, XD_PROF_ME, s );
     xd_me_search_kernel<<<grid, ME_WARPS * 32, 0, s>>>( *g, fenc_slot, fref_slot, *params,
-                                                        ctx->cost_mv_dev[params->qp] + 4096, n, blocks, results );
+                                                        ctx->cost_mv_dev[params->qp] + 4096, n, blocks, results,
+                                                        mode, halfpel_thresh );
     xd_prof_end( ctx, XD_PROF_ME, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
     return 0;
+}
+
+extern "C" int x264dsp_me_search_batch_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g,
+                                             const uint8_t *fenc_slot, const uint8_t *fref_slot,
+                                             const x264dsp_me_params_t *params, int n,
+                                             const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
+                                             void *stream )
+{
+    return x264dsp_me_search_batch_ex_dev( ctx, g, fenc_slot, fref_slot, params, n, blocks, results,
+                                           X264DSP_ME_MODE_SEARCH, nullptr, stream );
 }

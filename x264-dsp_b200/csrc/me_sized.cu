@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "leaf.cuh"
 
+int xd_me_params_ok( const x264dsp_me_params_t *p );   // me.cu
+
 #define MES_COST_MAX ( 1 << 28 )
 #define MES_THREADS 128
 
@@ -39,6 +41,7 @@ struct xd_mes_blk
     int mvpx, mvpy;
     int minx, miny, maxx, maxy;     // full-pel limits
     int sminx, sminy, smaxx, smaxy; // sub-pel limits
+    bool fpel_satd;                 // fpelcmp == satd: me=TESA with subme >= 2 (encoder/encoder.c:412-432)
 };
 
 __device__ __forceinline__ int xd_mes_bits( const xd_mes_blk &B, int qx, int qy )
@@ -152,7 +155,7 @@ struct xd_mes_state
     int mvx, mvy, cost, cost_mv;
 };
 
-#define MES_SAD( qx, qy ) ( xd_mes_cost<W, H>( B, f, tile0, ( qx ), ( qy ), false, gmask ) + xd_mes_bits( B, ( qx ), ( qy ) ) )
+#define MES_SAD( qx, qy ) ( xd_mes_cost<W, H>( B, f, tile0, ( qx ), ( qy ), B.fpel_satd, gmask ) + xd_mes_bits( B, ( qx ), ( qy ) ) )
 #define MES_SATD( qx, qy ) ( xd_mes_cost<W, H>( B, f, tile0, ( qx ), ( qy ), true, gmask ) + xd_mes_bits( B, ( qx ), ( qy ) ) )
 
 // refine_subpel (me.c:466-587) with p_halfpel_thresh == NULL
@@ -183,7 +186,7 @@ __device__ void xd_mes_refine( const xd_mes_blk &B, const uint32_t *f, int tile0
         if( bmx == omx && bmy == omy )
             break;
     }
-    if( !final_refine )                                                  // me.c:519-524
+    if( !final_refine && !B.fpel_satd )                                  // me.c:519-524 (mbcmp_unaligned != fpelcmp)
         bcost = MES_SATD( bmx, bmy );
 
     if( subme != 1 )
@@ -258,6 +261,7 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
     B.smaxx = in->mv_max_spel[0]; B.smaxy = in->mv_max_spel[1];
     const int n_mvc = min( max( in->i_mvc, 0 ), 16 );
     const int subme = P.subpel_refine;
+    B.fpel_satd = P.me_method == X264DSP_ME_TESA && subme >= 2;
 
     // this lane's source tile(s) stay in registers for the whole search
     const int tile0 = sub * C::NT;
@@ -320,7 +324,7 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
         // me.c:194-229: rounded MVP without mv cost, then the rounded / clipped candidates
         bmx = pmx;
         bmy = pmy;
-        bcost = xd_mes_cost<W, H>( B, f, tile0, pmx << 2, pmy << 2, false, gmask );
+        bcost = xd_mes_cost<W, H>( B, f, tile0, pmx << 2, pmy << 2, B.fpel_satd, gmask );
         pmv = xd_mes_pack( pmx, pmy );
         int sel_x = pmx, sel_y = pmy;
         for( int i = 0; i < n_mvc; i++ )
@@ -363,7 +367,7 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
             bmy = omy + xd_mes_dia[best][1];
         } while( --left && xd_mes_in_range( B, bmx, bmy ) );
     }
-    else
+    else if( P.me_method == X264DSP_ME_HEX )
     {
         // me.c:276-388: hexagon, then square refinement
         int dir = -1;
@@ -411,6 +415,7 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
             bmy += xd_mes_square[sq][1];
         }
     }
+    // UMH / ESA / TESA: no case in the reference's switch (me.c:389-394) -- predictors and sub-pel refinement only
 
     // me.c:397-414
     xd_mes_state S;
@@ -467,9 +472,8 @@ extern "C" int x264dsp_me_search_sized_frames_dev( x264dsp_ctx_t *ctx, const x26
     if( !ctx || !g || !fenc_slot || !fref_slot || !params || n < 0 || i_pixel < 0 || i_pixel > 7 || n_frames <= 0
         || n_frames > 65535 )
         return X264DSP_E_ARG;
-    if( params->subpel_refine < 1 || params->subpel_refine > 5 || params->qp < 0 || params->qp > 51
-        || params->me_method < X264DSP_ME_DIA || params->me_method > X264DSP_ME_HEX || params->me_range < 1 )
-        return X264DSP_E_ARG;                        // subme 0 and UMH/ESA/TESA do not exist in the reference
+    if( !xd_me_params_ok( params ) )
+        return X264DSP_E_ARG;                        // subme 0 does not exist in the reference
     if( n == 0 )
         return 0;
     if( !blocks || !results )
