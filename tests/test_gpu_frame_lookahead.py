@@ -59,7 +59,7 @@ def diff_report(a, b, g):
 # the benchmark geometries, plus widths whose right-edge remainder (n_units % 30, n_units = W16/8 + 1) lands in each of the
 # hpel kernel's narrow tail strips: 1080p / 4K -> 1 unit (4 lanes), 256 -> 3 units (8 lanes), 320 -> 11 units (16 lanes),
 # 352 / 368 -> 15 / 17 units (32 lanes), 200 -> a single partial strip, 720 -> 1 unit after three full strips
-HPEL_SIZES = SIZES + [(1920, 1080), (3840, 2160), (256, 64), (320, 48), (720, 96), (1280, 720)]
+HPEL_SIZES = SIZES + [(1920, 1080), (3840, 2160), (256, 64), (320, 64), (720, 96), (1280, 720)]
 
 
 @pytest.mark.parametrize("w,h", HPEL_SIZES)

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--qp", type=int, default=26)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--batched-only", action="store_true", help="skip the one-frame-per-launch variants (ncu captures)")
     args = ap.parse_args()
 
     import torch
@@ -193,10 +194,11 @@ def main():
         def run_res():
             for p in range(P):
                 ctx.residual_frame(g, sl(slots, p + 1), sl(pred, p), args.qp, lv, nz, cbp[p])
-        run_res()                                # warm-up (first launch of the kernel)
+        run_res()                                # warm-up (first launch of the kernel); fills cbp[]
         run_mc()
-        t = timed(run_res, warm=0, reps=1)       # in place: one pass over freshly predicted frames
-        report("residual_frame", t, P, nmb * (384 * 3 + 784 + 29), "one frame per launch; SURVEY 8(d): ~2.0 kB/MB")
+        if not args.batched_only:
+            t = timed(run_res, warm=0, reps=1)   # in place: one pass over freshly predicted frames
+            report("residual_frame", t, P, nmb * (384 * 3 + 784 + 29), "one frame per launch; SURVEY 8(d): ~2.0 kB/MB")
         lv_all = torch.zeros((P, nmb, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda")
         nz_all = torch.zeros((P, nmb, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda")
         cbp_b = torch.zeros((P, nmb), dtype=torch.int16, device="cuda")
@@ -215,10 +217,13 @@ def main():
         def run_db1():
             for p in range(P):
                 ctx.deblock_frame(g, sl(pred, p), mb_type[p], part[p], cbp[p], bs[p], args.qp, 0, 0)
-        run_db1()                                # warm-up; deblocking an already deblocked frame is still a full pass
-        t = timed(run_db1, warm=0, reps=1)
-        report("deblock_frame_one_per_launch", t, P, nmb * (768 + 64),
-               "one frame per launch: bound by the wavefront critical path (mb_w + 2 mb_h macroblock times)")
+        if not args.batched_only:
+            run_db1()                            # warm-up; deblocking an already deblocked frame is still a full pass
+            t = timed(run_db1, warm=0, reps=1)
+            report("deblock_frame_one_per_launch", t, P, nmb * (768 + 64),
+                   "one frame per launch: bound by the wavefront critical path (mb_w + 2 mb_h macroblock times)")
+        else:
+            ctx.deblock_frames(g, pred, P, mb_type, part, cbp_all, bs, args.qp, 0, 0)
         t = timed(lambda: ctx.deblock_frames(g, pred, P, mb_type, part, cbp_all, bs, args.qp, 0, 0), warm=0, reps=1)
         report("deblock_frames_batched", t, P, nmb * (768 + 64), f"{P} frames per launch; SURVEY 8(d): 768 B rd+wr + 64 B bS per MB")
         # one frame per call is a 2 us kernel behind a launch; a clip's macroblocks go in one call

@@ -250,20 +250,31 @@ __device__ __noinline__ static int xd_optimize_chroma_dc( int dc[4], int dmf )
 
 // ---------------------------------------------------------------------------------------------
 // deblocking line filters
-static __constant__ int8_t xd_tc0_tab[52][3] =
+#define XD_TC0_ROWS \
+{ \
+    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0}, \
+    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,1},{0,0,1},{0,0,1}, \
+    {0,0,1},{0,1,1},{0,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,2},{1,1,2},{1,1,2}, \
+    {1,1,2},{1,2,3},{1,2,3},{2,2,3},{2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6}, \
+    {4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},{10,13,20}, \
+    {11,15,23},{13,17,25} \
+}
+static __constant__ int8_t xd_tc0_tab[52][3] = XD_TC0_ROWS;
+static const int8_t xd_tc0_host[52][3] = XD_TC0_ROWS;
+// tc0 of bS = 1, 2, 3 at a (clamped) indexA, one byte each; indexA < 0: zeros
+static inline uint32_t xd_tc0_packed( int ia )
 {
-    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},
-    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,1},{0,0,1},{0,0,1},
-    {0,0,1},{0,1,1},{0,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,2},{1,1,2},{1,1,2},
-    {1,1,2},{1,2,3},{1,2,3},{2,2,3},{2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},
-    {4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},{10,13,20},
-    {11,15,23},{13,17,25}
-};
+    if( ia < 0 )
+        return 0;
+    return (uint32_t)xd_tc0_host[ia][0] | ( (uint32_t)xd_tc0_host[ia][1] << 8 ) | ( (uint32_t)xd_tc0_host[ia][2] << 16 );
+}
+
 
 struct xd_db_params
 {
     int alpha, beta, alphac, betac;     // luma / chroma thresholds from the slice QP
     int ia, iac;                        // clamped indexA (luma, chroma); < 0 : tc0 = 0
+    uint32_t tc_luma, tc_chroma;        // tc0 for bS = 1, 2, 3 at ia / iac, one byte each (xd_tc0_packed)
 };
 
 __device__ __forceinline__ int xd_tc0( int index_a, int bs )
