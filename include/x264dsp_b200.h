@@ -329,6 +329,16 @@ int x264dsp_me_search_sized_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t
                                         const x264dsp_me_block_t *blocks, x264dsp_me_result_t *results,
                                         void *stream );
 
+/* The same from HOST memory (SURVEY 8(d) config 3 end to end): luma holds n_pairs + 1 pictures of width x height bytes,
+ * frame f + 1 is searched in frame f, whose border expansion and half-pel planes (x264_frame_expand_border,
+ * x264_frame_filter) are built on the device.  For each of the n_sizes partition sizes i_pixel[s], blocks[s] is a host
+ * array of n_pairs x n_blocks[s] block descriptions (pair-major) and results[s] receives as many results.  Copies of
+ * the pictures, the block lists and the results are inside the call; the sizes run on separate streams. */
+int x264dsp_me_search_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_pairs, const uint8_t *luma,
+                                   const x264dsp_me_params_t *params, int n_sizes, const int32_t *i_pixel,
+                                   const int32_t *n_blocks, const x264dsp_me_block_t *const *blocks,
+                                   x264dsp_me_result_t *const *results );
+
 /* ------------------------------------------------------------------ residual
  * The inter-macroblock branch of x264_macroblock_encode + x264_mb_encode_chroma
  * (encoder/macroblock.c:175-305, 379-471) for every macroblock of a frame, b_dct_decimate = 1,
@@ -438,6 +448,19 @@ int x264dsp_deblock_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uin
                                 const int8_t *mb_type, const uint8_t *partition, const int16_t *cbp,
                                 const uint8_t *bs, int qp, int alpha_c0_offset, int beta_offset,
                                 void *stream );
+
+/* SURVEY 8(d) config 4 from HOST memory: n_frames P frames of P_L0 16x16 macroblocks.  i420 holds n_frames + 1 planar
+ * pictures; frame f + 1 is predicted from frame f with mv16[f][mb][2] (x264_mb_mc), coded (x264_macroblock_encode: levels,
+ * nnz, cbp as in x264dsp_residual_frames_dev) and its reconstruction deblocked (x264_frame_deblock_row with the caller's
+ * mb_type / partition / bs per macroblock, the cbp just computed); recon_i420 receives the n_frames deblocked pictures
+ * as planar I420 (width x height).  All copies are inside the call; groups of frames run on separate streams. */
+int x264dsp_recon_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                               const int16_t *mv16, int qp, const int8_t *mb_type, const uint8_t *partition,
+                               const uint8_t *bs, int alpha_c0_offset, int beta_offset,
+                               int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 );
+/* slot -> planar I420 (picture area only): the inverse of x264dsp_frame_load_i420_dev */
+int x264dsp_frame_store_i420_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots,
+                                  uint8_t *i420, int n_frames, void *stream );
 
 /* deblock_strength_c (common/deblock.c:297-323) for n macroblocks:
  * nnz [n][120], ref [n][2][40], mv [n][2][40][2] -> bs [n][2][8][4] (scan8 layout). */

@@ -474,6 +474,100 @@ int xref_encode_inter_mb( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c
     return h->mb.cbp[0];
 }
 
+/* A whole P frame of P_L0 16x16 macroblocks through the reference's own functions -- x264_mb_mc (mc_luma + mc_chroma,
+ * common/macroblock.c:8-28), x264_macroblock_encode (encoder/macroblock.c:310) -- the CPU side of SURVEY 8(d) config 4:
+ * fenc = source frame, fref = reference frame with its filtered planes, fdec receives the reconstruction (luma plane +
+ * NV12 chroma, not yet deblocked; xref_deblock_frame does that).  mv16 [mb][2]; levels [mb][392], nnz [mb][27],
+ * cbp [mb] as in xref_encode_inter_mb. */
+void xref_recon_frame( void *hv, void *fencv, void *frefv, void *fdecv, const int16_t *mv16, int qp,
+                       int16_t *levels, uint8_t *nnz, int16_t *cbp )
+{
+    x264_t *h = hv;
+    x264_frame_t *fenc = fencv, *fref = frefv, *fdec = fdecv;
+    const int W = h->mb.i_mb_width, H = h->mb.i_mb_height;
+    const int ls = fref->i_stride[0], cs = fref->i_stride[1];
+    int mb_x, mb_y, i, y;
+    h->sh.i_type = SLICE_TYPE_P;
+    x264_macroblock_thread_init( h );
+    h->mb.b_noise_reduction = 0;
+    h->mb.b_transform_8x8 = 0;
+    h->nr_count = h->nr_count_buf[0];
+    h->mb.i_qp = qp;
+    h->mb.i_chroma_qp = h->chroma_qp_table[qp];
+    h->mb.pic.i_stride[0] = ls;
+    h->mb.pic.i_stride[1] = cs;
+    for( mb_y = 0; mb_y < H; mb_y++ )
+        for( mb_x = 0; mb_x < W; mb_x++ )
+        {
+            const int xy = mb_y * W + mb_x;
+            const intptr_t oy = (intptr_t)( mb_y << 4 ) * ls + ( mb_x << 4 ), oc = (intptr_t)( mb_y << 3 ) * cs + ( mb_x << 4 );
+            int16_t *lv = levels + (size_t)xy * 392;
+            uint8_t *nz = nnz + (size_t)xy * 27;
+            h->mb.i_mb_x = mb_x;
+            h->mb.i_mb_y = mb_y;
+            h->mb.i_mb_xy = 0;                      /* h->mb.cbp[] etc. are per-frame arrays: slot 0 is scratch here */
+            h->mb.i_type = P_L0;
+            h->mb.i_partition = D_16x16;
+            h->mb.b_skip_mc = 0;
+            h->mb.mv_min[0] = ( -( mb_x << 4 ) - 24 ) << 2;                                   /* analyse.c:378-393 */
+            h->mb.mv_max[0] = ( ( ( W - mb_x - 1 ) << 4 ) + 24 ) << 2;
+            h->mb.mv_min[1] = ( -( mb_y << 4 ) - 24 ) << 2;
+            h->mb.mv_max[1] = ( ( ( H - mb_y - 1 ) << 4 ) + 24 ) << 2;
+            for( i = 0; i < 4; i++ )
+                h->mb.pic.p_fref[0][0][i] = fref->filtered[0][i] + oy;
+            h->mb.pic.p_fref[0][0][4] = fref->plane[1] + oc;
+            h->mb.cache.ref[0][x264_scan8[0]] = 0;
+            h->mb.cache.mv[0][x264_scan8[0]][0] = mv16[2*xy];
+            h->mb.cache.mv[0][x264_scan8[0]][1] = mv16[2*xy+1];
+            h->mb.cache.pskip_mv[0] = (int16_t)( mv16[2*xy] + 1 );      /* != mv: keep the type P_L0 */
+            h->mb.cache.pskip_mv[1] = mv16[2*xy+1];
+            memset( &h->dct, 0, sizeof(h->dct) );
+            memset( h->mb.cache.non_zero_count, 0, sizeof(h->mb.cache.non_zero_count) );
+            for( y = 0; y < 16; y++ )
+                memcpy( h->mb.pic.p_fenc[0] + y*FENC_STRIDE, fenc->plane[0] + oy + (intptr_t)y * fenc->i_stride[0], 16 );
+            for( y = 0; y < 8; y++ )
+            {
+                /* NV12 -> the reference's fenc chroma layout: U at +0, V at +8 (x264_macroblock_load_pic_pointers) */
+                const pixel *src = fenc->plane[1] + oc + (intptr_t)y * fenc->i_stride[1];
+                for( i = 0; i < 8; i++ )
+                {
+                    h->mb.pic.p_fenc[1][y*FENC_STRIDE + i] = src[2*i];
+                    h->mb.pic.p_fenc[2][y*FENC_STRIDE + i] = src[2*i+1];
+                }
+            }
+            x264_mb_mc( h );
+            h->mb.b_skip_mc = 1;
+            x264_macroblock_encode( h );
+            for( y = 0; y < 16; y++ )
+                memcpy( fdec->plane[0] + oy + (intptr_t)y * ls, h->mb.pic.p_fdec[0] + y*FDEC_STRIDE, 16 );
+            for( y = 0; y < 8; y++ )
+            {
+                pixel *dst = fdec->plane[1] + oc + (intptr_t)y * cs;
+                for( i = 0; i < 8; i++ )
+                {
+                    dst[2*i] = h->mb.pic.p_fdec[1][y*FDEC_STRIDE + i];
+                    dst[2*i+1] = h->mb.pic.p_fdec[2][y*FDEC_STRIDE + i];
+                }
+            }
+            memcpy( lv, h->dct.luma4x4[0], 16*16*sizeof(int16_t) );
+            memcpy( lv + 256, h->dct.chroma_dc[0], 4*sizeof(int16_t) );
+            memcpy( lv + 260, h->dct.chroma_dc[1], 4*sizeof(int16_t) );
+            memcpy( lv + 264, h->dct.luma4x4[16], 4*16*sizeof(int16_t) );
+            memcpy( lv + 328, h->dct.luma4x4[32], 4*16*sizeof(int16_t) );
+            for( i = 0; i < 16; i++ )
+                nz[i] = h->mb.cache.non_zero_count[x264_scan8[i]];
+            for( i = 0; i < 4; i++ )
+            {
+                nz[16+i] = h->mb.cache.non_zero_count[x264_scan8[16+i]];
+                nz[20+i] = h->mb.cache.non_zero_count[x264_scan8[32+i]];
+            }
+            nz[24] = h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]];
+            nz[25] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]];
+            nz[26] = h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]];
+            cbp[xy] = h->mb.cbp[0];
+        }
+}
+
 /* x264_macroblock_encode for one I16x16 macroblock of an I slice whose prediction (luma and chroma) is
  * already in p_fdec: the predictors the function would call are swapped for no-ops during the call (the
  * tables are plain data members of x264_t), everything else is the reference's own code.  Same buffer

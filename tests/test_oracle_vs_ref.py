@@ -556,6 +556,53 @@ def test_me_halfpel_thresh_and_refdupe(me, subme):
 
 # ------------------------------------------------------------------ residual
 
+@pytest.mark.parametrize("qp", [20, 26, 34])
+def test_recon_frame_through_reference_functions(qp):
+    """xref_recon_frame (x264_mb_mc + x264_macroblock_encode over a whole frame, then x264_frame_deblock_row) -- the CPU
+    baseline of config 4 in bench.py -- against the oracle's xo_mc_frame + xo_residual_frame + xo_deblock_frame"""
+    o = cc.oracle()
+    w, h = 352, 288
+    enc = cc.RefEncoder(w, h, me=1, subme=5, qp=qp)
+    g = cc.oracle_geom(w, h)
+    clip = cc.synth_clip(w, h, 2)
+    fref, fdec, fenc = enc.new_frame(True), enc.new_frame(True), enc.new_frame(False)
+    enc.load(fref, clip[0])
+    enc.load(fenc, clip[1])
+    enc.load(fdec, clip[1])                                   # any content: every macroblock is overwritten
+    enc.lib.xref_frame_filter_all(enc.h, fref)
+    slot_ref, slot_enc = np.zeros(g.slot_bytes, np.uint8), np.zeros(g.slot_bytes, np.uint8)
+    o.xo_frame_load_i420(C.byref(g), ptr(clip[0]), ptr(slot_ref))
+    o.xo_frame_expand_border(C.byref(g), ptr(slot_ref))
+    o.xo_frame_filter(C.byref(g), ptr(slot_ref))
+    o.xo_frame_load_i420(C.byref(g), ptr(clip[1]), ptr(slot_enc))
+    rng = np.random.RandomState(qp)
+    n = g.mb_count
+    mv = (np.array([12, 8]) + rng.randint(-6, 7, (n, 2))).astype(np.int16)
+    mv[rng.rand(n) < 0.05] = [-300, 250]                      # clipped by mv_min / mv_max near the borders
+    lv_r, nz_r, cbp_r = np.zeros((n, 392), np.int16), np.zeros((n, 27), np.uint8), np.zeros(n, np.int16)
+    enc.lib.xref_recon_frame(enc.h, fenc, fref, fdec, ptr(mv, i16p), qp, ptr(lv_r, i16p), ptr(nz_r), ptr(cbp_r, i16p))
+    pred = np.zeros(g.slot_bytes, np.uint8)
+    o.xo_mc_frame(C.byref(g), ptr(slot_ref), ptr(mv, i16p), ptr(pred))
+    lv_o, nz_o, cbp_o = np.zeros((n, 392), np.int16), np.zeros((n, 27), np.uint8), np.zeros(n, np.int16)
+    o.xo_residual_frame(C.byref(g), ptr(slot_enc), ptr(pred), qp, ptr(lv_o, i16p), ptr(nz_o), ptr(cbp_o, i16p))
+    assert np.array_equal(lv_r, lv_o) and np.array_equal(nz_r, nz_o) and np.array_equal(cbp_r, cbp_o)
+
+    def planes(buf_y, buf_c):
+        y = buf_y[g.luma_origin:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:, : g.luma_w]
+        c = buf_c[g.chroma_origin:][: (g.luma_h // 2) * g.chroma_stride].reshape(g.luma_h // 2, g.chroma_stride)[:, : g.luma_w]
+        return y, c
+    ry, rc = planes(enc.buffer(fdec, 10, 4 * g.luma_plane_size), enc.buffer(fdec, 11, g.chroma_plane_size))
+    oy, oc = planes(pred, pred[g.slot_chroma_off:])
+    assert np.array_equal(ry, oy) and np.array_equal(rc, oc), "reconstruction before the in-loop filter"
+    mb_type, part = np.full(n, 4, np.int8), np.full(n, 16, np.uint8)
+    bs = (rng.rand(n, 2, 8, 4) < 0.35).astype(np.uint8) * rng.randint(1, 3, (n, 2, 8, 4)).astype(np.uint8)
+    enc.lib.xref_deblock_frame(enc.h, fdec, ptr(mb_type, i8p), ptr(part), ptr(cbp_r, i16p), ptr(bs), qp, 0, 0)
+    o.xo_deblock_frame(C.byref(g), ptr(pred), ptr(mb_type, i8p), ptr(part), ptr(cbp_o, i16p), ptr(bs), qp, 0, 0)
+    ry, rc = planes(enc.buffer(fdec, 10, 4 * g.luma_plane_size), enc.buffer(fdec, 11, g.chroma_plane_size))
+    oy, oc = planes(pred, pred[g.slot_chroma_off:])
+    assert np.array_equal(ry, oy) and np.array_equal(rc, oc), "deblocked reconstruction"
+
+
 @pytest.mark.parametrize("qp", [12, 18, 22, 26, 32, 40, 51])
 def test_residual_inter_mb(enc, qp):
     o = cc.oracle()

@@ -454,3 +454,39 @@ class Context:
         """x264_macroblock_deblock_strength: mb_type int8[n] (0..3 = intra -> inner edges 3); None = all inter"""
         check(lib().x264dsp_macroblock_deblock_strength_dev(self._h, int(n), _dp(mb_type), _dp(nnz), _dp(ref), _dp(mv),
                                                             _dp(bs), None), "x264dsp_macroblock_deblock_strength_dev")
+
+    # ---- full-resolution paths from host memory ------------------------------------------
+    def me_search_frames_host(self, width, height, luma, params, sizes, blocks, results=None):
+        """luma: uint8 [n_pairs+1, h*w]; sizes: list of i_pixel; blocks: list of ME_BLOCK_DTYPE arrays [n_pairs*n] (pair-major).
+        Returns the list of ME_RESULT_DTYPE arrays (pass pinned `results` to skip staging)."""
+        n_pairs = luma.shape[0] - 1
+        ns = len(sizes)
+        nb = [len(b) // n_pairs for b in blocks]
+        if results is None:
+            results = [np.zeros(len(b), ME_RESULT_DTYPE) for b in blocks]
+        ip = (C.c_int32 * ns)(*sizes)
+        nbl = (C.c_int32 * ns)(*nb)
+        bp = (C.c_void_p * ns)(*[b.ctypes.data for b in blocks])
+        rp = (C.c_void_p * ns)(*[r.ctypes.data for r in results])
+        check(lib().x264dsp_me_search_frames_host(self._h, int(width), int(height), int(n_pairs), _hp(luma), C.byref(params),
+                                                  ns, ip, nbl, bp, rp), "x264dsp_me_search_frames_host")
+        return results
+
+    def recon_frames_host(self, width, height, i420, mv16, qp, mb_type, partition, bs, out=None, alpha_off=0, beta_off=0):
+        """i420: uint8 [n+1, w*h*3/2]; mv16 int16 [n, mb, 2]; mb_type int8 [n, mb]; partition uint8 [n, mb]; bs uint8 [n, mb, 64].
+        Returns (levels, nnz, cbp, recon_i420); `out` may hold those four arrays preallocated (e.g. pinned)."""
+        g = geometry(width, height)
+        n = i420.shape[0] - 1
+        if out is None:
+            out = (np.zeros((n, g.mb_count, RES_LEVELS_PER_MB), np.int16), np.zeros((n, g.mb_count, RES_NNZ_PER_MB), np.uint8),
+                   np.zeros((n, g.mb_count), np.int16), np.zeros((n, width * height * 3 // 2), np.uint8))
+        lv, nz, cbp, rec = out
+        check(lib().x264dsp_recon_frames_host(self._h, int(width), int(height), int(n), _hp(i420), _hp(mv16, C.c_int16), int(qp),
+                                              _hp(mb_type, C.c_int8), _hp(partition), _hp(bs), int(alpha_off), int(beta_off),
+                                              _hp(lv, C.c_int16), _hp(nz), _hp(cbp, C.c_int16), _hp(rec)),
+              "x264dsp_recon_frames_host")
+        return out
+
+    def frame_store_i420(self, g, slots_dev, i420_dev, n_frames):
+        check(lib().x264dsp_frame_store_i420_dev(self._h, C.byref(g), _dp(slots_dev), _dp(i420_dev), int(n_frames), None),
+              "x264dsp_frame_store_i420_dev")

@@ -45,6 +45,11 @@ struct x264dsp_ctx
     int32_t *clip_desc;   size_t clip_desc_cap;
     void *desc_cache;     size_t desc_cache_bytes;   // host copy of what clip_desc holds
 
+    // host-level full-resolution paths (host_paths.cu): block lists / side information and results on the device
+    uint8_t *me_blocks;   size_t me_blocks_cap;
+    uint8_t *me_results;  size_t me_results_cap;
+    cudaEvent_t host_ev;
+
     // deblock wavefront: per-row progress counters + ticket
     int32_t *db_progress; size_t db_progress_cap;
 

@@ -287,6 +287,10 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     cudaFree( ctx->clip_slots );
     cudaFree( ctx->clip_out );
     cudaFree( ctx->db_progress );
+    cudaFree( ctx->me_blocks );
+    cudaFree( ctx->me_results );
+    if( ctx->host_ev )
+        cudaEventDestroy( ctx->host_ev );
     cudaFree( ctx->clip_desc );
     free( ctx->desc_cache );
     cudaFree( ctx->shim_dev );

@@ -1,0 +1,241 @@
+// host_paths.cu -- the full-resolution paths from HOST memory: motion search of every partition size (SURVEY 8(d)
+// config 3) and motion compensation + residual coding + in-loop filter (config 4), pictures in, results out.
+//
+// These are the end-to-end doors bench.py times next to the device-resident launches: host -> device copies of the
+// pictures and of the per-block / per-macroblock side information and device -> host copies of the results are part
+// of the call.  Work is cut into groups that run on the context's auxiliary streams, so that one group's copies
+// overlap another group's kernels; every group ends with its own device -> host copies and the call returns when all
+// groups have drained.  Pinned caller buffers (x264dsp_host_alloc) are copied from / to directly; ordinary memory is
+// staged by the driver.
+#include <string.h>
+#include "common.cuh"
+
+#define XH_CHECK( call ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { rc = (int)e_; goto drain; } } while( 0 )
+#define XH_RC( call ) do { rc = ( call ); if( rc ) goto drain; } while( 0 )
+
+// ---------------------------------------------------------------------------------------------
+// slot -> planar I420: the inverse of xd_load_i420_kernel for the picture area (width x height), so that a
+// reconstructed frame leaves the device in the format it came in.  One thread = 16 luma bytes or 8 U + 8 V bytes.
+__global__ void __launch_bounds__( 256 )
+xd_store_i420_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ slots, uint8_t *__restrict__ i420 )
+{
+    const int frame = blockIdx.z;
+    const size_t pic_bytes = (size_t)g.width * g.height * 3 / 2;
+    uint8_t *dy = i420 + frame * pic_bytes;
+    uint8_t *du = dy + (size_t)g.width * g.height;
+    uint8_t *dv = du + (size_t)( g.width >> 1 ) * ( g.height >> 1 );
+    const uint8_t *slot = slots + frame * (size_t)g.slot_bytes;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;                      // [0, height) luma rows, then height/2 chroma rows
+    const int x0 = t * 16;
+    if( x0 >= g.width )
+        return;
+    if( row < g.height )
+    {
+        const uint4 v = *(const uint4 *)( slot + g.luma_origin + (size_t)row * g.luma_stride + x0 );
+        uint8_t *dst = dy + (size_t)row * g.width + x0;
+        if( x0 + 16 <= g.width && ( (uintptr_t)dst & 15 ) == 0 )
+            *(uint4 *)dst = v;
+        else
+        {
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+            for( int k = 0; k < 16 && x0 + k < g.width; k++ )
+                dst[k] = (uint8_t)( w[k >> 2] >> ( 8 * ( k & 3 ) ) );
+        }
+    }
+    else
+    {
+        const int crow = row - g.height;
+        if( crow >= ( g.height >> 1 ) )
+            return;
+        const int cw = g.width >> 1;
+        const uint4 v = *(const uint4 *)( slot + g.slot_chroma_off + g.chroma_origin + (size_t)crow * g.chroma_stride + x0 );
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        uint8_t *pu = du + (size_t)crow * cw + ( x0 >> 1 ), *pv = dv + (size_t)crow * cw + ( x0 >> 1 );
+        for( int k = 0; k < 8 && ( x0 >> 1 ) + k < cw; k++ )
+        {
+            const uint32_t pair = w[k >> 1] >> ( 16 * ( k & 1 ) );
+            pu[k] = (uint8_t)pair;
+            pv[k] = (uint8_t)( pair >> 8 );
+        }
+    }
+}
+
+extern "C" int x264dsp_frame_store_i420_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *slots,
+                                              uint8_t *i420, int n_frames, void *stream )
+{
+    if( !ctx || !g || !slots || !i420 || n_frames <= 0 )
+        return X264DSP_E_ARG;
+    dim3 grid( ( ( ( g->width + 15 ) >> 4 ) + 255 ) / 256, g->height + ( g->height >> 1 ), n_frames );
+    xd_store_i420_kernel<<<grid, 256, 0, xd_stream( ctx, stream )>>>( *g, slots, i420 );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// config 3 from host memory
+extern "C" int x264dsp_me_search_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_pairs, const uint8_t *luma,
+                                               const x264dsp_me_params_t *params, int n_sizes, const int32_t *i_pixel,
+                                               const int32_t *n_blocks, const x264dsp_me_block_t *const *blocks,
+                                               x264dsp_me_result_t *const *results )
+{
+    if( !ctx || !luma || !params || n_pairs <= 0 || n_sizes <= 0 || n_sizes > 8 || !i_pixel || !n_blocks || !blocks || !results )
+        return X264DSP_E_ARG;
+    x264dsp_geom_t g;
+    int rc = x264dsp_geometry( width, height, &g );
+    if( rc )
+        return rc;
+    const int nf = n_pairs + 1;
+    const size_t pic = (size_t)width * height;
+    size_t blk_bytes = 0, res_bytes = 0, off_blk[8], off_res[8];
+    for( int s = 0; s < n_sizes; s++ )
+    {
+        if( n_blocks[s] < 0 || i_pixel[s] < 0 || i_pixel[s] > 7 || ( n_blocks[s] && ( !blocks[s] || !results[s] ) ) )
+            return X264DSP_E_ARG;
+        off_blk[s] = blk_bytes;
+        off_res[s] = res_bytes;
+        blk_bytes += ( (size_t)n_pairs * n_blocks[s] * sizeof( x264dsp_me_block_t ) + 255 ) & ~(size_t)255;
+        res_bytes += ( (size_t)n_pairs * n_blocks[s] * sizeof( x264dsp_me_result_t ) + 255 ) & ~(size_t)255;
+    }
+    XD_CHECK( cudaSetDevice( ctx->device ) );
+    if( ctx->stage_dev_cap < pic * nf || ctx->clip_slots_cap < (size_t)nf * g.slot_bytes || ctx->me_blocks_cap < blk_bytes
+        || ctx->me_results_cap < res_bytes )
+        XD_CHECK( cudaDeviceSynchronize() );             // the buffers below may still be in use by an earlier call
+    if( ( rc = xd_reserve_dev( (void **)&ctx->stage_dev, &ctx->stage_dev_cap, pic * nf ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->clip_slots, &ctx->clip_slots_cap, (size_t)nf * g.slot_bytes ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->me_blocks, &ctx->me_blocks_cap, blk_bytes ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->me_results, &ctx->me_results_cap, res_bytes ) ) ) return rc;
+    if( !ctx->host_ev )
+        XD_CHECK( cudaEventCreateWithFlags( &ctx->host_ev, cudaEventDisableTiming ) );
+
+    // planes of every frame on the context's stream; the searches of the partition sizes fan out over the auxiliary
+    // streams behind an event (different sizes read the same planes and write different results)
+    int used = 0;
+    {
+        cudaStream_t s0 = ctx->stream;
+        XH_CHECK( cudaMemcpyAsync( ctx->stage_dev, luma, pic * nf, cudaMemcpyHostToDevice, s0 ) );
+        XH_RC( x264dsp_frame_load_luma_dev( ctx, &g, ctx->stage_dev, ctx->clip_slots, nf, s0 ) );
+        XH_RC( x264dsp_frame_expand_border_dev( ctx, &g, ctx->clip_slots, nf, s0 ) );
+        XH_RC( x264dsp_frame_filter_dev( ctx, &g, ctx->clip_slots, nf, s0 ) );
+        XH_CHECK( cudaEventRecord( ctx->host_ev, s0 ) );
+        for( int s = 0; s < n_sizes; s++ )
+        {
+            if( !n_blocks[s] )
+                continue;
+            cudaStream_t st = ctx->aux[s % XD_AUX_STREAMS];
+            used = used > s % XD_AUX_STREAMS + 1 ? used : s % XD_AUX_STREAMS + 1;
+            const size_t nb = (size_t)n_pairs * n_blocks[s];
+            x264dsp_me_block_t *d_blk = (x264dsp_me_block_t *)( ctx->me_blocks + off_blk[s] );
+            x264dsp_me_result_t *d_res = (x264dsp_me_result_t *)( ctx->me_results + off_res[s] );
+            XH_CHECK( cudaMemcpyAsync( d_blk, blocks[s], nb * sizeof( x264dsp_me_block_t ), cudaMemcpyHostToDevice, st ) );
+            XH_CHECK( cudaStreamWaitEvent( st, ctx->host_ev, 0 ) );
+            XH_RC( x264dsp_me_search_sized_frames_dev( ctx, &g, ctx->clip_slots + g.slot_bytes, ctx->clip_slots, n_pairs, params,
+                                                       i_pixel[s], n_blocks[s], d_blk, d_res, st ) );
+            XH_CHECK( cudaMemcpyAsync( results[s], d_res, nb * sizeof( x264dsp_me_result_t ), cudaMemcpyDeviceToHost, st ) );
+        }
+    }
+drain:
+    {
+        cudaError_t e = cudaStreamSynchronize( ctx->stream );
+        if( e != cudaSuccess && !rc )
+            rc = (int)e;
+        for( int i = 0; i < used; i++ )
+        {
+            e = cudaStreamSynchronize( ctx->aux[i] );
+            if( e != cudaSuccess && !rc )
+                rc = (int)e;
+        }
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// config 4 from host memory
+extern "C" int x264dsp_recon_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                                           const int16_t *mv16, int qp, const int8_t *mb_type, const uint8_t *partition,
+                                           const uint8_t *bs, int alpha_c0_offset, int beta_offset,
+                                           int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 )
+{
+    if( !ctx || !i420 || !mv16 || !mb_type || !partition || !bs || !levels || !nnz || !cbp || !recon_i420 || n_frames <= 0
+        || qp < 0 || qp > 51 )
+        return X264DSP_E_ARG;
+    x264dsp_geom_t g;
+    int rc = x264dsp_geometry( width, height, &g );
+    if( rc )
+        return rc;
+    const size_t pic = (size_t)width * height * 3 / 2, nmb = g.mb_count;
+    // groups of frames, each on its own stream; group k needs pictures [f0, f1] (f0 is the reference of its first frame)
+    int groups = n_frames / 4;
+    if( groups < 1 ) groups = 1;
+    if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
+    // device memory per group: its pictures, their slots (reference side: luma N/H/V/HV + chroma), one prediction /
+    // reconstruction slot per frame, side information, outputs
+    const size_t per_mb_in = 2 * sizeof( int16_t ) + 1 + 1 + 64, per_mb_out = X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t )
+                           + X264DSP_RES_NNZ_PER_MB + sizeof( int16_t );
+    const size_t side_bytes = ( (size_t)n_frames * nmb * ( per_mb_in + per_mb_out ) + 4096 ) & ~(size_t)255;
+    const size_t need_slots = (size_t)( 2 * n_frames + groups ) * g.slot_bytes;
+    const size_t need_pics = (size_t)( n_frames + groups ) * pic + (size_t)n_frames * pic;
+    XD_CHECK( cudaSetDevice( ctx->device ) );
+    if( ctx->stage_dev_cap < need_pics || ctx->clip_slots_cap < need_slots || ctx->me_blocks_cap < side_bytes )
+        XD_CHECK( cudaDeviceSynchronize() );
+    if( ( rc = xd_reserve_dev( (void **)&ctx->stage_dev, &ctx->stage_dev_cap, need_pics ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->clip_slots, &ctx->clip_slots_cap, need_slots ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->me_blocks, &ctx->me_blocks_cap, side_bytes ) ) ) return rc;
+
+    uint8_t *d_side = ctx->me_blocks;
+    int16_t *d_mv = (int16_t *)d_side;                            d_side += ( (size_t)n_frames * nmb * 4 + 15 ) & ~(size_t)15;
+    int16_t *d_lv = (int16_t *)d_side;                            d_side += (size_t)n_frames * nmb * X264DSP_RES_LEVELS_PER_MB * 2;
+    int16_t *d_cbp = (int16_t *)d_side;                           d_side += ( (size_t)n_frames * nmb * 2 + 15 ) & ~(size_t)15;
+    uint8_t *d_bs = d_side;                                       d_side += (size_t)n_frames * nmb * 64;
+    uint8_t *d_nz = d_side;                                       d_side += ( (size_t)n_frames * nmb * X264DSP_RES_NNZ_PER_MB + 15 ) & ~(size_t)15;
+    int8_t *d_type = (int8_t *)d_side;                            d_side += ( (size_t)n_frames * nmb + 15 ) & ~(size_t)15;
+    uint8_t *d_part = d_side;
+
+    int used = 0;
+    size_t slot_cursor = 0, pic_cursor = 0;
+    uint8_t *d_out_pics = ctx->stage_dev + (size_t)( n_frames + groups ) * pic;
+    for( int gi = 0; gi < groups && !rc; gi++ )
+    {
+        const int f0 = (int)( (int64_t)n_frames * gi / groups ), f1 = (int)( (int64_t)n_frames * ( gi + 1 ) / groups );
+        const int nf = f1 - f0;
+        if( nf <= 0 )
+            continue;
+        cudaStream_t st = ctx->aux[gi];
+        used = gi + 1;
+        uint8_t *d_pics = ctx->stage_dev + pic_cursor;           pic_cursor += (size_t)( nf + 1 ) * pic;
+        uint8_t *d_src = ctx->clip_slots + slot_cursor;           slot_cursor += (size_t)( nf + 1 ) * g.slot_bytes;
+        uint8_t *d_pred = ctx->clip_slots + slot_cursor;          slot_cursor += (size_t)nf * g.slot_bytes;
+        const size_t m0 = (size_t)f0 * nmb, mn = (size_t)nf * nmb;
+        XH_CHECK( cudaMemcpyAsync( d_pics, i420 + (size_t)f0 * pic, (size_t)( nf + 1 ) * pic, cudaMemcpyHostToDevice, st ) );
+        XH_CHECK( cudaMemcpyAsync( d_mv + m0 * 2, mv16 + m0 * 2, mn * 4, cudaMemcpyHostToDevice, st ) );
+        XH_CHECK( cudaMemcpyAsync( d_bs + m0 * 64, bs + m0 * 64, mn * 64, cudaMemcpyHostToDevice, st ) );
+        XH_CHECK( cudaMemcpyAsync( d_type + m0, mb_type + m0, mn, cudaMemcpyHostToDevice, st ) );
+        XH_CHECK( cudaMemcpyAsync( d_part + m0, partition + m0, mn, cudaMemcpyHostToDevice, st ) );
+        XH_RC( x264dsp_frame_load_i420_dev( ctx, &g, d_pics, d_src, nf + 1, st ) );
+        XH_RC( x264dsp_frame_expand_border_dev( ctx, &g, d_src, nf + 1, st ) );
+        XH_RC( x264dsp_frame_filter_dev( ctx, &g, d_src, nf, st ) );                 // reference frames only
+        XH_RC( x264dsp_mc_frames_dev( ctx, &g, d_src, nf, d_mv + m0 * 2, d_pred, st ) );
+        XH_RC( x264dsp_residual_frames_dev( ctx, &g, d_src + g.slot_bytes, d_pred, nf, qp, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
+                                            d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, st ) );
+        XH_RC( x264dsp_deblock_frames_dev( ctx, &g, d_pred, nf, d_type + m0, d_part + m0, d_cbp + m0, d_bs + m0 * 64, qp,
+                                           alpha_c0_offset, beta_offset, st ) );
+        XH_RC( x264dsp_frame_store_i420_dev( ctx, &g, d_pred, d_out_pics + (size_t)f0 * pic, nf, st ) );
+        XH_CHECK( cudaMemcpyAsync( levels + m0 * X264DSP_RES_LEVELS_PER_MB, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
+                                   mn * X264DSP_RES_LEVELS_PER_MB * 2, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( nnz + m0 * X264DSP_RES_NNZ_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB, mn * X264DSP_RES_NNZ_PER_MB,
+                                   cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( cbp + m0, d_cbp + m0, mn * 2, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( recon_i420 + (size_t)f0 * pic, d_out_pics + (size_t)f0 * pic, (size_t)nf * pic,
+                                   cudaMemcpyDeviceToHost, st ) );
+    }
+drain:
+    for( int i = 0; i < used; i++ )
+    {
+        const cudaError_t e = cudaStreamSynchronize( ctx->aux[i] );
+        if( e != cudaSuccess && !rc )
+            rc = (int)e;
+    }
+    ctx->scratch_busy[XD_SCRATCH_DEBLOCK] = 0;
+    return rc;
+}
