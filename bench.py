@@ -44,7 +44,12 @@ def parse_args():
     ap.add_argument("--clip-len", type=int, default=8)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-me", action="store_true", help="skip the secondary full-resolution ME measurement")
+    ap.add_argument("--no-me", action="store_true", help="skip the configs[2] / configs[3] measurements (ME search, recon)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
+                    help="2 = the headline (BASELINE.json configs[1], 1080p lookahead, + configs[2] and [3] as sub-objects); "
+                         "5 = configs[4]: ONE 4K sequence of --seq-frames frames, lookahead + 16x16 / 8x8 motion search, "
+                         "split by frame range over the ranks, gathered with NCCL and compared with rank 0's own single-GPU run")
+    ap.add_argument("--seq-frames", type=int, default=64)
     return ap.parse_args()
 
 
@@ -258,6 +263,174 @@ def recon_cpu_check(pkg, g, check):
     return bool(ok), dt, int(np.count_nonzero(cbp))
 
 
+# --------------------------------------------------------------------------------------------
+# CPU baselines of configs[2] and configs[3] from the UNMODIFIED reference (oracle/_ref): its x264_me_search_ref +
+# x264_me_refine_qpel over the same block lists, its x264_mb_mc + x264_macroblock_encode + x264_frame_deblock_row over
+# the same frames, on all host threads (one encoder instance per thread), for the -O2 and the -O3 build
+
+def _run_threads(fn, threads):
+    """fn(t) on `threads` threads behind a barrier; returns the seconds between the common start and the last finish"""
+    barrier = threading.Barrier(threads + 1)
+    done = threading.Barrier(threads + 1)
+
+    def run(t):
+        barrier.wait()
+        fn(t)
+        done.wait()
+    ths = [threading.Thread(target=run, args=(t,), daemon=True) for t in range(threads)]
+    for th in ths:
+        th.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    dt = time.perf_counter() - t0
+    for th in ths:
+        th.join()
+    return dt
+
+
+def cpu_me_reference(which, w, h, pics, blocks_by_size, threads, qp=26, target_s=4.0):
+    """frame pair 0 of the ME measurement through the reference: every thread searches a contiguous share of every
+    partition size's block list.  Returns (frames/s for all sizes together, results by size of the last pass)"""
+    import cpu_checkers as cc
+    lib = cc.ref_o3() if which == "O3" else cc.ref()
+    if lib is None:
+        return None, None
+    state = []
+    for t in range(threads):
+        enc = cc.RefEncoder(w, h, me=1, subme=5, me_range=16, qp=qp, lib=lib)
+        fref, fenc = enc.new_frame(True), enc.new_frame(False)
+        enc.load(fref, pics[0])
+        enc.load(fenc, pics[1])
+        lib.xref_frame_filter_all(enc.h, fref)
+        state.append((enc, fenc, fref))
+    out = {name: np.zeros(len(b), cc.ME_RESULT_DTYPE) for name, b in blocks_by_size.items()}
+    shares = {name: np.linspace(0, len(b), threads + 1).astype(int) for name, b in blocks_by_size.items()}
+    sizes = {name: i for i, name in enumerate(ME_SIZES)}
+
+    def work(t):
+        enc, fenc, fref = state[t]
+        for name, b in blocks_by_size.items():
+            lo, hi = shares[name][t], shares[name][t + 1]
+            if hi > lo:
+                lib.xref_me_search_batch(enc.h, fenc, fref, qp, 1, 5, 16, 1, b[lo:hi].ctypes.data_as(C.c_void_p), int(hi - lo),
+                                         out[name][lo:hi].ctypes.data_as(C.c_void_p))
+    dt = _run_threads(work, threads)                       # warm-up and a first estimate
+    reps = max(1, min(64, int(target_s / max(dt, 1e-3))))
+    dt = _run_threads(lambda t: [work(t) for _ in range(reps)], threads)
+    return reps / dt, out
+
+
+def cpu_recon_reference(which, w, h, pics, mv, bs, threads, qp=26, target_s=4.0):
+    """frame 0 of the recon measurement through the reference, one frame per thread and pass.  Returns
+    (frames/s, (levels, nnz, cbp, deblocked luma plane area, deblocked chroma plane area) of thread 0)"""
+    import cpu_checkers as cc
+    from cpu_checkers import ptr, i16p, i8p
+    lib = cc.ref_o3() if which == "O3" else cc.ref()
+    if lib is None:
+        return None, None
+    g = cc.oracle_geom(w, h)
+    n = g.mb_count
+    mb_type, part = np.full(n, 4, np.int8), np.full(n, 16, np.uint8)
+    state = []
+    for t in range(threads):
+        enc = cc.RefEncoder(w, h, me=1, subme=5, me_range=16, qp=qp, lib=lib)
+        fref, fdec, fenc = enc.new_frame(True), enc.new_frame(True), enc.new_frame(False)
+        enc.load(fref, pics[0])
+        enc.load(fenc, pics[1])
+        enc.load(fdec, pics[1])
+        lib.xref_frame_filter_all(enc.h, fref)
+        state.append((enc, fenc, fref, fdec, np.zeros((n, 392), np.int16), np.zeros((n, 27), np.uint8), np.zeros(n, np.int16)))
+
+    def work(t):
+        enc, fenc, fref, fdec, lv, nz, cbp = state[t]
+        lib.xref_recon_frame(enc.h, fenc, fref, fdec, ptr(mv, i16p), qp, ptr(lv, i16p), ptr(nz), ptr(cbp, i16p))
+        lib.xref_deblock_frame(enc.h, fdec, ptr(mb_type, i8p), ptr(part), ptr(cbp, i16p), ptr(bs), qp, 0, 0)
+    dt = _run_threads(work, threads)
+    reps = max(1, min(64, int(target_s / max(dt, 1e-3))))
+    dt = _run_threads(lambda t: [work(t) for _ in range(reps)], threads)
+    enc, fenc, fref, fdec, lv, nz, cbp = state[0]
+    y = enc.buffer(fdec, 10, 4 * g.luma_plane_size)[g.luma_origin:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:, : g.luma_w]
+    c = enc.buffer(fdec, 11, g.chroma_plane_size)[g.chroma_origin:][: (g.luma_h // 2) * g.chroma_stride].reshape(
+        g.luma_h // 2, g.chroma_stride)[:, : g.luma_w]
+    return threads * reps / dt, (lv.copy(), nz.copy(), cbp.copy(), y.copy(), c.copy())
+
+
+def me_search_e2e(pkg, ctx, g, w, h, luma_host, la_mvs, pairs, reps=3, qp=26):
+    """configs[2] end to end through x264dsp_me_search_frames_host: pinned host pictures and block lists in, pinned
+    results out.  Returns (seconds per call, h2d bytes, d2h bytes, results of the last call by size)"""
+    prm = pkg.MeParams(pkg.ME_HEX, 5, 16, qp, 1)
+    luma = ctx.pinned_empty((pairs + 1, w * h), np.uint8)
+    luma[:] = luma_host[: pairs + 1]
+    blocks, results = [], []
+    for size in range(len(ME_SIZES)):
+        b = np.concatenate([pkg.tiling_blocks(g, size, la_mvs[p + 1]) for p in range(pairs)])
+        pb = ctx.pinned_empty((len(b),), pkg.ME_BLOCK_DTYPE)
+        pb[:] = b
+        blocks.append(pb)
+        results.append(ctx.pinned_empty((len(b),), pkg.ME_RESULT_DTYPE))
+    sizes = list(range(len(ME_SIZES)))
+    ctx.me_search_frames_host(w, h, luma, prm, sizes, blocks, results)          # warm-up (allocations)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ctx.me_search_frames_host(w, h, luma, prm, sizes, blocks, results)
+    dt = (time.perf_counter() - t0) / reps
+    h2d = luma.nbytes + sum(b.nbytes for b in blocks)
+    d2h = sum(r.nbytes for r in results)
+    return dt, h2d, d2h, results
+
+
+def recon_e2e(pkg, ctx, g, w, h, n_frames, reps=3, qp=26):
+    """configs[3] end to end through x264dsp_recon_frames_host (pinned buffers).  Same inputs as recon_measure."""
+    nmb = g.mb_count
+    rng = np.random.RandomState(5)
+    i420 = ctx.pinned_empty((n_frames + 1, w * h * 3 // 2), np.uint8)
+    for i in range(n_frames + 1):
+        i420[i] = pkg.synth_frame(w, h, i)
+    mv = ctx.pinned_empty((n_frames, nmb, 2), np.int16)
+    mv[:] = (np.array([12, 8]) + rng.randint(-1, 2, (n_frames, nmb, 2))).astype(np.int16)
+    bs = ctx.pinned_empty((n_frames, nmb, 64), np.uint8)
+    bs[:] = ((rng.rand(n_frames, nmb, 2, 8, 4) < 0.35).astype(np.uint8)
+             * rng.randint(1, 3, (n_frames, nmb, 2, 8, 4)).astype(np.uint8)).reshape(n_frames, nmb, 64)
+    mb_type = ctx.pinned_empty((n_frames, nmb), np.int8)
+    mb_type[:] = 4
+    part = ctx.pinned_empty((n_frames, nmb), np.uint8)
+    part[:] = 16
+    out = (ctx.pinned_empty((n_frames, nmb, pkg.RES_LEVELS_PER_MB), np.int16), ctx.pinned_empty((n_frames, nmb, pkg.RES_NNZ_PER_MB), np.uint8),
+           ctx.pinned_empty((n_frames, nmb), np.int16), ctx.pinned_empty((n_frames, w * h * 3 // 2), np.uint8))
+    ctx.recon_frames_host(w, h, i420, mv, qp, mb_type, part, bs, out)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ctx.recon_frames_host(w, h, i420, mv, qp, mb_type, part, bs, out)
+    dt = (time.perf_counter() - t0) / reps
+    h2d = i420.nbytes + mv.nbytes + bs.nbytes + mb_type.nbytes + part.nbytes
+    d2h = sum(o.nbytes for o in out)
+    return dt, h2d, d2h, out
+
+
+def lookahead_oracle_check(pkg, w, h, clip_len, luma_clip, mvs, costs, sums):
+    """the headline step's first clip through the CPU oracle (one core, a fraction of a second): True when the MVs, the
+    block costs and the frame sums the GPU returned are bit-exact"""
+    import cpu_checkers as cc
+    o = cc.oracle()
+    g = cc.oracle_geom(w, h)
+    slots = [np.zeros(g.slot_bytes, np.uint8) for _ in range(clip_len)]
+    chroma = np.full(w * h // 2, 128, np.uint8)
+    for i in range(clip_len):
+        pic = np.concatenate([luma_clip[i], chroma])
+        o.xo_frame_load_i420(C.byref(g), cc.ptr(pic), cc.ptr(slots[i]))
+        o.xo_frame_init_lowres(C.byref(g), cc.ptr(slots[i]))
+    ok = True
+    for i in range(clip_len):
+        mv_o, c_o, s_o = np.zeros((g.mb_count, 2), np.int16), np.zeros(g.mb_count, np.int32), np.zeros(8, np.int32)
+        o.xo_lookahead_frame_cost(C.byref(g), cc.ptr(slots[i]), cc.ptr(slots[i - 1]) if i else None, 1,
+                                  cc.ptr(mv_o, cc.i16p), cc.ptr(c_o, cc.i32p), cc.ptr(s_o, cc.i32p), None)
+        if i:
+            ok = ok and np.array_equal(mvs[i], mv_o) and np.array_equal(costs[i], c_o)
+        ok = ok and np.array_equal(sums[i][:5], s_o[:5])
+    return bool(ok)
+
+
 def int_pipe_roofline(sad_px, satd_px, seconds, kernels):
     """algorithmic integer instructions (SAD 0.25 per pixel comparison = one VABSDIFF4.U8.ACC per 4 pixels,
     SATD 3.5 packed instructions per pixel) / time / the measured ALU-pipe peak (tools/int_pipe_peak.cu on this pool's
@@ -280,11 +453,13 @@ def int_pipe_roofline(sad_px, satd_px, seconds, kernels):
 # --------------------------------------------------------------------------------------------
 # CPU arm: the reference's own C path (oracle/_ref) or, if that build is absent, the oracle port
 
-def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats):
+def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats, lib="O2"):
     """runs the lookahead pass of len(luma_clips) clips on `threads` host threads, one clip at a
-    time per thread; returns (seconds of the timed region, kind, frames processed)"""
+    time per thread; returns (seconds of the timed region, kind, frames processed).  lib: "O2" = oracle/_ref as the
+    reference's recipe builds it, "O3" = the same sources at -O3 -march=x86-64-v3."""
     import cpu_checkers as cc
-    lib = cc.ref() if os.path.exists(cc.REF_SO) or os.path.isdir(cc.REFERENCE_TREE) else None
+    have = os.path.exists(cc.REF_SO) or os.path.isdir(cc.REFERENCE_TREE)
+    lib = (cc.ref_o3() if lib == "O3" else cc.ref()) if have else None
     kind = "reference" if lib is not None else "port"
     n_clips = len(luma_clips)
     chroma = np.full(w * h // 2, 128, np.uint8)
@@ -303,7 +478,7 @@ def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats):
             if not work[t]:
                 state.append(None)
                 continue
-            enc = cc.RefEncoder(w, h)
+            enc = cc.RefEncoder(w, h, lib=lib)
             frames = [enc.new_frame(False) for _ in range(clip_len)]
             state.append((enc, frames))
     else:
@@ -324,7 +499,8 @@ def cpu_lookahead(w, h, clip_len, luma_clips, threads, repeats):
                     if kind == "reference":
                         enc, frames = state[t]
                         for i in range(clip_len):
-                            enc.load(frames[i], clip_pics[i])   # x264_frame_copy_picture (the GPU arm's e2e has its H2D copy)
+                            # luma part of x264_frame_copy_picture + mod-16 padding: what the GPU arm's e2e uploads
+                            enc.lib.xref_frame_load_luma(enc.h, frames[i], cc.ptr(clip_pics[i]))
                         arr = (C.c_void_p * clip_len)(*[f.value for f in frames])
                         costs = (C.c_int * clip_len)()
                         enc.lib.xref_time_lookahead(enc.h, arr, clip_len, costs)
@@ -360,13 +536,17 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_reference_arm(args, pkg):
+def run_reference_arm(args):
+    """the reference's own C path (oracle/_ref, unmodified sources) on all host threads; nothing of the product is loaded:
+    the synthetic pictures come from oracle/_build/libx264dsp_synth.so (the generator source every consumer shares)"""
+    import cpu_checkers as cc
     w, h = args.width, args.height
     threads = args.cpu_threads or host_cores()
     # four clips per thread and step: a bounded sample of the GPU arm's step (args.clips clips per GPU)
     n_clips = threads * 4
-    base = make_clips(pkg, w, h, min(n_clips, 8), args.clip_len)
-    luma_clips = [base.reshape(-1, args.clip_len, w * h)[c % min(n_clips, 8)] for c in range(n_clips)]
+    distinct = min(n_clips, 8)
+    base = np.stack([cc.synth_frame(w, h, i, -1, True) for i in range(distinct * args.clip_len)])
+    luma_clips = [base.reshape(-1, args.clip_len, w * h)[c % distinct] for c in range(n_clips)]
     for _ in range(max(args.warmup, 1)):
         cpu_lookahead(w, h, args.clip_len, luma_clips[: threads], threads, 1)
     times = []
@@ -377,16 +557,24 @@ def run_reference_arm(args, pkg):
     total = sum(times)
     frames_per_step = n_clips * args.clip_len
     value = frames_per_step * args.steps / total
+    o3 = None
+    if cc.ref_o3() is not None:
+        cpu_lookahead(w, h, args.clip_len, luma_clips[: threads], threads, 1, lib="O3")
+        dt3, _, frames3 = cpu_lookahead(w, h, args.clip_len, luma_clips, threads, max(1, min(args.steps, 5)), lib="O3")
+        o3 = frames3 / dt3
     line = {
         "impl": "reference",
         "metric": "1080p ME frames/sec" if (w, h) == (1920, 1080) else f"{w}x{h} ME frames/sec",
         "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, frames_per_step, sample=f"{n_clips} clips of {args.clip_len} frames per step, "
-                                  f"four clips per host thread"),
+        "config": workload_config(args, frames_per_step),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": f"{n_clips} clips x {args.clip_len} frames per step x {args.steps} steps"},
+                         "sample": f"{n_clips} clips x {args.clip_len} frames per step x {args.steps} steps, four clips per host "
+                                   f"thread (a bounded sample of the GPU arm's {args.clips} clips per step; throughput metric)",
+                         "build": "-O2, the reference's recipe (oracle/Makefile)",
+                         "value_O3_x86-64-v3": o3,
+                         "timed": "luma plane copy + mod-16 padding, x264_frame_init_lowres, x264_slicetype_frame_cost per frame"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -404,8 +592,6 @@ def workload_config(args, frames_per_step, sample=None):
                  "frames 1.. against their predecessor; both arms return lowres MVs, MV costs and frame costs"),
         "parallelism": f"frame-range sharding, {args.gpus} GPU(s), no data-path collective",
     }
-    if sample:
-        cfg["reference_sample"] = sample
     return cfg
 
 
@@ -432,6 +618,158 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
+# --------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: ONE sequence split by frame range over the ranks
+
+def run_sharded(args, pkg, rank, world, local_rank):
+    """One 3840x2160 (--width/--height) sequence of --seq-frames frames: every rank takes the contiguous range
+    x264dsp_frame_range gives it, uploads it plus the one overlap frame (the reference of its first frame), runs the lowres
+    lookahead and the full-resolution 16x16 + 8x8 motion search (HEX, subme 5; mvp from the lookahead) of its frames and
+    returns the results to its host; the per-frame cost tables are then all-gathered with NCCL and rank 0 compares the
+    stitched tables bit for bit with its own single-GPU pass over the whole sequence.  Strong scaling: the sequence is fixed."""
+    import torch
+    import torch.distributed as dist
+    w, h, n_seq = args.width, args.height, args.seq_frames
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
+    ctx = pkg.Context(local_rank)
+    g = pkg.geometry(w, h)
+    mbc = g.mb_count
+    prm = pkg.MeParams(pkg.ME_HEX, 5, 16, 26, 1)
+    sizes = (0, 3)                                            # 16x16 and 8x8: the two searches the reference's P analysis always runs
+    chunk = 8                                                 # frame pairs per launch group
+
+    def analyse(first, count, need_prev, timed):
+        """frames [first, first+count) of the sequence -> (la_mvs, la_costs, la_sums, me results by size) for exactly those
+        frames (frame 0 of the sequence: intra-only lookahead, no search); returns also the seconds of the second,
+        timed pass (pinned host pictures in, host results out)"""
+        lo = first - 1 if need_prev else first
+        nf = first + count - lo
+        luma = ctx.pinned_empty((nf, w * h), np.uint8)
+        for i in range(nf):
+            luma[i] = pkg.synth_frame(w, h, lo + i, -1, True)
+        la_m = ctx.pinned_empty((nf, mbc, 2), np.int16)
+        la_c = ctx.pinned_empty((nf, mbc), np.int32)
+        la_s = ctx.pinned_empty((nf, pkg.LA_SUMS), np.int32)
+        n_pairs = nf - 1
+
+        def lookahead():
+            # the whole range as one clip: frame lo intra-only, every other frame against its predecessor
+            ctx.lookahead_clips_host(w, h, 1, nf, luma, la_m, la_c, la_s)
+        lookahead()
+        blocks, results = [], []
+        for sz in sizes:
+            b = np.concatenate([pkg.tiling_blocks(g, sz, la_m[p + 1]) for p in range(n_pairs)]) if n_pairs else np.zeros(0, pkg.ME_BLOCK_DTYPE)
+            pb = ctx.pinned_empty((max(len(b), 1),), pkg.ME_BLOCK_DTYPE)[: len(b)]
+            pb[:] = b
+            blocks.append(pb)
+            results.append(ctx.pinned_empty((max(len(b), 1),), pkg.ME_RESULT_DTYPE)[: len(b)])
+
+        def search():
+            for p0 in range(0, n_pairs, chunk):
+                k = min(chunk, n_pairs - p0)
+                nb = [len(b) // n_pairs for b in blocks]
+                ctx.me_search_frames_host(w, h, luma[p0: p0 + k + 1], prm, list(sizes),
+                                          [b[p0 * n: (p0 + k) * n] for b, n in zip(blocks, nb)],
+                                          [r[p0 * n: (p0 + k) * n] for r, n in zip(results, nb)])
+        if n_pairs:
+            search()
+        dt = 0.0
+        if timed:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lookahead()
+            if n_pairs:
+                search()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        skip = 1 if need_prev else 0                          # the overlap frame's own (intra-only) result is not ours
+        nb = [len(b) // max(n_pairs, 1) for b in blocks]
+        me = []
+        for r, n in zip(results, nb):
+            arr = np.zeros((count, n), pkg.ME_RESULT_DTYPE)   # row i = sequence frame first + i; frame 0 has no search
+            got = r.reshape(n_pairs, n) if n_pairs else r.reshape(0, n)
+            arr[count - n_pairs:] = got
+            me.append(arr)
+        return la_m[skip:].copy(), la_c[skip:].copy(), la_s[skip:].copy(), me, dt
+
+    first, count, need_prev = pkg.frame_range(n_seq, rank, world)
+    launches0 = ctx.launches
+    mvs, costs, sums, me, dt = analyse(first, count, need_prev, True)
+    launches = ctx.launches - launches0
+
+    # ---- gather: every rank's tables, padded to the largest range, with NCCL
+    t_gather = 0.0
+    full = None
+    if world > 1:
+        cmax = (n_seq + world - 1) // world
+
+        def gather(a):
+            pad = np.zeros((cmax,) + a.shape[1:], a.dtype)
+            pad[: len(a)] = a
+            mine = torch.from_numpy(pad.view(np.uint8).reshape(cmax, -1)).cuda()
+            out = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(out, mine)
+            parts = []
+            for r in range(world):
+                _, c, _ = pkg.frame_range(n_seq, r, world)
+                parts.append(out[r][:c].cpu().numpy())
+            return np.concatenate(parts).view(a.dtype).reshape((n_seq,) + a.shape[1:])
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        full = [gather(mvs), gather(costs), gather(sums)] + [gather(m) for m in me]
+        torch.cuda.synchronize()
+        t_gather = time.perf_counter() - t0
+    else:
+        full = [mvs, costs, sums] + me
+    tt = torch.tensor([dt, t_gather], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt, t_gather = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        same = None
+        if world > 1:
+            ref = analyse(0, n_seq, False, False)             # rank 0 alone over the whole sequence
+            want = [ref[0], ref[1], ref[2]] + ref[3]
+            same = all(np.array_equal(a, b) for k, (a, b) in enumerate(zip(full, want)) if k != 2)
+            same = bool(same and np.array_equal(full[2][:, :5], want[2][:, :5]))     # sums: costs / counts (5.. are spare)
+        line = {
+            "metric": f"{w}x{h} ME + lookahead frames/sec (one {n_seq}-frame sequence, frame-range sharded)",
+            "value": n_seq / dt, "unit": "frames/s", "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"BASELINE.json configs[4]: {w}x{h}, {n_seq} frames: lowres lookahead of every frame + 16x16 and 8x8 "
+                                   "x264_me_search_ref (HEX, subme 5, qpel refine) of every P frame, split into contiguous frame ranges "
+                                   "with a one-frame overlap (x264dsp_frame_range)",
+                       "frames_per_rank": count, "timed": "pinned host pictures -> results in host memory, per rank; max over ranks",
+                       "parallelism": f"frame-range sharding over {world} GPU(s); NCCL all-gather of the cost tables after the timed region"},
+            "e2e": {"value": n_seq / dt, "unit": "frames/s", "h2d_bytes_per_step": int((count + (1 if need_prev else 0)) * w * h),
+                    "d2h_bytes_per_step": int(mvs.nbytes + costs.nbytes + sums.nbytes + sum(m.nbytes for m in me))},
+            "gather_ms": t_gather * 1e3, "gather": "torch.distributed all_gather (NCCL) of lookahead MVs / costs / sums and the ME results",
+            "sharded_equals_single_gpu": same, "gpu_launches": int(launches),
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -445,8 +783,13 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference_arm(args, pkg)
+            run_reference_arm(args)
         return 0
+    if args.config == 5:
+        if (args.width, args.height) == (1920, 1080):
+            args.width, args.height = 3840, 2160
+        sampler.stop()
+        return run_sharded(args, pkg, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist
@@ -551,21 +894,30 @@ def main():
     torch.cuda.synchronize()
     one_ms = ev0.elapsed_time(ev1) / args.steps
 
-    # ---- secondary: full-resolution motion search (configs[2]), rank 0 only
-    me_ms = me_blocks0 = me_slots = None
-    if rank == 0 and not args.no_me:
-        me_pairs = min(8, clip_len - 1)
-        me_ms, me_blocks0, me_slots = me_search_measure(pkg, ctx, torch, g, luma_dev, d_mvs[: clip_len].cpu().numpy(), me_pairs)
-    rc_ms = rc_check = None
-    if rank == 0 and not args.no_me:
-        rc_frames = 96 if w * h <= 1920 * 1088 else 16
-        rc_ms, rc_check = recon_measure(pkg, ctx, torch, g, w, h, rc_frames)
+    # ---- configs[2] and configs[3] on EVERY rank (each on its own frames): device-resident launches and the
+    # host-memory doors; times are max-reduced over the ranks below
+    me_ms = me_blocks0 = me_slots = rc_ms = rc_check = None
+    me_e2e = rc_e2e = None
+    me_pairs = min(8, clip_len - 1)
+    rc_frames = 96 if w * h <= 1920 * 1088 else 16
+    sec = [0.0, 0.0, 0.0, 0.0]                 # ME device ms per frame, ME e2e s per call, recon device ms per frame, recon e2e s
+    if not args.no_me:
+        la_mvs_host = d_mvs[: clip_len].cpu().numpy()
+        me_ms, me_blocks0, me_slots = me_search_measure(pkg, ctx, torch, g, luma_dev, la_mvs_host, me_pairs)
+        me_e2e = me_search_e2e(pkg, ctx, g, w, h, luma_host, la_mvs_host, me_pairs)
+        rc_ms, rc_check = recon_measure(pkg, ctx, torch, g, w, h, rc_frames, first_frame=rank * 7)
+        rc_e2e = recon_e2e(pkg, ctx, g, w, h, rc_frames)
+        sec = [sum(me_ms.values()), me_e2e[0], sum(rc_ms.values()), rc_e2e[0]]
+    rc_ms_big = None
+    if not args.no_me and world == 1 and rank == 0 and w * h <= 1920 * 1088:
+        rc_ms_big, _ = recon_measure(pkg, ctx, torch, g, w, h, 384, reps=2)
 
     # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3] + sec, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    me_dev_ms_max, me_e2e_s_max, rc_dev_ms_max, rc_e2e_s_max = (float(x) for x in t[2:6])
 
     if rank == 0:
         frames_total = world * n * args.steps
@@ -601,16 +953,17 @@ def main():
             "gpu_launches": int(launches),
             "host_affinity": numa,
             "clocks": clocks,
+            "bit_exact_vs_oracle": lookahead_oracle_check(pkg, w, h, clip_len, luma_host[:clip_len], mvs_host[:clip_len],
+                                                          costs_host[:clip_len], sums_host[:clip_len]),
             "roofline": {"kernel": "xd_la_multi_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(bytes_per_pair * pairs_per_launch),
                          "avg_launch_ms": inter_avg_s * 1e3, "launches_timed": inter_n,
                          "int_pipe": int_pipe_roofline(sad_px, satd_px, (prof["la_inter"][0] + prof["la_intra"][0]) / args.steps / 1e3,
                                                        "xd_la_multi_kernel<4> + xd_la_intra_kernel"),
-                         "note": "dependent-search wavefront kernel (SURVEY 8(d) config 2): HBM % reported as required; ncu "
-                                 "(profiles/r01k) shows instruction issue (56 % of 4 warp-inst/clk/SM), the ALU pipe (60 % of "
-                                 "its measured 2 warp-inst/clk/SM, profiles/int_pipe_peak.json) and the L1 data pipe (61 % of "
-                                 "peak wavefronts) as the limiters; DRAM traffic is below the algorithmic bytes because "
+                         "note": "dependent-search wavefront kernel (SURVEY 8(d) config 2): HBM % reported as required; the "
+                                 "kernel is bound by instruction issue and the ALU pipe, not by DRAM (ncu summaries under "
+                                 "profiles/, newest round first); DRAM traffic is below the algorithmic bytes because "
                                  "consecutive pairs share a reference frame in L2"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "pixel_cmp": {"sad_gpix_per_s": sad_px * world / step_s / 1e9, "satd_gpix_per_s": satd_px * world / step_s / 1e9,
@@ -630,33 +983,83 @@ def main():
                                               f"({frames} frames in {dt:.2f} s)"}
         else:
             line["cpu_baseline"] = None
+        threads = args.cpu_threads or host_cores()
+        baseline_ok = not args.no_cpu_baseline and world == 1
         if me_ms is not None:
-            tot_ms = sum(me_ms.values())
+            tot_ms = me_dev_ms_max                          # ms per frame, all 7 sizes, slowest rank
             me = {"workload": f"{w}x{h} x264_me_search_ref + x264_me_refine_qpel, HEX, subme 5, range 16, QP 26, one block list "
                               "per partition size tiling the frame (7 sizes), mvp from the lowres MVs",
-                  "frames_per_s_all_sizes": 1e3 / tot_ms, "ms_per_frame_by_size": me_ms,
-                  "launch": f"x264dsp_me_search_sized_frames_dev, {min(8, clip_len - 1)} frame pairs per launch"}
-            if not args.no_cpu_baseline and world == 1:
+                  "value": world * 1e3 / tot_ms, "unit": "frames/s (all 7 sizes)", "n_gpus": world,
+                  "frames_per_s_all_sizes": world * 1e3 / tot_ms, "ms_per_frame_by_size": me_ms,
+                  "launch": f"x264dsp_me_search_sized_frames_dev, {me_pairs} frame pairs per launch, every rank on its own frames",
+                  "e2e": {"value": world * me_pairs / me_e2e_s_max, "unit": "frames/s (all 7 sizes)",
+                          "h2d_bytes_per_step": int(me_e2e[1]), "d2h_bytes_per_step": int(me_e2e[2]),
+                          "api": "x264dsp_me_search_frames_host (pinned host pictures, block lists and results)",
+                          "note": "a block description is 116 bytes: the lists of the 7 sizes are 18x the bytes of the pictures, "
+                                  "so this door is bound by the host-to-device copy of the lists"}}
+            if baseline_ok:
                 cnt = me_search_cpu_counts(pkg, g, me_slots, me_blocks0)
                 sad = sum(c["sad_pix"] for c in cnt.values())
                 satd = sum(c["satd_pix"] for c in cnt.values())
+                ok = all(c["bit_exact"] for c in cnt.values())
+                e2e_ok = all(np.array_equal(me_e2e[3][i][: len(me_blocks0[nm][0])].view(np.uint8), me_blocks0[nm][1])
+                             for i, nm in enumerate(ME_SIZES))
                 me.update({"sad_gpix_per_s": sad / (tot_ms / 1e3) / 1e9, "satd_gpix_per_s": satd / (tot_ms / 1e3) / 1e9,
                            "sad_pix_per_frame": sad, "satd_pix_per_frame": satd,
                            "counted_by": "the CPU oracle's instrumented run of the same block lists (frame pair 0)",
-                           "bit_exact_vs_oracle": all(c["bit_exact"] for c in cnt.values()),
-                           "cpu_port_1core_frames_per_s": 1.0 / sum(c["cpu_s"] for c in cnt.values()),
-                           "int_pipe": int_pipe_roofline(sad, satd, tot_ms / 1e3, "xd_me_sized_kernel<W,H>, 7 sizes")})
+                           "bit_exact_vs_oracle": ok, "e2e_equals_device": bool(e2e_ok),
+                           "roofline": dict(int_pipe_roofline(sad, satd, tot_ms / 1e3, "xd_me_sized_kernel<W,H>, 7 sizes"), bound="int_pipe")})
+                pics = [pkg.synth_frame(w, h, rank * clips * clip_len + i) for i in range(2)]
+                blocks_by_size = {nm: me_blocks0[nm][0] for nm in ME_SIZES}
+                cb = {"unit": "frames/s (all 7 sizes)", "cores": threads, "kind": "reference",
+                      "sample": "the block lists of frame pair 0, every host thread a contiguous share of each list, repeated for ~4 s",
+                      "port_1core": 1.0 / sum(c["cpu_s"] for c in cnt.values())}
+                for which in ("O2", "O3"):
+                    fps, res = cpu_me_reference(which, w, h, pics, blocks_by_size, threads)
+                    if fps is not None:
+                        cb["value" if which == "O2" else "value_O3_x86-64-v3"] = fps
+                        same = all(np.array_equal(res[nm].view(np.uint8), me_blocks0[nm][1]) for nm in ME_SIZES)
+                        cb["gpu_equals_reference" + ("" if which == "O2" else "_O3")] = bool(same)
+                me["cpu_baseline"] = cb
             line["me_search"] = me
         if rc_ms is not None:
-            tot = sum(rc_ms.values())
+            tot = rc_dev_ms_max
+            hb = (w, h) == (1920, 1080)
             rc = {"workload": f"{w}x{h} inter macroblocks: x264_mb_mc 16x16 + x264_macroblock_encode (4x4 DCT, quant, dequant, "
                               "IDCT, decimation, chroma DC) + x264_frame_deblock_row, QP 26, frame-batched launches",
-                  "frames_per_s": 1e3 / tot, "ms_per_frame": rc_ms,
-                  "hbm_frac": {"residual": 16.5e6 / (rc_ms["residual"] / 1e3) / 1e9 / peak,
-                               "deblock": 6.8e6 / (rc_ms["deblock"] / 1e3) / 1e9 / peak} if (w, h) == (1920, 1080) else None}
-            if not args.no_cpu_baseline and world == 1:
+                  "value": world * 1e3 / tot, "unit": "frames/s", "n_gpus": world,
+                  "frames_per_s": world * 1e3 / tot, "ms_per_frame": rc_ms, "frames_per_launch": rc_frames,
+                  "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "algorithmic_MB_per_frame": {"mc": 6.27, "residual": 16.5, "deblock": 6.8},
+                               "frac": {"mc": 6.27e6 / (rc_ms["mc"] / 1e3) / 1e9 / peak,
+                                        "residual": 16.5e6 / (rc_ms["residual"] / 1e3) / 1e9 / peak,
+                                        "deblock": 6.8e6 / (rc_ms["deblock"] / 1e3) / 1e9 / peak}} if hb else None,
+                  "e2e": {"value": world * rc_frames / rc_e2e_s_max, "unit": "frames/s",
+                          "h2d_bytes_per_step": int(rc_e2e[1]), "d2h_bytes_per_step": int(rc_e2e[2]),
+                          "api": "x264dsp_recon_frames_host (pinned pictures, MVs, bS in; levels, nnz, cbp, deblocked I420 out)"}}
+            if rc_ms_big is not None and rc["roofline"]:
+                rc["ms_per_frame_at_384_frames_per_launch"] = rc_ms_big
+                rc["roofline"]["frac_at_384_frames_per_launch"] = {
+                    "mc": 6.27e6 / (rc_ms_big["mc"] / 1e3) / 1e9 / peak, "residual": 16.5e6 / (rc_ms_big["residual"] / 1e3) / 1e9 / peak,
+                    "deblock": 6.8e6 / (rc_ms_big["deblock"] / 1e3) / 1e9 / peak}
+            if baseline_ok:
                 ok, cpu_s, coded = recon_cpu_check(pkg, g, rc_check)
-                rc.update({"bit_exact_vs_oracle": ok, "coded_mbs_frame0": coded, "cpu_port_1core_frames_per_s": 1.0 / cpu_s})
+                rc.update({"bit_exact_vs_oracle": ok, "coded_mbs_frame0": coded})
+                pics = [pkg.synth_frame(w, h, rank * 7 + i) for i in range(2)]
+                cb = {"unit": "frames/s", "cores": threads, "kind": "reference", "port_1core": 1.0 / cpu_s,
+                      "sample": "frame 0 of the measurement (x264_mb_mc + x264_macroblock_encode per macroblock, then "
+                                "x264_frame_deblock_row), one frame per host thread and pass, repeated for ~4 s"}
+                for which in ("O2", "O3"):
+                    fps, res = cpu_recon_reference(which, w, h, pics, rc_check["mv"], rc_check["bs"], threads)
+                    if fps is not None:
+                        cb["value" if which == "O2" else "value_O3_x86-64-v3"] = fps
+                        go = rc_check
+                        gy = go["deblocked"][g.luma_origin:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:, : g.luma_w]
+                        gc = go["deblocked"][g.slot_chroma_off + g.chroma_origin:][: (g.luma_h // 2) * g.chroma_stride].reshape(
+                            g.luma_h // 2, g.chroma_stride)[:, : g.luma_w]
+                        same = (np.array_equal(res[0], go["levels"]) and np.array_equal(res[1], go["nnz"]) and np.array_equal(res[2], go["cbp"])
+                                and np.array_equal(res[3], gy) and np.array_equal(res[4], gc))
+                        cb["gpu_equals_reference" + ("" if which == "O2" else "_O3")] = bool(same)
+                rc["cpu_baseline"] = cb
             line["recon"] = rc
         print(json.dumps(line))
     ctx.close()

@@ -178,6 +178,18 @@ void xref_frame_load_i420( void *hv, void *fv, uint8_t *y, uint8_t *u, uint8_t *
         x264_frame_expand_border_mod16( h, f );
 }
 
+/* luma only, for callers that want nothing but the lookahead of a picture (it never reads chroma): the luma part of
+ * x264_frame_copy_picture (h->mc.plane_copy, common/frame.c:227) + x264_frame_expand_border_mod16.  This is what the
+ * GPU arm's end-to-end call uploads, so the reference arm of bench.py is not charged for a chroma copy it does not need. */
+void xref_frame_load_luma( void *hv, void *fv, uint8_t *y )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = fv;
+    h->mc.plane_copy( f->plane[0], f->i_stride[0], y, h->param.i_width, h->param.i_width, h->param.i_height );
+    if( h->param.i_width & 15 || h->param.i_height & 15 )
+        x264_frame_expand_border_mod16( h, f );
+}
+
 void xref_frame_init_lowres( void *hv, void *fv )
 {
     x264_frame_init_lowres( (x264_t *)hv, (x264_frame_t *)fv );

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libx264dsp_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libx264ref.so")
+REF_O3_SO = os.path.join(ORACLE_DIR, "_ref", "o3", "libx264ref.so")       # same sources at -O3 -march=x86-64-v3
 REF_CLI = os.path.join(ORACLE_DIR, "_ref", "x264ref")
 REFERENCE_TREE = "/root/reference"
 
@@ -84,7 +85,7 @@ def oracle():
     global _oracle
     if _oracle is None:
         srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
-        stale = (not os.path.exists(ORACLE_SO)
+        stale = (not os.path.exists(ORACLE_SO) or not os.path.exists(SYNTH_SO)
                  or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(s) for s in srcs))
         if stale:
             _make()
@@ -94,8 +95,44 @@ def oracle():
     return _oracle
 
 
+SYNTH_SO = os.path.join(ORACLE_DIR, "_build", "libx264dsp_synth.so")
+_synth = None
+
+
+def synth_frame(width, height, n, cut_frame=-1, luma_only=False):
+    """the shared synthetic generator (x264dsp_synth_frame) WITHOUT the product library: planar I420 or luma of frame n"""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_SO):
+            _make()
+        _synth = C.CDLL(SYNTH_SO)
+    y = np.empty(width * height, np.uint8)
+    if luma_only:
+        rc = _synth.x264dsp_synth_frame(width, height, n, cut_frame, ptr(y), None, None)
+        assert rc == 0
+        return y
+    cw, ch = width // 2, height // 2
+    buf = np.empty(width * height + 2 * cw * ch, np.uint8)
+    rc = _synth.x264dsp_synth_frame(width, height, n, cut_frame, ptr(buf), ptr(buf[width * height:]),
+                                    ptr(buf[width * height + cw * ch:]))
+    assert rc == 0
+    return buf
+
+
 def ref_available():
     return os.path.exists(REF_SO) or os.path.isdir(REFERENCE_TREE)
+
+
+def _load_ref(path):
+    lib = C.CDLL(path)
+    lib.xref_open.restype = C.c_void_p
+    lib.xref_frame_new.restype = C.c_void_p
+    lib.xref_frame_ptr.restype = C.c_void_p
+    lib.xref_cost_mv.restype = C.POINTER(C.c_uint16)
+    lib.xref_time_lookahead.restype = C.c_double
+    for name in ("xref_pixf", "xref_dctf", "xref_zigzagf", "xref_mcf", "xref_quantf", "xref_loopf"):
+        getattr(lib, name).restype = C.c_void_p
+    return lib
 
 
 def ref():
@@ -106,23 +143,28 @@ def ref():
             _make("ref")
         if not os.path.exists(REF_SO):
             return None
-        lib = C.CDLL(REF_SO)
-        lib.xref_open.restype = C.c_void_p
-        lib.xref_frame_new.restype = C.c_void_p
-        lib.xref_frame_ptr.restype = C.c_void_p
-        lib.xref_cost_mv.restype = C.POINTER(C.c_uint16)
-        lib.xref_time_lookahead.restype = C.c_double
-        for name in ("xref_pixf", "xref_dctf", "xref_zigzagf", "xref_mcf", "xref_quantf", "xref_loopf"):
-            getattr(lib, name).restype = C.c_void_p
-        _ref = lib
+        _ref = _load_ref(REF_SO)
     return _ref
+
+
+_ref_o3 = None
+
+
+def ref_o3():
+    """the same reference sources built at -O3 -march=x86-64-v3; None when absent"""
+    global _ref_o3
+    if _ref_o3 is None:
+        if ref() is None or not os.path.exists(REF_O3_SO):
+            return None
+        _ref_o3 = _load_ref(REF_O3_SO)
+    return _ref_o3
 
 
 class RefEncoder:
     """an encoder instance of the unmodified reference (x264_encoder_open)"""
 
-    def __init__(self, width, height, me=0, subme=2, me_range=16, qp=26, psub16x16=0):
-        self.lib = ref()
+    def __init__(self, width, height, me=0, subme=2, me_range=16, qp=26, psub16x16=0, lib=None):
+        self.lib = lib if lib is not None else ref()
         assert self.lib is not None
         self.h = C.c_void_p(self.lib.xref_open(width, height, me, subme, me_range, qp, psub16x16))
         assert self.h.value

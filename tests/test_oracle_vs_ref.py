@@ -871,3 +871,31 @@ def test_predict_mvc_16x16_frame(enc):
         assert np.array_equal(n1, n2), f"trial {trial}: counts differ at {np.nonzero(n1 != n2)[0][:5]}: {n1[n1 != n2][:5]} vs {n2[n1 != n2][:5]}"
         assert np.array_equal(m1, m2), f"trial {trial}: candidates differ at mb {np.nonzero((m1 != m2).any((1, 2)))[0][:5]}"
         assert n1.min() >= 4 and n1.max() == 4 + (lowres is not None) + 3 * (l0 is not None)
+
+
+def test_o3_build_of_the_reference_agrees_with_o2():
+    """the -O3 -march=x86-64-v3 build bench.py also times is the same code: identical lookahead and search results"""
+    lib3 = cc.ref_o3()
+    if lib3 is None:
+        pytest.skip("oracle/_ref/o3 not built")
+    w, h = 352, 288
+    clip = cc.synth_clip(w, h, 3)
+    res = []
+    for lib in (cc.ref(), lib3):
+        enc = cc.RefEncoder(w, h, me=1, subme=5, lib=lib)
+        frames = [enc.new_frame(False) for _ in range(3)]
+        for f, pic in zip(frames, clip):
+            enc.load(f, pic)
+        arr = (C.c_void_p * 3)(*[f.value for f in frames])
+        costs = (C.c_int * 3)()
+        lib.xref_time_lookahead(enc.h, arr, 3, costs)
+        g = cc.oracle_geom(w, h)
+        fref = enc.new_frame(True)
+        enc.load(fref, clip[0])
+        lib.xref_frame_filter_all(enc.h, fref)
+        blocks = make_me_blocks(g, np.random.RandomState(4), 3, 200, 30)
+        out = np.zeros(200, cc.ME_RESULT_DTYPE)
+        lib.xref_me_search_batch(enc.h, frames[1], fref, 26, 1, 5, 16, 1, blocks.ctypes.data_as(C.c_void_p), 200,
+                                 out.ctypes.data_as(C.c_void_p))
+        res.append((list(costs), out.copy()))
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])

@@ -155,11 +155,11 @@ struct xd_mes_state
     int mvx, mvy, cost, cost_mv;
 };
 
-#define MES_SAD( qx, qy ) ( xd_mes_cost<W, H>( B, f, tile0, ( qx ), ( qy ), B.fpel_satd, gmask ) + xd_mes_bits( B, ( qx ), ( qy ) ) )
+#define MES_SAD( qx, qy ) ( xd_mes_cost<W, H>( B, f, tile0, ( qx ), ( qy ), FS, gmask ) + xd_mes_bits( B, ( qx ), ( qy ) ) )
 #define MES_SATD( qx, qy ) ( xd_mes_cost<W, H>( B, f, tile0, ( qx ), ( qy ), true, gmask ) + xd_mes_bits( B, ( qx ), ( qy ) ) )
 
 // refine_subpel (me.c:466-587) with p_halfpel_thresh == NULL
-template<int W, int H>
+template<int W, int H, bool FS>
 __device__ void xd_mes_refine( const xd_mes_blk &B, const uint32_t *f, int tile0, unsigned gmask, xd_mes_state &S,
                                int subme, int hpel_iters, int qpel_iters, bool final_refine )
 {
@@ -186,7 +186,7 @@ __device__ void xd_mes_refine( const xd_mes_blk &B, const uint32_t *f, int tile0
         if( bmx == omx && bmy == omy )
             break;
     }
-    if( !final_refine && !B.fpel_satd )                                  // me.c:519-524 (mbcmp_unaligned != fpelcmp)
+    if( !final_refine && !FS )                                           // me.c:519-524 (mbcmp_unaligned != fpelcmp)
         bcost = MES_SATD( bmx, bmy );
 
     if( subme != 1 )
@@ -227,7 +227,9 @@ __device__ void xd_mes_refine( const xd_mes_blk &B, const uint32_t *f, int tile0
     S.cost_mv = xd_mes_bits( B, bmx, bmy );
 }
 
-template<int W, int H>
+// FS: the full-pel metric is SATD (me = TESA with subme >= 2); a compile-time property so that the ordinary search
+// carries none of it
+template<int W, int H, bool FS>
 __global__ void __launch_bounds__( MES_THREADS )
 xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, const uint8_t *__restrict__ fref_slot,
                     x264dsp_me_params_t P, const uint16_t *__restrict__ cost_mv, int n,
@@ -261,7 +263,7 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
     B.smaxx = in->mv_max_spel[0]; B.smaxy = in->mv_max_spel[1];
     const int n_mvc = min( max( in->i_mvc, 0 ), 16 );
     const int subme = P.subpel_refine;
-    B.fpel_satd = P.me_method == X264DSP_ME_TESA && subme >= 2;
+    B.fpel_satd = FS;
 
     // this lane's source tile(s) stay in registers for the whole search
     const int tile0 = sub * C::NT;
@@ -324,7 +326,7 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
         // me.c:194-229: rounded MVP without mv cost, then the rounded / clipped candidates
         bmx = pmx;
         bmy = pmy;
-        bcost = xd_mes_cost<W, H>( B, f, tile0, pmx << 2, pmy << 2, B.fpel_satd, gmask );
+        bcost = xd_mes_cost<W, H>( B, f, tile0, pmx << 2, pmy << 2, FS, gmask );
         pmv = xd_mes_pack( pmx, pmy );
         int sel_x = pmx, sel_y = pmy;
         for( int i = 0; i < n_mvc; i++ )
@@ -432,9 +434,9 @@ xd_me_sized_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fenc_slot, con
         S.cost += S.cost_mv;
 
     if( subme >= 2 )
-        xd_mes_refine<W, H>( B, f, tile0, gmask, S, subme, xd_mes_iters[subme][2], xd_mes_iters[subme][3], false );
+        xd_mes_refine<W, H, FS>( B, f, tile0, gmask, S, subme, xd_mes_iters[subme][2], xd_mes_iters[subme][3], false );
     if( P.refine_qpel )                                                  // me.c:426-435, i_ref_cost = 0
-        xd_mes_refine<W, H>( B, f, tile0, gmask, S, subme, xd_mes_iters[subme][0], xd_mes_iters[subme][1], true );
+        xd_mes_refine<W, H, FS>( B, f, tile0, gmask, S, subme, xd_mes_iters[subme][0], xd_mes_iters[subme][1], true );
 
     if( sub == 0 )
     {
@@ -455,8 +457,12 @@ static int xd_mes_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uin
     const int64_t threads = (int64_t)n * xd_mes_cfg<W, H>::G;
     const dim3 grid( (unsigned)( ( threads + MES_THREADS - 1 ) / MES_THREADS ), n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_ME, s );
-    xd_me_sized_kernel<W, H><<<grid, MES_THREADS, 0, s>>>( *g, fenc_slot, fref_slot, *params,
-                                                           ctx->cost_mv_dev[params->qp] + 4096, n, blocks, results );
+    if( params->me_method == X264DSP_ME_TESA && params->subpel_refine >= 2 )
+        xd_me_sized_kernel<W, H, true><<<grid, MES_THREADS, 0, s>>>( *g, fenc_slot, fref_slot, *params,
+                                                                     ctx->cost_mv_dev[params->qp] + 4096, n, blocks, results );
+    else
+        xd_me_sized_kernel<W, H, false><<<grid, MES_THREADS, 0, s>>>( *g, fenc_slot, fref_slot, *params,
+                                                                      ctx->cost_mv_dev[params->qp] + 4096, n, blocks, results );
     xd_prof_end( ctx, XD_PROF_ME, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
