@@ -74,10 +74,10 @@ xd_cost_batch_kernel( int cmp, int n, const uint8_t *__restrict__ pix1, const in
                         sa[r] = sb[r] = 0;
                     }
                 }
-                int s = xd_had_abs4x4( ra, rb );
+                int s = xd_satd4x4( ra, rb );
                 if( w >= 8 )
-                    s += xd_had_abs4x4( sa, sb );
-                acc += s >> 1;
+                    s += xd_satd4x4( sa, sb );
+                acc += s;
             }
         }
     }

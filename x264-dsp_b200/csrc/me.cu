@@ -12,6 +12,7 @@
 // into one integer and takes the min, which reproduces the reference's strict '<' / first-wins
 // ordering for every search stage.  All scalar search state is replicated in the 32 lanes.
 #include "common.cuh"
+#include "leaf.cuh"
 
 #define ME_COST_MAX ( 1 << 28 )
 #define ME_WARPS 4
@@ -96,30 +97,6 @@ __device__ __forceinline__ int xd_me_sad_raw( const xd_me_blk &B, int qx, int qy
     return acc;
 }
 
-__device__ __forceinline__ int xd_me_had4x4( const uint32_t a[4], const uint32_t b[4] )
-{
-    int t[4][4];
-#pragma unroll
-    for( int r = 0; r < 4; r++ )
-    {
-        const int d0 = (int)( a[r] & 255 ) - (int)( b[r] & 255 );
-        const int d1 = (int)( ( a[r] >> 8 ) & 255 ) - (int)( ( b[r] >> 8 ) & 255 );
-        const int d2 = (int)( ( a[r] >> 16 ) & 255 ) - (int)( ( b[r] >> 16 ) & 255 );
-        const int d3 = (int)( a[r] >> 24 ) - (int)( b[r] >> 24 );
-        const int s01 = d0 + d1, m01 = d0 - d1, s23 = d2 + d3, m23 = d2 - d3;
-        t[r][0] = s01 + s23; t[r][1] = s01 - s23; t[r][2] = m01 + m23; t[r][3] = m01 - m23;
-    }
-    int acc = 0;
-#pragma unroll
-    for( int c = 0; c < 4; c++ )
-    {
-        const int s01 = t[0][c] + t[1][c], m01 = t[0][c] - t[1][c];
-        const int s23 = t[2][c] + t[3][c], m23 = t[2][c] - t[3][c];
-        acc += abs( s01 + s23 ) + abs( s01 - s23 ) + abs( m01 + m23 ) + abs( m01 - m23 );
-    }
-    return acc;
-}
-
 // SATD (common/pixel.c:267-337) of the block at quarter-pel (qx,qy)
 __device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, int sub )
 {
@@ -140,7 +117,7 @@ __device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, i
                 const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)( y + r ) * B.stride + x );
                 pa[r] = p.x; pb[r] = p.y; fa[r] = f.x; fb[r] = f.y;
             }
-            acc += ( xd_me_had4x4( fa, pa ) + xd_me_had4x4( fb, pb ) ) >> 1;
+            acc += xd_satd4x4( fa, pa ) + xd_satd4x4( fb, pb );
         }
         else
         {
@@ -150,7 +127,7 @@ __device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, i
                 pa[r] = xd_me_pred4( s, B.stride, 0, y + r );
                 fa[r] = xd_load4_unaligned( B.fenc + (int64_t)( y + r ) * B.stride );
             }
-            acc += xd_me_had4x4( fa, pa ) >> 1;
+            acc += xd_satd4x4( fa, pa );
         }
     }
     acc += __shfl_xor_sync( 0xffffffffu, acc, 1 );

@@ -74,9 +74,9 @@ __device__ int xs_block_cost( int cmp, int w, int h, const uint8_t *p1, int s1, 
                     a[r] = xs_pack4( p1 + ( y + r ) * s1 + x + half );
                     b[r] = xs_pack4( p2 + ( y + r ) * s2 + x + half );
                 }
-                s += xd_had_abs4x4( a, b );
+                s += xd_satd4x4( a, b );
             }
-            acc += s >> 1;
+            acc += s;
         }
     }
     else
