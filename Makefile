@@ -3,6 +3,7 @@
 #   make oracle     -> oracle/_build/libx264dsp_oracle.so (CPU checker, test infrastructure)
 #   make ref        -> oracle/_ref/libx264ref.so          (unmodified reference, needs /root/reference)
 #   make sass       -> x264-dsp_b200/_build/*.sass        (cuobjdump -sass of every kernel)
+#   make glue       -> glue/_build/x264ref_gpu             (reference CLI + glue/*.c + the product, no Python)
 #   make examples   -> examples/_build/lookahead_host      (plain C host program on the C ABI, gcc only)
 
 NVCC     ?= /usr/local/cuda/bin/nvcc
@@ -38,6 +39,10 @@ oracle:
 ref:
 	$(MAKE) -C oracle ref
 
+# the unmodified reference CLI linked with glue/*.c and $(LIB): glue/_build/x264ref_gpu (needs /root/reference)
+glue: $(LIB)
+	$(MAKE) -C glue
+
 examples: examples/_build/lookahead_host
 
 examples/_build/lookahead_host: examples/lookahead_host.c include/x264dsp_b200.h $(LIB)
@@ -51,4 +56,4 @@ clean:
 	rm -rf $(OUT) $(LIB) examples/_build
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle ref sass clean examples
+.PHONY: all oracle ref glue sass clean examples

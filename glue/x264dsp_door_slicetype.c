@@ -13,7 +13,7 @@ int xref_slicetype_frame_cost( x264_t *h, x264_frame_t **frames, int p0, int p1,
     return x264_slicetype_frame_cost( h, frames, p0, p1, b );
 }
 
-/* Driver-level door (see hooks.c): x264_slicetype_frame_cost caches its result in the frame
+/* Driver-level door (see x264dsp_doors.c): x264_slicetype_frame_cost caches its result in the frame
  * (slicetype.c:238), so a batched implementation only has to fill that cache before the reference
  * asks.  x264_slicetype_analyse is about to ask for next.list[0] against last_nonb (slicetype.c:408-429),
  * and x264_rc_analyse_slice asks for the same pair later (slicetype.c:605-642). */

@@ -1,4 +1,4 @@
-/* Driver-level doors of the drop-in proof.  TEST INFRASTRUCTURE / integration example.
+/* Driver-level doors of the drop-in: the reference-side half of the glue (the device side is x264dsp_glue.c).
  *
  * Three drivers of the hot path are compiled under other names (see oracle/Makefile: the UNMODIFIED
  * sources, renamed with -D on the command line) so that the definitions below take their place:
@@ -12,7 +12,7 @@
  *
  *   x264_me_search_ref                  encoder/me.c:129     called from encoder/analyse.c:820 ... (every partition)
  *
- * and encoder/slicetype.c's x264_slicetype_decide is wrapped in wrap_slicetype.c.  With no hooks
+ * and encoder/slicetype.c's x264_slicetype_decide is wrapped in x264dsp_door_slicetype.c.  With no hooks
  * installed every definition forwards to the original, so the library and the CLI behave exactly like
  * the reference (tests/test_golden.py::test_reference_cli_bitstream pins that).  With hooks installed
  * (tests/test_gpu_dropin_drivers.py) the planes and the lookahead costs come from libx264dsp_b200.so;
@@ -312,7 +312,7 @@ void x264_macroblock_encode( x264_t *h )
             i4_modes[i] = (uint8_t)h->mb.cache.intra4x4_pred_mode[x264_scan8[i]];
         kind = 2 + ( ( h->mb.i_neighbour4[5] & (MB_TOPRIGHT|MB_TOP) ) == MB_TOP ? 4 : 0 );
     }
-    else if( !h->mb.b_skip_mc )
+    else if( inter && !h->mb.b_skip_mc )
         x264_mb_mc( h );
     memset( levels, 0, sizeof(levels) );
     memset( luma_dc, 0, sizeof(luma_dc) );

@@ -1,0 +1,391 @@
+/* x264dsp_glue.c -- the device side of the doors in x264dsp_doors.c, in plain C.
+ *
+ * This is the file a maintainer of the reference adds next to glue/x264dsp_doors.c and
+ * glue/x264dsp_door_slicetype.c: it is compiled against the reference's own headers (x264_t, x264_frame_t) and calls
+ * nothing but the C ABI of libx264dsp_b200.so (include/x264dsp_b200.h).  x264dsp_glue_install() puts one function
+ * behind every door:
+ *
+ *   x264_frame_init_lowres (common/mc.c:404)                         -> x264dsp_frame_init_lowres_dev
+ *   x264_frame_deblock_row + x264_frame_expand_border + x264_frame_filter + x264_frame_expand_border_filtered
+ *       (common/deblock.c:341, common/frame.c:386-413, common/mc.c:506; encoder/encoder.c:1359-1385)
+ *                                                                    -> x264dsp_deblock_frame_dev,
+ *                                                                       x264dsp_frame_expand_border_dev, x264dsp_frame_filter_dev
+ *   x264_slicetype_frame_cost (encoder/slicetype.c:223)              -> x264dsp_lookahead_frame_cost_dev
+ *   x264_me_search_ref (encoder/me.c:129)                            -> x264dsp_me_search_batch_dev
+ *   x264_mb_mc (common/macroblock.c:28)                              -> x264dsp_mc_frames_part_dev
+ *   x264_macroblock_probe_pskip (encoder/macroblock.c:492)           -> x264dsp_mc_frame_dev + x264dsp_probe_pskip_frames_dev
+ *   x264_macroblock_encode (encoder/macroblock.c:310)                -> x264dsp_residual_frames_typed_dev
+ *
+ * The reference calls these doors one macroblock (or one frame) at a time, so this glue is a CORRECTNESS drop-in -- every
+ * call is a round trip to the device -- and not the fast path (the frame-batched entry points are; bench.py times those).
+ * What it proves is the boundary: the unmodified encoder, linked with these three files and the library, writes the
+ * byte-identical bitstream (glue/Makefile builds it as x264ref_gpu; tests/test_gpu_glue_cli.py runs it).
+ *
+ * Frames the encoder will search in or read source samples from stay resident on the device (a small cache keyed by
+ * the x264_frame_t pointer, filled by the lowres door for source frames and by the in-loop-filter door for
+ * reconstructed frames).  A door whose frame is not resident declines (returns 1) and the reference's own code runs;
+ * the door statistics (xref_door_stats_read) count that, so a caller can insist on zero declines.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common/common.h"
+#include "x264dsp_b200.h"
+#include "x264dsp_glue.h"
+
+/* the doors (x264dsp_doors.c, x264dsp_door_slicetype.c) */
+typedef void (*xref_frame_cb)( void *h, void *frame );
+typedef void (*xref_cost_cb)( void *h, void *p0, void *b, int want_intra, int16_t *mvs, int *costs, int *sums );
+typedef void (*xref_fdec_cb)( void *h, void *frame, int do_deblock, const int8_t *mb_type, const uint8_t *partition,
+                              const int16_t *cbp, const uint8_t *bs, int qp, int alpha_off, int beta_off );
+typedef int (*xref_me_cb)( void *h, void *fenc, void *fref, const x264dsp_me_block_t *in, int me_method, int subme,
+                           int me_range, int qp, x264dsp_me_result_t *out );
+typedef int (*xref_mbenc_cb)( void *h, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y, uint8_t *fdec_c,
+                              int qp, int kind, const uint8_t *i4_modes, int16_t *levels, int16_t *luma_dc, uint8_t *nnz,
+                              int *cbp );
+typedef int (*xref_pskip_cb)( void *h, void *fenc, void *fref, int mb_x, int mb_y, int mvx, int mvy, int qp,
+                              uint8_t *fdec_y, uint8_t *fdec_c, int *skip );
+typedef int (*xref_mbmc_cb)( void *h, void *fref, int mb_x, int mb_y, const int16_t *mv8x8, uint8_t *fdec_y, uint8_t *fdec_c );
+void xref_set_driver_hooks( xref_frame_cb lowres, xref_frame_cb filter, xref_cost_cb cost );
+void xref_set_fdec_hook( xref_fdec_cb cb );
+void xref_set_me_hook( xref_me_cb cb );
+void xref_set_mbenc_hook( xref_mbenc_cb cb );
+void xref_set_pskip_hook( xref_pskip_cb cb );
+void xref_set_mbmc_hook( xref_mbmc_cb cb );
+void xref_driver_hook_calls( int out[3] );
+void xref_door_stats_read( int out[12] );
+
+#define GLUE_RESIDENT 8
+
+static struct
+{
+    x264dsp_ctx_t *ctx;
+    x264dsp_geom_t g, g1;                 /* the picture; one macroblock as a 16x16 "frame" (macroblock_encode door) */
+    uint8_t *pool;                        /* GLUE_RESIDENT resident slots + 2 work slots + 1 prediction slot */
+    void *res_frame[GLUE_RESIDENT];       /* x264_frame_t* held by each resident slot */
+    int res_next;
+    /* device scratch */
+    int8_t *d_mb_type;
+    uint8_t *d_partition, *d_bs, *d_skip, *d_mb_slots, *d_kind, *d_modes, *d_nnz;
+    int16_t *d_cbp, *d_mvs, *d_pmv, *d_mv4, *d_levels, *d_luma_dc, *d_cbp1;
+    int32_t *d_costs, *d_sums;
+    x264dsp_me_block_t *d_blk;
+    x264dsp_me_result_t *d_res;
+    /* host scratch */
+    uint8_t *mb_stage;                    /* two 16x16 slots */
+    uint8_t *rows;                        /* 16 luma rows of a macroblock as one linear piece of the plane */
+    int64_t launches0;
+    int calls[8];                         /* lowres, fdec, cost, me, mbenc, pskip, mbmc, deblocked frames */
+} G;
+
+#define GLUE_CHECK( call ) do { int rc_ = ( call ); if( rc_ ) { fprintf( stderr, "x264dsp glue: %s failed (%d) at %s:%d\n", \
+                                #call, rc_, __FILE__, __LINE__ ); abort(); } } while( 0 )
+
+static void *glue_dev( size_t bytes )
+{
+    void *p = NULL;
+    GLUE_CHECK( x264dsp_dev_alloc( G.ctx, bytes, &p ) );
+    GLUE_CHECK( x264dsp_dev_zero( G.ctx, p, bytes, NULL ) );
+    return p;
+}
+
+/* first call: the picture size is known from the encoder handle */
+static void glue_open( x264_t *h )
+{
+    if( G.ctx )
+        return;
+    GLUE_CHECK( x264dsp_create( 0, &G.ctx ) );
+    GLUE_CHECK( x264dsp_geometry( h->param.i_width, h->param.i_height, &G.g ) );
+    GLUE_CHECK( x264dsp_geometry( 16, 16, &G.g1 ) );
+    const size_t nmb = G.g.mb_count;
+    G.pool = glue_dev( (size_t)( GLUE_RESIDENT + 3 ) * G.g.slot_bytes );
+    G.d_mb_type = glue_dev( nmb );
+    G.d_partition = glue_dev( nmb );
+    G.d_cbp = glue_dev( 2 * nmb );
+    G.d_bs = glue_dev( 64 * nmb );
+    G.d_skip = glue_dev( nmb );
+    G.d_mvs = glue_dev( 4 * nmb );
+    G.d_pmv = glue_dev( 4 * nmb );
+    G.d_mv4 = glue_dev( 16 * nmb );
+    G.d_costs = glue_dev( 4 * nmb );
+    G.d_sums = glue_dev( X264DSP_LA_SUMS * sizeof(int32_t) );
+    G.d_blk = glue_dev( sizeof(x264dsp_me_block_t) );
+    G.d_res = glue_dev( sizeof(x264dsp_me_result_t) );
+    G.d_mb_slots = glue_dev( 2 * (size_t)G.g1.slot_bytes );
+    G.d_kind = glue_dev( 16 );
+    G.d_modes = glue_dev( 16 );
+    G.d_levels = glue_dev( X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t) );
+    G.d_luma_dc = glue_dev( 16 * sizeof(int16_t) );
+    G.d_nnz = glue_dev( 32 );
+    G.d_cbp1 = glue_dev( 16 );
+    G.mb_stage = calloc( 2, (size_t)G.g1.slot_bytes );
+    G.rows = malloc( (size_t)16 * G.g.luma_stride );
+    G.launches0 = x264dsp_launch_count( G.ctx );
+}
+
+static uint8_t *glue_slot( int i )      { return G.pool + (size_t)i * G.g.slot_bytes; }
+static uint8_t *glue_work( int i )      { return glue_slot( GLUE_RESIDENT + i ); }
+static uint8_t *glue_pred( void )       { return glue_slot( GLUE_RESIDENT + 2 ); }
+
+static uint8_t *glue_resident( const void *frame )
+{
+    for( int i = 0; i < GLUE_RESIDENT; i++ )
+        if( G.res_frame[i] == frame )
+            return glue_slot( i );
+    return NULL;
+}
+
+/* the slot that will hold `frame` from now on (the oldest entry makes room) */
+static uint8_t *glue_make_resident( void *frame )
+{
+    uint8_t *s = glue_resident( frame );
+    if( s )
+        return s;
+    const int i = G.res_next;
+    G.res_next = ( G.res_next + 1 ) % GLUE_RESIDENT;
+    G.res_frame[i] = frame;
+    return glue_slot( i );
+}
+
+/* ---- x264_frame_init_lowres: padded source plane in; four padded half-resolution planes out, and the source plane with
+ *      its duplicated last column / row (mc.c:412-415).  buffer[0] = planes N | H | V | HV, buffer[1] = NV12 chroma,
+ *      buffer_lowres[0] = the four lowres planes -- the layout of one frame slot (x264dsp_geom_t). */
+static void glue_lowres( void *hv, void *fv )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = fv;
+    glue_open( h );
+    const x264dsp_geom_t *g = &G.g;
+    uint8_t *slot = glue_make_resident( f );
+    GLUE_CHECK( x264dsp_h2d( G.ctx, slot, f->buffer[0], g->luma_plane_size, NULL ) );
+    GLUE_CHECK( x264dsp_h2d( G.ctx, slot + g->slot_chroma_off, f->buffer[1], g->chroma_plane_size, NULL ) );
+    GLUE_CHECK( x264dsp_frame_init_lowres_dev( G.ctx, g, slot, 1, NULL ) );
+    GLUE_CHECK( x264dsp_frame_export_lowres_dev( G.ctx, g, slot, 1, NULL ) );    /* the reference wants row-major lowres[0..3] */
+    GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[0], slot, g->luma_plane_size, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer_lowres[0], slot + g->slot_lowres_off, 4 * (size_t)g->lowres_plane_size, NULL ) );
+    G.calls[0]++;
+}
+
+/* ---- the in-loop filter of a reconstructed frame, once per frame: deblock -> expand_border -> hpel planes */
+static void glue_fdec( void *hv, void *fv, int do_deblock, const int8_t *mb_type, const uint8_t *partition,
+                       const int16_t *cbp, const uint8_t *bs, int qp, int alpha_off, int beta_off )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = fv;
+    glue_open( h );
+    const x264dsp_geom_t *g = &G.g;
+    const size_t nmb = g->mb_count;
+    uint8_t *slot = glue_make_resident( f );                 /* this reconstruction is the next frame's reference */
+    GLUE_CHECK( x264dsp_h2d( G.ctx, slot, f->buffer[0], g->luma_plane_size, NULL ) );
+    GLUE_CHECK( x264dsp_h2d( G.ctx, slot + g->slot_chroma_off, f->buffer[1], g->chroma_plane_size, NULL ) );
+    if( do_deblock )
+    {
+        GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_mb_type, mb_type, nmb, NULL ) );
+        GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_partition, partition, nmb, NULL ) );
+        GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_cbp, cbp, 2 * nmb, NULL ) );
+        GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_bs, bs, 64 * nmb, NULL ) );
+        GLUE_CHECK( x264dsp_deblock_frame_dev( G.ctx, g, slot, G.d_mb_type, G.d_partition, G.d_cbp, G.d_bs, qp, alpha_off,
+                                               beta_off, NULL ) );
+        G.calls[7]++;
+    }
+    GLUE_CHECK( x264dsp_frame_expand_border_dev( G.ctx, g, slot, 1, NULL ) );
+    GLUE_CHECK( x264dsp_frame_filter_dev( G.ctx, g, slot, 1, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[0], slot, 4 * (size_t)g->luma_plane_size, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[1], slot + g->slot_chroma_off, g->chroma_plane_size, NULL ) );
+    G.calls[1]++;
+}
+
+/* ---- x264_slicetype_frame_cost( p0, b, b ): the lowres planes as the caller holds them (row-major) go into two work
+ *      slots, are brought into the lookahead's tiled layout, and the per-block MVs / costs and the frame sums come back
+ *      into the reference's own arrays */
+static void glue_cost( void *hv, void *p0v, void *bv, int want_intra, int16_t *mvs, int *costs, int *sums )
+{
+    x264_t *h = hv;
+    x264_frame_t *p0 = p0v, *b = bv;
+    glue_open( h );
+    const x264dsp_geom_t *g = &G.g;
+    const size_t wps4 = 4 * (size_t)g->lowres_plane_size, nmb = g->mb_count;
+    const int32_t bi[1] = { GLUE_RESIDENT + 1 }, pi[1] = { GLUE_RESIDENT };
+    const uint8_t wi[1] = { (uint8_t)( want_intra != 0 ) };
+    int32_t s[X264DSP_LA_SUMS];
+    GLUE_CHECK( x264dsp_h2d( G.ctx, glue_work( 0 ) + g->slot_lowres_off, p0->buffer_lowres[0], wps4, NULL ) );
+    GLUE_CHECK( x264dsp_h2d( G.ctx, glue_work( 1 ) + g->slot_lowres_off, b->buffer_lowres[0], wps4, NULL ) );
+    GLUE_CHECK( x264dsp_frame_retile_lowres_dev( G.ctx, g, glue_work( 0 ), 2, NULL ) );
+    GLUE_CHECK( x264dsp_dev_zero( G.ctx, G.d_mvs, 4 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_dev_zero( G.ctx, G.d_costs, 4 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_dev_zero( G.ctx, G.d_sums, sizeof(s), NULL ) );
+    GLUE_CHECK( x264dsp_lookahead_frame_cost_dev( G.ctx, g, G.pool, 1, bi, pi, wi, G.d_mvs, G.d_costs, G.d_sums, NULL, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, mvs, G.d_mvs, 4 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, costs, G.d_costs, 4 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, s, G.d_sums, sizeof(s), NULL ) );
+    memcpy( sums, s, 8 * sizeof(int) );
+    G.calls[2]++;
+}
+
+/* ---- x264_me_search_ref for one partition: a one-block list on the resident source / reference frames */
+static int glue_me( void *hv, void *fenc, void *fref, const x264dsp_me_block_t *in, int me_method, int subme, int me_range,
+                    int qp, x264dsp_me_result_t *out )
+{
+    const uint8_t *se = glue_resident( fenc ), *sr = glue_resident( fref );
+    if( !G.ctx || !se || !sr )
+        return 1;
+    const x264dsp_me_params_t prm = { me_method, subme, me_range, qp, 0 };
+    GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_blk, in, sizeof(*in), NULL ) );
+    GLUE_CHECK( x264dsp_me_search_batch_dev( G.ctx, &G.g, se, sr, &prm, 1, G.d_blk, G.d_res, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, out, G.d_res, sizeof(*out), NULL ) );
+    G.calls[3]++;
+    return 0;
+}
+
+/* the 16x16 luma and 8x8 U / V samples of macroblock (mb_x, mb_y) of a prediction slot -> fdec (stride 32, U at +0 and
+ * V at +16 of the chroma rows, common/macroblock.c:242-265) */
+static void glue_fetch_mb( const uint8_t *slot, int mb_x, int mb_y, uint8_t *fdec_y, uint8_t *fdec_c )
+{
+    const x264dsp_geom_t *g = &G.g;
+    const size_t lo = (size_t)g->luma_origin + (size_t)mb_y * 16 * g->luma_stride + mb_x * 16;
+    const size_t co = (size_t)g->slot_chroma_off + g->chroma_origin + (size_t)mb_y * 8 * g->chroma_stride + mb_x * 16;
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.rows, slot + lo, (size_t)15 * g->luma_stride + 16, NULL ) );
+    for( int r = 0; r < 16; r++ )
+        memcpy( fdec_y + r * 32, G.rows + (size_t)r * g->luma_stride, 16 );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.rows, slot + co, (size_t)7 * g->chroma_stride + 16, NULL ) );
+    for( int r = 0; r < 8; r++ )
+        for( int x = 0; x < 8; x++ )
+        {
+            fdec_c[r * 32 + x] = G.rows[(size_t)r * g->chroma_stride + 2 * x];
+            fdec_c[r * 32 + 16 + x] = G.rows[(size_t)r * g->chroma_stride + 2 * x + 1];
+        }
+}
+
+/* ---- x264_mb_mc: the four 8x8 MVs of the macroblock -> prediction into fdec */
+static int glue_mbmc( void *hv, void *fref, int mb_x, int mb_y, const int16_t *mv8x8, uint8_t *fdec_y, uint8_t *fdec_c )
+{
+    const uint8_t *sr = glue_resident( fref );
+    if( !G.ctx || !sr )
+        return 1;
+    const size_t xy = (size_t)mb_y * G.g.mb_w + mb_x;
+    /* the frame kernel predicts every macroblock; only this one's vectors matter (the others stay zero) */
+    GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_mv4 + xy * 8, mv8x8, 16, NULL ) );
+    GLUE_CHECK( x264dsp_mc_frames_part_dev( G.ctx, &G.g, sr, 1, G.d_mv4, glue_pred(), NULL ) );
+    glue_fetch_mb( glue_pred(), mb_x, mb_y, fdec_y, fdec_c );
+    GLUE_CHECK( x264dsp_dev_zero( G.ctx, G.d_mv4 + xy * 8, 16, NULL ) );
+    G.calls[6]++;
+    return 0;
+}
+
+/* ---- x264_macroblock_probe_pskip: mc at the clipped pskip mv, then the "would anything be coded" test */
+static int glue_pskip( void *hv, void *fenc, void *fref, int mb_x, int mb_y, int mvx, int mvy, int qp, uint8_t *fdec_y,
+                       uint8_t *fdec_c, int *skip )
+{
+    const uint8_t *se = glue_resident( fenc ), *sr = glue_resident( fref );
+    if( !G.ctx || !se || !sr )
+        return 1;
+    const size_t xy = (size_t)mb_y * G.g.mb_w + mb_x;
+    const int16_t mv[2] = { (int16_t)mvx, (int16_t)mvy };
+    uint8_t s = 0;
+    GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_pmv + xy * 2, mv, 4, NULL ) );
+    GLUE_CHECK( x264dsp_mc_frame_dev( G.ctx, &G.g, sr, G.d_pmv, glue_pred(), NULL ) );
+    GLUE_CHECK( x264dsp_probe_pskip_frames_dev( G.ctx, &G.g, se, glue_pred(), 1, qp, G.d_skip, NULL ) );
+    glue_fetch_mb( glue_pred(), mb_x, mb_y, fdec_y, fdec_c );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, &s, G.d_skip + xy, 1, NULL ) );
+    GLUE_CHECK( x264dsp_dev_zero( G.ctx, G.d_pmv + xy * 2, 4, NULL ) );
+    *skip = s;
+    G.calls[5]++;
+    return 0;
+}
+
+/* ---- x264_macroblock_encode: one macroblock as a 16x16 "frame" -- source and prediction slots in the library's own
+ *      plane layout, levels / nnz / cbp back in the layout the door hands to the reference's entropy coder */
+static uint8_t *glue_mb_luma( uint8_t *slot )   { return slot + G.g1.luma_origin; }
+static uint8_t *glue_mb_chroma( uint8_t *slot ) { return slot + G.g1.slot_chroma_off + G.g1.chroma_origin; }
+
+static int glue_mbenc( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y, uint8_t *fdec_c, int qp,
+                       int kind, const uint8_t *i4_modes, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int *cbp )
+{
+    x264_t *h = hv;
+    glue_open( h );
+    const x264dsp_geom_t *g1 = &G.g1;
+    const int ls = g1->luma_stride, cs = g1->chroma_stride;
+    uint8_t *src = G.mb_stage, *prd = G.mb_stage + g1->slot_bytes;
+    const uint8_t k8 = (uint8_t)kind;
+    int16_t c16 = 0;
+    for( int r = 0; r < 16; r++ )
+    {
+        memcpy( glue_mb_luma( src ) + r * ls, fenc_y + r * 16, 16 );          /* FENC_STRIDE 16 */
+        memcpy( glue_mb_luma( prd ) + r * ls, fdec_y + r * 32, 16 );          /* FDEC_STRIDE 32 */
+    }
+    for( int r = 0; r < 8; r++ )
+        for( int x = 0; x < 8; x++ )
+        {
+            glue_mb_chroma( src )[r * cs + 2 * x] = fenc_c[r * 16 + x];       /* U at +0, V at +8 */
+            glue_mb_chroma( src )[r * cs + 2 * x + 1] = fenc_c[r * 16 + 8 + x];
+            glue_mb_chroma( prd )[r * cs + 2 * x] = fdec_c[r * 32 + x];       /* U at +0, V at +16 */
+            glue_mb_chroma( prd )[r * cs + 2 * x + 1] = fdec_c[r * 32 + 16 + x];
+        }
+    if( kind & 2 )
+    {
+        /* I4x4: the reconstructed neighbourhood fdec_buf holds around the macroblock goes into the slot's padding --
+         * the row above from column -1 to 19 and the column to the left */
+        memcpy( glue_mb_luma( prd ) - ls - 1, fdec_y - 33, 21 );
+        for( int r = 0; r < 16; r++ )
+            glue_mb_luma( prd )[r * ls - 1] = fdec_y[r * 32 - 1];
+        GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_modes, i4_modes, 16, NULL ) );
+    }
+    GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_mb_slots, G.mb_stage, 2 * (size_t)g1->slot_bytes, NULL ) );
+    GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_kind, &k8, 1, NULL ) );
+    GLUE_CHECK( x264dsp_residual_frames_typed_dev( G.ctx, g1, G.d_mb_slots, G.d_mb_slots + g1->slot_bytes, 1, qp, G.d_kind,
+                                                   G.d_modes, G.d_levels, G.d_luma_dc, G.d_nnz, G.d_cbp1, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, prd, G.d_mb_slots + g1->slot_bytes, g1->slot_bytes, NULL ) );
+    for( int r = 0; r < 16; r++ )
+        memcpy( fdec_y + r * 32, glue_mb_luma( prd ) + r * ls, 16 );
+    for( int r = 0; r < 8; r++ )
+        for( int x = 0; x < 8; x++ )
+        {
+            fdec_c[r * 32 + x] = glue_mb_chroma( prd )[r * cs + 2 * x];
+            fdec_c[r * 32 + 16 + x] = glue_mb_chroma( prd )[r * cs + 2 * x + 1];
+        }
+    GLUE_CHECK( x264dsp_d2h( G.ctx, levels, G.d_levels, X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t), NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, luma_dc, G.d_luma_dc, 16 * sizeof(int16_t), NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, nnz, G.d_nnz, X264DSP_RES_NNZ_PER_MB, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, &c16, G.d_cbp1, sizeof(c16), NULL ) );
+    *cbp = c16;
+    G.calls[4]++;
+    return 0;
+}
+
+void x264dsp_glue_install( void )
+{
+    xref_set_driver_hooks( glue_lowres, NULL, glue_cost );
+    xref_set_fdec_hook( glue_fdec );
+    xref_set_me_hook( glue_me );
+    xref_set_mbenc_hook( glue_mbenc );
+    xref_set_pskip_hook( glue_pskip );
+    xref_set_mbmc_hook( glue_mbmc );
+}
+
+void x264dsp_glue_uninstall( void )
+{
+    xref_set_driver_hooks( NULL, NULL, NULL );
+    xref_set_fdec_hook( NULL );
+    xref_set_me_hook( NULL );
+    xref_set_mbenc_hook( NULL );
+    xref_set_pskip_hook( NULL );
+    xref_set_mbmc_hook( NULL );
+}
+
+/* one JSON object: how often each door was served by the device, what the doors themselves counted
+ * ({entered, eligible, served} per door: eligible != served means a silent fallback), kernel launches */
+int x264dsp_glue_report( FILE *out )
+{
+    int hook[3], doors[12];
+    xref_driver_hook_calls( hook );
+    xref_door_stats_read( doors );
+    return fprintf( out, "{\"lowres\": %d, \"inloop_filter\": %d, \"deblocked_frames\": %d, \"lookahead_cost\": %d, "
+                    "\"me_search\": %d, \"macroblock_encode\": %d, \"probe_pskip\": %d, \"mb_mc\": %d, "
+                    "\"door_me\": [%d, %d, %d], \"door_mbenc\": [%d, %d, %d], \"door_pskip\": [%d, %d, %d], "
+                    "\"door_mbmc\": [%d, %d, %d], \"hook_calls\": [%d, %d, %d], \"kernel_launches\": %lld}\n",
+                    G.calls[0], G.calls[1], G.calls[7], G.calls[2], G.calls[3], G.calls[4], G.calls[5], G.calls[6],
+                    doors[0], doors[1], doors[2], doors[3], doors[4], doors[5], doors[6], doors[7], doors[8], doors[9],
+                    doors[10], doors[11], hook[0], hook[1], hook[2],
+                    G.ctx ? (long long)( x264dsp_launch_count( G.ctx ) - G.launches0 ) : 0LL );
+}

@@ -16,7 +16,7 @@ of its hot-path drivers served by libx264dsp_b200.so --
   two cases: DCT, quant, zig-zag, dequant, decimation, luma / chroma DC, IDCT; levels / nnz / cbp handed to the
   reference's CABAC writer)                     -> x264dsp_residual_frames_typed_dev
 
-through the doors of oracle/ref_shim/hooks.c (the glue INTEGRATION.md describes), and must emit the
+through the doors of glue/x264dsp_doors.c (the glue INTEGRATION.md describes; glue/x264dsp_glue.c is the same device side in C), and must emit the
 byte-identical bitstream.  Every plane the main encode searches in (half-pel planes of every
 reconstructed frame), every lowres MV used as an MV candidate and every frame cost that drives scenecut
 and rate control then comes from the CUDA path."""
@@ -311,7 +311,7 @@ def test_encoder_bitstream_identical_with_gpu_drivers(pkg, ctx, w, h, n, cut, me
             assert calls[2] == n - 1, f"lookahead cost hooked {calls[2]} times for {n} frames"
             assert ctx.launches - launches0 >= 2 * n, "the encode must have gone through the CUDA kernels"
             # per door {entered, eligible, served}: every eligible call must have been served by the device (a decline
-            # falls back to the reference's code silently inside hooks.c -- that must not happen), and the callbacks'
+            # falls back to the reference's code silently inside x264dsp_doors.c -- that must not happen), and the callbacks'
             # own counters must agree with the doors'
             st = {name: tuple(doors[3 * i: 3 * i + 3]) for i, name in enumerate(("me", "mbenc", "pskip", "mbmc"))}
             if mehook:
