@@ -877,6 +877,20 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(sums_host, sums_np), "host and device arms disagree"
+    # ---- copy-only probe: the same call with its kernels switched off -- same pinned buffers, same streams, same copy
+    # order on every rank at the same time -- i.e. what the host's DMA side alone allows at this rank count
+    ctx.debug_copies_only(True)
+    mv_keep, cost_keep, sum_keep = mvs_host.copy(), costs_host.copy(), sums_host.copy()
+    ctx.lookahead_clips_host(w, h, clips, clip_len, luma_host, mvs_host, costs_host, sums_host)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.lookahead_clips_host(w, h, clips, clip_len, luma_host, mvs_host, costs_host, sums_host)
+    torch.cuda.synchronize()
+    copy_s = time.perf_counter() - t0
+    ctx.debug_copies_only(False)
+    mvs_host[:], costs_host[:], sums_host[:] = mv_keep, cost_keep, sum_keep
+    del mv_keep, cost_keep, sum_keep
     clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
 
     # ---- single clip latency (exactly the 8-frame configuration), device resident
@@ -913,11 +927,12 @@ def main():
         rc_ms_big, _ = recon_measure(pkg, ctx, torch, g, w, h, 384, reps=2)
 
     # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3] + sec, dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3] + sec + [copy_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     me_dev_ms_max, me_e2e_s_max, rc_dev_ms_max, rc_e2e_s_max = (float(x) for x in t[2:6])
+    copy_ms = float(t[6])
 
     if rank == 0:
         frames_total = world * n * args.steps
@@ -949,7 +964,16 @@ def main():
             "config": workload_config(args, n),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(n * w * h),
                     "d2h_bytes_per_step": int(mvs_host.nbytes + costs_host.nbytes + sums_host.nbytes),
-                    "ms_per_step": e2e_ms / args.steps, "api": "x264dsp_lookahead_clips_host (pinned host buffers)"},
+                    "ms_per_step": e2e_ms / args.steps, "api": "x264dsp_lookahead_clips_host (pinned host buffers)",
+                    # the same call with its kernels switched off (x264dsp_debug_copies_only): same pinned buffers, same
+                    # 16 streams, same copy order, all ranks at once -- the DMA-only time of a step at this rank count
+                    "copy_only": {"ms_per_step": copy_ms / args.steps,
+                                  "h2d_gbs_per_rank": n * w * h / (copy_ms / args.steps / 1e3) / 1e9,
+                                  "h2d_gbs_all_ranks": world * n * w * h / (copy_ms / args.steps / 1e3) / 1e9,
+                                  "frames_per_s_if_copies_were_all": world * n / (copy_ms / args.steps / 1e3)},
+                    "copy_share_of_step": copy_ms / e2e_ms,
+                    "bound": ("host DMA: the copies alone take %.0f %% of the step (kernels are hidden behind them)"
+                              % (100 * copy_ms / e2e_ms)) if copy_ms >= 0.85 * e2e_ms else "kernels + copies"},
             "gpu_launches": int(launches),
             "host_affinity": numa,
             "clocks": clocks,

@@ -240,6 +240,9 @@ int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int height, int
  * instructions, best once a launch holds a few dozen pairs).  mode 0 = choose by batch size (default),
  * 1 = one row per warp, 2 = four rows per warp, 3 = eight rows per warp. */
 int x264dsp_lookahead_select_kernel( x264dsp_ctx_t *ctx, int mode );
+/* measurement aid: on != 0 makes x264dsp_lookahead_clips_host issue its copies (same buffers, streams and order) but none
+ * of its kernels -- what the host<->device DMA alone costs; results are meaningless while it is on (bench.py e2e.copy_only) */
+int x264dsp_debug_copies_only( x264dsp_ctx_t *ctx, int on );
 /* debug aid: clock64() cycles the inter kernel's warps spent per phase, summed over all warps since the
  * last reset: out[0..9] = waiting on the row below, block setup, zero-mv SATD probe, predictor
  * candidates, diamond search, sub-pel refine + SATD, publish/accounting, blocks processed, first wait

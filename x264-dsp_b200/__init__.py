@@ -303,6 +303,10 @@ class Context:
             _dp(mvs), _dp(costs), _dp(sums), _dp(row_satds), C.c_void_p(stream) if stream else None),
             "x264dsp_lookahead_frame_cost_dev")
 
+    def debug_copies_only(self, on):
+        """measurement aid: lookahead_clips_host issues its copies but none of its kernels"""
+        check(lib().x264dsp_debug_copies_only(self._h, int(bool(on))), "x264dsp_debug_copies_only")
+
     def lookahead_select_kernel(self, mode):
         """0 = by batch size, 1 = one block row per warp, 2 = four rows per warp, 3 = eight rows per warp"""
         check(lib().x264dsp_lookahead_select_kernel(self._h, int(mode)), "x264dsp_lookahead_select_kernel")

@@ -35,6 +35,7 @@ struct x264dsp_ctx
     uint32_t la_epoch;
     unsigned long long *la_timing; // phase-cycle counters of the inter kernel (debug aid, normally NULL)
     int la_kernel;                 // x264dsp_lookahead_select_kernel: 0 auto, 1 warp-per-row, 2 quad-row
+    int copies_only;               // x264dsp_debug_copies_only: the host entry points skip their kernels
 
     // host-API staging (x264dsp_lookahead_clip_host)
     uint8_t *stage_host;  size_t stage_host_cap;     // pinned

@@ -1716,12 +1716,12 @@ extern "C" int x264dsp_lookahead_clips_host( x264dsp_ctx_t *ctx, int width, int 
         }
         XD_GROUP_CHECK( cudaMemcpyAsync( ctx->stage_dev + (size_t)f0 * pic, src, pic * nf, cudaMemcpyHostToDevice, s ) );
         uint8_t *slots = ctx->clip_slots + (size_t)f0 * g.slot_bytes;
-        if( ( rc = xd_frame_lowres_from_luma( ctx, &g, ctx->stage_dev + (size_t)f0 * pic, slots, nf, s ) ) )
+        if( !ctx->copies_only && ( rc = xd_frame_lowres_from_luma( ctx, &g, ctx->stage_dev + (size_t)f0 * pic, slots, nf, s ) ) )
             break;
         // every clip of the group contributes clip_len-1 inter pairs, in frame order
         const int inter0 = c0 * ( clip_len - 1 ), ninter = ( c1 - c0 ) * ( clip_len - 1 );
-        if( ( rc = xd_la_launch( ctx, &g, ctx->clip_slots, f0, nf, b_dev, p0_dev, wi_dev, list_dev + inter0, ninter, gi,
-                                 d_mvs, d_costs, d_sums, NULL, s ) ) )
+        if( !ctx->copies_only && ( rc = xd_la_launch( ctx, &g, ctx->clip_slots, f0, nf, b_dev, p0_dev, wi_dev, list_dev + inter0,
+                                                      ninter, gi, d_mvs, d_costs, d_sums, NULL, s ) ) )
             break;
         uint8_t *o_mv = pinned_out ? (uint8_t *)mvs : h_out;
         uint8_t *o_cost = pinned_out ? (uint8_t *)costs : h_out + mv_bytes;
@@ -1755,6 +1755,17 @@ extern "C" int x264dsp_lookahead_clip_host( x264dsp_ctx_t *ctx, int width, int h
                                              const uint8_t *luma, int16_t *mvs, int32_t *costs, int32_t *sums )
 {
     return x264dsp_lookahead_clips_host( ctx, width, height, 1, n_frames, luma, mvs, costs, sums );
+}
+
+// Measurement aid (bench.py's copy-only probe): with on != 0 x264dsp_lookahead_clips_host issues exactly the copies it
+// always issues -- same buffers, same streams, same order -- and none of its kernels, so that the time of the call is
+// what the host-to-device / device-to-host DMA alone costs on this box.  The outputs are then meaningless.
+extern "C" int x264dsp_debug_copies_only( x264dsp_ctx_t *ctx, int on )
+{
+    if( !ctx )
+        return X264DSP_E_ARG;
+    ctx->copies_only = on != 0;
+    return 0;
 }
 
 // mode 0 = pick by batch size, 1 = warp per block row, 2 = four block rows per warp, 3 = eight (identical results)
