@@ -123,8 +123,16 @@ void x264_frame_expand_border( x264_t *h, x264_frame_t *frame, int mb_y )
         xref_orig_frame_expand_border( h, frame, mb_y );
 }
 
+/* observer: called when the last macroblock row of a frame has been reconstructed, before anything else happens to it
+ * (the capture point of the P-slice analysis pin, tests/test_oracle_pframe.py); changes nothing */
+typedef void (*xref_observe_cb)( void *h, void *frame );
+xref_observe_cb xref_hook_observe = NULL;
+void xref_set_observer( xref_observe_cb cb ) { xref_hook_observe = cb; }
+
 void x264_frame_expand_border_filtered( x264_t *h, x264_frame_t *frame, int mb_y, int b_end )
 {
+    if( b_end && xref_hook_observe )
+        xref_hook_observe( h, frame );
     if( xref_hook_fdec )
     {
         if( b_end )

@@ -435,6 +435,45 @@ int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const ui
 int x264dsp_mc_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slots,
                                 int n_frames, const int16_t *mv8x8, uint8_t *pred_slots, void *stream );
 
+/* ------------------------------------------------------------------ P-slice analysis + coding (8(f) N2)
+ * x264_macroblock_analyse for a P slice (encoder/analyse.c:1059-1232: x264_mb_analyse_init 327-420, the fast P_SKIP
+ * probe, x264_mb_analyse_inter_p16x16 787-860 with its early P_SKIP exit, x264_me_refine_qpel) followed by
+ * x264_macroblock_encode (encoder/macroblock.c:310-485: x264_mb_mc, residual coding, the forced-P_SKIP rule) for EVERY
+ * macroblock of a frame, with the reference's own data flow between macroblocks: the MV prediction, the P_SKIP vector,
+ * the 16x16 search's candidate list and the fast-skip condition of a macroblock read the FINAL types and vectors of its
+ * left, top, top-left and top-right neighbours, so the frame is a wavefront (row y may work on column x once row y-1 has
+ * finished column x+1).  One reference frame, analyse.inter == 0 (P16x16 only: the reference's default; its P-slice
+ * analysis has no intra candidates -- analyse.c:1206-1210 is compiled out), CABAC cbp packing.
+ *
+ *   fenc_slots   n_frames source frames (luma N + NV12 chroma)
+ *   fref_slots   n_frames reference frames (reconstructed, border-expanded, with their H / V / HV planes)
+ *   recon_slots  n_frames output slots: luma plane N and chroma receive the reconstruction (p_fdec)
+ *   lowres_mv    [frame][mb][2] the lookahead's vectors of the pair (fenc->lowres_mvs[0][0]) or NULL
+ *   l0_mv16      [frame][mb][2] the reference frame's own 16x16 vectors (its mvr output) for the temporal candidates,
+ *                scaled by params->mvc_scale = (curpoc - refpoc) * inv_ref_poc; NULL: reference frame was intra
+ * outputs, [frame][mb]...:
+ *   mb_type      X264DSP_MB_P_L0 / X264DSP_MB_P_SKIP (the reference's enum values, common/macroblock.h:41-50)
+ *   mv           [2] the macroblock's final vector (h->mb.cache.mv: the refined 16x16 vector, or the P_SKIP vector)
+ *   mvr          [2] h->mb.mvr[0][0] = fdec->mv16x16: the 16x16 search result as later macroblocks and the next frame
+ *                see it (zero for a macroblock skipped by the fast probe)
+ *   levels / nnz / cbp  as x264dsp_residual_frames_dev (all zero for P_SKIP)
+ * n_frames independent frames run as one launch (their wavefronts interleave); frames of one sequence depend on each
+ * other through the reference frame and are launched one after the other. */
+enum { X264DSP_MB_P_L0 = 4, X264DSP_MB_P_8x8 = 5, X264DSP_MB_P_SKIP = 6 };
+typedef struct x264dsp_pframe_params
+{
+    int32_t me_method, subpel_refine, me_range;   /* as x264dsp_me_params_t */
+    int32_t qp;                                    /* slice QP (h->sh.i_qp) */
+    int32_t mv_range;                              /* h->param.analyse.i_mv_range, full-pel */
+    int32_t fast_pskip;                            /* h->param.analyse.b_fast_pskip */
+    int32_t mvc_scale;                             /* temporal candidates: (curpoc - refpoc) * inv_ref_poc */
+} x264dsp_pframe_params_t;
+int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
+                          const uint8_t *fref_slots, uint8_t *recon_slots, int n_frames,
+                          const x264dsp_pframe_params_t *params, const int16_t *lowres_mv, const int16_t *l0_mv16,
+                          int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *levels, uint8_t *nnz, int16_t *cbp,
+                          void *stream );
+
 /* ------------------------------------------------------------------ deblock
  * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's
  * slice-QP rule.  mb_type / partition / cbp: per-MB; bs: [mb][2][8][4] boundary strengths.

@@ -46,6 +46,79 @@ void *xref_open( int width, int height, int me_method, int subme, int me_range, 
     return x264_encoder_open( &param );
 }
 
+/* the same with the in-loop deblocking filter switched on or off (a frame's reconstruction is then final when its last
+ * macroblock row is coded, which is what the P-slice analysis pin compares) */
+void *xref_open_ex( int width, int height, int me_method, int subme, int me_range, int qp, int psub16x16, int deblock )
+{
+    x264_param_t param;
+    x264_param_default( &param );
+    param.i_width = width;
+    param.i_height = height;
+    param.i_csp = X264_CSP_I420;
+    param.pf_log = xref_quiet_log;
+    param.i_log_level = X264_LOG_NONE;
+    param.analyse.i_me_method = me_method;
+    param.analyse.i_subpel_refine = subme;
+    param.analyse.i_me_range = me_range;
+    if( psub16x16 )
+        param.analyse.inter |= X264_ANALYSE_PSUB16x16;
+    param.rc.i_rc_method = X264_RC_CQP;
+    param.rc.i_qp_constant = qp;
+    param.b_deblocking_filter = deblock;
+    return x264_encoder_open( &param );
+}
+
+/* What the encoder holds at the end of a frame's macroblock loop (call from the observer of x264dsp_doors.c): the inputs
+ * x264_macroblock_analyse / x264_macroblock_encode worked from and the decisions they left behind. */
+typedef struct
+{
+    int32_t slice_type, qp, poc, ref_poc, inv_ref_poc, ref_is_inter, mv_range, b4_stride, have_lowres_mv, mb_count;
+    int32_t fast_pskip, i_frame, pad0;
+    void *fenc, *fref, *fdec;
+    const int8_t *mb_type;          /* h->mb.type */
+    const int16_t *mvr;             /* h->mb.mvr[0][0] = fdec->mv16x16 */
+    const int16_t *cbp;             /* h->mb.cbp */
+    const int16_t *mv4x4;           /* fdec->mv[0], one per 4x4, row stride b4_stride */
+    const int16_t *lowres_mv;       /* fenc->lowres_mvs[0][0] */
+    const int16_t *l0_mv16;         /* fref->mv16x16 */
+    const uint8_t *partition;       /* h->mb.partition */
+    const uint8_t *nnz;             /* h->mb.non_zero_count, 48 per macroblock */
+} xref_frame_capture_t;
+
+void xref_capture_frame( void *hv, xref_frame_capture_t *o )
+{
+    x264_t *h = hv;
+    x264_frame_t *fref = h->i_ref[0] > 0 ? h->fref[0][0] : NULL;
+    memset( o, 0, sizeof(*o) );
+    o->slice_type = h->sh.i_type;
+    o->qp = h->sh.i_qp;
+    o->poc = h->fdec->i_poc;
+    o->mv_range = h->param.analyse.i_mv_range;
+    o->b4_stride = h->mb.i_b4_stride;
+    o->mb_count = h->mb.i_mb_count;
+    o->fast_pskip = h->param.analyse.b_fast_pskip;
+    o->i_frame = h->fenc->i_frame;
+    o->fenc = h->fenc;
+    o->fdec = h->fdec;
+    o->fref = fref;
+    o->mb_type = h->mb.type;
+    o->mvr = &h->mb.mvr[0][0][0][0];
+    o->cbp = h->mb.cbp;
+    o->mv4x4 = &h->fdec->mv[0][0][0];
+    o->partition = h->mb.partition;
+    o->nnz = &h->mb.non_zero_count[0][0];
+    o->lowres_mv = &h->fenc->lowres_mvs[0][0][0][0];
+    if( fref )
+    {
+        o->ref_poc = fref->i_poc;
+        o->inv_ref_poc = fref->inv_ref_poc[0];
+        o->ref_is_inter = fref->i_ref[0] > 0;
+        o->l0_mv16 = &fref->mv16x16[0][0];
+        o->have_lowres_mv = h->frames.b_have_lowres && h->fenc->i_frame - fref->i_frame - 1 <= h->param.i_bframe
+                            && h->fenc->lowres_mvs[0][h->fenc->i_frame - fref->i_frame - 1][0][0] != 0x7fff;
+    }
+}
+
 void xref_close( void *hv )
 {
     /* x264_encoder_close prints stats and frees; leaking a test encoder is harmless
