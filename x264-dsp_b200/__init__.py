@@ -48,6 +48,14 @@ class MeParams(C.Structure):
                 ("qp", C.c_int32), ("refine_qpel", C.c_int32)]
 
 
+class PFrameParams(C.Structure):
+    """x264dsp_pframe_params_t"""
+    _fields_ = [("me_method", C.c_int32), ("subpel_refine", C.c_int32), ("me_range", C.c_int32), ("qp", C.c_int32),
+                ("mv_range", C.c_int32), ("fast_pskip", C.c_int32), ("mvc_scale", C.c_int32)]
+
+
+MB_P_L0, MB_P_8x8, MB_P_SKIP = 4, 5, 6
+
 ME_BLOCK_DTYPE = np.dtype([("i_pixel", "<i4"), ("bx", "<i4"), ("by", "<i4"), ("mvp", "<i2", (2,)),
                            ("i_mvc", "<i4"), ("mvc", "<i2", (16, 2)),
                            ("mv_min_fpel", "<i4", (2,)), ("mv_max_fpel", "<i4", (2,)),
@@ -403,6 +411,15 @@ class Context:
         """one MV per 8x8 block: int16[n][mb][4][2]"""
         check(lib().x264dsp_mc_frames_part_dev(self._h, C.byref(g), _dp(fref_slots), int(n_frames), _dp(mv8x8_dev),
                                                _dp(pred_slots), None), "x264dsp_mc_frames_part_dev")
+
+    def p_frames(self, g, fenc_slots, fref_slots, recon_slots, n_frames, prm, lowres_mv, l0_mv16, mb_type, mv, mvr,
+                 levels, nnz, cbp):
+        """x264_macroblock_analyse + x264_macroblock_encode for every macroblock of n_frames independent P frames
+        (x264dsp_p_frames_dev); lowres_mv / l0_mv16 may be None"""
+        check(lib().x264dsp_p_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(fref_slots), _dp(recon_slots),
+                                         int(n_frames), C.byref(prm), _dp(lowres_mv) if lowres_mv is not None else None,
+                                         _dp(l0_mv16) if l0_mv16 is not None else None, _dp(mb_type), _dp(mv), _dp(mvr),
+                                         _dp(levels), _dp(nnz), _dp(cbp), None), "x264dsp_p_frames_dev")
 
     def residual_frames(self, g, fenc_slots, pred_slots, n_frames, qp, levels, nnz, cbp):
         check(lib().x264dsp_residual_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),

@@ -1,0 +1,347 @@
+// pframe.cu -- the P-slice macroblock loop as a wavefront: analysis + coding of every macroblock of a P frame on the device
+// (SURVEY 8(f) N2), sm_100a.
+//
+// Reference: x264_macroblock_analyse for P slices (encoder/analyse.c:1059-1232) = x264_mb_analyse_init (327-420: MV limits),
+// the neighbour-derived predictions of x264_macroblock_cache_load (x264_mb_predict_mv_pskip, common/mvpred.c:139-155), the
+// fast P_SKIP probe (analyse.c:1093-1105), x264_mb_analyse_inter_p16x16 (787-860: x264_mb_predict_mv_16x16,
+// x264_mb_predict_mv_ref16x16, x264_me_search_ref, the early P_SKIP exit), x264_me_refine_qpel (1187-1191); then
+// x264_macroblock_encode (encoder/macroblock.c:310-485): x264_mb_mc, the residual coder, the forced-P_SKIP rule.
+// One reference frame, analyse.inter == 0 (P16x16 only, the reference's default); the reference's P-slice analysis has no
+// intra candidates (analyse.c:1206-1210 is compiled out), so every macroblock ends up P_L0 16x16 or P_SKIP.
+//
+// Mapping.  What one macroblock needs from others is small -- type, final vector and 16x16 search vector of its left, top,
+// top-left and top-right neighbours -- but it needs them FINAL, including the outcome of the residual coder (a macroblock
+// whose residual quantises to nothing at the P_SKIP vector becomes P_SKIP, and a skipped neighbour switches the fast probe
+// on).  So the whole per-macroblock chain runs inside the wavefront: ONE WARP WALKS ONE MACROBLOCK ROW left to right and
+// does, per macroblock, prediction -> [probe] -> search -> refine -> motion compensation -> residual coding with the same
+// warp-level device routines the frame kernels use (me_warp.cuh, residual_warp.cuh, mvpred.cuh); the left neighbour stays
+// in registers, the three upper neighbours are read after an acquire on the progress counter of the row above (row y may
+// start macroblock x once row y-1 has published macroblock x+1).  Rows are handed out through a ticket, frame-interleaved
+// and top rows first, so the row a warp waits for always holds a smaller ticket (no co-residency assumption).  One frame
+// alone is latency bound (mb_w + 2 mb_h macroblock times); throughput comes from many independent frames (closed GOPs /
+// streams) per launch, exactly as for the lookahead and the deblocking wavefronts.
+#include "me_warp.cuh"
+#include "residual_warp.cuh"
+#include "mvpred.cuh"
+
+#define PF_WARPS 2
+
+int xd_me_params_ok( const x264dsp_me_params_t *p );   // me.cu
+
+struct xd_pf_args
+{
+    x264dsp_geom_t g;
+    const uint8_t *fenc, *fref;
+    uint8_t *recon;
+    int n_frames;
+    x264dsp_pframe_params_t P;
+    x264dsp_me_params_t MP;
+    xd_res_tables T;
+    const uint16_t *cost_mv;
+    int lambda;
+    const int16_t *lowres_mv, *l0_mv16;
+    int8_t *mb_type;
+    int16_t *mv, *mvr, *levels;
+    uint8_t *nnz;
+    int16_t *cbp;
+    int32_t *progress, *ticket;
+};
+
+__device__ __forceinline__ int xd_pf_ld_acquire( const int32_t *p )
+{
+    int v;
+    asm volatile( "ld.acquire.gpu.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+    return v;
+}
+__device__ __forceinline__ int xd_pf_ld_relaxed( const int32_t *p )
+{
+    int v;
+    asm volatile( "ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+    return v;
+}
+__device__ __forceinline__ void xd_pf_st_release( int32_t *p, int v )
+{
+    asm volatile( "st.release.gpu.global.s32 [%0], %1;" :: "l"( p ), "r"( v ) : "memory" );
+}
+
+// x264_macroblock_probe_pskip: the prediction at the (clipped) P_SKIP vector goes into the reconstruction slot -- where it
+// stays if the macroblock is skipped -- then the "would anything be coded" test (residual_warp.cuh, PROBE)
+__device__ __forceinline__ int xd_pf_probe( const xd_pf_args &A, const uint8_t *fenc, const uint8_t *fref, uint8_t *recon, int mb,
+                                            uint32_t pskip, int lane )
+{
+    const int16_t mvs[2] = { (int16_t)( pskip & 0xFFFF ), (int16_t)( pskip >> 16 ) };
+    xd_mc_mb<1>( A.g, fref, mvs, recon, mb, lane );
+    xd_mc_mb<1>( A.g, fref, mvs, recon, mb, lane + 32 );
+    __syncwarp();
+    const int ok = xd_residual_mb<false, true>( A.g, fenc, recon, A.T, nullptr, nullptr, nullptr, nullptr, nullptr, mb, lane );
+    __syncwarp();
+    return ok;
+}
+
+__global__ void __launch_bounds__( PF_WARPS * 32 )
+xd_pframe_kernel( xd_pf_args A )
+{
+    __shared__ x264dsp_me_block_t s_blk[PF_WARPS];
+    const x264dsp_geom_t &g = A.g;
+    const int lane = threadIdx.x & 31;
+    x264dsp_me_block_t *blk = &s_blk[threadIdx.x >> 5];
+    const int W = g.mb_w, H = g.mb_h;
+    const int total = A.n_frames * H;
+    const int fmv_range = A.P.mv_range << 2, border = 6;
+    const int subme = A.P.subpel_refine;
+    for( ;; )
+    {
+        int t = 0;
+        if( lane == 0 )
+            t = atomicAdd( A.ticket, 1 );
+        t = __shfl_sync( 0xffffffffu, t, 0 );
+        if( t >= total )
+            return;
+        const int mb_y = t / A.n_frames, f = t - mb_y * A.n_frames;
+        const uint8_t *fenc = A.fenc + (size_t)f * g.slot_bytes, *fref = A.fref + (size_t)f * g.slot_bytes;
+        uint8_t *recon = A.recon + (size_t)f * g.slot_bytes;
+        const size_t mb0 = (size_t)f * g.mb_count;
+        int8_t *types = A.mb_type + mb0;
+        uint32_t *mvs = (uint32_t *)A.mv + mb0, *mvrs = (uint32_t *)A.mvr + mb0;
+        int16_t *levels = A.levels + mb0 * X264DSP_RES_LEVELS_PER_MB;
+        uint8_t *nnz = A.nnz + mb0 * X264DSP_RES_NNZ_PER_MB;
+        int16_t *cbp = A.cbp + mb0;
+        const uint32_t *lowres = A.lowres_mv ? (const uint32_t *)A.lowres_mv + mb0 : nullptr;
+        const uint32_t *l0 = A.l0_mv16 ? (const uint32_t *)A.l0_mv16 + mb0 : nullptr;
+        const bool have_lowres = lowres && ( __ldg( lowres ) & 0xFFFFu ) != 0x7fffu;
+        int32_t *mine = A.progress + (size_t)f * H + mb_y;
+        const int32_t *above = mine - 1;
+
+        // x264_mb_analyse_init (analyse.c:373-397): the vertical limits are set at the start of a row
+        const int min_y = ( -( mb_y << 4 ) - 24 ) << 2, max_y = ( ( ( H - mb_y - 1 ) << 4 ) + 24 ) << 2;
+        const int smin_y = xd_clip3( min_y, -fmv_range, fmv_range ), smax_y = xd_clip3( max_y, -fmv_range, fmv_range - 1 );
+
+        int left_type = -1;
+        uint32_t left_mv = 0, left_mvr = 0;
+        int seen = 0;
+        for( int mb_x = 0; mb_x < W; mb_x++ )
+        {
+            const int xy = mb_y * W + mb_x;
+            // ---- the row above must have published macroblock x+1
+            if( mb_y > 0 )
+            {
+                const int need = min( mb_x + 2, W );
+                if( seen < need )
+                {
+                    if( lane == 0 )
+                    {
+                        unsigned ns = 40;
+                        while( xd_pf_ld_relaxed( above ) < need )
+                        {
+                            __nanosleep( ns );
+                            if( ns < 1000 )
+                                ns += 40;
+                        }
+                    }
+                    __syncwarp();
+                    seen = xd_pf_ld_acquire( above );
+                }
+            }
+            // ---- neighbours A (left), B (top), C (top-right), D (top-left): reference 0 inside the frame, -2 outside
+            x264dsp_mv_neighbours_t nb;
+            int ntype[4] = { left_type, -1, -1, -1 };
+            uint32_t nmv[4] = { left_mv, 0, 0, 0 }, nmvr[4] = { left_mvr, 0, 0, 0 };
+            bool have[4] = { mb_x > 0, mb_y > 0, mb_y > 0 && mb_x < W - 1, mb_x > 0 && mb_y > 0 };
+            const int nxy[4] = { xy - 1, xy - W, xy - W + 1, xy - W - 1 };
+#pragma unroll
+            for( int k = 1; k < 4; k++ )
+                if( have[k] )
+                {
+                    ntype[k] = __ldcg( types + nxy[k] );
+                    nmv[k] = __ldcg( mvs + nxy[k] );
+                    nmvr[k] = __ldcg( mvrs + nxy[k] );
+                }
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                nb.ref[k] = have[k] ? 0 : -2;
+                nb.mv[k][0] = have[k] ? (int16_t)( nmv[k] & 0xFFFF ) : 0;
+                nb.mv[k][1] = have[k] ? (int16_t)( nmv[k] >> 16 ) : 0;
+            }
+            const uint32_t pskip = xd_predict_mv_pskip( nb );
+            const int pskip_x = (int16_t)( pskip & 0xFFFF ), pskip_y = (int16_t)( pskip >> 16 );
+
+            const int min_x = ( -( mb_x << 4 ) - 24 ) << 2, max_x = ( ( ( W - mb_x - 1 ) << 4 ) + 24 ) << 2;
+            const int smin_x = xd_clip3( min_x, -fmv_range, fmv_range - 1 ), smax_x = xd_clip3( max_x, -fmv_range, fmv_range - 1 );
+
+            int type = X264DSP_MB_P_L0, out_cbp = 0;
+            uint32_t out_mv = 0, out_mvr = 0;
+            bool done = false;
+            // ---- fast P_SKIP detection (analyse.c:1093-1105)
+            if( A.P.fast_pskip && subme < 3
+                && ( ntype[0] == X264DSP_MB_P_SKIP || ntype[1] == X264DSP_MB_P_SKIP || ntype[2] == X264DSP_MB_P_SKIP
+                     || ntype[3] == X264DSP_MB_P_SKIP ) )
+            {
+                if( xd_pf_probe( A, fenc, fref, recon, xy, pskip, lane ) )
+                {
+                    type = X264DSP_MB_P_SKIP;                  // analyse.c:1109-1117: later macroblocks see a zero 16x16 vector
+                    out_mv = pskip;
+                    out_mvr = 0;
+                    done = true;
+                }
+            }
+            if( !done )
+            {
+                // ---- x264_mb_analyse_inter_p16x16: MVP, candidate list (mvpred.c:167-219), search
+                const uint32_t mvp = xd_predict_mv_16x16( nb, 0 );
+                if( lane == 0 )
+                {
+                    int n = 0;
+                    if( have_lowres )
+                    {
+                        const uint32_t m = __ldg( lowres + xy );
+                        blk->mvc[n][0] = (int16_t)( (int16_t)( m & 0xFFFF ) * 2 );
+                        blk->mvc[n][1] = (int16_t)( (int16_t)( m >> 16 ) * 2 );
+                        n++;
+                    }
+                    const int order[4] = { 0, 1, 3, 2 };                          // left, top, top-left, top-right
+#pragma unroll
+                    for( int k = 0; k < 4; k++, n++ )
+                    {
+                        const uint32_t m = have[order[k]] ? nmvr[order[k]] : 0u;
+                        blk->mvc[n][0] = (int16_t)( m & 0xFFFF );
+                        blk->mvc[n][1] = (int16_t)( m >> 16 );
+                    }
+                    if( l0 )
+                    {
+                        const int tq[3] = { xy, mb_x < W - 1 ? xy + 1 : -1, mb_y < H - 1 ? xy + W : -1 };
+#pragma unroll
+                        for( int k = 0; k < 3; k++ )
+                            if( tq[k] >= 0 )
+                            {
+                                const uint32_t m = __ldg( l0 + tq[k] );
+                                blk->mvc[n][0] = (int16_t)( ( (int16_t)( m & 0xFFFF ) * A.P.mvc_scale + 128 ) >> 8 );
+                                blk->mvc[n][1] = (int16_t)( ( (int16_t)( m >> 16 ) * A.P.mvc_scale + 128 ) >> 8 );
+                                n++;
+                            }
+                    }
+                    blk->i_pixel = X264DSP_PIXEL_16x16;
+                    blk->bx = mb_x << 4;
+                    blk->by = mb_y << 4;
+                    blk->mvp[0] = (int16_t)( mvp & 0xFFFF );
+                    blk->mvp[1] = (int16_t)( mvp >> 16 );
+                    blk->i_mvc = n;
+                    blk->mv_min_spel[0] = smin_x; blk->mv_max_spel[0] = smax_x;
+                    blk->mv_min_spel[1] = smin_y; blk->mv_max_spel[1] = smax_y;
+                    blk->mv_min_fpel[0] = ( smin_x >> 2 ) + border; blk->mv_max_fpel[0] = ( smax_x >> 2 ) - border;
+                    blk->mv_min_fpel[1] = ( smin_y >> 2 ) + border; blk->mv_max_fpel[1] = ( smax_y >> 2 ) - border;
+                }
+                __syncwarp();
+                xd_me_state R;
+                R.mvx = R.mvy = R.cost = R.cost_mv = 0;
+                xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
+                out_mvr = xd_pack_mv( R.mvx, R.mvy );                                  // analyse.c:825
+                // ---- early termination (analyse.c:839-849)
+                if( A.P.fast_pskip && subme >= 3 && R.cost - R.cost_mv < 300 * A.lambda
+                    && abs( R.mvx - pskip_x ) + abs( R.mvy - pskip_y ) <= 1
+                    && xd_pf_probe( A, fenc, fref, recon, xy, pskip, lane ) )
+                {
+                    type = X264DSP_MB_P_SKIP;
+                    out_mv = pskip;
+                    done = true;
+                }
+                else
+                {
+                    // ---- x264_me_refine_qpel (analyse.c:1187-1191; one reference: i_ref_cost = 0)
+                    xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
+                    out_mv = xd_pack_mv( R.mvx, R.mvy );
+                }
+                __syncwarp();                                   // the block description is free for the next macroblock
+            }
+            if( !done )
+            {
+                // ---- x264_macroblock_encode, inter branch: x264_mb_mc, residual, forced P_SKIP (macroblock.c:379-485)
+                const int16_t v[2] = { (int16_t)( out_mv & 0xFFFF ), (int16_t)( out_mv >> 16 ) };
+                xd_mc_mb<1>( g, fref, v, recon, xy, lane );
+                xd_mc_mb<1>( g, fref, v, recon, xy, lane + 32 );
+                __syncwarp();
+                out_cbp = xd_residual_mb<false, false>( g, fenc, recon, A.T, levels, nnz, cbp, nullptr, nullptr, xy, lane );
+                if( !( out_cbp & 0x3f ) && out_mv == pskip )
+                    type = X264DSP_MB_P_SKIP;
+            }
+            // ---- publish
+            if( lane == 0 )
+            {
+                types[xy] = (int8_t)type;
+                mvs[xy] = out_mv;
+                mvrs[xy] = out_mvr;
+                if( done )
+                    cbp[xy] = 0;
+            }
+            __syncwarp();
+            if( lane == 0 )
+                xd_pf_st_release( mine, mb_x + 1 );
+            left_type = type;
+            left_mv = out_mv;
+            left_mvr = out_mvr;
+        }
+    }
+}
+
+extern "C" int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
+                                     const uint8_t *fref_slots, uint8_t *recon_slots, int n_frames,
+                                     const x264dsp_pframe_params_t *params, const int16_t *lowres_mv, const int16_t *l0_mv16,
+                                     int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *levels, uint8_t *nnz, int16_t *cbp,
+                                     void *stream )
+{
+    if( !ctx || !g || !fenc_slots || !fref_slots || !recon_slots || !params || !mb_type || !mv || !mvr || !levels || !nnz
+        || !cbp || n_frames <= 0 || n_frames > 65535 )
+        return X264DSP_E_ARG;
+    x264dsp_me_params_t mp = { params->me_method, params->subpel_refine, params->me_range, params->qp, 0 };
+    if( !xd_me_params_ok( &mp ) || params->mv_range < 1 )
+        return X264DSP_E_ARG;
+    cudaStream_t s = xd_stream( ctx, stream );
+    xd_pf_args A;
+    memset( &A, 0, sizeof( A ) );
+    A.g = *g;
+    A.fenc = fenc_slots;
+    A.fref = fref_slots;
+    A.recon = recon_slots;
+    A.n_frames = n_frames;
+    A.P = *params;
+    A.MP = mp;
+    xd_residual_tables( params->qp, &A.T );
+    A.cost_mv = ctx->cost_mv_dev[params->qp] + 4096;
+    A.lambda = x264dsp_lambda( params->qp );
+    A.lowres_mv = lowres_mv;
+    A.l0_mv16 = l0_mv16;
+    A.mb_type = mb_type;
+    A.mv = mv;
+    A.mvr = mvr;
+    A.levels = levels;
+    A.nnz = nnz;
+    A.cbp = cbp;
+    // progress counters (one per macroblock row of every frame) + the ticket: the deblocking wavefront's scratch
+    const size_t rows = (size_t)n_frames * g->mb_h, need = ( rows + 1 ) * sizeof( int32_t );
+    if( ctx->db_progress_cap < need )
+        XD_CHECK( cudaDeviceSynchronize() );
+    int rc = xd_reserve_dev( (void **)&ctx->db_progress, &ctx->db_progress_cap, need );
+    if( rc )
+        return rc;
+    if( ( rc = xd_scratch_acquire( ctx, XD_SCRATCH_DEBLOCK, s ) ) )
+        return rc;
+    XD_CHECK( cudaMemsetAsync( ctx->db_progress, 0, need, s ) );
+    A.progress = ctx->db_progress;
+    A.ticket = ctx->db_progress + rows;
+    // skipped macroblocks code nothing
+    const size_t nmb = (size_t)n_frames * g->mb_count;
+    XD_CHECK( cudaMemsetAsync( levels, 0, nmb * X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ), s ) );
+    XD_CHECK( cudaMemsetAsync( nnz, 0, nmb * X264DSP_RES_NNZ_PER_MB, s ) );
+    int per_sm = 0;
+    XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, xd_pframe_kernel, PF_WARPS * 32, 0 ) );
+    if( per_sm < 1 )
+        per_sm = 1;
+    int64_t ctas = (int64_t)ctx->sm_count * per_sm;
+    const int64_t wanted = ( (int64_t)rows + PF_WARPS - 1 ) / PF_WARPS;
+    if( ctas > wanted )
+        ctas = wanted;
+    xd_pframe_kernel<<<(unsigned)ctas, PF_WARPS * 32, 0, s>>>( A );
+    ctx->launches++;
+    XD_CHECK( cudaGetLastError() );
+    return xd_scratch_release( ctx, XD_SCRATCH_DEBLOCK, s );
+}
