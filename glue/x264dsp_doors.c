@@ -254,6 +254,104 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * x264_macroblock_analyse     encoder/analyse.c:1059       called from encoder/encoder.c:1526 (slice loop)
+ *
+ * The whole P-slice macroblock loop on the device: when the first macroblock of a P slice arrives, the
+ * hook runs x264dsp_p_frames_dev on the resident source / reference frames and hands back, for every macroblock of the
+ * frame, what x264_macroblock_analyse and x264_macroblock_encode would have left behind -- type, vector, 16x16 search
+ * vector, levels, nnz, cbp, reconstruction.  This door then only installs macroblock xy's decisions where the rest of the
+ * slice loop reads them (what x264_mb_analyse_init and x264_analyse_update_cache write, analyse.c:327-420, 1236-1300),
+ * and the x264_macroblock_encode door below serves the macroblock's coded data from the same frame result: the host is
+ * left with the entropy coder.  Eligible: one reference frame, analyse.inter == 0, no trellis / noise reduction.
+ * Both doors also keep the time the reference spends in its own two functions (bench.py's cpu_baseline for this path). */
+typedef struct
+{
+    const int8_t *mb_type;          /* [mb] */
+    const int16_t *mv, *mvr;        /* [mb][2] */
+    const int16_t *cbp;             /* [mb] */
+    const int16_t *levels;          /* [mb][392] */
+    const uint8_t *nnz;             /* [mb][27] */
+    const uint8_t *recon_y, *recon_c;   /* sample (0,0) of the reconstructed luma / NV12 chroma planes */
+    int stride_y, stride_c;
+} xref_pframe_out_t;
+typedef int (*xref_pframe_cb)( void *h, xref_pframe_out_t *out );
+xref_pframe_cb xref_hook_pframe = NULL;
+static xref_pframe_out_t xref_pframe;
+static int xref_pframe_live = 0;            /* the current slice is served from xref_pframe */
+int xref_pframe_stats[3];                   /* P slices seen with the hook installed, served, macroblocks served */
+double xref_door_seconds[2];                /* time inside the reference's own x264_macroblock_analyse / _encode */
+int xref_door_timing = 0;
+
+void xref_set_pframe_hook( xref_pframe_cb cb )
+{
+    xref_hook_pframe = cb;
+    xref_pframe_live = 0;
+    xref_pframe_stats[0] = xref_pframe_stats[1] = xref_pframe_stats[2] = 0;
+}
+void xref_pframe_stats_read( int out[3] ) { memcpy( out, xref_pframe_stats, sizeof(xref_pframe_stats) ); }
+void xref_set_door_timing( int on ) { xref_door_timing = on; xref_door_seconds[0] = xref_door_seconds[1] = 0; }
+void xref_door_seconds_read( double out[2] ) { out[0] = xref_door_seconds[0]; out[1] = xref_door_seconds[1]; }
+
+#include <time.h>
+static double xref_clock( void )
+{
+    struct timespec ts;
+    clock_gettime( CLOCK_MONOTONIC, &ts );
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+void xref_orig_macroblock_analyse( x264_t *h );
+
+void x264_macroblock_analyse( x264_t *h )
+{
+    if( h->sh.i_type == SLICE_TYPE_P && xref_hook_pframe && h->mb.i_mb_xy == h->sh.i_first_mb )
+    {
+        xref_pframe_stats[0]++;
+        xref_pframe_live = h->i_ref[0] == 1 && !h->param.analyse.inter && !h->param.analyse.i_trellis
+                           && !h->param.analyse.i_noise_reduction && h->sh.i_first_mb == 0 && h->sh.i_qp <= QP_MAX_SPEC
+                           && !xref_hook_pframe( h, &xref_pframe );
+        xref_pframe_stats[1] += xref_pframe_live;
+    }
+    else if( h->sh.i_type != SLICE_TYPE_P )
+        xref_pframe_live = 0;
+    if( !xref_pframe_live )
+    {
+        if( xref_door_timing )
+        {
+            const double t0 = xref_clock();
+            xref_orig_macroblock_analyse( h );
+            xref_door_seconds[0] += xref_clock() - t0;
+        }
+        else
+            xref_orig_macroblock_analyse( h );
+        return;
+    }
+    {
+        const int xy = h->mb.i_mb_xy;
+        const int type = xref_pframe.mb_type[xy];
+        /* x264_mb_analyse_init */
+        h->mb.i_qp = h->sh.i_qp;
+        h->mb.i_chroma_qp = h->chroma_qp_table[h->sh.i_qp];
+        h->mb.b_transform_8x8 = 0;
+        h->mb.b_noise_reduction = 0;
+        h->mb.b_trellis = 0;
+        h->mb.b_skip_mc = 1;                 /* the prediction never has to be built on the host */
+        h->mb.i_skip_intra = 1;
+        h->mb.mv_min[0] = ( -( h->mb.i_mb_x << 4 ) - 24 ) << 2;
+        h->mb.mv_max[0] = ( ( ( h->mb.i_mb_width - h->mb.i_mb_x - 1 ) << 4 ) + 24 ) << 2;
+        h->mb.mv_min[1] = ( -( h->mb.i_mb_y << 4 ) - 24 ) << 2;
+        h->mb.mv_max[1] = ( ( ( h->mb.i_mb_height - h->mb.i_mb_y - 1 ) << 4 ) + 24 ) << 2;
+        /* x264_analyse_update_cache: P_L0 16x16 or P_SKIP, reference 0 */
+        h->mb.i_type = type;
+        h->mb.i_partition = D_16x16;
+        x264_macroblock_cache_ref( h, 0, 0, 4, 4, 0, 0 );
+        x264_macroblock_cache_mv_ptr( h, 0, 0, 4, 4, 0, (int16_t *)( xref_pframe.mv + 2 * xy ) );
+        CP32( h->mb.mvr[0][0][xy], xref_pframe.mvr + 2 * xy );
+        xref_pframe_stats[2]++;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * x264_macroblock_encode      encoder/macroblock.c:310     called from encoder/encoder.c (slice loop)
  *
  * Inter macroblocks of a P slice (P_L0, P_8x8; any partition -- the residual is one 16x16 transform
@@ -296,8 +394,54 @@ void x264_macroblock_encode( x264_t *h )
     uint8_t i4_modes[16];
     int kind = i16;
     const int inter = !IS_INTRA( h->mb.i_type ) && h->mb.i_type != P_SKIP && h->sh.i_type == SLICE_TYPE_P && h->mb.b_dct_decimate;
+    if( xref_pframe_live && h->sh.i_type == SLICE_TYPE_P )
+    {
+        /* the macroblock was coded on the device with the rest of its frame: reconstruction into fdec, coded data where
+         * the entropy coder reads them (layout as below) */
+        const int xy = h->mb.i_mb_xy;
+        const uint8_t *ry = xref_pframe.recon_y + (intptr_t)( h->mb.i_mb_y << 4 ) * xref_pframe.stride_y + ( h->mb.i_mb_x << 4 );
+        const uint8_t *rc = xref_pframe.recon_c + (intptr_t)( h->mb.i_mb_y << 3 ) * xref_pframe.stride_c + ( h->mb.i_mb_x << 4 );
+        const int16_t *lv = xref_pframe.levels + (size_t)xy * 392;
+        const uint8_t *nz = xref_pframe.nnz + (size_t)xy * 27;
+        int x, y;
+        cbp = xref_pframe.cbp[xy];
+        for( y = 0; y < 16; y++ )
+            memcpy( h->mb.pic.p_fdec[0] + y * FDEC_STRIDE, ry + (intptr_t)y * xref_pframe.stride_y, 16 );
+        for( y = 0; y < 8; y++ )
+            for( x = 0; x < 8; x++ )
+            {
+                h->mb.pic.p_fdec[1][y * FDEC_STRIDE + x] = rc[(intptr_t)y * xref_pframe.stride_c + 2 * x];
+                h->mb.pic.p_fdec[2][y * FDEC_STRIDE + x] = rc[(intptr_t)y * xref_pframe.stride_c + 2 * x + 1];
+            }
+        memcpy( h->dct.luma4x4[0], lv, 16*16*sizeof(int16_t) );
+        memcpy( h->dct.chroma_dc[0], lv + 256, 4*sizeof(int16_t) );
+        memcpy( h->dct.chroma_dc[1], lv + 260, 4*sizeof(int16_t) );
+        memcpy( h->dct.luma4x4[16], lv + 264, 4*16*sizeof(int16_t) );
+        memcpy( h->dct.luma4x4[32], lv + 328, 4*16*sizeof(int16_t) );
+        for( i = 0; i < 16; i++ )
+            h->mb.cache.non_zero_count[x264_scan8[i]] = nz[i];
+        for( i = 0; i < 4; i++ )
+        {
+            h->mb.cache.non_zero_count[x264_scan8[16+i]] = nz[16+i];
+            h->mb.cache.non_zero_count[x264_scan8[32+i]] = nz[20+i];
+        }
+        h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = 0;
+        h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]] = nz[25];
+        h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]] = nz[26];
+        h->mb.i_cbp_luma = cbp & 15;
+        h->mb.i_cbp_chroma = ( cbp >> 4 ) & 3;
+        h->mb.cbp[xy] = h->param.b_cabac ? cbp : ( cbp & 0x3f );
+        return;
+    }
     if( xref_hook_mbenc )
         xref_door_stats[XREF_DOOR_MBENC][0]++;
+    if( xref_door_timing && !xref_hook_mbenc )
+    {
+        const double t0 = xref_clock();
+        xref_orig_macroblock_encode( h );
+        xref_door_seconds[1] += xref_clock() - t0;
+        return;
+    }
     if( !xref_hook_mbenc || !( i16 || i4 || inter ) || h->mb.b_noise_reduction || h->mb.b_transform_8x8 || h->mb.b_lossless
         || h->mb.i_chroma_qp != h->chroma_qp_table[h->mb.i_qp] )
     {

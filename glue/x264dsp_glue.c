@@ -15,6 +15,9 @@
  *   x264_mb_mc (common/macroblock.c:28)                              -> x264dsp_mc_frames_part_dev
  *   x264_macroblock_probe_pskip (encoder/macroblock.c:492)           -> x264dsp_mc_frame_dev + x264dsp_probe_pskip_frames_dev
  *   x264_macroblock_encode (encoder/macroblock.c:310)                -> x264dsp_residual_frames_typed_dev
+ *   x264_macroblock_analyse + x264_macroblock_encode of a whole P slice (encoder/analyse.c:1059, encoder.c:1523-1578)
+ *                                                                    -> x264dsp_p_frames_dev, once per frame: the host
+ *                                                                       keeps the entropy coder (x264dsp_glue_install_pframe)
  *
  * The reference calls these doors one macroblock (or one frame) at a time, so this glue is a CORRECTNESS drop-in -- every
  * call is a round trip to the device -- and not the fast path (the frame-batched entry points are; bench.py times those).
@@ -53,6 +56,19 @@ void xref_set_me_hook( xref_me_cb cb );
 void xref_set_mbenc_hook( xref_mbenc_cb cb );
 void xref_set_pskip_hook( xref_pskip_cb cb );
 void xref_set_mbmc_hook( xref_mbmc_cb cb );
+typedef struct
+{
+    const int8_t *mb_type;
+    const int16_t *mv, *mvr;
+    const int16_t *cbp;
+    const int16_t *levels;
+    const uint8_t *nnz;
+    const uint8_t *recon_y, *recon_c;
+    int stride_y, stride_c;
+} xref_pframe_out_t;
+typedef int (*xref_pframe_cb)( void *h, xref_pframe_out_t *out );
+void xref_set_pframe_hook( xref_pframe_cb cb );
+void xref_pframe_stats_read( int out[3] );
 void xref_driver_hook_calls( int out[3] );
 void xref_door_stats_read( int out[12] );
 
@@ -72,11 +88,16 @@ static struct
     int32_t *d_costs, *d_sums;
     x264dsp_me_block_t *d_blk;
     x264dsp_me_result_t *d_res;
+    /* whole-P-frame results: device, and their host copies */
+    int8_t *d_pf_type, *h_pf_type;
+    int16_t *d_pf_mv, *d_pf_mvr, *d_pf_cbp, *d_pf_levels, *d_pf_lmv, *d_pf_l0;
+    int16_t *h_pf_mv, *h_pf_mvr, *h_pf_cbp, *h_pf_levels;
+    uint8_t *d_pf_nnz, *h_pf_nnz, *h_pf_luma, *h_pf_chroma;
     /* host scratch */
     uint8_t *mb_stage;                    /* two 16x16 slots */
     uint8_t *rows;                        /* 16 luma rows of a macroblock as one linear piece of the plane */
     int64_t launches0;
-    int calls[8];                         /* lowres, fdec, cost, me, mbenc, pskip, mbmc, deblocked frames */
+    int calls[9];                         /* lowres, fdec, cost, me, mbenc, pskip, mbmc, deblocked frames, P frames */
 } G;
 
 #define GLUE_CHECK( call ) do { int rc_ = ( call ); if( rc_ ) { fprintf( stderr, "x264dsp glue: %s failed (%d) at %s:%d\n", \
@@ -121,6 +142,22 @@ static void glue_open( x264_t *h )
     G.d_cbp1 = glue_dev( 16 );
     G.mb_stage = calloc( 2, (size_t)G.g1.slot_bytes );
     G.rows = malloc( (size_t)16 * G.g.luma_stride );
+    G.d_pf_type = glue_dev( nmb );
+    G.d_pf_mv = glue_dev( 4 * nmb );
+    G.d_pf_mvr = glue_dev( 4 * nmb );
+    G.d_pf_cbp = glue_dev( 2 * nmb );
+    G.d_pf_levels = glue_dev( nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t) );
+    G.d_pf_nnz = glue_dev( nmb * X264DSP_RES_NNZ_PER_MB );
+    G.d_pf_lmv = glue_dev( 4 * nmb );
+    G.d_pf_l0 = glue_dev( 4 * nmb );
+    G.h_pf_type = malloc( nmb );
+    G.h_pf_mv = malloc( 4 * nmb );
+    G.h_pf_mvr = malloc( 4 * nmb );
+    G.h_pf_cbp = malloc( 2 * nmb );
+    G.h_pf_levels = malloc( nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t) );
+    G.h_pf_nnz = malloc( nmb * X264DSP_RES_NNZ_PER_MB );
+    G.h_pf_luma = malloc( G.g.luma_plane_size );
+    G.h_pf_chroma = malloc( G.g.chroma_plane_size );
     G.launches0 = x264dsp_launch_count( G.ctx );
 }
 
@@ -353,6 +390,65 @@ static int glue_mbenc( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, u
     return 0;
 }
 
+/* ---- the macroblock loop of a whole P slice: x264dsp_p_frames_dev on the resident source and reference frame, with the
+ *      lookahead's vectors of the pair and the reference frame's 16x16 vectors as the search's extra candidates exactly
+ *      as x264_mb_predict_mv_ref16x16 takes them (common/mvpred.c:167-219) */
+static int glue_pframe( void *hv, xref_pframe_out_t *out )
+{
+    x264_t *h = hv;
+    x264_frame_t *fref = h->fref[0][0];
+    const uint8_t *se = glue_resident( h->fenc ), *sr = glue_resident( fref );
+    if( !G.ctx || !se || !sr )
+        return 1;
+    const x264dsp_geom_t *g = &G.g;
+    const size_t nmb = g->mb_count;
+    const int idx = h->fenc->i_frame - fref->i_frame - 1;
+    const int have_lowres = h->frames.b_have_lowres && idx >= 0 && idx <= h->param.i_bframe
+                            && h->fenc->lowres_mvs[0][idx][0][0] != 0x7fff;
+    const int have_l0 = fref->i_ref[0] > 0;
+    x264dsp_pframe_params_t prm;
+    prm.me_method = h->mb.i_me_method;
+    prm.subpel_refine = h->mb.i_subpel_refine;
+    prm.me_range = h->param.analyse.i_me_range;
+    prm.qp = h->sh.i_qp;
+    prm.mv_range = h->param.analyse.i_mv_range;
+    prm.fast_pskip = h->param.analyse.b_fast_pskip;
+    prm.mvc_scale = have_l0 ? ( h->fdec->i_poc - fref->i_poc ) * fref->inv_ref_poc[0] : 0;
+    if( have_lowres )
+        GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_pf_lmv, h->fenc->lowres_mvs[0][idx], 4 * nmb, NULL ) );
+    if( have_l0 )
+        GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_pf_l0, fref->mv16x16, 4 * nmb, NULL ) );
+    if( x264dsp_p_frames_dev( G.ctx, g, se, sr, glue_pred(), 1, &prm, have_lowres ? G.d_pf_lmv : NULL, have_l0 ? G.d_pf_l0 : NULL,
+                              G.d_pf_type, G.d_pf_mv, G.d_pf_mvr, G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL ) )
+        return 1;                                              /* parameters the device path does not take: the host's own loop */
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_type, G.d_pf_type, nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_mv, G.d_pf_mv, 4 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_mvr, G.d_pf_mvr, 4 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_cbp, G.d_pf_cbp, 2 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_levels, G.d_pf_levels, nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t), NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_nnz, G.d_pf_nnz, nmb * X264DSP_RES_NNZ_PER_MB, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_luma, glue_pred(), g->luma_plane_size, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_chroma, glue_pred() + g->slot_chroma_off, g->chroma_plane_size, NULL ) );
+    out->mb_type = G.h_pf_type;
+    out->mv = G.h_pf_mv;
+    out->mvr = G.h_pf_mvr;
+    out->cbp = G.h_pf_cbp;
+    out->levels = G.h_pf_levels;
+    out->nnz = G.h_pf_nnz;
+    out->recon_y = G.h_pf_luma + g->luma_origin;
+    out->recon_c = G.h_pf_chroma + g->chroma_origin;
+    out->stride_y = g->luma_stride;
+    out->stride_c = g->chroma_stride;
+    G.calls[8]++;
+    return 0;
+}
+
+/* the whole P-slice macroblock loop on the device (on top of x264dsp_glue_install) */
+void x264dsp_glue_install_pframe( void )
+{
+    xref_set_pframe_hook( glue_pframe );
+}
+
 void x264dsp_glue_install( void )
 {
     xref_set_driver_hooks( glue_lowres, NULL, glue_cost );
@@ -371,21 +467,24 @@ void x264dsp_glue_uninstall( void )
     xref_set_mbenc_hook( NULL );
     xref_set_pskip_hook( NULL );
     xref_set_mbmc_hook( NULL );
+    xref_set_pframe_hook( NULL );
 }
 
 /* one JSON object: how often each door was served by the device, what the doors themselves counted
  * ({entered, eligible, served} per door: eligible != served means a silent fallback), kernel launches */
 int x264dsp_glue_report( FILE *out )
 {
-    int hook[3], doors[12];
+    int hook[3], doors[12], pf[3];
     xref_driver_hook_calls( hook );
+    xref_pframe_stats_read( pf );
     xref_door_stats_read( doors );
     return fprintf( out, "{\"lowres\": %d, \"inloop_filter\": %d, \"deblocked_frames\": %d, \"lookahead_cost\": %d, "
                     "\"me_search\": %d, \"macroblock_encode\": %d, \"probe_pskip\": %d, \"mb_mc\": %d, "
                     "\"door_me\": [%d, %d, %d], \"door_mbenc\": [%d, %d, %d], \"door_pskip\": [%d, %d, %d], "
-                    "\"door_mbmc\": [%d, %d, %d], \"hook_calls\": [%d, %d, %d], \"kernel_launches\": %lld}\n",
+                    "\"door_mbmc\": [%d, %d, %d], \"hook_calls\": [%d, %d, %d], \"p_frames\": %d, "
+                    "\"p_slices\": [%d, %d, %d], \"kernel_launches\": %lld}\n",
                     G.calls[0], G.calls[1], G.calls[7], G.calls[2], G.calls[3], G.calls[4], G.calls[5], G.calls[6],
                     doors[0], doors[1], doors[2], doors[3], doors[4], doors[5], doors[6], doors[7], doors[8], doors[9],
-                    doors[10], doors[11], hook[0], hook[1], hook[2],
+                    doors[10], doors[11], hook[0], hook[1], hook[2], G.calls[8], pf[0], pf[1], pf[2],
                     G.ctx ? (long long)( x264dsp_launch_count( G.ctx ) - G.launches0 ) : 0LL );
 }

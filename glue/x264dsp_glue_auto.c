@@ -1,5 +1,6 @@
 /* Linked into x264ref_gpu only: installs the glue before main() runs, so that the reference's CLI (x264.c, input.c,
- * output.c -- compiled unmodified) needs no change at all.  X264DSP_GLUE=0 leaves the doors closed (the binary then
+ * output.c -- compiled unmodified) needs no change at all.  X264DSP_GLUE_PFRAME=0 keeps the P-slice macroblock loop on the
+ * host (per-macroblock doors only); X264DSP_GLUE=0 leaves the doors closed (the binary then
  * behaves exactly like the reference CLI); X264DSP_GLUE_STATS=<file> writes x264dsp_glue_report() there at exit. */
 #include <execinfo.h>
 #include <signal.h>
@@ -42,5 +43,8 @@ __attribute__((constructor)) static void glue_auto( void )
     if( e && !strcmp( e, "0" ) )
         return;
     x264dsp_glue_install();
+    e = getenv( "X264DSP_GLUE_PFRAME" );           /* 0: per-macroblock doors only */
+    if( !e || strcmp( e, "0" ) )
+        x264dsp_glue_install_pframe();
     atexit( glue_atexit );
 }

@@ -48,13 +48,36 @@ def test_glue_cli_with_doors_closed_is_the_reference(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("w,h,n,cut", [(352, 288, 30, 17), (1920, 1080, 3, -1)])
-def test_glue_cli_bitstream_identical(tmp_path, w, h, n, cut):
+def test_glue_cli_p_slices_on_the_device(tmp_path, w, h, n, cut):
+    """the default mode: the macroblock loop of every P slice (x264_macroblock_analyse + x264_macroblock_encode) is ONE
+    x264dsp_p_frames_dev call per frame, the host keeps the entropy coder; I slices go through the per-macroblock doors"""
     assert os.path.exists(GPU_CLI), "glue/_build/x264ref_gpu must travel to the GPU box (make -C glue)"
     assert os.path.exists(cc.REF_CLI), "oracle/_ref/x264ref must travel to the GPU box (make -C oracle ref)"
     src = make_clip(tmp_path, w, h, n, cut)
     want = run_cli(cc.REF_CLI, src, str(tmp_path / "ref.264"))
     stats_path = str(tmp_path / "stats.json")
     got = run_cli(GPU_CLI, src, str(tmp_path / "gpu.264"), {"X264DSP_GLUE_STATS": stats_path})
+    st = json.load(open(stats_path))
+    print("GLUESTATS pframe", f"{w}x{h}x{n}", json.dumps(st))
+    assert want.size > 0 and got.size == want.size and np.array_equal(want, got), \
+        f"bitstreams differ: {got.size} vs {want.size} bytes"
+    mbs = ((w + 15) // 16) * ((h + 15) // 16)
+    seen, served, served_mbs = st["p_slices"]
+    assert seen == served == st["p_frames"] >= n - 2, st             # every P slice of the clip, none declined
+    assert served_mbs == served * mbs, st
+    assert st["me_search"] == 0 and st["probe_pskip"] == 0 and st["mb_mc"] == 0, st    # no per-macroblock round trips left
+    assert st["lowres"] == n and st["inloop_filter"] == n and st["lookahead_cost"] == n - 1, st
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,cut", [(352, 288, 30, 17), (1920, 1080, 3, -1)])
+def test_glue_cli_bitstream_identical(tmp_path, w, h, n, cut):
+    assert os.path.exists(GPU_CLI), "glue/_build/x264ref_gpu must travel to the GPU box (make -C glue)"
+    assert os.path.exists(cc.REF_CLI), "oracle/_ref/x264ref must travel to the GPU box (make -C oracle ref)"
+    src = make_clip(tmp_path, w, h, n, cut)
+    want = run_cli(cc.REF_CLI, src, str(tmp_path / "ref.264"))
+    stats_path = str(tmp_path / "stats.json")
+    got = run_cli(GPU_CLI, src, str(tmp_path / "gpu.264"), {"X264DSP_GLUE_STATS": stats_path, "X264DSP_GLUE_PFRAME": "0"})
     st = json.load(open(stats_path))
     print("GLUESTATS", f"{w}x{h}x{n}", json.dumps(st))
     assert want.size > 0 and got.size == want.size and np.array_equal(want, got), \
