@@ -356,6 +356,120 @@ def cpu_recon_reference(which, w, h, pics, mv, bs, threads, qp=26, target_s=4.0)
     return threads * reps / dt, (lv.copy(), nz.copy(), cbp.copy(), y.copy(), c.copy())
 
 
+def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3):
+    """BASELINE north_star's closed loop, SURVEY 8(f) N2: x264_macroblock_analyse + x264_macroblock_encode for every macroblock
+    of n_frames independent 1080p P frames in ONE launch (x264dsp_p_frames_dev).  Inputs as an encoder has them: reference
+    frame border-expanded and half-pel filtered, the lookahead's vectors of each pair as first search candidate.  Returns
+    (ms per frame, ms for one frame alone, skipped share, (host slots of pair 0, lowres mvs, results of frame 0))"""
+    stream = ctx.torch_stream()
+    nmb = g.mb_count
+    distinct = min(n_frames, 24) + 1
+    frames = np.stack([pkg.synth_frame(w, h, i) for i in range(distinct)])
+    one = torch.zeros(distinct * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    ctx.frame_load_i420(g, torch.from_numpy(frames).cuda(), one, distinct)
+    ctx.frame_expand_border(g, one, distinct)
+    ctx.frame_filter(g, one, distinct)
+    ctx.frame_init_lowres(g, one, distinct)
+    src = torch.zeros((n_frames + 1) * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    for k in range(n_frames + 1):                      # pair k = slot k -> slot k + 1, cycling through the distinct frames
+        j = k % distinct
+        src[k * g.slot_bytes:(k + 1) * g.slot_bytes] = one[j * g.slot_bytes:(j + 1) * g.slot_bytes]
+    del one
+    b = np.arange(1, n_frames + 1, dtype=np.int32)
+    d_lmv = torch.zeros((n_frames, nmb, 2), dtype=torch.int16, device="cuda")
+    d_lc = torch.zeros((n_frames, nmb), dtype=torch.int32, device="cuda")
+    d_ls = torch.zeros((n_frames, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
+    ctx.lookahead_frame_cost(g, src, b, b - 1, np.ones(n_frames, np.uint8), d_lmv, d_lc, d_ls)
+    o = dict(mb_type=torch.zeros((n_frames, nmb), dtype=torch.int8, device="cuda"),
+             mv=torch.zeros((n_frames, nmb, 2), dtype=torch.int16, device="cuda"),
+             mvr=torch.zeros((n_frames, nmb, 2), dtype=torch.int16, device="cuda"),
+             levels=torch.zeros((n_frames, nmb, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda"),
+             nnz=torch.zeros((n_frames, nmb, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda"),
+             cbp=torch.zeros((n_frames, nmb), dtype=torch.int16, device="cuda"))
+    recon = torch.zeros(n_frames * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    prm = pkg.PFrameParams(me, subme, 16, qp, 512, 1, 0)
+
+    def run(n):
+        ctx.p_frames(g, src[g.slot_bytes:], src, recon, n, prm, d_lmv[:n], None, o["mb_type"], o["mv"], o["mvr"], o["levels"],
+                     o["nnz"], o["cbp"])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = []
+    for n in (n_frames, 1):
+        run(n)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(reps):
+            run(n)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        out.append(ev0.elapsed_time(ev1) / reps / n)
+    run(n_frames)
+    torch.cuda.synchronize()
+    types = o["mb_type"].cpu().numpy()
+    check = (src[: 2 * g.slot_bytes].cpu().numpy(), d_lmv[0].cpu().numpy(),
+             {k: v[0].cpu().numpy() for k, v in o.items()}, recon[: g.slot_bytes].cpu().numpy(), (me, subme, qp))
+    return out[0], out[1], float((types == pkg.MB_P_SKIP).mean()), check
+
+
+def pframe_oracle_check(g, check):
+    """frame 0 of the P-frame measurement against the CPU oracle's xo_p_frame (pinned to the running reference encoder)"""
+    import cpu_checkers as cc
+    from cpu_checkers import ptr
+    slots, lmv, got, recon, (me, subme, qp) = check
+    o = cc.oracle()
+    go = cc.oracle_geom(g.width, g.height)
+    nmb = g.mb_count
+
+    class P(C.Structure):
+        _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale")]
+    want = {"mb_type": np.zeros(nmb, np.int8), "mv": np.zeros((nmb, 2), np.int16), "mvr": np.zeros((nmb, 2), np.int16),
+            "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8), "cbp": np.zeros(nmb, np.int16)}
+    wrecon = np.zeros(g.slot_bytes, np.uint8)
+    prm = P(me, subme, 16, qp, 512, 1, 0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    o.xo_p_frame(C.byref(go), ptr(slots[g.slot_bytes:]), ptr(slots[: g.slot_bytes]), ptr(wrecon), C.byref(prm), vp(lmv), None,
+                 vp(want["mb_type"]), vp(want["mv"]), vp(want["mvr"]), vp(want["levels"]), vp(want["nnz"]), vp(want["cbp"]))
+    ok = all(np.array_equal(got[k], want[k]) for k in want)
+    lo = g.luma_origin
+    a = recon[lo:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:, : g.luma_w]
+    bb = wrecon[lo:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:, : g.luma_w]
+    return bool(ok and np.array_equal(a, bb))
+
+
+def cpu_pframe_reference(which, w, h, threads, me, subme, qp=26, n_frames=5):
+    """the reference's own x264_macroblock_analyse + x264_macroblock_encode on P slices: every host thread encodes its own
+    1080p clip with its own encoder instance (unmodified reference, oracle/_ref); the doors in front of the two functions
+    keep the time each thread spends inside them on P slices.  Returns (P frames/s of that path summed over the threads,
+    whole-encoder frames/s by wall clock, share of the encoder's time the path takes)"""
+    import cpu_checkers as cc
+    from cpu_checkers import ptr
+    lib = cc.ref_o3() if which == "O3" else cc.ref()
+    if lib is None or not hasattr(lib, "xref_open_ex"):
+        return None
+    lib.xref_open_ex.restype = C.c_void_p
+    clips = [np.concatenate([cc.synth_frame(w, h, 3 * t + i) for i in range(n_frames)]) for t in range(min(threads, 4))]
+    encs = [C.c_void_p(lib.xref_open_ex(w, h, me, subme, 16, qp, 0, 1)) for _ in range(threads)]
+    mbs = ((w + 15) // 16) * ((h + 15) // 16)
+    rates, secs = [0.0] * threads, [0.0] * threads
+    lib.xref_set_door_timing(1)
+
+    def work(t):
+        out = np.zeros(8 << 20, np.uint8)
+        t0 = time.perf_counter()
+        size = lib.xref_encode_clip(encs[t], ptr(clips[t % len(clips)]), n_frames, ptr(out), out.size)
+        secs[t] = time.perf_counter() - t0
+        acc = (C.c_double * 3)()
+        lib.xref_door_seconds_read(acc)
+        assert size > 0 and acc[2] > 0
+        rates[t] = (acc[2] / mbs) / (acc[0] + acc[1])          # P frames per second of analyse + encode on this thread
+        secs[t] = (acc[0] + acc[1]) / secs[t]
+    try:
+        dt = _run_threads(work, threads)
+    finally:
+        lib.xref_set_door_timing(0)
+    return sum(rates), threads * n_frames / dt, float(np.mean(secs))
+
+
 def me_search_e2e(pkg, ctx, g, w, h, luma_host, la_mvs, pairs, reps=3, qp=26):
     """configs[2] end to end through x264dsp_me_search_frames_host: pinned host pictures and block lists in, pinned
     results out.  Returns (seconds per call, h2d bytes, d2h bytes, results of the last call by size)"""
@@ -925,6 +1039,15 @@ def main():
     rc_ms_big = None
     if not args.no_me and world == 1 and rank == 0 and w * h <= 1920 * 1088:
         rc_ms_big, _ = recon_measure(pkg, ctx, torch, g, w, h, 384, reps=2)
+    # ---- the closed loop of a P frame on the device, every rank on its own frames
+    pf = None
+    if not args.no_me and w * h <= 1920 * 1088:
+        pf = {}
+        for name, (pme, psub) in (("dia_subme1", (0, 1)), ("hex_subme5", (1, 5))):
+            pf[name] = pframe_measure(pkg, ctx, torch, g, w, h, 96, pme, psub)
+        sec += [pf["dia_subme1"][0], pf["hex_subme5"][0]]
+    else:
+        sec += [0.0, 0.0]
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3] + sec + [copy_s * 1e3], dtype=torch.float64, device="cuda")
@@ -932,7 +1055,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     me_dev_ms_max, me_e2e_s_max, rc_dev_ms_max, rc_e2e_s_max = (float(x) for x in t[2:6])
-    copy_ms = float(t[6])
+    pf_ms_max = (float(t[6]), float(t[7]))
+    copy_ms = float(t[8])
 
     if rank == 0:
         frames_total = world * n * args.steps
@@ -1085,6 +1209,35 @@ def main():
                         cb["gpu_equals_reference" + ("" if which == "O2" else "_O3")] = bool(same)
                 rc["cpu_baseline"] = cb
             line["recon"] = rc
+        if pf is not None:
+            pfl = {"workload": f"{w}x{h} P frames, the whole macroblock loop on the device: x264_macroblock_analyse (MV prediction, "
+                               "fast / early P_SKIP probe, 16x16 search with the reference's candidate list, refine_qpel) + "
+                               "x264_macroblock_encode (mc, residual, forced P_SKIP) for every macroblock as a wavefront; "
+                               "QP 26, one reference frame, analyse.inter = 0 (the reference's default); the host keeps CABAC",
+                   "launch": "x264dsp_p_frames_dev, 96 independent frames per launch, every rank on its own frames",
+                   "unit": "frames/s", "n_gpus": world, "settings": {}}
+            for k, (name, (pme, psub)) in enumerate((("dia_subme1", (0, 1)), ("hex_subme5", (1, 5)))):
+                ms_f, ms_one, skipped, check = pf[name]
+                ent = {"value": world * 1e3 / pf_ms_max[k], "ms_per_frame": pf_ms_max[k], "ms_one_frame_alone": ms_one,
+                       "skipped_mb_share": skipped, "me_method": pme, "subme": psub}
+                if baseline_ok:
+                    ent["bit_exact_vs_oracle"] = pframe_oracle_check(g, check)
+                    cb = {"unit": "frames/s", "cores": threads, "kind": "reference",
+                          "sample": "every host thread encodes its own 5-frame 1080p clip with its own instance of the unmodified "
+                                    "reference; the doors in front of x264_macroblock_analyse and x264_macroblock_encode keep the "
+                                    "time each thread spends inside them on P slices; value = sum over the threads of P frames per "
+                                    "second of that path"}
+                    for which in ("O2", "O3"):
+                        r = cpu_pframe_reference(which, w, h, threads, pme, psub)
+                        if r is not None:
+                            sfx = "" if which == "O2" else "_O3_x86-64-v3"
+                            cb["value" + sfx] = r[0]
+                            cb["whole_encoder_frames_per_s" + sfx] = r[1]
+                            cb["path_share_of_encoder_time" + sfx] = r[2]
+                    ent["cpu_baseline"] = cb
+                pfl["settings"][name] = ent
+            pfl["value"] = pfl["settings"]["dia_subme1"]["value"]
+            line["pframe"] = pfl
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -279,7 +279,10 @@ xref_pframe_cb xref_hook_pframe = NULL;
 static xref_pframe_out_t xref_pframe;
 static int xref_pframe_live = 0;            /* the current slice is served from xref_pframe */
 int xref_pframe_stats[3];                   /* P slices seen with the hook installed, served, macroblocks served */
-double xref_door_seconds[2];                /* time inside the reference's own x264_macroblock_analyse / _encode */
+/* time this THREAD has spent inside the reference's own x264_macroblock_analyse / x264_macroblock_encode on P slices,
+ * and the macroblocks it covers (every encoder instance runs on its own thread in the benchmark) */
+static __thread double xref_door_seconds[2];
+static __thread long xref_door_mbs;
 int xref_door_timing = 0;
 
 void xref_set_pframe_hook( xref_pframe_cb cb )
@@ -289,8 +292,14 @@ void xref_set_pframe_hook( xref_pframe_cb cb )
     xref_pframe_stats[0] = xref_pframe_stats[1] = xref_pframe_stats[2] = 0;
 }
 void xref_pframe_stats_read( int out[3] ) { memcpy( out, xref_pframe_stats, sizeof(xref_pframe_stats) ); }
-void xref_set_door_timing( int on ) { xref_door_timing = on; xref_door_seconds[0] = xref_door_seconds[1] = 0; }
-void xref_door_seconds_read( double out[2] ) { out[0] = xref_door_seconds[0]; out[1] = xref_door_seconds[1]; }
+void xref_set_door_timing( int on ) { xref_door_timing = on; }
+/* read and reset the calling thread's counters: out = { seconds in analyse, seconds in encode, macroblocks } */
+void xref_door_seconds_read( double out[3] )
+{
+    out[0] = xref_door_seconds[0]; out[1] = xref_door_seconds[1]; out[2] = (double)xref_door_mbs;
+    xref_door_seconds[0] = xref_door_seconds[1] = 0;
+    xref_door_mbs = 0;
+}
 
 #include <time.h>
 static double xref_clock( void )
@@ -316,11 +325,12 @@ void x264_macroblock_analyse( x264_t *h )
         xref_pframe_live = 0;
     if( !xref_pframe_live )
     {
-        if( xref_door_timing )
+        if( xref_door_timing && h->sh.i_type == SLICE_TYPE_P )
         {
             const double t0 = xref_clock();
             xref_orig_macroblock_analyse( h );
             xref_door_seconds[0] += xref_clock() - t0;
+            xref_door_mbs++;
         }
         else
             xref_orig_macroblock_analyse( h );
@@ -435,7 +445,7 @@ void x264_macroblock_encode( x264_t *h )
     }
     if( xref_hook_mbenc )
         xref_door_stats[XREF_DOOR_MBENC][0]++;
-    if( xref_door_timing && !xref_hook_mbenc )
+    if( xref_door_timing && !xref_hook_mbenc && h->sh.i_type == SLICE_TYPE_P )
     {
         const double t0 = xref_clock();
         xref_orig_macroblock_encode( h );

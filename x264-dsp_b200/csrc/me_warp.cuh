@@ -10,6 +10,14 @@
 #include "leaf.cuh"
 
 #define ME_COST_MAX ( 1 << 28 )
+// XD_ME_CALL / XD_ME_REFINE_CALL: __noinline__ makes the cost routines / the sub-pel refinement real calls (small code),
+// __forceinline__ / nothing inlines them at every site (see the note at xd_me_sad_call)
+#ifndef XD_ME_CALL
+#define XD_ME_CALL __forceinline__
+#endif
+#ifndef XD_ME_REFINE_CALL
+#define XD_ME_REFINE_CALL
+#endif
 
 struct xd_me_blk
 {
@@ -65,8 +73,17 @@ __device__ __forceinline__ uint32_t xd_me_pred4( const xd_qpel_src &s, int strid
 }
 
 // SAD of the block at quarter-pel (qx,qy); lanes of one candidate group cooperate (sub = lane & 7)
-__device__ __forceinline__ int xd_me_sad_raw( const xd_me_blk &B, int qx, int qy, int sub )
+// The two cost routines take the block description as scalars so that they can be compiled as real calls
+// (-DXD_ME_CALL=__noinline__): the search has some thirty call sites, a kernel that inlines them all is 25 000
+// instructions, and ncu shows the warps of the P-slice wavefront waiting for instruction fetches more than for anything
+// else (stall no_instruction 10.4 per issue).  Measured (round 2, 96 1080p P frames per launch): as calls the kernel is
+// 7 600 instructions and SLOWER -- 158 against 139 us per frame (DIA, subme 1), 292 against 284 (HEX, subme 5); with the
+// refinement a call as well 179 / 308 -- so everything stays inlined.
+static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint8_t *ref, size_t plane_size, int stride,
+                                                   int wh, int qx, int qy, int sub )
 {
+    xd_me_blk B;
+    B.fenc = fenc; B.ref = ref; B.plane_size = plane_size; B.stride = stride; B.w = wh & 255; B.h = wh >> 8;
     const xd_qpel_src s = xd_me_src( B, qx, qy );
     int acc = 0;
     if( B.w >= 8 )
@@ -92,8 +109,11 @@ __device__ __forceinline__ int xd_me_sad_raw( const xd_me_blk &B, int qx, int qy
 }
 
 // SATD (common/pixel.c:267-337) of the block at quarter-pel (qx,qy)
-__device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, int sub )
+static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uint8_t *ref, size_t plane_size, int stride,
+                                                    int wh, int qx, int qy, int sub )
 {
+    xd_me_blk B;
+    B.fenc = fenc; B.ref = ref; B.plane_size = plane_size; B.stride = stride; B.w = wh & 255; B.h = wh >> 8;
     const xd_qpel_src s = xd_me_src( B, qx, qy );
     int acc = 0;
     const int per_row = B.w >= 8 ? B.w >> 3 : 1;
@@ -128,6 +148,15 @@ __device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, i
     acc += __shfl_xor_sync( 0xffffffffu, acc, 2 );
     acc += __shfl_xor_sync( 0xffffffffu, acc, 4 );
     return acc;
+}
+
+__device__ __forceinline__ int xd_me_sad_raw( const xd_me_blk &B, int qx, int qy, int sub )
+{
+    return xd_me_sad_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub );
+}
+__device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, int sub )
+{
+    return xd_me_satd_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub );
 }
 
 // h->pixf.fpelcmp[i_pixel]: SAD, except under TESA where mbcmp_init (encoder.c:429-432) makes it SATD
@@ -167,7 +196,7 @@ struct xd_me_state
 
 // refine_subpel (me.c:466-587).  thresh = *p_halfpel_thresh (nullptr: the caller passed NULL); when the early
 // termination of me.c:527-536 fires, mv and cost are stored and cost_mv keeps its previous value, as there.
-static __device__ void xd_me_refine( const xd_me_blk &B, xd_me_state &S, int subme, int hpel_iters, int qpel_iters,
+static __device__ XD_ME_REFINE_CALL void xd_me_refine( const xd_me_blk &B, xd_me_state &S, int subme, int hpel_iters, int qpel_iters,
                               bool final_refine, int lane, int *thresh = nullptr )
 {
     const int cand = lane >> 3, sub = lane & 7;

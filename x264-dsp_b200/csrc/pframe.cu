@@ -24,7 +24,12 @@
 #include "residual_warp.cuh"
 #include "mvpred.cuh"
 
+#ifndef PF_WARPS
 #define PF_WARPS 2
+#endif
+#ifndef PF_MINB
+#define PF_MINB 8                   // resident CTAs per SM the register allocation aims at
+#endif
 
 int xd_me_params_ok( const x264dsp_me_params_t *p );   // me.cu
 
@@ -70,15 +75,16 @@ __device__ __forceinline__ int xd_pf_probe( const xd_pf_args &A, const uint8_t *
                                             uint32_t pskip, int lane )
 {
     const int16_t mvs[2] = { (int16_t)( pskip & 0xFFFF ), (int16_t)( pskip >> 16 ) };
-    xd_mc_mb<1>( A.g, fref, mvs, recon, mb, lane );
-    xd_mc_mb<1>( A.g, fref, mvs, recon, mb, lane + 32 );
+#pragma unroll 1
+    for( int half = 0; half < 2; half++ )
+        xd_mc_mb<1>( A.g, fref, mvs, recon, mb, lane + 32 * half );
     __syncwarp();
     const int ok = xd_residual_mb<false, true>( A.g, fenc, recon, A.T, nullptr, nullptr, nullptr, nullptr, nullptr, mb, lane );
     __syncwarp();
     return ok;
 }
 
-__global__ void __launch_bounds__( PF_WARPS * 32 )
+__global__ void __launch_bounds__( PF_WARPS * 32, PF_MINB )
 xd_pframe_kernel( xd_pf_args A )
 {
     __shared__ x264dsp_me_block_t s_blk[PF_WARPS];
@@ -172,21 +178,28 @@ xd_pframe_kernel( xd_pf_args A )
             int type = X264DSP_MB_P_L0, out_cbp = 0;
             uint32_t out_mv = 0, out_mvr = 0;
             bool done = false;
-            // ---- fast P_SKIP detection (analyse.c:1093-1105)
-            if( A.P.fast_pskip && subme < 3
-                && ( ntype[0] == X264DSP_MB_P_SKIP || ntype[1] == X264DSP_MB_P_SKIP || ntype[2] == X264DSP_MB_P_SKIP
-                     || ntype[3] == X264DSP_MB_P_SKIP ) )
+            // The probe has two callers -- the fast P_SKIP detection before the search (analyse.c:1093-1105) and the early
+            // termination after it (analyse.c:839-849) -- and ONE site here (the kernel's code has to stay small: see
+            // me_warp.cuh): the loop body runs probe?, search, probe? in that order.
+            bool try_probe = A.P.fast_pskip && subme < 3
+                             && ( ntype[0] == X264DSP_MB_P_SKIP || ntype[1] == X264DSP_MB_P_SKIP || ntype[2] == X264DSP_MB_P_SKIP
+                                  || ntype[3] == X264DSP_MB_P_SKIP );
+            bool searched = false;
+            xd_me_state R;
+            R.mvx = R.mvy = R.cost = R.cost_mv = 0;
+#pragma unroll 1
+            for( ;; )
             {
-                if( xd_pf_probe( A, fenc, fref, recon, xy, pskip, lane ) )
+                if( try_probe && xd_pf_probe( A, fenc, fref, recon, xy, pskip, lane ) )
                 {
-                    type = X264DSP_MB_P_SKIP;                  // analyse.c:1109-1117: later macroblocks see a zero 16x16 vector
+                    type = X264DSP_MB_P_SKIP;
                     out_mv = pskip;
-                    out_mvr = 0;
+                    if( !searched )
+                        out_mvr = 0;                           // analyse.c:1109-1117: later macroblocks see a zero 16x16 vector
                     done = true;
                 }
-            }
-            if( !done )
-            {
+                if( done || searched )
+                    break;
                 // ---- x264_mb_analyse_inter_p16x16: MVP, candidate list (mvpred.c:167-219), search
                 const uint32_t mvp = xd_predict_mv_16x16( nb, 0 );
                 if( lane == 0 )
@@ -232,33 +245,25 @@ xd_pframe_kernel( xd_pf_args A )
                     blk->mv_min_fpel[1] = ( smin_y >> 2 ) + border; blk->mv_max_fpel[1] = ( smax_y >> 2 ) - border;
                 }
                 __syncwarp();
-                xd_me_state R;
-                R.mvx = R.mvy = R.cost = R.cost_mv = 0;
                 xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
+                searched = true;
                 out_mvr = xd_pack_mv( R.mvx, R.mvy );                                  // analyse.c:825
-                // ---- early termination (analyse.c:839-849)
-                if( A.P.fast_pskip && subme >= 3 && R.cost - R.cost_mv < 300 * A.lambda
-                    && abs( R.mvx - pskip_x ) + abs( R.mvy - pskip_y ) <= 1
-                    && xd_pf_probe( A, fenc, fref, recon, xy, pskip, lane ) )
-                {
-                    type = X264DSP_MB_P_SKIP;
-                    out_mv = pskip;
-                    done = true;
-                }
-                else
-                {
-                    // ---- x264_me_refine_qpel (analyse.c:1187-1191; one reference: i_ref_cost = 0)
-                    xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
-                    out_mv = xd_pack_mv( R.mvx, R.mvy );
-                }
-                __syncwarp();                                   // the block description is free for the next macroblock
+                try_probe = A.P.fast_pskip && subme >= 3 && R.cost - R.cost_mv < 300 * A.lambda
+                            && abs( R.mvx - pskip_x ) + abs( R.mvy - pskip_y ) <= 1;
+                if( !try_probe )
+                    break;
             }
             if( !done )
             {
+                // ---- x264_me_refine_qpel (analyse.c:1187-1191; one reference: i_ref_cost = 0)
+                xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
+                out_mv = xd_pack_mv( R.mvx, R.mvy );
+                __syncwarp();                                   // the block description is free for the next macroblock
                 // ---- x264_macroblock_encode, inter branch: x264_mb_mc, residual, forced P_SKIP (macroblock.c:379-485)
                 const int16_t v[2] = { (int16_t)( out_mv & 0xFFFF ), (int16_t)( out_mv >> 16 ) };
-                xd_mc_mb<1>( g, fref, v, recon, xy, lane );
-                xd_mc_mb<1>( g, fref, v, recon, xy, lane + 32 );
+#pragma unroll 1
+                for( int half = 0; half < 2; half++ )
+                    xd_mc_mb<1>( g, fref, v, recon, xy, lane + 32 * half );
                 __syncwarp();
                 out_cbp = xd_residual_mb<false, false>( g, fenc, recon, A.T, levels, nnz, cbp, nullptr, nullptr, xy, lane );
                 if( !( out_cbp & 0x3f ) && out_mv == pskip )
