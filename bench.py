@@ -431,7 +431,7 @@ def pframe_oracle_check(g, check):
     prm = P(me, subme, 16, qp, 512, 1, 0)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     o.xo_p_frame(C.byref(go), ptr(slots[g.slot_bytes:]), ptr(slots[: g.slot_bytes]), ptr(wrecon), C.byref(prm), vp(lmv), None,
-                 vp(want["mb_type"]), vp(want["mv"]), vp(want["mvr"]), vp(want["levels"]), vp(want["nnz"]), vp(want["cbp"]))
+                 vp(want["mb_type"]), vp(want["mv"]), vp(want["mvr"]), None, vp(want["levels"]), vp(want["nnz"]), vp(want["cbp"]))
     ok = all(np.array_equal(got[k], want[k]) for k in want)
     lo = g.luma_origin
     a = recon[lo:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:, : g.luma_w]

@@ -419,7 +419,7 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     if( have_l0 )
         GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_pf_l0, fref->mv16x16, 4 * nmb, NULL ) );
     if( x264dsp_p_frames_dev( G.ctx, g, se, sr, glue_pred(), 1, &prm, have_lowres ? G.d_pf_lmv : NULL, have_l0 ? G.d_pf_l0 : NULL,
-                              G.d_pf_type, G.d_pf_mv, G.d_pf_mvr, G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL ) )
+                              G.d_pf_type, G.d_pf_mv, G.d_pf_mvr, NULL, G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL ) )
         return 1;                                              /* parameters the device path does not take: the host's own loop */
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_type, G.d_pf_type, nmb, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_mv, G.d_pf_mv, 4 * nmb, NULL ) );

@@ -456,6 +456,9 @@ int x264dsp_mc_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, con
  *   mv           [2] the macroblock's final vector (h->mb.cache.mv: the refined 16x16 vector, or the P_SKIP vector)
  *   mvr          [2] h->mb.mvr[0][0] = fdec->mv16x16: the 16x16 search result as later macroblocks and the next frame
  *                see it (zero for a macroblock skipped by the fast probe)
+ *   mvd          [2] the vector difference the entropy coder writes (encoder/cabac.c:278-300: mv minus the prediction of
+ *                x264_mb_predict_mv for the 16x16 partition; zero for P_SKIP); h->mb.mvd, the context the CABAC writer
+ *                keeps for the neighbours, is min(|mvd|, 66) of it.  May be NULL.  (8(f) N3: the hand-off)
  *   levels / nnz / cbp  as x264dsp_residual_frames_dev (all zero for P_SKIP)
  * n_frames independent frames run as one launch (their wavefronts interleave); frames of one sequence depend on each
  * other through the reference frame and are launched one after the other. */
@@ -471,8 +474,8 @@ typedef struct x264dsp_pframe_params
 int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
                           const uint8_t *fref_slots, uint8_t *recon_slots, int n_frames,
                           const x264dsp_pframe_params_t *params, const int16_t *lowres_mv, const int16_t *l0_mv16,
-                          int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *levels, uint8_t *nnz, int16_t *cbp,
-                          void *stream );
+                          int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz,
+                          int16_t *cbp, void *stream );
 
 /* ------------------------------------------------------------------ deblock
  * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's

@@ -83,6 +83,8 @@ typedef struct
     const int16_t *l0_mv16;         /* fref->mv16x16 */
     const uint8_t *partition;       /* h->mb.partition */
     const uint8_t *nnz;             /* h->mb.non_zero_count, 48 per macroblock */
+    const uint8_t *mvd;             /* h->mb.mvd[0]: [mb][8][2], min(|mvd|, 66) of the bottom row / right column (CABAC) */
+    int32_t keyint_max, keyint_min, scenecut, icost, pcost, pad1;
 } xref_frame_capture_t;
 
 void xref_capture_frame( void *hv, xref_frame_capture_t *o )
@@ -107,6 +109,12 @@ void xref_capture_frame( void *hv, xref_frame_capture_t *o )
     o->mv4x4 = &h->fdec->mv[0][0][0];
     o->partition = h->mb.partition;
     o->nnz = &h->mb.non_zero_count[0][0];
+    o->mvd = h->param.b_cabac ? &h->mb.mvd[0][0][0][0] : NULL;
+    o->keyint_max = h->param.i_keyint_max;
+    o->keyint_min = h->param.i_keyint_min;
+    o->scenecut = h->param.i_scenecut_threshold;
+    o->icost = h->fenc->i_cost_est[0][0];
+    o->pcost = h->fenc->i_cost_est[1][0];
     o->lowres_mv = &h->fenc->lowres_mvs[0][0][0][0];
     if( fref )
     {

@@ -153,7 +153,7 @@ int xo_encode_intra16_mb( const pixel_t *fenc_y, const pixel_t *fenc_c, pixel_t 
 /* the P-slice macroblock loop: x264_macroblock_analyse + x264_macroblock_encode for every macroblock (xo_pframe.c) */
 void xo_p_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *fref_slot, uint8_t *recon_slot,
                  const x264dsp_pframe_params_t *prm, const int16_t *lowres_mv, const int16_t *l0_mv16,
-                 int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *levels, uint8_t *nnz, int16_t *cbp );
+                 int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp );
 
 /* work counters of the last xo_me_search_batch / xo_lookahead_frame_cost call on this thread:
  * counts[0] = pixel comparisons done by SAD, counts[1] = by SATD, [2] = SAD calls, [3] = SATD calls */

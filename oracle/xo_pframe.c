@@ -97,7 +97,7 @@ static int probe_pskip( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const
 
 void xo_p_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *fref_slot, uint8_t *recon_slot,
                  const x264dsp_pframe_params_t *prm, const int16_t *lowres_mv, const int16_t *l0_mv16,
-                 int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *levels, uint8_t *nnz, int16_t *cbp )
+                 int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp )
 {
     const int W = g->mb_w, H = g->mb_h;
     const int fmv_range = prm->mv_range << 2, border = 6;
@@ -127,6 +127,8 @@ void xo_p_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_
                 nb.mv[k][1] = nxy[k] >= 0 ? mv[2 * nxy[k] + 1] : 0;
             }
             xo_predict_mv_pskip( &nb, pskip_mv );                      /* x264_macroblock_cache_load, P slices */
+            if( mvd )
+                mvd[2 * xy] = mvd[2 * xy + 1] = 0;
 
             /* x264_mb_analyse_init (analyse.c:373-397); the vertical limits change at the start of a row only */
             L.mv_min[0] = ( -( mb_x << 4 ) - 24 ) << 2;
@@ -242,6 +244,12 @@ void xo_p_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_
                 if( !( c & 0x3f ) && mv[2 * xy] == pskip_mv[0] && mv[2 * xy + 1] == pskip_mv[1] )
                     type = X264DSP_MB_P_SKIP;
                 mb_type[xy] = (int8_t)type;
+                /* what x264_cabac_mvd writes for the 16x16 partition (encoder/cabac.c:278-300) */
+                if( mvd && type == X264DSP_MB_P_L0 )
+                {
+                    mvd[2 * xy] = (int16_t)( mv[2 * xy] - mvp[0] );
+                    mvd[2 * xy + 1] = (int16_t)( mv[2 * xy + 1] - mvp[1] );
+                }
             }
         }
 }

@@ -54,6 +54,7 @@ def test_p_frames_match_oracle(pkg, ctx, w, h, n, me, subme, qp, cut):
         out = {"mb_type": torch.full((count, nmb), -1, dtype=torch.int8, device="cuda"),
                "mv": torch.zeros((count, nmb, 2), dtype=torch.int16, device="cuda"),
                "mvr": torch.zeros((count, nmb, 2), dtype=torch.int16, device="cuda"),
+               "mvd": torch.full((count, nmb, 2), 77, dtype=torch.int16, device="cuda"),
                "levels": torch.ones((count, nmb, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda"),
                "nnz": torch.ones((count, nmb, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda"),
                "cbp": torch.full((count, nmb), -1, dtype=torch.int16, device="cuda")}
@@ -61,7 +62,7 @@ def test_p_frames_match_oracle(pkg, ctx, w, h, n, me, subme, qp, cut):
         prm = pkg.PFrameParams(me, subme, 16, qp, 128, 1, 256 if l0 is not None else 0)
         ctx.p_frames(g, slots[(first + 1) * g.slot_bytes:], slots[first * g.slot_bytes:], recon, count, prm,
                      d_lmv[first:first + count].contiguous(), l0, out["mb_type"], out["mv"], out["mvr"], out["levels"],
-                     out["nnz"], out["cbp"])
+                     out["nnz"], out["cbp"], mvd=out["mvd"])
         ctx.sync()
         res = {k: v.cpu().numpy() for k, v in out.items()}
         res["recon"] = recon.cpu().numpy().reshape(count, g.slot_bytes)
@@ -69,16 +70,16 @@ def test_p_frames_match_oracle(pkg, ctx, w, h, n, me, subme, qp, cut):
 
     def oracle_run(k, l0):
         res = {"mb_type": np.zeros(nmb, np.int8), "mv": np.zeros((nmb, 2), np.int16), "mvr": np.zeros((nmb, 2), np.int16),
-               "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8), "cbp": np.zeros(nmb, np.int16)}
+               "mvd": np.zeros((nmb, 2), np.int16), "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8), "cbp": np.zeros(nmb, np.int16)}
         recon = np.zeros(g.slot_bytes, np.uint8)
         prm = OPFrameParams(me, subme, 16, qp, 128, 1, 256 if l0 is not None else 0)
         o.xo_p_frame(C.byref(go), ptr(host_slots[k + 1]), ptr(host_slots[k]), ptr(recon), C.byref(prm), vp(lmv[k]), vp(l0),
-                     vp(res["mb_type"]), vp(res["mv"]), vp(res["mvr"]), vp(res["levels"]), vp(res["nnz"]), vp(res["cbp"]))
+                     vp(res["mb_type"]), vp(res["mv"]), vp(res["mvr"]), vp(res["mvd"]), vp(res["levels"]), vp(res["nnz"]), vp(res["cbp"]))
         res["recon"] = recon
         return res
 
     def compare(got, want, tag):
-        for key in ("mb_type", "mv", "mvr", "cbp", "nnz", "levels"):
+        for key in ("mb_type", "mv", "mvr", "mvd", "cbp", "nnz", "levels"):
             if not np.array_equal(got[key], want[key]):
                 d = np.flatnonzero((got[key].reshape(nmb, -1) != want[key].reshape(nmb, -1)).any(1))
                 raise AssertionError(f"{tag}: {key} differs at macroblocks {d[:8]} ({d.size} in all): "

@@ -19,7 +19,8 @@ class Capture(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("slice_type", "qp", "poc", "ref_poc", "inv_ref_poc", "ref_is_inter", "mv_range",
                                          "b4_stride", "have_lowres_mv", "mb_count", "fast_pskip", "i_frame", "pad0")] + \
                [(n, C.c_void_p) for n in ("fenc", "fref", "fdec", "mb_type", "mvr", "cbp", "mv4x4", "lowres_mv", "l0_mv16",
-                                          "partition", "nnz")]
+                                          "partition", "nnz", "mvd")] + \
+               [(n, C.c_int32) for n in ("keyint_max", "keyint_min", "scenecut", "icost", "pcost", "pad1")]
 
 
 class PFrameParams(C.Structure):
@@ -61,6 +62,8 @@ def capture_encode(w, h, n, cut, me, subme, qp, deblock):
         d["mv4_uniform"] = all(np.array_equal(mv4[dy::4, dx:4 * g.mb_w:4].reshape(nmb, 2), d["mv"])
                                for dy in range(4) for dx in range(4))
         d["lowres_mv"] = view(c.lowres_mv, nmb * 2, np.int16) if c.have_lowres_mv else None
+        d["mvd_ctx"] = view(c.mvd, nmb * 16, np.uint8).reshape(nmb, 8, 2) if c.mvd else None
+        d.update(keyint_max=c.keyint_max, keyint_min=c.keyint_min, scenecut=c.scenecut, icost=c.icost, pcost=c.pcost)
         if c.fref:
             slot = np.zeros(g.slot_bytes, np.uint8)
             slot[: 4 * lps] = view(lib.xref_frame_ptr(c.fref, 10), 4 * lps, np.uint8)
@@ -96,13 +99,15 @@ def run_oracle_pframe(g, frames, d, me, subme):
     prm = PFrameParams(me, subme, 16, d["qp"], d["mv_range"], d["fast_pskip"],
                        (d["poc"] - d["ref_poc"]) * d["inv_ref_poc"] if d["l0_mv16"] is not None else 0)
     res = {"mb_type": np.zeros(nmb, np.int8), "mv": np.zeros((nmb, 2), np.int16), "mvr": np.zeros((nmb, 2), np.int16),
+           "mvd": np.zeros((nmb, 2), np.int16),
            "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8), "cbp": np.zeros(nmb, np.int16)}
     lm, l0 = d["lowres_mv"], d["l0_mv16"]
     o.xo_p_frame(C.byref(g), ptr(fenc), ptr(d["fref_slot"]), ptr(recon), C.byref(prm),
                  lm.ctypes.data_as(C.c_void_p) if lm is not None else None,
                  l0.ctypes.data_as(C.c_void_p) if l0 is not None else None,
                  res["mb_type"].ctypes.data_as(C.c_void_p), res["mv"].ctypes.data_as(C.c_void_p),
-                 res["mvr"].ctypes.data_as(C.c_void_p), res["levels"].ctypes.data_as(C.c_void_p),
+                 res["mvr"].ctypes.data_as(C.c_void_p), res["mvd"].ctypes.data_as(C.c_void_p),
+                 res["levels"].ctypes.data_as(C.c_void_p),
                  res["nnz"].ctypes.data_as(C.c_void_p), res["cbp"].ctypes.data_as(C.c_void_p))
     res["recon"] = recon
     return res
@@ -131,6 +136,10 @@ def test_p_frame_oracle_reproduces_the_encoder(w, h, n, cut, me, subme, qp, debl
         assert bad.size == 0, f"{tag}: type differs at macroblocks {bad[:8]}: {res['mb_type'][bad[:8]]} vs {d['mb_type'][bad[:8]]}"
         assert np.array_equal(res["mv"], d["mv"]), f"{tag}: final vectors differ at {np.flatnonzero((res['mv'] != d['mv']).any(1))[:8]}"
         assert np.array_equal(res["mvr"], d["mvr"]), f"{tag}: mvr differs at {np.flatnonzero((res['mvr'] != d['mvr']).any(1))[:8]}"
+        # the entropy coder's hand-off (8(f) N3): what x264_cabac_mvd wrote and kept as context for the neighbours
+        want_ctx = np.minimum(np.abs(res["mvd"].astype(np.int32)), 66).astype(np.uint8)
+        for k in range(7):              # bottom row (4) and right column (3) of the macroblock; the eighth entry is padding
+            assert np.array_equal(d["mvd_ctx"][:, k, :], want_ctx), f"{tag}: mvd context differs"
         coded = d["mb_type"] != 6
         assert np.array_equal(res["cbp"][coded], d["cbp"][coded]), f"{tag}: cbp differs"
         if not deblock:

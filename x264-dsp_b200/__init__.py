@@ -413,13 +413,13 @@ class Context:
                                                _dp(pred_slots), None), "x264dsp_mc_frames_part_dev")
 
     def p_frames(self, g, fenc_slots, fref_slots, recon_slots, n_frames, prm, lowres_mv, l0_mv16, mb_type, mv, mvr,
-                 levels, nnz, cbp):
+                 levels, nnz, cbp, mvd=None):
         """x264_macroblock_analyse + x264_macroblock_encode for every macroblock of n_frames independent P frames
         (x264dsp_p_frames_dev); lowres_mv / l0_mv16 may be None"""
         check(lib().x264dsp_p_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(fref_slots), _dp(recon_slots),
                                          int(n_frames), C.byref(prm), _dp(lowres_mv) if lowres_mv is not None else None,
                                          _dp(l0_mv16) if l0_mv16 is not None else None, _dp(mb_type), _dp(mv), _dp(mvr),
-                                         _dp(levels), _dp(nnz), _dp(cbp), None), "x264dsp_p_frames_dev")
+                                         _dp(mvd), _dp(levels), _dp(nnz), _dp(cbp), None), "x264dsp_p_frames_dev")
 
     def residual_frames(self, g, fenc_slots, pred_slots, n_frames, qp, levels, nnz, cbp):
         check(lib().x264dsp_residual_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),

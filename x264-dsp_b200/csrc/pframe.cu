@@ -46,7 +46,7 @@ struct xd_pf_args
     int lambda;
     const int16_t *lowres_mv, *l0_mv16;
     int8_t *mb_type;
-    int16_t *mv, *mvr, *levels;
+    int16_t *mv, *mvr, *mvd, *levels;
     uint8_t *nnz;
     int16_t *cbp;
     int32_t *progress, *ticket;
@@ -109,6 +109,7 @@ xd_pframe_kernel( xd_pf_args A )
         const size_t mb0 = (size_t)f * g.mb_count;
         int8_t *types = A.mb_type + mb0;
         uint32_t *mvs = (uint32_t *)A.mv + mb0, *mvrs = (uint32_t *)A.mvr + mb0;
+        uint32_t *mvds = A.mvd ? (uint32_t *)A.mvd + mb0 : nullptr;
         int16_t *levels = A.levels + mb0 * X264DSP_RES_LEVELS_PER_MB;
         uint8_t *nnz = A.nnz + mb0 * X264DSP_RES_NNZ_PER_MB;
         int16_t *cbp = A.cbp + mb0;
@@ -275,6 +276,13 @@ xd_pframe_kernel( xd_pf_args A )
                 types[xy] = (int8_t)type;
                 mvs[xy] = out_mv;
                 mvrs[xy] = out_mvr;
+                if( mvds )
+                {
+                    // encoder/cabac.c:284-287: the 16x16 partition's prediction is x264_mb_predict_mv_16x16's
+                    const uint32_t mvp = xd_predict_mv_16x16( nb, 0 );
+                    mvds[xy] = type == X264DSP_MB_P_SKIP ? 0u
+                             : xd_pack_mv( (int16_t)( out_mv & 0xFFFF ) - (int16_t)( mvp & 0xFFFF ), (int16_t)( out_mv >> 16 ) - (int16_t)( mvp >> 16 ) );
+                }
                 if( done )
                     cbp[xy] = 0;
             }
@@ -291,8 +299,8 @@ xd_pframe_kernel( xd_pf_args A )
 extern "C" int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
                                      const uint8_t *fref_slots, uint8_t *recon_slots, int n_frames,
                                      const x264dsp_pframe_params_t *params, const int16_t *lowres_mv, const int16_t *l0_mv16,
-                                     int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *levels, uint8_t *nnz, int16_t *cbp,
-                                     void *stream )
+                                     int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz,
+                                     int16_t *cbp, void *stream )
 {
     if( !ctx || !g || !fenc_slots || !fref_slots || !recon_slots || !params || !mb_type || !mv || !mvr || !levels || !nnz
         || !cbp || n_frames <= 0 || n_frames > 65535 )
@@ -318,6 +326,7 @@ extern "C" int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g
     A.mb_type = mb_type;
     A.mv = mv;
     A.mvr = mvr;
+    A.mvd = mvd;
     A.levels = levels;
     A.nnz = nnz;
     A.cbp = cbp;
