@@ -435,6 +435,26 @@ int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const ui
 int x264dsp_mc_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slots,
                                 int n_frames, const int16_t *mv8x8, uint8_t *pred_slots, void *stream );
 
+/* ------------------------------------------------------------------ slice types, GOPs and their sharding (8(f) N4)
+ * x264_slicetype_analyse + scenecut + the key-frame rules of x264_slicetype_decide (encoder/slicetype.c:322-435, 508-537;
+ * no B frames, closed GOPs) for a WHOLE sequence at once: icost[k] / pcost[k] are frame k's intra estimate and its inter
+ * estimate against frame k-1 (sums[X264DSP_LA_COST_INTRA] / [X264DSP_LA_COST_INTER] of the lookahead; pcost[0] is not read).
+ * Both come from source frames only, so one lookahead pass decides every type: types[k] = X264DSP_TYPE_IDR / _I / _P
+ * (the reference's X264_TYPE_* values, common/x264.h).  Host code, no device work. */
+enum { X264DSP_TYPE_IDR = 1, X264DSP_TYPE_I = 2, X264DSP_TYPE_P = 3 };
+typedef struct x264dsp_gop_params
+{
+    int32_t keyint_max, keyint_min;        /* h->param.i_keyint_max / i_keyint_min (after x264's validation) */
+    int32_t scenecut_threshold;            /* h->param.i_scenecut_threshold, 0 = off */
+} x264dsp_gop_params_t;
+int x264dsp_slicetype_decide( int n_frames, const int32_t *icost, const int32_t *pcost,
+                              const x264dsp_gop_params_t *p, uint8_t *types );
+/* every I / IDR frame opens a GOP: gop_first[i], gop_count[i] for i < *n_gops (arrays of n_frames entries suffice) */
+int x264dsp_gop_ranges( int n_frames, const uint8_t *types, int32_t *gop_first, int32_t *gop_count, int *n_gops );
+/* the GOPs rank `rank` of `world` encodes: whole GOPs, in order, contiguous, balanced by frame count.  With one reference
+ * frame nothing reaches across an I frame, so the ranks need no exchange until the bitstreams are concatenated. */
+int x264dsp_gop_shard( int n_gops, const int32_t *gop_count, int rank, int world, int *first_gop, int *count );
+
 /* ------------------------------------------------------------------ P-slice analysis + coding (8(f) N2)
  * x264_macroblock_analyse for a P slice (encoder/analyse.c:1059-1232: x264_mb_analyse_init 327-420, the fast P_SKIP
  * probe, x264_mb_analyse_inter_p16x16 787-860 with its early P_SKIP exit, x264_me_refine_qpel) followed by

@@ -46,6 +46,15 @@ void *xref_open( int width, int height, int me_method, int subme, int me_range, 
     return x264_encoder_open( &param );
 }
 
+/* key-frame parameters of the next xref_open_ex (0 = the reference's defaults) */
+static int xref_open_keyint_max = 0, xref_open_keyint_min = 0, xref_open_scenecut = 0;
+void xref_set_keyint( int keyint_max, int keyint_min, int scenecut )
+{
+    xref_open_keyint_max = keyint_max;
+    xref_open_keyint_min = keyint_min;
+    xref_open_scenecut = scenecut;
+}
+
 /* the same with the in-loop deblocking filter switched on or off (a frame's reconstruction is then final when its last
  * macroblock row is coded, which is what the P-slice analysis pin compares) */
 void *xref_open_ex( int width, int height, int me_method, int subme, int me_range, int qp, int psub16x16, int deblock )
@@ -65,6 +74,12 @@ void *xref_open_ex( int width, int height, int me_method, int subme, int me_rang
     param.rc.i_rc_method = X264_RC_CQP;
     param.rc.i_qp_constant = qp;
     param.b_deblocking_filter = deblock;
+    if( xref_open_keyint_max > 0 )
+    {
+        param.i_keyint_max = xref_open_keyint_max;
+        param.i_keyint_min = xref_open_keyint_min;
+        param.i_scenecut_threshold = xref_open_scenecut;
+    }
     return x264_encoder_open( &param );
 }
 
@@ -73,7 +88,7 @@ void *xref_open_ex( int width, int height, int me_method, int subme, int me_rang
 typedef struct
 {
     int32_t slice_type, qp, poc, ref_poc, inv_ref_poc, ref_is_inter, mv_range, b4_stride, have_lowres_mv, mb_count;
-    int32_t fast_pskip, i_frame, pad0;
+    int32_t fast_pskip, i_frame, frame_type;      /* frame_type: fenc->i_type (X264_TYPE_IDR / I / P) */
     void *fenc, *fref, *fdec;
     const int8_t *mb_type;          /* h->mb.type */
     const int16_t *mvr;             /* h->mb.mvr[0][0] = fdec->mv16x16 */
@@ -100,6 +115,7 @@ void xref_capture_frame( void *hv, xref_frame_capture_t *o )
     o->mb_count = h->mb.i_mb_count;
     o->fast_pskip = h->param.analyse.b_fast_pskip;
     o->i_frame = h->fenc->i_frame;
+    o->frame_type = h->fenc->i_type;
     o->fenc = h->fenc;
     o->fdec = h->fdec;
     o->fref = fref;

@@ -17,7 +17,7 @@ OBS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 
 class Capture(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("slice_type", "qp", "poc", "ref_poc", "inv_ref_poc", "ref_is_inter", "mv_range",
-                                         "b4_stride", "have_lowres_mv", "mb_count", "fast_pskip", "i_frame", "pad0")] + \
+                                         "b4_stride", "have_lowres_mv", "mb_count", "fast_pskip", "i_frame", "frame_type")] + \
                [(n, C.c_void_p) for n in ("fenc", "fref", "fdec", "mb_type", "mvr", "cbp", "mv4x4", "lowres_mv", "l0_mv16",
                                           "partition", "nnz", "mvd")] + \
                [(n, C.c_int32) for n in ("keyint_max", "keyint_min", "scenecut", "icost", "pcost", "pad1")]
@@ -32,7 +32,7 @@ def view(addr, count, dtype):
     return np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(dtype).copy()
 
 
-def capture_encode(w, h, n, cut, me, subme, qp, deblock):
+def capture_encode(w, h, n, cut, me, subme, qp, deblock, keyint=None, light=False):
     """encode the clip with the reference; returns (geometry, clip frames, [captured frame dicts])"""
     lib = cc.ref()
     assert lib is not None, "oracle/_ref/libx264ref.so not built"
@@ -42,7 +42,9 @@ def capture_encode(w, h, n, cut, me, subme, qp, deblock):
     g = cc.oracle_geom(w, h)
     frames = [cc.synth_frame(w, h, i, cut_frame=cut) for i in range(n)]
     clip = np.concatenate(frames)
+    lib.xref_set_keyint(*(keyint or (0, 0, 0)))
     enc = C.c_void_p(lib.xref_open_ex(w, h, me, subme, 16, qp, 0, deblock))
+    lib.xref_set_keyint(0, 0, 0)
     assert enc.value
     got = []
     lps, cps = g.luma_plane_size, g.chroma_plane_size
@@ -53,7 +55,11 @@ def capture_encode(w, h, n, cut, me, subme, qp, deblock):
         lib.xref_capture_frame(C.c_void_p(hv), C.byref(c))
         nmb = c.mb_count
         d = {k: getattr(c, k) for k in ("slice_type", "qp", "poc", "ref_poc", "inv_ref_poc", "ref_is_inter", "mv_range",
-                                        "have_lowres_mv", "fast_pskip", "i_frame")}
+                                        "have_lowres_mv", "fast_pskip", "i_frame", "frame_type")}
+        d.update(keyint_max=c.keyint_max, keyint_min=c.keyint_min, scenecut=c.scenecut, icost=c.icost, pcost=c.pcost)
+        if light:                       # frame-level facts only (tests/test_gop.py)
+            got.append(d)
+            return
         d["mb_type"] = view(c.mb_type, nmb, np.int8)
         d["cbp"] = view(c.cbp, nmb, np.int16)
         d["mvr"] = view(c.mvr, nmb * 2, np.int16).reshape(nmb, 2)

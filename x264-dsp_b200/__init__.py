@@ -157,6 +157,44 @@ def frame_range(n_frames, rank, world):
     return first.value, count.value, bool(prev.value)
 
 
+class GopParams(C.Structure):
+    """x264dsp_gop_params_t"""
+    _fields_ = [("keyint_max", C.c_int32), ("keyint_min", C.c_int32), ("scenecut_threshold", C.c_int32)]
+
+
+TYPE_IDR, TYPE_I, TYPE_P = 1, 2, 3
+
+
+def slicetype_decide(icost, pcost, keyint_max, keyint_min, scenecut_threshold):
+    """frame types of a whole sequence from the lookahead's frame costs (x264dsp_slicetype_decide)"""
+    ic = np.ascontiguousarray(icost, np.int32)
+    pc = np.ascontiguousarray(pcost, np.int32)
+    types = np.zeros(ic.size, np.uint8)
+    prm = GopParams(keyint_max, keyint_min, scenecut_threshold)
+    check(lib().x264dsp_slicetype_decide(int(ic.size), _hp(ic, C.c_int32), _hp(pc, C.c_int32), C.byref(prm), _hp(types)),
+          "x264dsp_slicetype_decide")
+    return types
+
+
+def gop_ranges(types):
+    """[(first frame, frame count)] of every GOP (x264dsp_gop_ranges)"""
+    t = np.ascontiguousarray(types, np.uint8)
+    first, count = np.zeros(max(t.size, 1), np.int32), np.zeros(max(t.size, 1), np.int32)
+    n = C.c_int(0)
+    check(lib().x264dsp_gop_ranges(int(t.size), _hp(t), _hp(first, C.c_int32), _hp(count, C.c_int32), C.byref(n)),
+          "x264dsp_gop_ranges")
+    return [(int(first[i]), int(count[i])) for i in range(n.value)]
+
+
+def gop_shard(gops, rank, world):
+    """the GOPs (a slice of `gops`) rank `rank` of `world` encodes (x264dsp_gop_shard)"""
+    count = np.array([c for _, c in gops], np.int32)
+    first, n = C.c_int(0), C.c_int(0)
+    check(lib().x264dsp_gop_shard(len(gops), _hp(count, C.c_int32) if len(gops) else None, int(rank), int(world),
+                                  C.byref(first), C.byref(n)), "x264dsp_gop_shard")
+    return gops[first.value: first.value + n.value]
+
+
 def lookahead_sharded(analyse, luma, rank, world, gather=None):
     """Frame-range sharded lookahead pass of ONE sequence.
 
