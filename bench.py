@@ -414,6 +414,30 @@ def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3)
     return out[0], out[1], float((types == pkg.MB_P_SKIP).mean()), check
 
 
+def pframe_e2e(pkg, ctx, g, w, h, n_frames, me, subme, qp=26, reps=3):
+    """the same through the host-memory door (x264dsp_p_frames_host): pinned pictures in; types, vectors, levels, nnz, cbp and
+    the reconstructed pictures out; every copy inside the timed region.  Returns (seconds per call, h2d bytes, d2h bytes)"""
+    nmb = g.mb_count
+    pics = ctx.pinned_empty((n_frames + 1, w * h * 3 // 2), np.uint8)
+    for i in range(n_frames + 1):
+        pics[i] = pkg.synth_frame(w, h, i % 25)
+    o = {"mb_type": ctx.pinned_empty((n_frames, nmb), np.int8), "mv": ctx.pinned_empty((n_frames, nmb, 2), np.int16),
+         "mvr": ctx.pinned_empty((n_frames, nmb, 2), np.int16), "mvd": ctx.pinned_empty((n_frames, nmb, 2), np.int16),
+         "levels": ctx.pinned_empty((n_frames, nmb, pkg.RES_LEVELS_PER_MB), np.int16),
+         "nnz": ctx.pinned_empty((n_frames, nmb, pkg.RES_NNZ_PER_MB), np.uint8), "cbp": ctx.pinned_empty((n_frames, nmb), np.int16)}
+    recon = ctx.pinned_empty((n_frames, w * h * 3 // 2), np.uint8)
+    prm = pkg.PFrameParams(me, subme, 16, qp, 512, 1, 0)
+
+    def run():
+        ctx.p_frames_host(w, h, n_frames, pics, prm, o["mb_type"], o["mv"], o["mvr"], o["mvd"], o["levels"], o["nnz"], o["cbp"], recon)
+    run()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run()
+    dt = (time.perf_counter() - t0) / reps
+    return dt, int(pics.nbytes), int(sum(a.nbytes for a in o.values()) + recon.nbytes)
+
+
 def pframe_oracle_check(g, check):
     """frame 0 of the P-frame measurement against the CPU oracle's xo_p_frame (pinned to the running reference encoder)"""
     import cpu_checkers as cc
@@ -1048,9 +1072,10 @@ def main():
         pf = {}
         for name, (pme, psub) in (("dia_subme1", (0, 1)), ("hex_subme5", (1, 5))):
             pf[name] = pframe_measure(pkg, ctx, torch, g, w, h, PF_FRAMES, pme, psub)
-        sec += [pf["dia_subme1"][0], pf["hex_subme5"][0]]
+        pf_e2e = pframe_e2e(pkg, ctx, g, w, h, 96, 0, 1)
+        sec += [pf["dia_subme1"][0], pf["hex_subme5"][0], pf_e2e[0]]
     else:
-        sec += [0.0, 0.0]
+        sec += [0.0, 0.0, 0.0]
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3] + sec + [copy_s * 1e3], dtype=torch.float64, device="cuda")
@@ -1059,7 +1084,8 @@ def main():
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     me_dev_ms_max, me_e2e_s_max, rc_dev_ms_max, rc_e2e_s_max = (float(x) for x in t[2:6])
     pf_ms_max = (float(t[6]), float(t[7]))
-    copy_ms = float(t[8])
+    pf_e2e_s_max = float(t[8])
+    copy_ms = float(t[9])
 
     if rank == 0:
         frames_total = world * n * args.steps
@@ -1241,6 +1267,11 @@ def main():
                     ent["cpu_baseline"] = cb
                 pfl["settings"][name] = ent
             pfl["value"] = pfl["settings"]["dia_subme1"]["value"]
+            pfl["e2e"] = {"value": world * 96 / pf_e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": pf_e2e[1],
+                          "d2h_bytes_per_step": pf_e2e[2], "setting": "dia_subme1, 96 frames per call",
+                          "api": "x264dsp_p_frames_host (pinned I420 pictures in; types, vectors, mvd, levels, nnz, cbp and the "
+                                 "reconstructed I420 pictures out; reference planes, lowres planes and the lookahead of every pair "
+                                 "built on the device inside the call)"}
             line["pframe"] = pfl
         print(json.dumps(line))
     ctx.close()

@@ -497,6 +497,14 @@ int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uin
                           int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz,
                           int16_t *cbp, void *stream );
 
+/* The same from HOST memory: i420 holds n_frames + 1 planar pictures, frame f + 1 is coded against picture f (the source
+ * picture standing in for the reconstruction, as in x264dsp_recon_frames_host).  The reference planes (border, half-pel),
+ * the half-resolution planes and the lookahead's vectors of every pair are built on the device; outputs are host arrays laid
+ * out like the _dev ones, recon_i420 receives the n_frames reconstructions as planar I420.  All copies are inside the call. */
+int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                           const x264dsp_pframe_params_t *params, int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd,
+                           int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 );
+
 /* ------------------------------------------------------------------ deblock
  * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's
  * slice-QP rule.  mb_type / partition / cbp: per-MB; bs: [mb][2][8][4] boundary strengths.

@@ -78,3 +78,54 @@ def test_recon_frames_host(pkg, ctx, w, h, n, qp):
         c = pred[go.slot_chroma_off + go.chroma_origin:][: (go.luma_h // 2) * go.chroma_stride].reshape(go.luma_h // 2, go.chroma_stride)[: h // 2, :w]
         want = np.concatenate([y.ravel(), c[:, 0::2].ravel(), c[:, 1::2].ravel()])
         assert np.array_equal(rec[f], want), f"frame {f}: deblocked reconstruction ({np.count_nonzero(rec[f] != want)} bytes differ)"
+
+
+@pytest.mark.parametrize("w,h,n,me,subme,qp", [(352, 288, 9, 0, 1, 28), (208, 160, 17, 1, 4, 26)])
+def test_p_frames_host_matches_oracle(pkg, ctx, w, h, n, me, subme, qp):
+    """x264dsp_p_frames_host: pictures in host memory in, the coded P frames out -- reference planes, half-resolution planes,
+    the lookahead's vectors and the macroblock loop all on the device, several stream groups -- against the oracle's
+    xo_p_frame fed with the oracle's own planes and lookahead vectors"""
+    import ctypes as C
+    from cpu_checkers import ptr, i16p, i32p
+    o = cc.oracle()
+    go = cc.oracle_geom(w, h)
+    g = pkg.geometry(w, h)
+    nmb = g.mb_count
+    pics = np.stack([pkg.synth_frame(w, h, i) for i in range(n + 1)])
+    out = {"mb_type": np.zeros((n, nmb), np.int8), "mv": np.zeros((n, nmb, 2), np.int16), "mvr": np.zeros((n, nmb, 2), np.int16),
+           "mvd": np.zeros((n, nmb, 2), np.int16), "levels": np.zeros((n, nmb, pkg.RES_LEVELS_PER_MB), np.int16),
+           "nnz": np.zeros((n, nmb, pkg.RES_NNZ_PER_MB), np.uint8), "cbp": np.zeros((n, nmb), np.int16)}
+    recon = np.zeros((n, w * h * 3 // 2), np.uint8)
+    prm = pkg.PFrameParams(me, subme, 16, qp, 128, 1, 0)
+    ctx.p_frames_host(w, h, n, pics, prm, out["mb_type"], out["mv"], out["mvr"], out["mvd"], out["levels"], out["nnz"],
+                      out["cbp"], recon)
+
+    class P(C.Structure):
+        _fields_ = [(k, C.c_int32) for k in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale")]
+    slots = [np.zeros(g.slot_bytes, np.uint8) for _ in range(n + 1)]
+    for i in range(n + 1):
+        o.xo_frame_load_i420(C.byref(go), ptr(pics[i]), ptr(slots[i]))
+        o.xo_frame_expand_border(C.byref(go), ptr(slots[i]))
+        o.xo_frame_filter(C.byref(go), ptr(slots[i]))
+        o.xo_frame_init_lowres(C.byref(go), ptr(slots[i]))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for k in range(n):
+        lmv = np.zeros((nmb, 2), np.int16)
+        lc = np.zeros(nmb, np.int32)
+        ls = np.zeros(8, np.int32)
+        o.xo_lookahead_frame_cost(C.byref(go), ptr(slots[k + 1]), ptr(slots[k]), 0, ptr(lmv, i16p), ptr(lc, i32p), ptr(ls, i32p), None)
+        want = {"mb_type": np.zeros(nmb, np.int8), "mv": np.zeros((nmb, 2), np.int16), "mvr": np.zeros((nmb, 2), np.int16),
+                "mvd": np.zeros((nmb, 2), np.int16), "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8),
+                "cbp": np.zeros(nmb, np.int16)}
+        wrec = np.zeros(g.slot_bytes, np.uint8)
+        p = P(me, subme, 16, qp, 128, 1, 0)
+        o.xo_p_frame(C.byref(go), ptr(slots[k + 1]), ptr(slots[k]), ptr(wrec), C.byref(p), vp(lmv), None, vp(want["mb_type"]),
+                     vp(want["mv"]), vp(want["mvr"]), vp(want["mvd"]), vp(want["levels"]), vp(want["nnz"]), vp(want["cbp"]))
+        for key in want:
+            assert np.array_equal(out[key][k], want[key]), f"frame {k + 1}: {key} differs"
+        wy = wrec[g.luma_origin:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:h, :w]
+        assert np.array_equal(recon[k][: w * h].reshape(h, w), wy), f"frame {k + 1}: luma reconstruction differs"
+        co = g.slot_chroma_off + g.chroma_origin
+        wc = wrec[co:][: (g.luma_h // 2) * g.chroma_stride].reshape(g.luma_h // 2, g.chroma_stride)[: h // 2, :w]
+        assert np.array_equal(recon[k][w * h: w * h + w * h // 4].reshape(h // 2, w // 2), wc[:, 0::2]), f"frame {k + 1}: U differs"
+        assert np.array_equal(recon[k][w * h + w * h // 4:].reshape(h // 2, w // 2), wc[:, 1::2]), f"frame {k + 1}: V differs"

@@ -459,6 +459,14 @@ class Context:
                                          _dp(l0_mv16) if l0_mv16 is not None else None, _dp(mb_type), _dp(mv), _dp(mvr),
                                          _dp(mvd), _dp(levels), _dp(nnz), _dp(cbp), None), "x264dsp_p_frames_dev")
 
+    def p_frames_host(self, w, h, n_frames, i420, prm, mb_type, mv, mvr, mvd, levels, nnz, cbp, recon_i420):
+        """x264dsp_p_frames_host: numpy (ideally pinned) arrays in and out"""
+        check(lib().x264dsp_p_frames_host(self._h, int(w), int(h), int(n_frames), _hp(i420), C.byref(prm),
+                                          mb_type.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p),
+                                          mvr.ctypes.data_as(C.c_void_p), mvd.ctypes.data_as(C.c_void_p) if mvd is not None else None,
+                                          levels.ctypes.data_as(C.c_void_p), _hp(nnz), cbp.ctypes.data_as(C.c_void_p),
+                                          _hp(recon_i420)), "x264dsp_p_frames_host")
+
     def residual_frames(self, g, fenc_slots, pred_slots, n_frames, qp, levels, nnz, cbp):
         check(lib().x264dsp_residual_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
                                                 int(qp), _dp(levels), _dp(nnz), _dp(cbp), None),

@@ -239,3 +239,115 @@ drain:
     ctx->scratch_busy[XD_SCRATCH_DEBLOCK] = 0;
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// the P-slice macroblock loop from host memory (SURVEY 8(f) N2 as a door): n_frames independent P frames, frame f + 1 coded
+// against picture f.  Everything an encoder would have on the device is built there -- reference planes (border, half-pel),
+// half-resolution planes, the lookahead's vectors of each pair (the search's first candidate) -- then x264dsp_p_frames_dev;
+// types, vectors, mvr, mvd, levels, nnz, cbp and the reconstruction (planar I420) come back.  All copies are inside the call;
+// groups of frames run on separate streams (their wavefronts queue behind each other, their copies overlap).
+extern "C" int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                                       const x264dsp_pframe_params_t *params, int8_t *mb_type, int16_t *mv, int16_t *mvr,
+                                       int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 )
+{
+    if( !ctx || !i420 || !params || !mb_type || !mv || !mvr || !levels || !nnz || !cbp || !recon_i420 || n_frames <= 0 )
+        return X264DSP_E_ARG;
+    x264dsp_geom_t g;
+    int rc = x264dsp_geometry( width, height, &g );
+    if( rc )
+        return rc;
+    if( g.mb_w < 3 || g.mb_h < 3 )
+        return X264DSP_E_ARG;
+    const size_t pic = (size_t)width * height * 3 / 2, nmb = g.mb_count;
+    int groups = n_frames / 8;
+    if( groups < 1 ) groups = 1;
+    if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
+    const size_t per_mb = 1 + 4 * 2 * sizeof( int16_t ) + X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ) + X264DSP_RES_NNZ_PER_MB
+                        + sizeof( int16_t ) + 4 + X264DSP_LA_SUMS;
+    const size_t side_bytes = ( (size_t)n_frames * nmb * per_mb + (size_t)n_frames * 64 + 8192 ) & ~(size_t)255;
+    const size_t need_slots = (size_t)( 2 * n_frames + groups ) * g.slot_bytes;
+    const size_t need_pics = (size_t)( n_frames + groups ) * pic + (size_t)n_frames * pic;
+    XD_CHECK( cudaSetDevice( ctx->device ) );
+    if( ctx->stage_dev_cap < need_pics || ctx->clip_slots_cap < need_slots || ctx->me_blocks_cap < side_bytes )
+        XD_CHECK( cudaDeviceSynchronize() );
+    if( ( rc = xd_reserve_dev( (void **)&ctx->stage_dev, &ctx->stage_dev_cap, need_pics ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->clip_slots, &ctx->clip_slots_cap, need_slots ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->me_blocks, &ctx->me_blocks_cap, side_bytes ) ) ) return rc;
+    const size_t N = (size_t)n_frames * nmb;
+    uint8_t *d_side = ctx->me_blocks;
+    int16_t *d_lv = (int16_t *)d_side;      d_side += N * X264DSP_RES_LEVELS_PER_MB * 2;
+    int16_t *d_mv = (int16_t *)d_side;      d_side += N * 4;
+    int16_t *d_mvr = (int16_t *)d_side;     d_side += N * 4;
+    int16_t *d_mvd = (int16_t *)d_side;     d_side += N * 4;
+    int16_t *d_lmv = (int16_t *)d_side;     d_side += N * 4;
+    int32_t *d_lc = (int32_t *)d_side;      d_side += N * 4;
+    int32_t *d_ls = (int32_t *)d_side;      d_side += ( (size_t)n_frames * X264DSP_LA_SUMS * 4 + 15 ) & ~(size_t)15;
+    int16_t *d_cbp = (int16_t *)d_side;     d_side += ( N * 2 + 15 ) & ~(size_t)15;
+    uint8_t *d_nz = d_side;                 d_side += ( N * X264DSP_RES_NNZ_PER_MB + 15 ) & ~(size_t)15;
+    int8_t *d_type = (int8_t *)d_side;
+
+    int used = 0;
+    size_t slot_cursor = 0, pic_cursor = 0;
+    uint8_t *d_out_pics = ctx->stage_dev + (size_t)( n_frames + groups ) * pic;
+    int32_t *idx = (int32_t *)malloc( ( (size_t)n_frames + 1 ) * ( 2 * sizeof( int32_t ) + 1 ) );
+    if( !idx )
+        return X264DSP_E_NOMEM;
+    for( int gi = 0; gi < groups && !rc; gi++ )
+    {
+        const int f0 = (int)( (int64_t)n_frames * gi / groups ), f1 = (int)( (int64_t)n_frames * ( gi + 1 ) / groups );
+        const int nf = f1 - f0;
+        if( nf <= 0 )
+            continue;
+        cudaStream_t st = ctx->aux[gi];
+        used = gi + 1;
+        uint8_t *d_pics = ctx->stage_dev + pic_cursor;           pic_cursor += (size_t)( nf + 1 ) * pic;
+        uint8_t *d_src = ctx->clip_slots + slot_cursor;           slot_cursor += (size_t)( nf + 1 ) * g.slot_bytes;
+        uint8_t *d_rec = ctx->clip_slots + slot_cursor;           slot_cursor += (size_t)nf * g.slot_bytes;
+        const size_t m0 = (size_t)f0 * nmb, mn = (size_t)nf * nmb;
+        XH_CHECK( cudaMemcpyAsync( d_pics, i420 + (size_t)f0 * pic, (size_t)( nf + 1 ) * pic, cudaMemcpyHostToDevice, st ) );
+        XH_RC( x264dsp_frame_load_i420_dev( ctx, &g, d_pics, d_src, nf + 1, st ) );
+        XH_RC( x264dsp_frame_expand_border_dev( ctx, &g, d_src, nf + 1, st ) );
+        XH_RC( x264dsp_frame_filter_dev( ctx, &g, d_src, nf, st ) );                 // reference frames only
+        XH_RC( x264dsp_frame_init_lowres_dev( ctx, &g, d_src, nf + 1, st ) );
+        {
+            // the lookahead of every pair of the group: frame k + 1 against frame k, no intra estimate
+            int32_t *b = idx, *p0 = idx + nf;
+            uint8_t *wi = (uint8_t *)( p0 + nf );
+            for( int k = 0; k < nf; k++ )
+            {
+                b[k] = k + 1;
+                p0[k] = k;
+                wi[k] = 0;
+            }
+            XH_RC( x264dsp_lookahead_frame_cost_dev( ctx, &g, d_src, nf, b, p0, wi, d_lmv + m0 * 2, d_lc + m0,
+                                                     d_ls + (size_t)f0 * X264DSP_LA_SUMS, NULL, st ) );
+        }
+        XH_RC( x264dsp_p_frames_dev( ctx, &g, d_src + g.slot_bytes, d_src, d_rec, nf, params, d_lmv + m0 * 2, NULL, d_type + m0,
+                                     d_mv + m0 * 2, d_mvr + m0 * 2, d_mvd + m0 * 2, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
+                                     d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, st ) );
+        XH_RC( x264dsp_frame_store_i420_dev( ctx, &g, d_rec, d_out_pics + (size_t)f0 * pic, nf, st ) );
+        XH_CHECK( cudaMemcpyAsync( mb_type + m0, d_type + m0, mn, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( mv + m0 * 2, d_mv + m0 * 2, mn * 4, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( mvr + m0 * 2, d_mvr + m0 * 2, mn * 4, cudaMemcpyDeviceToHost, st ) );
+        if( mvd )
+            XH_CHECK( cudaMemcpyAsync( mvd + m0 * 2, d_mvd + m0 * 2, mn * 4, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( levels + m0 * X264DSP_RES_LEVELS_PER_MB, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
+                                   mn * X264DSP_RES_LEVELS_PER_MB * 2, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( nnz + m0 * X264DSP_RES_NNZ_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB, mn * X264DSP_RES_NNZ_PER_MB,
+                                   cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( cbp + m0, d_cbp + m0, mn * 2, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( recon_i420 + (size_t)f0 * pic, d_out_pics + (size_t)f0 * pic, (size_t)nf * pic,
+                                   cudaMemcpyDeviceToHost, st ) );
+    }
+drain:
+    for( int i = 0; i < used; i++ )
+    {
+        const cudaError_t e = cudaStreamSynchronize( ctx->aux[i] );
+        if( e != cudaSuccess && !rc )
+            rc = (int)e;
+    }
+    free( idx );
+    ctx->scratch_busy[XD_SCRATCH_DEBLOCK] = 0;
+    ctx->scratch_busy[XD_SCRATCH_LOOKAHEAD] = 0;
+    return rc;
+}
