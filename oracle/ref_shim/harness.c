@@ -100,6 +100,8 @@ typedef struct
     const uint8_t *nnz;             /* h->mb.non_zero_count, 48 per macroblock */
     const uint8_t *mvd;             /* h->mb.mvd[0]: [mb][8][2], min(|mvd|, 66) of the bottom row / right column (CABAC) */
     int32_t keyint_max, keyint_min, scenecut, icost, pcost, pad1;
+    const int8_t *i4_edge_modes;    /* h->mb.intra4x4_pred_mode: [mb][8] = blocks 10 11 14 15 | 5 7 13 | pad */
+    const int8_t *chroma_pred_mode; /* h->mb.chroma_pred_mode (CABAC) */
 } xref_frame_capture_t;
 
 void xref_capture_frame( void *hv, xref_frame_capture_t *o )
@@ -126,6 +128,8 @@ void xref_capture_frame( void *hv, xref_frame_capture_t *o )
     o->partition = h->mb.partition;
     o->nnz = &h->mb.non_zero_count[0][0];
     o->mvd = h->param.b_cabac ? &h->mb.mvd[0][0][0][0] : NULL;
+    o->i4_edge_modes = &h->mb.intra4x4_pred_mode[0][0];
+    o->chroma_pred_mode = h->mb.chroma_pred_mode;
     o->keyint_max = h->param.i_keyint_max;
     o->keyint_min = h->param.i_keyint_min;
     o->scenecut = h->param.i_scenecut_threshold;

@@ -155,6 +155,13 @@ void xo_p_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_
                  const x264dsp_pframe_params_t *prm, const int16_t *lowres_mv, const int16_t *l0_mv16,
                  int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp );
 
+/* the I-slice macroblock loop: intra analysis + coding of every macroblock (xo_iframe.c) */
+void xo_predict_16x16( int mode, pixel_t *src );
+void xo_predict_chroma( int mode, pixel_t *src );
+void xo_i_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, uint8_t *recon_slot, int qp, int8_t *mb_type,
+                 uint8_t *mode16, uint8_t *chroma_mode, uint8_t *modes4, int16_t *levels, int16_t *luma_dc, uint8_t *nnz,
+                 int16_t *cbp );
+
 /* work counters of the last xo_me_search_batch / xo_lookahead_frame_cost call on this thread:
  * counts[0] = pixel comparisons done by SAD, counts[1] = by SATD, [2] = SAD calls, [3] = SATD calls */
 void xo_work_counters( int64_t counts[4], int reset );

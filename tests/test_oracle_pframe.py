@@ -20,7 +20,8 @@ class Capture(C.Structure):
                                          "b4_stride", "have_lowres_mv", "mb_count", "fast_pskip", "i_frame", "frame_type")] + \
                [(n, C.c_void_p) for n in ("fenc", "fref", "fdec", "mb_type", "mvr", "cbp", "mv4x4", "lowres_mv", "l0_mv16",
                                           "partition", "nnz", "mvd")] + \
-               [(n, C.c_int32) for n in ("keyint_max", "keyint_min", "scenecut", "icost", "pcost", "pad1")]
+               [(n, C.c_int32) for n in ("keyint_max", "keyint_min", "scenecut", "icost", "pcost", "pad1")] + \
+               [(n, C.c_void_p) for n in ("i4_edge_modes", "chroma_pred_mode")]
 
 
 class PFrameParams(C.Structure):
@@ -61,6 +62,8 @@ def capture_encode(w, h, n, cut, me, subme, qp, deblock, keyint=None, light=Fals
             got.append(d)
             return
         d["mb_type"] = view(c.mb_type, nmb, np.int8)
+        d["i4_edge_modes"] = view(c.i4_edge_modes, nmb * 8, np.int8).reshape(nmb, 8)
+        d["chroma_pred_mode"] = view(c.chroma_pred_mode, nmb, np.int8)
         d["cbp"] = view(c.cbp, nmb, np.int16)
         d["mvr"] = view(c.mvr, nmb * 2, np.int16).reshape(nmb, 2)
         mv4 = view(c.mv4x4, c.b4_stride * g.mb_h * 4 * 2, np.int16).reshape(g.mb_h * 4, c.b4_stride, 2)
