@@ -435,6 +435,23 @@ int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const ui
 int x264dsp_mc_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fref_slots,
                                 int n_frames, const int16_t *mv8x8, uint8_t *pred_slots, void *stream );
 
+/* ------------------------------------------------------------------ I-slice analysis + coding (8(f) N1)
+ * The I-slice branch of x264_macroblock_analyse (encoder/analyse.c:1079-1088: x264_mb_analyse_intra 565-763 -- the 16x16 modes,
+ * the sixteen 4x4 blocks with their mode lists, shortcuts, early exits and in-place coding --, the I16x16 / I4x4 decision,
+ * x264_mb_analyse_intra_chroma 509-563) followed by x264_macroblock_encode's intra branches, for EVERY macroblock of a frame.
+ * A macroblock predicts from the reconstruction of its left, top-left, top and top-right neighbours and from the 4x4 modes
+ * next to it, so the frame is a wavefront (row y may do column x once row y-1 has finished column x+1).  analyse.intra =
+ * I4x4 (no 8x8 transform: the reference's build), SATD metric (every subme the reference accepts).
+ *   recon_slots  n_frames output slots: luma plane N and chroma receive the reconstruction
+ *   mb_type      [frame][mb] 0 = I_4x4, 2 = I_16x16 (the reference's enum values)
+ *   mode16 / chroma_mode  [frame][mb] I_PRED_16x16_* / I_PRED_CHROMA_* as chosen (common/predict.h; mode16 is what an
+ *                I_16x16 macroblock codes, the best 16x16 mode otherwise)
+ *   modes4       [frame][mb][16] I_PRED_4x4_* in coding order (I_16x16 macroblocks: all 2 = DC, as their neighbours see them)
+ *   levels / luma_dc / nnz / cbp  as x264dsp_residual_frames_typed_dev */
+int x264dsp_i_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots, uint8_t *recon_slots,
+                          int n_frames, int qp, int8_t *mb_type, uint8_t *mode16, uint8_t *chroma_mode, uint8_t *modes4,
+                          int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int16_t *cbp, void *stream );
+
 /* ------------------------------------------------------------------ slice types, GOPs and their sharding (8(f) N4)
  * x264_slicetype_analyse + scenecut + the key-frame rules of x264_slicetype_decide (encoder/slicetype.c:322-435, 508-537;
  * no B frames, closed GOPs) for a WHOLE sequence at once: icost[k] / pcost[k] are frame k's intra estimate and its inter

@@ -459,6 +459,12 @@ class Context:
                                          _dp(l0_mv16) if l0_mv16 is not None else None, _dp(mb_type), _dp(mv), _dp(mvr),
                                          _dp(mvd), _dp(levels), _dp(nnz), _dp(cbp), None), "x264dsp_p_frames_dev")
 
+    def i_frames(self, g, fenc_slots, recon_slots, n_frames, qp, mb_type, mode16, chroma_mode, modes4, levels, luma_dc, nnz, cbp):
+        """intra analysis + coding of every macroblock of n_frames independent I frames (x264dsp_i_frames_dev)"""
+        check(lib().x264dsp_i_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(recon_slots), int(n_frames), int(qp),
+                                         _dp(mb_type), _dp(mode16), _dp(chroma_mode), _dp(modes4), _dp(levels), _dp(luma_dc),
+                                         _dp(nnz), _dp(cbp), None), "x264dsp_i_frames_dev")
+
     def p_frames_host(self, w, h, n_frames, i420, prm, mb_type, mv, mvr, mvd, levels, nnz, cbp, recon_i420):
         """x264dsp_p_frames_host: numpy (ideally pinned) arrays in and out"""
         check(lib().x264dsp_p_frames_host(self._h, int(w), int(h), int(n_frames), _hp(i420), C.byref(prm),
