@@ -273,9 +273,13 @@ typedef struct
     const uint8_t *nnz;             /* [mb][27] */
     const uint8_t *recon_y, *recon_c;   /* sample (0,0) of the reconstructed luma / NV12 chroma planes */
     int stride_y, stride_c;
+    /* I slices (x264dsp_i_frames_dev): */
+    const uint8_t *mode16, *chroma_mode;    /* [mb] */
+    const uint8_t *modes4;                  /* [mb][16], coding order */
+    const int16_t *luma_dc;                 /* [mb][16] */
 } xref_pframe_out_t;
 typedef int (*xref_pframe_cb)( void *h, xref_pframe_out_t *out );
-xref_pframe_cb xref_hook_pframe = NULL;
+xref_pframe_cb xref_hook_pframe = NULL, xref_hook_iframe = NULL;
 static xref_pframe_out_t xref_pframe;
 static int xref_pframe_live = 0;            /* the current slice is served from xref_pframe */
 int xref_pframe_stats[3];                   /* P slices seen with the hook installed, served, macroblocks served */
@@ -292,6 +296,15 @@ void xref_set_pframe_hook( xref_pframe_cb cb )
     xref_pframe_stats[0] = xref_pframe_stats[1] = xref_pframe_stats[2] = 0;
 }
 void xref_pframe_stats_read( int out[3] ) { memcpy( out, xref_pframe_stats, sizeof(xref_pframe_stats) ); }
+/* the same for I slices (x264_mb_analyse_intra and the intra branches of x264_macroblock_encode on the device) */
+int xref_iframe_stats[3];
+void xref_set_iframe_hook( xref_pframe_cb cb )
+{
+    xref_hook_iframe = cb;
+    xref_pframe_live = 0;
+    xref_iframe_stats[0] = xref_iframe_stats[1] = xref_iframe_stats[2] = 0;
+}
+void xref_iframe_stats_read( int out[3] ) { memcpy( out, xref_iframe_stats, sizeof(xref_iframe_stats) ); }
 void xref_set_door_timing( int on ) { xref_door_timing = on; }
 /* read and reset the calling thread's counters: out = { seconds in analyse, seconds in encode, macroblocks } */
 void xref_door_seconds_read( double out[3] )
@@ -321,7 +334,15 @@ void x264_macroblock_analyse( x264_t *h )
                            && !xref_hook_pframe( h, &xref_pframe );
         xref_pframe_stats[1] += xref_pframe_live;
     }
-    else if( h->sh.i_type != SLICE_TYPE_P )
+    else if( h->sh.i_type == SLICE_TYPE_I && xref_hook_iframe && h->mb.i_mb_xy == h->sh.i_first_mb )
+    {
+        xref_iframe_stats[0]++;
+        xref_pframe_live = ( h->param.analyse.intra & X264_ANALYSE_I4x4 ) && !h->param.analyse.b_transform_8x8
+                           && !h->param.analyse.i_trellis && !h->param.analyse.i_noise_reduction && h->sh.i_first_mb == 0
+                           && h->sh.i_qp <= QP_MAX_SPEC && !xref_hook_iframe( h, &xref_pframe );
+        xref_iframe_stats[1] += xref_pframe_live;
+    }
+    else if( h->mb.i_mb_xy == h->sh.i_first_mb )
         xref_pframe_live = 0;
     if( !xref_pframe_live )
     {
@@ -334,6 +355,27 @@ void x264_macroblock_analyse( x264_t *h )
         }
         else
             xref_orig_macroblock_analyse( h );
+        return;
+    }
+    if( h->sh.i_type == SLICE_TYPE_I )
+    {
+        /* what x264_mb_analyse_init, x264_mb_analyse_intra and x264_analyse_update_cache leave behind for an intra macroblock */
+        const int xy = h->mb.i_mb_xy;
+        int i;
+        h->mb.i_qp = h->sh.i_qp;
+        h->mb.i_chroma_qp = h->chroma_qp_table[h->sh.i_qp];
+        h->mb.b_transform_8x8 = 0;
+        h->mb.b_noise_reduction = 0;
+        h->mb.b_trellis = 0;
+        h->mb.i_skip_intra = 0;
+        h->mb.i_type = xref_pframe.mb_type[xy];
+        if( h->mb.i_type == I_4x4 )
+            for( i = 0; i < 16; i++ )
+                h->mb.cache.intra4x4_pred_mode[x264_scan8[i]] = (int8_t)xref_pframe.modes4[16 * xy + i];
+        else
+            h->mb.i_intra16x16_pred_mode = xref_pframe.mode16[xy];
+        h->mb.i_chroma_pred_mode = xref_pframe.chroma_mode[xy];
+        xref_iframe_stats[2]++;
         return;
     }
     {
@@ -404,7 +446,7 @@ void x264_macroblock_encode( x264_t *h )
     uint8_t i4_modes[16];
     int kind = i16;
     const int inter = !IS_INTRA( h->mb.i_type ) && h->mb.i_type != P_SKIP && h->sh.i_type == SLICE_TYPE_P && h->mb.b_dct_decimate;
-    if( xref_pframe_live && h->sh.i_type == SLICE_TYPE_P )
+    if( xref_pframe_live && ( h->sh.i_type == SLICE_TYPE_P || h->sh.i_type == SLICE_TYPE_I ) )
     {
         /* the macroblock was coded on the device with the rest of its frame: reconstruction into fdec, coded data where
          * the entropy coder reads them (layout as below) */
@@ -435,7 +477,9 @@ void x264_macroblock_encode( x264_t *h )
             h->mb.cache.non_zero_count[x264_scan8[16+i]] = nz[16+i];
             h->mb.cache.non_zero_count[x264_scan8[32+i]] = nz[20+i];
         }
-        h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = 0;
+        h->mb.cache.non_zero_count[x264_scan8[LUMA_DC]] = h->mb.i_type == I_16x16 ? nz[24] : 0;
+        if( h->mb.i_type == I_16x16 )
+            memcpy( h->dct.luma16x16_dc[0], xref_pframe.luma_dc + 16 * xy, 16*sizeof(int16_t) );
         h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC]] = nz[25];
         h->mb.cache.non_zero_count[x264_scan8[CHROMA_DC+1]] = nz[26];
         h->mb.i_cbp_luma = cbp & 15;

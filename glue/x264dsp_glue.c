@@ -65,10 +65,14 @@ typedef struct
     const uint8_t *nnz;
     const uint8_t *recon_y, *recon_c;
     int stride_y, stride_c;
+    const uint8_t *mode16, *chroma_mode, *modes4;
+    const int16_t *luma_dc;
 } xref_pframe_out_t;
 typedef int (*xref_pframe_cb)( void *h, xref_pframe_out_t *out );
 void xref_set_pframe_hook( xref_pframe_cb cb );
 void xref_pframe_stats_read( int out[3] );
+void xref_set_iframe_hook( xref_pframe_cb cb );
+void xref_iframe_stats_read( int out[3] );
 void xref_driver_hook_calls( int out[3] );
 void xref_door_stats_read( int out[12] );
 
@@ -93,11 +97,13 @@ static struct
     int16_t *d_pf_mv, *d_pf_mvr, *d_pf_cbp, *d_pf_levels, *d_pf_lmv, *d_pf_l0;
     int16_t *h_pf_mv, *h_pf_mvr, *h_pf_cbp, *h_pf_levels;
     uint8_t *d_pf_nnz, *h_pf_nnz, *h_pf_luma, *h_pf_chroma;
+    uint8_t *d_if_mode16, *d_if_cmode, *d_if_modes4, *h_if_mode16, *h_if_cmode, *h_if_modes4;
+    int16_t *d_if_dc, *h_if_dc;
     /* host scratch */
     uint8_t *mb_stage;                    /* two 16x16 slots */
     uint8_t *rows;                        /* 16 luma rows of a macroblock as one linear piece of the plane */
     int64_t launches0;
-    int calls[9];                         /* lowres, fdec, cost, me, mbenc, pskip, mbmc, deblocked frames, P frames */
+    int calls[10];                        /* lowres, fdec, cost, me, mbenc, pskip, mbmc, deblocked frames, P frames, I frames */
 } G;
 
 #define GLUE_CHECK( call ) do { int rc_ = ( call ); if( rc_ ) { fprintf( stderr, "x264dsp glue: %s failed (%d) at %s:%d\n", \
@@ -150,6 +156,14 @@ static void glue_open( x264_t *h )
     G.d_pf_nnz = glue_dev( nmb * X264DSP_RES_NNZ_PER_MB );
     G.d_pf_lmv = glue_dev( 4 * nmb );
     G.d_pf_l0 = glue_dev( 4 * nmb );
+    G.d_if_mode16 = glue_dev( nmb );
+    G.d_if_cmode = glue_dev( nmb );
+    G.d_if_modes4 = glue_dev( 16 * nmb );
+    G.d_if_dc = glue_dev( 32 * nmb );
+    G.h_if_mode16 = malloc( nmb );
+    G.h_if_cmode = malloc( nmb );
+    G.h_if_modes4 = malloc( 16 * nmb );
+    G.h_if_dc = malloc( 32 * nmb );
     G.h_pf_type = malloc( nmb );
     G.h_pf_mv = malloc( 4 * nmb );
     G.h_pf_mvr = malloc( 4 * nmb );
@@ -429,6 +443,7 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_nnz, G.d_pf_nnz, nmb * X264DSP_RES_NNZ_PER_MB, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_luma, glue_pred(), g->luma_plane_size, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_chroma, glue_pred() + g->slot_chroma_off, g->chroma_plane_size, NULL ) );
+    memset( out, 0, sizeof(*out) );
     out->mb_type = G.h_pf_type;
     out->mv = G.h_pf_mv;
     out->mvr = G.h_pf_mvr;
@@ -443,10 +458,56 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     return 0;
 }
 
+/* ---- the macroblock loop of a whole I slice: x264dsp_i_frames_dev on the resident source frame */
+static int glue_iframe( void *hv, xref_pframe_out_t *out )
+{
+    x264_t *h = hv;
+    const uint8_t *se = glue_resident( h->fenc );
+    if( !G.ctx || !se )
+        return 1;
+    const x264dsp_geom_t *g = &G.g;
+    const size_t nmb = g->mb_count;
+    if( x264dsp_i_frames_dev( G.ctx, g, se, glue_pred(), 1, h->sh.i_qp, G.d_pf_type, G.d_if_mode16, G.d_if_cmode, G.d_if_modes4,
+                              G.d_pf_levels, G.d_if_dc, G.d_pf_nnz, G.d_pf_cbp, NULL ) )
+        return 1;
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_type, G.d_pf_type, nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_if_mode16, G.d_if_mode16, nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_if_cmode, G.d_if_cmode, nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_if_modes4, G.d_if_modes4, 16 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_if_dc, G.d_if_dc, 32 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_cbp, G.d_pf_cbp, 2 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_levels, G.d_pf_levels, nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t), NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_nnz, G.d_pf_nnz, nmb * X264DSP_RES_NNZ_PER_MB, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_luma, glue_pred(), g->luma_plane_size, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_chroma, glue_pred() + g->slot_chroma_off, g->chroma_plane_size, NULL ) );
+    memset( out, 0, sizeof(*out) );
+    out->mb_type = G.h_pf_type;
+    out->cbp = G.h_pf_cbp;
+    out->levels = G.h_pf_levels;
+    out->nnz = G.h_pf_nnz;
+    out->recon_y = G.h_pf_luma + g->luma_origin;
+    out->recon_c = G.h_pf_chroma + g->chroma_origin;
+    out->stride_y = g->luma_stride;
+    out->stride_c = g->chroma_stride;
+    out->mode16 = G.h_if_mode16;
+    out->chroma_mode = G.h_if_cmode;
+    out->modes4 = G.h_if_modes4;
+    out->luma_dc = G.h_if_dc;
+    G.calls[9]++;
+    return 0;
+}
+
 /* the whole P-slice macroblock loop on the device (on top of x264dsp_glue_install) */
 void x264dsp_glue_install_pframe( void )
 {
     xref_set_pframe_hook( glue_pframe );
+}
+
+/* the whole I-slice macroblock loop on the device as well: with both installed the host runs no analysis and no
+ * macroblock coding at all, only the entropy coder */
+void x264dsp_glue_install_iframe( void )
+{
+    xref_set_iframe_hook( glue_iframe );
 }
 
 void x264dsp_glue_install( void )
@@ -468,23 +529,25 @@ void x264dsp_glue_uninstall( void )
     xref_set_pskip_hook( NULL );
     xref_set_mbmc_hook( NULL );
     xref_set_pframe_hook( NULL );
+    xref_set_iframe_hook( NULL );
 }
 
 /* one JSON object: how often each door was served by the device, what the doors themselves counted
  * ({entered, eligible, served} per door: eligible != served means a silent fallback), kernel launches */
 int x264dsp_glue_report( FILE *out )
 {
-    int hook[3], doors[12], pf[3];
+    int hook[3], doors[12], pf[3], iff[3];
     xref_driver_hook_calls( hook );
     xref_pframe_stats_read( pf );
+    xref_iframe_stats_read( iff );
     xref_door_stats_read( doors );
     return fprintf( out, "{\"lowres\": %d, \"inloop_filter\": %d, \"deblocked_frames\": %d, \"lookahead_cost\": %d, "
                     "\"me_search\": %d, \"macroblock_encode\": %d, \"probe_pskip\": %d, \"mb_mc\": %d, "
                     "\"door_me\": [%d, %d, %d], \"door_mbenc\": [%d, %d, %d], \"door_pskip\": [%d, %d, %d], "
                     "\"door_mbmc\": [%d, %d, %d], \"hook_calls\": [%d, %d, %d], \"p_frames\": %d, "
-                    "\"p_slices\": [%d, %d, %d], \"kernel_launches\": %lld}\n",
+                    "\"p_slices\": [%d, %d, %d], \"i_frames\": %d, \"i_slices\": [%d, %d, %d], \"kernel_launches\": %lld}\n",
                     G.calls[0], G.calls[1], G.calls[7], G.calls[2], G.calls[3], G.calls[4], G.calls[5], G.calls[6],
                     doors[0], doors[1], doors[2], doors[3], doors[4], doors[5], doors[6], doors[7], doors[8], doors[9],
-                    doors[10], doors[11], hook[0], hook[1], hook[2], G.calls[8], pf[0], pf[1], pf[2],
+                    doors[10], doors[11], hook[0], hook[1], hook[2], G.calls[8], pf[0], pf[1], pf[2], G.calls[9], iff[0], iff[1], iff[2],
                     G.ctx ? (long long)( x264dsp_launch_count( G.ctx ) - G.launches0 ) : 0LL );
 }

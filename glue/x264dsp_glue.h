@@ -14,6 +14,9 @@ void x264dsp_glue_install( void );
  * one reference frame, analyse.inter == 0) runs as ONE x264dsp_p_frames_dev call per frame; the host keeps the entropy
  * coder.  Other slices and settings fall back to the per-macroblock doors. */
 void x264dsp_glue_install_pframe( void );
+/* likewise the macroblock loop of every I slice (x264_mb_analyse_intra + the intra branches of x264_macroblock_encode) as ONE
+ * x264dsp_i_frames_dev call per frame */
+void x264dsp_glue_install_iframe( void );
 /* every door forwards to the reference's own code again */
 void x264dsp_glue_uninstall( void );
 /* one JSON line: calls served per door, the doors' own {entered, eligible, served} counters, kernel launches */

@@ -45,6 +45,9 @@ __attribute__((constructor)) static void glue_auto( void )
     x264dsp_glue_install();
     e = getenv( "X264DSP_GLUE_PFRAME" );           /* 0: per-macroblock doors only */
     if( !e || strcmp( e, "0" ) )
+    {
         x264dsp_glue_install_pframe();
+        x264dsp_glue_install_iframe();
+    }
     atexit( glue_atexit );
 }

@@ -49,8 +49,8 @@ def test_glue_cli_with_doors_closed_is_the_reference(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("w,h,n,cut", [(352, 288, 30, 17), (1920, 1080, 3, -1)])
 def test_glue_cli_p_slices_on_the_device(tmp_path, w, h, n, cut):
-    """the default mode: the macroblock loop of every P slice (x264_macroblock_analyse + x264_macroblock_encode) is ONE
-    x264dsp_p_frames_dev call per frame, the host keeps the entropy coder; I slices go through the per-macroblock doors"""
+    """the default mode: the macroblock loop of every slice (x264_macroblock_analyse + x264_macroblock_encode) is ONE device
+    call per frame -- x264dsp_p_frames_dev for P slices, x264dsp_i_frames_dev for I slices -- and the host keeps the entropy coder"""
     assert os.path.exists(GPU_CLI), "glue/_build/x264ref_gpu must travel to the GPU box (make -C glue)"
     assert os.path.exists(cc.REF_CLI), "oracle/_ref/x264ref must travel to the GPU box (make -C oracle ref)"
     src = make_clip(tmp_path, w, h, n, cut)
@@ -66,6 +66,10 @@ def test_glue_cli_p_slices_on_the_device(tmp_path, w, h, n, cut):
     assert seen == served == st["p_frames"] >= n - 2, st             # every P slice of the clip, none declined
     assert served_mbs == served * mbs, st
     assert st["me_search"] == 0 and st["probe_pskip"] == 0 and st["mb_mc"] == 0, st    # no per-macroblock round trips left
+    iseen, iserved, iserved_mbs = st["i_slices"]
+    assert iseen == iserved == st["i_frames"] == n - served >= 1 and iserved_mbs == iserved * mbs, st   # nor for the I slices:
+    assert st["macroblock_encode"] == 0, st                    # x264_mb_analyse_intra and the intra coding ran on the device too
+    assert st["kernel_launches"] < 40 * n, st                  # a handful of launches per frame
     assert st["lowres"] == n and st["inloop_filter"] == n and st["lookahead_cost"] == n - 1, st
 
 
