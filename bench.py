@@ -497,6 +497,45 @@ def cpu_pframe_reference(which, w, h, threads, me, subme, qp=26, n_frames=5):
     return sum(rates), threads * n_frames / dt, float(np.mean(secs))
 
 
+def cli_measure(pkg, w, h, frames=48, lead=4):
+    """the reference's own CLI against the same CLI with the library behind its drivers (glue/_build/x264ref_gpu: every source
+    of the reference compiled unmodified + glue/*.c; lowres, lookahead, in-loop filter and the macroblock loop of every slice on
+    the device, the entropy coder on the host): wall-clock frames/s of an encode, start-up taken out by differencing a short
+    and a long clip.  Returns None when a binary is missing."""
+    import subprocess
+    import tempfile
+    import cpu_checkers as cc
+    gpu_cli = os.path.join(ROOT, "glue", "_build", "x264ref_gpu")
+    if not (os.path.exists(gpu_cli) and os.path.exists(cc.REF_CLI)):
+        return None
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        clip = np.concatenate([cc.synth_frame(w, h, i) for i in range(lead + frames)])
+        srcs = {}
+        for tag, n in (("short", lead), ("long", lead + frames)):
+            d = os.path.join(td, tag)
+            os.makedirs(d)
+            srcs[tag] = os.path.join(d, f"syn_{w}x{h}.yuv")
+            clip[: n * w * h * 3 // 2].tofile(srcs[tag])
+        streams = {}
+        for name, exe in (("reference", cc.REF_CLI), ("gpu", gpu_cli)):
+            t = {}
+            for tag in ("short", "long"):
+                dst = os.path.join(td, f"{name}_{tag}.264")
+                t0 = time.perf_counter()
+                subprocess.run([exe, srcs[tag], dst], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                t[tag] = time.perf_counter() - t0
+                if tag == "long":
+                    streams[name] = np.fromfile(dst, np.uint8)
+            out[name] = {"frames_per_s": frames / max(t["long"] - t["short"], 1e-9), "wall_s_long_clip": t["long"],
+                         "wall_s_short_clip": t["short"]}
+        out["bitstreams_identical"] = bool(np.array_equal(streams["reference"], streams["gpu"]))
+        out["bitstream_bytes"] = int(streams["reference"].size)
+    out["frames"] = frames
+    out["speedup"] = out["gpu"]["frames_per_s"] / out["reference"]["frames_per_s"]
+    return out
+
+
 def me_search_e2e(pkg, ctx, g, w, h, luma_host, la_mvs, pairs, reps=3, qp=26):
     """configs[2] end to end through x264dsp_me_search_frames_host: pinned host pictures and block lists in, pinned
     results out.  Returns (seconds per call, h2d bytes, d2h bytes, results of the last call by size)"""
@@ -1266,6 +1305,13 @@ def main():
                             cb["path_share_of_encoder_time" + sfx] = r[2]
                     ent["cpu_baseline"] = cb
                 pfl["settings"][name] = ent
+            if baseline_ok:
+                cli = cli_measure(pkg, w, h)
+                if cli is not None:
+                    pfl["encoder_cli"] = dict(cli, note="one stream, one process each: the reference's CLI (single-threaded by "
+                                              "construction) against glue/_build/x264ref_gpu, whose host side is the same code "
+                                              "minus the doors' work plus synchronous pageable copies per frame; CABAC, rate "
+                                              "control and file I/O stay on the host in both")
             pfl["value"] = pfl["settings"]["dia_subme1"]["value"]
             pfl["e2e"] = {"value": world * 96 / pf_e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": pf_e2e[1],
                           "d2h_bytes_per_step": pf_e2e[2], "setting": "dia_subme1, 96 frames per call",
