@@ -448,7 +448,7 @@ def pframe_oracle_check(g, check):
     nmb = g.mb_count
 
     class P(C.Structure):
-        _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale")]
+        _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale", "analyse_inter")]
     want = {"mb_type": np.zeros(nmb, np.int8), "mv": np.zeros((nmb, 2), np.int16), "mvr": np.zeros((nmb, 2), np.int16),
             "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8), "cbp": np.zeros(nmb, np.int16)}
     wrecon = np.zeros(g.slot_bytes, np.uint8)

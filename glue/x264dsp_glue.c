@@ -428,6 +428,7 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     prm.mv_range = h->param.analyse.i_mv_range;
     prm.fast_pskip = h->param.analyse.b_fast_pskip;
     prm.mvc_scale = have_l0 ? ( h->fdec->i_poc - fref->i_poc ) * fref->inv_ref_poc[0] : 0;
+    prm.analyse_inter = 0;
     if( have_lowres )
         GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_pf_lmv, h->fenc->lowres_mvs[0][idx], 4 * nmb, NULL ) );
     if( have_l0 )

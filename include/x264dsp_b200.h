@@ -507,6 +507,8 @@ typedef struct x264dsp_pframe_params
     int32_t mv_range;                              /* h->param.analyse.i_mv_range, full-pel */
     int32_t fast_pskip;                            /* h->param.analyse.b_fast_pskip */
     int32_t mvc_scale;                             /* temporal candidates: (curpoc - refpoc) * inv_ref_poc */
+    int32_t analyse_inter;                         /* h->param.analyse.inter: 0, or != 0 = X264_ANALYSE_PSUB16x16 (P8x8 / P16x8 /
+                                                    * P8x16 are analysed as well: x264dsp_p_frames_part_dev) */
 } x264dsp_pframe_params_t;
 int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
                           const uint8_t *fref_slots, uint8_t *recon_slots, int n_frames,

@@ -155,6 +155,12 @@ void xo_p_frame( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_
                  const x264dsp_pframe_params_t *prm, const int16_t *lowres_mv, const int16_t *l0_mv16,
                  int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp );
 
+/* the same with every partition the reference analyses (analyse.inter = PSUB16x16): vectors per 8x8 block */
+void xo_p_frame_part( const x264dsp_geom_t *g, const uint8_t *fenc_slot, const uint8_t *fref_slot, uint8_t *recon_slot,
+                      const x264dsp_pframe_params_t *prm, const int16_t *lowres_mv, const int16_t *l0_mv16,
+                      int8_t *mb_type, uint8_t *partition, int16_t *mv8, int16_t *mvr, int16_t *mvd8, int16_t *levels,
+                      uint8_t *nnz, int16_t *cbp );
+
 /* the I-slice macroblock loop: intra analysis + coding of every macroblock (xo_iframe.c) */
 void xo_predict_16x16( int mode, pixel_t *src );
 void xo_predict_chroma( int mode, pixel_t *src );

@@ -101,7 +101,7 @@ def test_p_frames_host_matches_oracle(pkg, ctx, w, h, n, me, subme, qp):
                       out["cbp"], recon)
 
     class P(C.Structure):
-        _fields_ = [(k, C.c_int32) for k in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale")]
+        _fields_ = [(k, C.c_int32) for k in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale", "analyse_inter")]
     slots = [np.zeros(g.slot_bytes, np.uint8) for _ in range(n + 1)]
     for i in range(n + 1):
         o.xo_frame_load_i420(C.byref(go), ptr(pics[i]), ptr(slots[i]))

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 class OPFrameParams(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale")]
+    _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale", "analyse_inter")]
 
 
 def vp(a):

@@ -25,7 +25,7 @@ class Capture(C.Structure):
 
 
 class PFrameParams(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale")]
+    _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale", "analyse_inter")]
 
 
 def view(addr, count, dtype):
@@ -33,7 +33,7 @@ def view(addr, count, dtype):
     return np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(dtype).copy()
 
 
-def capture_encode(w, h, n, cut, me, subme, qp, deblock, keyint=None, light=False):
+def capture_encode(w, h, n, cut, me, subme, qp, deblock, keyint=None, light=False, psub=0):
     """encode the clip with the reference; returns (geometry, clip frames, [captured frame dicts])"""
     lib = cc.ref()
     assert lib is not None, "oracle/_ref/libx264ref.so not built"
@@ -44,7 +44,7 @@ def capture_encode(w, h, n, cut, me, subme, qp, deblock, keyint=None, light=Fals
     frames = [cc.synth_frame(w, h, i, cut_frame=cut) for i in range(n)]
     clip = np.concatenate(frames)
     lib.xref_set_keyint(*(keyint or (0, 0, 0)))
-    enc = C.c_void_p(lib.xref_open_ex(w, h, me, subme, 16, qp, 0, deblock))
+    enc = C.c_void_p(lib.xref_open_ex(w, h, me, subme, 16, qp, psub, deblock))
     lib.xref_set_keyint(0, 0, 0)
     assert enc.value
     got = []
@@ -70,6 +70,10 @@ def capture_encode(w, h, n, cut, me, subme, qp, deblock, keyint=None, light=Fals
         d["mv"] = mv4[0::4, 0:4 * g.mb_w:4].reshape(nmb, 2).copy()
         d["mv4_uniform"] = all(np.array_equal(mv4[dy::4, dx:4 * g.mb_w:4].reshape(nmb, 2), d["mv"])
                                for dy in range(4) for dx in range(4))
+        d["mv8"] = np.stack([mv4[2 * (k >> 1)::4, 2 * (k & 1):4 * g.mb_w:4].reshape(nmb, 2) for k in range(4)], axis=1)
+        d["mv8_uniform"] = all(np.array_equal(mv4[2 * (k >> 1) + dy::4, 2 * (k & 1) + dx:4 * g.mb_w:4].reshape(nmb, 2), d["mv8"][:, k])
+                               for k in range(4) for dy in range(2) for dx in range(2))
+        d["partition"] = view(c.partition, nmb, np.uint8)
         d["lowres_mv"] = view(c.lowres_mv, nmb * 2, np.int16) if c.have_lowres_mv else None
         d["mvd_ctx"] = view(c.mvd, nmb * 16, np.uint8).reshape(nmb, 8, 2) if c.mvd else None
         d.update(keyint_max=c.keyint_max, keyint_min=c.keyint_min, scenecut=c.scenecut, icost=c.icost, pcost=c.pcost)
@@ -159,3 +163,81 @@ def test_p_frame_oracle_reproduces_the_encoder(w, h, n, cut, me, subme, qp, debl
         n_skip += int((d["mb_type"] == 6).sum())
         n_l0 += int((d["mb_type"] == 4).sum())
     assert n_skip > 0 and n_l0 > 0, f"one-sided clip: {n_skip} skipped, {n_l0} coded macroblocks"
+
+
+def run_oracle_pframe_part(g, frames, d, me, subme, inter=1):
+    o = cc.oracle()
+    nmb = g.mb_count
+    fenc = np.zeros(g.slot_bytes, np.uint8)
+    o.xo_frame_load_i420(C.byref(g), ptr(frames[d["i_frame"]]), ptr(fenc))
+    recon = np.zeros(g.slot_bytes, np.uint8)
+    prm = PFrameParams(me, subme, 16, d["qp"], d["mv_range"], d["fast_pskip"],
+                       (d["poc"] - d["ref_poc"]) * d["inv_ref_poc"] if d["l0_mv16"] is not None else 0, inter)
+    res = {"mb_type": np.zeros(nmb, np.int8), "partition": np.zeros(nmb, np.uint8), "mv8": np.zeros((nmb, 4, 2), np.int16),
+           "mvr": np.zeros((nmb, 2), np.int16), "mvd8": np.zeros((nmb, 4, 2), np.int16),
+           "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8), "cbp": np.zeros(nmb, np.int16)}
+    lm, l0 = d["lowres_mv"], d["l0_mv16"]
+    o.xo_p_frame_part(C.byref(g), ptr(fenc), ptr(d["fref_slot"]), ptr(recon), C.byref(prm),
+                      lm.ctypes.data_as(C.c_void_p) if lm is not None else None,
+                      l0.ctypes.data_as(C.c_void_p) if l0 is not None else None,
+                      *[res[k].ctypes.data_as(C.c_void_p) for k in ("mb_type", "partition", "mv8", "mvr", "mvd8", "levels", "nnz", "cbp")])
+    res["recon"] = recon
+    return res
+
+
+# h->mb.mvd[mb][0..6] holds the bottom row (4x4 cells (0..3, 3)) and the right column (cells (3, 0..2)) of the macroblock:
+# the 8x8 blocks those cells lie in
+MVD_CTX_BLOCK = [2, 2, 3, 3, 1, 1, 3]
+
+
+def check_part_frame(g, d, res, tag, deblock):
+    bad = np.flatnonzero(res["mb_type"] != d["mb_type"])
+    assert bad.size == 0, f"{tag}: type differs at macroblocks {bad[:8]}: {res['mb_type'][bad[:8]]} vs {d['mb_type'][bad[:8]]}"
+    coded = d["mb_type"] != 6
+    assert np.array_equal(res["partition"][coded], d["partition"][coded]), \
+        f"{tag}: partition differs at {np.flatnonzero(coded & (res['partition'] != d['partition']))[:8]}"
+    assert np.array_equal(res["mv8"], d["mv8"]), f"{tag}: final vectors differ at {np.flatnonzero((res['mv8'] != d['mv8']).any((1, 2)))[:8]}"
+    assert np.array_equal(res["mvr"], d["mvr"]), f"{tag}: mvr differs"
+    want_ctx = np.minimum(np.abs(res["mvd8"].astype(np.int32)), 66).astype(np.uint8)
+    for k, blk in enumerate(MVD_CTX_BLOCK):
+        assert np.array_equal(d["mvd_ctx"][:, k, :], want_ctx[:, blk, :]), f"{tag}: mvd context {k} differs"
+    assert np.array_equal(res["cbp"][coded], d["cbp"][coded]), f"{tag}: cbp differs"
+    if not deblock:
+        ry, rc = interior(g, res["recon"][: g.luma_plane_size], res["recon"][g.slot_chroma_off: g.slot_chroma_off + g.chroma_plane_size])
+        wy, wc = interior(g, d["recon_y"], d["recon_c"])
+        assert np.array_equal(ry, wy), f"{tag}: luma reconstruction differs"
+        assert np.array_equal(rc, wc), f"{tag}: chroma reconstruction differs"
+
+
+@pytest.mark.parametrize("w,h,n,cut,me,subme,qp,deblock", [
+    (176, 144, 6, -1, 0, 1, 26, 0), (352, 288, 8, 5, 1, 2, 26, 0), (208, 160, 7, 3, 1, 5, 30, 0),
+    (176, 144, 6, 4, 0, 3, 22, 0), (352, 288, 6, -1, 1, 4, 20, 0), (352, 288, 6, -1, 1, 5, 28, 1)])
+def test_p_frame_partitions_reproduce_the_encoder(w, h, n, cut, me, subme, qp, deblock):
+    """analyse.inter = PSUB16x16: P8x8 / P16x8 / P8x16 as well (xo_p_frame_part)"""
+    if cc.ref() is None:
+        pytest.skip("oracle/_ref not built")
+    g, frames, got = capture_encode(w, h, n, cut, me, subme, qp, deblock, psub=1)
+    p_frames = [d for d in got if d["slice_type"] == SLICE_TYPE_P]
+    assert len(p_frames) >= n - 2
+    seen = set()
+    for d in p_frames:
+        assert d["mv8_uniform"], "a sub-8x8 partition in a PSUB16x16 encode"
+        assert set(np.unique(d["mb_type"])) <= {4, 5, 6}, np.unique(d["mb_type"])
+        res = run_oracle_pframe_part(g, frames, d, me, subme)
+        check_part_frame(g, d, res, f"frame {d['i_frame']} ({w}x{h} me={me} subme={subme} qp={d['qp']} deblock={deblock})", deblock)
+        seen |= set(np.unique(d["partition"][d["mb_type"] != 6]).tolist())
+    assert seen >= {13, 16} and (seen & {14, 15}), f"clip exercises partitions {seen} only"
+
+
+def test_p_frame_part_without_partitions_is_the_16x16_loop():
+    """xo_p_frame_part( analyse_inter = 0 ) == xo_p_frame"""
+    if cc.ref() is None:
+        pytest.skip("oracle/_ref not built")
+    g, frames, got = capture_encode(208, 160, 5, 3, 1, 5, 28, 0)
+    for d in [d for d in got if d["slice_type"] == SLICE_TYPE_P]:
+        a = run_oracle_pframe(g, frames, d, 1, 5)
+        b = run_oracle_pframe_part(g, frames, d, 1, 5, inter=0)
+        assert np.array_equal(a["mb_type"], b["mb_type"]) and np.array_equal(a["cbp"], b["cbp"])
+        assert all(np.array_equal(b["mv8"][:, k], a["mv"]) for k in range(4))
+        assert all(np.array_equal(b["mvd8"][:, k], a["mvd"]) for k in range(4))
+        assert np.array_equal(a["levels"], b["levels"]) and np.array_equal(a["nnz"], b["nnz"]) and np.array_equal(a["recon"], b["recon"])

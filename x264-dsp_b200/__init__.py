@@ -51,7 +51,7 @@ class MeParams(C.Structure):
 class PFrameParams(C.Structure):
     """x264dsp_pframe_params_t"""
     _fields_ = [("me_method", C.c_int32), ("subpel_refine", C.c_int32), ("me_range", C.c_int32), ("qp", C.c_int32),
-                ("mv_range", C.c_int32), ("fast_pskip", C.c_int32), ("mvc_scale", C.c_int32)]
+                ("mv_range", C.c_int32), ("fast_pskip", C.c_int32), ("mvc_scale", C.c_int32), ("analyse_inter", C.c_int32)]
 
 
 MB_P_L0, MB_P_8x8, MB_P_SKIP = 4, 5, 6
