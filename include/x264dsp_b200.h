@@ -516,6 +516,23 @@ int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uin
                           int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *levels, uint8_t *nnz,
                           int16_t *cbp, void *stream );
 
+/* The same with the sub-16x16 partitions the reference analyses when params->analyse_inter has X264_ANALYSE_PSUB16x16:
+ * x264_mb_analyse_inter_p8x8 (analyse.c:864-921), _p16x8 (923-990), _p8x16 (992-1054) with their early exits, the cost
+ * comparison (1133-1172), x264_me_refine_qpel on every partition of the winner (1176-1203) and x264_mb_mc per partition.
+ * Outputs as above except
+ *   mb_type      also X264DSP_MB_P_8x8
+ *   partition    h->mb.partition: 13 = D_8x8, 14 = D_16x8, 15 = D_8x16, 16 = D_16x16 (common/macroblock.h:92-101)
+ *   mv8          [4][2] the final vector of each 8x8 block in raster order (all h->mb.cache.mv can hold without sub-8x8
+ *                partitions; a 16x8 / 8x16 / 16x16 partition repeats its vector)
+ *   mvd8         [4][2] the difference the entropy coder writes for the partition each 8x8 block lies in, predicted from the
+ *                final vectors in coding order (encoder/cabac.c:352-412).  May be NULL.
+ * params->analyse_inter == 0 gives x264dsp_p_frames_dev's decisions in this layout. */
+int x264dsp_p_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
+                               const uint8_t *fref_slots, uint8_t *recon_slots, int n_frames,
+                               const x264dsp_pframe_params_t *params, const int16_t *lowres_mv, const int16_t *l0_mv16,
+                               int8_t *mb_type, uint8_t *partition, int16_t *mv8, int16_t *mvr, int16_t *mvd8,
+                               int16_t *levels, uint8_t *nnz, int16_t *cbp, void *stream );
+
 /* The same from HOST memory: i420 holds n_frames + 1 planar pictures, frame f + 1 is coded against picture f (the source
  * picture standing in for the reconstruction, as in x264dsp_recon_frames_host).  The reference planes (border, half-pel),
  * the half-resolution planes and the lookahead's vectors of every pair are built on the device; outputs are host arrays laid

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--subme", type=int, default=5)
     ap.add_argument("--qp", type=int, default=26)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--part", type=int, default=-1, help="-1: x264dsp_p_frames_dev; 0 / 1: x264dsp_p_frames_part_dev with analyse_inter = 0 / PSUB16x16")
     args = ap.parse_args()
     import torch
     import __graft_entry__ as ge
@@ -49,7 +50,7 @@ def main():
     d_ls = torch.zeros((nmax, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
     ctx.lookahead_frame_cost(g, src, b, b - 1, np.ones(nmax, np.uint8), d_lmv, d_lc, d_ls)
     ctx.sync()
-    out = {"config": {"width": w, "height": h, "me": args.me, "subme": args.subme, "qp": args.qp}, "runs": []}
+    out = {"config": {"width": w, "height": h, "me": args.me, "subme": args.subme, "qp": args.qp, "part": args.part}, "runs": []}
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for n in counts:
         o = dict(mb_type=torch.zeros((n, nmb), dtype=torch.int8, device="cuda"),
@@ -59,9 +60,15 @@ def main():
                  nnz=torch.zeros((n, nmb, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda"),
                  cbp=torch.zeros((n, nmb), dtype=torch.int16, device="cuda"))
         recon = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
-        prm = pkg.PFrameParams(args.me, args.subme, 16, args.qp, 512, 1, 0)
+        prm = pkg.PFrameParams(args.me, args.subme, 16, args.qp, 512, 1, 0, max(args.part, 0))
+        part = torch.zeros((n, nmb), dtype=torch.uint8, device="cuda")
+        mv8 = torch.zeros((n, nmb, 4, 2), dtype=torch.int16, device="cuda")
 
         def run():
+            if args.part >= 0:
+                ctx.p_frames_part(g, src[g.slot_bytes:], src, recon, n, prm, d_lmv[:n], None, o["mb_type"], part, mv8, o["mvr"],
+                                  o["levels"], o["nnz"], o["cbp"])
+                return
             ctx.p_frames(g, src[g.slot_bytes:], src, recon, n, prm, d_lmv[:n], None, o["mb_type"], o["mv"], o["mvr"],
                          o["levels"], o["nnz"], o["cbp"])
         run()
@@ -74,7 +81,9 @@ def main():
         ms = ev[0].elapsed_time(ev[1]) / args.reps
         t = o["mb_type"].cpu().numpy()
         out["runs"].append({"frames_per_launch": n, "ms_per_launch": ms, "ms_per_frame": ms / n, "frames_per_s": 1e3 * n / ms,
-                            "skipped_mb_share": float((t == pkg.MB_P_SKIP).mean())})
+                            "skipped_mb_share": float((t == pkg.MB_P_SKIP).mean()),
+                            "partition_share": {str(k): float(((part.cpu().numpy() == k) & (t != pkg.MB_P_SKIP)).mean())
+                                                for k in (13, 14, 15, 16)} if args.part >= 0 else None})
     print(json.dumps(out))
 
 

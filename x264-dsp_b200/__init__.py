@@ -459,6 +459,16 @@ class Context:
                                          _dp(l0_mv16) if l0_mv16 is not None else None, _dp(mb_type), _dp(mv), _dp(mvr),
                                          _dp(mvd), _dp(levels), _dp(nnz), _dp(cbp), None), "x264dsp_p_frames_dev")
 
+    def p_frames_part(self, g, fenc_slots, fref_slots, recon_slots, n_frames, prm, lowres_mv, l0_mv16, mb_type, partition,
+                      mv8, mvr, levels, nnz, cbp, mvd8=None):
+        """the P-slice loop with the sub-16x16 partitions of analyse.inter = PSUB16x16 (x264dsp_p_frames_part_dev): vectors
+        and differences per 8x8 block, int16[n][mb][4][2]"""
+        check(lib().x264dsp_p_frames_part_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(fref_slots), _dp(recon_slots),
+                                              int(n_frames), C.byref(prm), _dp(lowres_mv) if lowres_mv is not None else None,
+                                              _dp(l0_mv16) if l0_mv16 is not None else None, _dp(mb_type), _dp(partition),
+                                              _dp(mv8), _dp(mvr), _dp(mvd8), _dp(levels), _dp(nnz), _dp(cbp), None),
+              "x264dsp_p_frames_part_dev")
+
     def i_frames(self, g, fenc_slots, recon_slots, n_frames, qp, mb_type, mode16, chroma_mode, modes4, levels, luma_dc, nnz, cbp):
         """intra analysis + coding of every macroblock of n_frames independent I frames (x264dsp_i_frames_dev)"""
         check(lib().x264dsp_i_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(recon_slots), int(n_frames), int(qp),
