@@ -262,7 +262,8 @@ void x264_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, 
  * vector, levels, nnz, cbp, reconstruction.  This door then only installs macroblock xy's decisions where the rest of the
  * slice loop reads them (what x264_mb_analyse_init and x264_analyse_update_cache write, analyse.c:327-420, 1236-1300),
  * and the x264_macroblock_encode door below serves the macroblock's coded data from the same frame result: the host is
- * left with the entropy coder.  Eligible: one reference frame, analyse.inter == 0, no trellis / noise reduction.
+ * left with the entropy coder.  Eligible: one reference frame, analyse.inter == 0 or X264_ANALYSE_PSUB16x16 (the only
+ * inter flag the reference's analysis reads), no trellis / noise reduction.
  * Both doors also keep the time the reference spends in its own two functions (bench.py's cpu_baseline for this path). */
 typedef struct
 {
@@ -277,6 +278,9 @@ typedef struct
     const uint8_t *mode16, *chroma_mode;    /* [mb] */
     const uint8_t *modes4;                  /* [mb][16], coding order */
     const int16_t *luma_dc;                 /* [mb][16] */
+    /* P slices with analyse.inter = PSUB16x16 (x264dsp_p_frames_part_dev): h->mb.partition per macroblock, and mv is then
+     * [mb][4][2], one vector per 8x8 block; NULL: 16x16 only */
+    const uint8_t *partition;
 } xref_pframe_out_t;
 typedef int (*xref_pframe_cb)( void *h, xref_pframe_out_t *out );
 xref_pframe_cb xref_hook_pframe = NULL, xref_hook_iframe = NULL;
@@ -329,7 +333,7 @@ void x264_macroblock_analyse( x264_t *h )
     if( h->sh.i_type == SLICE_TYPE_P && xref_hook_pframe && h->mb.i_mb_xy == h->sh.i_first_mb )
     {
         xref_pframe_stats[0]++;
-        xref_pframe_live = h->i_ref[0] == 1 && !h->param.analyse.inter && !h->param.analyse.i_trellis
+        xref_pframe_live = h->i_ref[0] == 1 && !( h->param.analyse.inter & ~X264_ANALYSE_PSUB16x16 ) && !h->param.analyse.i_trellis
                            && !h->param.analyse.i_noise_reduction && h->sh.i_first_mb == 0 && h->sh.i_qp <= QP_MAX_SPEC
                            && !xref_hook_pframe( h, &xref_pframe );
         xref_pframe_stats[1] += xref_pframe_live;
@@ -393,11 +397,24 @@ void x264_macroblock_analyse( x264_t *h )
         h->mb.mv_max[0] = ( ( ( h->mb.i_mb_width - h->mb.i_mb_x - 1 ) << 4 ) + 24 ) << 2;
         h->mb.mv_min[1] = ( -( h->mb.i_mb_y << 4 ) - 24 ) << 2;
         h->mb.mv_max[1] = ( ( ( h->mb.i_mb_height - h->mb.i_mb_y - 1 ) << 4 ) + 24 ) << 2;
-        /* x264_analyse_update_cache: P_L0 16x16 or P_SKIP, reference 0 */
+        /* x264_analyse_update_cache: P_L0 (16x16, 16x8, 8x16), P_8x8 with four 8x8 sub-partitions, or P_SKIP; reference 0 */
         h->mb.i_type = type;
-        h->mb.i_partition = D_16x16;
         x264_macroblock_cache_ref( h, 0, 0, 4, 4, 0, 0 );
-        x264_macroblock_cache_mv_ptr( h, 0, 0, 4, 4, 0, (int16_t *)( xref_pframe.mv + 2 * xy ) );
+        if( xref_pframe.partition )
+        {
+            int k;
+            h->mb.i_partition = xref_pframe.partition[xy];
+            for( k = 0; k < 4; k++ )
+            {
+                x264_macroblock_cache_mv_ptr( h, 2 * ( k & 1 ), 2 * ( k >> 1 ), 2, 2, 0, (int16_t *)( xref_pframe.mv + 8 * xy + 2 * k ) );
+                h->mb.i_sub_partition[k] = D_L0_8x8;
+            }
+        }
+        else
+        {
+            h->mb.i_partition = D_16x16;
+            x264_macroblock_cache_mv_ptr( h, 0, 0, 4, 4, 0, (int16_t *)( xref_pframe.mv + 2 * xy ) );
+        }
         CP32( h->mb.mvr[0][0][xy], xref_pframe.mvr + 2 * xy );
         xref_pframe_stats[2]++;
     }

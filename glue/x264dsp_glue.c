@@ -67,6 +67,7 @@ typedef struct
     int stride_y, stride_c;
     const uint8_t *mode16, *chroma_mode, *modes4;
     const int16_t *luma_dc;
+    const uint8_t *partition;
 } xref_pframe_out_t;
 typedef int (*xref_pframe_cb)( void *h, xref_pframe_out_t *out );
 void xref_set_pframe_hook( xref_pframe_cb cb );
@@ -96,7 +97,7 @@ static struct
     int8_t *d_pf_type, *h_pf_type;
     int16_t *d_pf_mv, *d_pf_mvr, *d_pf_cbp, *d_pf_levels, *d_pf_lmv, *d_pf_l0;
     int16_t *h_pf_mv, *h_pf_mvr, *h_pf_cbp, *h_pf_levels;
-    uint8_t *d_pf_nnz, *h_pf_nnz, *h_pf_luma, *h_pf_chroma;
+    uint8_t *d_pf_nnz, *h_pf_nnz, *h_pf_luma, *h_pf_chroma, *d_pf_part, *h_pf_part;
     uint8_t *d_if_mode16, *d_if_cmode, *d_if_modes4, *h_if_mode16, *h_if_cmode, *h_if_modes4;
     int16_t *d_if_dc, *h_if_dc;
     /* host scratch */
@@ -149,7 +150,8 @@ static void glue_open( x264_t *h )
     G.mb_stage = calloc( 2, (size_t)G.g1.slot_bytes );
     G.rows = malloc( (size_t)16 * G.g.luma_stride );
     G.d_pf_type = glue_dev( nmb );
-    G.d_pf_mv = glue_dev( 4 * nmb );
+    G.d_pf_mv = glue_dev( 16 * nmb );                          /* [mb][4][2] when partitions are analysed */
+    G.d_pf_part = glue_dev( nmb );
     G.d_pf_mvr = glue_dev( 4 * nmb );
     G.d_pf_cbp = glue_dev( 2 * nmb );
     G.d_pf_levels = glue_dev( nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t) );
@@ -165,7 +167,8 @@ static void glue_open( x264_t *h )
     G.h_if_modes4 = malloc( 16 * nmb );
     G.h_if_dc = malloc( 32 * nmb );
     G.h_pf_type = malloc( nmb );
-    G.h_pf_mv = malloc( 4 * nmb );
+    G.h_pf_mv = malloc( 16 * nmb );
+    G.h_pf_part = malloc( nmb );
     G.h_pf_mvr = malloc( 4 * nmb );
     G.h_pf_cbp = malloc( 2 * nmb );
     G.h_pf_levels = malloc( nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t) );
@@ -428,16 +431,22 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     prm.mv_range = h->param.analyse.i_mv_range;
     prm.fast_pskip = h->param.analyse.b_fast_pskip;
     prm.mvc_scale = have_l0 ? ( h->fdec->i_poc - fref->i_poc ) * fref->inv_ref_poc[0] : 0;
-    prm.analyse_inter = 0;
+    prm.analyse_inter = h->param.analyse.inter & X264_ANALYSE_PSUB16x16;
+    const int by_part = prm.analyse_inter != 0;
     if( have_lowres )
         GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_pf_lmv, h->fenc->lowres_mvs[0][idx], 4 * nmb, NULL ) );
     if( have_l0 )
         GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_pf_l0, fref->mv16x16, 4 * nmb, NULL ) );
-    if( x264dsp_p_frames_dev( G.ctx, g, se, sr, glue_pred(), 1, &prm, have_lowres ? G.d_pf_lmv : NULL, have_l0 ? G.d_pf_l0 : NULL,
-                              G.d_pf_type, G.d_pf_mv, G.d_pf_mvr, NULL, G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL ) )
+    if( by_part ? x264dsp_p_frames_part_dev( G.ctx, g, se, sr, glue_pred(), 1, &prm, have_lowres ? G.d_pf_lmv : NULL,
+                                             have_l0 ? G.d_pf_l0 : NULL, G.d_pf_type, G.d_pf_part, G.d_pf_mv, G.d_pf_mvr, NULL,
+                                             G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL )
+                : x264dsp_p_frames_dev( G.ctx, g, se, sr, glue_pred(), 1, &prm, have_lowres ? G.d_pf_lmv : NULL, have_l0 ? G.d_pf_l0 : NULL,
+                                        G.d_pf_type, G.d_pf_mv, G.d_pf_mvr, NULL, G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL ) )
         return 1;                                              /* parameters the device path does not take: the host's own loop */
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_type, G.d_pf_type, nmb, NULL ) );
-    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_mv, G.d_pf_mv, 4 * nmb, NULL ) );
+    GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_mv, G.d_pf_mv, ( by_part ? 16 : 4 ) * nmb, NULL ) );
+    if( by_part )
+        GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_part, G.d_pf_part, nmb, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_mvr, G.d_pf_mvr, 4 * nmb, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_cbp, G.d_pf_cbp, 2 * nmb, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_levels, G.d_pf_levels, nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t), NULL ) );
@@ -447,6 +456,7 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     memset( out, 0, sizeof(*out) );
     out->mb_type = G.h_pf_type;
     out->mv = G.h_pf_mv;
+    out->partition = by_part ? G.h_pf_part : NULL;
     out->mvr = G.h_pf_mvr;
     out->cbp = G.h_pf_cbp;
     out->levels = G.h_pf_levels;

@@ -96,3 +96,44 @@ def test_glue_cli_bitstream_identical(tmp_path, w, h, n, cut):
     assert st["macroblock_encode"] == st["door_mbenc"][2] >= mbs, st
     assert st["probe_pskip"] == st["door_pskip"][2] and st["mb_mc"] == st["door_mbmc"][2], st
     assert st["kernel_launches"] > 3 * n, st
+
+
+API_GPU = os.path.join(ROOT, "glue", "_build", "x264api_gpu")
+
+
+def run_api(src, out, w, h, psub, me, subme, qp, env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    subprocess.run([API_GPU, src, out, str(w), str(h), str(psub), str(me), str(subme), str(qp)], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, timeout=1500)
+    return np.fromfile(out, np.uint8)
+
+
+def test_api_example_with_doors_closed_runs_partitions(tmp_path):
+    """glue/x264dsp_api_example.c on the CPU alone: X264_ANALYSE_PSUB16x16 reaches the reference's analysis (the stream changes)"""
+    if not os.path.exists(API_GPU):
+        pytest.skip("glue/_build/x264api_gpu not built")
+    src = make_clip(tmp_path, 176, 144, 6, 3)
+    a = run_api(src, str(tmp_path / "a.264"), 176, 144, 0, 1, 5, 26, {"X264DSP_GLUE": "0"})
+    b = run_api(src, str(tmp_path / "b.264"), 176, 144, 1, 1, 5, 26, {"X264DSP_GLUE": "0"})
+    assert a.size > 0 and b.size > 0 and not np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,cut,psub,me,subme,qp", [(352, 288, 12, 7, 1, 1, 5, 26), (352, 288, 8, -1, 1, 0, 1, 30),
+                                                       (1920, 1080, 3, -1, 1, 1, 4, 28), (352, 288, 8, 5, 0, 1, 2, 26)])
+def test_api_user_with_partitions_on_the_device(tmp_path, w, h, n, cut, psub, me, subme, qp):
+    """an application of the library API with analyse.inter = X264_ANALYSE_PSUB16x16: every P slice goes through
+    x264dsp_p_frames_part_dev, the bitstream is the reference library's byte for byte"""
+    assert os.path.exists(API_GPU), "glue/_build/x264api_gpu must travel to the GPU box (make -C glue)"
+    src = make_clip(tmp_path, w, h, n, cut)
+    want = run_api(src, str(tmp_path / "ref.264"), w, h, psub, me, subme, qp, {"X264DSP_GLUE": "0"})
+    stats_path = str(tmp_path / "stats.json")
+    got = run_api(src, str(tmp_path / "gpu.264"), w, h, psub, me, subme, qp, {"X264DSP_GLUE_STATS": stats_path})
+    st = json.load(open(stats_path))
+    print("GLUESTATS api", f"{w}x{h}x{n} psub={psub}", json.dumps(st))
+    assert want.size > 0 and got.size == want.size and np.array_equal(want, got), f"bitstreams differ: {got.size} vs {want.size} bytes"
+    mbs = ((w + 15) // 16) * ((h + 15) // 16)
+    seen, served, served_mbs = st["p_slices"]
+    assert seen == served == st["p_frames"] >= n - 2 and served_mbs == served * mbs, st
+    assert st["me_search"] == 0 and st["probe_pskip"] == 0 and st["mb_mc"] == 0 and st["macroblock_encode"] == 0, st
