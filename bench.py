@@ -357,9 +357,12 @@ def cpu_recon_reference(which, w, h, pics, mv, bs, threads, qp=26, target_s=4.0)
 
 
 PF_FRAMES = 384
+PF_E2E_FRAMES = 384
+# (name, (me_method, subme, analyse.inter != 0))
+PF_SETTINGS = (("dia_subme1", (0, 1, 0)), ("hex_subme5", (1, 5, 0)), ("hex_subme5_psub16x16", (1, 5, 1)))
 
 
-def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3):
+def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3, part=0):
     """BASELINE north_star's closed loop, SURVEY 8(f) N2: x264_macroblock_analyse + x264_macroblock_encode for every macroblock
     of n_frames independent 1080p P frames in ONE launch (x264dsp_p_frames_dev).  Inputs as an encoder has them: reference
     frame border-expanded and half-pel filtered, the lookahead's vectors of each pair as first search candidate.  Returns
@@ -384,15 +387,21 @@ def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3)
     d_ls = torch.zeros((n_frames, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
     ctx.lookahead_frame_cost(g, src, b, b - 1, np.ones(n_frames, np.uint8), d_lmv, d_lc, d_ls)
     o = dict(mb_type=torch.zeros((n_frames, nmb), dtype=torch.int8, device="cuda"),
-             mv=torch.zeros((n_frames, nmb, 2), dtype=torch.int16, device="cuda"),
+             mv=torch.zeros((n_frames, nmb, 4, 2) if part else (n_frames, nmb, 2), dtype=torch.int16, device="cuda"),
              mvr=torch.zeros((n_frames, nmb, 2), dtype=torch.int16, device="cuda"),
              levels=torch.zeros((n_frames, nmb, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda"),
              nnz=torch.zeros((n_frames, nmb, pkg.RES_NNZ_PER_MB), dtype=torch.uint8, device="cuda"),
              cbp=torch.zeros((n_frames, nmb), dtype=torch.int16, device="cuda"))
+    if part:
+        o["partition"] = torch.zeros((n_frames, nmb), dtype=torch.uint8, device="cuda")
     recon = torch.zeros(n_frames * g.slot_bytes, dtype=torch.uint8, device="cuda")
-    prm = pkg.PFrameParams(me, subme, 16, qp, 512, 1, 0)
+    prm = pkg.PFrameParams(me, subme, 16, qp, 512, 1, 0, part)
 
     def run(n):
+        if part:
+            ctx.p_frames_part(g, src[g.slot_bytes:], src, recon, n, prm, d_lmv[:n], None, o["mb_type"], o["partition"], o["mv"],
+                              o["mvr"], o["levels"], o["nnz"], o["cbp"])
+            return
         ctx.p_frames(g, src[g.slot_bytes:], src, recon, n, prm, d_lmv[:n], None, o["mb_type"], o["mv"], o["mvr"], o["levels"],
                      o["nnz"], o["cbp"])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -410,7 +419,7 @@ def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3)
     torch.cuda.synchronize()
     types = o["mb_type"].cpu().numpy()
     check = (src[: 2 * g.slot_bytes].cpu().numpy(), d_lmv[0].cpu().numpy(),
-             {k: v[0].cpu().numpy() for k, v in o.items()}, recon[: g.slot_bytes].cpu().numpy(), (me, subme, qp))
+             {k: v[0].cpu().numpy() for k, v in o.items()}, recon[: g.slot_bytes].cpu().numpy(), (me, subme, qp, part))
     return out[0], out[1], float((types == pkg.MB_P_SKIP).mean()), check
 
 
@@ -442,7 +451,7 @@ def pframe_oracle_check(g, check):
     """frame 0 of the P-frame measurement against the CPU oracle's xo_p_frame (pinned to the running reference encoder)"""
     import cpu_checkers as cc
     from cpu_checkers import ptr
-    slots, lmv, got, recon, (me, subme, qp) = check
+    slots, lmv, got, recon, (me, subme, qp, part) = check
     o = cc.oracle()
     go = cc.oracle_geom(g.width, g.height)
     nmb = g.mb_count
@@ -452,10 +461,18 @@ def pframe_oracle_check(g, check):
     want = {"mb_type": np.zeros(nmb, np.int8), "mv": np.zeros((nmb, 2), np.int16), "mvr": np.zeros((nmb, 2), np.int16),
             "levels": np.zeros((nmb, 392), np.int16), "nnz": np.zeros((nmb, 27), np.uint8), "cbp": np.zeros(nmb, np.int16)}
     wrecon = np.zeros(g.slot_bytes, np.uint8)
-    prm = P(me, subme, 16, qp, 512, 1, 0)
+    prm = P(me, subme, 16, qp, 512, 1, 0, part)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    o.xo_p_frame(C.byref(go), ptr(slots[g.slot_bytes:]), ptr(slots[: g.slot_bytes]), ptr(wrecon), C.byref(prm), vp(lmv), None,
-                 vp(want["mb_type"]), vp(want["mv"]), vp(want["mvr"]), None, vp(want["levels"]), vp(want["nnz"]), vp(want["cbp"]))
+    if part:
+        want["mv"] = np.zeros((nmb, 4, 2), np.int16)
+        want["partition"] = np.zeros(nmb, np.uint8)
+        mvd8 = np.zeros((nmb, 4, 2), np.int16)
+        o.xo_p_frame_part(C.byref(go), ptr(slots[g.slot_bytes:]), ptr(slots[: g.slot_bytes]), ptr(wrecon), C.byref(prm), vp(lmv), None,
+                          vp(want["mb_type"]), vp(want["partition"]), vp(want["mv"]), vp(want["mvr"]), vp(mvd8), vp(want["levels"]),
+                          vp(want["nnz"]), vp(want["cbp"]))
+    else:
+        o.xo_p_frame(C.byref(go), ptr(slots[g.slot_bytes:]), ptr(slots[: g.slot_bytes]), ptr(wrecon), C.byref(prm), vp(lmv), None,
+                     vp(want["mb_type"]), vp(want["mv"]), vp(want["mvr"]), None, vp(want["levels"]), vp(want["nnz"]), vp(want["cbp"]))
     ok = all(np.array_equal(got[k], want[k]) for k in want)
     lo = g.luma_origin
     a = recon[lo:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:, : g.luma_w]
@@ -463,7 +480,7 @@ def pframe_oracle_check(g, check):
     return bool(ok and np.array_equal(a, bb))
 
 
-def cpu_pframe_reference(which, w, h, threads, me, subme, qp=26, n_frames=5):
+def cpu_pframe_reference(which, w, h, threads, me, subme, qp=26, n_frames=5, psub=0):
     """the reference's own x264_macroblock_analyse + x264_macroblock_encode on P slices: every host thread encodes its own
     1080p clip with its own encoder instance (unmodified reference, oracle/_ref); the doors in front of the two functions
     keep the time each thread spends inside them on P slices.  Returns (P frames/s of that path summed over the threads,
@@ -475,7 +492,7 @@ def cpu_pframe_reference(which, w, h, threads, me, subme, qp=26, n_frames=5):
         return None
     lib.xref_open_ex.restype = C.c_void_p
     clips = [np.concatenate([cc.synth_frame(w, h, 3 * t + i) for i in range(n_frames)]) for t in range(min(threads, 4))]
-    encs = [C.c_void_p(lib.xref_open_ex(w, h, me, subme, 16, qp, 0, 1)) for _ in range(threads)]
+    encs = [C.c_void_p(lib.xref_open_ex(w, h, me, subme, 16, qp, psub, 1)) for _ in range(threads)]
     mbs = ((w + 15) // 16) * ((h + 15) // 16)
     rates, secs = [0.0] * threads, [0.0] * threads
     lib.xref_set_door_timing(1)
@@ -522,9 +539,11 @@ def cli_measure(pkg, w, h, frames=48, lead=4):
             t = {}
             for tag in ("short", "long"):
                 dst = os.path.join(td, f"{name}_{tag}.264")
-                t0 = time.perf_counter()
-                subprocess.run([exe, srcs[tag], dst], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-                t[tag] = time.perf_counter() - t0
+                t[tag] = 1e30
+                for _ in range(3):                 # start-up (CUDA context creation: 0.8 .. 2.3 s) varies from run to run: best of 3
+                    t0 = time.perf_counter()
+                    subprocess.run([exe, srcs[tag], dst], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                    t[tag] = min(t[tag], time.perf_counter() - t0)
                 if tag == "long":
                     streams[name] = np.fromfile(dst, np.uint8)
             out[name] = {"frames_per_s": frames / max(t["long"] - t["short"], 1e-9), "wall_s_long_clip": t["long"],
@@ -1109,12 +1128,12 @@ def main():
     pf = None
     if not args.no_me and w * h <= 1920 * 1088:
         pf = {}
-        for name, (pme, psub) in (("dia_subme1", (0, 1)), ("hex_subme5", (1, 5))):
-            pf[name] = pframe_measure(pkg, ctx, torch, g, w, h, PF_FRAMES, pme, psub)
-        pf_e2e = pframe_e2e(pkg, ctx, g, w, h, 96, 0, 1)
-        sec += [pf["dia_subme1"][0], pf["hex_subme5"][0], pf_e2e[0]]
+        for name, (pme, psub, ppart) in PF_SETTINGS:
+            pf[name] = pframe_measure(pkg, ctx, torch, g, w, h, PF_FRAMES if not ppart else PF_FRAMES // 2, pme, psub, part=ppart)
+        pf_e2e = pframe_e2e(pkg, ctx, g, w, h, PF_E2E_FRAMES, 0, 1)
+        sec += [pf["dia_subme1"][0], pf["hex_subme5"][0], pf_e2e[0], pf["hex_subme5_psub16x16"][0]]
     else:
-        sec += [0.0, 0.0, 0.0]
+        sec += [0.0, 0.0, 0.0, 0.0]
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3] + sec + [copy_s * 1e3], dtype=torch.float64, device="cuda")
@@ -1122,9 +1141,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     me_dev_ms_max, me_e2e_s_max, rc_dev_ms_max, rc_e2e_s_max = (float(x) for x in t[2:6])
-    pf_ms_max = (float(t[6]), float(t[7]))
+    pf_ms_max = (float(t[6]), float(t[7]), float(t[9]))
     pf_e2e_s_max = float(t[8])
-    copy_ms = float(t[9])
+    copy_ms = float(t[10])
 
     if rank == 0:
         frames_total = world * n * args.steps
@@ -1285,10 +1304,11 @@ def main():
                    "launch": f"x264dsp_p_frames_dev, {PF_FRAMES} independent frames per launch (the rows of all frames share one ticket queue; 96 per "
                              "launch: 139 / 284 us per frame, one frame alone: the wavefront's critical path), every rank on its own frames",
                    "unit": "frames/s", "n_gpus": world, "settings": {}}
-            for k, (name, (pme, psub)) in enumerate((("dia_subme1", (0, 1)), ("hex_subme5", (1, 5)))):
+            for k, (name, (pme, psub, ppart)) in enumerate(PF_SETTINGS):
                 ms_f, ms_one, skipped, check = pf[name]
                 ent = {"value": world * 1e3 / pf_ms_max[k], "ms_per_frame": pf_ms_max[k], "ms_one_frame_alone": ms_one,
-                       "skipped_mb_share": skipped, "me_method": pme, "subme": psub}
+                       "skipped_mb_share": skipped, "me_method": pme, "subme": psub,
+                       "analyse_inter": "PSUB16x16 (P8x8 / P16x8 / P8x16 analysed as well: x264dsp_p_frames_part_dev)" if ppart else 0}
                 if baseline_ok:
                     ent["bit_exact_vs_oracle"] = pframe_oracle_check(g, check)
                     cb = {"unit": "frames/s", "cores": threads, "kind": "reference",
@@ -1297,7 +1317,7 @@ def main():
                                     "time each thread spends inside them on P slices; value = sum over the threads of P frames per "
                                     "second of that path"}
                     for which in ("O2", "O3"):
-                        r = cpu_pframe_reference(which, w, h, threads, pme, psub)
+                        r = cpu_pframe_reference(which, w, h, threads, pme, psub, psub=ppart)
                         if r is not None:
                             sfx = "" if which == "O2" else "_O3_x86-64-v3"
                             cb["value" + sfx] = r[0]
@@ -1310,11 +1330,12 @@ def main():
                 if cli is not None:
                     pfl["encoder_cli"] = dict(cli, note="one stream, one process each: the reference's CLI (single-threaded by "
                                               "construction) against glue/_build/x264ref_gpu, whose host side is the same code "
-                                              "minus the doors' work plus synchronous pageable copies per frame; CABAC, rate "
-                                              "control and file I/O stay on the host in both")
+                                              "minus the doors' work plus synchronous copies per frame; CABAC, rate "
+                                              "control and file I/O stay on the host in both (about 6.5 ms of the GPU CLI's 15 ms per "
+                                              "1080p frame: glue/x264dsp_glue.c's own clock, X264DSP_GLUE_STATS)")
             pfl["value"] = pfl["settings"]["dia_subme1"]["value"]
-            pfl["e2e"] = {"value": world * 96 / pf_e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": pf_e2e[1],
-                          "d2h_bytes_per_step": pf_e2e[2], "setting": "dia_subme1, 96 frames per call",
+            pfl["e2e"] = {"value": world * PF_E2E_FRAMES / pf_e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": pf_e2e[1],
+                          "d2h_bytes_per_step": pf_e2e[2], "setting": f"dia_subme1, {PF_E2E_FRAMES} frames per call (four stream groups)",
                           "api": "x264dsp_p_frames_host (pinned I420 pictures in; types, vectors, mvd, levels, nnz, cbp and the "
                                  "reconstructed I420 pictures out; reference planes, lowres planes and the lookahead of every pair "
                                  "built on the device inside the call)"}

@@ -105,7 +105,17 @@ static struct
     uint8_t *rows;                        /* 16 luma rows of a macroblock as one linear piece of the plane */
     int64_t launches0;
     int calls[10];                        /* lowres, fdec, cost, me, mbenc, pskip, mbmc, deblocked frames, P frames, I frames */
+    double seconds[10];                   /* wall time inside the hooks, same order (copies and waits included) */
+    double t_install, seconds_open;       /* seconds_open: context creation + allocations, inside the first hook call */
 } G;
+
+#include <time.h>
+static double glue_clock( void )
+{
+    struct timespec ts;
+    clock_gettime( CLOCK_MONOTONIC, &ts );
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 #define GLUE_CHECK( call ) do { int rc_ = ( call ); if( rc_ ) { fprintf( stderr, "x264dsp glue: %s failed (%d) at %s:%d\n", \
                                 #call, rc_, __FILE__, __LINE__ ); abort(); } } while( 0 )
@@ -123,6 +133,7 @@ static void glue_open( x264_t *h )
 {
     if( G.ctx )
         return;
+    const double t_open = glue_clock();
     GLUE_CHECK( x264dsp_create( 0, &G.ctx ) );
     GLUE_CHECK( x264dsp_geometry( h->param.i_width, h->param.i_height, &G.g ) );
     GLUE_CHECK( x264dsp_geometry( 16, 16, &G.g1 ) );
@@ -162,20 +173,51 @@ static void glue_open( x264_t *h )
     G.d_if_cmode = glue_dev( nmb );
     G.d_if_modes4 = glue_dev( 16 * nmb );
     G.d_if_dc = glue_dev( 32 * nmb );
-    G.h_if_mode16 = malloc( nmb );
-    G.h_if_cmode = malloc( nmb );
-    G.h_if_modes4 = malloc( 16 * nmb );
-    G.h_if_dc = malloc( 32 * nmb );
-    G.h_pf_type = malloc( nmb );
-    G.h_pf_mv = malloc( 16 * nmb );
-    G.h_pf_part = malloc( nmb );
-    G.h_pf_mvr = malloc( 4 * nmb );
-    G.h_pf_cbp = malloc( 2 * nmb );
-    G.h_pf_levels = malloc( nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t) );
-    G.h_pf_nnz = malloc( nmb * X264DSP_RES_NNZ_PER_MB );
-    G.h_pf_luma = malloc( G.g.luma_plane_size );
-    G.h_pf_chroma = malloc( G.g.chroma_plane_size );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, nmb, (void **)&G.h_if_mode16 ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, nmb, (void **)&G.h_if_cmode ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, 16 * nmb, (void **)&G.h_if_modes4 ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, 32 * nmb, (void **)&G.h_if_dc ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, nmb, (void **)&G.h_pf_type ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, 16 * nmb, (void **)&G.h_pf_mv ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, nmb, (void **)&G.h_pf_part ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, 4 * nmb, (void **)&G.h_pf_mvr ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, 2 * nmb, (void **)&G.h_pf_cbp ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, nmb * X264DSP_RES_LEVELS_PER_MB * sizeof(int16_t), (void **)&G.h_pf_levels ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, nmb * X264DSP_RES_NNZ_PER_MB, (void **)&G.h_pf_nnz ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, G.g.luma_plane_size, (void **)&G.h_pf_luma ) );
+    GLUE_CHECK( x264dsp_host_alloc( G.ctx, G.g.chroma_plane_size, (void **)&G.h_pf_chroma ) );
     G.launches0 = x264dsp_launch_count( G.ctx );
+    G.seconds_open = glue_clock() - t_open;
+}
+
+/* page-lock the encoder's own frame buffers the first time they are seen (the reference allocates its frames once and
+ * recycles them): pageable copies run at a fraction of the link's rate and were a third of the glue's time per frame */
+#define GLUE_PINNED_MAX 256
+static struct { void *p; } glue_pinned[GLUE_PINNED_MAX];
+static int glue_n_pinned;
+static void glue_pin( void *p, size_t bytes )
+{
+    for( int i = 0; i < glue_n_pinned; i++ )
+        if( glue_pinned[i].p == p )
+            return;
+    if( glue_n_pinned == GLUE_PINNED_MAX )
+        return;
+    glue_pinned[glue_n_pinned++].p = p;
+    if( x264dsp_host_register( G.ctx, p, bytes ) )
+        fprintf( stderr, "x264dsp glue: could not page-lock a frame buffer (copies from it stay pageable)\n" );
+}
+static void glue_pin_frame( x264_frame_t *f )
+{
+    const x264dsp_geom_t *g = &G.g;
+    static int on = -1;
+    if( on < 0 )
+        on = getenv( "X264DSP_GLUE_PIN" ) && atoi( getenv( "X264DSP_GLUE_PIN" ) );
+    if( !on )
+        return;
+    glue_pin( f->buffer[0], 4 * (size_t)g->luma_plane_size );
+    glue_pin( f->buffer[1], g->chroma_plane_size );
+    if( f->buffer_lowres[0] )
+        glue_pin( f->buffer_lowres[0], 4 * (size_t)g->lowres_plane_size );
 }
 
 static uint8_t *glue_slot( int i )      { return G.pool + (size_t)i * G.g.slot_bytes; }
@@ -207,17 +249,20 @@ static uint8_t *glue_make_resident( void *frame )
  *      buffer_lowres[0] = the four lowres planes -- the layout of one frame slot (x264dsp_geom_t). */
 static void glue_lowres( void *hv, void *fv )
 {
+    const double t0_ = glue_clock();
     x264_t *h = hv;
     x264_frame_t *f = fv;
     glue_open( h );
     const x264dsp_geom_t *g = &G.g;
     uint8_t *slot = glue_make_resident( f );
+    glue_pin_frame( f );
     GLUE_CHECK( x264dsp_h2d( G.ctx, slot, f->buffer[0], g->luma_plane_size, NULL ) );
     GLUE_CHECK( x264dsp_h2d( G.ctx, slot + g->slot_chroma_off, f->buffer[1], g->chroma_plane_size, NULL ) );
     GLUE_CHECK( x264dsp_frame_init_lowres_dev( G.ctx, g, slot, 1, NULL ) );
     GLUE_CHECK( x264dsp_frame_export_lowres_dev( G.ctx, g, slot, 1, NULL ) );    /* the reference wants row-major lowres[0..3] */
     GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[0], slot, g->luma_plane_size, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer_lowres[0], slot + g->slot_lowres_off, 4 * (size_t)g->lowres_plane_size, NULL ) );
+    G.seconds[0] += glue_clock() - t0_;
     G.calls[0]++;
 }
 
@@ -225,12 +270,14 @@ static void glue_lowres( void *hv, void *fv )
 static void glue_fdec( void *hv, void *fv, int do_deblock, const int8_t *mb_type, const uint8_t *partition,
                        const int16_t *cbp, const uint8_t *bs, int qp, int alpha_off, int beta_off )
 {
+    const double t0_ = glue_clock();
     x264_t *h = hv;
     x264_frame_t *f = fv;
     glue_open( h );
     const x264dsp_geom_t *g = &G.g;
     const size_t nmb = g->mb_count;
     uint8_t *slot = glue_make_resident( f );                 /* this reconstruction is the next frame's reference */
+    glue_pin_frame( f );
     GLUE_CHECK( x264dsp_h2d( G.ctx, slot, f->buffer[0], g->luma_plane_size, NULL ) );
     GLUE_CHECK( x264dsp_h2d( G.ctx, slot + g->slot_chroma_off, f->buffer[1], g->chroma_plane_size, NULL ) );
     if( do_deblock )
@@ -247,6 +294,7 @@ static void glue_fdec( void *hv, void *fv, int do_deblock, const int8_t *mb_type
     GLUE_CHECK( x264dsp_frame_filter_dev( G.ctx, g, slot, 1, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[0], slot, 4 * (size_t)g->luma_plane_size, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[1], slot + g->slot_chroma_off, g->chroma_plane_size, NULL ) );
+    G.seconds[1] += glue_clock() - t0_;
     G.calls[1]++;
 }
 
@@ -255,6 +303,7 @@ static void glue_fdec( void *hv, void *fv, int do_deblock, const int8_t *mb_type
  *      into the reference's own arrays */
 static void glue_cost( void *hv, void *p0v, void *bv, int want_intra, int16_t *mvs, int *costs, int *sums )
 {
+    const double t0_ = glue_clock();
     x264_t *h = hv;
     x264_frame_t *p0 = p0v, *b = bv;
     glue_open( h );
@@ -274,6 +323,7 @@ static void glue_cost( void *hv, void *p0v, void *bv, int want_intra, int16_t *m
     GLUE_CHECK( x264dsp_d2h( G.ctx, costs, G.d_costs, 4 * nmb, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, s, G.d_sums, sizeof(s), NULL ) );
     memcpy( sums, s, 8 * sizeof(int) );
+    G.seconds[2] += glue_clock() - t0_;
     G.calls[2]++;
 }
 
@@ -281,6 +331,7 @@ static void glue_cost( void *hv, void *p0v, void *bv, int want_intra, int16_t *m
 static int glue_me( void *hv, void *fenc, void *fref, const x264dsp_me_block_t *in, int me_method, int subme, int me_range,
                     int qp, x264dsp_me_result_t *out )
 {
+    const double t0_ = glue_clock();
     const uint8_t *se = glue_resident( fenc ), *sr = glue_resident( fref );
     if( !G.ctx || !se || !sr )
         return 1;
@@ -288,6 +339,7 @@ static int glue_me( void *hv, void *fenc, void *fref, const x264dsp_me_block_t *
     GLUE_CHECK( x264dsp_h2d( G.ctx, G.d_blk, in, sizeof(*in), NULL ) );
     GLUE_CHECK( x264dsp_me_search_batch_dev( G.ctx, &G.g, se, sr, &prm, 1, G.d_blk, G.d_res, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, out, G.d_res, sizeof(*out), NULL ) );
+    G.seconds[3] += glue_clock() - t0_;
     G.calls[3]++;
     return 0;
 }
@@ -314,6 +366,7 @@ static void glue_fetch_mb( const uint8_t *slot, int mb_x, int mb_y, uint8_t *fde
 /* ---- x264_mb_mc: the four 8x8 MVs of the macroblock -> prediction into fdec */
 static int glue_mbmc( void *hv, void *fref, int mb_x, int mb_y, const int16_t *mv8x8, uint8_t *fdec_y, uint8_t *fdec_c )
 {
+    const double t0_ = glue_clock();
     const uint8_t *sr = glue_resident( fref );
     if( !G.ctx || !sr )
         return 1;
@@ -323,6 +376,7 @@ static int glue_mbmc( void *hv, void *fref, int mb_x, int mb_y, const int16_t *m
     GLUE_CHECK( x264dsp_mc_frames_part_dev( G.ctx, &G.g, sr, 1, G.d_mv4, glue_pred(), NULL ) );
     glue_fetch_mb( glue_pred(), mb_x, mb_y, fdec_y, fdec_c );
     GLUE_CHECK( x264dsp_dev_zero( G.ctx, G.d_mv4 + xy * 8, 16, NULL ) );
+    G.seconds[6] += glue_clock() - t0_;
     G.calls[6]++;
     return 0;
 }
@@ -331,6 +385,7 @@ static int glue_mbmc( void *hv, void *fref, int mb_x, int mb_y, const int16_t *m
 static int glue_pskip( void *hv, void *fenc, void *fref, int mb_x, int mb_y, int mvx, int mvy, int qp, uint8_t *fdec_y,
                        uint8_t *fdec_c, int *skip )
 {
+    const double t0_ = glue_clock();
     const uint8_t *se = glue_resident( fenc ), *sr = glue_resident( fref );
     if( !G.ctx || !se || !sr )
         return 1;
@@ -344,6 +399,7 @@ static int glue_pskip( void *hv, void *fenc, void *fref, int mb_x, int mb_y, int
     GLUE_CHECK( x264dsp_d2h( G.ctx, &s, G.d_skip + xy, 1, NULL ) );
     GLUE_CHECK( x264dsp_dev_zero( G.ctx, G.d_pmv + xy * 2, 4, NULL ) );
     *skip = s;
+    G.seconds[5] += glue_clock() - t0_;
     G.calls[5]++;
     return 0;
 }
@@ -356,6 +412,7 @@ static uint8_t *glue_mb_chroma( uint8_t *slot ) { return slot + G.g1.slot_chroma
 static int glue_mbenc( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, uint8_t *fdec_y, uint8_t *fdec_c, int qp,
                        int kind, const uint8_t *i4_modes, int16_t *levels, int16_t *luma_dc, uint8_t *nnz, int *cbp )
 {
+    const double t0_ = glue_clock();
     x264_t *h = hv;
     glue_open( h );
     const x264dsp_geom_t *g1 = &G.g1;
@@ -403,6 +460,7 @@ static int glue_mbenc( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, u
     GLUE_CHECK( x264dsp_d2h( G.ctx, nnz, G.d_nnz, X264DSP_RES_NNZ_PER_MB, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, &c16, G.d_cbp1, sizeof(c16), NULL ) );
     *cbp = c16;
+    G.seconds[4] += glue_clock() - t0_;
     G.calls[4]++;
     return 0;
 }
@@ -412,6 +470,7 @@ static int glue_mbenc( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, u
  *      as x264_mb_predict_mv_ref16x16 takes them (common/mvpred.c:167-219) */
 static int glue_pframe( void *hv, xref_pframe_out_t *out )
 {
+    const double t0_ = glue_clock();
     x264_t *h = hv;
     x264_frame_t *fref = h->fref[0][0];
     const uint8_t *se = glue_resident( h->fenc ), *sr = glue_resident( fref );
@@ -465,6 +524,7 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     out->recon_c = G.h_pf_chroma + g->chroma_origin;
     out->stride_y = g->luma_stride;
     out->stride_c = g->chroma_stride;
+    G.seconds[8] += glue_clock() - t0_;
     G.calls[8]++;
     return 0;
 }
@@ -472,6 +532,7 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
 /* ---- the macroblock loop of a whole I slice: x264dsp_i_frames_dev on the resident source frame */
 static int glue_iframe( void *hv, xref_pframe_out_t *out )
 {
+    const double t0_ = glue_clock();
     x264_t *h = hv;
     const uint8_t *se = glue_resident( h->fenc );
     if( !G.ctx || !se )
@@ -504,6 +565,7 @@ static int glue_iframe( void *hv, xref_pframe_out_t *out )
     out->chroma_mode = G.h_if_cmode;
     out->modes4 = G.h_if_modes4;
     out->luma_dc = G.h_if_dc;
+    G.seconds[9] += glue_clock() - t0_;
     G.calls[9]++;
     return 0;
 }
@@ -523,6 +585,7 @@ void x264dsp_glue_install_iframe( void )
 
 void x264dsp_glue_install( void )
 {
+    G.t_install = glue_clock();
     xref_set_driver_hooks( glue_lowres, NULL, glue_cost );
     xref_set_fdec_hook( glue_fdec );
     xref_set_me_hook( glue_me );
@@ -556,9 +619,13 @@ int x264dsp_glue_report( FILE *out )
                     "\"me_search\": %d, \"macroblock_encode\": %d, \"probe_pskip\": %d, \"mb_mc\": %d, "
                     "\"door_me\": [%d, %d, %d], \"door_mbenc\": [%d, %d, %d], \"door_pskip\": [%d, %d, %d], "
                     "\"door_mbmc\": [%d, %d, %d], \"hook_calls\": [%d, %d, %d], \"p_frames\": %d, "
-                    "\"p_slices\": [%d, %d, %d], \"i_frames\": %d, \"i_slices\": [%d, %d, %d], \"kernel_launches\": %lld}\n",
+                    "\"p_slices\": [%d, %d, %d], \"i_frames\": %d, \"i_slices\": [%d, %d, %d], \"kernel_launches\": %lld, "
+                    "\"seconds\": {\"lowres\": %.4f, \"inloop_filter\": %.4f, \"lookahead_cost\": %.4f, \"p_frames\": %.4f, "
+                    "\"i_frames\": %.4f, \"per_macroblock_doors\": %.4f, \"open\": %.4f, \"since_install\": %.4f}}\n",
                     G.calls[0], G.calls[1], G.calls[7], G.calls[2], G.calls[3], G.calls[4], G.calls[5], G.calls[6],
                     doors[0], doors[1], doors[2], doors[3], doors[4], doors[5], doors[6], doors[7], doors[8], doors[9],
                     doors[10], doors[11], hook[0], hook[1], hook[2], G.calls[8], pf[0], pf[1], pf[2], G.calls[9], iff[0], iff[1], iff[2],
-                    G.ctx ? (long long)( x264dsp_launch_count( G.ctx ) - G.launches0 ) : 0LL );
+                    G.ctx ? (long long)( x264dsp_launch_count( G.ctx ) - G.launches0 ) : 0LL,
+                    G.seconds[0] - G.seconds_open, G.seconds[1], G.seconds[2], G.seconds[8], G.seconds[9],
+                    G.seconds[3] + G.seconds[4] + G.seconds[5] + G.seconds[6], G.seconds_open, glue_clock() - G.t_install );
 }

@@ -120,6 +120,9 @@ int x264dsp_d2h( x264dsp_ctx_t *ctx, void *host, const void *dev, size_t bytes, 
 /* pinned host memory: buffers obtained here are copied from / to directly by the *_host entry points */
 int x264dsp_host_alloc( x264dsp_ctx_t *ctx, size_t bytes, void **host );
 int x264dsp_host_free( x264dsp_ctx_t *ctx, void *host );
+/* ... or page-lock memory the caller already owns (the reference's x264_frame_t buffers: glue/x264dsp_glue.c) */
+int x264dsp_host_register( x264dsp_ctx_t *ctx, void *host, size_t bytes );
+int x264dsp_host_unregister( x264dsp_ctx_t *ctx, void *host );
 
 /* per-kernel timing with CUDA events recorded around each launch on its own stream.
  * kind: one of X264DSP_PROF_*; total_ms / count cover the launches since x264dsp_profile_enable. */
@@ -540,6 +543,10 @@ int x264dsp_p_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, cons
 int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
                            const x264dsp_pframe_params_t *params, int8_t *mb_type, int16_t *mv, int16_t *mvr, int16_t *mvd,
                            int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 );
+/* ... with partitions (x264dsp_p_frames_part_dev's outputs: partition [frame][mb], mv8 / mvd8 [frame][mb][4][2]) */
+int x264dsp_p_frames_part_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                                const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv8,
+                                int16_t *mvr, int16_t *mvd8, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 );
 
 /* ------------------------------------------------------------------ deblock
  * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's

@@ -81,11 +81,12 @@ def test_recon_frames_host(pkg, ctx, w, h, n, qp):
 
 
 @pytest.mark.parametrize("w,h,n,me,subme,qp", [(352, 288, 9, 0, 1, 28), (208, 160, 17, 1, 4, 26)])
-def test_p_frames_host_matches_oracle(pkg, ctx, w, h, n, me, subme, qp):
+def test_p_frames_host_matches_oracle(pkg, ctx, w, h, n, me, subme, qp, monkeypatch):
     """x264dsp_p_frames_host: pictures in host memory in, the coded P frames out -- reference planes, half-resolution planes,
     the lookahead's vectors and the macroblock loop all on the device, several stream groups -- against the oracle's
     xo_p_frame fed with the oracle's own planes and lookahead vectors"""
     import ctypes as C
+    monkeypatch.setenv("X264DSP_PF_HOST_GROUPS", "3")        # the default is one group per ~96 frames
     from cpu_checkers import ptr, i16p, i32p
     o = cc.oracle()
     go = cc.oracle_geom(w, h)
@@ -129,3 +130,49 @@ def test_p_frames_host_matches_oracle(pkg, ctx, w, h, n, me, subme, qp):
         wc = wrec[co:][: (g.luma_h // 2) * g.chroma_stride].reshape(g.luma_h // 2, g.chroma_stride)[: h // 2, :w]
         assert np.array_equal(recon[k][w * h: w * h + w * h // 4].reshape(h // 2, w // 2), wc[:, 0::2]), f"frame {k + 1}: U differs"
         assert np.array_equal(recon[k][w * h + w * h // 4:].reshape(h // 2, w // 2), wc[:, 1::2]), f"frame {k + 1}: V differs"
+
+
+@pytest.mark.parametrize("w,h,n,me,subme,qp", [(352, 288, 9, 1, 5, 24), (208, 160, 17, 0, 2, 28)])
+def test_p_frames_part_host_matches_oracle(pkg, ctx, w, h, n, me, subme, qp, monkeypatch):
+    """x264dsp_p_frames_part_host (analyse.inter = PSUB16x16) against xo_p_frame_part on the oracle's own planes and vectors"""
+    import ctypes as C
+    monkeypatch.setenv("X264DSP_PF_HOST_GROUPS", "2")
+    from cpu_checkers import ptr, i16p, i32p
+    o = cc.oracle()
+    go = cc.oracle_geom(w, h)
+    g = pkg.geometry(w, h)
+    nmb = g.mb_count
+    pics = np.stack([pkg.synth_frame(w, h, i, cut_frame=4) for i in range(n + 1)])
+    shapes = {"mb_type": ((nmb,), np.int8), "partition": ((nmb,), np.uint8), "mv8": ((nmb, 4, 2), np.int16), "mvr": ((nmb, 2), np.int16),
+              "mvd8": ((nmb, 4, 2), np.int16), "levels": ((nmb, 392), np.int16), "nnz": ((nmb, 27), np.uint8), "cbp": ((nmb,), np.int16)}
+    out = {k: np.zeros((n,) + s, t) for k, (s, t) in shapes.items()}
+    recon = np.zeros((n, w * h * 3 // 2), np.uint8)
+    ctx.p_frames_part_host(w, h, n, pics, pkg.PFrameParams(me, subme, 16, qp, 128, 1, 0, 1), out["mb_type"], out["partition"], out["mv8"],
+                           out["mvr"], out["mvd8"], out["levels"], out["nnz"], out["cbp"], recon)
+
+    class P(C.Structure):
+        _fields_ = [(k, C.c_int32) for k in ("me_method", "subpel_refine", "me_range", "qp", "mv_range", "fast_pskip", "mvc_scale", "analyse_inter")]
+    slots = [np.zeros(g.slot_bytes, np.uint8) for _ in range(n + 1)]
+    for i in range(n + 1):
+        o.xo_frame_load_i420(C.byref(go), ptr(pics[i]), ptr(slots[i]))
+        o.xo_frame_expand_border(C.byref(go), ptr(slots[i]))
+        o.xo_frame_filter(C.byref(go), ptr(slots[i]))
+        o.xo_frame_init_lowres(C.byref(go), ptr(slots[i]))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    seen = set()
+    for k in range(n):
+        lmv = np.zeros((nmb, 2), np.int16)
+        lc = np.zeros(nmb, np.int32)
+        ls = np.zeros(8, np.int32)
+        o.xo_lookahead_frame_cost(C.byref(go), ptr(slots[k + 1]), ptr(slots[k]), 0, ptr(lmv, i16p), ptr(lc, i32p), ptr(ls, i32p), None)
+        want = {key: np.zeros(s, t) for key, (s, t) in shapes.items()}
+        wrec = np.zeros(g.slot_bytes, np.uint8)
+        p = P(me, subme, 16, qp, 128, 1, 0, 1)
+        o.xo_p_frame_part(C.byref(go), ptr(slots[k + 1]), ptr(slots[k]), ptr(wrec), C.byref(p), vp(lmv), None,
+                          *[vp(want[key]) for key in ("mb_type", "partition", "mv8", "mvr", "mvd8", "levels", "nnz", "cbp")])
+        for key in want:
+            assert np.array_equal(out[key][k], want[key]), f"frame {k + 1}: {key} differs"
+        wy = wrec[g.luma_origin:][: g.luma_h * g.luma_stride].reshape(g.luma_h, g.luma_stride)[:h, :w]
+        assert np.array_equal(recon[k][: w * h].reshape(h, w), wy), f"frame {k + 1}: luma reconstruction differs"
+        seen |= set(np.unique(want["partition"]).tolist())
+    assert seen >= {13, 16}, seen

@@ -483,6 +483,15 @@ class Context:
                                           levels.ctypes.data_as(C.c_void_p), _hp(nnz), cbp.ctypes.data_as(C.c_void_p),
                                           _hp(recon_i420)), "x264dsp_p_frames_host")
 
+    def p_frames_part_host(self, w, h, n_frames, i420, prm, mb_type, partition, mv8, mvr, mvd8, levels, nnz, cbp, recon_i420):
+        """x264dsp_p_frames_part_host: as p_frames_host with partition uint8[n][mb] and mv8 / mvd8 int16[n][mb][4][2]"""
+        check(lib().x264dsp_p_frames_part_host(self._h, int(w), int(h), int(n_frames), _hp(i420), C.byref(prm),
+                                               mb_type.ctypes.data_as(C.c_void_p), _hp(partition), mv8.ctypes.data_as(C.c_void_p),
+                                               mvr.ctypes.data_as(C.c_void_p),
+                                               mvd8.ctypes.data_as(C.c_void_p) if mvd8 is not None else None,
+                                               levels.ctypes.data_as(C.c_void_p), _hp(nnz), cbp.ctypes.data_as(C.c_void_p),
+                                               _hp(recon_i420)), "x264dsp_p_frames_part_host")
+
     def residual_frames(self, g, fenc_slots, pred_slots, n_frames, qp, levels, nnz, cbp):
         check(lib().x264dsp_residual_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
                                                 int(qp), _dp(levels), _dp(nnz), _dp(cbp), None),

@@ -388,6 +388,29 @@ extern "C" int x264dsp_host_free( x264dsp_ctx_t *ctx, void *host )
     return 0;
 }
 
+// page-lock memory the caller already owns (an encoder's frame buffers), so that copies from / to it run at the link's rate
+extern "C" int x264dsp_host_register( x264dsp_ctx_t *ctx, void *host, size_t bytes )
+{
+    if( !ctx || !host || !bytes )
+        return X264DSP_E_ARG;
+    XD_CHECK( cudaSetDevice( ctx->device ) );
+    const cudaError_t e = cudaHostRegister( host, bytes, cudaHostRegisterDefault );
+    if( e != cudaSuccess )
+    {
+        (void)cudaGetLastError();                     // e.g. a page shared with an earlier registration: not sticky
+        return (int)e;
+    }
+    return 0;
+}
+
+extern "C" int x264dsp_host_unregister( x264dsp_ctx_t *ctx, void *host )
+{
+    if( !ctx || !host )
+        return X264DSP_E_ARG;
+    XD_CHECK( cudaHostUnregister( host ) );
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ profiling
 
 extern "C" int x264dsp_profile_enable( x264dsp_ctx_t *ctx, int on )

@@ -8,6 +8,7 @@
 // groups have drained.  Pinned caller buffers (x264dsp_host_alloc) are copied from / to directly; ordinary memory is
 // staged by the driver.
 #include <string.h>
+#include <cstdlib>
 #include "common.cuh"
 
 #define XH_CHECK( call ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { rc = (int)e_; goto drain; } } while( 0 )
@@ -246,10 +247,12 @@ drain:
 // half-resolution planes, the lookahead's vectors of each pair (the search's first candidate) -- then x264dsp_p_frames_dev;
 // types, vectors, mvr, mvd, levels, nnz, cbp and the reconstruction (planar I420) come back.  All copies are inside the call;
 // groups of frames run on separate streams (their wavefronts queue behind each other, their copies overlap).
-extern "C" int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
-                                       const x264dsp_pframe_params_t *params, int8_t *mb_type, int16_t *mv, int16_t *mvr,
-                                       int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 )
+// partition == NULL: x264dsp_p_frames_dev, one vector per macroblock; else x264dsp_p_frames_part_dev, four (one per 8x8)
+static int xh_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                             const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv, int16_t *mvr,
+                             int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 )
 {
+    const size_t nv = partition ? 4 : 1;
     if( !ctx || !i420 || !params || !mb_type || !mv || !mvr || !levels || !nnz || !cbp || !recon_i420 || n_frames <= 0 )
         return X264DSP_E_ARG;
     x264dsp_geom_t g;
@@ -259,10 +262,16 @@ extern "C" int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height,
     if( g.mb_w < 3 || g.mb_h < 3 )
         return X264DSP_E_ARG;
     const size_t pic = (size_t)width * height * 3 / 2, nmb = g.mb_count;
-    int groups = n_frames / 8;
+    // Stream groups: each group uploads, prepares, codes and downloads its frames on its own stream, so group k's copies run
+    // under group k+1's kernels.  The wavefront wants many frames per launch (a frame alone is latency bound) and two
+    // wavefront kernels do not share the SMs well: measured on 384 1080p frames (tools/bench_pframe_host.py, DIA / subme 1)
+    // 1 / 2 / 4 / 8 / 16 groups = 2.7 / 3.5 / 4.1 / 3.9 / 2.7 k frames/s -- about a hundred frames per group.
+    int groups = ( n_frames + 48 ) / 96;
+    if( const char *e = getenv( "X264DSP_PF_HOST_GROUPS" ) )     // measurement knob (tools/bench_pframe_host.py, tests)
+        groups = atoi( e );
     if( groups < 1 ) groups = 1;
     if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
-    const size_t per_mb = 1 + 4 * 2 * sizeof( int16_t ) + X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ) + X264DSP_RES_NNZ_PER_MB
+    const size_t per_mb = 2 + ( 2 + 2 * nv ) * 2 * sizeof( int16_t ) + X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ) + X264DSP_RES_NNZ_PER_MB
                         + sizeof( int16_t ) + 4 + X264DSP_LA_SUMS;
     const size_t side_bytes = ( (size_t)n_frames * nmb * per_mb + (size_t)n_frames * 64 + 8192 ) & ~(size_t)255;
     const size_t need_slots = (size_t)( 2 * n_frames + groups ) * g.slot_bytes;
@@ -276,15 +285,16 @@ extern "C" int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height,
     const size_t N = (size_t)n_frames * nmb;
     uint8_t *d_side = ctx->me_blocks;
     int16_t *d_lv = (int16_t *)d_side;      d_side += N * X264DSP_RES_LEVELS_PER_MB * 2;
-    int16_t *d_mv = (int16_t *)d_side;      d_side += N * 4;
+    int16_t *d_mv = (int16_t *)d_side;      d_side += N * 4 * nv;
+    int16_t *d_mvd = (int16_t *)d_side;     d_side += N * 4 * nv;
     int16_t *d_mvr = (int16_t *)d_side;     d_side += N * 4;
-    int16_t *d_mvd = (int16_t *)d_side;     d_side += N * 4;
     int16_t *d_lmv = (int16_t *)d_side;     d_side += N * 4;
     int32_t *d_lc = (int32_t *)d_side;      d_side += N * 4;
     int32_t *d_ls = (int32_t *)d_side;      d_side += ( (size_t)n_frames * X264DSP_LA_SUMS * 4 + 15 ) & ~(size_t)15;
     int16_t *d_cbp = (int16_t *)d_side;     d_side += ( N * 2 + 15 ) & ~(size_t)15;
     uint8_t *d_nz = d_side;                 d_side += ( N * X264DSP_RES_NNZ_PER_MB + 15 ) & ~(size_t)15;
-    int8_t *d_type = (int8_t *)d_side;
+    int8_t *d_type = (int8_t *)d_side;      d_side += ( N + 15 ) & ~(size_t)15;
+    uint8_t *d_part = d_side;
 
     int used = 0;
     size_t slot_cursor = 0, pic_cursor = 0;
@@ -322,15 +332,22 @@ extern "C" int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height,
             XH_RC( x264dsp_lookahead_frame_cost_dev( ctx, &g, d_src, nf, b, p0, wi, d_lmv + m0 * 2, d_lc + m0,
                                                      d_ls + (size_t)f0 * X264DSP_LA_SUMS, NULL, st ) );
         }
-        XH_RC( x264dsp_p_frames_dev( ctx, &g, d_src + g.slot_bytes, d_src, d_rec, nf, params, d_lmv + m0 * 2, NULL, d_type + m0,
-                                     d_mv + m0 * 2, d_mvr + m0 * 2, d_mvd + m0 * 2, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
-                                     d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, st ) );
+        if( partition )
+            XH_RC( x264dsp_p_frames_part_dev( ctx, &g, d_src + g.slot_bytes, d_src, d_rec, nf, params, d_lmv + m0 * 2, NULL, d_type + m0,
+                                              d_part + m0, d_mv + m0 * 8, d_mvr + m0 * 2, d_mvd + m0 * 8,
+                                              d_lv + m0 * X264DSP_RES_LEVELS_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, st ) );
+        else
+            XH_RC( x264dsp_p_frames_dev( ctx, &g, d_src + g.slot_bytes, d_src, d_rec, nf, params, d_lmv + m0 * 2, NULL, d_type + m0,
+                                         d_mv + m0 * 2, d_mvr + m0 * 2, d_mvd + m0 * 2, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
+                                         d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, st ) );
         XH_RC( x264dsp_frame_store_i420_dev( ctx, &g, d_rec, d_out_pics + (size_t)f0 * pic, nf, st ) );
         XH_CHECK( cudaMemcpyAsync( mb_type + m0, d_type + m0, mn, cudaMemcpyDeviceToHost, st ) );
-        XH_CHECK( cudaMemcpyAsync( mv + m0 * 2, d_mv + m0 * 2, mn * 4, cudaMemcpyDeviceToHost, st ) );
+        if( partition )
+            XH_CHECK( cudaMemcpyAsync( partition + m0, d_part + m0, mn, cudaMemcpyDeviceToHost, st ) );
+        XH_CHECK( cudaMemcpyAsync( mv + m0 * 2 * nv, d_mv + m0 * 2 * nv, mn * 4 * nv, cudaMemcpyDeviceToHost, st ) );
         XH_CHECK( cudaMemcpyAsync( mvr + m0 * 2, d_mvr + m0 * 2, mn * 4, cudaMemcpyDeviceToHost, st ) );
         if( mvd )
-            XH_CHECK( cudaMemcpyAsync( mvd + m0 * 2, d_mvd + m0 * 2, mn * 4, cudaMemcpyDeviceToHost, st ) );
+            XH_CHECK( cudaMemcpyAsync( mvd + m0 * 2 * nv, d_mvd + m0 * 2 * nv, mn * 4 * nv, cudaMemcpyDeviceToHost, st ) );
         XH_CHECK( cudaMemcpyAsync( levels + m0 * X264DSP_RES_LEVELS_PER_MB, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
                                    mn * X264DSP_RES_LEVELS_PER_MB * 2, cudaMemcpyDeviceToHost, st ) );
         XH_CHECK( cudaMemcpyAsync( nnz + m0 * X264DSP_RES_NNZ_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB, mn * X264DSP_RES_NNZ_PER_MB,
@@ -350,4 +367,21 @@ drain:
     ctx->scratch_busy[XD_SCRATCH_DEBLOCK] = 0;
     ctx->scratch_busy[XD_SCRATCH_LOOKAHEAD] = 0;
     return rc;
+}
+
+extern "C" int x264dsp_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                                       const x264dsp_pframe_params_t *params, int8_t *mb_type, int16_t *mv, int16_t *mvr,
+                                       int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 )
+{
+    return xh_p_frames_host( ctx, width, height, n_frames, i420, params, mb_type, nullptr, mv, mvr, mvd, levels, nnz, cbp, recon_i420 );
+}
+
+extern "C" int x264dsp_p_frames_part_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                                            const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition,
+                                            int16_t *mv8, int16_t *mvr, int16_t *mvd8, int16_t *levels, uint8_t *nnz, int16_t *cbp,
+                                            uint8_t *recon_i420 )
+{
+    if( !partition )
+        return X264DSP_E_ARG;
+    return xh_p_frames_host( ctx, width, height, n_frames, i420, params, mb_type, partition, mv8, mvr, mvd8, levels, nnz, cbp, recon_i420 );
 }
