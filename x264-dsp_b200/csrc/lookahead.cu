@@ -746,12 +746,38 @@ __device__ __forceinline__ uint2 xd_lm_assemble( uint2 lo, uint2 hi, uint32_t sh
     return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
 }
 
+// LA_WORD_LOADS (a measured alternative, off): the 8 (or 12) bytes a lane needs from a tiled row start at an arbitrary byte,
+// i.e. they are three (four) consecutive 32-bit words of the ROW -- which in the tiled plane sit at byte offsets {0,4,64,68}
+// or {4,64,68,128} from the row chunk of the tile holding X, depending on which half of the chunk X falls in.  Loading those
+// words one by one (offsets = two multiply-adds on the FMA pipe per fetch) needs no selects: SEL 229 -> 79 in the SASS of
+// xd_la_multi_kernel<4>, LDG 127 -> 174.  Measured on B200 (bench.py --no-me, 1792 pairs per launch): 4.87 ms per launch
+// against 4.23 ms with the 8-byte loads + three SELs per row (4.94 ms with the registers held at 80) -- the extra L1
+// wavefronts cost more than the selects saved; the ALU pipe is not the only thing this kernel is short of.
+#ifndef LA_WORD_LOADS
+#define LA_WORD_LOADS 0
+#endif
+
 // the lane's RPL rows, 8 pixels each, at padded coordinates (X,Y) of the tiled plane at byte offset poff
 template<int RPL>
 __device__ __forceinline__ void xd_lm_tile( const xd_lm_block<RPL> &B, int poff, int X, int Y, uint2 out[RPL] )
 {
     const int off = poff + ( ( ( Y >> 3 ) * B.tw + ( X >> 3 ) ) << 6 ) + ( ( Y & 7 ) << 3 );
     const uint32_t sh = (uint32_t)X << 3;
+#if LA_WORD_LOADS
+    const int up = ( X >> 2 ) & 1;
+    const int o0 = up * 4, o1 = 4 + up * 60, o2 = 64 + up * 4;
+    const uint8_t *w = B.tref + off;
+    const uint32_t a0 = __ldg( (const uint32_t *)( w + o0 ) ), a1 = __ldg( (const uint32_t *)( w + o1 ) ),
+                   a2 = __ldg( (const uint32_t *)( w + o2 ) );
+    if( RPL == 2 )
+    {
+        const uint8_t *w1 = w + ( ( Y & 7 ) == 7 ? ( B.tw << 6 ) - 56 : 8 );
+        const uint32_t b0 = __ldg( (const uint32_t *)( w1 + o0 ) ), b1 = __ldg( (const uint32_t *)( w1 + o1 ) ),
+                       b2 = __ldg( (const uint32_t *)( w1 + o2 ) );
+        out[RPL - 1] = make_uint2( __funnelshift_r( b0, b1, sh ), __funnelshift_r( b1, b2, sh ) );
+    }
+    out[0] = make_uint2( __funnelshift_r( a0, a1, sh ), __funnelshift_r( a1, a2, sh ) );
+#else
     const bool up = ( X & 4 ) != 0;
     const uint2 *w = (const uint2 *)( B.tref + off );
     const uint2 lo = __ldg( w ), hi = __ldg( w + 8 );
@@ -763,6 +789,7 @@ __device__ __forceinline__ void xd_lm_tile( const xd_lm_block<RPL> &B, int poff,
         out[RPL - 1] = xd_lm_assemble( lo1, hi1, sh, up );
     }
     out[0] = xd_lm_assemble( lo, hi, sh, up );
+#endif
 }
 
 // the lane's rows of the prediction at quarter-pel (qx,qy): get_ref / mc_luma (mc.c:192-264)
@@ -828,6 +855,26 @@ __device__ __forceinline__ void xd_lm_sad_dia( const xd_lm_block<RPL> &B, int mx
         const bool hi4 = ( o & 4 ) != 0, third = o == 7;
         const int jump = ( B.tw << 6 ) - 56;                       // from row 7 of a tile to row 0 of the tile below
         uint32_t V[4][3];                                          // bytes X-1 .. X+10 of the four rows
+#if LA_WORD_LOADS
+        const int hw = hi4 ? 1 : 0;
+        const int o0 = hw * 4, o1 = 4 + hw * 60, o2 = 64 + hw * 4, o3 = 68 + hw * 60;
+        const bool fourth = ( o & 3 ) == 3;                        // only then do bytes of a fourth word reach columns X-1 .. X+8
+        (void)third;
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            const uint8_t *w = B.tref + off;
+            const uint32_t w0 = __ldg( (const uint32_t *)( w + o0 ) ), w1 = __ldg( (const uint32_t *)( w + o1 ) ),
+                           w2 = __ldg( (const uint32_t *)( w + o2 ) );
+            uint32_t w3 = 0;
+            if( fourth )
+                w3 = __ldg( (const uint32_t *)( w + o3 ) );
+            V[r][0] = __funnelshift_r( w0, w1, sh );
+            V[r][1] = __funnelshift_r( w1, w2, sh );
+            V[r][2] = __funnelshift_r( w2, w3, sh );
+            off += ( ( R0 + r ) & 7 ) == 7 ? jump : 8;
+        }
+#else
 #pragma unroll
         for( int r = 0; r < 4; r++ )
         {
@@ -842,6 +889,7 @@ __device__ __forceinline__ void xd_lm_sad_dia( const xd_lm_block<RPL> &B, int mx
             V[r][2] = __funnelshift_r( w2, w3, sh );
             off += ( ( R0 + r ) & 7 ) == 7 ? jump : 8;
         }
+#endif
         uint2 c[4];                                                // the rows at column X
 #pragma unroll
         for( int r = 0; r < 4; r++ )
@@ -895,6 +943,19 @@ __device__ __forceinline__ void xd_lm_sad_hpel_dia( const xd_lm_block<RPL> &B, i
             const uint32_t sh = (uint32_t)X << 3;
             const bool hi4 = ( X & 4 ) != 0;
             uint2 c[3];
+#if LA_WORD_LOADS
+            const int hw = hi4 ? 1 : 0;
+            const int o0 = hw * 4, o1 = 4 + hw * 60, o2 = 64 + hw * 4;
+#pragma unroll
+            for( int r = 0; r < 3; r++ )
+            {
+                const uint8_t *w = B.tref + off;
+                const uint32_t w0 = __ldg( (const uint32_t *)( w + o0 ) ), w1 = __ldg( (const uint32_t *)( w + o1 ) ),
+                               w2 = __ldg( (const uint32_t *)( w + o2 ) );
+                c[r] = make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+                off += ( ( R0 + r ) & 7 ) == 7 ? jump : 8;
+            }
+#else
 #pragma unroll
             for( int r = 0; r < 3; r++ )
             {
@@ -902,6 +963,7 @@ __device__ __forceinline__ void xd_lm_sad_hpel_dia( const xd_lm_block<RPL> &B, i
                 c[r] = xd_lm_assemble( __ldg( w ), __ldg( w + 8 ), sh, hi4 );
                 off += ( ( R0 + r ) & 7 ) == 7 ? jump : 8;
             }
+#endif
             up = xd_lq_sad8( c[1], B.fenc[1], xd_lq_sad8( c[0], B.fenc[0], 0u ) );
             dn = xd_lq_sad8( c[2], B.fenc[1], xd_lq_sad8( c[1], B.fenc[0], 0u ) );
         }
@@ -912,6 +974,22 @@ __device__ __forceinline__ void xd_lm_sad_hpel_dia( const xd_lm_block<RPL> &B, i
             const uint32_t sh = (uint32_t)XL << 3;
             const bool hi4 = ( XL & 4 ) != 0;
             uint32_t V[2][3];
+#if LA_WORD_LOADS
+            // columns XL .. XL+8: nine bytes from byte (XL & 3) of the first word, so a fourth word never contributes
+            const int hw = hi4 ? 1 : 0;
+            const int o0 = hw * 4, o1 = 4 + hw * 60, o2 = 64 + hw * 4;
+#pragma unroll
+            for( int r = 0; r < 2; r++ )
+            {
+                const uint8_t *w = B.tref + off;
+                const uint32_t w0 = __ldg( (const uint32_t *)( w + o0 ) ), w1 = __ldg( (const uint32_t *)( w + o1 ) ),
+                               w2 = __ldg( (const uint32_t *)( w + o2 ) );
+                V[r][0] = __funnelshift_r( w0, w1, sh );
+                V[r][1] = __funnelshift_r( w1, w2, sh );
+                V[r][2] = __funnelshift_r( w2, 0u, sh );
+                off += ( Y & 7 ) == 7 ? jump : 8;
+            }
+#else
 #pragma unroll
             for( int r = 0; r < 2; r++ )
             {
@@ -923,6 +1001,7 @@ __device__ __forceinline__ void xd_lm_sad_hpel_dia( const xd_lm_block<RPL> &B, i
                 V[r][2] = __funnelshift_r( w2, w3, sh );
                 off += ( Y & 7 ) == 7 ? jump : 8;
             }
+#endif
             lf = xd_lq_sad8( make_uint2( V[1][0], V[1][1] ), B.fenc[1], xd_lq_sad8( make_uint2( V[0][0], V[0][1] ), B.fenc[0], 0u ) );
             const uint2 r0 = make_uint2( __funnelshift_r( V[0][0], V[0][1], 8 ), __funnelshift_r( V[0][1], V[0][2], 8 ) );
             const uint2 r1 = make_uint2( __funnelshift_r( V[1][0], V[1][1], 8 ), __funnelshift_r( V[1][1], V[1][2], 8 ) );
