@@ -193,7 +193,9 @@ int x264dsp_frame_retile_lowres_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g
 /* ------------------------------------------------------------------ block costs
  * x264_pixel_function_t::sad / ssd / satd  (common/pixel.c:44-102, 267-337) on n independent
  * block pairs.  Block i compares  pix1 + off1[i] (stride1)  with  pix2 + off2[i] (stride2);
- * size[i] is an X264DSP_PIXEL_* value.  off1/off2/size/out are device arrays. */
+ * size[i] is an X264DSP_PIXEL_* value.  off1/off2/size/out are device arrays.
+ * The kernels assemble unaligned rows from aligned 32-bit words and always fetch the word after the last one they need:
+ * pix1 and pix2 must have at least 4 readable bytes after the last byte of the last block (frame slots do: they are padded). */
 int x264dsp_cost_batch_dev( x264dsp_ctx_t *ctx, int cmp, int n,
                             const uint8_t *pix1, const int64_t *off1, int stride1,
                             const uint8_t *pix2, const int64_t *off2, int stride2,

@@ -16,6 +16,9 @@
  * x264dsp_b200.h are the fast path with identical per-block semantics.  The shims use a process
  * wide context on device $X264DSP_DEVICE (default 0), created by the first init call; if no CUDA
  * device can be opened the init functions abort() -- there is no CPU fallback to fall back to.
+ * All shims stage through ONE buffer of that context: table members must be called from one thread at a time (the
+ * reference itself has no slice or lookahead threads; two encoders in two threads of one process need a lock around their
+ * table calls, or the frame-batched entry points, which take a context per caller).
  *
  * Members the hot path does not cover stay NULL, exactly as listed in DESIGN.md ("out of scope"):
  * coeff_level_run*, denoise_dct (entropy side / off by default), intra_*_x4_4x4_{h,v} and

@@ -72,16 +72,18 @@ def _rank_main(rank, world, port, w, h, n, q):
         dist.all_gather(parts, pad)
         return np.concatenate([p[: int(s.item())].numpy() for p, s in zip(parts, sizes)]).astype(a.dtype)
 
-    first, mvs, costs, sums = pkg.lookahead_sharded(oracle_analyse(w, h), luma, rank, world)
-    _, gm, gc, gs = pkg.lookahead_sharded(oracle_analyse(w, h), luma, rank, world, gather=gather)
+    mbc = cc.oracle_geom(w, h).mb_count
+    first, mvs, costs, sums = pkg.lookahead_sharded(oracle_analyse(w, h), luma, rank, world, mb_count=mbc)
+    _, gm, gc, gs = pkg.lookahead_sharded(oracle_analyse(w, h), luma, rank, world, gather=gather, mb_count=mbc)
     q.put((rank, first, mvs, costs, sums, gm, gc, gs))
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_lookahead_sharded_two_ranks_gloo(pkg):
+@pytest.mark.parametrize("n,world", [(7, 2), (2, 3)])       # (2, 3): more ranks than frames, one rank owns nothing
+def test_lookahead_sharded_two_ranks_gloo(pkg, n, world):
     import torch.multiprocessing as mp
-    w, h, n, world = 176, 144, 7, 2
+    w, h = 176, 144
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -98,6 +100,7 @@ def test_lookahead_sharded_two_ranks_gloo(pkg):
     want_m, want_c, want_s = oracle_analyse(w, h)(luma)
     stitched = [np.concatenate([g[k] for g in got]) for k in (2, 3, 4)]
     assert got[0][1] == 0 and got[1][1] == pkg.frame_range(n, 1, world)[0]
+    assert all(g[2].shape[1:] == want_m.shape[1:] and g[3].shape[1:] == want_c.shape[1:] for g in got)     # empty ranks too
     assert np.array_equal(stitched[0], want_m) and np.array_equal(stitched[1], want_c)
     assert np.array_equal(stitched[2][:, :5], want_s[:, :5])
     for g in got:       # gathered view: every rank holds the full-sequence tables

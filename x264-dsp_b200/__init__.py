@@ -195,7 +195,7 @@ def gop_shard(gops, rank, world):
     return gops[first.value: first.value + n.value]
 
 
-def lookahead_sharded(analyse, luma, rank, world, gather=None):
+def lookahead_sharded(analyse, luma, rank, world, gather=None, mb_count=None):
     """Frame-range sharded lookahead pass of ONE sequence.
 
     `luma` [n, h*w] is the whole sequence (every rank sees the same host input; only its own range
@@ -206,14 +206,17 @@ def lookahead_sharded(analyse, luma, rank, world, gather=None):
     sequence keeps its intra-only result.  If `gather` is given (a callable doing an all-gather of
     a numpy array along axis 0, e.g. over torch.distributed) every rank gets the full-sequence
     arrays instead -- the only collective of the path, and an optional one.
+    `mb_count` (lowres blocks per frame) shapes the empty result of a rank that owns no frame (world > n); with a `gather`
+    it must be given so that every rank contributes arrays of the same trailing shape.
     """
     n = luma.shape[0]
     first, count, need_prev = frame_range(n, rank, world)
     lo = first - 1 if need_prev else first
     if count == 0:
-        g = None
-        mvs = np.zeros((0,), np.int16)
-        costs = np.zeros((0,), np.int32)
+        if mb_count is None and gather is not None:
+            raise ValueError("lookahead_sharded: a rank without frames needs mb_count to shape what it gathers")
+        mvs = np.zeros((0, mb_count or 0, 2), np.int16)
+        costs = np.zeros((0, mb_count or 0), np.int32)
         sums = np.zeros((0, LA_SUMS), np.int32)
     else:
         mvs, costs, sums = analyse(luma[lo:first + count])
