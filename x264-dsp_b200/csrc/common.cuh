@@ -143,6 +143,15 @@ __device__ __forceinline__ uint32_t xd_avg4( uint32_t a, uint32_t b )
     return ( a | b ) - ( ( ( a ^ b ) & 0xFEFEFEFEu ) >> 1 );
 }
 
+// clip to 0..255 and pack four values, a0 in the lowest byte (two I2IP)
+__device__ __forceinline__ uint32_t xd_pack_sat4( int a0, int a1, int a2, int a3 )
+{
+    uint32_t t, d;
+    asm( "cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"( t ) : "r"( a3 ), "r"( a2 ), "r"( 0 ) );
+    asm( "cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a1 ), "r"( a0 ), "r"( t ) );
+    return d;
+}
+
 // four-pixel SAD with accumulate: one VABSDIFF4.U8.ACC
 __device__ __forceinline__ uint32_t xd_sad4( uint32_t a, uint32_t b, uint32_t acc )
 {

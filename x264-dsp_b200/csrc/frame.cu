@@ -418,14 +418,6 @@ __device__ __forceinline__ int xd_dp2a_hi_us( uint32_t a, uint32_t b, int c )
     asm( "dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a ), "r"( b ), "r"( c ) );
     return d;
 }
-// clip to 0..255 and pack four values, a0 in the lowest byte
-__device__ __forceinline__ uint32_t xd_pack_sat4( int a0, int a1, int a2, int a3 )
-{
-    uint32_t t, d;
-    asm( "cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"( t ) : "r"( a3 ), "r"( a2 ), "r"( 0 ) );
-    asm( "cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a1 ), "r"( a0 ), "r"( t ) );
-    return d;
-}
 
 template<int GW>
 __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *__restrict__ slot, int unit0, int strip_units, int wseg,

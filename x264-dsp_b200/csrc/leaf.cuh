@@ -75,18 +75,20 @@ __device__ __forceinline__ void xd_inv4( int a, int b, int c, int d, int &o0, in
     o0 = e + gg; o1 = f + hh; o2 = f - hh; o3 = e - gg;
 }
 
-// residual 4x4 DCT: f, p = four packed rows each (dct.c:115-150)
+// residual 4x4 DCT: f, p = four packed rows each (dct.c:115-150).  The horizontal stage of a row is four dot products of
+// its differences with (1,1,1,1) (2,1,-1,-2) (1,-1,-1,1) (1,-2,2,-1); a difference never has to exist as a number: the source
+// bytes take the weights, the prediction bytes their negatives (IDP.4A u8 x s8, FMA pipe).  8 IDP per row against 20 ALU
+// instructions for unpack / subtract / butterfly.
 __device__ __forceinline__ void xd_sub4x4_dct( int dct[16], const uint32_t f[4], const uint32_t p[4] )
 {
     int t[16];
 #pragma unroll
     for( int r = 0; r < 4; r++ )
     {
-        const int d0 = (int)( f[r] & 255 ) - (int)( p[r] & 255 );
-        const int d1 = (int)( ( f[r] >> 8 ) & 255 ) - (int)( ( p[r] >> 8 ) & 255 );
-        const int d2 = (int)( ( f[r] >> 16 ) & 255 ) - (int)( ( p[r] >> 16 ) & 255 );
-        const int d3 = (int)( f[r] >> 24 ) - (int)( p[r] >> 24 );
-        xd_fwd4( d0, d1, d2, d3, t[r], t[4 + r], t[8 + r], t[12 + r] );
+        t[r]      = xd_dp4a_u8s8( f[r], 0x01010101u, xd_dp4a_u8s8( p[r], 0xFFFFFFFFu, 0 ) );
+        t[4 + r]  = xd_dp4a_u8s8( f[r], 0xFEFF0102u, xd_dp4a_u8s8( p[r], 0x0201FFFEu, 0 ) );
+        t[8 + r]  = xd_dp4a_u8s8( f[r], 0x01FFFF01u, xd_dp4a_u8s8( p[r], 0xFF0101FFu, 0 ) );
+        t[12 + r] = xd_dp4a_u8s8( f[r], 0xFF02FE01u, xd_dp4a_u8s8( p[r], 0x01FE02FFu, 0 ) );
     }
 #pragma unroll
     for( int i = 0; i < 4; i++ )
@@ -113,15 +115,12 @@ __device__ __forceinline__ void xd_add4x4_idct( uint32_t p[4], const int dct[16]
         r[i] = (int16_t)( ( o0 + 32 ) >> 6 ); r[4 + i] = (int16_t)( ( o1 + 32 ) >> 6 );
         r[8 + i] = (int16_t)( ( o2 + 32 ) >> 6 ); r[12 + i] = (int16_t)( ( o3 + 32 ) >> 6 );
     }
+    // prediction byte + residual = one dot product of the packed row with a unit weight, accumulated onto the residual;
+    // clip and pack two samples per I2IP
 #pragma unroll
     for( int y = 0; y < 4; y++ )
-    {
-        uint32_t w = 0;
-#pragma unroll
-        for( int x = 0; x < 4; x++ )
-            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + r[4 * y + x] ) << ( 8 * x );
-        p[y] = w;
-    }
+        p[y] = xd_pack_sat4( xd_dp4a_u8s8( p[y], 0x00000001u, r[4 * y] ), xd_dp4a_u8s8( p[y], 0x00000100u, r[4 * y + 1] ),
+                             xd_dp4a_u8s8( p[y], 0x00010000u, r[4 * y + 2] ), xd_dp4a_u8s8( p[y], 0x01000000u, r[4 * y + 3] ) );
 }
 
 __device__ __forceinline__ void xd_add4x4_dc( uint32_t p[4], int dc )
@@ -129,19 +128,21 @@ __device__ __forceinline__ void xd_add4x4_dc( uint32_t p[4], int dc )
     dc = (int16_t)( ( dc + 32 ) >> 6 );
 #pragma unroll
     for( int y = 0; y < 4; y++ )
-    {
-        uint32_t w = 0;
-#pragma unroll
-        for( int x = 0; x < 4; x++ )
-            w |= (uint32_t)xd_clip_u8( (int)( ( p[y] >> ( 8 * x ) ) & 255 ) + dc ) << ( 8 * x );
-        p[y] = w;
-    }
+        p[y] = xd_pack_sat4( xd_dp4a_u8s8( p[y], 0x00000001u, dc ), xd_dp4a_u8s8( p[y], 0x00000100u, dc ),
+                             xd_dp4a_u8s8( p[y], 0x00010000u, dc ), xd_dp4a_u8s8( p[y], 0x01000000u, dc ) );
 }
 
-// quant.c:29-36
+// quant.c:29-36: coef > 0 ? (bias + coef) * mf >> 16 : -((bias - coef) * mf >> 16), i.e. (bias + |coef|) * mf >> 16 with the
+// sign put back.  |coef| < 2^15, mf <= 26214 and bias * mf <= 2^15 for every table the reference builds, so nothing wraps
+// and the dctcoef store truncates nothing; bias * mf is the same for all coefficients of a class (one multiply-add each).
+__device__ __forceinline__ uint32_t xd_quant1_abs( int c, int mf, int bias )
+{
+    return ( (uint32_t)abs( c ) * (uint32_t)mf + (uint32_t)bias * (uint32_t)mf ) >> 16;
+}
 __device__ __forceinline__ int xd_quant1( int c, int mf, int bias )
 {
-    return (int16_t)( c > 0 ? ( ( bias + c ) * mf ) >> 16 : -( ( ( bias - c ) * mf ) >> 16 ) );
+    const int s = c >> 31;
+    return ( (int)xd_quant1_abs( c, mf, bias ) ^ s ) - s;
 }
 
 // position class of coefficient i for the flat quant matrices: 0 (even,even) 1 (mixed) 2 (odd,odd)
@@ -152,6 +153,27 @@ struct xd_qparams
     int mf[3], bias[3], dmf[3];      // per position class
     int qbits;                       // qp/6 - 4
 };
+
+// position of raster coefficient i in zig-zag order (the inverse of xd_zigzag below)
+#define XD_ZZ_POS( i ) ( ( 0xFDC6EB75A8419320ull >> ( 4 * ( i ) ) ) & 15 )
+
+// quant + what the decimation score needs: min(|level|, 2) of every coefficient as a 2-bit code at its ZIG-ZAG position
+// (the absolute level exists on the way anyway); xd_decimate_codes then scores a block with a dozen bit operations instead
+// of walking sixteen levels.  Returns nz like xd_quant_4x4.
+__device__ __forceinline__ int xd_quant_4x4_codes( int dct[16], const xd_qparams &Q, uint32_t &codes )
+{
+    uint32_t w = 0;
+#pragma unroll
+    for( int i = 0; i < 16; i++ )
+    {
+        const int s = dct[i] >> 31;
+        const uint32_t q = xd_quant1_abs( dct[i], Q.mf[XD_POS_CLASS( i )], Q.bias[XD_POS_CLASS( i )] );
+        dct[i] = ( (int)q ^ s ) - s;
+        w += min( q, 2u ) << ( 2 * (int)XD_ZZ_POS( i ) );
+    }
+    codes = w;
+    return w != 0;
+}
 
 __device__ __forceinline__ int xd_quant_4x4( int dct[16], const xd_qparams &Q )
 {
@@ -170,9 +192,10 @@ __device__ __forceinline__ void xd_dequant_4x4( int dct[16], const xd_qparams &Q
 {
     if( Q.qbits >= 0 )
     {
+        const int m[3] = { Q.dmf[0] << Q.qbits, Q.dmf[1] << Q.qbits, Q.dmf[2] << Q.qbits };      // (a * b) << s == a * (b << s) mod 2^32
 #pragma unroll
         for( int i = 0; i < 16; i++ )
-            dct[i] = (int16_t)( ( dct[i] * Q.dmf[XD_POS_CLASS( i )] ) << Q.qbits );
+            dct[i] = (int16_t)( dct[i] * m[XD_POS_CLASS( i )] );
     }
     else
     {
@@ -217,6 +240,24 @@ __device__ __forceinline__ int xd_decimate( const int lv[16], int first )
     if( seen )
         score += run == 0 ? 3 : run <= 2 ? 2 : run <= 5 ? 1 : 0;
     return big ? 9 : score;
+}
+
+// x264_decimate_score_internal on the 2-bit codes of xd_quant_4x4_codes.  A level above 1 anywhere scores 9.  Otherwise every
+// nonzero level adds table[run] with run = the zeros between it and the next lower nonzero level (table = 3 2 2 1 1 1 0 ...):
+// "run <= k" is "one of the k+1 positions below is set", so the three thresholds are three AND + POPC; the lowest nonzero
+// level has nothing below it and counts its zeros down to `first` (1 for chroma AC: position 0 is the DC's) separately.
+__device__ __forceinline__ int xd_decimate_codes( uint32_t codes, int first )
+{
+    if( first )
+        codes &= ~3u;
+    if( codes & 0xAAAAAAAAu )
+        return 9;
+    if( !codes )
+        return 0;
+    const uint32_t n = codes;
+    const uint32_t b = ( n << 2 ) | ( n << 4 ) | ( n << 6 ), c = b | ( n << 8 ) | ( n << 10 ) | ( n << 12 );
+    const int run0 = ( ( __ffs( (int)n ) - 1 ) >> 1 ) - first;
+    return __popc( n & ( n << 2 ) ) + __popc( n & b ) + __popc( n & c ) + ( run0 == 0 ? 3 : run0 <= 2 ? 2 : run0 <= 5 ? 1 : 0 );
 }
 
 __device__ __forceinline__ void xd_store_levels( int16_t *dst, const int lv[16] )

@@ -76,9 +76,7 @@ __device__ __forceinline__ int xd_pf_probe( const xd_pf_args &A, const uint8_t *
                                             uint32_t pskip, int lane )
 {
     const int16_t mvs[2] = { (int16_t)( pskip & 0xFFFF ), (int16_t)( pskip >> 16 ) };
-#pragma unroll 1
-    for( int half = 0; half < 2; half++ )
-        xd_mc_mb<1>( A.g, fref, mvs, recon, mb, lane + 32 * half );
+    xd_mc_mb32<1>( A.g, fref, mvs, recon, mb % A.g.mb_w, mb / A.g.mb_w, lane );
     __syncwarp();
     const int ok = xd_residual_mb<false, true>( A.g, fenc, recon, A.T, nullptr, nullptr, nullptr, nullptr, nullptr, mb, lane );
     __syncwarp();
@@ -263,9 +261,7 @@ xd_pframe_kernel( xd_pf_args A )
                 __syncwarp();                                   // the block description is free for the next macroblock
                 // ---- x264_macroblock_encode, inter branch: x264_mb_mc, residual, forced P_SKIP (macroblock.c:379-485)
                 const int16_t v[2] = { (int16_t)( out_mv & 0xFFFF ), (int16_t)( out_mv >> 16 ) };
-#pragma unroll 1
-                for( int half = 0; half < 2; half++ )
-                    xd_mc_mb<1>( g, fref, v, recon, xy, lane + 32 * half );
+                xd_mc_mb32<1>( g, fref, v, recon, mb_x, mb_y, lane );
                 __syncwarp();
                 out_cbp = xd_residual_mb<false, false>( g, fenc, recon, A.T, levels, nnz, cbp, nullptr, nullptr, xy, lane );
                 if( !( out_cbp & 0x3f ) && out_mv == pskip )
@@ -682,9 +678,7 @@ xd_pframe_part_kernel( xd_pf_args A )
                 }
                 __syncwarp();
                 // ---- x264_macroblock_encode, inter branch: x264_mb_mc per partition, residual, forced P_SKIP
-#pragma unroll 1
-                for( int half = 0; half < 2; half++ )
-                    xd_mc_mb<4>( g, fref, (const int16_t *)S->final_mv, recon, xy, lane + 32 * half );
+                xd_mc_mb32<4>( g, fref, (const int16_t *)S->final_mv, recon, mb_x, mb_y, lane );
                 __syncwarp();
                 out_cbp = xd_residual_mb<false, false>( g, fenc, recon, A.T, levels, nnz, cbp, nullptr, nullptr, xy, lane );
                 if( type == X264DSP_MB_P_L0 && part == 16 && !( out_cbp & 0x3f ) && S->final_mv[0] == pskip )

@@ -27,18 +27,33 @@ __global__ void __launch_bounds__( 256 )
 xd_mc_frame_kernel( x264dsp_geom_t g, const uint8_t *__restrict__ fref, const int16_t *__restrict__ mv,
                     uint8_t *__restrict__ pred )
 {
-    const int mb = blockIdx.x * 4 + ( threadIdx.x >> 6 );
-    if( mb >= g.mb_count )
+    // a warp per macroblock, eight macroblocks of a macroblock row per CTA (blockIdx.y = the row: no division anywhere)
+    const int mb_x = blockIdx.x * 8 + ( threadIdx.x >> 5 ), mb_y = blockIdx.y;
+    if( mb_x >= g.mb_w )
         return;
-    // blockIdx.y = frame of a batch: consecutive slots, mb_count MVs per frame
-    fref += blockIdx.y * (size_t)g.slot_bytes;
-    pred += blockIdx.y * (size_t)g.slot_bytes;
-    mv += ( blockIdx.y * (size_t)g.mb_count + mb ) * 2 * NMV;
+    // blockIdx.z = frame of a batch: consecutive slots, mb_count MVs per frame
+    fref += blockIdx.z * (size_t)g.slot_bytes;
+    pred += blockIdx.z * (size_t)g.slot_bytes;
+    mv += ( blockIdx.z * (size_t)g.mb_count + mb_y * g.mb_w + mb_x ) * 2 * NMV;
     int16_t mvs[2 * NMV];
+    if( NMV == 4 )
+    {
+        const uint32_t *mw = (const uint32_t *)mv;              // (x, y) pairs: 4-byte aligned, nothing more is promised
+        const uint32_t w[4] = { __ldg( mw ), __ldg( mw + 1 ), __ldg( mw + 2 ), __ldg( mw + 3 ) };
 #pragma unroll
-    for( int k = 0; k < 2 * NMV; k++ )
-        mvs[k] = mv[k];
-    xd_mc_mb<NMV>( g, fref, mvs, pred, mb, threadIdx.x & 63 );
+        for( int k = 0; k < 4; k++ )
+        {
+            mvs[2 * k] = (int16_t)( w[k] & 0xFFFF );
+            mvs[2 * k + 1] = (int16_t)( w[k] >> 16 );
+        }
+    }
+    else
+    {
+        const uint32_t v = __ldg( (const uint32_t *)mv );
+        mvs[0] = (int16_t)( v & 0xFFFF );
+        mvs[1] = (int16_t)( v >> 16 );
+    }
+    xd_mc_mb32<NMV>( g, fref, mvs, pred, mb_x, mb_y, threadIdx.x & 31 );
 }
 
 template<bool TYPED, bool PROBE = false>
@@ -316,7 +331,7 @@ extern "C" int x264dsp_mc_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *
     if( !ctx || !g || !fref_slot || !mv || !pred_slot || fref_slot == pred_slot || n_frames <= 0 || n_frames > 65535 )
         return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
-    const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
+    const dim3 grid( ( g->mb_w + 7 ) / 8, g->mb_h, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_MC, s );
     xd_mc_frame_kernel<1><<<grid, 256, 0, s>>>( *g, fref_slot, mv, pred_slot );
     xd_prof_end( ctx, XD_PROF_MC, pslot, s );
@@ -331,7 +346,7 @@ extern "C" int x264dsp_mc_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geo
     if( !ctx || !g || !fref_slot || !mv8x8 || !pred_slot || fref_slot == pred_slot || n_frames <= 0 || n_frames > 65535 )
         return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
-    const dim3 grid( ( g->mb_count + 3 ) / 4, n_frames );
+    const dim3 grid( ( g->mb_w + 7 ) / 8, g->mb_h, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_MC, s );
     xd_mc_frame_kernel<4><<<grid, 256, 0, s>>>( *g, fref_slot, mv8x8, pred_slot );
     xd_prof_end( ctx, XD_PROF_MC, pslot, s );

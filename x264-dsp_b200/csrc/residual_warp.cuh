@@ -50,6 +50,58 @@ __device__ __forceinline__ void xd_mc_mb( const x264dsp_geom_t &g, const uint8_t
     }
 }
 
+// The same prediction by ONE WARP (the mapping every caller uses now): lane = half a luma row (8 pixels: one unaligned
+// 8-byte fetch per plane instead of two 4-byte ones, the vector clip and the address arithmetic once per 8 pixels) and two
+// adjacent UV pairs of a chroma row, whose four taps are one byte dot product per sample: the weights (8-dx)(8-dy), dx(8-dy),
+// (8-dx)dy, dx dy are at most 64 and go into one word, the taps U(x,y) U(x+1,y) U(x,y+1) U(x+1,y+1) are picked out of the
+// two rows' words with PRMT (IDP.4A on the FMA pipe; the first version spent sixteen integer instructions per sample).
+// Measured with tools/bench_paths.py on 1080p: see DESIGN.md section 3.
+template<int NMV>
+__device__ __forceinline__ void xd_mc_mb32( const x264dsp_geom_t &g, const uint8_t *__restrict__ fref, const int16_t *mvs,
+                                            uint8_t *pred, int mb_x, int mb_y, int lane )
+{
+    const int ls = g.luma_stride, cs = g.chroma_stride;
+    const int lo_x = ( -( mb_x << 4 ) - 24 ) << 2, hi_x = ( ( ( g.mb_w - mb_x - 1 ) << 4 ) + 24 ) << 2;
+    const int lo_y = ( -( mb_y << 4 ) - 24 ) << 2, hi_y = ( ( ( g.mb_h - mb_y - 1 ) << 4 ) + 24 ) << 2;
+    {
+        // luma: row lane/2, pixels 8*(lane%2) .. +7
+        const int y = lane >> 1, x = ( lane & 1 ) * 8;
+        const int part = NMV == 4 ? ( y >> 3 ) * 2 + ( lane & 1 ) : 0;
+        const int mvx = xd_clip3( mvs[2 * part], lo_x, hi_x ), mvy = xd_clip3( mvs[2 * part + 1], lo_y, hi_y );
+        const int fx = mvx & 3, fy = mvy & 3, phase = fy * 4 + fx;
+        const int64_t pos = (int64_t)( ( mb_y << 4 ) + y + ( mvy >> 2 ) ) * ls + ( mb_x << 4 ) + x + ( mvx >> 2 );
+        const uint8_t *base = fref + g.luma_origin;
+        uint2 a = xd_load8_unaligned( base + (size_t)xd_qpel_plane_a( phase ) * g.luma_plane_size + pos + ( fy == 3 ? ls : 0 ) );
+        if( phase & 5 )
+        {
+            const uint2 b = xd_load8_unaligned( base + (size_t)xd_qpel_plane_b( phase ) * g.luma_plane_size + pos + ( fx == 3 ? 1 : 0 ) );
+            a.x = xd_avg4( a.x, b.x );
+            a.y = xd_avg4( a.y, b.y );
+        }
+        *(uint2 *)( pred + g.luma_origin + (int64_t)( ( mb_y << 4 ) + y ) * ls + ( mb_x << 4 ) + x ) = a;
+    }
+    {
+        // chroma: row lane/4, UV pairs 2*(lane%4) and 2*(lane%4)+1; eighth-pel bilinear on NV12 (mc.c:290-323)
+        const int y = lane >> 2, x = ( lane & 3 ) * 2;
+        const int part = NMV == 4 ? ( y >> 2 ) * 2 + ( x >> 2 ) : 0;
+        const int mvx = xd_clip3( mvs[2 * part], lo_x, hi_x ), mvy = xd_clip3( mvs[2 * part + 1], lo_y, hi_y );
+        const int dx = mvx & 7, dy = mvy & 7;
+        const uint32_t coef = (uint32_t)( ( 8 - dx ) * ( 8 - dy ) ) | ( (uint32_t)( dx * ( 8 - dy ) ) << 8 )
+                            | ( (uint32_t)( ( 8 - dx ) * dy ) << 16 ) | ( (uint32_t)( dx * dy ) << 24 );
+        const uint8_t *s0 = fref + g.slot_chroma_off + g.chroma_origin
+                          + (int64_t)( ( mb_y << 3 ) + y + ( mvy >> 3 ) ) * cs + ( mb_x << 4 ) + 2 * ( x + ( mvx >> 3 ) );
+        // bytes U0 V0 U1 V1 U2 V2 of the two rows (the 8-byte fetch brings two more)
+        const uint2 r0 = xd_load8_unaligned( s0 ), r1 = xd_load8_unaligned( s0 + cs );
+        const uint32_t m0 = __funnelshift_r( r0.x, r0.y, 16 ), m1 = __funnelshift_r( r1.x, r1.y, 16 );     // U1 V1 U2 V2
+        const uint32_t u0 = ( __dp4a( __byte_perm( r0.x, r1.x, 0x6420 ), coef, 32u ) ) >> 6;
+        const uint32_t v0 = ( __dp4a( __byte_perm( r0.x, r1.x, 0x7531 ), coef, 32u ) ) >> 6;
+        const uint32_t u1 = ( __dp4a( __byte_perm( m0, m1, 0x6420 ), coef, 32u ) ) >> 6;
+        const uint32_t v1 = ( __dp4a( __byte_perm( m0, m1, 0x7531 ), coef, 32u ) ) >> 6;
+        *(uint32_t *)( pred + g.slot_chroma_off + g.chroma_origin + (int64_t)( ( mb_y << 3 ) + y ) * cs + ( mb_x << 4 ) + 2 * x )
+            = u0 | ( v0 << 8 ) | ( u1 << 16 ) | ( v1 << 24 );
+    }
+}
+
 struct xd_res_tables
 {
     xd_qparams luma, chroma;
@@ -198,12 +250,13 @@ __device__ __forceinline__ int xd_residual_mb( const x264dsp_geom_t &g, const ui
     int nz = 0, score = 0;
     if( is_luma || ( is_chroma && !early ) )
     {
-        nz = xd_quant_4x4( dct, Q );
+        uint32_t codes;
+        nz = xd_quant_4x4_codes( dct, Q, codes );
         xd_zigzag( lv, dct );
         if( nz )
         {
             xd_dequant_4x4( dct, Q );
-            score = xd_decimate( lv, is_luma ? 0 : 1 );
+            score = xd_decimate_codes( codes, is_luma ? 0 : 1 );
         }
     }
     else
