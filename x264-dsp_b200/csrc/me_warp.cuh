@@ -15,6 +15,10 @@
 #ifndef XD_ME_CALL
 #define XD_ME_CALL __forceinline__
 #endif
+#ifndef XD_ME_SAD16_UNROLL
+#define XD_ME_SAD16_UNROLL 1
+#endif
+constexpr int xd_me_sad16_unroll = XD_ME_SAD16_UNROLL;
 #ifndef XD_ME_REFINE_CALL
 #define XD_ME_REFINE_CALL
 #endif
@@ -31,6 +35,7 @@ struct xd_me_blk
     int minx, miny, maxx, maxy;     // full-pel limits
     int sminx, sminy, smaxx, smaxy; // sub-pel limits
     bool fpel_satd;                 // h->pixf.fpelcmp == satd: me=TESA with subme >= 2 (encoder/encoder.c:412-432)
+    bool fixed16;                   // compile-time knowledge that the block is 16x16 (xd_me_search_warp<true>): unrolled cost loops
 };
 
 __device__ __forceinline__ int xd_me_bits( const xd_me_blk &B, int qx, int qy )
@@ -80,18 +85,35 @@ __device__ __forceinline__ uint32_t xd_me_pred4( const xd_qpel_src &s, int strid
 // 7 600 instructions and SLOWER -- 158 against 139 us per frame (DIA, subme 1), 292 against 284 (HEX, subme 5); with the
 // refinement a call as well 179 / 308 -- so everything stays inlined.
 static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint8_t *ref, size_t plane_size, int stride,
-                                                   int wh, int qx, int qy, int sub )
+                                                   int wh, int qx, int qy, int sub, bool fixed16 = false )
 {
     xd_me_blk B;
     B.fenc = fenc; B.ref = ref; B.plane_size = plane_size; B.stride = stride; B.w = wh & 255; B.h = wh >> 8;
     const xd_qpel_src s = xd_me_src( B, qx, qy );
     int acc = 0;
-    if( B.w >= 8 )
+    if( fixed16 )
     {
-        const int per_row = B.w >> 3, nseg = B.h * per_row;
+        // 32 segments of 8 pixels, four per lane.  XD_ME_SAD16_UNROLL = 4 puts all loads of a lane in flight together and
+        // wins 2 % at DIA / subme 1, but the kernel grows from 14 k to 17 k instructions and HEX / subme 5 -- which walks far
+        // more of the code per macroblock -- loses 11 % (177 -> 197 us per 1080p frame): instruction fetch, again.
+#pragma unroll xd_me_sad16_unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            const int i = sub + 8 * k, y = i >> 1, x = ( i & 1 ) * 8;
+            const uint2 p = xd_me_pred8( s, B.stride, x, y );
+            const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)y * B.stride + x );
+            acc += __vsadu4( p.x, f.x ) + __vsadu4( p.y, f.y );
+        }
+    }
+    else if( B.w >= 8 )
+    {
+        // one or two 8-pixel segments per row: the split of i into (row, segment) is a shift and a mask, not a division.
+        // Rolled on purpose: the partition kernel is instruction-fetch bound (28 k instructions), every unrolled copy costs
+        const int wide = B.w >> 4, nseg = B.h << wide;
+#pragma unroll 1
         for( int i = sub; i < nseg; i += 8 )
         {
-            const int y = i / per_row, x = ( i % per_row ) * 8;
+            const int y = i >> wide, x = ( i & wide ) * 8;
             const uint2 p = xd_me_pred8( s, B.stride, x, y );
             const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)y * B.stride + x );
             acc += __vsadu4( p.x, f.x ) + __vsadu4( p.y, f.y );
@@ -99,6 +121,7 @@ static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint
     }
     else
     {
+#pragma unroll 1
         for( int y = sub; y < B.h; y += 8 )
             acc += __vsadu4( xd_me_pred4( s, B.stride, 0, y ), xd_load4_unaligned( B.fenc + (int64_t)y * B.stride ) );
     }
@@ -110,17 +133,36 @@ static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint
 
 // SATD (common/pixel.c:267-337) of the block at quarter-pel (qx,qy)
 static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uint8_t *ref, size_t plane_size, int stride,
-                                                    int wh, int qx, int qy, int sub )
+                                                    int wh, int qx, int qy, int sub, bool fixed16 = false )
 {
     xd_me_blk B;
     B.fenc = fenc; B.ref = ref; B.plane_size = plane_size; B.stride = stride; B.w = wh & 255; B.h = wh >> 8;
     const xd_qpel_src s = xd_me_src( B, qx, qy );
     int acc = 0;
-    const int per_row = B.w >= 8 ? B.w >> 3 : 1;
-    const int units = ( B.h >> 2 ) * per_row;
+    if( fixed16 )
+    {
+        // eight 8x4 units, exactly one per lane of the group: no loop at all
+        const int y = ( sub >> 1 ) * 4, x = ( sub & 1 ) * 8;
+        uint32_t pa[4], pb[4], fa[4], fb[4];
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            const uint2 p = xd_me_pred8( s, B.stride, x, y + r );
+            const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)( y + r ) * B.stride + x );
+            pa[r] = p.x; pb[r] = p.y; fa[r] = f.x; fb[r] = f.y;
+        }
+        acc = xd_satd4x4( fa, pa ) + xd_satd4x4( fb, pb );
+        acc += __shfl_xor_sync( 0xffffffffu, acc, 1 );
+        acc += __shfl_xor_sync( 0xffffffffu, acc, 2 );
+        acc += __shfl_xor_sync( 0xffffffffu, acc, 4 );
+        return acc;
+    }
+    const int wide = B.w >> 4;                          // 16-wide blocks have two 8x4 units per row of units
+    const int units = ( B.h >> 2 ) << wide;
+#pragma unroll 1
     for( int u = sub; u < units; u += 8 )
     {
-        const int y = ( u / per_row ) * 4, x = ( u % per_row ) * 8;
+        const int y = ( u >> wide ) * 4, x = ( u & wide ) * 8;
         uint32_t pa[4], pb[4], fa[4], fb[4];
         if( B.w >= 8 )
         {
@@ -152,11 +194,11 @@ static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uin
 
 __device__ __forceinline__ int xd_me_sad_raw( const xd_me_blk &B, int qx, int qy, int sub )
 {
-    return xd_me_sad_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub );
+    return xd_me_sad_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub, B.fixed16 );
 }
 __device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, int sub )
 {
-    return xd_me_satd_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub );
+    return xd_me_satd_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub, B.fixed16 );
 }
 
 // h->pixf.fpelcmp[i_pixel]: SAD, except under TESA where mbcmp_init (encoder.c:429-432) makes it SATD
@@ -196,9 +238,19 @@ struct xd_me_state
 
 // refine_subpel (me.c:466-587).  thresh = *p_halfpel_thresh (nullptr: the caller passed NULL); when the early
 // termination of me.c:527-536 fires, mv and cost are stored and cost_mv keeps its previous value, as there.
-static __device__ XD_ME_REFINE_CALL void xd_me_refine( const xd_me_blk &B, xd_me_state &S, int subme, int hpel_iters, int qpel_iters,
+// (a function of its own where the compiler keeps it one: FIXED16 repeats the caller's compile-time knowledge inside it)
+template<bool FIXED16 = false>
+static __device__ XD_ME_REFINE_CALL void xd_me_refine( const xd_me_blk &Bin, xd_me_state &S, int subme, int hpel_iters, int qpel_iters,
                               bool final_refine, int lane, int *thresh = nullptr )
 {
+    xd_me_blk B = Bin;
+    if( FIXED16 )
+    {
+        B.w = B.h = 16;
+        B.fixed16 = true;
+    }
+    else
+        B.fixed16 = false;
     const int cand = lane >> 3, sub = lane & 7;
     const int dx = cand == 2 ? -1 : cand == 3 ? 1 : 0;
     const int dy = cand == 0 ? -1 : cand == 1 ? 1 : 0;
@@ -288,6 +340,9 @@ static __device__ XD_ME_REFINE_CALL void xd_me_refine( const xd_me_blk &B, xd_me
 // The search of one block.  `in` may live in global or shared memory (plain loads); mode and R as in
 // x264dsp_me_search_batch_ex_dev: X264DSP_ME_MODE_SEARCH fills R, the two refine modes start from R.  thresh = pointer to
 // this block's *p_halfpel_thresh (nullptr: the reference's NULL).  Every lane returns the same R.
+// FIXED16: the caller only ever searches 16x16 blocks (the P-slice wavefront without partitions) -- width and height become
+// constants, the cost loops unroll and the four segments' loads of a lane are in flight together instead of one after the other.
+template<bool FIXED16 = false>
 __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, const uint8_t *__restrict__ fenc_slot,
                                                    const uint8_t *__restrict__ fref_slot, const x264dsp_me_params_t &P,
                                                    const uint16_t *__restrict__ cost_mv, const x264dsp_me_block_t *in,
@@ -297,9 +352,10 @@ __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, cons
     static const uint8_t bw[8] = { 16, 16, 8, 8, 8, 4, 4, 4 }, bh[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
 
     xd_me_blk B;
-    const int size = in->i_pixel & 7;
-    B.w = bw[size];
-    B.h = bh[size];
+    const int size = FIXED16 ? 0 : in->i_pixel & 7;
+    B.w = FIXED16 ? 16 : bw[size];
+    B.h = FIXED16 ? 16 : bh[size];
+    B.fixed16 = FIXED16;
     B.stride = g.luma_stride;
     B.plane_size = (size_t)g.luma_plane_size;
     const int64_t pos = (int64_t)in->by * g.luma_stride + in->bx;
@@ -322,9 +378,9 @@ __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, cons
         // already taken i_ref_cost off the cost): m->mv, m->cost, m->cost_mv come in through results[blk]
         xd_me_state S = R;
         if( mode == X264DSP_ME_MODE_REFDUPE )
-            xd_me_refine( B, S, subme, 0, min( 2, (int)xd_subpel_iters[subme][3] ), false, lane, thresh );
+            xd_me_refine<FIXED16>( B, S, subme, 0, min( 2, (int)xd_subpel_iters[subme][3] ), false, lane, thresh );
         else
-            xd_me_refine( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
+            xd_me_refine<FIXED16>( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
         R = S;
         return;
     }
@@ -515,9 +571,9 @@ __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, cons
         S.cost += S.cost_mv;
 
     if( subme >= 2 )
-        xd_me_refine( B, S, subme, xd_subpel_iters[subme][2], xd_subpel_iters[subme][3], false, lane, thresh );
+        xd_me_refine<FIXED16>( B, S, subme, xd_subpel_iters[subme][2], xd_subpel_iters[subme][3], false, lane, thresh );
     if( P.refine_qpel )                                                  // me.c:426-435, i_ref_cost = 0
-        xd_me_refine( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
+        xd_me_refine<FIXED16>( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
 
     R = S;
 }

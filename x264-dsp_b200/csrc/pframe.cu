@@ -245,7 +245,7 @@ xd_pframe_kernel( xd_pf_args A )
                     blk->mv_min_fpel[1] = ( smin_y >> 2 ) + border; blk->mv_max_fpel[1] = ( smax_y >> 2 ) - border;
                 }
                 __syncwarp();
-                xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
+                xd_me_search_warp<true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
                 searched = true;
                 out_mvr = xd_pack_mv( R.mvx, R.mvy );                                  // analyse.c:825
                 try_probe = A.P.fast_pskip && subme >= 3 && R.cost - R.cost_mv < 300 * A.lambda
@@ -256,7 +256,7 @@ xd_pframe_kernel( xd_pf_args A )
             if( !done )
             {
                 // ---- x264_me_refine_qpel (analyse.c:1187-1191; one reference: i_ref_cost = 0)
-                xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
+                xd_me_search_warp<true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
                 out_mv = xd_pack_mv( R.mvx, R.mvy );
                 __syncwarp();                                   // the block description is free for the next macroblock
                 // ---- x264_macroblock_encode, inter branch: x264_mb_mc, residual, forced P_SKIP (macroblock.c:379-485)
