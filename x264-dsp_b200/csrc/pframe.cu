@@ -28,7 +28,10 @@
 #define PF_WARPS 2
 #endif
 #ifndef PF_MINB
-#define PF_MINB 8                   // resident CTAs per SM the register allocation aims at
+#define PF_MINB 12                  // resident CTAs per SM the register allocation aims at (80 registers, 24 warps per SM)
+#endif
+#ifndef PF_PART_MINB
+#define PF_PART_MINB 8              // ... of the partition kernel (128 registers; 96 / 80 spill and measure the same)
 #endif
 
 int xd_me_params_ok( const x264dsp_me_params_t *p );   // me.cu
@@ -355,7 +358,7 @@ __device__ __forceinline__ void xd_pp_write_cells( xd_pp_warp *S, int x, int y, 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__( PF_WARPS * 32, PF_MINB )
+__global__ void __launch_bounds__( PF_WARPS * 32, PF_PART_MINB )
 xd_pframe_part_kernel( xd_pf_args A )
 {
     __shared__ xd_pp_warp s_warp[PF_WARPS];
