@@ -36,6 +36,7 @@ struct xd_me_blk
     int sminx, sminy, smaxx, smaxy; // sub-pel limits
     bool fpel_satd;                 // h->pixf.fpelcmp == satd: me=TESA with subme >= 2 (encoder/encoder.c:412-432)
     bool fixed16;                   // compile-time knowledge that the block is 16x16 (xd_me_search_warp<true>): unrolled cost loops
+    bool src_aligned;               // ... that the source block sits at a multiple of min(width, 8) (xd_me_search_warp<.., true>)
 };
 
 __device__ __forceinline__ int xd_me_bits( const xd_me_blk &B, int qx, int qy )
@@ -77,6 +78,18 @@ __device__ __forceinline__ uint32_t xd_me_pred4( const xd_qpel_src &s, int strid
     return p;
 }
 
+// A segment of the SOURCE block.  A caller that builds its own block lists (the P-slice wavefront: macroblocks and their
+// partitions) knows that a block sits at a multiple of its width in a plane whose rows are 8-byte aligned, so a segment is ONE
+// aligned load; blocks handed in from outside may sit anywhere and take the three-words-and-two-funnel-shifts path.
+__device__ __forceinline__ uint2 xd_me_src8( const uint8_t *p, bool aligned )
+{
+    return aligned ? __ldg( (const uint2 *)p ) : xd_load8_unaligned( p );
+}
+__device__ __forceinline__ uint32_t xd_me_src4( const uint8_t *p, bool aligned )
+{
+    return aligned ? __ldg( (const uint32_t *)p ) : xd_load4_unaligned( p );
+}
+
 // SAD of the block at quarter-pel (qx,qy); lanes of one candidate group cooperate (sub = lane & 7)
 // The two cost routines take the block description as scalars so that they can be compiled as real calls
 // (-DXD_ME_CALL=__noinline__): the search has some thirty call sites, a kernel that inlines them all is 25 000
@@ -85,7 +98,7 @@ __device__ __forceinline__ uint32_t xd_me_pred4( const xd_qpel_src &s, int strid
 // 7 600 instructions and SLOWER -- 158 against 139 us per frame (DIA, subme 1), 292 against 284 (HEX, subme 5); with the
 // refinement a call as well 179 / 308 -- so everything stays inlined.
 static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint8_t *ref, size_t plane_size, int stride,
-                                                   int wh, int qx, int qy, int sub, bool fixed16 = false )
+                                                   int wh, int qx, int qy, int sub, bool fixed16 = false, bool al = false )
 {
     xd_me_blk B;
     B.fenc = fenc; B.ref = ref; B.plane_size = plane_size; B.stride = stride; B.w = wh & 255; B.h = wh >> 8;
@@ -101,7 +114,7 @@ static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint
         {
             const int i = sub + 8 * k, y = i >> 1, x = ( i & 1 ) * 8;
             const uint2 p = xd_me_pred8( s, B.stride, x, y );
-            const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)y * B.stride + x );
+            const uint2 f = xd_me_src8( B.fenc + (int64_t)y * B.stride + x, al );
             acc += __vsadu4( p.x, f.x ) + __vsadu4( p.y, f.y );
         }
     }
@@ -115,7 +128,7 @@ static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint
         {
             const int y = i >> wide, x = ( i & wide ) * 8;
             const uint2 p = xd_me_pred8( s, B.stride, x, y );
-            const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)y * B.stride + x );
+            const uint2 f = xd_me_src8( B.fenc + (int64_t)y * B.stride + x, al );
             acc += __vsadu4( p.x, f.x ) + __vsadu4( p.y, f.y );
         }
     }
@@ -123,7 +136,7 @@ static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint
     {
 #pragma unroll 1
         for( int y = sub; y < B.h; y += 8 )
-            acc += __vsadu4( xd_me_pred4( s, B.stride, 0, y ), xd_load4_unaligned( B.fenc + (int64_t)y * B.stride ) );
+            acc += __vsadu4( xd_me_pred4( s, B.stride, 0, y ), xd_me_src4( B.fenc + (int64_t)y * B.stride, al ) );
     }
     acc += __shfl_xor_sync( 0xffffffffu, acc, 1 );
     acc += __shfl_xor_sync( 0xffffffffu, acc, 2 );
@@ -133,7 +146,7 @@ static __device__ XD_ME_CALL int xd_me_sad_call( const uint8_t *fenc, const uint
 
 // SATD (common/pixel.c:267-337) of the block at quarter-pel (qx,qy)
 static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uint8_t *ref, size_t plane_size, int stride,
-                                                    int wh, int qx, int qy, int sub, bool fixed16 = false )
+                                                    int wh, int qx, int qy, int sub, bool fixed16 = false, bool al = false )
 {
     xd_me_blk B;
     B.fenc = fenc; B.ref = ref; B.plane_size = plane_size; B.stride = stride; B.w = wh & 255; B.h = wh >> 8;
@@ -148,7 +161,7 @@ static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uin
         for( int r = 0; r < 4; r++ )
         {
             const uint2 p = xd_me_pred8( s, B.stride, x, y + r );
-            const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)( y + r ) * B.stride + x );
+            const uint2 f = xd_me_src8( B.fenc + (int64_t)( y + r ) * B.stride + x, al );
             pa[r] = p.x; pb[r] = p.y; fa[r] = f.x; fb[r] = f.y;
         }
         acc = xd_satd4x4( fa, pa ) + xd_satd4x4( fb, pb );
@@ -170,7 +183,7 @@ static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uin
             for( int r = 0; r < 4; r++ )
             {
                 const uint2 p = xd_me_pred8( s, B.stride, x, y + r );
-                const uint2 f = xd_load8_unaligned( B.fenc + (int64_t)( y + r ) * B.stride + x );
+                const uint2 f = xd_me_src8( B.fenc + (int64_t)( y + r ) * B.stride + x, al );
                 pa[r] = p.x; pb[r] = p.y; fa[r] = f.x; fb[r] = f.y;
             }
             acc += xd_satd4x4( fa, pa ) + xd_satd4x4( fb, pb );
@@ -181,7 +194,7 @@ static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uin
             for( int r = 0; r < 4; r++ )
             {
                 pa[r] = xd_me_pred4( s, B.stride, 0, y + r );
-                fa[r] = xd_load4_unaligned( B.fenc + (int64_t)( y + r ) * B.stride );
+                fa[r] = xd_me_src4( B.fenc + (int64_t)( y + r ) * B.stride, al );
             }
             acc += xd_satd4x4( fa, pa );
         }
@@ -194,11 +207,11 @@ static __device__ XD_ME_CALL int xd_me_satd_call( const uint8_t *fenc, const uin
 
 __device__ __forceinline__ int xd_me_sad_raw( const xd_me_blk &B, int qx, int qy, int sub )
 {
-    return xd_me_sad_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub, B.fixed16 );
+    return xd_me_sad_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub, B.fixed16, B.src_aligned );
 }
 __device__ __forceinline__ int xd_me_satd( const xd_me_blk &B, int qx, int qy, int sub )
 {
-    return xd_me_satd_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub, B.fixed16 );
+    return xd_me_satd_call( B.fenc, B.ref, B.plane_size, B.stride, B.w | ( B.h << 8 ), qx, qy, sub, B.fixed16, B.src_aligned );
 }
 
 // h->pixf.fpelcmp[i_pixel]: SAD, except under TESA where mbcmp_init (encoder.c:429-432) makes it SATD
@@ -239,7 +252,7 @@ struct xd_me_state
 // refine_subpel (me.c:466-587).  thresh = *p_halfpel_thresh (nullptr: the caller passed NULL); when the early
 // termination of me.c:527-536 fires, mv and cost are stored and cost_mv keeps its previous value, as there.
 // (a function of its own where the compiler keeps it one: FIXED16 repeats the caller's compile-time knowledge inside it)
-template<bool FIXED16 = false>
+template<bool FIXED16 = false, bool ALIGNED_SRC = false>
 static __device__ XD_ME_REFINE_CALL void xd_me_refine( const xd_me_blk &Bin, xd_me_state &S, int subme, int hpel_iters, int qpel_iters,
                               bool final_refine, int lane, int *thresh = nullptr )
 {
@@ -251,6 +264,7 @@ static __device__ XD_ME_REFINE_CALL void xd_me_refine( const xd_me_blk &Bin, xd_
     }
     else
         B.fixed16 = false;
+    B.src_aligned = ALIGNED_SRC;
     const int cand = lane >> 3, sub = lane & 7;
     const int dx = cand == 2 ? -1 : cand == 3 ? 1 : 0;
     const int dy = cand == 0 ? -1 : cand == 1 ? 1 : 0;
@@ -342,7 +356,7 @@ static __device__ XD_ME_REFINE_CALL void xd_me_refine( const xd_me_blk &Bin, xd_
 // this block's *p_halfpel_thresh (nullptr: the reference's NULL).  Every lane returns the same R.
 // FIXED16: the caller only ever searches 16x16 blocks (the P-slice wavefront without partitions) -- width and height become
 // constants, the cost loops unroll and the four segments' loads of a lane are in flight together instead of one after the other.
-template<bool FIXED16 = false>
+template<bool FIXED16 = false, bool ALIGNED_SRC = false>
 __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, const uint8_t *__restrict__ fenc_slot,
                                                    const uint8_t *__restrict__ fref_slot, const x264dsp_me_params_t &P,
                                                    const uint16_t *__restrict__ cost_mv, const x264dsp_me_block_t *in,
@@ -356,6 +370,7 @@ __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, cons
     B.w = FIXED16 ? 16 : bw[size];
     B.h = FIXED16 ? 16 : bh[size];
     B.fixed16 = FIXED16;
+    B.src_aligned = ALIGNED_SRC;
     B.stride = g.luma_stride;
     B.plane_size = (size_t)g.luma_plane_size;
     const int64_t pos = (int64_t)in->by * g.luma_stride + in->bx;
@@ -378,9 +393,9 @@ __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, cons
         // already taken i_ref_cost off the cost): m->mv, m->cost, m->cost_mv come in through results[blk]
         xd_me_state S = R;
         if( mode == X264DSP_ME_MODE_REFDUPE )
-            xd_me_refine<FIXED16>( B, S, subme, 0, min( 2, (int)xd_subpel_iters[subme][3] ), false, lane, thresh );
+            xd_me_refine<FIXED16, ALIGNED_SRC>( B, S, subme, 0, min( 2, (int)xd_subpel_iters[subme][3] ), false, lane, thresh );
         else
-            xd_me_refine<FIXED16>( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
+            xd_me_refine<FIXED16, ALIGNED_SRC>( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
         R = S;
         return;
     }
@@ -571,9 +586,9 @@ __device__ __forceinline__ void xd_me_search_warp( const x264dsp_geom_t &g, cons
         S.cost += S.cost_mv;
 
     if( subme >= 2 )
-        xd_me_refine<FIXED16>( B, S, subme, xd_subpel_iters[subme][2], xd_subpel_iters[subme][3], false, lane, thresh );
+        xd_me_refine<FIXED16, ALIGNED_SRC>( B, S, subme, xd_subpel_iters[subme][2], xd_subpel_iters[subme][3], false, lane, thresh );
     if( P.refine_qpel )                                                  // me.c:426-435, i_ref_cost = 0
-        xd_me_refine<FIXED16>( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
+        xd_me_refine<FIXED16, ALIGNED_SRC>( B, S, subme, xd_subpel_iters[subme][0], xd_subpel_iters[subme][1], true, lane );
 
     R = S;
 }

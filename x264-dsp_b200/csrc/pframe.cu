@@ -248,7 +248,7 @@ xd_pframe_kernel( xd_pf_args A )
                     blk->mv_min_fpel[1] = ( smin_y >> 2 ) + border; blk->mv_max_fpel[1] = ( smax_y >> 2 ) - border;
                 }
                 __syncwarp();
-                xd_me_search_warp<true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
+                xd_me_search_warp<true, true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
                 searched = true;
                 out_mvr = xd_pack_mv( R.mvx, R.mvy );                                  // analyse.c:825
                 try_probe = A.P.fast_pskip && subme >= 3 && R.cost - R.cost_mv < 300 * A.lambda
@@ -259,7 +259,7 @@ xd_pframe_kernel( xd_pf_args A )
             if( !done )
             {
                 // ---- x264_me_refine_qpel (analyse.c:1187-1191; one reference: i_ref_cost = 0)
-                xd_me_search_warp<true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
+                xd_me_search_warp<true, true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
                 out_mv = xd_pack_mv( R.mvx, R.mvy );
                 __syncwarp();                                   // the block description is free for the next macroblock
                 // ---- x264_macroblock_encode, inter branch: x264_mb_mc, residual, forced P_SKIP (macroblock.c:379-485)
@@ -572,7 +572,7 @@ xd_pframe_part_kernel( xd_pf_args A )
                     blk->i_mvc = n;
                 }
                 __syncwarp();
-                xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
+                xd_me_search_warp<false, true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_SEARCH, nullptr, lane );
                 const uint32_t found = xd_pack_mv( R.mvx, R.mvy );
                 if( lane == 0 )
                 {
@@ -673,7 +673,7 @@ xd_pframe_part_kernel( xd_pf_args A )
                     R.mvy = (int16_t)( m >> 16 );
                     R.cost = S->job_cost[first + k];
                     R.cost_mv = S->job_cost_mv[first + k];
-                    xd_me_search_warp( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
+                    xd_me_search_warp<false, true>( g, fenc, fref, A.MP, A.cost_mv, blk, R, X264DSP_ME_MODE_REFINE_QPEL, nullptr, lane );
                     __syncwarp();
                     // the 8x8 blocks this partition covers
                     if( lane < ( pw >> 1 ) * ( ph >> 1 ) )
