@@ -424,27 +424,44 @@ def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3,
 
 
 def pframe_e2e(pkg, ctx, g, w, h, n_frames, me, subme, qp=26, reps=3):
-    """the same through the host-memory door (x264dsp_p_frames_host): pinned pictures in; types, vectors, levels, nnz, cbp and
-    the reconstructed pictures out; every copy inside the timed region.  Returns (seconds per call, h2d bytes, d2h bytes)"""
+    """the same through the host-memory door (x264dsp_p_frames_host_packed): pinned pictures in; types, vectors, mvd, nnz, cbp and
+    the levels as the compact stream the entropy coder reads out (the reconstruction stays on the device, where an encoder needs
+    it as the next reference); every copy inside the timed region.  Returns (seconds per call, h2d bytes, d2h bytes,
+    seconds per call of the dense door x264dsp_p_frames_host with the reconstruction, its d2h bytes)"""
     nmb = g.mb_count
     pics = ctx.pinned_empty((n_frames + 1, w * h * 3 // 2), np.uint8)
     for i in range(n_frames + 1):
         pics[i] = pkg.synth_frame(w, h, i % 25)
     o = {"mb_type": ctx.pinned_empty((n_frames, nmb), np.int8), "mv": ctx.pinned_empty((n_frames, nmb, 2), np.int16),
          "mvr": ctx.pinned_empty((n_frames, nmb, 2), np.int16), "mvd": ctx.pinned_empty((n_frames, nmb, 2), np.int16),
-         "levels": ctx.pinned_empty((n_frames, nmb, pkg.RES_LEVELS_PER_MB), np.int16),
-         "nnz": ctx.pinned_empty((n_frames, nmb, pkg.RES_NNZ_PER_MB), np.uint8), "cbp": ctx.pinned_empty((n_frames, nmb), np.int16)}
-    recon = ctx.pinned_empty((n_frames, w * h * 3 // 2), np.uint8)
+         "nnz": ctx.pinned_empty((n_frames, nmb, pkg.RES_NNZ_PER_MB), np.uint8), "cbp": ctx.pinned_empty((n_frames, nmb), np.int16),
+         "mb_offset": ctx.pinned_empty((n_frames, nmb), np.int32)}
+    packed = ctx.pinned_empty((n_frames * nmb * pkg.RES_LEVELS_PER_MB // 4,), np.int16)
+    f_off = np.zeros(n_frames + 1, np.int64)
     prm = pkg.PFrameParams(me, subme, 16, qp, 512, 1, 0)
 
     def run():
-        ctx.p_frames_host(w, h, n_frames, pics, prm, o["mb_type"], o["mv"], o["mvr"], o["mvd"], o["levels"], o["nnz"], o["cbp"], recon)
+        ctx.p_frames_host_packed(w, h, n_frames, pics, prm, o["mb_type"], None, o["mv"], o["mvr"], o["mvd"], packed, f_off,
+                                 o["mb_offset"], o["nnz"], o["cbp"])
     run()
     t0 = time.perf_counter()
     for _ in range(reps):
         run()
     dt = (time.perf_counter() - t0) / reps
-    return dt, int(pics.nbytes), int(sum(a.nbytes for a in o.values()) + recon.nbytes)
+    d2h = int(sum(a.nbytes for a in o.values()) + 2 * int(f_off[-1]))
+    # the dense door for comparison: all 392 levels of every macroblock and the reconstructed pictures come back as well
+    levels = ctx.pinned_empty((n_frames, nmb, pkg.RES_LEVELS_PER_MB), np.int16)
+    recon = ctx.pinned_empty((n_frames, w * h * 3 // 2), np.uint8)
+
+    def run_dense():
+        ctx.p_frames_host(w, h, n_frames, pics, prm, o["mb_type"], o["mv"], o["mvr"], o["mvd"], levels, o["nnz"], o["cbp"], recon)
+    run_dense()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run_dense()
+    dt_dense = (time.perf_counter() - t0) / reps
+    d2h_dense = int(sum(a.nbytes for k, a in o.items() if k != "mb_offset") + levels.nbytes + recon.nbytes)
+    return dt, int(pics.nbytes), d2h, dt_dense, d2h_dense
 
 
 def pframe_oracle_check(g, check):
@@ -1335,10 +1352,13 @@ def main():
                                               "1080p frame: glue/x264dsp_glue.c's own clock, X264DSP_GLUE_STATS)")
             pfl["value"] = pfl["settings"]["dia_subme1"]["value"]
             pfl["e2e"] = {"value": world * PF_E2E_FRAMES / pf_e2e_s_max, "unit": "frames/s", "h2d_bytes_per_step": pf_e2e[1],
-                          "d2h_bytes_per_step": pf_e2e[2], "setting": f"dia_subme1, {PF_E2E_FRAMES} frames per call (four stream groups)",
-                          "api": "x264dsp_p_frames_host (pinned I420 pictures in; types, vectors, mvd, levels, nnz, cbp and the "
-                                 "reconstructed I420 pictures out; reference planes, lowres planes and the lookahead of every pair "
-                                 "built on the device inside the call)"}
+                          "d2h_bytes_per_step": pf_e2e[2], "setting": f"dia_subme1, {PF_E2E_FRAMES} frames per call",
+                          "api": "x264dsp_p_frames_host_packed (pinned I420 pictures in; types, vectors, mvd, nnz, cbp and the levels "
+                                 "as the compact stream the entropy coder reads out, the reconstruction stays on the device; reference "
+                                 "planes, lowres planes and the lookahead of every pair built on the device inside the call)",
+                          "dense_door": {"value": PF_E2E_FRAMES / pf_e2e[3], "d2h_bytes_per_step": pf_e2e[4],
+                                         "api": "x264dsp_p_frames_host: all 392 levels per macroblock and the reconstructed "
+                                                "pictures come back too (rank 0's own time)"}}
             line["pframe"] = pfl
         print(json.dumps(line))
     ctx.close()

@@ -550,6 +550,26 @@ int x264dsp_p_frames_part_host( x264dsp_ctx_t *ctx, int width, int height, int n
                                 const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv8,
                                 int16_t *mvr, int16_t *mvd8, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 );
 
+/* ------------------------------------------------------------------ entropy hand-off, compact (8(f) N3)
+ * The dense levels are 392 int16 per macroblock, 6.4 MB per 1080p frame, and the writer (x264_macroblock_write_cabac,
+ * encoder/cabac.c:571-700) only reads a block whose non_zero_count flag is set.  The compact stream keeps exactly those units
+ * in the writer's order, back to back, per macroblock:
+ *   unit  0..15  luma 4x4 block k (16 levels)          present iff nnz[k]
+ *   unit 16, 17  chroma DC of U, V (4 levels each)     present iff nnz[25], nnz[26]
+ *   unit 18..25  U AC 0..3, V AC 0..3 (16 levels)      present iff nnz[16..19], nnz[20..23]
+ * packed[frame * packed_stride + mb_offset[frame][mb] ...] = the macroblock's units; frame_total[frame] = the stream's length in
+ * int16 units.  packed_stride >= mb_count * X264DSP_RES_LEVELS_PER_MB (the dense size is the worst case), a multiple of 4. */
+int x264dsp_levels_pack_dev( x264dsp_ctx_t *ctx, int n_frames, int mb_count, const int16_t *levels, const uint8_t *nnz,
+                             int16_t *packed, int64_t packed_stride, int32_t *mb_offset, int32_t *frame_total, void *stream );
+/* x264dsp_p_frames_host / _part_host (partition != NULL: mv / mvd are [mb][4][2]) with that stream instead of the dense levels:
+ * packed_levels (capacity in int16 units; X264DSP_E_ARG when the content does not fit) receives the frames back to back,
+ * frame f at frame_offset[f] .. frame_offset[f + 1] (n_frames + 1 entries), macroblocks at mb_offset[f][mb] inside it.
+ * recon_i420 may be NULL: the reconstruction then stays on the device. */
+int x264dsp_p_frames_host_packed( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                                  const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv,
+                                  int16_t *mvr, int16_t *mvd, int16_t *packed_levels, int64_t packed_capacity,
+                                  int64_t *frame_offset, int32_t *mb_offset, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 );
+
 /* ------------------------------------------------------------------ deblock
  * x264_frame_deblock_row for every MB row (common/deblock.c:341-427) with the reference's
  * slice-QP rule.  mb_type / partition / cbp: per-MB; bs: [mb][2][8][4] boundary strengths.

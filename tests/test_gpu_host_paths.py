@@ -176,3 +176,96 @@ def test_p_frames_part_host_matches_oracle(pkg, ctx, w, h, n, me, subme, qp, mon
         assert np.array_equal(recon[k][: w * h].reshape(h, w), wy), f"frame {k + 1}: luma reconstruction differs"
         seen |= set(np.unique(want["partition"]).tolist())
     assert seen >= {13, 16}, seen
+
+
+HO_FLAG = list(range(16)) + [25, 26] + list(range(16, 24))                 # nnz index of unit u
+HO_DENSE = [16 * u for u in range(16)] + [256, 260] + [264 + 16 * k for k in range(8)]
+HO_LEN = [16] * 16 + [4, 4] + [16] * 8
+
+
+def expand_packed(stream, mb_offset, nnz):
+    """the compact hand-off of one frame back to the dense [mb][392] form (units without a flag stay zero)"""
+    nmb = nnz.shape[0]
+    dense = np.zeros((nmb, 392), np.int16)
+    for mb in range(nmb):
+        at = int(mb_offset[mb])
+        for u in range(26):
+            if nnz[mb, HO_FLAG[u]]:
+                dense[mb, HO_DENSE[u]: HO_DENSE[u] + HO_LEN[u]] = stream[at: at + HO_LEN[u]]
+                at += HO_LEN[u]
+    return dense
+
+
+def mask_dense(levels, nnz):
+    """the dense levels with every unit the entropy coder does not read (flag 0) cleared"""
+    out = np.zeros_like(levels)
+    for u in range(26):
+        on = nnz[:, HO_FLAG[u]] != 0
+        out[on, HO_DENSE[u]: HO_DENSE[u] + HO_LEN[u]] = levels[on, HO_DENSE[u]: HO_DENSE[u] + HO_LEN[u]]
+    return out
+
+
+def test_levels_pack_matches_dense(pkg, ctx):
+    """x264dsp_levels_pack_dev on random flags / levels: offsets are the running sum of the present units' lengths, the stream
+    holds exactly those units in order"""
+    import torch
+    rng = np.random.RandomState(5)
+    n, nmb = 3, 700
+    nnz = (rng.rand(n, nmb, 27) < 0.3).astype(np.uint8) * rng.randint(1, 17, (n, nmb, 27)).astype(np.uint8)
+    nnz[1, :50] = 0                                                   # macroblocks with nothing coded
+    nnz[2, 100:130] = 3                                               # and with everything coded
+    levels = rng.randint(-300, 300, (n, nmb, 392)).astype(np.int16)
+    stride = nmb * 392
+    d_packed = torch.full((n * stride,), 12345, dtype=torch.int16, device="cuda")
+    d_off = torch.zeros((n, nmb), dtype=torch.int32, device="cuda")
+    d_tot = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx.levels_pack(n, nmb, torch.from_numpy(levels).cuda(), torch.from_numpy(nnz).cuda(), d_packed, stride, d_off, d_tot)
+    ctx.sync()
+    packed, off, tot = d_packed.cpu().numpy().reshape(n, stride), d_off.cpu().numpy(), d_tot.cpu().numpy()
+    for f in range(n):
+        sizes = sum((nnz[f][:, HO_FLAG[u]] != 0).astype(np.int64) * HO_LEN[u] for u in range(26))
+        assert np.array_equal(off[f], np.concatenate([[0], np.cumsum(sizes)[:-1]])), f"frame {f}: offsets"
+        assert tot[f] == sizes.sum()
+        assert np.array_equal(expand_packed(packed[f], off[f], nnz[f]), mask_dense(levels[f], nnz[f])), f"frame {f}: stream"
+        assert (packed[f][tot[f]:] == 12345).all(), "wrote past the stream's end"
+
+
+@pytest.mark.parametrize("w,h,n,me,subme,qp,part", [(352, 288, 9, 1, 5, 24, 0), (208, 160, 11, 0, 2, 28, 1)])
+def test_p_frames_host_packed_matches_dense(pkg, ctx, w, h, n, me, subme, qp, part, monkeypatch):
+    """x264dsp_p_frames_host_packed == x264dsp_p_frames_host (which is checked against the oracle) with the levels compacted
+    and the reconstruction left on the device"""
+    monkeypatch.setenv("X264DSP_PF_HOST_GROUPS", "3")
+    g = pkg.geometry(w, h)
+    nmb = g.mb_count
+    nv = 4 if part else 1
+    pics = np.stack([pkg.synth_frame(w, h, i, cut_frame=4) for i in range(n + 1)])
+    prm = pkg.PFrameParams(me, subme, 16, qp, 128, 1, 0, part)
+    mk = lambda: {"mb_type": np.zeros((n, nmb), np.int8), "partition": np.zeros((n, nmb), np.uint8),
+                  "mv": np.zeros((n, nmb, nv, 2), np.int16), "mvr": np.zeros((n, nmb, 2), np.int16),
+                  "mvd": np.zeros((n, nmb, nv, 2), np.int16), "nnz": np.zeros((n, nmb, 27), np.uint8), "cbp": np.zeros((n, nmb), np.int16)}
+    a, b = mk(), mk()
+    levels = np.zeros((n, nmb, 392), np.int16)
+    recon = np.zeros((n, w * h * 3 // 2), np.uint8)
+    if part:
+        ctx.p_frames_part_host(w, h, n, pics, prm, a["mb_type"], a["partition"], a["mv"], a["mvr"], a["mvd"], levels, a["nnz"], a["cbp"], recon)
+    else:
+        ctx.p_frames_host(w, h, n, pics, prm, a["mb_type"], a["mv"], a["mvr"], a["mvd"], levels, a["nnz"], a["cbp"], recon)
+    packed = np.full(n * nmb * 392, 777, np.int16)
+    f_off = np.zeros(n + 1, np.int64)
+    mb_off = np.zeros((n, nmb), np.int32)
+    ctx.p_frames_host_packed(w, h, n, pics, prm, b["mb_type"], b["partition"] if part else None, b["mv"], b["mvr"], b["mvd"], packed,
+                             f_off, mb_off, b["nnz"], b["cbp"])
+    for key in a:
+        if key == "partition" and not part:
+            continue
+        assert np.array_equal(a[key], b[key]), key
+    assert f_off[0] == 0 and (np.diff(f_off) >= 0).all() and f_off[-1] < packed.size // 2, f_off
+    for f in range(n):
+        got = expand_packed(packed[f_off[f]: f_off[f + 1]], mb_off[f], b["nnz"][f])
+        assert np.array_equal(got, mask_dense(levels[f], a["nnz"][f])), f"frame {f}: compact stream != dense levels"
+    assert (packed[f_off[-1]:] == 777).all()
+    # a buffer that cannot hold the content is refused, not overrun
+    small = np.zeros(max(int(f_off[-1]) // 2, 4), np.int16)
+    with pytest.raises(pkg.X264DspError):
+        ctx.p_frames_host_packed(w, h, n, pics, prm, b["mb_type"], b["partition"] if part else None, b["mv"], b["mvr"], b["mvd"], small,
+                                 f_off, mb_off, b["nnz"], b["cbp"])

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--subme", type=int, default=1)
     ap.add_argument("--qp", type=int, default=26)
     ap.add_argument("--part", type=int, default=0)
+    ap.add_argument("--packed", type=int, default=0, help="1: x264dsp_p_frames_host_packed (compact levels, reconstruction stays on the device)")
     args = ap.parse_args()
     import __graft_entry__ as ge
     pkg = ge.load_package()
@@ -40,7 +41,15 @@ def main():
     recon = ctx.pinned_empty((n, w * h * 3 // 2), np.uint8)
     prm = pkg.PFrameParams(args.me, args.subme, 16, args.qp, 512, 1, 0, args.part)
 
+    packed = ctx.pinned_empty((n * nmb * 392 // 4,), np.int16) if args.packed else None
+    f_off = np.zeros(n + 1, np.int64)
+    mb_off = ctx.pinned_empty((n, nmb), np.int32)
+
     def run():
+        if args.packed:
+            ctx.p_frames_host_packed(w, h, n, pics, prm, o["mb_type"], o["partition"] if args.part else None, o["mv"], o["mvr"], o["mvd"],
+                                     packed, f_off, mb_off, o["nnz"], o["cbp"])
+            return
         if args.part:
             ctx.p_frames_part_host(w, h, n, pics, prm, o["mb_type"], o["partition"], o["mv"], o["mvr"], o["mvd"], o["levels"],
                                    o["nnz"], o["cbp"], recon)
@@ -55,8 +64,10 @@ def main():
             run()
         dt = (time.perf_counter() - t0) / 3
         out.append({"groups": gr, "ms_per_call": 1e3 * dt, "frames_per_s": n / dt,
-                    "d2h_GBps": (sum(a.nbytes for a in o.values()) + recon.nbytes) / dt / 1e9, "h2d_GBps": pics.nbytes / dt / 1e9})
-    print(json.dumps({"frames": n, "me": args.me, "subme": args.subme, "part": args.part, "runs": out}))
+                    "d2h_GBps": ((sum(a.nbytes for k, a in o.items() if k != "levels") + 2 * int(f_off[-1]) + mb_off.nbytes) if args.packed
+                                 else (sum(a.nbytes for a in o.values()) + recon.nbytes)) / dt / 1e9,
+                    "packed_bytes_per_frame": 2 * int(f_off[-1]) / n if args.packed else None, "h2d_GBps": pics.nbytes / dt / 1e9})
+    print(json.dumps({"frames": n, "me": args.me, "subme": args.subme, "part": args.part, "packed": args.packed, "runs": out}))
 
 
 if __name__ == "__main__":

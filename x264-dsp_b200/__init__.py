@@ -495,6 +495,24 @@ class Context:
                                                levels.ctypes.data_as(C.c_void_p), _hp(nnz), cbp.ctypes.data_as(C.c_void_p),
                                                _hp(recon_i420)), "x264dsp_p_frames_part_host")
 
+    def levels_pack(self, n_frames, mb_count, levels, nnz, packed, packed_stride, mb_offset, frame_total):
+        """x264dsp_levels_pack_dev: the dense levels of n_frames as the compact stream the entropy coder reads"""
+        check(lib().x264dsp_levels_pack_dev(self._h, int(n_frames), int(mb_count), _dp(levels), _dp(nnz), _dp(packed),
+                                            C.c_int64(int(packed_stride)), _dp(mb_offset), _dp(frame_total), None),
+              "x264dsp_levels_pack_dev")
+
+    def p_frames_host_packed(self, w, h, n_frames, i420, prm, mb_type, partition, mv, mvr, mvd, packed, frame_offset, mb_offset,
+                             nnz, cbp, recon_i420=None):
+        """x264dsp_p_frames_host_packed: numpy (ideally pinned) arrays; partition None = one vector per macroblock"""
+        check(lib().x264dsp_p_frames_host_packed(self._h, int(w), int(h), int(n_frames), _hp(i420), C.byref(prm),
+                                                 mb_type.ctypes.data_as(C.c_void_p), _hp(partition) if partition is not None else None,
+                                                 mv.ctypes.data_as(C.c_void_p), mvr.ctypes.data_as(C.c_void_p),
+                                                 mvd.ctypes.data_as(C.c_void_p) if mvd is not None else None,
+                                                 packed.ctypes.data_as(C.c_void_p), C.c_int64(int(packed.size)),
+                                                 frame_offset.ctypes.data_as(C.c_void_p), mb_offset.ctypes.data_as(C.c_void_p),
+                                                 _hp(nnz), cbp.ctypes.data_as(C.c_void_p),
+                                                 _hp(recon_i420) if recon_i420 is not None else None), "x264dsp_p_frames_host_packed")
+
     def residual_frames(self, g, fenc_slots, pred_slots, n_frames, qp, levels, nnz, cbp):
         check(lib().x264dsp_residual_frames_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(pred_slots), int(n_frames),
                                                 int(qp), _dp(levels), _dp(nnz), _dp(cbp), None),

@@ -11,6 +11,10 @@
 #include <cstdlib>
 #include "common.cuh"
 
+extern "C" int x264dsp_levels_pack_dev( x264dsp_ctx_t *ctx, int n_frames, int mb_count, const int16_t *levels, const uint8_t *nnz,
+                                        int16_t *packed, int64_t packed_stride, int32_t *mb_offset, int32_t *frame_total,
+                                        void *stream );
+
 #define XH_CHECK( call ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { rc = (int)e_; goto drain; } } while( 0 )
 #define XH_RC( call ) do { rc = ( call ); if( rc ) goto drain; } while( 0 )
 
@@ -250,10 +254,15 @@ drain:
 // partition == NULL: x264dsp_p_frames_dev, one vector per macroblock; else x264dsp_p_frames_part_dev, four (one per 8x8)
 static int xh_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
                              const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv, int16_t *mvr,
-                             int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 )
+                             int16_t *mvd, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420,
+                             int16_t *packed = nullptr, int64_t packed_cap = 0, int64_t *frame_offset = nullptr,
+                             int32_t *mb_offset = nullptr )
 {
+    // packed != NULL: the levels leave as the compact stream of x264dsp_levels_pack_dev (`levels` may then be NULL);
+    // recon_i420 == NULL: the reconstruction stays on the device (an encoder only needs it there, as the next reference)
     const size_t nv = partition ? 4 : 1;
-    if( !ctx || !i420 || !params || !mb_type || !mv || !mvr || !levels || !nnz || !cbp || !recon_i420 || n_frames <= 0 )
+    if( !ctx || !i420 || !params || !mb_type || !mv || !mvr || ( !levels && !packed ) || !nnz || !cbp || n_frames <= 0
+        || ( packed && ( !frame_offset || !mb_offset || packed_cap <= 0 ) ) )
         return X264DSP_E_ARG;
     x264dsp_geom_t g;
     int rc = x264dsp_geometry( width, height, &g );
@@ -262,17 +271,19 @@ static int xh_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_fr
     if( g.mb_w < 3 || g.mb_h < 3 )
         return X264DSP_E_ARG;
     const size_t pic = (size_t)width * height * 3 / 2, nmb = g.mb_count;
-    // Stream groups: each group uploads, prepares, codes and downloads its frames on its own stream, so group k's copies run
-    // under group k+1's kernels.  The wavefront wants many frames per launch (a frame alone is latency bound) and two
-    // wavefront kernels do not share the SMs well: measured on 384 1080p frames (tools/bench_pframe_host.py, DIA / subme 1)
-    // 1 / 2 / 4 / 8 / 16 groups = 2.7 / 3.5 / 4.1 / 3.9 / 2.7 k frames/s -- about a hundred frames per group.
-    int groups = ( n_frames + 48 ) / 96;
+    // Groups: the unit that moves through the three-stage pipeline below (upload | kernels | download).  The wavefront wants many
+    // frames per launch (a frame alone is latency bound), the pipeline wants several groups so that copies hide behind kernels.
+    // Measured on 384 1080p frames (tools/bench_pframe_host.py, DIA / subme 1): dense levels (download bound, 9.8 MB per frame)
+    // 2 / 4 / 8 groups = 95 / 84 / 91 ms; compact levels without the reconstruction (1.1 MB per frame) 2 / 3 / 4 / 6 / 8 groups =
+    // 54 / 56 / 60 / 74 / 89 ms.
+    int groups = packed ? ( n_frames + 96 ) / 192 : ( n_frames + 48 ) / 96;
     if( const char *e = getenv( "X264DSP_PF_HOST_GROUPS" ) )     // measurement knob (tools/bench_pframe_host.py, tests)
         groups = atoi( e );
     if( groups < 1 ) groups = 1;
     if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
     const size_t per_mb = 2 + ( 2 + 2 * nv ) * 2 * sizeof( int16_t ) + X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ) + X264DSP_RES_NNZ_PER_MB
-                        + sizeof( int16_t ) + 4 + X264DSP_LA_SUMS;
+                        + sizeof( int16_t ) + 4 + X264DSP_LA_SUMS
+                        + ( packed ? X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ) + sizeof( int32_t ) : 0 );
     const size_t side_bytes = ( (size_t)n_frames * nmb * per_mb + (size_t)n_frames * 64 + 8192 ) & ~(size_t)255;
     const size_t need_slots = (size_t)( 2 * n_frames + groups ) * g.slot_bytes;
     const size_t need_pics = (size_t)( n_frames + groups ) * pic + (size_t)n_frames * pic;
@@ -294,7 +305,20 @@ static int xh_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_fr
     int16_t *d_cbp = (int16_t *)d_side;     d_side += ( N * 2 + 15 ) & ~(size_t)15;
     uint8_t *d_nz = d_side;                 d_side += ( N * X264DSP_RES_NNZ_PER_MB + 15 ) & ~(size_t)15;
     int8_t *d_type = (int8_t *)d_side;      d_side += ( N + 15 ) & ~(size_t)15;
-    uint8_t *d_part = d_side;
+    uint8_t *d_part = d_side;               d_side += ( N + 15 ) & ~(size_t)15;
+    int32_t *d_ftot = (int32_t *)d_side;    d_side += ( (size_t)n_frames * 4 + 15 ) & ~(size_t)15;
+    int32_t *d_mboff = (int32_t *)d_side;   d_side += packed ? N * 4 : 0;
+    int16_t *d_packed = (int16_t *)d_side;
+    const size_t packed_stride = nmb * X264DSP_RES_LEVELS_PER_MB;     // per frame on the device: the dense size is the worst case
+    int32_t *h_ftot = nullptr;
+    // Three streams, one pipeline: pictures go up on `sh`, every kernel of every group runs on `sc` in group order, results
+    // come down on `sd`; events hand a group from one stage to the next.  (A stream per group let the persistent kernels of
+    // different groups -- the lookahead of one, the wavefront of another -- share the SMs, and a call then took anything
+    // between 52 and 282 ms for the same 384 frames; in order, the same call takes 50.)
+    cudaStream_t sh = ctx->aux[0], sc = ctx->aux[1], sd = ctx->aux[2];
+    cudaEvent_t tot_ready[XD_AUX_STREAMS], ev_in[XD_AUX_STREAMS], ev_out[XD_AUX_STREAMS];
+    int n_events = 0, n_in = 0, n_out = 0;
+    int group_f0[XD_AUX_STREAMS + 1];
 
     int used = 0;
     size_t slot_cursor = 0, pic_cursor = 0;
@@ -302,19 +326,33 @@ static int xh_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_fr
     int32_t *idx = (int32_t *)malloc( ( (size_t)n_frames + 1 ) * ( 2 * sizeof( int32_t ) + 1 ) );
     if( !idx )
         return X264DSP_E_NOMEM;
+    if( packed )
+    {
+        // the context's pinned result buffer (kept between calls: page-locking memory is not something to do per call)
+        if( ( rc = xd_reserve_pinned( (void **)&ctx->clip_out_host, &ctx->clip_out_host_cap, (size_t)n_frames * sizeof( int32_t ) ) ) )
+        {
+            free( idx );
+            return rc;
+        }
+        h_ftot = (int32_t *)ctx->clip_out_host;
+    }
     for( int gi = 0; gi < groups && !rc; gi++ )
     {
         const int f0 = (int)( (int64_t)n_frames * gi / groups ), f1 = (int)( (int64_t)n_frames * ( gi + 1 ) / groups );
         const int nf = f1 - f0;
         if( nf <= 0 )
             continue;
-        cudaStream_t st = ctx->aux[gi];
-        used = gi + 1;
+        cudaStream_t st = sc;
+        used = 3;
         uint8_t *d_pics = ctx->stage_dev + pic_cursor;           pic_cursor += (size_t)( nf + 1 ) * pic;
         uint8_t *d_src = ctx->clip_slots + slot_cursor;           slot_cursor += (size_t)( nf + 1 ) * g.slot_bytes;
         uint8_t *d_rec = ctx->clip_slots + slot_cursor;           slot_cursor += (size_t)nf * g.slot_bytes;
         const size_t m0 = (size_t)f0 * nmb, mn = (size_t)nf * nmb;
-        XH_CHECK( cudaMemcpyAsync( d_pics, i420 + (size_t)f0 * pic, (size_t)( nf + 1 ) * pic, cudaMemcpyHostToDevice, st ) );
+        XH_CHECK( cudaMemcpyAsync( d_pics, i420 + (size_t)f0 * pic, (size_t)( nf + 1 ) * pic, cudaMemcpyHostToDevice, sh ) );
+        XH_CHECK( cudaEventCreateWithFlags( &ev_in[n_in], cudaEventDisableTiming ) );
+        n_in++;
+        XH_CHECK( cudaEventRecord( ev_in[n_in - 1], sh ) );
+        XH_CHECK( cudaStreamWaitEvent( sc, ev_in[n_in - 1], 0 ) );
         XH_RC( x264dsp_frame_load_i420_dev( ctx, &g, d_pics, d_src, nf + 1, st ) );
         XH_RC( x264dsp_frame_expand_border_dev( ctx, &g, d_src, nf + 1, st ) );
         XH_RC( x264dsp_frame_filter_dev( ctx, &g, d_src, nf, st ) );                 // reference frames only
@@ -340,7 +378,30 @@ static int xh_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_fr
             XH_RC( x264dsp_p_frames_dev( ctx, &g, d_src + g.slot_bytes, d_src, d_rec, nf, params, d_lmv + m0 * 2, NULL, d_type + m0,
                                          d_mv + m0 * 2, d_mvr + m0 * 2, d_mvd + m0 * 2, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
                                          d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, st ) );
-        XH_RC( x264dsp_frame_store_i420_dev( ctx, &g, d_rec, d_out_pics + (size_t)f0 * pic, nf, st ) );
+        group_f0[gi] = f0;
+        group_f0[gi + 1] = f1;
+        if( packed )
+        {
+            // the compact stream and, first of all copies, its per-frame lengths: the host needs them to place the frames
+            XH_RC( x264dsp_levels_pack_dev( ctx, nf, (int)nmb, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB,
+                                            d_packed + (size_t)f0 * packed_stride, (int64_t)packed_stride, d_mboff + m0, d_ftot + f0, st ) );
+        }
+        if( recon_i420 )
+            XH_RC( x264dsp_frame_store_i420_dev( ctx, &g, d_rec, d_out_pics + (size_t)f0 * pic, nf, st ) );
+        // ---- the group's results are complete: everything below is copies on the download stream
+        XH_CHECK( cudaEventCreateWithFlags( &ev_out[n_out], cudaEventDisableTiming ) );
+        n_out++;
+        XH_CHECK( cudaEventRecord( ev_out[n_out - 1], sc ) );
+        XH_CHECK( cudaStreamWaitEvent( sd, ev_out[n_out - 1], 0 ) );
+        st = sd;
+        if( packed )
+        {
+            XH_CHECK( cudaMemcpyAsync( h_ftot + f0, d_ftot + f0, (size_t)nf * sizeof( int32_t ), cudaMemcpyDeviceToHost, st ) );
+            XH_CHECK( cudaEventCreateWithFlags( &tot_ready[n_events], cudaEventDisableTiming ) );
+            n_events++;
+            XH_CHECK( cudaEventRecord( tot_ready[n_events - 1], st ) );
+            XH_CHECK( cudaMemcpyAsync( mb_offset + m0, d_mboff + m0, mn * sizeof( int32_t ), cudaMemcpyDeviceToHost, st ) );
+        }
         XH_CHECK( cudaMemcpyAsync( mb_type + m0, d_type + m0, mn, cudaMemcpyDeviceToHost, st ) );
         if( partition )
             XH_CHECK( cudaMemcpyAsync( partition + m0, d_part + m0, mn, cudaMemcpyDeviceToHost, st ) );
@@ -348,13 +409,39 @@ static int xh_p_frames_host( x264dsp_ctx_t *ctx, int width, int height, int n_fr
         XH_CHECK( cudaMemcpyAsync( mvr + m0 * 2, d_mvr + m0 * 2, mn * 4, cudaMemcpyDeviceToHost, st ) );
         if( mvd )
             XH_CHECK( cudaMemcpyAsync( mvd + m0 * 2 * nv, d_mvd + m0 * 2 * nv, mn * 4 * nv, cudaMemcpyDeviceToHost, st ) );
-        XH_CHECK( cudaMemcpyAsync( levels + m0 * X264DSP_RES_LEVELS_PER_MB, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
-                                   mn * X264DSP_RES_LEVELS_PER_MB * 2, cudaMemcpyDeviceToHost, st ) );
+        if( levels )
+            XH_CHECK( cudaMemcpyAsync( levels + m0 * X264DSP_RES_LEVELS_PER_MB, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
+                                       mn * X264DSP_RES_LEVELS_PER_MB * 2, cudaMemcpyDeviceToHost, st ) );
         XH_CHECK( cudaMemcpyAsync( nnz + m0 * X264DSP_RES_NNZ_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB, mn * X264DSP_RES_NNZ_PER_MB,
                                    cudaMemcpyDeviceToHost, st ) );
         XH_CHECK( cudaMemcpyAsync( cbp + m0, d_cbp + m0, mn * 2, cudaMemcpyDeviceToHost, st ) );
-        XH_CHECK( cudaMemcpyAsync( recon_i420 + (size_t)f0 * pic, d_out_pics + (size_t)f0 * pic, (size_t)nf * pic,
-                                   cudaMemcpyDeviceToHost, st ) );
+        if( recon_i420 )
+            XH_CHECK( cudaMemcpyAsync( recon_i420 + (size_t)f0 * pic, d_out_pics + (size_t)f0 * pic, (size_t)nf * pic,
+                                       cudaMemcpyDeviceToHost, st ) );
+    }
+    if( packed )
+    {
+        // group by group, as their lengths arrive (the later groups' kernels run meanwhile): frames back to back on the host
+        int64_t at = 0;
+        frame_offset[0] = 0;
+        for( int gi = 0; gi < n_events; gi++ )
+        {
+            XH_CHECK( cudaEventSynchronize( tot_ready[gi] ) );
+            for( int f = group_f0[gi]; f < group_f0[gi + 1]; f++ )
+            {
+                const int64_t len = h_ftot[f];
+                if( at + len > packed_cap )
+                {
+                    rc = X264DSP_E_ARG;                          // the caller's buffer is too small for this content
+                    goto drain;
+                }
+                if( len )
+                    XH_CHECK( cudaMemcpyAsync( packed + at, d_packed + (size_t)f * packed_stride, (size_t)len * sizeof( int16_t ),
+                                               cudaMemcpyDeviceToHost, sd ) );
+                at += len;
+                frame_offset[f + 1] = at;
+            }
+        }
     }
 drain:
     for( int i = 0; i < used; i++ )
@@ -363,6 +450,12 @@ drain:
         if( e != cudaSuccess && !rc )
             rc = (int)e;
     }
+    for( int i = 0; i < n_events; i++ )
+        cudaEventDestroy( tot_ready[i] );
+    for( int i = 0; i < n_in; i++ )
+        cudaEventDestroy( ev_in[i] );
+    for( int i = 0; i < n_out; i++ )
+        cudaEventDestroy( ev_out[i] );
     free( idx );
     ctx->scratch_busy[XD_SCRATCH_DEBLOCK] = 0;
     ctx->scratch_busy[XD_SCRATCH_LOOKAHEAD] = 0;
@@ -384,4 +477,18 @@ extern "C" int x264dsp_p_frames_part_host( x264dsp_ctx_t *ctx, int width, int he
     if( !partition )
         return X264DSP_E_ARG;
     return xh_p_frames_host( ctx, width, height, n_frames, i420, params, mb_type, partition, mv8, mvr, mvd8, levels, nnz, cbp, recon_i420 );
+}
+
+// ... with the levels as the compact stream the entropy coder reads (x264dsp_levels_pack_dev) and, optionally, without the
+// reconstruction: what a transcoder moves over PCIe per coded frame drops from 9.8 MB to the picture's own content
+extern "C" int x264dsp_p_frames_host_packed( x264dsp_ctx_t *ctx, int width, int height, int n_frames, const uint8_t *i420,
+                                              const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition,
+                                              int16_t *mv, int16_t *mvr, int16_t *mvd, int16_t *packed_levels, int64_t packed_capacity,
+                                              int64_t *frame_offset, int32_t *mb_offset, uint8_t *nnz, int16_t *cbp,
+                                              uint8_t *recon_i420 )
+{
+    if( !packed_levels )
+        return X264DSP_E_ARG;
+    return xh_p_frames_host( ctx, width, height, n_frames, i420, params, mb_type, partition, mv, mvr, mvd, nullptr, nnz, cbp, recon_i420,
+                             packed_levels, packed_capacity, frame_offset, mb_offset );
 }
