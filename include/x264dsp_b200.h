@@ -550,6 +550,39 @@ int x264dsp_p_frames_part_host( x264dsp_ctx_t *ctx, int width, int height, int n
                                 const x264dsp_pframe_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv8,
                                 int16_t *mvr, int16_t *mvd8, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *recon_i420 );
 
+/* ------------------------------------------------------------------ closed GOPs on the device (8(f) N4 + the in-loop filter)
+ * Boundary strengths from the slice kernels' own outputs: x264_macroblock_deblock_strength (common/macroblock.c:677-691) +
+ * deblock_strength_c (common/deblock.c:297-323) for every macroblock of n_frames frames, one reference frame:
+ *   mb_type [frame][mb], nnz [frame][mb][27] (entries 0..15: the luma 4x4 blocks in coding order), mv8 [frame][mb][4][2]
+ *   (may be NULL when every macroblock is intra) -> bs [frame][mb][2][8][4] as x264dsp_deblock_frames_dev reads it.
+ * Segments of edge 0 at the picture's left / top border are 0 (the reference never filters them). */
+int x264dsp_boundary_strength_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, int n_frames, const int8_t *mb_type,
+                                          const uint8_t *nnz, const int16_t *mv8, uint8_t *bs, void *stream );
+
+/* n_gops closed GOPs of gop_len frames each (frame 0 an I frame, the rest P frames against their predecessor: the reference
+ * without B frames, encoder/encoder.c:1180-1385) coded entirely on the device.  Slots and outputs are POSITION-major:
+ * slot / entry [t * n_gops + gop] is frame t of GOP gop, so that one launch of each stage covers position t of every GOP:
+ *   x264dsp_i_frames_dev (t = 0) or x264dsp_p_frames_dev / _part_dev against recon[t - 1]  ->  boundary strengths ->
+ *   x264dsp_deblock_frames_dev -> x264dsp_frame_expand_border_dev -> x264dsp_frame_filter_dev on recon[t]
+ * fenc_slots: gop_len * n_gops staged source frames; recon_slots: as many slots, which end up holding every frame's final
+ * reference planes (N, H, V, HV, chroma).  lowres_mv [t][gop][mb][2]: the lookahead's vectors of frame t against frame t - 1
+ * (entries of t = 0 unused) or NULL.  The previous frame's 16x16 vectors serve as temporal candidates from t = 2 on.
+ * Outputs [t][gop][mb]...: mb_type, partition, mv8 / mvd8 [4][2] (one vector per 8x8 whatever params->analyse_inter), mvr [2],
+ * levels, nnz, cbp as the slice kernels write them; mode16, chroma_mode, modes4 [16], luma_dc [16]: position 0 only
+ * ([gop][mb]...).  Fixed QPs (qp_i for position 0, qp_p after it: constant-QP rate control). */
+typedef struct x264dsp_gop_encode_params
+{
+    int32_t me_method, subpel_refine, me_range;
+    int32_t qp_i, qp_p;
+    int32_t mv_range, fast_pskip, analyse_inter;
+    int32_t deblock, alpha_c0_offset, beta_offset;     /* h->param.b_deblocking_filter, h->sh.i_alpha_c0_offset, i_beta_offset */
+} x264dsp_gop_encode_params_t;
+int x264dsp_gops_encode_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots, uint8_t *recon_slots,
+                             int n_gops, int gop_len, const x264dsp_gop_encode_params_t *params, const int16_t *lowres_mv,
+                             int8_t *mb_type, uint8_t *partition, int16_t *mv8, int16_t *mvr, int16_t *mvd8, int16_t *levels,
+                             uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode, uint8_t *modes4,
+                             int16_t *luma_dc, void *stream );
+
 /* ------------------------------------------------------------------ entropy hand-off, compact (8(f) N3)
  * The dense levels are 392 int16 per macroblock, 6.4 MB per 1080p frame, and the writer (x264_macroblock_write_cabac,
  * encoder/cabac.c:571-700) only reads a block whose non_zero_count flag is set.  The compact stream keeps exactly those units

@@ -157,6 +157,12 @@ def frame_range(n_frames, rank, world):
     return first.value, count.value, bool(prev.value)
 
 
+class GopEncodeParams(C.Structure):
+    """x264dsp_gop_encode_params_t"""
+    _fields_ = [(n, C.c_int32) for n in ("me_method", "subpel_refine", "me_range", "qp_i", "qp_p", "mv_range", "fast_pskip",
+                                         "analyse_inter", "deblock", "alpha_c0_offset", "beta_offset")]
+
+
 class GopParams(C.Structure):
     """x264dsp_gop_params_t"""
     _fields_ = [("keyint_max", C.c_int32), ("keyint_min", C.c_int32), ("scenecut_threshold", C.c_int32)]
@@ -494,6 +500,20 @@ class Context:
                                                mvd8.ctypes.data_as(C.c_void_p) if mvd8 is not None else None,
                                                levels.ctypes.data_as(C.c_void_p), _hp(nnz), cbp.ctypes.data_as(C.c_void_p),
                                                _hp(recon_i420)), "x264dsp_p_frames_part_host")
+
+    def boundary_strength_frames(self, g, n_frames, mb_type, nnz, mv8, bs):
+        check(lib().x264dsp_boundary_strength_frames_dev(self._h, C.byref(g), int(n_frames), _dp(mb_type), _dp(nnz), _dp(mv8), _dp(bs),
+                                                         None), "x264dsp_boundary_strength_frames_dev")
+
+    def gops_encode(self, g, fenc_slots, recon_slots, n_gops, gop_len, prm, lowres_mv, out):
+        """x264dsp_gops_encode_dev; out: dict of device tensors mb_type, partition, mv8, mvr, mvd8, levels, nnz, cbp, mode16,
+        chroma_mode, modes4, luma_dc (position-major: [t][gop][mb]...)"""
+        check(lib().x264dsp_gops_encode_dev(self._h, C.byref(g), _dp(fenc_slots), _dp(recon_slots), int(n_gops), int(gop_len),
+                                            C.byref(prm), _dp(lowres_mv) if lowres_mv is not None else None, _dp(out["mb_type"]),
+                                            _dp(out["partition"]), _dp(out["mv8"]), _dp(out["mvr"]), _dp(out.get("mvd8")),
+                                            _dp(out["levels"]), _dp(out["nnz"]), _dp(out["cbp"]), _dp(out["mode16"]),
+                                            _dp(out["chroma_mode"]), _dp(out["modes4"]), _dp(out["luma_dc"]), None),
+              "x264dsp_gops_encode_dev")
 
     def levels_pack(self, n_frames, mb_count, levels, nnz, packed, packed_stride, mb_offset, frame_total):
         """x264dsp_levels_pack_dev: the dense levels of n_frames as the compact stream the entropy coder reads"""
