@@ -358,6 +358,7 @@ def cpu_recon_reference(which, w, h, pics, mv, bs, threads, qp=26, target_s=4.0)
 
 PF_FRAMES = 384
 PF_E2E_FRAMES = 384
+GOPS_N, GOPS_LEN = 64, 12            # closed GOPs per call, frames per GOP (the `gops` entry)
 # (name, (me_method, subme, analyse.inter != 0))
 PF_SETTINGS = (("dia_subme1", (0, 1, 0)), ("hex_subme5", (1, 5, 0)), ("hex_subme5_psub16x16", (1, 5, 1)))
 
@@ -462,6 +463,66 @@ def pframe_e2e(pkg, ctx, g, w, h, n_frames, me, subme, qp=26, reps=3):
     dt_dense = (time.perf_counter() - t0) / reps
     d2h_dense = int(sum(a.nbytes for k, a in o.items() if k != "mb_offset") + levels.nbytes + recon.nbytes)
     return dt, int(pics.nbytes), d2h, dt_dense, d2h_dense
+
+
+def gops_measure(pkg, ctx, torch, g, w, h, n_gops, gop_len, me, subme, qp=26):
+    """closed GOPs (an I frame and gop_len - 1 P frames, in-loop filter on) coded entirely on the device
+    (x264dsp_gops_encode_dev: one launch of every stage per GOP position over the frames of all GOPs), and the same through host
+    memory (x264dsp_gops_encode_host: pinned pictures in, the entropy coder's input out).  Returns (device ms per call, host
+    seconds per call, h2d bytes, d2h bytes)"""
+    stream = ctx.torch_stream()
+    nmb, n = g.mb_count, n_gops * gop_len
+    prm = pkg.GopEncodeParams(me, subme, 16, qp - 3, qp, 512, 1, 0, 1, 0, 0)
+    distinct = [pkg.synth_frame(w, h, i) for i in range(25)]
+    one = torch.zeros(25 * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    ctx.frame_load_i420(g, torch.from_numpy(np.stack(distinct)).cuda(), one, 25)
+    ctx.frame_expand_border(g, one, 25)
+    ctx.frame_init_lowres(g, one, 25)
+    fenc = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    for t in range(gop_len):
+        for gop in range(n_gops):
+            k, j = t * n_gops + gop, (3 * gop + t) % 25
+            fenc[k * g.slot_bytes:(k + 1) * g.slot_bytes] = one[j * g.slot_bytes:(j + 1) * g.slot_bytes]
+    del one
+    b = np.arange(n_gops, n, dtype=np.int32)
+    d_lmv = torch.zeros((n, nmb, 2), dtype=torch.int16, device="cuda")
+    d_lc = torch.zeros((n, nmb), dtype=torch.int32, device="cuda")
+    d_ls = torch.zeros((n, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
+    ctx.lookahead_frame_cost(g, fenc, b, b - n_gops, np.zeros(b.size, np.uint8), d_lmv[n_gops:], d_lc[n_gops:], d_ls[n_gops:])
+    shapes = {"mb_type": ((n, nmb), np.int8), "partition": ((n, nmb), np.uint8), "mv8": ((n, nmb, 4, 2), np.int16),
+              "mvr": ((n, nmb, 2), np.int16), "mvd8": ((n, nmb, 4, 2), np.int16), "nnz": ((n, nmb, 27), np.uint8), "cbp": ((n, nmb), np.int16),
+              "mode16": ((n_gops, nmb), np.uint8), "chroma_mode": ((n_gops, nmb), np.uint8), "modes4": ((n_gops, nmb, 16), np.uint8),
+              "luma_dc": ((n_gops, nmb, 16), np.int16)}
+    dev = {k: torch.zeros(s, dtype=getattr(torch, np.dtype(t).name), device="cuda") for k, (s, t) in shapes.items()}
+    dev["levels"] = torch.zeros((n, nmb, pkg.RES_LEVELS_PER_MB), dtype=torch.int16, device="cuda")
+    recon = torch.zeros_like(fenc)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.gops_encode(g, fenc, recon, n_gops, gop_len, prm, d_lmv, dev)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(2):
+        ctx.gops_encode(g, fenc, recon, n_gops, gop_len, prm, d_lmv, dev)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1) / 2
+    del fenc, recon, dev, d_lmv, d_lc, d_ls
+    torch.cuda.empty_cache()
+    pics = ctx.pinned_empty((n, w * h * 3 // 2), np.uint8)
+    for gop in range(n_gops):
+        for t in range(gop_len):
+            pics[gop * gop_len + t] = distinct[(3 * gop + t) % 25]
+    out = {k: ctx.pinned_empty(s, t) for k, (s, t) in shapes.items()}
+    packed = ctx.pinned_empty((n * nmb * pkg.RES_LEVELS_PER_MB // 3,), np.int16)
+    f_off, f_size = np.zeros(n, np.int64), np.zeros(n, np.int32)
+    mb_off = ctx.pinned_empty((n, nmb), np.int32)
+    run = lambda: ctx.gops_encode_host(w, h, n_gops, gop_len, pics, prm, out, packed, f_off, f_size, mb_off)
+    run()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        run()
+    dt = (time.perf_counter() - t0) / 2
+    d2h = int(sum(a.nbytes for a in out.values()) + mb_off.nbytes + 2 * int(f_size.sum()))
+    return dev_ms, dt, int(pics.nbytes), d2h
 
 
 def pframe_oracle_check(g, check):
@@ -1161,6 +1222,7 @@ def main():
         for name, (pme, psub, ppart) in PF_SETTINGS:
             pf[name] = pframe_measure(pkg, ctx, torch, g, w, h, PF_FRAMES if not ppart else PF_FRAMES // 2, pme, psub, part=ppart)
         pf_e2e = pframe_e2e(pkg, ctx, g, w, h, PF_E2E_FRAMES, 0, 1)
+        gops = gops_measure(pkg, ctx, torch, g, w, h, GOPS_N, GOPS_LEN, 0, 1) if world == 1 else None
         sec += [pf["dia_subme1"][0], pf["hex_subme5"][0], pf_e2e[0], pf["hex_subme5_psub16x16"][0]]
     else:
         sec += [0.0, 0.0, 0.0, 0.0]
@@ -1373,6 +1435,16 @@ def main():
                           "dense_door": {"value": PF_E2E_FRAMES / pf_e2e[3], "d2h_bytes_per_step": pf_e2e[4],
                                          "api": "x264dsp_p_frames_host: all 392 levels per macroblock and the reconstructed "
                                                 "pictures come back too (rank 0's own time)"}}
+            if gops is not None:
+                frames_g = GOPS_N * GOPS_LEN
+                pfl["gops"] = {"workload": f"{GOPS_N} closed GOPs of {GOPS_LEN} 1080p frames (I + P, DIA / subme 1, QP 23 / 26, in-loop filter on), every "
+                                           "stage on the device: slice kernels, boundary strengths, deblocking, border, half-pel planes; each "
+                                           "frame predicts from the device's own previous reconstruction (tests/test_gpu_gop_chain.py: identical "
+                                           "to the running reference encoder frame by frame)",
+                               "value": 1e3 * frames_g / gops[0], "unit": "frames/s", "us_per_frame": 1e3 * gops[0] / frames_g,
+                               "note": "an I frame costs about 0.6 ms, a P frame with its filter stages about 0.11 ms at this batch size",
+                               "e2e": {"value": frames_g / gops[1], "unit": "frames/s", "h2d_bytes_per_step": gops[2],
+                                       "d2h_bytes_per_step": gops[3], "api": "x264dsp_gops_encode_host"}}
             line["pframe"] = pfl
         print(json.dumps(line))
     ctx.close()

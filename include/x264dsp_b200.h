@@ -583,6 +583,19 @@ int x264dsp_gops_encode_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const 
                              uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode, uint8_t *modes4,
                              int16_t *luma_dc, void *stream );
 
+/* The same from HOST memory: i420 holds the GOPs one after the other ([gop][t] planar pictures); source staging, the
+ * half-resolution planes and the lookahead's vectors of every (t - 1, t) pair are built on the device, then
+ * x264dsp_gops_encode_dev, then x264dsp_levels_pack_dev.  Host outputs are position-major over all GOPs ([t][gop][mb]...,
+ * index k = t * n_gops + gop) except mode16 / chroma_mode / modes4 / luma_dc ([gop][mb]...: the I frames); the compact
+ * levels of frame k are packed_levels[frame_offset[k] .. + frame_size[k]), its macroblocks at mb_offset[k][mb] inside it
+ * (X264DSP_E_ARG when packed_capacity, in int16 units, is too small for the content).  The reconstructions stay on the
+ * device.  All copies are inside the call; the GOPs move through an upload | kernels | download pipeline in two groups. */
+int x264dsp_gops_encode_host( x264dsp_ctx_t *ctx, int width, int height, int n_gops, int gop_len, const uint8_t *i420,
+                              const x264dsp_gop_encode_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv8,
+                              int16_t *mvr, int16_t *mvd8, uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode,
+                              uint8_t *modes4, int16_t *luma_dc, int16_t *packed_levels, int64_t packed_capacity,
+                              int64_t *frame_offset, int32_t *frame_size, int32_t *mb_offset );
+
 /* ------------------------------------------------------------------ entropy hand-off, compact (8(f) N3)
  * The dense levels are 392 int16 per macroblock, 6.4 MB per 1080p frame, and the writer (x264_macroblock_write_cabac,
  * encoder/cabac.c:571-700) only reads a block whose non_zero_count flag is set.  The compact stream keeps exactly those units

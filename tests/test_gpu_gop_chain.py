@@ -86,3 +86,52 @@ def test_gop_chain_reproduces_the_encoder(pkg, ctx, w, h, n, me, subme, qp, psub
                 assert np.array_equal(a, b), f"{tag}: chroma reference plane differs in {np.count_nonzero(a != b)} bytes"
     if psub:
         assert seen_parts >= {13, 16}, seen_parts
+
+
+@pytest.mark.parametrize("w,h,n_gops,gop_len,me,subme,psub,groups", [(208, 160, 5, 4, 1, 5, 1, 2), (352, 288, 3, 3, 0, 1, 0, 1)])
+def test_gops_encode_host_matches_the_device_chain(pkg, ctx, w, h, n_gops, gop_len, me, subme, psub, groups, monkeypatch):
+    """x264dsp_gops_encode_host (pictures in host memory, [gop][t]; groups of GOPs through the copy / kernel pipeline; compact
+    levels) against the same stages called one by one on device memory"""
+    import torch
+    from test_gpu_host_paths import expand_packed, mask_dense
+    monkeypatch.setenv("X264DSP_GOPS_HOST_GROUPS", str(groups))
+    g = pkg.geometry(w, h)
+    nmb = g.mb_count
+    n = n_gops * gop_len
+    pics = np.stack([pkg.synth_frame(w, h, 7 * gop + t, cut_frame=-1) for gop in range(n_gops) for t in range(gop_len)])     # [gop][t]
+    prm = pkg.GopEncodeParams(me, subme, 16, 23, 26, 128, 1, psub, 1, 0, 0)
+    shapes = {"mb_type": ((n, nmb), np.int8), "partition": ((n, nmb), np.uint8), "mv8": ((n, nmb, 4, 2), np.int16),
+              "mvr": ((n, nmb, 2), np.int16), "mvd8": ((n, nmb, 4, 2), np.int16), "nnz": ((n, nmb, 27), np.uint8), "cbp": ((n, nmb), np.int16),
+              "mode16": ((n_gops, nmb), np.uint8), "chroma_mode": ((n_gops, nmb), np.uint8), "modes4": ((n_gops, nmb, 16), np.uint8),
+              "luma_dc": ((n_gops, nmb, 16), np.int16)}
+    out = {k: np.zeros(s, t) for k, (s, t) in shapes.items()}
+    packed = np.full(n * nmb * 392 // 2, 999, np.int16)
+    f_off, f_size, mb_off = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros((n, nmb), np.int32)
+    ctx.gops_encode_host(w, h, n_gops, gop_len, pics, prm, out, packed, f_off, f_size, mb_off)
+    # ---- the same, stage by stage, position-major
+    order = [gop * gop_len + t for t in range(gop_len) for gop in range(n_gops)]
+    fenc = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    ctx.frame_load_i420(g, torch.from_numpy(pics[order]).cuda(), fenc, n)
+    ctx.frame_expand_border(g, fenc, n)
+    ctx.frame_init_lowres(g, fenc, n)
+    b = np.arange(n_gops, n, dtype=np.int32)
+    d_lmv = torch.zeros((n, nmb, 2), dtype=torch.int16, device="cuda")
+    d_lc = torch.zeros((n, nmb), dtype=torch.int32, device="cuda")
+    d_ls = torch.zeros((n, pkg.LA_SUMS), dtype=torch.int32, device="cuda")
+    ctx.lookahead_frame_cost(g, fenc, b, b - n_gops, np.zeros(b.size, np.uint8), d_lmv[n_gops:], d_lc[n_gops:], d_ls[n_gops:])
+    dev = {k: torch.zeros(s, dtype=getattr(torch, np.dtype(t).name), device="cuda") for k, (s, t) in shapes.items()}
+    dev["levels"] = torch.zeros((n, nmb, 392), dtype=torch.int16, device="cuda")
+    recon = torch.zeros_like(fenc)
+    ctx.gops_encode(g, fenc, recon, n_gops, gop_len, prm, d_lmv, dev)
+    ctx.sync()
+    for k in shapes:
+        assert np.array_equal(out[k], dev[k].cpu().numpy()), k
+    levels, nnz = dev["levels"].cpu().numpy(), out["nnz"]
+    assert (out["mb_type"][:n_gops] <= 3).all() and (out["mb_type"][n_gops:] >= 4).all()          # position 0 intra, the rest inter
+    used = np.zeros(packed.size, bool)
+    for k in range(n):
+        stream = packed[f_off[k]: f_off[k] + f_size[k]]
+        assert np.array_equal(expand_packed(stream, mb_off[k], nnz[k]), mask_dense(levels[k], nnz[k])), f"frame {k}: compact levels"
+        assert not used[f_off[k]: f_off[k] + f_size[k]].any(), "two frames share bytes of the stream"
+        used[f_off[k]: f_off[k] + f_size[k]] = True
+    assert (packed[~used] == 999).all()

@@ -515,6 +515,16 @@ class Context:
                                             _dp(out["chroma_mode"]), _dp(out["modes4"]), _dp(out["luma_dc"]), None),
               "x264dsp_gops_encode_dev")
 
+    def gops_encode_host(self, w, h, n_gops, gop_len, i420, prm, out, packed, frame_offset, frame_size, mb_offset):
+        """x264dsp_gops_encode_host: numpy (ideally pinned) arrays; out: dict mb_type, partition, mv8, mvr, mvd8, nnz, cbp, mode16,
+        chroma_mode, modes4, luma_dc"""
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        check(lib().x264dsp_gops_encode_host(self._h, int(w), int(h), int(n_gops), int(gop_len), _hp(i420), C.byref(prm), vp(out["mb_type"]),
+                                             vp(out["partition"]), vp(out["mv8"]), vp(out["mvr"]), vp(out.get("mvd8")), vp(out["nnz"]),
+                                             vp(out["cbp"]), vp(out["mode16"]), vp(out["chroma_mode"]), vp(out["modes4"]),
+                                             vp(out["luma_dc"]), vp(packed), C.c_int64(int(packed.size)), vp(frame_offset),
+                                             vp(frame_size), vp(mb_offset)), "x264dsp_gops_encode_host")
+
     def levels_pack(self, n_frames, mb_count, levels, nnz, packed, packed_stride, mb_offset, frame_total):
         """x264dsp_levels_pack_dev: the dense levels of n_frames as the compact stream the entropy coder reads"""
         check(lib().x264dsp_levels_pack_dev(self._h, int(n_frames), int(mb_count), _dp(levels), _dp(nnz), _dp(packed),

@@ -492,3 +492,195 @@ extern "C" int x264dsp_p_frames_host_packed( x264dsp_ctx_t *ctx, int width, int 
     return xh_p_frames_host( ctx, width, height, n_frames, i420, params, mb_type, partition, mv, mvr, mvd, nullptr, nnz, cbp, recon_i420,
                              packed_levels, packed_capacity, frame_offset, mb_offset );
 }
+
+// ---------------------------------------------------------------------------------------------
+// Closed GOPs from host memory (x264dsp_gops_encode_dev behind a door): pictures in, what the entropy coder needs out.  The
+// GOPs are cut into groups that move through the same three-stage pipeline as the P-slice door (upload | kernels | download);
+// inside a group everything is position-major (one launch per stage and GOP position), the host arrays are position-major
+// over ALL GOPs, so every result array of a group lands with one strided copy.
+extern "C" int x264dsp_gops_encode_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots, uint8_t *recon_slots,
+                                        int n_gops, int gop_len, const x264dsp_gop_encode_params_t *params, const int16_t *lowres_mv,
+                                        int8_t *mb_type, uint8_t *partition, int16_t *mv8, int16_t *mvr, int16_t *mvd8, int16_t *levels,
+                                        uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode, uint8_t *modes4,
+                                        int16_t *luma_dc, void *stream );
+
+extern "C" int x264dsp_gops_encode_host( x264dsp_ctx_t *ctx, int width, int height, int n_gops, int gop_len, const uint8_t *i420,
+                                          const x264dsp_gop_encode_params_t *params, int8_t *mb_type, uint8_t *partition,
+                                          int16_t *mv8, int16_t *mvr, int16_t *mvd8, uint8_t *nnz, int16_t *cbp, uint8_t *mode16,
+                                          uint8_t *chroma_mode, uint8_t *modes4, int16_t *luma_dc, int16_t *packed_levels,
+                                          int64_t packed_capacity, int64_t *frame_offset, int32_t *frame_size, int32_t *mb_offset )
+{
+    if( !ctx || !i420 || !params || !mb_type || !partition || !mv8 || !mvr || !nnz || !cbp || !mode16 || !chroma_mode || !modes4
+        || !luma_dc || !packed_levels || !frame_offset || !frame_size || !mb_offset || n_gops <= 0 || gop_len <= 0 || packed_capacity <= 0 )
+        return X264DSP_E_ARG;
+    x264dsp_geom_t g;
+    int rc = x264dsp_geometry( width, height, &g );
+    if( rc )
+        return rc;
+    if( g.mb_w < 3 || g.mb_h < 3 )
+        return X264DSP_E_ARG;
+    const size_t pic = (size_t)width * height * 3 / 2, nmb = g.mb_count;
+    const size_t n_frames = (size_t)n_gops * gop_len, N = n_frames * nmb;
+    int groups = n_gops >= 32 ? 2 : 1;
+    if( const char *e = getenv( "X264DSP_GOPS_HOST_GROUPS" ) )    // measurement knob, tests
+        groups = atoi( e );
+    if( groups < 1 ) groups = 1;
+    if( groups > n_gops ) groups = n_gops;
+    if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
+    // device memory: pictures, source + reconstruction slots, side arrays (all per frame, groups one after the other)
+    const size_t per_mb = 1 + 1 + 16 + 4 + 16 + X264DSP_RES_NNZ_PER_MB + 2 + 4 /* lowres mv */ + 4 /* lookahead cost */
+                        + 2 * X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ) + 4 /* mb_offset */ + 1 + 1 + 16 + 32 /* I-frame side */;
+    const size_t side_bytes = ( N * per_mb + n_frames * ( 4 + X264DSP_LA_SUMS * 4 ) + 65536 ) & ~(size_t)255;
+    XD_CHECK( cudaSetDevice( ctx->device ) );
+    if( ctx->stage_dev_cap < n_frames * pic || ctx->clip_slots_cap < 2 * n_frames * g.slot_bytes || ctx->me_blocks_cap < side_bytes )
+        XD_CHECK( cudaDeviceSynchronize() );
+    if( ( rc = xd_reserve_dev( (void **)&ctx->stage_dev, &ctx->stage_dev_cap, n_frames * pic ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->clip_slots, &ctx->clip_slots_cap, 2 * n_frames * g.slot_bytes ) ) ) return rc;
+    if( ( rc = xd_reserve_dev( (void **)&ctx->me_blocks, &ctx->me_blocks_cap, side_bytes ) ) ) return rc;
+    if( ( rc = xd_reserve_pinned( (void **)&ctx->clip_out_host, &ctx->clip_out_host_cap, n_frames * sizeof( int32_t ) ) ) ) return rc;
+    int32_t *h_ftot = (int32_t *)ctx->clip_out_host;
+    uint8_t *d = ctx->me_blocks;
+#define XG_TAKE( type, name, count ) type *name = (type *)d; d += ( (size_t)( count ) * sizeof( type ) + 255 ) & ~(size_t)255
+    XG_TAKE( int16_t, d_lv, N * X264DSP_RES_LEVELS_PER_MB );
+    XG_TAKE( int16_t, d_packed, N * X264DSP_RES_LEVELS_PER_MB );
+    XG_TAKE( int16_t, d_mv8, N * 8 );
+    XG_TAKE( int16_t, d_mvd8, N * 8 );
+    XG_TAKE( int16_t, d_mvr, N * 2 );
+    XG_TAKE( int16_t, d_lmv, N * 2 );
+    XG_TAKE( int32_t, d_lc, N );
+    XG_TAKE( int32_t, d_ls, n_frames * X264DSP_LA_SUMS );
+    XG_TAKE( int32_t, d_mboff, N );
+    XG_TAKE( int32_t, d_ftot, n_frames );
+    XG_TAKE( int16_t, d_cbp, N );
+    XG_TAKE( int16_t, d_dc, N * 16 );
+    XG_TAKE( uint8_t, d_nz, N * X264DSP_RES_NNZ_PER_MB );
+    XG_TAKE( int8_t, d_type, N );
+    XG_TAKE( uint8_t, d_part, N );
+    XG_TAKE( uint8_t, d_m16, N );
+    XG_TAKE( uint8_t, d_cm, N );
+    XG_TAKE( uint8_t, d_m4, N * 16 );
+#undef XG_TAKE
+    const size_t packed_stride = nmb * X264DSP_RES_LEVELS_PER_MB;
+    cudaStream_t sh = ctx->aux[0], sc = ctx->aux[1], sd = ctx->aux[2];
+    cudaEvent_t ev_in[XD_AUX_STREAMS], ev_out[XD_AUX_STREAMS], tot_ready[XD_AUX_STREAMS];
+    int n_in = 0, n_out = 0, n_tot = 0, used = 0;
+    int group_g0[XD_AUX_STREAMS + 1];
+    int32_t *idx = (int32_t *)malloc( ( n_frames + 1 ) * ( 2 * sizeof( int32_t ) + 1 ) );
+    if( !idx )
+        return X264DSP_E_NOMEM;
+    size_t fcur = 0;                                              // frames placed so far (device arrays: group after group)
+    for( int gi = 0; gi < groups && !rc; gi++ )
+    {
+        const int g0 = (int)( (int64_t)n_gops * gi / groups ), g1 = (int)( (int64_t)n_gops * ( gi + 1 ) / groups ), ng = g1 - g0;
+        group_g0[gi] = g0;
+        group_g0[gi + 1] = g1;
+        if( ng <= 0 )
+            continue;
+        used = 3;
+        const size_t nf = (size_t)ng * gop_len, m0 = fcur * nmb;
+        uint8_t *d_pics = ctx->stage_dev + fcur * pic;
+        uint8_t *d_src = ctx->clip_slots + 2 * fcur * g.slot_bytes, *d_rec = d_src + nf * g.slot_bytes;
+        // ---- upload: the host holds [gop][t] pictures, the device wants [t][gop]: one strided copy per position
+        for( int t = 0; t < gop_len; t++ )
+            XH_CHECK( cudaMemcpy2DAsync( d_pics + (size_t)t * ng * pic, pic, i420 + ( (size_t)g0 * gop_len + t ) * pic, (size_t)gop_len * pic,
+                                         pic, ng, cudaMemcpyHostToDevice, sh ) );
+        XH_CHECK( cudaEventCreateWithFlags( &ev_in[n_in], cudaEventDisableTiming ) );
+        n_in++;
+        XH_CHECK( cudaEventRecord( ev_in[n_in - 1], sh ) );
+        XH_CHECK( cudaStreamWaitEvent( sc, ev_in[n_in - 1], 0 ) );
+        // ---- kernels: staging, half-resolution planes, the lookahead of every (t - 1, t) pair, the GOP chain, the compact levels
+        XH_RC( x264dsp_frame_load_i420_dev( ctx, &g, d_pics, d_src, (int)nf, sc ) );
+        XH_RC( x264dsp_frame_expand_border_dev( ctx, &g, d_src, (int)nf, sc ) );
+        XH_RC( x264dsp_frame_init_lowres_dev( ctx, &g, d_src, (int)nf, sc ) );
+        if( gop_len > 1 )
+        {
+            const int np = ng * ( gop_len - 1 );
+            int32_t *b = idx, *p0 = idx + np;
+            uint8_t *wi = (uint8_t *)( p0 + np );
+            for( int k = 0; k < np; k++ )
+            {
+                b[k] = ng + k;                                    // position-major: pair k is frame ng + k against the one a GOP position earlier
+                p0[k] = k;
+                wi[k] = 0;
+            }
+            XH_RC( x264dsp_lookahead_frame_cost_dev( ctx, &g, d_src, np, b, p0, wi, d_lmv + ( m0 + (size_t)ng * nmb ) * 2,
+                                                     d_lc + m0 + (size_t)ng * nmb, d_ls + ( fcur + ng ) * X264DSP_LA_SUMS, NULL, sc ) );
+        }
+        XH_RC( x264dsp_gops_encode_dev( ctx, &g, d_src, d_rec, ng, gop_len, params, d_lmv + m0 * 2, d_type + m0, d_part + m0, d_mv8 + m0 * 8,
+                                        d_mvr + m0 * 2, d_mvd8 + m0 * 8, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
+                                        d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, d_m16 + m0, d_cm + m0, d_m4 + m0 * 16, d_dc + m0 * 16, sc ) );
+        XH_RC( x264dsp_levels_pack_dev( ctx, (int)nf, (int)nmb, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB,
+                                        d_packed + fcur * packed_stride, (int64_t)packed_stride, d_mboff + m0, d_ftot + fcur, sc ) );
+        XH_CHECK( cudaEventCreateWithFlags( &ev_out[n_out], cudaEventDisableTiming ) );
+        n_out++;
+        XH_CHECK( cudaEventRecord( ev_out[n_out - 1], sc ) );
+        XH_CHECK( cudaStreamWaitEvent( sd, ev_out[n_out - 1], 0 ) );
+        // ---- download: group-local [t][gop in group] -> host [t][gop]: rows = positions, one strided copy per array
+        XH_CHECK( cudaMemcpyAsync( h_ftot + fcur, d_ftot + fcur, nf * sizeof( int32_t ), cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaEventCreateWithFlags( &tot_ready[n_tot], cudaEventDisableTiming ) );
+        n_tot++;
+        XH_CHECK( cudaEventRecord( tot_ready[n_tot - 1], sd ) );
+#define XG_DOWN( host, dev, elem_bytes ) \
+        XH_CHECK( cudaMemcpy2DAsync( (uint8_t *)( host ) + (size_t)g0 * nmb * ( elem_bytes ), (size_t)n_gops * nmb * ( elem_bytes ), \
+                                     (const uint8_t *)( dev ) + m0 * ( elem_bytes ), (size_t)ng * nmb * ( elem_bytes ), \
+                                     (size_t)ng * nmb * ( elem_bytes ), gop_len, cudaMemcpyDeviceToHost, sd ) )
+        XG_DOWN( mb_type, d_type, 1 );
+        XG_DOWN( partition, d_part, 1 );
+        XG_DOWN( mv8, d_mv8, 16 );
+        XG_DOWN( mvr, d_mvr, 4 );
+        if( mvd8 )
+            XG_DOWN( mvd8, d_mvd8, 16 );
+        XG_DOWN( nnz, d_nz, X264DSP_RES_NNZ_PER_MB );
+        XG_DOWN( cbp, d_cbp, 2 );
+        XG_DOWN( mb_offset, d_mboff, 4 );
+#undef XG_DOWN
+        // the I frames' side information: position 0 only, [gop][mb]
+        XH_CHECK( cudaMemcpyAsync( mode16 + (size_t)g0 * nmb, d_m16 + m0, (size_t)ng * nmb, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( chroma_mode + (size_t)g0 * nmb, d_cm + m0, (size_t)ng * nmb, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( modes4 + (size_t)g0 * nmb * 16, d_m4 + m0 * 16, (size_t)ng * nmb * 16, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( luma_dc + (size_t)g0 * nmb * 16, d_dc + m0 * 16, (size_t)ng * nmb * 32, cudaMemcpyDeviceToHost, sd ) );
+        fcur += nf;
+    }
+    if( !rc )
+    {
+        // the compact levels, frame by frame as the groups' lengths arrive
+        int64_t at = 0;
+        size_t f = 0;
+        for( int gi = 0; gi < n_tot; gi++ )
+        {
+            XH_CHECK( cudaEventSynchronize( tot_ready[gi] ) );
+            const int g0 = group_g0[gi], ng = group_g0[gi + 1] - g0;
+            for( int t = 0; t < gop_len; t++ )
+                for( int k = 0; k < ng; k++, f++ )
+                {
+                    const int64_t len = h_ftot[f];
+                    const size_t out = (size_t)t * n_gops + g0 + k;           // position-major over all GOPs
+                    if( at + len > packed_capacity )
+                    {
+                        rc = X264DSP_E_ARG;
+                        goto drain;
+                    }
+                    if( len )
+                        XH_CHECK( cudaMemcpyAsync( packed_levels + at, d_packed + f * packed_stride, (size_t)len * sizeof( int16_t ),
+                                                   cudaMemcpyDeviceToHost, sd ) );
+                    frame_offset[out] = at;
+                    frame_size[out] = (int32_t)len;
+                    at += len;
+                }
+        }
+    }
+drain:
+    for( int i = 0; i < used; i++ )
+    {
+        const cudaError_t e = cudaStreamSynchronize( ctx->aux[i] );
+        if( e != cudaSuccess && !rc )
+            rc = (int)e;
+    }
+    for( int i = 0; i < n_in; i++ ) cudaEventDestroy( ev_in[i] );
+    for( int i = 0; i < n_out; i++ ) cudaEventDestroy( ev_out[i] );
+    for( int i = 0; i < n_tot; i++ ) cudaEventDestroy( tot_ready[i] );
+    free( idx );
+    ctx->scratch_busy[XD_SCRATCH_DEBLOCK] = 0;
+    ctx->scratch_busy[XD_SCRATCH_LOOKAHEAD] = 0;
+    return rc;
+}

@@ -21,6 +21,9 @@
 #include "predict_warp.cuh"
 
 #define IF_WARPS 2
+#ifndef IF_MINB
+#define IF_MINB 6                   // resident CTAs per SM the register allocation aims at
+#endif
 #define IF_COST_MAX ( 1 << 28 )
 enum { NB_LEFT = 1, NB_TOP = 2, NB_TOPRIGHT = 4, NB_TOPLEFT = 8 };           // common/macroblock.h:10-13
 
@@ -141,7 +144,7 @@ __device__ __forceinline__ int xd_if_code4x4( const uint8_t *src, uint8_t *dst, 
     return nz;
 }
 
-__global__ void __launch_bounds__( IF_WARPS * 32 )
+__global__ void __launch_bounds__( IF_WARPS * 32, IF_MINB )
 xd_iframe_kernel( xd_if_args A )
 {
     __shared__ __align__( 16 ) xd_if_smem s_mb[IF_WARPS];
