@@ -583,13 +583,21 @@ int x264dsp_gops_encode_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const 
                              uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode, uint8_t *modes4,
                              int16_t *luma_dc, void *stream );
 
+/* Position t alone (same arrays and layout; positions in order: t reads the reconstruction and the 16x16 vectors of t - 1):
+ * for a caller that feeds the positions as they arrive, as x264dsp_gops_encode_host does. */
+int x264dsp_gops_encode_step_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots, uint8_t *recon_slots,
+                                  int n_gops, int gop_len, int t, const x264dsp_gop_encode_params_t *params,
+                                  const int16_t *lowres_mv, int8_t *mb_type, uint8_t *partition, int16_t *mv8, int16_t *mvr,
+                                  int16_t *mvd8, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode,
+                                  uint8_t *modes4, int16_t *luma_dc, void *stream );
+
 /* The same from HOST memory: i420 holds the GOPs one after the other ([gop][t] planar pictures); source staging, the
  * half-resolution planes and the lookahead's vectors of every (t - 1, t) pair are built on the device, then
  * x264dsp_gops_encode_dev, then x264dsp_levels_pack_dev.  Host outputs are position-major over all GOPs ([t][gop][mb]...,
  * index k = t * n_gops + gop) except mode16 / chroma_mode / modes4 / luma_dc ([gop][mb]...: the I frames); the compact
  * levels of frame k are packed_levels[frame_offset[k] .. + frame_size[k]), its macroblocks at mb_offset[k][mb] inside it
  * (X264DSP_E_ARG when packed_capacity, in int16 units, is too small for the content).  The reconstructions stay on the
- * device.  All copies are inside the call; the GOPs move through an upload | kernels | download pipeline in two groups. */
+ * device.  All copies are inside the call: position t + 1 is uploaded and position t - 1 downloaded while position t is coded. */
 int x264dsp_gops_encode_host( x264dsp_ctx_t *ctx, int width, int height, int n_gops, int gop_len, const uint8_t *i420,
                               const x264dsp_gop_encode_params_t *params, int8_t *mb_type, uint8_t *partition, int16_t *mv8,
                               int16_t *mvr, int16_t *mvd8, uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode,

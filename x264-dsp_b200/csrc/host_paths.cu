@@ -495,14 +495,14 @@ extern "C" int x264dsp_p_frames_host_packed( x264dsp_ctx_t *ctx, int width, int 
 
 // ---------------------------------------------------------------------------------------------
 // Closed GOPs from host memory (x264dsp_gops_encode_dev behind a door): pictures in, what the entropy coder needs out.  The
-// GOPs are cut into groups that move through the same three-stage pipeline as the P-slice door (upload | kernels | download);
-// inside a group everything is position-major (one launch per stage and GOP position), the host arrays are position-major
-// over ALL GOPs, so every result array of a group lands with one strided copy.
-extern "C" int x264dsp_gops_encode_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots, uint8_t *recon_slots,
-                                        int n_gops, int gop_len, const x264dsp_gop_encode_params_t *params, const int16_t *lowres_mv,
-                                        int8_t *mb_type, uint8_t *partition, int16_t *mv8, int16_t *mvr, int16_t *mvd8, int16_t *levels,
-                                        uint8_t *nnz, int16_t *cbp, uint8_t *mode16, uint8_t *chroma_mode, uint8_t *modes4,
-                                        int16_t *luma_dc, void *stream );
+// unit of the pipeline is a GOP POSITION: while position t of all GOPs is coded (every launch at the full batch size), position
+// t + 1 is uploaded and position t - 1 downloaded -- three streams, events between the stages.  Device and host arrays are both
+// position-major, so every result array of a position is one contiguous copy; only the upload is strided ([gop][t] on the host).
+extern "C" int x264dsp_gops_encode_step_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots, uint8_t *recon_slots,
+                                             int n_gops, int gop_len, int t, const x264dsp_gop_encode_params_t *params,
+                                             const int16_t *lowres_mv, int8_t *mb_type, uint8_t *partition, int16_t *mv8, int16_t *mvr,
+                                             int16_t *mvd8, int16_t *levels, uint8_t *nnz, int16_t *cbp, uint8_t *mode16,
+                                             uint8_t *chroma_mode, uint8_t *modes4, int16_t *luma_dc, void *stream );
 
 extern "C" int x264dsp_gops_encode_host( x264dsp_ctx_t *ctx, int width, int height, int n_gops, int gop_len, const uint8_t *i420,
                                           const x264dsp_gop_encode_params_t *params, int8_t *mb_type, uint8_t *partition,
@@ -520,14 +520,7 @@ extern "C" int x264dsp_gops_encode_host( x264dsp_ctx_t *ctx, int width, int heig
     if( g.mb_w < 3 || g.mb_h < 3 )
         return X264DSP_E_ARG;
     const size_t pic = (size_t)width * height * 3 / 2, nmb = g.mb_count;
-    const size_t n_frames = (size_t)n_gops * gop_len, N = n_frames * nmb;
-    int groups = n_gops >= 32 ? 2 : 1;
-    if( const char *e = getenv( "X264DSP_GOPS_HOST_GROUPS" ) )    // measurement knob, tests
-        groups = atoi( e );
-    if( groups < 1 ) groups = 1;
-    if( groups > n_gops ) groups = n_gops;
-    if( groups > XD_AUX_STREAMS ) groups = XD_AUX_STREAMS;
-    // device memory: pictures, source + reconstruction slots, side arrays (all per frame, groups one after the other)
+    const size_t n_frames = (size_t)n_gops * gop_len, N = n_frames * nmb, PP = (size_t)n_gops * nmb;       // PP: macroblocks per position
     const size_t per_mb = 1 + 1 + 16 + 4 + 16 + X264DSP_RES_NNZ_PER_MB + 2 + 4 /* lowres mv */ + 4 /* lookahead cost */
                         + 2 * X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ) + 4 /* mb_offset */ + 1 + 1 + 16 + 32 /* I-frame side */;
     const size_t side_bytes = ( N * per_mb + n_frames * ( 4 + X264DSP_LA_SUMS * 4 ) + 65536 ) & ~(size_t)255;
@@ -552,121 +545,108 @@ extern "C" int x264dsp_gops_encode_host( x264dsp_ctx_t *ctx, int width, int heig
     XG_TAKE( int32_t, d_mboff, N );
     XG_TAKE( int32_t, d_ftot, n_frames );
     XG_TAKE( int16_t, d_cbp, N );
-    XG_TAKE( int16_t, d_dc, N * 16 );
+    XG_TAKE( int16_t, d_dc, PP * 16 );
     XG_TAKE( uint8_t, d_nz, N * X264DSP_RES_NNZ_PER_MB );
     XG_TAKE( int8_t, d_type, N );
     XG_TAKE( uint8_t, d_part, N );
-    XG_TAKE( uint8_t, d_m16, N );
-    XG_TAKE( uint8_t, d_cm, N );
-    XG_TAKE( uint8_t, d_m4, N * 16 );
+    XG_TAKE( uint8_t, d_m16, PP );
+    XG_TAKE( uint8_t, d_cm, PP );
+    XG_TAKE( uint8_t, d_m4, PP * 16 );
 #undef XG_TAKE
     const size_t packed_stride = nmb * X264DSP_RES_LEVELS_PER_MB;
+    uint8_t *d_pics = ctx->stage_dev, *d_src = ctx->clip_slots, *d_rec = ctx->clip_slots + n_frames * g.slot_bytes;
     cudaStream_t sh = ctx->aux[0], sc = ctx->aux[1], sd = ctx->aux[2];
-    cudaEvent_t ev_in[XD_AUX_STREAMS], ev_out[XD_AUX_STREAMS], tot_ready[XD_AUX_STREAMS];
-    int n_in = 0, n_out = 0, n_tot = 0, used = 0;
-    int group_g0[XD_AUX_STREAMS + 1];
-    int32_t *idx = (int32_t *)malloc( ( n_frames + 1 ) * ( 2 * sizeof( int32_t ) + 1 ) );
-    if( !idx )
-        return X264DSP_E_NOMEM;
-    size_t fcur = 0;                                              // frames placed so far (device arrays: group after group)
-    for( int gi = 0; gi < groups && !rc; gi++ )
+    cudaEvent_t *ev = (cudaEvent_t *)calloc( (size_t)gop_len * 3, sizeof( cudaEvent_t ) );
+    int32_t *idx = (int32_t *)malloc( ( (size_t)n_gops + 1 ) * ( 2 * sizeof( int32_t ) + 1 ) );
+    int n_ev = 0, used = 0, positions = 0;
+    if( !ev || !idx )
     {
-        const int g0 = (int)( (int64_t)n_gops * gi / groups ), g1 = (int)( (int64_t)n_gops * ( gi + 1 ) / groups ), ng = g1 - g0;
-        group_g0[gi] = g0;
-        group_g0[gi + 1] = g1;
-        if( ng <= 0 )
-            continue;
+        free( ev );
+        free( idx );
+        return X264DSP_E_NOMEM;
+    }
+    for( int t = 0; t < gop_len; t++ )
+    {
+        const size_t f0 = (size_t)t * n_gops, m0 = f0 * nmb;
+        cudaEvent_t *e_in = &ev[3 * t], *e_out = &ev[3 * t + 1], *e_tot = &ev[3 * t + 2];
         used = 3;
-        const size_t nf = (size_t)ng * gop_len, m0 = fcur * nmb;
-        uint8_t *d_pics = ctx->stage_dev + fcur * pic;
-        uint8_t *d_src = ctx->clip_slots + 2 * fcur * g.slot_bytes, *d_rec = d_src + nf * g.slot_bytes;
-        // ---- upload: the host holds [gop][t] pictures, the device wants [t][gop]: one strided copy per position
-        for( int t = 0; t < gop_len; t++ )
-            XH_CHECK( cudaMemcpy2DAsync( d_pics + (size_t)t * ng * pic, pic, i420 + ( (size_t)g0 * gop_len + t ) * pic, (size_t)gop_len * pic,
-                                         pic, ng, cudaMemcpyHostToDevice, sh ) );
-        XH_CHECK( cudaEventCreateWithFlags( &ev_in[n_in], cudaEventDisableTiming ) );
-        n_in++;
-        XH_CHECK( cudaEventRecord( ev_in[n_in - 1], sh ) );
-        XH_CHECK( cudaStreamWaitEvent( sc, ev_in[n_in - 1], 0 ) );
-        // ---- kernels: staging, half-resolution planes, the lookahead of every (t - 1, t) pair, the GOP chain, the compact levels
-        XH_RC( x264dsp_frame_load_i420_dev( ctx, &g, d_pics, d_src, (int)nf, sc ) );
-        XH_RC( x264dsp_frame_expand_border_dev( ctx, &g, d_src, (int)nf, sc ) );
-        XH_RC( x264dsp_frame_init_lowres_dev( ctx, &g, d_src, (int)nf, sc ) );
-        if( gop_len > 1 )
+        for( int k = 0; k < 3; k++ )
         {
-            const int np = ng * ( gop_len - 1 );
-            int32_t *b = idx, *p0 = idx + np;
-            uint8_t *wi = (uint8_t *)( p0 + np );
-            for( int k = 0; k < np; k++ )
+            XH_CHECK( cudaEventCreateWithFlags( &ev[3 * t + k], cudaEventDisableTiming ) );
+            n_ev = 3 * t + k + 1;
+        }
+        // ---- upload position t: the host holds [gop][t] pictures, one strided copy brings frame t of every GOP
+        XH_CHECK( cudaMemcpy2DAsync( d_pics + f0 * pic, pic, i420 + (size_t)t * pic, (size_t)gop_len * pic, pic, n_gops,
+                                     cudaMemcpyHostToDevice, sh ) );
+        XH_CHECK( cudaEventRecord( *e_in, sh ) );
+        XH_CHECK( cudaStreamWaitEvent( sc, *e_in, 0 ) );
+        // ---- kernels: staging and half-resolution planes of the new frames, the lookahead of every (t - 1, t) pair, the chain step
+        XH_RC( x264dsp_frame_load_i420_dev( ctx, &g, d_pics + f0 * pic, d_src + f0 * g.slot_bytes, n_gops, sc ) );
+        XH_RC( x264dsp_frame_expand_border_dev( ctx, &g, d_src + f0 * g.slot_bytes, n_gops, sc ) );
+        XH_RC( x264dsp_frame_init_lowres_dev( ctx, &g, d_src + f0 * g.slot_bytes, n_gops, sc ) );
+        if( t > 0 )
+        {
+            int32_t *b = idx, *p0 = idx + n_gops;
+            uint8_t *wi = (uint8_t *)( p0 + n_gops );
+            for( int k = 0; k < n_gops; k++ )
             {
-                b[k] = ng + k;                                    // position-major: pair k is frame ng + k against the one a GOP position earlier
-                p0[k] = k;
+                b[k] = (int32_t)f0 + k;
+                p0[k] = (int32_t)( f0 - n_gops ) + k;
                 wi[k] = 0;
             }
-            XH_RC( x264dsp_lookahead_frame_cost_dev( ctx, &g, d_src, np, b, p0, wi, d_lmv + ( m0 + (size_t)ng * nmb ) * 2,
-                                                     d_lc + m0 + (size_t)ng * nmb, d_ls + ( fcur + ng ) * X264DSP_LA_SUMS, NULL, sc ) );
+            XH_RC( x264dsp_lookahead_frame_cost_dev( ctx, &g, d_src, n_gops, b, p0, wi, d_lmv + m0 * 2, d_lc + m0, d_ls + f0 * X264DSP_LA_SUMS,
+                                                     NULL, sc ) );
         }
-        XH_RC( x264dsp_gops_encode_dev( ctx, &g, d_src, d_rec, ng, gop_len, params, d_lmv + m0 * 2, d_type + m0, d_part + m0, d_mv8 + m0 * 8,
-                                        d_mvr + m0 * 2, d_mvd8 + m0 * 8, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB,
-                                        d_nz + m0 * X264DSP_RES_NNZ_PER_MB, d_cbp + m0, d_m16 + m0, d_cm + m0, d_m4 + m0 * 16, d_dc + m0 * 16, sc ) );
-        XH_RC( x264dsp_levels_pack_dev( ctx, (int)nf, (int)nmb, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB,
-                                        d_packed + fcur * packed_stride, (int64_t)packed_stride, d_mboff + m0, d_ftot + fcur, sc ) );
-        XH_CHECK( cudaEventCreateWithFlags( &ev_out[n_out], cudaEventDisableTiming ) );
-        n_out++;
-        XH_CHECK( cudaEventRecord( ev_out[n_out - 1], sc ) );
-        XH_CHECK( cudaStreamWaitEvent( sd, ev_out[n_out - 1], 0 ) );
-        // ---- download: group-local [t][gop in group] -> host [t][gop]: rows = positions, one strided copy per array
-        XH_CHECK( cudaMemcpyAsync( h_ftot + fcur, d_ftot + fcur, nf * sizeof( int32_t ), cudaMemcpyDeviceToHost, sd ) );
-        XH_CHECK( cudaEventCreateWithFlags( &tot_ready[n_tot], cudaEventDisableTiming ) );
-        n_tot++;
-        XH_CHECK( cudaEventRecord( tot_ready[n_tot - 1], sd ) );
-#define XG_DOWN( host, dev, elem_bytes ) \
-        XH_CHECK( cudaMemcpy2DAsync( (uint8_t *)( host ) + (size_t)g0 * nmb * ( elem_bytes ), (size_t)n_gops * nmb * ( elem_bytes ), \
-                                     (const uint8_t *)( dev ) + m0 * ( elem_bytes ), (size_t)ng * nmb * ( elem_bytes ), \
-                                     (size_t)ng * nmb * ( elem_bytes ), gop_len, cudaMemcpyDeviceToHost, sd ) )
-        XG_DOWN( mb_type, d_type, 1 );
-        XG_DOWN( partition, d_part, 1 );
-        XG_DOWN( mv8, d_mv8, 16 );
-        XG_DOWN( mvr, d_mvr, 4 );
+        XH_RC( x264dsp_gops_encode_step_dev( ctx, &g, d_src, d_rec, n_gops, gop_len, t, params, d_lmv, d_type, d_part, d_mv8, d_mvr, d_mvd8,
+                                             d_lv, d_nz, d_cbp, d_m16, d_cm, d_m4, d_dc, sc ) );
+        XH_RC( x264dsp_levels_pack_dev( ctx, n_gops, (int)nmb, d_lv + m0 * X264DSP_RES_LEVELS_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB,
+                                        d_packed + f0 * packed_stride, (int64_t)packed_stride, d_mboff + m0, d_ftot + f0, sc ) );
+        XH_CHECK( cudaEventRecord( *e_out, sc ) );
+        XH_CHECK( cudaStreamWaitEvent( sd, *e_out, 0 ) );
+        // ---- download position t
+        XH_CHECK( cudaMemcpyAsync( h_ftot + f0, d_ftot + f0, (size_t)n_gops * sizeof( int32_t ), cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaEventRecord( *e_tot, sd ) );
+        positions = t + 1;
+        XH_CHECK( cudaMemcpyAsync( mb_type + m0, d_type + m0, PP, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( partition + m0, d_part + m0, PP, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( mv8 + m0 * 8, d_mv8 + m0 * 8, PP * 16, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( mvr + m0 * 2, d_mvr + m0 * 2, PP * 4, cudaMemcpyDeviceToHost, sd ) );
         if( mvd8 )
-            XG_DOWN( mvd8, d_mvd8, 16 );
-        XG_DOWN( nnz, d_nz, X264DSP_RES_NNZ_PER_MB );
-        XG_DOWN( cbp, d_cbp, 2 );
-        XG_DOWN( mb_offset, d_mboff, 4 );
-#undef XG_DOWN
-        // the I frames' side information: position 0 only, [gop][mb]
-        XH_CHECK( cudaMemcpyAsync( mode16 + (size_t)g0 * nmb, d_m16 + m0, (size_t)ng * nmb, cudaMemcpyDeviceToHost, sd ) );
-        XH_CHECK( cudaMemcpyAsync( chroma_mode + (size_t)g0 * nmb, d_cm + m0, (size_t)ng * nmb, cudaMemcpyDeviceToHost, sd ) );
-        XH_CHECK( cudaMemcpyAsync( modes4 + (size_t)g0 * nmb * 16, d_m4 + m0 * 16, (size_t)ng * nmb * 16, cudaMemcpyDeviceToHost, sd ) );
-        XH_CHECK( cudaMemcpyAsync( luma_dc + (size_t)g0 * nmb * 16, d_dc + m0 * 16, (size_t)ng * nmb * 32, cudaMemcpyDeviceToHost, sd ) );
-        fcur += nf;
-    }
-    if( !rc )
-    {
-        // the compact levels, frame by frame as the groups' lengths arrive
-        int64_t at = 0;
-        size_t f = 0;
-        for( int gi = 0; gi < n_tot; gi++ )
+            XH_CHECK( cudaMemcpyAsync( mvd8 + m0 * 8, d_mvd8 + m0 * 8, PP * 16, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( nnz + m0 * X264DSP_RES_NNZ_PER_MB, d_nz + m0 * X264DSP_RES_NNZ_PER_MB, PP * X264DSP_RES_NNZ_PER_MB,
+                                   cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( cbp + m0, d_cbp + m0, PP * 2, cudaMemcpyDeviceToHost, sd ) );
+        XH_CHECK( cudaMemcpyAsync( mb_offset + m0, d_mboff + m0, PP * 4, cudaMemcpyDeviceToHost, sd ) );
+        if( t == 0 )
         {
-            XH_CHECK( cudaEventSynchronize( tot_ready[gi] ) );
-            const int g0 = group_g0[gi], ng = group_g0[gi + 1] - g0;
-            for( int t = 0; t < gop_len; t++ )
-                for( int k = 0; k < ng; k++, f++ )
+            XH_CHECK( cudaMemcpyAsync( mode16, d_m16, PP, cudaMemcpyDeviceToHost, sd ) );
+            XH_CHECK( cudaMemcpyAsync( chroma_mode, d_cm, PP, cudaMemcpyDeviceToHost, sd ) );
+            XH_CHECK( cudaMemcpyAsync( modes4, d_m4, PP * 16, cudaMemcpyDeviceToHost, sd ) );
+            XH_CHECK( cudaMemcpyAsync( luma_dc, d_dc, PP * 32, cudaMemcpyDeviceToHost, sd ) );
+        }
+    }
+    {
+        // the compact levels, position by position as their lengths arrive (later positions are being coded meanwhile)
+        int64_t at = 0;
+        for( int t = 0; t < positions; t++ )
+        {
+            XH_CHECK( cudaEventSynchronize( ev[3 * t + 2] ) );
+            for( int k = 0; k < n_gops; k++ )
+            {
+                const size_t f = (size_t)t * n_gops + k;
+                const int64_t len = h_ftot[f];
+                if( at + len > packed_capacity )
                 {
-                    const int64_t len = h_ftot[f];
-                    const size_t out = (size_t)t * n_gops + g0 + k;           // position-major over all GOPs
-                    if( at + len > packed_capacity )
-                    {
-                        rc = X264DSP_E_ARG;
-                        goto drain;
-                    }
-                    if( len )
-                        XH_CHECK( cudaMemcpyAsync( packed_levels + at, d_packed + f * packed_stride, (size_t)len * sizeof( int16_t ),
-                                                   cudaMemcpyDeviceToHost, sd ) );
-                    frame_offset[out] = at;
-                    frame_size[out] = (int32_t)len;
-                    at += len;
+                    rc = X264DSP_E_ARG;
+                    goto drain;
                 }
+                if( len )
+                    XH_CHECK( cudaMemcpyAsync( packed_levels + at, d_packed + f * packed_stride, (size_t)len * sizeof( int16_t ),
+                                               cudaMemcpyDeviceToHost, sd ) );
+                frame_offset[f] = at;
+                frame_size[f] = (int32_t)len;
+                at += len;
+            }
         }
     }
 drain:
@@ -676,9 +656,9 @@ drain:
         if( e != cudaSuccess && !rc )
             rc = (int)e;
     }
-    for( int i = 0; i < n_in; i++ ) cudaEventDestroy( ev_in[i] );
-    for( int i = 0; i < n_out; i++ ) cudaEventDestroy( ev_out[i] );
-    for( int i = 0; i < n_tot; i++ ) cudaEventDestroy( tot_ready[i] );
+    for( int i = 0; i < n_ev; i++ )
+        cudaEventDestroy( ev[i] );
+    free( ev );
     free( idx );
     ctx->scratch_busy[XD_SCRATCH_DEBLOCK] = 0;
     ctx->scratch_busy[XD_SCRATCH_LOOKAHEAD] = 0;
