@@ -49,6 +49,7 @@ struct x264dsp_ctx
     // host-level full-resolution paths (host_paths.cu): block lists / side information and results on the device
     uint8_t *me_blocks;   size_t me_blocks_cap;
     uint8_t *me_results;  size_t me_results_cap;
+    void *if_weights;                                // iframe.cu: the 4x4 predictors' weight table
     uint8_t *gc_scratch;  size_t gc_scratch_cap;     // gop_chain.cu: boundary strengths of one GOP position (+ 16x16 vectors)
     cudaEvent_t host_ev;
 

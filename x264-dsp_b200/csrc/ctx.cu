@@ -297,6 +297,7 @@ extern "C" void x264dsp_destroy( x264dsp_ctx_t *ctx )
     if( ctx->stage_host ) cudaFreeHost( ctx->stage_host );
     if( ctx->clip_out_host ) cudaFreeHost( ctx->clip_out_host );
     if( ctx->gc_scratch ) cudaFree( ctx->gc_scratch );
+    if( ctx->if_weights ) cudaFree( ctx->if_weights );
     if( ctx->shim_host ) cudaFreeHost( ctx->shim_host );
     for( int k = 0; k < XD_PROF_KINDS; k++ )
         for( int i = 0; i < XD_PROF_MAX; i++ )

@@ -40,6 +40,7 @@ struct xd_if_args
     uint8_t *nnz;
     int16_t *cbp;
     int32_t *progress, *ticket;
+    const uint4 *weights;           // xd_if_weights_kernel's table
 };
 
 struct xd_if_smem
@@ -144,10 +145,67 @@ __device__ __forceinline__ int xd_if_code4x4( const uint8_t *src, uint8_t *dst, 
     return nz;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The 4x4 predictors as byte dot products.  Every sample of every I_PRED_4x4 mode is (sum_k w_k e_k + rnd) >> sh over the
+// thirteen neighbouring samples e[0..12] = l3 l2 l1 l0 lt t0..t7 (common/predict.c:330-470): the three-tap and two-tap filters
+// with weights 1 2 1 and 2 2 over four, a copied sample with weight 4 (all rnd 2, sh 2), DC as eight weights of 1 (rnd 4, sh 3),
+// DC_128 as no weights and rnd 514.  With one lane per candidate mode a switch over the mode runs all twelve cases one after
+// the other (ncu r02at: 30 % of the kernel's instructions, 40 % of its stall samples); as a table of weights -- one 16-byte entry
+// per (mode, sample): the thirteen weights as bytes -- a sample is one shared-memory load and four IDP.4A, the same code on every
+// lane.  The table is DERIVED from xd_pred4x4_px (the per-sample restatement of the reference that tests/ pin): the response to
+// 4 at neighbour k and 0 elsewhere is w_k for the rnd 2 / sh 2 modes and for DC alike.
+#define IF_W_ENTRIES ( 12 * 16 )
+
+__global__ void xd_if_weights_kernel( uint4 *table )
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if( t >= IF_W_ENTRIES )
+        return;
+    const int mode = t >> 4, x = t & 3, y = ( t >> 2 ) & 3;
+    uint32_t w[4] = { 0, 0, 0, 0 };
+    if( mode != PR_DC_128 )
+        for( int k = 0; k < 13; k++ )
+        {
+            int e[13];
+            for( int j = 0; j < 13; j++ )
+                e[j] = j == k ? 4 : 0;
+            // DC = (l0 + .. + l3 + t0 + .. + t3 + 4) >> 3: a weight of 1 on each of its eight samples
+            const int r = mode == PR_DC ? ( ( k < 4 || ( k >= 5 && k < 9 ) ) ? 1 : 0 ) : xd_pred4x4_px( mode, x, y, e );
+            w[k >> 2] |= (uint32_t)r << ( 8 * ( k & 3 ) );
+        }
+    table[t] = make_uint4( w[0], w[1], w[2], w[3] );
+}
+
+// the thirteen neighbours of the 4x4 block at dst (shared-memory fdec, stride FDEC_STRIDE) packed four to a word
+struct xd_if_edges
+{
+    uint32_t e0, e1, e2, e3;
+};
+__device__ __forceinline__ xd_if_edges xd_if_load_edges( const uint8_t *dst )
+{
+    const uint32_t t0 = *(const uint32_t *)( dst - FDEC_STRIDE ), t1 = *(const uint32_t *)( dst - FDEC_STRIDE + 4 );
+    xd_if_edges E;
+    E.e0 = (uint32_t)dst[3 * FDEC_STRIDE - 1] | ( (uint32_t)dst[2 * FDEC_STRIDE - 1] << 8 ) | ( (uint32_t)dst[FDEC_STRIDE - 1] << 16 )
+         | ( (uint32_t)dst[-1] << 24 );
+    E.e1 = (uint32_t)dst[-FDEC_STRIDE - 1] | ( t0 << 8 );
+    E.e2 = ( t0 >> 24 ) | ( t1 << 8 );
+    E.e3 = t1 >> 24;
+    return E;
+}
+__device__ __forceinline__ int xd_if_pred_px( const xd_if_edges &E, const uint4 w, int mode )
+{
+    const int rnd = mode == PR_DC ? 4 : mode == PR_DC_128 ? 514 : 2, sh = mode == PR_DC ? 3 : 2;
+    return (int)( __dp4a( E.e0, w.x, __dp4a( E.e1, w.y, __dp4a( E.e2, w.z, __dp4a( E.e3, w.w, (uint32_t)rnd ) ) ) ) >> sh );
+}
+
 __global__ void __launch_bounds__( IF_WARPS * 32, IF_MINB )
 xd_iframe_kernel( xd_if_args A )
 {
     __shared__ __align__( 16 ) xd_if_smem s_mb[IF_WARPS];
+    __shared__ uint4 s_w[IF_W_ENTRIES];
+    for( int i = threadIdx.x; i < IF_W_ENTRIES; i += IF_WARPS * 32 )
+        s_w[i] = A.weights[i];
+    __syncthreads();
     const x264dsp_geom_t &g = A.g;
     const int lane = threadIdx.x & 31;
     xd_if_smem &S = s_mb[threadIdx.x >> 5];
@@ -310,22 +368,16 @@ xd_iframe_kernel( xd_if_args A )
                     // every candidate mode's SATD, one lane per mode
                     int satd[12];
                     {
-                        int e[13];
-#pragma unroll
-                        for( int k = 0; k < 4; k++ )
-                            e[3 - k] = dst[k * FDEC_STRIDE - 1];
-                        e[4] = dst[-FDEC_STRIDE - 1];
-#pragma unroll
-                        for( int k = 0; k < 8; k++ )
-                            e[5 + k] = dst[-FDEC_STRIDE + k];
+                        const xd_if_edges E = xd_if_load_edges( dst );
                         const int m = lane < 12 ? lane : 0;
                         uint32_t a[4], b[4];
 #pragma unroll
                         for( int r = 0; r < 4; r++ )
                         {
                             a[r] = *(const uint32_t *)( src + r * 16 );
-                            b[r] = (uint32_t)xd_pred4x4_px( m, 0, r, e ) | ( (uint32_t)xd_pred4x4_px( m, 1, r, e ) << 8 )
-                                 | ( (uint32_t)xd_pred4x4_px( m, 2, r, e ) << 16 ) | ( (uint32_t)xd_pred4x4_px( m, 3, r, e ) << 24 );
+                            b[r] = (uint32_t)xd_if_pred_px( E, s_w[m * 16 + 4 * r], m ) | ( (uint32_t)xd_if_pred_px( E, s_w[m * 16 + 4 * r + 1], m ) << 8 )
+                                 | ( (uint32_t)xd_if_pred_px( E, s_w[m * 16 + 4 * r + 2], m ) << 16 )
+                                 | ( (uint32_t)xd_if_pred_px( E, s_w[m * 16 + 4 * r + 3], m ) << 24 );
                         }
                         const int c = xd_satd4x4( a, b );
 #pragma unroll
@@ -403,17 +455,10 @@ xd_iframe_kernel( xd_if_args A )
                         cache = best_mode;
                     // predict with the chosen mode and code the block: the next ones predict from its reconstruction
                     {
-                        int e[13];
-#pragma unroll
-                        for( int k = 0; k < 4; k++ )
-                            e[3 - k] = dst[k * FDEC_STRIDE - 1];
-                        e[4] = dst[-FDEC_STRIDE - 1];
-#pragma unroll
-                        for( int k = 0; k < 8; k++ )
-                            e[5 + k] = dst[-FDEC_STRIDE + k];
+                        const xd_if_edges E = xd_if_load_edges( dst );
                         __syncwarp();
                         if( lane < 16 )
-                            dst[( lane >> 2 ) * FDEC_STRIDE + ( lane & 3 )] = (uint8_t)xd_pred4x4_px( best_mode, lane & 3, lane >> 2, e );
+                            dst[( lane >> 2 ) * FDEC_STRIDE + ( lane & 3 )] = (uint8_t)xd_if_pred_px( E, s_w[best_mode * 16 + lane], best_mode );
                         __syncwarp();
                     }
                     if( xd_if_code4x4( src, dst, A.T, levels + (size_t)xy * X264DSP_RES_LEVELS_PER_MB + idx * 16, lane ) )
@@ -429,17 +474,10 @@ xd_iframe_kernel( xd_if_args A )
                     {
                         // I_4x4 it is: block 15 is coded now (x264_macroblock_encode does it, macroblock.c:360-377)
                         uint8_t *dst = fy + 12 * FDEC_STRIDE + 12;
-                        int e[13];
-#pragma unroll
-                        for( int k = 0; k < 4; k++ )
-                            e[3 - k] = dst[k * FDEC_STRIDE - 1];
-                        e[4] = dst[-FDEC_STRIDE - 1];
-#pragma unroll
-                        for( int k = 0; k < 8; k++ )
-                            e[5 + k] = dst[-FDEC_STRIDE + k];
+                        const xd_if_edges E = xd_if_load_edges( dst );
                         __syncwarp();
                         if( lane < 16 )
-                            dst[( lane >> 2 ) * FDEC_STRIDE + ( lane & 3 )] = (uint8_t)xd_pred4x4_px( mode15, lane & 3, lane >> 2, e );
+                            dst[( lane >> 2 ) * FDEC_STRIDE + ( lane & 3 )] = (uint8_t)xd_if_pred_px( E, s_w[mode15 * 16 + lane], mode15 );
                         __syncwarp();
                         if( xd_if_code4x4( S.fenc_y + 12 * 16 + 12, dst, A.T, levels + (size_t)xy * X264DSP_RES_LEVELS_PER_MB + 15 * 16, lane ) )
                         {
@@ -553,6 +591,14 @@ extern "C" int x264dsp_i_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g
     A.progress = ctx->db_progress;
     A.ticket = ctx->db_progress + rows;
     A.mb_kind = (uint8_t *)( ctx->db_progress + rows + 1 );
+    if( !ctx->if_weights )
+    {
+        // the predictors' weight table, once per context
+        XD_CHECK( cudaMalloc( &ctx->if_weights, IF_W_ENTRIES * sizeof( uint4 ) ) );
+        xd_if_weights_kernel<<<( IF_W_ENTRIES + 63 ) / 64, 64, 0, s>>>( (uint4 *)ctx->if_weights );
+        ctx->launches++;
+    }
+    A.weights = (const uint4 *)ctx->if_weights;
     XD_CHECK( cudaMemsetAsync( levels, 0, nmb * X264DSP_RES_LEVELS_PER_MB * sizeof( int16_t ), s ) );
     int per_sm = 0;
     XD_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, xd_iframe_kernel, IF_WARPS * 32, 0 ) );
