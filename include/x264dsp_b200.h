@@ -531,7 +531,8 @@ int x264dsp_p_frames_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uin
  *                partitions; a 16x8 / 8x16 / 16x16 partition repeats its vector)
  *   mvd8         [4][2] the difference the entropy coder writes for the partition each 8x8 block lies in, predicted from the
  *                final vectors in coding order (encoder/cabac.c:352-412).  May be NULL.
- * params->analyse_inter == 0 gives x264dsp_p_frames_dev's decisions in this layout. */
+ * params->analyse_inter == 0 gives x264dsp_p_frames_dev's decisions in this layout.
+ * Slots, mv8 and mvd8 must start on 16-byte boundaries (the kernels use aligned vector accesses; X264DSP_E_ARG otherwise). */
 int x264dsp_p_frames_part_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, const uint8_t *fenc_slots,
                                const uint8_t *fref_slots, uint8_t *recon_slots, int n_frames,
                                const x264dsp_pframe_params_t *params, const int16_t *lowres_mv, const int16_t *l0_mv16,

@@ -88,13 +88,12 @@ def test_gop_chain_reproduces_the_encoder(pkg, ctx, w, h, n, me, subme, qp, psub
         assert seen_parts >= {13, 16}, seen_parts
 
 
-@pytest.mark.parametrize("w,h,n_gops,gop_len,me,subme,psub,groups", [(208, 160, 5, 4, 1, 5, 1, 2), (352, 288, 3, 3, 0, 1, 0, 1)])
-def test_gops_encode_host_matches_the_device_chain(pkg, ctx, w, h, n_gops, gop_len, me, subme, psub, groups, monkeypatch):
-    """x264dsp_gops_encode_host (pictures in host memory, [gop][t]; groups of GOPs through the copy / kernel pipeline; compact
-    levels) against the same stages called one by one on device memory"""
+@pytest.mark.parametrize("w,h,n_gops,gop_len,me,subme,psub", [(208, 160, 5, 4, 1, 5, 1), (352, 288, 3, 3, 0, 1, 0)])
+def test_gops_encode_host_matches_the_device_chain(pkg, ctx, w, h, n_gops, gop_len, me, subme, psub):
+    """x264dsp_gops_encode_host (pictures in host memory, [gop][t]; one GOP position after the other through the copy / kernel
+    pipeline; compact levels) against the same stages called one by one on device memory"""
     import torch
     from test_gpu_host_paths import expand_packed, mask_dense
-    monkeypatch.setenv("X264DSP_GOPS_HOST_GROUPS", str(groups))
     g = pkg.geometry(w, h)
     nmb = g.mb_count
     n = n_gops * gop_len

@@ -745,6 +745,12 @@ static int xd_p_frames_launch( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, cons
     x264dsp_me_params_t mp = { params->me_method, params->subpel_refine, params->me_range, params->qp, 0 };
     if( !xd_me_params_ok( &mp ) || params->mv_range < 1 )
         return X264DSP_E_ARG;
+    // the kernels read source segments and write vectors with aligned 8 / 16-byte accesses: slots on 16-byte boundaries (slot_bytes is
+    // a multiple of 256), per-8x8 vector arrays on 16-byte boundaries
+    if( ( (uintptr_t)fenc_slots | (uintptr_t)fref_slots | (uintptr_t)recon_slots ) & 15 )
+        return X264DSP_E_ARG;
+    if( by_part && ( ( (uintptr_t)mv | (uintptr_t)mvd ) & 15 ) )
+        return X264DSP_E_ARG;
     cudaStream_t s = xd_stream( ctx, stream );
     xd_pf_args A;
     memset( &A, 0, sizeof( A ) );
