@@ -43,9 +43,10 @@ def main():
     with open(out, "w") as f:
         f.write("# SASS opcode histogram per kernel (`cuobjdump -sass x264-dsp_b200/libx264dsp_b200.so`, sm_100a)\n\n")
         f.write("Static instruction counts per kernel; columns are prefix matches on the full mnemonic (so `LDG.E.128` counts\n"
-                "`LDG.E.128.CONSTANT`, `LDG.E.128.STRONG.GPU`, ...; plain `LDG.E` counts only the 32-bit loads).  No `UTMALDG` /\n"
-                "`UBLKCP` (TMA) and no `*MMA` (tensor cores) appear: the path is byte-integer work on the ALU / FMA pipes, staged\n"
-                "through registers and shared memory (DESIGN.md section 3 says why).\n\n")
+                "`LDG.E.128.CONSTANT`, `LDG.E.128.STRONG.GPU`, ...; plain `LDG.E` counts only the 32-bit loads).  `UTMALDG`\n"
+                "(TMA) appears in one kernel only, `xd_hpel_tma_kernel`, a measured variant that is off by default; no `*MMA` (tensor\n"
+                "cores) anywhere: the path is byte-integer work on the ALU / FMA pipes, staged through registers and shared memory\n"
+                "(DESIGN.md section 3 says why, with the measurements).\n\n")
         for name, c in kernels.items():
             total = sum(c.values())
             f.write(f"## `{demangle(name)}`\n\n{total} instructions.  ")

@@ -10,6 +10,8 @@
 //   x264_frame_expand_border_filtered                          common/frame.c:398-413
 //
 // Every kernel is batched over frame slots (blockIdx.z) so that one launch covers a whole clip.
+#include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -419,9 +421,54 @@ __device__ __forceinline__ int xd_dp2a_hi_us( uint32_t a, uint32_t b, int c )
     return d;
 }
 
-template<int GW>
+// ---- TMA variant of the row source (full strips only): one elected lane fetches HP_TROWS rows x 256 bytes -- the strip with
+// its two halo units -- per cp.async.bulk.tensor into a three-stage ring of the warp, completion on an mbarrier per stage; a
+// lane then reads its eight bytes of a row from the tile.  The tensor is (byte in row, row of plane N, slot), so rows past
+// the plane come back as zeros (they only feed rows that are not stored).
+// A box has to START on a 16-byte boundary of the innermost dimension (tools/tma_probe.cu: the same load at byte 24 of a row
+// raises "illegal instruction", at 16 or 32 it lands) -- TMA does not fetch byte windows at arbitrary positions.  A strip of 30
+// units + 2 halo units starts at byte 24 + 240 k of a row, never aligned; with 29 units per strip it starts at 24 + 232 k, and
+// either that or the 8 bytes before it are aligned: the box is the 256 aligned bytes around the strip's 31 units, a lane reads
+// at 8 * lane + (0 or 8).
+#define HP_TROWS 6                      // = the unroll of the row loop: tile and row-in-tile are compile-time there
+#define HP_TSTAGES 3
+#define HP_TILE_BYTES ( HP_TROWS * 256 )
+#define HP_UNITS_TMA 29
+
+struct xd_hp_tma
+{
+    const void *tmap;               // CUtensorMap in kernel parameter space
+    uint8_t *tiles;                 // this warp's HP_TSTAGES tiles
+    uint64_t *bars;                 // this warp's HP_TSTAGES mbarriers
+    int x, y, z;                    // tensor coordinates of the segment's first source row (x: a multiple of 16)
+    int lead;                       // bytes between the box's first byte and the strip's first (halo) unit: 0 or 8
+};
+
+__device__ __forceinline__ void xd_hp_tma_issue( const xd_hp_tma &T, int tile )
+{
+    const int st = tile % HP_TSTAGES;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared( T.bars + st );
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared( T.tiles + st * HP_TILE_BYTES );
+    asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"( bar ), "r"( HP_TILE_BYTES ) : "memory" );
+    asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                  :: "r"( dst ), "l"( (uint64_t)T.tmap ), "r"( bar ), "r"( T.x ), "r"( T.y + tile * HP_TROWS ), "r"( T.z ) : "memory" );
+}
+__device__ __forceinline__ void xd_hp_tma_wait( const xd_hp_tma &T, int stage, uint32_t parity )
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared( T.bars + stage );
+    uint32_t ok = 0, spins = 0;
+    while( !ok )
+    {
+        asm volatile( "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                      : "=r"( ok ) : "r"( bar ), "r"( parity ) : "memory" );
+        if( ++spins > ( 1u << 26 ) )
+            __trap();                                            // a tile that never lands is a bug, not something to wait for
+    }
+}
+
+template<int GW, bool TMA = false>
 __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *__restrict__ slot, int unit0, int strip_units, int wseg,
-                                              uint2 *s_ring )
+                                              uint2 *s_ring, xd_hp_tma T = xd_hp_tma() )
 {
     const int lane = threadIdx.x & 31;
     const int gl = lane & ( GW - 1 );
@@ -444,10 +491,36 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
 
     uint32_t A[6][4];                                            // rows y-2 .. y+3 as (p0,p1) (p2,p3) (p4,p5) (p6,p7)
     uint2 R[3];                                                  // rows y .. y+2 as loaded
+    // TMA: tile 0 = source rows -1 .. 4 of the segment (row -1 is fetched only so that the tiles line up with the row loop:
+    // its iteration i reads tile i + 1, row u of the tile in step u), tiles 1 .. 8 the 48 rows the loop consumes
+    constexpr int n_tiles = 1 + HP_ROWS / 6;
+    const uint8_t *trow = nullptr;                               // this lane's eight bytes in row 0 of stage 0
+    int st = 0;                                                  // stage / parity of the tile being read
+    uint32_t ph = 0;
+    if( TMA )
+    {
+        T.y += y0 - 3;
+        trow = T.tiles + min( lane * 8 + T.lead, 248 );
+        if( lane == 0 )
+        {
+            for( int k = 0; k < HP_TSTAGES; k++ )
+                asm volatile( "mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"( (uint32_t)__cvta_generic_to_shared( T.bars + k ) ) : "memory" );
+            asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+            asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" );
+            for( int k = 0; k < HP_TSTAGES && k < n_tiles; k++ )
+                xd_hp_tma_issue( T, k );
+        }
+        __syncwarp();
+        xd_hp_tma_wait( T, 0, 0 );
+    }
 #pragma unroll
     for( int k = 0; k < 5; k++ )
     {
-        const uint2 w = *(const uint2 *)ps;
+        uint2 w;
+        if( TMA )
+            w = *(const uint2 *)( trow + ( k + 1 ) * 256 );
+        else
+            w = *(const uint2 *)ps;
         ps += ls;
         A[k][0] = __byte_perm( w.x, 0u, 0x4140 );
         A[k][1] = __byte_perm( w.x, 0u, 0x4342 );
@@ -460,12 +533,23 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
     // prefetch loads into registers did not get past two rows: the loads of a warp share scoreboards, waiting for the
     // oldest one waits for all of them (2, 3 and 6 rows ahead all measured 2.65 us per frame, 40 % of the stall samples
     // on the first use of the row); cp.async groups complete in order and are waited for by count.
-    uint2 *ring = s_ring + threadIdx.x;                          // slot k of this thread: ring[k * 128]
-#pragma unroll
-    for( int k = 0; k < HP_AHEAD; k++ )
+    int tile = 1;
+    if( TMA )
     {
-        xd_cp_async8( ring + k * 128, ps );
-        ps += ls;
+        __syncwarp();                                            // every lane has read tile 0
+        if( lane == 0 && HP_TSTAGES < n_tiles )
+            xd_hp_tma_issue( T, HP_TSTAGES );
+        st = 1;
+    }
+    uint2 *ring = s_ring + threadIdx.x;                          // slot k of this thread: ring[k * 128]
+    if( !TMA )
+    {
+#pragma unroll
+        for( int k = 0; k < HP_AHEAD; k++ )
+        {
+            xd_cp_async8( ring + k * 128, ps );
+            ps += ls;
+        }
     }
     const uint32_t TA0 = 0x1414FB01u, TB0 = 0x000001FBu;         // (1,-5,20,20) (-5,1,0,0)
     const uint32_t TA1 = 0x14FB0100u, TB1 = 0x0001FB14u;         // (0,1,-5,20) (20,-5,1,0)
@@ -480,10 +564,32 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
             const int i0 = u % 6, i1 = ( u + 1 ) % 6, i2 = ( u + 2 ) % 6, i3 = ( u + 3 ) % 6, i4 = ( u + 4 ) % 6, i5 = ( u + 5 ) % 6;
             const uint2 cur = R[u % 3];
             {
-                xd_cp_async_wait<HP_AHEAD - 1>();                 // the oldest row in flight has landed
-                const uint2 w = ring[( u % HP_RING ) * 128];
-                xd_cp_async8( ring + ( ( u + HP_AHEAD ) % HP_RING ) * 128, ps );    // the slot read one row ago
-                ps += ls;
+                uint2 w;
+                if( TMA )
+                {
+                    if( u == 0 )
+                        xd_hp_tma_wait( T, st, ph );
+                    w = *(const uint2 *)( trow + st * HP_TILE_BYTES + u * 256 );
+                    if( u == 5 )
+                    {
+                        __syncwarp();                            // every lane has read the tile's last row
+                        if( lane == 0 && tile + HP_TSTAGES < n_tiles )
+                            xd_hp_tma_issue( T, tile + HP_TSTAGES );
+                        tile++;
+                        if( ++st == HP_TSTAGES )
+                        {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                }
+                else
+                {
+                    xd_cp_async_wait<HP_AHEAD - 1>();             // the oldest row in flight has landed
+                    w = ring[( u % HP_RING ) * 128];
+                    xd_cp_async8( ring + ( ( u + HP_AHEAD ) % HP_RING ) * 128, ps );    // the slot read one row ago
+                    ps += ls;
+                }
                 A[i5][0] = __byte_perm( w.x, 0u, 0x4140 );
                 A[i5][1] = __byte_perm( w.x, 0u, 0x4342 );
                 A[i5][2] = __byte_perm( w.y, 0u, 0x4140 );
@@ -547,7 +653,8 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
             dc += ls;
         }
     }
-    xd_cp_async_wait<0>();                                       // nothing of this thread's may still be landing at exit
+    if( !TMA )
+        xd_cp_async_wait<0>();                                   // nothing of this thread's may still be landing at exit
 }
 
 // The four warps of a block take four ADJACENT strips of the same row segment (they start together and stay close, so
@@ -566,6 +673,44 @@ xd_hpel_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, int n_full, int t
         return;
     if( strip < n_full || tail_gw == 32 )
         xd_hpel_body<32>( g, slot, unit0, strip < n_full ? HP_UNITS : tail_units, wseg, s_ring );
+    else if( tail_gw == 4 )
+        xd_hpel_body<4>( g, slot, unit0, tail_units, wseg, s_ring );
+    else if( tail_gw == 8 )
+        xd_hpel_body<8>( g, slot, unit0, tail_units, wseg, s_ring );
+    else
+        xd_hpel_body<16>( g, slot, unit0, tail_units, wseg, s_ring );
+}
+
+// The same with the full strips' source rows fetched by TMA (the tail strips keep the cp.async ring).
+__global__ void __launch_bounds__( 128, 6 )
+xd_hpel_tma_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, int n_full, int tail_units, int tail_gw,
+                    const __grid_constant__ CUtensorMap tmap )
+{
+    __shared__ uint2 s_ring[HP_RING * 128];
+    __shared__ __align__( 128 ) uint8_t s_tiles[4 * HP_TSTAGES * HP_TILE_BYTES];
+    __shared__ __align__( 8 ) uint64_t s_bars[4 * HP_TSTAGES];
+    uint8_t *slot = slots + blockIdx.z * (size_t)g.slot_bytes;
+    const int warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * 4 + warp;
+    const int wseg = blockIdx.y;
+    const int unit0 = strip * HP_UNITS_TMA;                      // n_full / tail_units count strips of HP_UNITS_TMA units here
+    if( strip > n_full || ( strip == n_full && !tail_units ) )
+        return;
+    if( strip < n_full )
+    {
+        xd_hp_tma T;
+        T.tmap = &tmap;
+        T.tiles = s_tiles + warp * HP_TSTAGES * HP_TILE_BYTES;
+        T.bars = s_bars + warp * HP_TSTAGES;
+        const int x0 = g.luma_origin % g.luma_stride + 8 * ( unit0 - 1 );     // the strip's left halo unit
+        T.lead = x0 & 15;
+        T.x = x0 - T.lead;
+        T.y = g.luma_origin / g.luma_stride;                     // + the segment's first source row, added in the body
+        T.z = blockIdx.z;
+        xd_hpel_body<32, true>( g, slot, unit0, HP_UNITS_TMA, wseg, s_ring, T );
+    }
+    else if( tail_gw == 32 )
+        xd_hpel_body<32>( g, slot, unit0, tail_units, wseg, s_ring );
     else if( tail_gw == 4 )
         xd_hpel_body<4>( g, slot, unit0, tail_units, wseg, s_ring );
     else if( tail_gw == 8 )
@@ -859,6 +1004,34 @@ extern "C" int x264dsp_frame_load_luma_lowres_dev( x264dsp_ctx_t *ctx, const x26
     return xd_launch_lowres( ctx, g, slots, luma, n_frames, xd_stream( ctx, stream ) );
 }
 
+// plane N of n_frames consecutive slots as a (byte in row, row, slot) tensor of bytes; box = 256 bytes x HP_TROWS rows
+#ifndef XD_HPEL_TMA_DEFAULT
+#define XD_HPEL_TMA_DEFAULT 0
+#endif
+typedef CUresult ( *xd_encode_tiled_fn )( CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                          const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+static int xd_hpel_tensor_map( const x264dsp_geom_t *g, uint8_t *slots, int n_frames, CUtensorMap *out )
+{
+    static xd_encode_tiled_fn encode = nullptr;
+    static bool tried = false;
+    if( !tried )
+    {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q ) == cudaSuccess && q == cudaDriverEntryPointSuccess )
+            encode = (xd_encode_tiled_fn)fn;
+    }
+    if( !encode || ( (uintptr_t)slots & 15 ) || ( g->luma_stride & 15 ) || ( g->slot_bytes & 15 ) )
+        return 1;
+    const cuuint64_t dims[3] = { (cuuint64_t)g->luma_stride, (cuuint64_t)( g->luma_plane_size / g->luma_stride ), (cuuint64_t)n_frames };
+    const cuuint64_t strides[2] = { (cuuint64_t)g->luma_stride, (cuuint64_t)g->slot_bytes };
+    const cuuint32_t box[3] = { 256, HP_TROWS, 1 }, estr[3] = { 1, 1, 1 };
+    return encode( out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, slots, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE ) == CUDA_SUCCESS ? 0 : 1;
+}
+
 extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_t *g, uint8_t *slots,
                                           int n_frames, void *stream )
 {
@@ -870,7 +1043,18 @@ extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_
     const int tail_gw = tail_units <= 2 ? 4 : tail_units <= 6 ? 8 : tail_units <= 14 ? 16 : 32;
     dim3 grid( ( n_full + ( tail_units ? 1 : 0 ) + 3 ) / 4, n_segs, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_HPEL, s );
-    xd_hpel_kernel<<<grid, 128, 0, s>>>( *g, slots, n_full, tail_units, tail_gw );
+    static const int use_tma = getenv( "X264DSP_HPEL_TMA" ) ? atoi( getenv( "X264DSP_HPEL_TMA" ) ) : XD_HPEL_TMA_DEFAULT;
+    CUtensorMap tmap;
+    if( use_tma && n_units >= HP_UNITS_TMA && ( g->luma_origin % g->luma_stride ) % 8 == 0
+        && xd_hpel_tensor_map( g, slots, n_frames, &tmap ) == 0 )
+    {
+        const int nf = n_units / HP_UNITS_TMA, tu = n_units % HP_UNITS_TMA;
+        const int tg = tu <= 2 ? 4 : tu <= 6 ? 8 : tu <= 14 ? 16 : 32;
+        dim3 tgrid( ( nf + ( tu ? 1 : 0 ) + 3 ) / 4, n_segs, n_frames );
+        xd_hpel_tma_kernel<<<tgrid, 128, 0, s>>>( *g, slots, nf, tu, tg, tmap );
+    }
+    else
+        xd_hpel_kernel<<<grid, 128, 0, s>>>( *g, slots, n_full, tail_units, tail_gw );
     xd_prof_end( ctx, XD_PROF_HPEL, pslot, s );
     ctx->launches++;
     XD_CHECK( cudaGetLastError() );
