@@ -90,6 +90,27 @@ def test_frame_planes_match_oracle(pkg, ctx, w, h):
         assert diff_report(got[i], want[i], g) == "", "expand_border + hpel filter"
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160), (352, 288), (720, 96), (256, 64)])
+def test_hpel_tma_variant_matches_oracle(pkg, ctx, w, h, monkeypatch):
+    """xd_hpel_tma_kernel (the full strips' source rows through cp.async.bulk.tensor: a measured variant, off by default,
+    X264DSP_HPEL_TMA=1) produces the same planes; widths below one 29-unit strip fall back to the cp.async kernel"""
+    torch = _torch()
+    monkeypatch.setenv("X264DSP_HPEL_TMA", "1")
+    n = 3
+    frames = [pkg.synth_frame(w, h, i) for i in range(n)]
+    g = pkg.geometry(w, h)
+    go = cc.oracle_geom(w, h)
+    slots = torch.zeros(n * g.slot_bytes, dtype=torch.uint8, device="cuda")
+    ctx.frame_load_i420(g, torch.from_numpy(np.concatenate(frames)).cuda(), slots, n)
+    ctx.frame_expand_border(g, slots, n)
+    ctx.frame_filter(g, slots, n)
+    ctx.sync()
+    want = oracle_slots(go, frames, border=True, hpel=True)
+    got = slots.cpu().numpy().reshape(n, -1)
+    for i in range(n):
+        assert diff_report(got[i], want[i], g) == "", "expand_border + hpel filter (TMA variant)"
+
+
 @pytest.mark.parametrize("w,h", SIZES + [(1920, 1080)])
 def test_lowres_planes_match_oracle(pkg, ctx, w, h):
     torch = _torch()

@@ -1043,7 +1043,8 @@ extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_
     const int tail_gw = tail_units <= 2 ? 4 : tail_units <= 6 ? 8 : tail_units <= 14 ? 16 : 32;
     dim3 grid( ( n_full + ( tail_units ? 1 : 0 ) + 3 ) / 4, n_segs, n_frames );
     const int pslot = xd_prof_begin( ctx, XD_PROF_HPEL, s );
-    static const int use_tma = getenv( "X264DSP_HPEL_TMA" ) ? atoi( getenv( "X264DSP_HPEL_TMA" ) ) : XD_HPEL_TMA_DEFAULT;
+    const char *tma_env = getenv( "X264DSP_HPEL_TMA" );          // measurement / test switch for the TMA variant
+    const int use_tma = tma_env ? atoi( tma_env ) : XD_HPEL_TMA_DEFAULT;
     CUtensorMap tmap;
     if( use_tma && n_units >= HP_UNITS_TMA && ( g->luma_origin % g->luma_stride ) % 8 == 0
         && xd_hpel_tensor_map( g, slots, n_frames, &tmap ) == 0 )
