@@ -426,22 +426,23 @@ __device__ __forceinline__ int xd_dp2a_hi_us( uint32_t a, uint32_t b, int c )
 // lane then reads its eight bytes of a row from the tile.  The tensor is (byte in row, row of plane N, slot), so rows past
 // the plane come back as zeros (they only feed rows that are not stored).
 // A box has to START on a 16-byte boundary of the innermost dimension (tools/tma_probe.cu: the same load at byte 24 of a row
-// raises "illegal instruction", at 16 or 32 it lands) -- TMA does not fetch byte windows at arbitrary positions.  A strip of 30
-// units + 2 halo units starts at byte 24 + 240 k of a row, never aligned; with 29 units per strip it starts at 24 + 232 k, and
-// either that or the 8 bytes before it are aligned: the box is the 256 aligned bytes around the strip's 31 units, a lane reads
-// at 8 * lane + (0 or 8).
+// raises "illegal instruction", at 16 or 32 it lands) -- TMA does not fetch byte windows at arbitrary positions.  A strip's 32
+// units (30 + two halo units) start at byte 24 + 240 k of a row, 8 bytes off.  So a stage takes TWO boxes: 256 bytes from the
+// strip's first real unit (aligned) -- lanes 1 .. 31 -- and 16 bytes ending with the left halo unit -- lane 0.  (The first
+// version kept one box and shrank the strips to 29 units: 1080p's 241 units then leave a tail of 9 units in half-warp strips
+// instead of 1 unit in a quarter-warp strip, 24 % more instructions, 2.75 against 2.43 us per frame.)
 #define HP_TROWS 6                      // = the unroll of the row loop: tile and row-in-tile are compile-time there
 #define HP_TSTAGES 3
-#define HP_TILE_BYTES ( HP_TROWS * 256 )
-#define HP_UNITS_TMA 29
+#define HP_TMAIN ( HP_TROWS * 256 )
+#define HP_THALO ( HP_TROWS * 16 )
+#define HP_TILE_BYTES ( HP_TMAIN + 128 ) // the halo box sits behind the main one, on a 128-byte boundary
 
 struct xd_hp_tma
 {
-    const void *tmap;               // CUtensorMap in kernel parameter space
-    uint8_t *tiles;                 // this warp's HP_TSTAGES tiles
+    const void *tmap, *tmap_halo;   // CUtensorMaps in kernel parameter space: boxes of 256 and of 16 bytes per row
+    uint8_t *tiles;                 // this warp's HP_TSTAGES stages
     uint64_t *bars;                 // this warp's HP_TSTAGES mbarriers
-    int x, y, z;                    // tensor coordinates of the segment's first source row (x: a multiple of 16)
-    int lead;                       // bytes between the box's first byte and the strip's first (halo) unit: 0 or 8
+    int x, y, z;                    // tensor coordinates of the segment's first source row (x: the strip's first real unit)
 };
 
 __device__ __forceinline__ void xd_hp_tma_issue( const xd_hp_tma &T, int tile )
@@ -449,9 +450,12 @@ __device__ __forceinline__ void xd_hp_tma_issue( const xd_hp_tma &T, int tile )
     const int st = tile % HP_TSTAGES;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared( T.bars + st );
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared( T.tiles + st * HP_TILE_BYTES );
-    asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"( bar ), "r"( HP_TILE_BYTES ) : "memory" );
+    asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"( bar ), "r"( HP_TMAIN + HP_THALO ) : "memory" );
     asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                   :: "r"( dst ), "l"( (uint64_t)T.tmap ), "r"( bar ), "r"( T.x ), "r"( T.y + tile * HP_TROWS ), "r"( T.z ) : "memory" );
+    asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                  :: "r"( dst + HP_TMAIN ), "l"( (uint64_t)T.tmap_halo ), "r"( bar ), "r"( T.x - 16 ), "r"( T.y + tile * HP_TROWS ), "r"( T.z )
+                  : "memory" );
 }
 __device__ __forceinline__ void xd_hp_tma_wait( const xd_hp_tma &T, int stage, uint32_t parity )
 {
@@ -495,12 +499,14 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
     // its iteration i reads tile i + 1, row u of the tile in step u), tiles 1 .. 8 the 48 rows the loop consumes
     constexpr int n_tiles = 1 + HP_ROWS / 6;
     const uint8_t *trow = nullptr;                               // this lane's eight bytes in row 0 of stage 0
+    int trs = 256;                                               // ... and the distance to its next row
     int st = 0;                                                  // stage / parity of the tile being read
     uint32_t ph = 0;
     if( TMA )
     {
         T.y += y0 - 3;
-        trow = T.tiles + min( lane * 8 + T.lead, 248 );
+        trow = lane ? T.tiles + ( lane - 1 ) * 8 : T.tiles + HP_TMAIN + 8;         // lane 0: the left halo unit, in the 16-byte box
+        trs = lane ? 256 : 16;
         if( lane == 0 )
         {
             for( int k = 0; k < HP_TSTAGES; k++ )
@@ -518,7 +524,7 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
     {
         uint2 w;
         if( TMA )
-            w = *(const uint2 *)( trow + ( k + 1 ) * 256 );
+            w = *(const uint2 *)( trow + ( k + 1 ) * trs );
         else
             w = *(const uint2 *)ps;
         ps += ls;
@@ -569,7 +575,7 @@ __device__ __forceinline__ void xd_hpel_body( const x264dsp_geom_t &g, uint8_t *
                 {
                     if( u == 0 )
                         xd_hp_tma_wait( T, st, ph );
-                    w = *(const uint2 *)( trow + st * HP_TILE_BYTES + u * 256 );
+                    w = *(const uint2 *)( trow + st * HP_TILE_BYTES + u * trs );
                     if( u == 5 )
                     {
                         __syncwarp();                            // every lane has read the tile's last row
@@ -684,7 +690,7 @@ xd_hpel_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, int n_full, int t
 // The same with the full strips' source rows fetched by TMA (the tail strips keep the cp.async ring).
 __global__ void __launch_bounds__( 128, 6 )
 xd_hpel_tma_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, int n_full, int tail_units, int tail_gw,
-                    const __grid_constant__ CUtensorMap tmap )
+                    const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_halo )
 {
     __shared__ uint2 s_ring[HP_RING * 128];
     __shared__ __align__( 128 ) uint8_t s_tiles[4 * HP_TSTAGES * HP_TILE_BYTES];
@@ -693,21 +699,20 @@ xd_hpel_tma_kernel( x264dsp_geom_t g, uint8_t *__restrict__ slots, int n_full, i
     const int warp = threadIdx.x >> 5;
     const int strip = blockIdx.x * 4 + warp;
     const int wseg = blockIdx.y;
-    const int unit0 = strip * HP_UNITS_TMA;                      // n_full / tail_units count strips of HP_UNITS_TMA units here
+    const int unit0 = strip * HP_UNITS;
     if( strip > n_full || ( strip == n_full && !tail_units ) )
         return;
     if( strip < n_full )
     {
         xd_hp_tma T;
         T.tmap = &tmap;
+        T.tmap_halo = &tmap_halo;
         T.tiles = s_tiles + warp * HP_TSTAGES * HP_TILE_BYTES;
         T.bars = s_bars + warp * HP_TSTAGES;
-        const int x0 = g.luma_origin % g.luma_stride + 8 * ( unit0 - 1 );     // the strip's left halo unit
-        T.lead = x0 & 15;
-        T.x = x0 - T.lead;
+        T.x = g.luma_origin % g.luma_stride + 8 * unit0;         // the strip's first real unit: a multiple of 16 (launcher checks)
         T.y = g.luma_origin / g.luma_stride;                     // + the segment's first source row, added in the body
         T.z = blockIdx.z;
-        xd_hpel_body<32, true>( g, slot, unit0, HP_UNITS_TMA, wseg, s_ring, T );
+        xd_hpel_body<32, true>( g, slot, unit0, HP_UNITS, wseg, s_ring, T );
     }
     else if( tail_gw == 32 )
         xd_hpel_body<32>( g, slot, unit0, tail_units, wseg, s_ring );
@@ -1004,14 +1009,14 @@ extern "C" int x264dsp_frame_load_luma_lowres_dev( x264dsp_ctx_t *ctx, const x26
     return xd_launch_lowres( ctx, g, slots, luma, n_frames, xd_stream( ctx, stream ) );
 }
 
-// plane N of n_frames consecutive slots as a (byte in row, row, slot) tensor of bytes; box = 256 bytes x HP_TROWS rows
+// plane N of n_frames consecutive slots as a (byte in row, row, slot) tensor of bytes; box = box_bytes x HP_TROWS rows
 #ifndef XD_HPEL_TMA_DEFAULT
 #define XD_HPEL_TMA_DEFAULT 0
 #endif
 typedef CUresult ( *xd_encode_tiled_fn )( CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                           const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
-static int xd_hpel_tensor_map( const x264dsp_geom_t *g, uint8_t *slots, int n_frames, CUtensorMap *out )
+static int xd_hpel_tensor_map( const x264dsp_geom_t *g, uint8_t *slots, int n_frames, int box_bytes, CUtensorMap *out )
 {
     static xd_encode_tiled_fn encode = nullptr;
     static bool tried = false;
@@ -1027,7 +1032,7 @@ static int xd_hpel_tensor_map( const x264dsp_geom_t *g, uint8_t *slots, int n_fr
         return 1;
     const cuuint64_t dims[3] = { (cuuint64_t)g->luma_stride, (cuuint64_t)( g->luma_plane_size / g->luma_stride ), (cuuint64_t)n_frames };
     const cuuint64_t strides[2] = { (cuuint64_t)g->luma_stride, (cuuint64_t)g->slot_bytes };
-    const cuuint32_t box[3] = { 256, HP_TROWS, 1 }, estr[3] = { 1, 1, 1 };
+    const cuuint32_t box[3] = { (cuuint32_t)box_bytes, HP_TROWS, 1 }, estr[3] = { 1, 1, 1 };
     return encode( out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, slots, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE ) == CUDA_SUCCESS ? 0 : 1;
 }
@@ -1045,15 +1050,11 @@ extern "C" int x264dsp_frame_filter_dev( x264dsp_ctx_t *ctx, const x264dsp_geom_
     const int pslot = xd_prof_begin( ctx, XD_PROF_HPEL, s );
     const char *tma_env = getenv( "X264DSP_HPEL_TMA" );          // measurement / test switch for the TMA variant
     const int use_tma = tma_env ? atoi( tma_env ) : XD_HPEL_TMA_DEFAULT;
-    CUtensorMap tmap;
-    if( use_tma && n_units >= HP_UNITS_TMA && ( g->luma_origin % g->luma_stride ) % 8 == 0
-        && xd_hpel_tensor_map( g, slots, n_frames, &tmap ) == 0 )
-    {
-        const int nf = n_units / HP_UNITS_TMA, tu = n_units % HP_UNITS_TMA;
-        const int tg = tu <= 2 ? 4 : tu <= 6 ? 8 : tu <= 14 ? 16 : 32;
-        dim3 tgrid( ( nf + ( tu ? 1 : 0 ) + 3 ) / 4, n_segs, n_frames );
-        xd_hpel_tma_kernel<<<tgrid, 128, 0, s>>>( *g, slots, nf, tu, tg, tmap );
-    }
+    CUtensorMap tmap, tmap_halo;
+    // strips start at origin + 240 k bytes: aligned boxes need the plane's first sample on a 16-byte boundary of its row
+    if( use_tma && n_full > 0 && ( g->luma_origin % g->luma_stride ) % 16 == 0 && xd_hpel_tensor_map( g, slots, n_frames, 256, &tmap ) == 0
+        && xd_hpel_tensor_map( g, slots, n_frames, 16, &tmap_halo ) == 0 )
+        xd_hpel_tma_kernel<<<grid, 128, 0, s>>>( *g, slots, n_full, tail_units, tail_gw, tmap, tmap_halo );
     else
         xd_hpel_kernel<<<grid, 128, 0, s>>>( *g, slots, n_full, tail_units, tail_gw );
     xd_prof_end( ctx, XD_PROF_HPEL, pslot, s );
