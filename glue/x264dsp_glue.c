@@ -85,7 +85,10 @@ static struct
     x264dsp_geom_t g, g1;                 /* the picture; one macroblock as a 16x16 "frame" (macroblock_encode door) */
     uint8_t *pool;                        /* GLUE_RESIDENT resident slots + 2 work slots + 1 prediction slot */
     void *res_frame[GLUE_RESIDENT];       /* x264_frame_t* held by each resident slot */
+    uint8_t res_stale[GLUE_RESIDENT];     /* the host's copy of this frame's H / V / HV planes has not been brought up to date */
     int res_next;
+    int slice_hooks;                      /* both slice loops are on the device: the host never reads the half-pel planes */
+    int lazy_planes;                      /* frames whose half-pel planes were fetched after all (a slice fell back to the host) */
     /* device scratch */
     int8_t *d_mb_type;
     uint8_t *d_partition, *d_bs, *d_skip, *d_mb_slots, *d_kind, *d_modes, *d_nnz;
@@ -241,6 +244,7 @@ static uint8_t *glue_make_resident( void *frame )
     const int i = G.res_next;
     G.res_next = ( G.res_next + 1 ) % GLUE_RESIDENT;
     G.res_frame[i] = frame;
+    G.res_stale[i] = 0;
     return glue_slot( i );
 }
 
@@ -292,8 +296,19 @@ static void glue_fdec( void *hv, void *fv, int do_deblock, const int8_t *mb_type
     }
     GLUE_CHECK( x264dsp_frame_expand_border_dev( G.ctx, g, slot, 1, NULL ) );
     GLUE_CHECK( x264dsp_frame_filter_dev( G.ctx, g, slot, 1, NULL ) );
-    GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[0], slot, 4 * (size_t)g->luma_plane_size, NULL ) );
+    /* With the macroblock loops of both slice types on the device the host never reads a reference frame's half-pel planes
+     * (no search, no motion compensation on its side): only the reconstruction itself goes back (PSNR, dumps), the other three
+     * planes -- two thirds of the bytes -- stay behind and are fetched by glue_fetch_planes should a slice ever fall back. */
+    /* ... and only while every P slice is certain to be offered to the device: the door in front of x264_macroblock_analyse
+     * does not even ask when the stream has several references or slices, trellis or noise reduction (x264dsp_doors.c) */
+    const int lazy = G.slice_hooks && h->param.i_frame_reference == 1 && !h->param.analyse.i_trellis && !h->param.analyse.i_noise_reduction
+                     && !( h->param.analyse.inter & ~X264_ANALYSE_PSUB16x16 ) && h->param.i_slice_count <= 1 && !h->param.i_slice_max_size
+                     && !h->param.i_slice_max_mbs;
+    GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[0], slot, ( lazy ? 1 : 4 ) * (size_t)g->luma_plane_size, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[1], slot + g->slot_chroma_off, g->chroma_plane_size, NULL ) );
+    for( int i = 0; i < GLUE_RESIDENT; i++ )
+        if( G.res_frame[i] == f )
+            G.res_stale[i] = (uint8_t)lazy;
     G.seconds[1] += glue_clock() - t0_;
     G.calls[1]++;
 }
@@ -468,6 +483,19 @@ static int glue_mbenc( void *hv, const uint8_t *fenc_y, const uint8_t *fenc_c, u
 /* ---- the macroblock loop of a whole P slice: x264dsp_p_frames_dev on the resident source and reference frame, with the
  *      lookahead's vectors of the pair and the reference frame's 16x16 vectors as the search's extra candidates exactly
  *      as x264_mb_predict_mv_ref16x16 takes them (common/mvpred.c:167-219) */
+/* the slice is going back to the host's own loop: its reference frame needs the half-pel planes the in-loop filter left behind */
+static void glue_fetch_planes( x264_frame_t *f )
+{
+    for( int i = 0; i < GLUE_RESIDENT; i++ )
+        if( G.res_frame[i] == f && G.res_stale[i] )
+        {
+            GLUE_CHECK( x264dsp_d2h( G.ctx, f->buffer[0] + G.g.luma_plane_size, glue_slot( i ) + G.g.luma_plane_size,
+                                     3 * (size_t)G.g.luma_plane_size, NULL ) );
+            G.res_stale[i] = 0;
+            G.lazy_planes++;
+        }
+}
+
 static int glue_pframe( void *hv, xref_pframe_out_t *out )
 {
     const double t0_ = glue_clock();
@@ -475,7 +503,11 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
     x264_frame_t *fref = h->fref[0][0];
     const uint8_t *se = glue_resident( h->fenc ), *sr = glue_resident( fref );
     if( !G.ctx || !se || !sr )
+    {
+        if( G.ctx )
+            glue_fetch_planes( fref );
         return 1;
+    }
     const x264dsp_geom_t *g = &G.g;
     const size_t nmb = g->mb_count;
     const int idx = h->fenc->i_frame - fref->i_frame - 1;
@@ -501,7 +533,10 @@ static int glue_pframe( void *hv, xref_pframe_out_t *out )
                                              G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL )
                 : x264dsp_p_frames_dev( G.ctx, g, se, sr, glue_pred(), 1, &prm, have_lowres ? G.d_pf_lmv : NULL, have_l0 ? G.d_pf_l0 : NULL,
                                         G.d_pf_type, G.d_pf_mv, G.d_pf_mvr, NULL, G.d_pf_levels, G.d_pf_nnz, G.d_pf_cbp, NULL ) )
+    {
+        glue_fetch_planes( fref );
         return 1;                                              /* parameters the device path does not take: the host's own loop */
+    }
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_type, G.d_pf_type, nmb, NULL ) );
     GLUE_CHECK( x264dsp_d2h( G.ctx, G.h_pf_mv, G.d_pf_mv, ( by_part ? 16 : 4 ) * nmb, NULL ) );
     if( by_part )
@@ -581,6 +616,7 @@ void x264dsp_glue_install_pframe( void )
 void x264dsp_glue_install_iframe( void )
 {
     xref_set_iframe_hook( glue_iframe );
+    G.slice_hooks = 1;                                         /* installed on top of the P-slice hook (x264dsp_glue_auto.c) */
 }
 
 void x264dsp_glue_install( void )
@@ -621,11 +657,12 @@ int x264dsp_glue_report( FILE *out )
                     "\"door_mbmc\": [%d, %d, %d], \"hook_calls\": [%d, %d, %d], \"p_frames\": %d, "
                     "\"p_slices\": [%d, %d, %d], \"i_frames\": %d, \"i_slices\": [%d, %d, %d], \"kernel_launches\": %lld, "
                     "\"seconds\": {\"lowres\": %.4f, \"inloop_filter\": %.4f, \"lookahead_cost\": %.4f, \"p_frames\": %.4f, "
-                    "\"i_frames\": %.4f, \"per_macroblock_doors\": %.4f, \"open\": %.4f, \"since_install\": %.4f}}\n",
+                    "\"i_frames\": %.4f, \"per_macroblock_doors\": %.4f, \"open\": %.4f, \"since_install\": %.4f}, "
+                    "\"half_pel_planes_fetched_late\": %d}\n",
                     G.calls[0], G.calls[1], G.calls[7], G.calls[2], G.calls[3], G.calls[4], G.calls[5], G.calls[6],
                     doors[0], doors[1], doors[2], doors[3], doors[4], doors[5], doors[6], doors[7], doors[8], doors[9],
                     doors[10], doors[11], hook[0], hook[1], hook[2], G.calls[8], pf[0], pf[1], pf[2], G.calls[9], iff[0], iff[1], iff[2],
                     G.ctx ? (long long)( x264dsp_launch_count( G.ctx ) - G.launches0 ) : 0LL,
                     G.seconds[0] - G.seconds_open, G.seconds[1], G.seconds[2], G.seconds[8], G.seconds[9],
-                    G.seconds[3] + G.seconds[4] + G.seconds[5] + G.seconds[6], G.seconds_open, glue_clock() - G.t_install );
+                    G.seconds[3] + G.seconds[4] + G.seconds[5] + G.seconds[6], G.seconds_open, glue_clock() - G.t_install, G.lazy_planes );
 }
