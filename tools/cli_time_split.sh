@@ -1,3 +1,7 @@
+#!/bin/bash
+# Where the GPU CLI's time goes, per door: runs glue/_build/x264ref_gpu on a 52-frame 1080p synthetic clip twice and prints the
+# glue's own clock (X264DSP_GLUE_STATS: seconds inside each door, context creation, whole process).  Run on a GPU box:
+#   gpurun -- 'bash tools/cli_time_split.sh'
 python - <<'PY'
 import sys, numpy as np
 sys.path.insert(0,'tests')
