@@ -33,9 +33,31 @@ def pkg():
     return mod
 
 
+class _OrderedContext:
+    """The context's streams are non-blocking: nothing orders them behind torch's stream, on which a test has just filled its
+    device tensors (torch.zeros / ones / full are asynchronous kernels).  A production caller orders its streams itself; the
+    tests simply let torch finish before every call into the library -- without this a prefill could land AFTER the library's
+    own memset and show up as stale values in macroblocks the kernel does not write (seen once in 200 runs)."""
+
+    def __init__(self, inner):
+        object.__setattr__(self, "_inner", inner)
+
+    def __getattr__(self, name):
+        attr = getattr(self._inner, name)
+        if not callable(attr) or name.startswith("_") or name in ("close", "sync", "torch_stream", "pinned_empty"):
+            return attr
+
+        def call(*args, **kwargs):
+            import torch
+            if torch.cuda.is_available() and torch.cuda.is_initialized():
+                torch.cuda.synchronize()
+            return attr(*args, **kwargs)
+        return call
+
+
 @pytest.fixture(scope="session")
 def ctx(pkg):
     """a device context; GPU tests fail (not skip) when the CUDA library cannot open a device"""
     c = pkg.Context(0)
-    yield c
+    yield _OrderedContext(c)
     c.close()
