@@ -381,6 +381,7 @@ def pframe_measure(pkg, ctx, torch, g, w, h, n_frames, me, subme, qp=26, reps=3,
     for k in range(n_frames + 1):                      # pair k = slot k -> slot k + 1, cycling through the distinct frames
         j = k % distinct
         src[k * g.slot_bytes:(k + 1) * g.slot_bytes] = one[j * g.slot_bytes:(j + 1) * g.slot_bytes]
+    torch.cuda.synchronize()                           # torch's copies are on its own stream; the context's streams do not wait for it
     del one
     b = np.arange(1, n_frames + 1, dtype=np.int32)
     d_lmv = torch.zeros((n_frames, nmb, 2), dtype=torch.int16, device="cuda")
@@ -485,6 +486,7 @@ def gops_measure(pkg, ctx, torch, g, w, h, n_gops, gop_len, me, subme, qp=26):
         for gop in range(n_gops):
             k, j = t * n_gops + gop, (3 * gop + t) % 25
             fenc[k * g.slot_bytes:(k + 1) * g.slot_bytes] = one[j * g.slot_bytes:(j + 1) * g.slot_bytes]
+    torch.cuda.synchronize()                           # as in pframe_measure
     del one
     b = np.arange(n_gops, n, dtype=np.int32)
     d_lmv = torch.zeros((n, nmb, 2), dtype=torch.int16, device="cuda")

@@ -46,6 +46,7 @@ def main():
             k = t * G + gop
             j = (3 * gop + t) % 25
             fenc[k * g.slot_bytes:(k + 1) * g.slot_bytes] = one[j * g.slot_bytes:(j + 1) * g.slot_bytes]
+    torch.cuda.synchronize()            # torch's copies run on its own stream; the context's streams do not wait for it
     del one
     b = np.arange(G, n, dtype=np.int32)
     d_lmv = torch.zeros((n, nmb, 2), dtype=torch.int16, device="cuda")

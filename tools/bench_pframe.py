@@ -44,6 +44,7 @@ def main():
     for k in range(nmax + 1):           # pair k = (slot k -> slot k+1); slots cycle through the distinct frames
         j = k % distinct
         src[k * g.slot_bytes:(k + 1) * g.slot_bytes] = one[j * g.slot_bytes:(j + 1) * g.slot_bytes]
+    torch.cuda.synchronize()            # torch's copies run on its own stream; the context's streams do not wait for it
     b = np.arange(1, nmax + 1, dtype=np.int32)
     d_lmv = torch.zeros((nmax, nmb, 2), dtype=torch.int16, device="cuda")
     d_lc = torch.zeros((nmax, nmb), dtype=torch.int32, device="cuda")
